@@ -1,0 +1,327 @@
+// bf16 x bf16 -> f32 GEMM on the 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM),
+// operands staged by TMA into 128B-swizzled shared memory, persistent over output tiles with a
+// double-buffered TMEM accumulator so the epilogue of tile i overlaps the main loop of tile i+1.
+//
+// This is the dense-contraction workhorse of the LAS step (SURVEY.md §2.1 K1-i, K4, K6 and the
+// wgrad/dgrad GEMMs behind them):
+//   D[m,n] = sum_k A[m,k] * B[n,k]   (+ bias[n]) (relu) (+= C)
+// Each operand can be K-major (row-major [rows, K]) or MN-major (row-major [K, rows]); the
+// MN-major form is what lets the weight-gradient GEMMs (dW = dY^T X) read dY and X in place
+// instead of through transposed copies.
+#include "common.cuh"
+#include "las_internal.h"
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+namespace las {
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;   // 64 bf16 = 128 bytes = one swizzle atom row
+constexpr int UMMA_K = 16;
+constexpr int kStages = 6;
+constexpr int kAccStages = 2;
+constexpr int kThreads = 256;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps4-7 epilogue
+
+template <int BN>
+struct SmemLayout {
+  static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
+  static constexpr int kBBytes = BN * BLOCK_K * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarOffset = kStages * kStageBytes;
+  static constexpr int kTotal = kBarOffset + 256 + 1024;  // barriers + alignment slack
+};
+
+struct GemmParams {
+  void* C;
+  const float* bias;
+  int64_t ldc;
+  int M, N, K;
+  int relu;
+  int accumulate;
+};
+
+template <int BN, bool A_MN, bool B_MN, typename OutT>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+            GemmParams p) {
+  using L = SmemLayout<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tfull_bar = empty_bar + kStages;
+  uint64_t* tempty_bar = tfull_bar + kAccStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + kAccStages);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_blocks = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int n_blocks = (p.N + BN - 1) / BN;
+  const int k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int num_tiles = m_blocks * n_blocks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < kAccStages; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);  // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, kAccStages * BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / n_blocks) * BLOCK_M;
+      const int n0 = (tile % n_blocks) * BN;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * L::kStageBytes;
+        uint8_t* sb = sa + L::kABytes;
+        mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
+        const int k0 = kb * BLOCK_K;
+        if constexpr (!A_MN) {
+          tma_load_2d(sa, &tmap_a, &full_bar[stage], k0, m0);           // box {64 k, 128 rows}
+        } else {
+#pragma unroll
+          for (int j = 0; j < BLOCK_M / 64; ++j)                          // boxes {64 mn, 64 k}
+            tma_load_2d(sa + j * (BLOCK_K * 128), &tmap_a, &full_bar[stage], m0 + j * 64, k0);
+        }
+        if constexpr (!B_MN) {
+          tma_load_2d(sb, &tmap_b, &full_bar[stage], k0, n0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j)
+            tma_load_2d(sb + j * (BLOCK_K * 128), &tmap_b, &full_bar[stage], n0 + j * 64, k0);
+        }
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer (single thread) =====================
+    constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
+        const uint32_t sb = sa + L::kABytes;
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+          // K-major: advance 16 elements = 32 bytes inside the swizzle row.
+          // MN-major: advance 16 k-rows of 128 bytes; atoms along MN are one 64-row box apart.
+          const uint64_t adesc = A_MN ? make_smem_desc_sw128(sa + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
+                                      : make_smem_desc_sw128(sa + k * (UMMA_K * 2), 16, 1024);
+          const uint64_t bdesc = B_MN ? make_smem_desc_sw128(sb + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
+                                      : make_smem_desc_sw128(sb + k * (UMMA_K * 2), 16, 1024);
+          umma_bf16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
+        }
+        umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+        if (kb == k_blocks - 1) umma_commit(&tfull_bar[acc]);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    const int q = warp & 3;  // TMEM lane quadrant this warp may touch
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    OutT* Cout = reinterpret_cast<OutT*>(p.C);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / n_blocks) * BLOCK_M;
+      const int n0 = (tile % n_blocks) * BN;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + c0, v);
+        tmem_ld_wait();
+        const int col0 = n0 + c0;
+        if (row < p.M && col0 < p.N) {
+          OutT* crow = Cout + static_cast<int64_t>(row) * p.ldc + col0;
+          const int ncols = min(32, p.N - col0);
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = __uint_as_float(v[j]);
+            if (p.bias != nullptr && j < ncols) x += __ldg(p.bias + col0 + j);
+            if (p.relu) x = fmaxf(x, 0.0f);
+            f[j] = x;
+          }
+          if constexpr (sizeof(OutT) == 4) {
+            const bool vec = (ncols == 32) && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0);
+            if (vec) {
+              float4* c4 = reinterpret_cast<float4*>(crow);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float4 o = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                if (p.accumulate) {
+                  float4 old = c4[j];
+                  o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                }
+                c4[j] = o;
+              }
+            } else {
+              for (int j = 0; j < ncols; ++j) {
+                float o = f[j];
+                if (p.accumulate) o += crow[j];
+                crow[j] = o;
+              }
+            }
+          } else {
+            const bool vec = (ncols == 32) && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0);
+            if (vec && !p.accumulate) {
+              uint4* c4 = reinterpret_cast<uint4*>(crow);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 o;
+                o.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
+                o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+                o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+                o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+                c4[j] = o;
+              }
+            } else {
+              for (int j = 0; j < ncols; ++j) {
+                float o = f[j];
+                if (p.accumulate) o += __bfloat162float(crow[j]);
+                crow[j] = __float2bfloat16(o);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kAccStages * BN);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+
+int get_encode() {
+  if (g_encode) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  LAS_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  LAS_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess,
+              "cuTensorMapEncodeTiled not available from the driver");
+  g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  return 0;
+}
+
+// 2-D bf16 tensor map over a row-major [rows, cols] matrix with leading dimension ld (elements);
+// box = {box_cols (inner), box_rows}; 128B swizzle, zero fill out of bounds.
+int make_tmap(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld,
+              int box_cols, int box_rows) {
+  LAS_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "gemm operand base not 16B aligned");
+  LAS_REQUIRE((ld * 2) % 16 == 0, "gemm operand leading dimension %lld not a multiple of 8 elements",
+              static_cast<long long>(ld));
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims,
+                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  LAS_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d): rows=%lld cols=%lld ld=%lld",
+              static_cast<int>(r), static_cast<long long>(rows), static_cast<long long>(cols),
+              static_cast<long long>(ld));
+  return 0;
+}
+
+template <int BN, bool A_MN, bool B_MN, typename OutT>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+  using L = SmemLayout<BN>;
+  auto kern = gemm_kernel<BN, A_MN, B_MN, OutT>;
+  static bool configured = false;
+  if (!configured) {
+    LAS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    configured = true;
+  }
+  const int tiles = ((p.M + BLOCK_M - 1) / BLOCK_M) * ((p.N + BN - 1) / BN);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  kern<<<grid, kThreads, L::kTotal, stream>>>(ta, tb, p);
+  LAS_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int BN, typename OutT>
+int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb,
+                   const GemmParams& p, cudaStream_t s) {
+  if (!a_mn && !b_mn) return launch<BN, false, false, OutT>(ta, tb, p, s);
+  if (a_mn && b_mn) return launch<BN, true, true, OutT>(ta, tb, p, s);
+  if (a_mn && !b_mn) return launch<BN, true, false, OutT>(ta, tb, p, s);
+  return launch<BN, false, true, OutT>(ta, tb, p, s);
+}
+
+}  // namespace
+
+int gemm_bf16(const void* A, int64_t lda, bool a_mn, const void* B, int64_t ldb, bool b_mn, void* C,
+              int64_t ldc, bool c_bf16, const float* bias, int M, int N, int K, bool relu,
+              bool accumulate, cudaStream_t stream) {
+  if (M == 0 || N == 0) return 0;
+  LAS_REQUIRE(K > 0, "gemm: K must be positive");
+  int rc = get_encode();
+  if (rc) return rc;
+  // Narrow outputs (vocabulary logits, pyramid projections) use the 64-wide tile.
+  const int BN = (N <= 64) ? 64 : 128;
+  CUtensorMap ta, tb;
+  if (!a_mn) rc = make_tmap(&ta, A, M, K, lda, BLOCK_K, BLOCK_M);
+  else       rc = make_tmap(&ta, A, K, M, lda, 64, BLOCK_K);
+  if (rc) return rc;
+  if (!b_mn) rc = make_tmap(&tb, B, N, K, ldb, BLOCK_K, BN);
+  else       rc = make_tmap(&tb, B, K, N, ldb, 64, BLOCK_K);
+  if (rc) return rc;
+  GemmParams p{C, bias, ldc, M, N, K, relu ? 1 : 0, accumulate ? 1 : 0};
+  if (BN == 64) {
+    return c_bf16 ? dispatch_major<64, __nv_bfloat16>(a_mn, b_mn, ta, tb, p, stream)
+                  : dispatch_major<64, float>(a_mn, b_mn, ta, tb, p, stream);
+  }
+  return c_bf16 ? dispatch_major<128, __nv_bfloat16>(a_mn, b_mn, ta, tb, p, stream)
+                : dispatch_major<128, float>(a_mn, b_mn, ta, tb, p, stream);
+}
+
+}  // namespace las
