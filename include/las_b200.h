@@ -11,7 +11,7 @@
  *   - all pointers are DEVICE pointers unless the name ends in _host.
  *   - the library never allocates, frees or synchronises: callers pass workspaces and the CUDA
  *     stream (cudaStream_t as void*) the work is enqueued on.
- *   - "bf16" buffers are uint16 bfloat16; "f32" are float; lengths are int32.
+ *   - "bf16" buffers are uint16 bfloat16; "f16" IEEE half; "f32" float; lengths int32; tokens int64.
  *   - sm_100a only. There is no CPU path.
  */
 #ifndef LAS_B200_H_
@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define LAS_B200_VERSION 1
+#define LAS_B200_VERSION 2
 
 /* ------------------------------------------------------------------------------------------
  * core
@@ -45,6 +45,143 @@ int las_num_sms(void);
 int las_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb,
                   int b_mn_major, void* C, int64_t ldc, int c_is_bf16, const float* bias, int M,
                   int N, int K, int relu, int accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * element-wise / reduction helpers (HBM-bound)
+ * ---------------------------------------------------------------------------------------- */
+/* dst[r, c] = bf16(src[r, c]) for c < cols, 0 for cols <= c < ld_dst (utils.py:154 to_gpu + the
+ * implicit fp32->compute-dtype cast). */
+int las_cvt_pad_bf16(const float* src, int64_t ld_src, int64_t rows, int cols, void* dst,
+                     int64_t ld_dst, void* stream);
+int las_add2(const float* a, const float* b, float* out, int64_t n, void* stream);
+/* ReLU backward of model.py:94: dz = dout * (out > 0), dz in bf16 */
+int las_relu_bwd(const float* dout, const void* out, int out_is_bf16, void* dz, int64_t n, void* stream);
+/* out[c] += sum_r x[r, c] (bias gradients) */
+int las_colsum(const void* x, int x_is_bf16, int64_t ld, int64_t rows, int cols, float* out, void* stream);
+/* nn.Embedding forward (model.py:261, 310, 465): out[i,:] = bf16(table[idx[i],:]), zero-padded to ld_out */
+int las_gather_rows_bf16(const float* table, int dim, const int64_t* idx, int64_t n, void* out,
+                         int64_t ld_out, void* stream);
+/* nn.Embedding backward with padding_idx */
+int las_scatter_add_rows(const float* d, int64_t ld, int dim, const int64_t* idx, int64_t n, int64_t pad,
+                         float* dtable, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * loss: log-softmax + gather + unigram label smoothing (model.py:353-366, 523-530)
+ *   row r = (b, t) with b = r / rows_per_b, t = r % rows_per_b lives at logits + b*ld_b + t*ld.
+ *   targets == NULL -> gather at the row's own argmax (free-running decode, model.py:360-361).
+ *   out_prob / out_pred optional (LM.forward returns probabilities; Decoder returns argmax).
+ * backward: dlogits (same addressing) from g_logp[r] (and g_prob[r], may be NULL).
+ * ---------------------------------------------------------------------------------------- */
+int las_ce_ls_fwd(const float* logits, int64_t ld, int64_t ld_b, int64_t rows_per_b, int64_t rows, int V,
+                  const int64_t* targets, const float* dist, float ls, float* out_logp, float* out_prob,
+                  int64_t* out_pred, void* stream);
+int las_ce_ls_bwd(const float* logits, int64_t ld, int64_t ld_b, int64_t rows_per_b, int64_t rows, int V,
+                  const int64_t* targets, const float* dist, float ls, const float* g_logp,
+                  const float* g_prob, float* dlogits, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * optimiser: global-norm clip + Adam / AMSGrad on flat f32 buffers
+ * (torch.nn.utils.clip_grad_norm_ + torch.optim.Adam; solver.py:152-153, 171-173, 296-297, 384-385)
+ * ---------------------------------------------------------------------------------------- */
+int las_grad_norm(const float* g, int64_t n, void* partials_ws /* 256 doubles */, float* out_norm, void* stream);
+/* step_dev: device int32 holding the 1-based step count (so a captured graph can be replayed);
+ * vmax == NULL -> plain Adam. norm_ptr (device) + max_norm > 0 -> gradients are scaled by
+ * min(1, max_norm / (norm + 1e-6)); grad_scale multiplies gradients first (DDP averaging). */
+int las_adam_step(float* p, const float* g, float* m, float* v, float* vmax, int64_t n, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, const int32_t* step_dev,
+                  float max_norm, const float* norm_ptr, float grad_scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * recurrences (model.py:67, 79-81 packed BLSTM; model.py:466, 515-517 LM LSTM)
+ * ---------------------------------------------------------------------------------------- */
+/* f32 weight matrix -> bf16 mma A-fragments. mode 0: rows in order; mode 1: LSTM gate-interleaved
+ * (rows = 4H, logical row gate*H + unit). transposed: logical A[r][c] = W[c*ld + col_offset + r]. */
+int las_pack_afrag(const float* W, int64_t ld, int rows, int cols, int col_offset, int mode, int H,
+                   int transposed, void* out, void* stream);
+int64_t las_afrag_bytes(int rows, int cols, int mode, int H);
+/* out[n, m] = sum_k A[m,k] v[n,k] (+bias[m]) (+add[n,m]) with pre-packed A (mode 0) */
+int las_smallmm(const void* a_pk, int M, int K, const void* v, int v_is_f32, int64_t ldv, int N,
+                const float* bias, const float* add, int64_t ld_add, float* out_f32, int64_t ld_out,
+                void* out_bf16, int64_t ld_outb, void* stream);
+int64_t las_lstm_ws_bytes(int B, int H, int ndir);
+int las_lstm_seq_fwd(const float* xproj, const void* whh_pk, const int32_t* lens, int B, int T, int H,
+                     int ndir, void* y, int64_t y_ld_b, int64_t y_ld_t, int rep_row, void* hprev,
+                     int64_t hp_ld_b, int64_t hp_ld_t, void* gates_save, float* c_save, void* ws,
+                     void* stream);
+int las_lstm_seq_bwd(const float* dy, int64_t dy_ld_b, int64_t dy_ld_t, int rep_row,
+                     const void* whhT_pk, const int32_t* lens, int B, int T, int H, int ndir,
+                     const void* gates_save, const float* c_save, void* dG, int64_t dg_ld_b,
+                     int64_t dg_ld_t, void* ws, void* stream);
+/* lens_out[b] = (lens_in[b] + 1) / sub   (model.py:92) */
+int las_pyramid_lens(const int32_t* lens_in, int B, int sub, int32_t* lens_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * attention decoder (model.py:139-173 AttLoc.forward, 283-367 Decoder.forward_step / forward)
+ *
+ * All per-step buffers are [B, L+1, width]: row r holds what step r-1 produced, row 0 the
+ * initial state (zeros; ws row 0 = the initial alignment from las_att_init).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct las_dec_args {
+  int32_t B, L, Te;          /* batch, decoder steps, encoder frames (padded extent)            */
+  int32_t Hd, O, A, V, E, H; /* dec hidden, att_odim, att_dim, vocab, embedding, encoder dim    */
+  int32_t C, K;              /* conv channels, conv_kernel_size (taps = 2K+1)                   */
+  int32_t mode;              /* 0 teacher forcing, 1 greedy free-run, 2 smooth free-run         */
+  float att_scaling;         /* AttLoc softmax scaling (2.0, model.py:139)                      */
+  float smooth_scaling;      /* softmax temperature of the smooth embedding (model.py:341)      */
+  int32_t denc_accumulate;
+  int32_t _pad;
+  /* inputs */
+  const void* enc_h;         /* bf16 [B, Te, H]                                                 */
+  const float* P;            /* f32 [B, Te, A] = mlp_enc(enc_h)                                 */
+  const float* embx;         /* mode 0: f32 [B, L+1, 4Hd] = W_ih[:, :E] emb(ys_in) + b_ih + b_hh */
+  const float* cell_bias;    /* mode 1/2: f32 [4Hd] = b_ih + b_hh                               */
+  const void* wr_pk;         /* fragments (mode 1) of [W_hh | W_ih[:, E:]]  ([4Hd, Hd+O])       */
+  const void* we_pk;         /* mode 1/2: fragments (mode 1) of W_ih[:, :E]                     */
+  const void* mlp_dec_pk;    /* fragments (mode 0) of mlp_dec.weight [A, Hd]                    */
+  const void* mlp_o_pk;      /* fragments of mlp_o.weight [O, H]                                */
+  const float* mlp_o_b;      /* [O]                                                             */
+  const void* out_pk;        /* mode 1/2: fragments of output_layer.weight [V, Hd+O]            */
+  const float* out_b;        /* mode 1/2: [V]                                                   */
+  const float* emb_w;        /* mode 1/2: embedding.weight [V, E]                               */
+  const float* conv_w;       /* loc_conv.weight [C, 2K+1]                                       */
+  const float* mlp_att;      /* mlp_att.weight [A, C]                                           */
+  const float* gvec;         /* gvec.weight [A]                                                 */
+  /* state / outputs (caller-zeroed unless noted) */
+  float* ws;                 /* f32 [B, L+1, Te] alignments                                     */
+  void* zc;                  /* bf16 [B, L+1, Hd+O] (+64 elements slack): [z_t | c_t]           */
+  void* ctx;                 /* bf16 [B, L+1, H] attention context before mlp_o                 */
+  float* c_state;            /* f32 [B, Hd] LSTM cell state                                     */
+  void* emb_op;              /* mode 1/2: bf16 [B, L+1, Ep] step input embeddings (row 0 = BOS) */
+  float* logits;             /* mode 1/2: f32 [B, L+1, V]                                       */
+  int64_t* pred;             /* mode 1/2: [B, L]                                                */
+  float* e_buf;              /* scratch f32 [B, Te]                                             */
+  float* dzf;                /* f32 [B, L, A] mlp_dec(z_t)                                      */
+  void* gates_save;          /* f16 [B, L, Hd, 4]                                               */
+  float* c_save;             /* f32 [B, L, Hd]                                                  */
+  /* backward only */
+  const void* wrT_pk;        /* fragments (mode 0, transposed) of [W_hh | W_ih[:, E:]]          */
+  const void* mlp_oT_pk;     /* fragments of mlp_o.weight^T                                     */
+  const void* mlp_decT_pk;   /* fragments of mlp_dec.weight^T                                   */
+  const float* dzc_all;      /* f32 [B, L+1, Hd+O]: dlogits @ output_layer.weight               */
+  float* dcz_tot;            /* scratch f32 [B, Hd+O]                                           */
+  void* dcz_all;             /* bf16 [B, L+1, Hd+O] total gradient of [z_t | c_t]               */
+  float* dctx_all;           /* f32 [B, L, H]                                                   */
+  float* dw_buf;             /* scratch f32 [B, Te]                                             */
+  float* dattc_all;          /* f32 [L, B, Te, C]                                               */
+  float* ddz_all;            /* f32 [B, L+1, A] (+64 slack), zeroed                             */
+  float* dP;                 /* f32 [B, Te, A], zeroed                                          */
+  float* att_part;           /* scratch f32 [ceil(Te/32)*B, 17, roundup32(A)]                   */
+  float* dc_state;           /* scratch f32 [B, Hd]                                             */
+  void* dgates;              /* bf16 [B, L+1, 4Hd], zeroed (row L stays zero)                   */
+  float* dmlp_att;           /* += [A, C]                                                       */
+  float* dgvec;              /* += [A]                                                          */
+  float* dconv_w;            /* += [C, 2K+1]                                                    */
+  float* denc;               /* f32 [B, Te, H] gradient through the context (see denc_accumulate) */
+} las_dec_args;
+
+int las_att_init(const int32_t* enc_lens, int B, int Te, float* w, int64_t w_ld, void* stream);
+int las_dec_fwd(const las_dec_args* args_host, void* stream);
+int las_dec_bwd(const las_dec_args* args_host, void* stream);
 
 #ifdef __cplusplus
 }

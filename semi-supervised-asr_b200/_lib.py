@@ -5,6 +5,7 @@ compute entry point is called without a CUDA device, this module raises.
 """
 import ctypes
 import os
+from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liblas_b200.so")
@@ -14,6 +15,51 @@ _lib = None
 
 class LasError(RuntimeError):
     pass
+
+
+class DecArgs(ctypes.Structure):
+    """Mirror of `struct las_dec_args` (include/las_b200.h)."""
+    _fields_ = (
+        [(n, c_int32) for n in ("B", "L", "Te", "Hd", "O", "A", "V", "E", "H", "C", "K", "mode")]
+        + [("att_scaling", c_float), ("smooth_scaling", c_float), ("denc_accumulate", c_int32), ("_pad", c_int32)]
+        + [(n, c_void_p) for n in (
+            "enc_h", "P", "embx", "cell_bias", "wr_pk", "we_pk", "mlp_dec_pk", "mlp_o_pk", "mlp_o_b", "out_pk",
+            "out_b", "emb_w", "conv_w", "mlp_att", "gvec",
+            "ws", "zc", "ctx", "c_state", "emb_op", "logits", "pred", "e_buf", "dzf", "gates_save", "c_save",
+            "wrT_pk", "mlp_oT_pk", "mlp_decT_pk", "dzc_all", "dcz_tot", "dcz_all", "dctx_all", "dw_buf",
+            "dattc_all", "ddz_all", "dP", "att_part", "dc_state", "dgates", "dmlp_att", "dgvec", "dconv_w",
+            "denc")]
+    )
+
+
+P, I, L, F = c_void_p, c_int, c_int64, c_float
+# name -> (restype, argtypes); every symbol include/las_b200.h declares
+SIGNATURES = {
+    "las_last_error": (c_char_p, []),
+    "las_version": (c_int, []),
+    "las_num_sms": (c_int, []),
+    "las_gemm_bf16": (c_int, [P, L, I, P, L, I, P, L, I, P, I, I, I, I, I, P]),
+    "las_cvt_pad_bf16": (c_int, [P, L, L, I, P, L, P]),
+    "las_add2": (c_int, [P, P, P, L, P]),
+    "las_relu_bwd": (c_int, [P, P, I, P, L, P]),
+    "las_colsum": (c_int, [P, I, L, L, I, P, P]),
+    "las_gather_rows_bf16": (c_int, [P, I, P, L, P, L, P]),
+    "las_scatter_add_rows": (c_int, [P, L, I, P, L, L, P, P]),
+    "las_ce_ls_fwd": (c_int, [P, L, L, L, L, I, P, P, F, P, P, P, P]),
+    "las_ce_ls_bwd": (c_int, [P, L, L, L, L, I, P, P, F, P, P, P, P]),
+    "las_grad_norm": (c_int, [P, L, P, P, P]),
+    "las_adam_step": (c_int, [P, P, P, P, P, L, F, F, F, F, F, P, F, P, F, P]),
+    "las_pack_afrag": (c_int, [P, L, I, I, I, I, I, I, P, P]),
+    "las_afrag_bytes": (c_int64, [I, I, I, I]),
+    "las_smallmm": (c_int, [P, I, I, P, I, L, I, P, P, L, P, L, P, L, P]),
+    "las_lstm_ws_bytes": (c_int64, [I, I, I]),
+    "las_lstm_seq_fwd": (c_int, [P, P, P, I, I, I, I, P, L, L, I, P, L, L, P, P, P, P]),
+    "las_lstm_seq_bwd": (c_int, [P, L, L, I, P, P, I, I, I, I, P, P, P, L, L, P, P]),
+    "las_pyramid_lens": (c_int, [P, I, I, P, P]),
+    "las_att_init": (c_int, [P, I, I, P, L, P]),
+    "las_dec_fwd": (c_int, [ctypes.POINTER(DecArgs), P]),
+    "las_dec_bwd": (c_int, [ctypes.POINTER(DecArgs), P]),
+}
 
 
 def build(verbose=False):
@@ -40,7 +86,10 @@ def lib():
                 "(there is no fallback path)"
             )
         _lib = ctypes.CDLL(LIB_PATH)
-        _lib.las_last_error.restype = ctypes.c_char_p
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(_lib, name)
+            fn.restype = res
+            fn.argtypes = args
     return _lib
 
 
@@ -52,29 +101,19 @@ def check(rc):
 def ptr(t):
     """Device pointer of a torch tensor (or None -> NULL)."""
     if t is None:
-        return ctypes.c_void_p(0)
-    return ctypes.c_void_p(t.data_ptr())
+        return None
+    return t.data_ptr()
 
 
 def stream_ptr():
     import torch
 
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-
-
-def i64(v):
-    return ctypes.c_int64(int(v))
-
-
-def i32(v):
-    return ctypes.c_int(int(v))
-
-
-def f32(v):
-    return ctypes.c_float(float(v))
+    if not torch.cuda.is_available():
+        raise LasError("liblas_b200 needs a CUDA device (sm_100a); there is no CPU path")
+    return torch.cuda.current_stream().cuda_stream
 
 
 def call(name, *args):
-    """Invoke an int-returning C-ABI function and raise LasError on a non-zero return."""
+    """Invoke an int-returning C-ABI function on torch's current stream; raise LasError on failure."""
     fn = getattr(lib(), name)
-    check(fn(*args))
+    check(fn(*args, stream_ptr()))

@@ -1,0 +1,623 @@
+// Attention decoder (model.py:114-173 AttLoc, 256-367 Decoder) as a stream of per-timestep
+// kernels: LSTM cell step (rnn.cu), decoder-state projection, location-aware attention energy,
+// softmax + context, output projections; and the matching backward recursion which recomputes
+// tanh/softmax instead of storing the [B, Te, att_dim] attention state of every step.
+//
+// Row conventions: every per-step buffer is [B, L+1, width]; row r of zc/ctx/ws/logits holds the
+// value produced by step r-1 (row 0 = initial state), so "the state entering step t" is row t and
+// the shifted weight-gradient GEMMs after the loop need no special case at t = 0.
+#include "common.cuh"
+#include "las_internal.h"
+#include "../../include/las_b200.h"
+
+namespace las {
+
+constexpr int kTT = 32;  // encoder frames per CTA in the attention energy kernels
+
+__device__ __forceinline__ float block_reduce_sum(float v, float* red, int nwarps) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int k = 0; k < nwarps; ++k) t += red[k];
+  return t;
+}
+__device__ __forceinline__ float block_reduce_max(float v, float* red, int nwarps) {
+  v = warp_max(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = -INFINITY;
+  for (int k = 0; k < nwarps; ++k) t = fmaxf(t, red[k]);
+  return t;
+}
+
+struct AttGeom {
+  int B, Te, A, C, K;  // K = conv_kernel_size (taps = 2K+1)
+  int H;               // encoder feature dim
+};
+
+// Shared prologue of the energy kernels: previous alignment (zero padded by K on both sides),
+// conv weights, and the location conv for this CTA's frame tile:
+//   conv[tl][c] = sum_k wprev[te + k - K] * cw[c][k]            (model.py:120, 156)
+template <int CM>
+__device__ __forceinline__ void conv_tile(const AttGeom& g, const float* __restrict__ wprev_row,
+                                          const float* __restrict__ conv_w, int te0, float* wp,
+                                          float* cw, float* conv) {
+  const int ksz = 2 * g.K + 1;
+  for (int i = threadIdx.x; i < g.Te + 2 * g.K; i += blockDim.x) {
+    const int j = i - g.K;
+    wp[i] = (j >= 0 && j < g.Te) ? wprev_row[j] : 0.f;
+  }
+  for (int i = threadIdx.x; i < g.C * ksz; i += blockDim.x) cw[i] = conv_w[i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < kTT * g.C; i += blockDim.x) {
+    const int tl = i / g.C, c = i % g.C;
+    const int te = te0 + tl;
+    float s = 0.f;
+    if (te < g.Te) {
+      const float* wrow = wp + te;  // wp[te + k] = wprev[te + k - K]
+      const float* crow = cw + c * ksz;
+      for (int k = 0; k < ksz; ++k) s = fmaf(wrow[k], crow[k], s);
+    }
+    conv[tl * CM + c] = s;
+  }
+  __syncthreads();
+}
+
+struct EnergyFwdParams {
+  AttGeom g;
+  const float* P;        // [B, Te, A] mlp_enc(enc_h) + bias
+  const float* dz;       // [B, A] (row stride dz_ld) mlp_dec(z_t)
+  int64_t dz_ld;
+  const float* wprev;    // [B] rows of Te (row stride w_ld)
+  int64_t w_ld;
+  const float* conv_w;   // [C, 2K+1]
+  const float* mlp_att;  // [A, C]
+  const float* gvec;     // [A]
+  float* e;              // [B, Te]
+};
+
+// grid (ceil(Te/kTT), B), block = A rounded up to a warp multiple; thread a owns attention dim a.
+template <int CM>
+__global__ void __launch_bounds__(512) att_energy_fwd_kernel(EnergyFwdParams p) {
+  extern __shared__ float sm[];
+  const AttGeom& g = p.g;
+  const int ksz = 2 * g.K + 1;
+  float* wp = sm;
+  float* cw = wp + g.Te + 2 * g.K;
+  float* conv = cw + g.C * ksz;
+  float* red = conv + kTT * CM;  // [nwarps][kTT]
+  const int b = blockIdx.y, te0 = blockIdx.x * kTT;
+  const int a = threadIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwarps = blockDim.x >> 5;
+  conv_tile<CM>(g, p.wprev + b * p.w_ld, p.conv_w, te0, wp, cw, conv);
+
+  float matt[CM];
+#pragma unroll
+  for (int c = 0; c < CM; ++c) matt[c] = (a < g.A && c < g.C) ? p.mlp_att[a * g.C + c] : 0.f;
+  const float dza = (a < g.A) ? p.dz[b * p.dz_ld + a] : 0.f;
+  const float gv = (a < g.A) ? p.gvec[a] : 0.f;
+  const float* Pb = p.P + (static_cast<int64_t>(b) * g.Te + te0) * g.A + a;
+  const int ntl = min(kTT, g.Te - te0);
+  for (int tl = 0; tl < ntl; ++tl) {
+    float x = dza;
+    if (a < g.A) x += Pb[static_cast<int64_t>(tl) * g.A];
+#pragma unroll
+    for (int c = 0; c < CM; ++c) x = fmaf(matt[c], conv[tl * CM + c], x);
+    float v = gv * tanh_acc(x);
+    v = warp_sum(v);
+    if (lane == 0) red[warp * kTT + tl] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < ntl) {
+    float s = 0.f;
+    for (int w = 0; w < nwarps; ++w) s += red[w * kTT + threadIdx.x];
+    p.e[b * g.Te + te0 + threadIdx.x] = s;
+  }
+}
+
+struct CtxFwdParams {
+  int B, Te, H;
+  float scaling;
+  const float* e;               // [B, Te]
+  const __nv_bfloat16* enc_h;   // [B, Te, H]
+  float* w_out;                 // row b at w_out + b*w_ld (Te floats)
+  int64_t w_ld;
+  __nv_bfloat16* ctx;           // row b at ctx + b*ctx_ld (H bf16)
+  int64_t ctx_ld;
+};
+
+// grid (B, ceil(H/64)), block 256: softmax over ALL Te padded frames (no mask, model.py:167),
+// then the context for a 64-column slice: thread = (column pair, frame group of 8).
+__global__ void __launch_bounds__(256) att_ctx_fwd_kernel(CtxFwdParams p) {
+  extern __shared__ float sm[];
+  float* w_s = sm;               // [Te]
+  float* red = w_s + ((p.Te + 1) & ~1);  // [8]
+  float2* part = reinterpret_cast<float2*>(red + 8);  // [8][32]
+  const int b = blockIdx.x;
+  const float* eb = p.e + static_cast<int64_t>(b) * p.Te;
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < p.Te; i += 256) mx = fmaxf(mx, p.scaling * eb[i]);
+  mx = block_reduce_max(mx, red, 8);
+  float se = 0.f;
+  for (int i = threadIdx.x; i < p.Te; i += 256) {
+    const float v = __expf(p.scaling * eb[i] - mx);
+    w_s[i] = v;
+    se += v;
+  }
+  se = block_reduce_sum(se, red, 8);
+  const float inv = 1.f / se;
+  __syncthreads();
+  for (int i = threadIdx.x; i < p.Te; i += 256) {
+    const float v = w_s[i] * inv;
+    w_s[i] = v;
+    if (blockIdx.y == 0) p.w_out[b * p.w_ld + i] = v;
+  }
+  __syncthreads();
+  const int cp = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int col = blockIdx.y * 64 + 2 * cp;
+  float2 acc = make_float2(0.f, 0.f);
+  if (col < p.H) {
+    const __nv_bfloat16* eh = p.enc_h + static_cast<int64_t>(b) * p.Te * p.H + col;
+    for (int te = grp; te < p.Te; te += 8) {
+      const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(eh + static_cast<int64_t>(te) * p.H));
+      acc.x = fmaf(w_s[te], v.x, acc.x);
+      acc.y = fmaf(w_s[te], v.y, acc.y);
+    }
+  }
+  part[grp * 32 + cp] = acc;
+  __syncthreads();
+  if (grp == 0 && col < p.H) {
+    float2 s = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { s.x += part[k * 32 + cp].x; s.y += part[k * 32 + cp].y; }
+    *reinterpret_cast<uint32_t*>(p.ctx + b * p.ctx_ld + col) = pack_bf16x2(s.x, s.y);
+  }
+}
+
+// Next input embedding in free-running modes (model.py:331-341): argmax token, then either its
+// embedding row (greedy) or softmax(scaling * logit) @ E (smooth). One warp per utterance.
+struct NextEmbParams {
+  int B, V, E;
+  const float* logits; int64_t lg_ld;   // row b at logits + b*lg_ld
+  const float* emb_w;                   // [V, E]
+  float scaling; int smooth;
+  int64_t* pred; int64_t pred_ld;       // pred[b*pred_ld]
+  __nv_bfloat16* emb_out; int64_t eo_ld;
+};
+__global__ void __launch_bounds__(128) next_emb_kernel(NextEmbParams p) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (b >= p.B) return;
+  const float* x = p.logits + b * p.lg_ld;
+  float mx = -INFINITY;
+  int amax = 0x7fffffff;
+  for (int v = lane; v < p.V; v += 32) {
+    const float xv = x[v];
+    if (xv > mx) { mx = xv; amax = v; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, amax, o);
+    if (om > mx || (om == mx && oa < amax)) { mx = om; amax = oa; }
+  }
+  if (lane == 0) p.pred[b * p.pred_ld] = amax;
+  if (!p.smooth) {
+    for (int j = lane; j < p.E; j += 32) p.emb_out[b * p.eo_ld + j] = __float2bfloat16(p.emb_w[amax * p.E + j]);
+    return;
+  }
+  float se = 0.f;
+  for (int v = lane; v < p.V; v += 32) se += __expf(p.scaling * (x[v] - mx));
+  se = warp_sum(se);
+  const float inv = 1.f / se;
+  for (int j = lane; j < p.E; j += 32) {
+    float s = 0.f;
+    for (int v = 0; v < p.V; ++v) s = fmaf(__expf(p.scaling * (x[v] - mx)) * inv, p.emb_w[v * p.E + j], s);
+    p.emb_out[b * p.eo_ld + j] = __float2bfloat16(s);
+  }
+}
+
+// Initial alignment (model.py:151-153): 1/len over valid frames, exact zeros beyond.
+__global__ void att_init_kernel(const int32_t* __restrict__ enc_lens, int B, int Te, float* w, int64_t w_ld) {
+  const int b = blockIdx.x;
+  const int len = enc_lens[b];
+  const float v = 1.0f / static_cast<float>(len);
+  for (int i = threadIdx.x; i < Te; i += blockDim.x) w[b * w_ld + i] = (i < len) ? v : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------
+// backward kernels
+// ------------------------------------------------------------------------------------------
+struct DwParams {
+  AttGeom g;
+  const float* dctx; int64_t dctx_ld;   // [B] rows of H
+  const __nv_bfloat16* enc_h;           // [B, Te, H]
+  const float* dattc_next;              // [B, Te, C] conv-input gradient of step t+1, or nullptr
+  const float* conv_w;                  // [C, 2K+1]
+  float* dw;                            // [B, Te]
+};
+// dw[b,te] = <dctx[b], enc_h[b,te]> + sum_c sum_te' dattc_next[b,te',c] * cw[c, te - te' + K]
+// grid (ceil(Te/kTT), B), block 256: one warp per frame.
+__global__ void __launch_bounds__(256) att_dw_kernel(DwParams p) {
+  extern __shared__ float sm[];
+  const AttGeom& g = p.g;
+  const int ksz = 2 * g.K + 1;
+  float* dctx_s = sm;               // [H]
+  float* cw = dctx_s + g.H;         // [C*ksz]
+  const int b = blockIdx.y, te0 = blockIdx.x * kTT;
+  for (int i = threadIdx.x; i < g.H; i += 256) dctx_s[i] = p.dctx[b * p.dctx_ld + i];
+  if (p.dattc_next)
+    for (int i = threadIdx.x; i < g.C * ksz; i += 256) cw[i] = p.conv_w[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int tl = warp; tl < kTT; tl += 8) {
+    const int te = te0 + tl;
+    if (te >= g.Te) break;
+    const __nv_bfloat16* row = p.enc_h + (static_cast<int64_t>(b) * g.Te + te) * g.H;
+    float s = 0.f;
+    for (int h = 2 * lane; h < g.H; h += 64) {
+      const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(row + h));
+      s = fmaf(dctx_s[h], v.x, s);
+      s = fmaf(dctx_s[h + 1], v.y, s);
+    }
+    if (p.dattc_next) {
+      const int lo = max(0, te - g.K), hi = min(g.Te - 1, te + g.K);
+      const float* dn = p.dattc_next + static_cast<int64_t>(b) * g.Te * g.C;
+      for (int tp = lo + lane; tp <= hi; tp += 32) {
+        const int k = te - tp + g.K;
+        for (int c = 0; c < g.C; ++c) s = fmaf(dn[tp * g.C + c], cw[c * ksz + k], s);
+      }
+    }
+    s = warp_sum(s);
+    if (lane == 0) p.dw[b * g.Te + te] = s;
+  }
+}
+
+struct EnergyBwdParams {
+  AttGeom g;
+  float scaling;
+  const float* P;
+  const float* dz; int64_t dz_ld;
+  const float* wprev; int64_t w_ld;     // alignment entering the step (rows of Te)
+  const float* wcur;                    // alignment produced by the step (same row stride)
+  const float* dw;                      // [B, Te]
+  const float* conv_w;
+  const float* mlp_att;
+  const float* gvec;
+  float* dP;                            // [B, Te, A]  +=
+  float* ddz; int64_t ddz_ld;           // [B] rows of A, atomically accumulated (pre-zeroed)
+  float* dattc;                         // [B, Te, C] out
+  float* part;                          // [gridDim.y*gridDim.x][CM+1][Ap] per-CTA running sums (dmlp_att, dgvec)
+  int Ap;
+};
+
+template <int CM>
+__global__ void __launch_bounds__(512) att_energy_bwd_kernel(EnergyBwdParams p) {
+  extern __shared__ float sm[];
+  const AttGeom& g = p.g;
+  const int ksz = 2 * g.K + 1;
+  float* wp = sm;
+  float* cw = wp + g.Te + 2 * g.K;
+  float* conv = cw + g.C * ksz;
+  float* de_s = conv + kTT * CM;       // [kTT]
+  float* red = de_s + kTT;             // [32]
+  float* red2 = red + 32;              // [nwarps][kTT][CM]
+  const int b = blockIdx.y, te0 = blockIdx.x * kTT;
+  const int a = threadIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwarps = blockDim.x >> 5;
+  conv_tile<CM>(g, p.wprev + b * p.w_ld, p.conv_w, te0, wp, cw, conv);
+
+  // softmax backward: de = scaling * w * (dw - <w, dw>)
+  const float* wc = p.wcur + b * p.w_ld;
+  const float* dwb = p.dw + static_cast<int64_t>(b) * g.Te;
+  float dot = 0.f;
+  for (int i = threadIdx.x; i < g.Te; i += blockDim.x) dot = fmaf(wc[i], dwb[i], dot);
+  dot = block_reduce_sum(dot, red, nwarps);
+  const int ntl = min(kTT, g.Te - te0);
+  if (threadIdx.x < kTT) {
+    const int te = te0 + threadIdx.x;
+    de_s[threadIdx.x] = (threadIdx.x < ntl) ? p.scaling * wc[te] * (dwb[te] - dot) : 0.f;
+  }
+  __syncthreads();
+
+  float matt[CM], dmatt[CM];
+#pragma unroll
+  for (int c = 0; c < CM; ++c) {
+    matt[c] = (a < g.A && c < g.C) ? p.mlp_att[a * g.C + c] : 0.f;
+    dmatt[c] = 0.f;
+  }
+  const float dza = (a < g.A) ? p.dz[b * p.dz_ld + a] : 0.f;
+  const float gv = (a < g.A) ? p.gvec[a] : 0.f;
+  float dgv = 0.f, ddz = 0.f;
+  const int64_t pb = (static_cast<int64_t>(b) * g.Te + te0) * g.A + a;
+  for (int tl = 0; tl < ntl; ++tl) {
+    float x = dza;
+    if (a < g.A) x += p.P[pb + static_cast<int64_t>(tl) * g.A];
+#pragma unroll
+    for (int c = 0; c < CM; ++c) x = fmaf(matt[c], conv[tl * CM + c], x);
+    const float s = tanh_acc(x);
+    const float de = de_s[tl];
+    const float ds = de * gv * (1.f - s * s);   // gv == 0 for a >= A
+    dgv = fmaf(de, s, dgv);
+    ddz += ds;
+    if (a < g.A) p.dP[pb + static_cast<int64_t>(tl) * g.A] += ds;
+#pragma unroll
+    for (int c = 0; c < CM; ++c) {
+      dmatt[c] = fmaf(ds, conv[tl * CM + c], dmatt[c]);
+      const float v = warp_sum(ds * matt[c]);
+      if (lane == 0) red2[(warp * kTT + tl) * CM + c] = v;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < ntl * g.C; i += blockDim.x) {
+    const int tl = i / g.C, c = i % g.C;
+    float s = 0.f;
+    for (int w = 0; w < nwarps; ++w) s += red2[(w * kTT + tl) * CM + c];
+    p.dattc[(static_cast<int64_t>(b) * g.Te + te0 + tl) * g.C + c] = s;
+  }
+  if (a < g.A) {
+    atomicAdd(p.ddz + b * p.ddz_ld + a, ddz);
+    float* pp = p.part + static_cast<int64_t>(blockIdx.y * gridDim.x + blockIdx.x) * (CM + 1) * p.Ap + a;
+#pragma unroll
+    for (int c = 0; c < CM; ++c)
+      if (c < g.C) pp[c * p.Ap] += dmatt[c];
+    pp[CM * p.Ap] += dgv;
+  }
+}
+
+// Final reduction of the per-CTA running sums: dmlp_att[a, c] (+=), dgvec[a] (+=).
+__global__ void att_part_reduce_kernel(const float* __restrict__ part, int ncta, int CM, int Ap, int A, int C,
+                                       float* __restrict__ dmlp_att, float* __restrict__ dgvec) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (C + 1) * A) return;
+  const int c = idx / A, a = idx % A;
+  const int slot = (c < C) ? c : CM;
+  float s = 0.f;
+  for (int k = 0; k < ncta; ++k) s += part[(static_cast<int64_t>(k) * (CM + 1) + slot) * Ap + a];
+  if (c < C) dmlp_att[a * C + c] += s;
+  else dgvec[a] += s;
+}
+
+// dconv_w[c, k] += sum_{t, b, te} dattc[t, b, te, c] * w_{t-1}[b, te + k - K]
+// (w_{t-1} = ws_alloc row t). grid (2K+1), block 256; every thread strides over (t, b, te).
+__global__ void __launch_bounds__(256) att_dconv_kernel(const float* __restrict__ dattc_all, const float* __restrict__ ws_alloc,
+                                                        int L, int B, int Te, int C, int K, float* __restrict__ dconv_w) {
+  __shared__ float red[8];
+  const int k = blockIdx.x;
+  const int ksz = 2 * K + 1;
+  float acc[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) acc[c] = 0.f;
+  const int64_t total = static_cast<int64_t>(L) * B * Te;
+  for (int64_t i = threadIdx.x; i < total; i += 256) {
+    const int te = i % Te;
+    const int64_t tb = i / Te;
+    const int b = tb % B, t = tb / B;
+    const int j = te + k - K;
+    if (j < 0 || j >= Te) continue;
+    const float w = ws_alloc[(static_cast<int64_t>(b) * (L + 1) + t) * Te + j];
+    const float* d = dattc_all + i * C;
+#pragma unroll
+    for (int c = 0; c < 16; ++c)
+      if (c < C) acc[c] = fmaf(d[c], w, acc[c]);
+  }
+  for (int c = 0; c < C; ++c) {
+    const float s = block_reduce_sum(acc[c], red, 8);
+    if (threadIdx.x == 0) dconv_w[c * ksz + k] += s;
+  }
+}
+
+// denc[b, te, h] (+)= sum_t ws[b, t, te] * dctx[b, t, h]     (gradient of the context bmm)
+__global__ void __launch_bounds__(256) att_denc_kernel(const float* __restrict__ ws_alloc, const float* __restrict__ dctx_all,
+                                                       int L, int B, int Te, int H, float* __restrict__ denc, int accumulate) {
+  const int b = blockIdx.y, te = blockIdx.x;
+  const float* w = ws_alloc + (static_cast<int64_t>(b) * (L + 1) + 1) * Te + te;
+  const float* d = dctx_all + static_cast<int64_t>(b) * L * H;
+  for (int h = threadIdx.x; h < H; h += 256) {
+    float s = 0.f;
+    for (int t = 0; t < L; ++t) s = fmaf(w[static_cast<int64_t>(t) * Te], d[static_cast<int64_t>(t) * H + h], s);
+    float* o = denc + (static_cast<int64_t>(b) * Te + te) * H + h;
+    *o = accumulate ? *o + s : s;
+  }
+}
+
+static size_t energy_smem(const las_dec_args* a, int CM, int nwarps, bool bwd) {
+  const int ksz = 2 * a->K + 1;
+  size_t f = a->Te + 2 * a->K + static_cast<size_t>(a->C) * ksz + kTT * CM;
+  if (!bwd) f += static_cast<size_t>(nwarps) * kTT;
+  else f += kTT + 32 + static_cast<size_t>(nwarps) * kTT * CM;
+  return f * sizeof(float);
+}
+
+template <typename Kern>
+static int ensure_smem(Kern kern, size_t bytes) {
+  if (bytes > 48 * 1024) {
+    LAS_REQUIRE(bytes <= 227 * 1024, "decoder: attention kernel needs %zu bytes of shared memory", bytes);
+    LAS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
+  }
+  return 0;
+}
+
+static int check_args(const las_dec_args* a) {
+  LAS_REQUIRE(a->Hd % 8 == 0 && a->O % 8 == 0 && a->H % 8 == 0, "decoder: hidden/att_odim/encoder dims must be multiples of 8");
+  LAS_REQUIRE(a->A >= 1 && a->A <= 512, "decoder: att_dim %d out of range [1,512]", a->A);
+  LAS_REQUIRE(a->C >= 1 && a->C <= 16, "decoder: conv_channels %d out of range [1,16]", a->C);
+  LAS_REQUIRE(a->B >= 1 && a->L >= 1 && a->Te >= 1, "decoder: empty batch / sequence");
+  return 0;
+}
+
+}  // namespace las
+
+using namespace las;
+
+extern "C" {
+
+int las_att_init(const int32_t* enc_lens, int B, int Te, float* w, int64_t w_ld, void* stream) {
+  if (B == 0) return 0;
+  att_init_kernel<<<B, 128, 0, static_cast<cudaStream_t>(stream)>>>(enc_lens, B, Te, w, w_ld);
+  LAS_LAUNCH_CHECK();
+  return 0;
+}
+
+int las_dec_fwd(const las_dec_args* a, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (int rc = check_args(a)) return rc;
+  const int B = a->B, L = a->L, Te = a->Te, Hd = a->Hd, O = a->O, A = a->A, V = a->V, E = a->E;
+  const int ZC = Hd + O;
+  const int64_t R = L + 1;  // rows per utterance in the per-step buffers
+  const int CM = (a->C <= 4) ? 4 : 16;
+  const int ethreads = (A + 31) / 32 * 32, ewarps = ethreads / 32;
+  const size_t esmem = energy_smem(a, CM, ewarps, false);
+  if (CM == 4) { if (int rc = ensure_smem(att_energy_fwd_kernel<4>, esmem)) return rc; }
+  else         { if (int rc = ensure_smem(att_energy_fwd_kernel<16>, esmem)) return rc; }
+  const size_t csmem = (Te + 2 + 8 + 8 * 32 * 2) * sizeof(float);
+  if (int rc = ensure_smem(att_ctx_fwd_kernel, csmem)) return rc;
+  const bool free_run = a->mode != 0;
+  __nv_bfloat16* zc = static_cast<__nv_bfloat16*>(a->zc);
+  __nv_bfloat16* ctx = static_cast<__nv_bfloat16*>(a->ctx);
+  __nv_bfloat16* emb_op = static_cast<__nv_bfloat16*>(a->emb_op);
+  const int Ep = (E + 15) / 16 * 16;
+
+  CellFwdParams cp = {};
+  cp.B = B; cp.T = L; cp.H = Hd; cp.ndir = 1; cp.UG = Hd / 8;
+  cp.a1 = static_cast<const uint32_t*>(a->wr_pk); cp.KT1 = (ZC + 15) / 16; cp.a_dir = 0;
+  cp.v1_ld = R * ZC; cp.v1_dir = 0; cp.hout_ld = R * ZC; cp.hout_dir = 0;
+  cp.lens = nullptr; cp.c_state = a->c_state; cp.y = nullptr; cp.hprev = nullptr;
+  cp.gates_save = static_cast<__half*>(a->gates_save); cp.c_save = a->c_save; cp.rep_row = 0;
+  if (free_run) {
+    cp.xproj = a->cell_bias; cp.xp_ld_b = 0; cp.xp_ld_t = 0; cp.xp_ld_dir = 0;
+    cp.a2 = static_cast<const uint32_t*>(a->we_pk); cp.KT2 = Ep / 16; cp.v2_ld = R * Ep;
+  } else {
+    cp.xproj = a->embx; cp.xp_ld_b = R * 4 * Hd; cp.xp_ld_t = 4 * Hd; cp.xp_ld_dir = 0;
+    cp.a2 = nullptr; cp.v2 = nullptr; cp.KT2 = 0;
+  }
+
+  EnergyFwdParams ep = {};
+  ep.g = {B, Te, A, a->C, a->K, a->H};
+  ep.P = a->P; ep.dz_ld = static_cast<int64_t>(L) * A; ep.w_ld = R * Te;
+  ep.conv_w = a->conv_w; ep.mlp_att = a->mlp_att; ep.gvec = a->gvec; ep.e = a->e_buf;
+  CtxFwdParams xp = {};
+  xp.B = B; xp.Te = Te; xp.H = a->H; xp.scaling = a->att_scaling; xp.e = a->e_buf;
+  xp.enc_h = static_cast<const __nv_bfloat16*>(a->enc_h); xp.w_ld = R * Te; xp.ctx_ld = R * a->H;
+
+  const dim3 egrid((Te + kTT - 1) / kTT, B), cgrid(B, (a->H + 63) / 64);
+  for (int t = 0; t < L; ++t) {
+    // (1) LSTMCell: gates = W [emb; c_{t-1}; z_{t-1}] + b   (model.py:284-286)
+    cp.step = t;
+    cp.v1 = zc + static_cast<int64_t>(t) * ZC;
+    cp.hout = zc + static_cast<int64_t>(t + 1) * ZC;
+    if (free_run) cp.v2 = emb_op + static_cast<int64_t>(t) * Ep;
+    launch_cell_fwd(cp, stream);
+    // (2) decoder-state projection mlp_dec(z_t)   (model.py:163)
+    float* dz_t = a->dzf + static_cast<int64_t>(t) * A;
+    smallmm(static_cast<const uint32_t*>(a->mlp_dec_pk), A, Hd, zc + static_cast<int64_t>(t + 1) * ZC, 0, R * ZC, B,
+            nullptr, nullptr, 0, dz_t, static_cast<int64_t>(L) * A, nullptr, 0, stream);
+    // (3) energies e = gvec . tanh(P + dz + mlp_att(conv(w_{t-1})))   (model.py:156-165)
+    ep.dz = dz_t;
+    ep.wprev = a->ws + static_cast<int64_t>(t) * Te;
+    if (CM == 4) att_energy_fwd_kernel<4><<<egrid, ethreads, esmem, stream>>>(ep);
+    else att_energy_fwd_kernel<16><<<egrid, ethreads, esmem, stream>>>(ep);
+    // (4) w = softmax(scaling * e) over all Te, context = w @ enc_h   (model.py:167-171)
+    xp.w_out = a->ws + static_cast<int64_t>(t + 1) * Te;
+    xp.ctx = ctx + static_cast<int64_t>(t + 1) * a->H;
+    att_ctx_fwd_kernel<<<cgrid, 256, csmem, stream>>>(xp);
+    // (5) c_t = mlp_o(context)   (model.py:172) -> second half of zc row t+1
+    smallmm(static_cast<const uint32_t*>(a->mlp_o_pk), O, a->H, ctx + static_cast<int64_t>(t + 1) * a->H, 0, R * a->H, B,
+            a->mlp_o_b, nullptr, 0, nullptr, 0, zc + static_cast<int64_t>(t + 1) * ZC + Hd, R * ZC, stream);
+    if (free_run) {
+      // (6) logit_t = output_layer([z_t; c_t]) (model.py:290-293), (7) next input embedding
+      float* lg = a->logits + static_cast<int64_t>(t + 1) * V;
+      smallmm(static_cast<const uint32_t*>(a->out_pk), V, ZC, zc + static_cast<int64_t>(t + 1) * ZC, 0, R * ZC, B,
+              a->out_b, nullptr, 0, lg, R * V, nullptr, 0, stream);
+      NextEmbParams np = {};
+      np.B = B; np.V = V; np.E = E; np.logits = lg; np.lg_ld = R * V; np.emb_w = a->emb_w;
+      np.scaling = a->smooth_scaling; np.smooth = (a->mode == 2);
+      np.pred = a->pred + t; np.pred_ld = L;
+      np.emb_out = emb_op + static_cast<int64_t>(t + 1) * Ep; np.eo_ld = R * Ep;
+      next_emb_kernel<<<(B + 3) / 4, 128, 0, stream>>>(np);
+    }
+  }
+  LAS_LAUNCH_CHECK();
+  return 0;
+}
+
+int las_dec_bwd(const las_dec_args* a, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (int rc = check_args(a)) return rc;
+  LAS_REQUIRE(a->mode == 0, "decoder backward: only the teacher-forced mode is implemented here");
+  const int B = a->B, L = a->L, Te = a->Te, Hd = a->Hd, O = a->O, A = a->A;
+  const int ZC = Hd + O;
+  const int64_t R = L + 1;
+  const int CM = (a->C <= 4) ? 4 : 16;
+  const int ethreads = (A + 31) / 32 * 32, ewarps = ethreads / 32;
+  const int Ap = ethreads;
+  const size_t esmem = energy_smem(a, CM, ewarps, true);
+  if (CM == 4) { if (int rc = ensure_smem(att_energy_bwd_kernel<4>, esmem)) return rc; }
+  else         { if (int rc = ensure_smem(att_energy_bwd_kernel<16>, esmem)) return rc; }
+  const int ksz = 2 * a->K + 1;
+  const size_t dsmem = (a->H + static_cast<size_t>(a->C) * ksz) * sizeof(float);
+  if (int rc = ensure_smem(att_dw_kernel, dsmem)) return rc;
+  const dim3 egrid((Te + kTT - 1) / kTT, B);
+  const int ncta = egrid.x * egrid.y;
+  LAS_CUDA(cudaMemsetAsync(a->att_part, 0, static_cast<size_t>(ncta) * (CM + 1) * Ap * sizeof(float), stream));
+  LAS_CUDA(cudaMemsetAsync(a->dc_state, 0, static_cast<size_t>(B) * Hd * sizeof(float), stream));
+
+  __nv_bfloat16* dgates = static_cast<__nv_bfloat16*>(a->dgates);
+  __nv_bfloat16* dcz_all = static_cast<__nv_bfloat16*>(a->dcz_all);
+
+  DwParams wp = {};
+  wp.g = {B, Te, A, a->C, a->K, a->H};
+  wp.dctx_ld = static_cast<int64_t>(L) * a->H;
+  wp.enc_h = static_cast<const __nv_bfloat16*>(a->enc_h); wp.conv_w = a->conv_w; wp.dw = a->dw_buf;
+  EnergyBwdParams ep = {};
+  ep.g = wp.g; ep.scaling = a->att_scaling; ep.P = a->P; ep.dz_ld = static_cast<int64_t>(L) * A;
+  ep.w_ld = R * Te; ep.dw = a->dw_buf; ep.conv_w = a->conv_w; ep.mlp_att = a->mlp_att; ep.gvec = a->gvec;
+  ep.dP = a->dP; ep.ddz_ld = R * A; ep.part = a->att_part; ep.Ap = Ap;
+  CellBwdParams cb = {};
+  cb.dy = nullptr; cb.rep_row = 0;
+  cb.dh_extra = a->dcz_tot; cb.dhx_ld = ZC;
+  cb.a_pk = static_cast<const uint32_t*>(a->mlp_decT_pk); cb.a_dir = 0; cb.KT = (A + 15) / 16;
+  cb.v_f32 = 1; cb.v_ld = R * A; cb.v_dir = 0; cb.v_ld_t = A; cb.v_t_rev = 0;
+  cb.lens = nullptr; cb.gates_save = static_cast<const __half*>(a->gates_save); cb.c_save = a->c_save;
+  cb.dG = dgates; cb.dg_ld_b = R * 4 * Hd; cb.dg_ld_t = 4 * Hd;
+  cb.dc_state = a->dc_state; cb.B = B; cb.T = L; cb.H = Hd; cb.ndir = 1;
+
+  for (int t = L - 1; t >= 0; --t) {
+    // (1) d[z_t; c_t] = dzc_all (from the output layer) + Wr^T dgates_{t+1}  (row L of dgates is zero)
+    smallmm(static_cast<const uint32_t*>(a->wrT_pk), ZC, 4 * Hd, dgates + static_cast<int64_t>(t + 1) * 4 * Hd, 0, R * 4 * Hd, B,
+            nullptr, a->dzc_all + static_cast<int64_t>(t + 1) * ZC, R * ZC, a->dcz_tot, ZC,
+            dcz_all + static_cast<int64_t>(t + 1) * ZC, R * ZC, stream);
+    // (2) dcontext = mlp_o^T dc_t
+    float* dctx_t = a->dctx_all + static_cast<int64_t>(t) * a->H;
+    smallmm(static_cast<const uint32_t*>(a->mlp_oT_pk), a->H, O, dcz_all + static_cast<int64_t>(t + 1) * ZC + Hd, 0, R * ZC, B,
+            nullptr, nullptr, 0, dctx_t, static_cast<int64_t>(L) * a->H, nullptr, 0, stream);
+    // (3) dw_t = <dcontext, enc_h> + conv-input gradient of step t+1
+    wp.dctx = dctx_t;
+    wp.dattc_next = (t + 1 < L) ? a->dattc_all + static_cast<int64_t>(t + 1) * B * Te * a->C : nullptr;
+    att_dw_kernel<<<egrid, 256, dsmem, stream>>>(wp);
+    // (4) softmax + energy backward (tanh recomputed)
+    ep.dz = a->dzf + static_cast<int64_t>(t) * A;
+    ep.wprev = a->ws + static_cast<int64_t>(t) * Te;
+    ep.wcur = a->ws + static_cast<int64_t>(t + 1) * Te;
+    ep.ddz = a->ddz_all + static_cast<int64_t>(t + 1) * A;
+    ep.dattc = a->dattc_all + static_cast<int64_t>(t) * B * Te * a->C;
+    if (CM == 4) att_energy_bwd_kernel<4><<<egrid, ethreads, esmem, stream>>>(ep);
+    else att_energy_bwd_kernel<16><<<egrid, ethreads, esmem, stream>>>(ep);
+    // (5) dz_t += mlp_dec^T ddz ; LSTMCell backward -> dgates_t
+    cb.step = L - 1 - t;
+    cb.v = a->ddz_all; cb.v_t_fwd = t + 1;
+    launch_cell_bwd(cb, stream);
+  }
+  // reductions that were deferred out of the loop
+  att_part_reduce_kernel<<<((a->C + 1) * A + 255) / 256, 256, 0, stream>>>(a->att_part, ncta, CM, Ap, A, a->C,
+                                                                             a->dmlp_att, a->dgvec);
+  att_dconv_kernel<<<ksz, 256, 0, stream>>>(a->dattc_all, a->ws, L, B, Te, a->C, a->K, a->dconv_w);
+  att_denc_kernel<<<dim3(Te, B), 256, 0, stream>>>(a->ws, a->dctx_all, L, B, Te, a->H, a->denc, a->denc_accumulate);
+  LAS_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,380 @@
+// HBM-bound helper kernels around the GEMMs and recurrences: dtype conversion with padding,
+// bias sums, ReLU backward, column sums (bias gradients), embedding gather / scatter-add,
+// fused log-softmax + gather + unigram label smoothing (forward and backward), and the fused
+// global-norm clip + Adam/AMSGrad step over a flat parameter buffer.
+#include "common.cuh"
+#include "las_internal.h"
+#include "../../include/las_b200.h"
+
+namespace las {
+
+static inline int grid_for(int64_t n, int block = 256, int per_sm = 8) {
+  int64_t b = (n + block - 1) / block;
+  int64_t cap = static_cast<int64_t>(num_sms()) * per_sm;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return static_cast<int>(b);
+}
+
+// dst[r, c] = bf16(src[r, c]) for c < cols, 0 for cols <= c < ld_dst
+__global__ void cvt_pad_bf16_kernel(const float* __restrict__ src, int64_t ld_src, int64_t rows,
+                                    int cols, __nv_bfloat16* __restrict__ dst, int64_t ld_dst) {
+  const int64_t pairs_per_row = ld_dst / 2;
+  const int64_t total = rows * pairs_per_row;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / pairs_per_row;
+    const int c = static_cast<int>(i % pairs_per_row) * 2;
+    const float* s = src + r * ld_src;
+    const float a = (c < cols) ? s[c] : 0.f;
+    const float b = (c + 1 < cols) ? s[c + 1] : 0.f;
+    reinterpret_cast<uint32_t*>(dst + r * ld_dst)[c / 2] = pack_bf16x2(a, b);
+  }
+}
+
+__global__ void add2_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                            float* __restrict__ out, int64_t n) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    out[i] = a[i] + (b ? b[i] : 0.f);
+}
+
+// dz = dout * (out > 0): ReLU backward; out_is_bf16 selects the saved activation's type.
+__global__ void relu_bwd_kernel(const float* __restrict__ dout, const void* __restrict__ out,
+                                int out_is_bf16, __nv_bfloat16* __restrict__ dz, int64_t n) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float o = out_is_bf16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(out)[i])
+                                : static_cast<const float*>(out)[i];
+    dz[i] = __float2bfloat16(o > 0.f ? dout[i] : 0.f);
+  }
+}
+
+// Column sums of a [rows, cols] matrix (bf16 or f32) into out[cols] (+=): each CTA reduces a
+// 32-column x ROWS_PER_CTA-row slab, one atomicAdd per column per CTA.
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ x, int64_t ld, int64_t rows, int cols,
+                              float* __restrict__ out, int rows_per_cta) {
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int ry = threadIdx.x >> 5;  // 0..7
+  const int64_t r0 = static_cast<int64_t>(blockIdx.y) * rows_per_cta;
+  const int64_t r1 = min(rows, r0 + rows_per_cta);
+  float s = 0.f;
+  if (c < cols) {
+    for (int64_t r = r0 + ry; r < r1; r += 8) {
+      if constexpr (sizeof(T) == 2) s += __bfloat162float(x[r * ld + c]);
+      else s += x[r * ld + c];
+    }
+  }
+  red[ry][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (ry == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x & 31];
+    atomicAdd(out + c, t);
+  }
+}
+
+// out[i, :] = bf16(table[idx[i], :]), zero-padded to ld_out
+__global__ void gather_rows_bf16_kernel(const float* __restrict__ table, int dim,
+                                        const int64_t* __restrict__ idx, int64_t n,
+                                        __nv_bfloat16* __restrict__ out, int64_t ld_out) {
+  for (int64_t i = blockIdx.x; i < n; i += gridDim.x) {
+    const float* src = table + idx[i] * dim;
+    for (int c = threadIdx.x; c < ld_out; c += blockDim.x)
+      out[i * ld_out + c] = __float2bfloat16(c < dim ? src[c] : 0.f);
+  }
+}
+
+// dtable[idx[i], :] += d[i, :] except for idx == pad (nn.Embedding(padding_idx), model.py:261)
+__global__ void scatter_add_rows_kernel(const float* __restrict__ d, int64_t ld, int dim,
+                                        const int64_t* __restrict__ idx, int64_t n, int64_t pad,
+                                        float* __restrict__ dtable) {
+  for (int64_t i = blockIdx.x; i < n; i += gridDim.x) {
+    const int64_t row = idx[i];
+    if (row == pad) continue;
+    for (int c = threadIdx.x; c < dim; c += blockDim.x) atomicAdd(dtable + row * dim + c, d[i * ld + c]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// log-softmax + gather + unigram label smoothing (model.py:354-366, 523-530), one warp per row
+//   out_logp[r] = (1-ls) * logp[r, y_r] + ls * sum_v dist[v] * logp[r, v]      (ls = 0: plain gather)
+//   out_prob[r] = softmax[r, y_r]                                               (optional)
+//   out_pred[r] = argmax_v logits[r, v] (first maximal index)                   (optional)
+// backward (given g = dL/d out_logp[r], gp = dL/d out_prob[r]):
+//   dlogits[r, v] = g * ((1-ls) * (1[v=y] - p_v) + ls * (dist_v - p_v * sum(dist)))
+//                 + gp * p_y * (1[v=y] - p_v)
+// ------------------------------------------------------------------------------------------
+__global__ void ce_ls_fwd_kernel(const float* __restrict__ logits, int64_t ld, int64_t ld_b,
+                                 int64_t rows_per_b, int64_t rows, int V,
+                                 const int64_t* __restrict__ targets, const float* __restrict__ dist,
+                                 float ls, float* __restrict__ out_logp, float* __restrict__ out_prob,
+                                 int64_t* __restrict__ out_pred) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = blockIdx.x * static_cast<int64_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const float* x = logits + (r / rows_per_b) * ld_b + (r % rows_per_b) * ld;
+  float mx = -INFINITY;
+  int amax = 0x7fffffff;
+  for (int v = lane; v < V; v += 32) {
+    const float xv = x[v];
+    if (xv > mx) { mx = xv; amax = v; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, amax, o);
+    if (om > mx || (om == mx && oa < amax)) { mx = om; amax = oa; }
+  }
+  float se = 0.f;
+  for (int v = lane; v < V; v += 32) se += expf(x[v] - mx);
+  se = warp_sum(se);
+  const float lse = mx + logf(se);
+  float reg = 0.f;
+  if (ls > 0.f) {
+    for (int v = lane; v < V; v += 32) reg += dist[v] * (x[v] - lse);
+    reg = warp_sum(reg);
+  }
+  if (lane == 0) {
+    int64_t y = targets ? targets[r] : amax;
+    const float lp = x[y] - lse;
+    out_logp[r] = (ls > 0.f) ? (1.f - ls) * lp + ls * reg : lp;
+    if (out_prob) out_prob[r] = expf(lp);
+    if (out_pred) out_pred[r] = amax;
+  }
+}
+
+__global__ void ce_ls_bwd_kernel(const float* __restrict__ logits, int64_t ld, int64_t ld_b,
+                                 int64_t rows_per_b, int64_t rows, int V,
+                                 const int64_t* __restrict__ targets, const float* __restrict__ dist,
+                                 float ls, const float* __restrict__ g_logp,
+                                 const float* __restrict__ g_prob, float* __restrict__ dlogits) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = blockIdx.x * static_cast<int64_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int64_t roff = (r / rows_per_b) * ld_b + (r % rows_per_b) * ld;
+  const float* x = logits + roff;
+  float mx = -INFINITY;
+  for (int v = lane; v < V; v += 32) mx = fmaxf(mx, x[v]);
+  mx = warp_max(mx);
+  float se = 0.f, sd = 0.f;
+  for (int v = lane; v < V; v += 32) {
+    se += expf(x[v] - mx);
+    if (ls > 0.f) sd += dist[v];
+  }
+  se = warp_sum(se);
+  sd = warp_sum(sd);
+  const float inv = 1.f / se;
+  int64_t y;
+  if (targets) {
+    y = targets[r];
+  } else {  // free-running decode gathers at the row's own argmax (first maximal index)
+    int amax = 0x7fffffff;
+    for (int v = lane; v < V; v += 32)
+      if (x[v] == mx && v < amax) amax = v;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = min(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    y = amax;
+  }
+  const float g = g_logp ? g_logp[r] : 0.f;
+  const float py = expf(x[y] - mx) * inv;
+  const float gp = g_prob ? g_prob[r] * py : 0.f;
+  for (int v = lane; v < V; v += 32) {
+    const float pv = expf(x[v] - mx) * inv;
+    const float ind = (v == y) ? 1.f : 0.f;
+    float d = g * (1.f - ls) * (ind - pv) + gp * (ind - pv);
+    if (ls > 0.f) d += g * ls * (dist[v] - pv * sd);
+    dlogits[roff + v] = d;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// fused global-norm clip + Adam / AMSGrad on a flat f32 buffer
+// (torch.nn.utils.clip_grad_norm_ + torch.optim.Adam; solver.py:152-153, 171-173, 296-297, 384-385)
+// ------------------------------------------------------------------------------------------
+__global__ void sqnorm_partial_kernel(const float* __restrict__ g, int64_t n, double* __restrict__ partials) {
+  __shared__ double red[8];
+  double s = 0.0;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const double v = g[i];
+    s += v * v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int k = 0; k < (blockDim.x >> 5); ++k) t += red[k];
+    partials[blockIdx.x] = t;
+  }
+}
+
+// Deterministic second stage: one warp sums the per-CTA partials in a fixed order.
+__global__ void sqnorm_final_kernel(const double* __restrict__ partials, int np, float* __restrict__ out_norm) {
+  double s = 0.0;
+  for (int i = threadIdx.x; i < np; i += 32) s += partials[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (threadIdx.x == 0) *out_norm = static_cast<float>(sqrt(s));
+}
+
+__global__ void adam_step_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                 float* __restrict__ m, float* __restrict__ v,
+                                 float* __restrict__ vmax, int64_t n, float lr, float b1, float b2,
+                                 float eps, float wd, const int32_t* __restrict__ step_dev, float max_norm,
+                                 const float* __restrict__ norm_ptr, float grad_scale) {
+  const float stepf = static_cast<float>(*step_dev);
+  const float bc1 = 1.f - powf(b1, stepf);
+  const float bc2_sqrt = sqrtf(1.f - powf(b2, stepf));
+  float coef = grad_scale;
+  if (norm_ptr && max_norm > 0.f) {
+    const float c = max_norm / (*norm_ptr * grad_scale + 1e-6f);
+    coef *= fminf(c, 1.f);
+  }
+  const float step_size = lr / bc1;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float pi = p[i];
+    float gi = g[i] * coef;
+    if (wd != 0.f) gi += wd * pi;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    float denom;
+    if (vmax) {
+      const float vm = fmaxf(vmax[i], vi);
+      vmax[i] = vm;
+      denom = sqrtf(vm) / bc2_sqrt + eps;
+    } else {
+      denom = sqrtf(vi) / bc2_sqrt + eps;
+    }
+    p[i] = pi - step_size * (mi / denom);
+  }
+}
+
+}  // namespace las
+
+using namespace las;
+
+extern "C" {
+
+int las_cvt_pad_bf16(const float* src, int64_t ld_src, int64_t rows, int cols, void* dst,
+                     int64_t ld_dst, void* stream) {
+  LAS_REQUIRE(ld_dst % 2 == 0 && ld_dst >= cols, "cvt_pad: bad ld_dst");
+  if (rows == 0) return 0;
+  cvt_pad_bf16_kernel<<<grid_for(rows * (ld_dst / 2)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, ld_src, rows, cols, static_cast<__nv_bfloat16*>(dst), ld_dst);
+  LAS_LAUNCH_CHECK();
+  return 0;
+}
+
+int las_add2(const float* a, const float* b, float* out, int64_t n, void* stream) {
+  if (n == 0) return 0;
+  add2_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, b, out, n);
+  LAS_LAUNCH_CHECK();
+  return 0;
+}
+
+int las_relu_bwd(const float* dout, const void* out, int out_is_bf16, void* dz, int64_t n, void* stream) {
+  if (n == 0) return 0;
+  relu_bwd_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      dout, out, out_is_bf16, static_cast<__nv_bfloat16*>(dz), n);
+  LAS_LAUNCH_CHECK();
+  return 0;
+}
+
+int las_colsum(const void* x, int x_is_bf16, int64_t ld, int64_t rows, int cols, float* out, void* stream) {
+  if (rows == 0 || cols == 0) return 0;
+  const int rows_per_cta = 512;
+  dim3 grid((cols + 31) / 32, static_cast<unsigned>((rows + rows_per_cta - 1) / rows_per_cta));
+  if (x_is_bf16)
+    colsum_kernel<__nv_bfloat16><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(x), ld, rows, cols, out, rows_per_cta);
+  else
+    colsum_kernel<float><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const float*>(x), ld, rows, cols, out, rows_per_cta);
+  LAS_LAUNCH_CHECK();
+  return 0;
+}
+
+int las_gather_rows_bf16(const float* table, int dim, const int64_t* idx, int64_t n, void* out,
+                         int64_t ld_out, void* stream) {
+  if (n == 0) return 0;
+  gather_rows_bf16_kernel<<<static_cast<int>(n < 4096 ? n : 4096), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      table, dim, idx, n, static_cast<__nv_bfloat16*>(out), ld_out);
+  LAS_LAUNCH_CHECK();
+  return 0;
+}
+
+int las_scatter_add_rows(const float* d, int64_t ld, int dim, const int64_t* idx, int64_t n, int64_t pad,
+                         float* dtable, void* stream) {
+  if (n == 0) return 0;
+  scatter_add_rows_kernel<<<static_cast<int>(n < 4096 ? n : 4096), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      d, ld, dim, idx, n, pad, dtable);
+  LAS_LAUNCH_CHECK();
+  return 0;
+}
+
+int las_ce_ls_fwd(const float* logits, int64_t ld, int64_t ld_b, int64_t rows_per_b, int64_t rows, int V,
+                  const int64_t* targets, const float* dist, float ls, float* out_logp, float* out_prob,
+                  int64_t* out_pred, void* stream) {
+  if (rows == 0) return 0;
+  const int wpb = 8;
+  ce_ls_fwd_kernel<<<static_cast<unsigned>((rows + wpb - 1) / wpb), wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      logits, ld, ld_b, rows_per_b, rows, V, targets, dist, ls, out_logp, out_prob, out_pred);
+  LAS_LAUNCH_CHECK();
+  return 0;
+}
+
+int las_ce_ls_bwd(const float* logits, int64_t ld, int64_t ld_b, int64_t rows_per_b, int64_t rows, int V,
+                  const int64_t* targets, const float* dist, float ls, const float* g_logp,
+                  const float* g_prob, float* dlogits, void* stream) {
+  if (rows == 0) return 0;
+  const int wpb = 8;
+  ce_ls_bwd_kernel<<<static_cast<unsigned>((rows + wpb - 1) / wpb), wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      logits, ld, ld_b, rows_per_b, rows, V, targets, dist, ls, g_logp, g_prob, dlogits);
+  LAS_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void pyramid_lens_kernel(const int32_t* __restrict__ in, int B, int sub, int32_t* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B) out[i] = (in[i] + 1) / sub;
+}
+
+int las_pyramid_lens(const int32_t* lens_in, int B, int sub, int32_t* lens_out, void* stream) {
+  if (B == 0) return 0;
+  LAS_REQUIRE(sub >= 1, "pyramid_lens: subsample factor must be >= 1");
+  pyramid_lens_kernel<<<(B + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(lens_in, B, sub, lens_out);
+  LAS_LAUNCH_CHECK();
+  return 0;
+}
+
+int las_grad_norm(const float* g, int64_t n, void* partials_ws, float* out_norm, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int np = 256;
+  sqnorm_partial_kernel<<<np, 256, 0, stream>>>(g, n, static_cast<double*>(partials_ws));
+  sqnorm_final_kernel<<<1, 32, 0, stream>>>(static_cast<const double*>(partials_ws), np, out_norm);
+  LAS_LAUNCH_CHECK();
+  return 0;
+}
+
+int las_adam_step(float* p, const float* g, float* m, float* v, float* vmax, int64_t n, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, const int32_t* step_dev,
+                  float max_norm, const float* norm_ptr, float grad_scale, void* stream) {
+  if (n == 0) return 0;
+  LAS_REQUIRE(step_dev != nullptr, "adam: step_dev must point to the device step counter");
+  adam_step_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      p, g, m, v, vmax, n, lr, beta1, beta2, eps, weight_decay, step_dev, max_norm, norm_ptr,
+      grad_scale);
+  LAS_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,454 @@
+// LSTM cell steps and small batched mat-vecs on warp-level bf16 MMA. Weights are pre-packed in
+// mma.m16n8k16 A-fragment order (one 128-bit load per lane per 16x16 tile), accumulation and the
+// cell state are f32.
+//
+//  * pack_afrag_kernel   : f32 weight matrix -> bf16 A fragments (plain or LSTM gate-interleaved
+//                          row order, optionally from the transposed source)
+//  * cell_fwd_kernel     : one timestep of an LSTM layer (both directions of a BLSTM in one launch),
+//                          per-sequence length predication, zero output past the length.
+//                          Replaces nn.LSTM over a PackedSequence (model.py:79-81, 515-517) and
+//                          nn.LSTMCell (model.py:286).
+//  * cell_bwd_kernel     : the matching BPTT step: dh = A^T-frag MMA + dy (+extra), gate derivatives.
+//  * smallmm_kernel      : out[n, m] = sum_k W[m,k] v[n,k] (+bias) (+add) for the per-step
+//                          projections of the decoder (mlp_dec, mlp_o, output_layer and transposes).
+//
+// These are the per-timestep kernels: the host loops in this file (encoder / LM sequences) and in
+// decoder.cu enqueue one launch per step on the caller's stream, which the Python side captures
+// into a CUDA graph. The cluster-persistent BLSTM kernel lives in blstm_persistent.cu.
+#include "common.cuh"
+#include "las_internal.h"
+#include "../../include/las_b200.h"
+
+namespace las {
+
+// ------------------------------------------------------------------------------------------
+// A-fragment packing
+// ------------------------------------------------------------------------------------------
+// out[((tile*KT + kt)*32 + lane)*4 + j]: j&1 -> row +8, j>>1 -> col +8 (mma.m16n8k16 A layout).
+// mode 0: tile rows are 16 consecutive logical rows.
+// mode 1: LSTM gate interleave: tile = 2*ug + half; rows 0-7 -> gate 2*half of units 8ug..8ug+7,
+//         rows 8-15 -> gate 2*half+1 of the same units (logical row = gate*H + unit).
+// transposed != 0: logical A[row][col] = W[col][row].
+__global__ void pack_afrag_kernel(const float* __restrict__ W, int64_t ld, int rows, int cols,
+                                  int col_offset, int mode, int H, int transposed, int tiles, int KT,
+                                  uint32_t* __restrict__ out) {
+  const int64_t total = static_cast<int64_t>(tiles) * KT * 128;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int j = idx & 3;
+    const int lane = (idx >> 2) & 31;
+    const int64_t tk = idx >> 7;
+    const int kt = tk % KT;
+    const int tile = tk / KT;
+    const int g = lane >> 2, tig = lane & 3;
+    const int rl = g + 8 * (j & 1);
+    const int c0 = 16 * kt + 2 * tig + 8 * (j >> 1);
+    int row;
+    if (mode == 0) {
+      row = 16 * tile + rl;
+    } else {
+      const int ug = tile >> 1, half = tile & 1;
+      const int unit = 8 * ug + (rl & 7);
+      const int gate = 2 * half + (rl >> 3);
+      row = (unit < H) ? gate * H + unit : rows;  // out of range -> zero
+    }
+    float v0 = 0.f, v1 = 0.f;
+    if (row < rows) {
+      if (!transposed) {
+        if (c0 < cols) v0 = W[row * ld + col_offset + c0];
+        if (c0 + 1 < cols) v1 = W[row * ld + col_offset + c0 + 1];
+      } else {
+        if (c0 < cols) v0 = W[static_cast<int64_t>(c0) * ld + col_offset + row];
+        if (c0 + 1 < cols) v1 = W[static_cast<int64_t>(c0 + 1) * ld + col_offset + row];
+      }
+    }
+    out[idx] = pack_bf16x2(v0, v1);
+  }
+}
+
+int pack_afrag(const float* W, int64_t ld, int rows, int cols, int col_offset, int mode, int H,
+               bool transposed, int tiles, int KT, uint32_t* out, cudaStream_t stream) {
+  const int64_t total = static_cast<int64_t>(tiles) * KT * 128;
+  if (total == 0) return 0;
+  int blocks = static_cast<int>((total + 255) / 256);
+  if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
+  pack_afrag_kernel<<<blocks, 256, 0, stream>>>(W, ld, rows, cols, col_offset, mode, H,
+                                                transposed ? 1 : 0, tiles, KT, out);
+  LAS_LAUNCH_CHECK();
+  return 0;
+}
+
+// B-operand fragment word: two consecutive K elements of row-major v (bf16, or f32 converted on
+// the fly). `off` is an even element offset.
+__device__ __forceinline__ uint32_t ldb_frag(const void* v, int is_f32, int64_t off) {
+  if (is_f32) {
+    const float2 f = *reinterpret_cast<const float2*>(static_cast<const float*>(v) + off);
+    return pack_bf16x2(f.x, f.y);
+  }
+  return *reinterpret_cast<const uint32_t*>(static_cast<const __nv_bfloat16*>(v) + off);
+}
+
+// ------------------------------------------------------------------------------------------
+// forward LSTM cell step
+// ------------------------------------------------------------------------------------------
+// grid (UG, ceil(B/32), ndir), 4 warps; warp w owns batch rows 32*blockIdx.y + 8w .. +7 and the
+// 8 hidden units of unit-group blockIdx.x (all four gates -> the cell update is thread-local).
+__global__ void __launch_bounds__(128) cell_fwd_kernel(CellFwdParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, tig = lane & 3;
+  const int ug = blockIdx.x;
+  const int n0 = (blockIdx.y * 4 + warp) * 8;
+  const int dir = blockIdx.z;
+  if (n0 >= p.B) return;
+  const int t = (dir == 0) ? p.step : (p.T - 1 - p.step);
+  const int nb = min(n0 + g, p.B - 1);  // clamp the operand row; results of rows >= B are dropped
+
+  float acc[2][2][4];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
+
+  if (p.KT1 > 0) {
+    const uint4* a_if = reinterpret_cast<const uint4*>(p.a1 + dir * p.a_dir) +
+                        static_cast<int64_t>(2 * ug) * p.KT1 * 32 + lane;
+    const uint4* a_go = a_if + static_cast<int64_t>(p.KT1) * 32;
+    const __nv_bfloat16* vin = p.v1 + dir * p.v1_dir + nb * p.v1_ld + 2 * tig;
+#pragma unroll 4
+    for (int kt = 0; kt < p.KT1; ++kt) {
+      const uint4 aif = __ldg(a_if + kt * 32);
+      const uint4 ago = __ldg(a_go + kt * 32);
+      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(vin + 16 * kt);
+      const uint32_t b1 = *reinterpret_cast<const uint32_t*>(vin + 16 * kt + 8);
+      const uint32_t A0[4] = {aif.x, aif.y, aif.z, aif.w};
+      const uint32_t A1[4] = {ago.x, ago.y, ago.z, ago.w};
+      mma_bf16_16816(acc[0][kt & 1], A0, b0, b1);
+      mma_bf16_16816(acc[1][kt & 1], A1, b0, b1);
+    }
+  }
+  if (p.KT2 > 0) {
+    const uint4* a_if = reinterpret_cast<const uint4*>(p.a2) + static_cast<int64_t>(2 * ug) * p.KT2 * 32 + lane;
+    const uint4* a_go = a_if + static_cast<int64_t>(p.KT2) * 32;
+    const __nv_bfloat16* vin = p.v2 + nb * p.v2_ld + 2 * tig;
+#pragma unroll 4
+    for (int kt = 0; kt < p.KT2; ++kt) {
+      const uint4 aif = __ldg(a_if + kt * 32);
+      const uint4 ago = __ldg(a_go + kt * 32);
+      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(vin + 16 * kt);
+      const uint32_t b1 = *reinterpret_cast<const uint32_t*>(vin + 16 * kt + 8);
+      const uint32_t A0[4] = {aif.x, aif.y, aif.z, aif.w};
+      const uint32_t A1[4] = {ago.x, ago.y, ago.z, ago.w};
+      mma_bf16_16816(acc[0][kt & 1], A0, b0, b1);
+      mma_bf16_16816(acc[1][kt & 1], A1, b0, b1);
+    }
+  }
+  const int u = 8 * ug + g;
+  if (u >= p.H) return;
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int n = n0 + 2 * tig + e;
+    if (n >= p.B) continue;
+    const int len = p.lens ? p.lens[n] : p.T;
+    const bool active = t < len;
+    const int64_t st = (static_cast<int64_t>(dir) * p.B + n) * p.H + u;  // c_state index
+    __nv_bfloat16 h_old = __float2bfloat16(0.f);
+    if (p.v1) h_old = p.v1[dir * p.v1_dir + n * p.v1_ld + u];
+    __nv_bfloat16 h_new = h_old;
+    __nv_bfloat16 y_val = __float2bfloat16(0.f);
+    if (active) {
+      const float* xp = p.xproj + n * p.xp_ld_b + t * p.xp_ld_t + dir * p.xp_ld_dir + u;
+      const float gi = acc[0][0][e] + acc[0][1][e] + xp[0];
+      const float gf = acc[0][0][2 + e] + acc[0][1][2 + e] + xp[p.H];
+      const float gg = acc[1][0][e] + acc[1][1][e] + xp[2 * p.H];
+      const float go = acc[1][0][2 + e] + acc[1][1][2 + e] + xp[3 * p.H];
+      const float i = sigmoid_acc(gi), f = sigmoid_acc(gf), gc = tanh_acc(gg), o = sigmoid_acc(go);
+      const float c = f * p.c_state[st] + i * gc;
+      const float h = o * tanh_acc(c);
+      p.c_state[st] = c;
+      h_new = __float2bfloat16(h);
+      y_val = h_new;
+      const int64_t sv = ((static_cast<int64_t>(dir) * p.B + n) * p.T + t) * p.H + u;
+      if (p.gates_save) {
+        __half2 lo = __floats2half2_rn(i, f), hi = __floats2half2_rn(gc, o);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&lo);
+        pk.y = *reinterpret_cast<uint32_t*>(&hi);
+        reinterpret_cast<uint2*>(p.gates_save)[sv] = pk;
+      }
+      if (p.c_save) p.c_save[sv] = c;
+    }
+    p.hout[dir * p.hout_dir + n * p.hout_ld + u] = h_new;
+    if (p.y) {
+      const int64_t yo = n * p.y_ld_b + t * p.y_ld_t + static_cast<int64_t>(dir) * p.H + u;
+      p.y[yo] = y_val;
+      if (p.rep_row && t == p.T - 1) p.y[yo + p.y_ld_t] = y_val;
+      if (p.hprev) p.hprev[n * p.hp_ld_b + t * p.hp_ld_t + static_cast<int64_t>(dir) * p.H + u] = h_old;
+    }
+  }
+}
+
+int launch_cell_fwd(const CellFwdParams& p, cudaStream_t stream) {
+  dim3 grid(p.UG, (p.B + 31) / 32, p.ndir);
+  cell_fwd_kernel<<<grid, 128, 0, stream>>>(p);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// backward LSTM cell step
+// ------------------------------------------------------------------------------------------
+// grid (ceil(H/16), ceil(B/32), ndir), 4 warps. dh[n, j] = sum_k A[j, k] v[n, k] + dy + extra;
+// A = W_hh^T (encoder/LM; v = gate gradients of the step that consumed h_t) or mlp_dec^T
+// (decoder; v = gradient of the attention's decoder-state projection).
+__global__ void __launch_bounds__(128) cell_bwd_kernel(CellBwdParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, tig = lane & 3;
+  const int jt = blockIdx.x;
+  const int n0 = (blockIdx.y * 4 + warp) * 8;
+  const int dir = blockIdx.z;
+  if (n0 >= p.B) return;
+  // BPTT order: forward direction walks t = T-1..0, reverse direction walks t = 0..T-1.
+  const int t = (dir == 0) ? (p.T - 1 - p.step) : p.step;
+
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
+
+  if (p.v != nullptr && p.KT > 0) {
+    const uint4* aT = reinterpret_cast<const uint4*>(p.a_pk + dir * p.a_dir) +
+                      static_cast<int64_t>(jt) * p.KT * 32 + lane;
+    const int nb = min(n0 + g, p.B - 1);
+    const int t_src = (dir == 0) ? p.v_t_fwd : p.v_t_rev;  // the step that consumed h_t
+    const int64_t off = dir * p.v_dir + nb * p.v_ld + t_src * p.v_ld_t + 2 * tig;
+#pragma unroll 4
+    for (int kt = 0; kt < p.KT; ++kt) {
+      const uint4 a = __ldg(aT + kt * 32);
+      const uint32_t b0 = ldb_frag(p.v, p.v_f32, off + 16 * kt);
+      const uint32_t b1 = ldb_frag(p.v, p.v_f32, off + 16 * kt + 8);
+      const uint32_t A[4] = {a.x, a.y, a.z, a.w};
+      mma_bf16_16816(acc[kt & 3], A, b0, b1);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int j = 16 * jt + g + 8 * (e >> 1);
+    const int n = n0 + 2 * tig + (e & 1);
+    if (j >= p.H || n >= p.B) continue;
+    const int len = p.lens ? p.lens[n] : p.T;
+    const bool active = t < len;
+    __nv_bfloat16* dg = p.dG + n * p.dg_ld_b + t * p.dg_ld_t + static_cast<int64_t>(dir) * 4 * p.H + j;
+    if (!active) {
+      const __nv_bfloat16 z = __float2bfloat16(0.f);
+      dg[0] = z; dg[p.H] = z; dg[2 * p.H] = z; dg[3 * p.H] = z;
+      continue;
+    }
+    const int64_t st = (static_cast<int64_t>(dir) * p.B + n) * p.H + j;
+    const int64_t sv = ((static_cast<int64_t>(dir) * p.B + n) * p.T + t) * p.H + j;
+    const uint2 pk = reinterpret_cast<const uint2*>(p.gates_save)[sv];
+    const float2 if_ = __half22float2(*reinterpret_cast<const __half2*>(&pk.x));
+    const float2 go_ = __half22float2(*reinterpret_cast<const __half2*>(&pk.y));
+    const float i = if_.x, f = if_.y, gc = go_.x, o = go_.y;
+    const float c = p.c_save[sv];
+    float c_prev = 0.f;
+    if (dir == 0) { if (t > 0) c_prev = p.c_save[sv - p.H]; }
+    else          { if (t + 1 < len) c_prev = p.c_save[sv + p.H]; }
+    float dh = acc[0][e] + acc[1][e] + acc[2][e] + acc[3][e];
+    if (p.dy) {
+      const float* dyp = p.dy + n * p.dy_ld_b + t * p.dy_ld_t + static_cast<int64_t>(dir) * p.H + j;
+      dh += dyp[0];
+      if (p.rep_row && t == p.T - 1) dh += dyp[p.dy_ld_t];
+    }
+    if (p.dh_extra) dh += p.dh_extra[n * p.dhx_ld + j];
+    const float tc = tanh_acc(c);
+    const float dc = dh * o * (1.f - tc * tc) + p.dc_state[st];
+    p.dc_state[st] = dc * f;
+    dg[0] = __float2bfloat16(dc * gc * i * (1.f - i));
+    dg[p.H] = __float2bfloat16(dc * c_prev * f * (1.f - f));
+    dg[2 * p.H] = __float2bfloat16(dc * i * (1.f - gc * gc));
+    dg[3 * p.H] = __float2bfloat16(dh * tc * o * (1.f - o));
+  }
+}
+
+int launch_cell_bwd(const CellBwdParams& p, cudaStream_t stream) {
+  dim3 grid((p.H + 15) / 16, (p.B + 31) / 32, p.ndir);
+  cell_bwd_kernel<<<grid, 128, 0, stream>>>(p);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// small batched mat-vec: out[n, m] = sum_k A[m, k] * v[n, k] (+ bias[m]) (+ add[n, m])
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) smallmm_kernel(SmallMMParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, tig = lane & 3;
+  const int mt = blockIdx.x;
+  const int n0 = (blockIdx.y * 4 + warp) * 8;
+  if (n0 >= p.N) return;
+  const uint4* a = reinterpret_cast<const uint4*>(p.a_pk) + static_cast<int64_t>(mt) * p.KT * 32 + lane;
+  const int64_t off = static_cast<int64_t>(min(n0 + g, p.N - 1)) * p.ldv + 2 * tig;
+  float acc[4][4];
+#pragma unroll
+  for (int x = 0; x < 4; ++x)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[x][c] = 0.f;
+#pragma unroll 4
+  for (int kt = 0; kt < p.KT; ++kt) {
+    const uint4 av = __ldg(a + kt * 32);
+    const uint32_t b0 = ldb_frag(p.v, p.v_f32, off + 16 * kt);
+    const uint32_t b1 = ldb_frag(p.v, p.v_f32, off + 16 * kt + 8);
+    const uint32_t A[4] = {av.x, av.y, av.z, av.w};
+    mma_bf16_16816(acc[kt & 3], A, b0, b1);
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int m = 16 * mt + g + 8 * (e >> 1);
+    const int n = n0 + 2 * tig + (e & 1);
+    if (m >= p.M || n >= p.N) continue;
+    float r = acc[0][e] + acc[1][e] + acc[2][e] + acc[3][e];
+    if (p.bias) r += p.bias[m];
+    if (p.add) r += p.add[n * p.ld_add + m];
+    if (p.out_f32) p.out_f32[n * p.ld_out + m] = r;
+    if (p.out_bf16) p.out_bf16[n * p.ld_outb + m] = __float2bfloat16(r);
+  }
+}
+
+int smallmm(const uint32_t* a_pk, int M, int K, const void* v, int v_f32, int64_t ldv, int N,
+            const float* bias, const float* add, int64_t ld_add, float* out_f32, int64_t ld_out,
+            __nv_bfloat16* out_bf16, int64_t ld_outb, cudaStream_t stream) {
+  if (M == 0 || N == 0) return 0;
+  SmallMMParams p;
+  p.a_pk = a_pk; p.v = v; p.v_f32 = v_f32; p.ldv = ldv; p.bias = bias; p.add = add; p.ld_add = ld_add;
+  p.out_f32 = out_f32; p.ld_out = ld_out; p.out_bf16 = out_bf16; p.ld_outb = ld_outb;
+  p.M = M; p.N = N; p.MT = (M + 15) / 16; p.KT = (K + 15) / 16;
+  dim3 grid(p.MT, (N + 31) / 32);
+  smallmm_kernel<<<grid, 128, 0, stream>>>(p);
+  return 0;
+}
+
+}  // namespace las
+
+// ==========================================================================================
+// C-ABI
+// ==========================================================================================
+using namespace las;
+
+extern "C" {
+
+int las_pack_afrag(const float* W, int64_t ld, int rows, int cols, int col_offset, int mode, int H,
+                   int transposed, void* out, void* stream) {
+  const int tiles = (mode == 1) ? 2 * ((H + 7) / 8) : (rows + 15) / 16;
+  const int KT = (cols + 15) / 16;
+  return pack_afrag(W, ld, rows, cols, col_offset, mode, H, transposed != 0, tiles, KT,
+                    static_cast<uint32_t*>(out), static_cast<cudaStream_t>(stream));
+}
+
+int64_t las_afrag_bytes(int rows, int cols, int mode, int H) {
+  const int64_t tiles = (mode == 1) ? 2 * ((H + 7) / 8) : (rows + 15) / 16;
+  const int64_t KT = (cols + 15) / 16;
+  return tiles * KT * 128 * 4;
+}
+
+int las_smallmm(const void* a_pk, int M, int K, const void* v, int v_is_f32, int64_t ldv, int N,
+                const float* bias, const float* add, int64_t ld_add, float* out_f32, int64_t ld_out,
+                void* out_bf16, int64_t ld_outb, void* stream) {
+  int rc = smallmm(static_cast<const uint32_t*>(a_pk), M, K, v, v_is_f32, ldv, N, bias, add, ld_add,
+                   out_f32, ld_out, static_cast<__nv_bfloat16*>(out_bf16), ld_outb,
+                   static_cast<cudaStream_t>(stream));
+  if (rc) return rc;
+  LAS_LAUNCH_CHECK();
+  return 0;
+}
+
+int64_t las_lstm_ws_bytes(int B, int H, int ndir) {
+  const int64_t Kp = (H + 15) / 16 * 16 + 16;
+  // bf16 state ping-pong (2 buffers) + f32 cell state
+  return 2 * static_cast<int64_t>(ndir) * B * Kp * 2 + static_cast<int64_t>(ndir) * B * H * 4 + 256;
+}
+
+// One LSTM layer (ndir = 1 or 2) over padded [B, T] sequences with per-sequence lengths.
+//   xproj      f32 [B, T, ndir*4H]: W_ih x + b_ih + b_hh (gate order i,f,g,o per direction)
+//   whh_pk     A fragments of W_hh per direction (las_pack_afrag mode 1), consecutive directions
+//   y          bf16, y[b*y_ld_b + t*y_ld_t + dir*H + u]; caller pre-zeroes it (positions >= len[b]
+//              stay exact zeros, the pad_packed_sequence semantics of model.py:81)
+//   rep_row    1: the value written at t = T-1 is also written at row T (replicate pad of an odd
+//              padded extent, model.py:88-89)
+//   hprev      bf16, hprev[b*hp_ld_b + t*hp_ld_t + dir*H + u]: the state entering step t (for the W_hh gradient)
+//   gates_save f16 [ndir, B, T, H, 4] post-activation (i,f,g,o); c_save f32 [ndir, B, T, H]
+int las_lstm_seq_fwd(const float* xproj, const void* whh_pk, const int32_t* lens, int B, int T, int H,
+                     int ndir, void* y, int64_t y_ld_b, int64_t y_ld_t, int rep_row, void* hprev,
+                     int64_t hp_ld_b, int64_t hp_ld_t, void* gates_save, float* c_save, void* ws,
+                     void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  LAS_REQUIRE(H % 8 == 0, "lstm: hidden size %d must be a multiple of 8", H);
+  LAS_REQUIRE(ndir == 1 || ndir == 2, "lstm: ndir must be 1 or 2");
+  if (B == 0 || T == 0) return 0;
+  const int KT = (H + 15) / 16;
+  const int64_t Kp = KT * 16 + 16;
+  CellFwdParams p = {};
+  p.B = B; p.T = T; p.H = H; p.ndir = ndir; p.UG = H / 8;
+  p.xproj = xproj; p.xp_ld_t = static_cast<int64_t>(ndir) * 4 * H; p.xp_ld_b = p.xp_ld_t * T;
+  p.xp_ld_dir = 4 * H;
+  p.a1 = static_cast<const uint32_t*>(whh_pk); p.KT1 = KT;
+  p.a_dir = static_cast<int64_t>(2) * p.UG * KT * 128;
+  p.a2 = nullptr; p.v2 = nullptr; p.KT2 = 0; p.v2_ld = 0;
+  p.lens = lens;
+  p.y = static_cast<__nv_bfloat16*>(y); p.y_ld_b = y_ld_b; p.y_ld_t = y_ld_t;
+  p.hprev = static_cast<__nv_bfloat16*>(hprev); p.hp_ld_b = hp_ld_b; p.hp_ld_t = hp_ld_t;
+  p.gates_save = static_cast<__half*>(gates_save); p.c_save = c_save;
+  p.rep_row = rep_row;
+  const size_t hbytes = static_cast<size_t>(ndir) * B * Kp * sizeof(__nv_bfloat16);
+  __nv_bfloat16* hbuf = static_cast<__nv_bfloat16*>(ws);
+  p.c_state = reinterpret_cast<float*>(static_cast<char*>(ws) + ((2 * hbytes + 255) / 256) * 256);
+  LAS_CUDA(cudaMemsetAsync(ws, 0, static_cast<size_t>(las_lstm_ws_bytes(B, H, ndir)), stream));
+  p.v1_ld = Kp; p.v1_dir = static_cast<int64_t>(B) * Kp;
+  p.hout_ld = Kp; p.hout_dir = p.v1_dir;
+  for (int s = 0; s < T; ++s) {
+    p.step = s;
+    p.v1 = hbuf + static_cast<size_t>(s & 1) * ndir * B * Kp;
+    p.hout = hbuf + static_cast<size_t>((s + 1) & 1) * ndir * B * Kp;
+    launch_cell_fwd(p, stream);
+  }
+  LAS_LAUNCH_CHECK();
+  return 0;
+}
+
+// BPTT through one LSTM layer. dy f32 indexed like y (may be NULL); dG bf16 out,
+// dG[b*dg_ld_b + t*dg_ld_t + dir*4H + gate*H + u] (zeros past the length); whhT_pk = fragments of
+// W_hh^T per direction (las_pack_afrag mode 0, transposed). ws: f32 [ndir, B, H] scratch.
+int las_lstm_seq_bwd(const float* dy, int64_t dy_ld_b, int64_t dy_ld_t, int rep_row,
+                     const void* whhT_pk, const int32_t* lens, int B, int T, int H, int ndir,
+                     const void* gates_save, const float* c_save, void* dG, int64_t dg_ld_b,
+                     int64_t dg_ld_t, void* ws, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  LAS_REQUIRE(H % 8 == 0, "lstm: hidden size %d must be a multiple of 8", H);
+  if (B == 0 || T == 0) return 0;
+  CellBwdParams p = {};
+  p.dy = dy; p.dy_ld_b = dy_ld_b; p.dy_ld_t = dy_ld_t; p.rep_row = rep_row;
+  p.dh_extra = nullptr; p.dhx_ld = 0;
+  p.a_pk = static_cast<const uint32_t*>(whhT_pk);
+  p.KT = (4 * H + 15) / 16;
+  p.a_dir = static_cast<int64_t>((H + 15) / 16) * p.KT * 128;
+  p.lens = lens;
+  p.gates_save = static_cast<const __half*>(gates_save); p.c_save = c_save;
+  p.dG = static_cast<__nv_bfloat16*>(dG); p.dg_ld_b = dg_ld_b; p.dg_ld_t = dg_ld_t;
+  p.dc_state = static_cast<float*>(ws);
+  p.B = B; p.T = T; p.H = H; p.ndir = ndir;
+  p.v_f32 = 0; p.v_ld = dg_ld_b; p.v_dir = 4 * H;
+  LAS_CUDA(cudaMemsetAsync(ws, 0, static_cast<size_t>(ndir) * B * H * sizeof(float), stream));
+  for (int s = 0; s < T; ++s) {
+    p.step = s;
+    // source row of the recurrent term: the step that consumed h_t (t+1 forward, t-1 reverse)
+    p.v = (s == 0) ? nullptr : p.dG;
+    p.v_t_fwd = (T - 1 - s) + 1;
+    p.v_t_rev = s - 1;
+    p.v_ld_t = dg_ld_t;
+    launch_cell_bwd(p, stream);
+  }
+  LAS_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,468 @@
+"""torch.autograd.Function wrappers around the C-ABI kernels (include/las_b200.h).
+
+Everything here runs on the CUDA stream torch considers current; tensors are allocated by torch,
+raw device pointers go through ctypes. There is no eager-PyTorch or CPU fallback: without
+liblas_b200.so (or without a CUDA device) the calls raise.
+
+Precision: bf16 MMA operands, f32 accumulation, f32 recurrent cell state, f32 master weights and
+gradients.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import DecArgs, call, ptr
+
+BF16 = torch.bfloat16
+
+
+def _r8(n):
+    return (n + 7) // 8 * 8
+
+
+def _r16(n):
+    return (n + 15) // 16 * 16
+
+
+# --------------------------------------------------------------------------------------------
+# thin op wrappers
+# --------------------------------------------------------------------------------------------
+def gemm(A, lda, a_mn, Bm, ldb, b_mn, M, N, K, out=None, out_bf16=False, bias=None, relu=False,
+         accumulate=False, ldc=None):
+    """D[m,n] = sum_k A[m,k] B[n,k] (+bias[n]) (relu) (+=D). A/Bm: bf16 tensors (base pointers)."""
+    if out is None:
+        out = torch.empty(M, N, device=A.device, dtype=BF16 if out_bf16 else torch.float32)
+    if ldc is None:
+        ldc = N
+    call("las_gemm_bf16", ptr(A), lda, int(a_mn), ptr(Bm), ldb, int(b_mn), ptr(out), ldc, int(out.dtype == BF16),
+         ptr(bias), M, N, K, int(relu), int(accumulate))
+    return out
+
+
+def cvt_bf16(src, cols=None, ld_dst=None, extra_rows=0):
+    """f32 [rows, cols] (row stride src.stride(0)) -> bf16 [rows(+extra zero rows), ld_dst], zero padded."""
+    src2 = src.reshape(-1, src.shape[-1]) if src.dim() != 2 else src
+    rows = src2.shape[0]
+    cols = src2.shape[1] if cols is None else cols
+    ld_dst = _r8(cols) if ld_dst is None else ld_dst
+    if extra_rows:
+        dst = torch.zeros(rows + extra_rows, ld_dst, device=src.device, dtype=BF16)
+    else:
+        dst = torch.empty(rows, ld_dst, device=src.device, dtype=BF16)
+    call("las_cvt_pad_bf16", ptr(src2), src2.stride(0), rows, cols, ptr(dst), ld_dst)
+    return dst
+
+
+def pack_afrag(W, mode, H=0, transposed=False, col_offset=0, cols=None):
+    """f32 weight matrix -> mma A fragments. Logical A is [rows, cols] (see las_pack_afrag)."""
+    W = W.contiguous()
+    if transposed:
+        rows = W.shape[1] if cols is None else cols
+        kcols = W.shape[0]
+        rows_arg, cols_arg = rows, kcols
+    else:
+        rows_arg = W.shape[0]
+        cols_arg = (W.shape[1] - col_offset) if cols is None else cols
+    nbytes = _lib.lib().las_afrag_bytes(rows_arg, cols_arg, mode, H)
+    out = torch.empty(nbytes // 4, device=W.device, dtype=torch.int32)
+    call("las_pack_afrag", ptr(W), W.stride(0), rows_arg, cols_arg, col_offset, mode, H, int(transposed), ptr(out))
+    return out
+
+
+def colsum(x, cols, out=None, ld=None, rows=None):
+    x_bf = x.dtype == BF16
+    ld = x.stride(0) if ld is None else ld
+    rows = x.shape[0] if rows is None else rows
+    if out is None:
+        out = torch.zeros(cols, device=x.device, dtype=torch.float32)
+    call("las_colsum", ptr(x), int(x_bf), ld, rows, cols, ptr(out))
+    return out
+
+
+def lens_tensor(lens, device):
+    if torch.is_tensor(lens):
+        return lens.to(device=device, dtype=torch.int32)
+    return torch.tensor([int(l) for l in lens], dtype=torch.int32, device=device)
+
+
+# --------------------------------------------------------------------------------------------
+# pyramidal BLSTM encoder (model.py:58-98)
+# --------------------------------------------------------------------------------------------
+class EncoderFn(torch.autograd.Function):
+    """x f32 [B, T, D] (zeros past each length), lens int32 [B] (device) ->
+    enc_h f32 [B, Te, H]. `weights` per layer: w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r,
+    b_hh_r, proj_w, proj_b."""
+
+    @staticmethod
+    def forward(ctx, x, lens, subsample, *weights):
+        B, T, D = x.shape
+        dev = x.device
+        n_layers = len(subsample)
+        assert len(weights) == 10 * n_layers
+        xin = cvt_bf16(x.reshape(B * T, D))          # [B*T, Dp] bf16, zero padded columns
+        Dp = xin.shape[1]
+        cur_lens = lens
+        saved = []
+        for i, sub in enumerate(subsample):
+            w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r, proj_w, proj_b = weights[10 * i:10 * i + 10]
+            H = w_hh.shape[1]
+            wcat = cvt_bf16(torch.cat([w_ih, w_ih_r], dim=0), ld_dst=Dp)           # [8H, Dp]
+            bcat = torch.cat([b_ih + b_hh, b_ih_r + b_hh_r])
+            xproj = gemm(xin, Dp, 0, wcat, Dp, 0, B * T, 8 * H, Dp, bias=bcat)      # f32 [B*T, 8H]
+            whh_pk = torch.cat([pack_afrag(w_hh, 1, H), pack_afrag(w_hh_r, 1, H)])
+            Tp = T + (T % 2) if sub > 1 else T
+            y = torch.zeros(B, Tp, 2 * H, device=dev, dtype=BF16)
+            hprev = torch.empty(B, T, 2 * H, device=dev, dtype=BF16)
+            gates = torch.empty(2, B, T, H, 4, device=dev, dtype=torch.float16)
+            csave = torch.empty(2, B, T, H, device=dev, dtype=torch.float32)
+            ws = torch.empty(_lib.lib().las_lstm_ws_bytes(B, H, 2), device=dev, dtype=torch.uint8)
+            rep = int(sub > 1 and T % 2 == 1)
+            call("las_lstm_seq_fwd", ptr(xproj), ptr(whh_pk), ptr(cur_lens), B, T, H, 2, ptr(y), Tp * 2 * H, 2 * H,
+                 rep, ptr(hprev), T * 2 * H, 2 * H, ptr(gates), ptr(csave), ptr(ws))
+            del xproj
+            if sub > 1:
+                T2, Kp = Tp // 2, 4 * H
+            else:
+                T2, Kp = T, 2 * H
+            wp = cvt_bf16(proj_w)                                                   # [H, Kp]
+            out = gemm(y, Kp, 0, wp, Kp, 0, B * T2, proj_w.shape[0], Kp, out_bf16=True, bias=proj_b, relu=True)
+            saved.append((xin, wcat, y, hprev, gates, csave, out, wp, cur_lens, T, Tp, T2, Dp, H, rep))
+            if sub > 1:
+                nl = torch.empty_like(cur_lens)
+                call("las_pyramid_lens", ptr(cur_lens), B, sub, ptr(nl))
+                cur_lens = nl
+            xin, T, Dp = out, T2, proj_w.shape[0]
+        ctx.saved = saved
+        ctx.subsample = list(subsample)
+        ctx.B = B
+        ctx.weights = weights
+        ctx.D = D
+        return out.view(B, T, Dp).float()
+
+    @staticmethod
+    def backward(ctx, denc):
+        B = ctx.B
+        n_layers = len(ctx.subsample)
+        grads = [None] * (10 * n_layers)
+        dout = denc.contiguous().float()
+        for i in reversed(range(n_layers)):
+            xin, wcat, y, hprev, gates, csave, out, wp, lens_i, T, Tp, T2, Dp, H, rep = ctx.saved[i]
+            w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r, proj_w, proj_b = ctx.weights[10 * i:10 * i + 10]
+            dev = dout.device
+            Ho, Kp = proj_w.shape
+            n = B * T2
+            dz = torch.empty(n, Ho, device=dev, dtype=BF16)
+            call("las_relu_bwd", ptr(dout), ptr(out), 1, ptr(dz), n * Ho)
+            # projection: dW = dz^T yview, db = colsum(dz), dy = dz W
+            d_proj_w = gemm(dz, Ho, 1, y, Kp, 1, Ho, Kp, n)
+            d_proj_b = colsum(dz, Ho)
+            dy = gemm(dz, Ho, 0, wp, Kp, 1, n, Kp, Ho)                               # f32 [B, Tp, 2H] view
+            # recurrence
+            whhT = torch.cat([pack_afrag(w_hh, 0, transposed=True), pack_afrag(w_hh_r, 0, transposed=True)])
+            dG = torch.empty(B * T, 8 * H, device=dev, dtype=BF16)
+            ws = torch.empty(2 * B * H, device=dev, dtype=torch.float32)
+            call("las_lstm_seq_bwd", ptr(dy), Tp * 2 * H, 2 * H, rep, ptr(whhT), ptr(lens_i), B, T, H, 2,
+                 ptr(gates), ptr(csave), ptr(dG), T * 8 * H, 8 * H, ptr(ws))
+            del dy
+            # weight gradients as dense contractions over all (b, t)
+            d_wcat = gemm(dG, 8 * H, 1, xin, Dp, 1, 8 * H, Dp, B * T)                # [8H, Dp]
+            d_bcat = colsum(dG, 8 * H)
+            Din = w_ih.shape[1]
+            d_whh = gemm(dG, 8 * H, 1, hprev, 2 * H, 1, 4 * H, H, B * T)
+            d_whh_r = gemm(dG[:, 4 * H:], 8 * H, 1, hprev.view(B * T, 2 * H)[:, H:], 2 * H, 1, 4 * H, H, B * T)
+            grads[10 * i:10 * i + 10] = [d_wcat[:4 * H, :Din], d_whh, d_bcat[:4 * H], d_bcat[:4 * H],
+                                         d_wcat[4 * H:, :Din], d_whh_r, d_bcat[4 * H:], d_bcat[4 * H:],
+                                         d_proj_w, d_proj_b]
+            if i > 0:
+                dout = gemm(dG, 8 * H, 0, wcat, Dp, 1, B * T, Dp, 8 * H)             # f32 [B*T, H_prev]
+        ctx.saved = None
+        return (None, None, None, *grads)
+
+
+# --------------------------------------------------------------------------------------------
+# attention decoder (model.py:139-173, 283-367)
+# --------------------------------------------------------------------------------------------
+DEC_WEIGHTS = ("emb_w", "w_ih", "w_hh", "b_ih", "b_hh", "out_w", "out_b", "mlp_enc_w", "mlp_enc_b", "mlp_dec_w",
+               "mlp_att_w", "conv_w", "gvec_w", "mlp_o_w", "mlp_o_b")
+
+
+def _dec_common(enc_h, W, L, K):
+    B, Te, H = enc_h.shape
+    Hd = W["w_hh"].shape[1]
+    O = W["mlp_o_w"].shape[0]
+    A = W["mlp_enc_w"].shape[0]
+    V, E = W["emb_w"].shape
+    C = W["conv_w"].shape[0]
+    a = DecArgs()
+    a.B, a.L, a.Te, a.Hd, a.O, a.A, a.V, a.E, a.H, a.C, a.K = B, L, Te, Hd, O, A, V, E, H, C, K
+    return a, (B, Te, H, Hd, O, A, V, E, C)
+
+
+class DecoderFn(torch.autograd.Function):
+    """Runs all L decoder steps. Returns (logits_alloc f32 [B, L+1, V] (row r = step r-1; row 0
+    unused), ws_alloc f32 [B, L+1, Te] (row 0 = initial alignment), pred int64 [B, L] or None)."""
+
+    @staticmethod
+    def forward(ctx, enc_h, enc_lens, ys_in, L, mode, smooth_scaling, att_scaling, K, bos, *wts):
+        W = dict(zip(DEC_WEIGHTS, wts))
+        dev = enc_h.device
+        a, (B, Te, H, Hd, O, A, V, E, C) = _dec_common(enc_h, W, L, K)
+        R, ZC, Ep = L + 1, Hd + O, _r16(E)
+        a.mode, a.att_scaling, a.smooth_scaling = mode, att_scaling, smooth_scaling
+        f32 = dict(device=dev, dtype=torch.float32)
+        keep = []  # keep tensors referenced by raw pointers alive until the launches are enqueued
+
+        enc_bf = cvt_bf16(enc_h.reshape(B * Te, H))
+        mlp_enc_bf = cvt_bf16(W["mlp_enc_w"])
+        Pm = gemm(enc_bf, H, 0, mlp_enc_bf, H, 0, B * Te, A, H, bias=W["mlp_enc_b"])
+        wr_cat = torch.cat([W["w_hh"], W["w_ih"][:, E:]], dim=1).contiguous()        # [4Hd, Hd+O]
+        wr_pk = pack_afrag(wr_cat, 1, Hd)
+        mlp_dec_pk = pack_afrag(W["mlp_dec_w"], 0)
+        mlp_o_pk = pack_afrag(W["mlp_o_w"], 0)
+        cell_bias = (W["b_ih"] + W["b_hh"]).contiguous()
+        we = W["w_ih"][:, :E]
+        ws = torch.zeros(B, R, Te, **f32)
+        call("las_att_init", ptr(enc_lens), B, Te, ptr(ws), R * Te)
+        zc = torch.zeros(B * R * ZC + 64, device=dev, dtype=BF16)
+        cx = torch.zeros(B * R * H + 64, device=dev, dtype=BF16)
+        c_state = torch.zeros(B, Hd, **f32)
+        e_buf = torch.empty(B, Te, **f32)
+        dzf = torch.empty(B, L, A, **f32)
+        gates = torch.empty(B, L, Hd, 4, device=dev, dtype=torch.float16)
+        csave = torch.empty(B, L, Hd, **f32)
+        conv_w = W["conv_w"].reshape(C, -1).contiguous()
+        mlp_att = W["mlp_att_w"].contiguous()
+        gvec = W["gvec_w"].reshape(-1).contiguous()
+        a.enc_h, a.P = ptr(enc_bf), ptr(Pm)
+        a.wr_pk, a.mlp_dec_pk, a.mlp_o_pk, a.mlp_o_b = ptr(wr_pk), ptr(mlp_dec_pk), ptr(mlp_o_pk), ptr(W["mlp_o_b"])
+        a.conv_w, a.mlp_att, a.gvec = ptr(conv_w), ptr(mlp_att), ptr(gvec)
+        a.ws, a.zc, a.ctx, a.c_state, a.e_buf, a.dzf = ptr(ws), ptr(zc), ptr(cx), ptr(c_state), ptr(e_buf), ptr(dzf)
+        a.gates_save, a.c_save = ptr(gates), ptr(csave)
+        emb_in = None
+        pred = None
+        logits = None
+        if mode == 0:
+            # teacher forcing: the embedding half of the LSTMCell input projection for all steps at once
+            emb_in = torch.empty(B * R, Ep, device=dev, dtype=BF16)
+            call("las_gather_rows_bf16", ptr(W["emb_w"]), E, ptr(ys_in), B * R, ptr(emb_in), Ep)
+            we_bf = cvt_bf16(we, ld_dst=Ep)
+            embx = gemm(emb_in, Ep, 0, we_bf, Ep, 0, B * R, 4 * Hd, Ep, bias=cell_bias)
+            a.embx = ptr(embx)
+            keep += [embx, we_bf]
+        else:
+            we_pk = pack_afrag(we.contiguous(), 1, Hd)
+            out_pk = pack_afrag(W["out_w"], 0)
+            emb_op = torch.zeros(B * R * Ep + 64, device=dev, dtype=BF16)
+            bos_row = torch.zeros(Ep, **f32)
+            bos_row[:E] = W["emb_w"][bos]
+            emb_op[:B * R * Ep].view(B, R, Ep)[:, 0, :] = bos_row.to(BF16)
+            logits = torch.zeros(B, R, V, **f32)
+            pred = torch.zeros(B, L, device=dev, dtype=torch.int64)
+            a.cell_bias, a.we_pk, a.out_pk, a.out_b = ptr(cell_bias), ptr(we_pk), ptr(out_pk), ptr(W["out_b"])
+            a.emb_w, a.emb_op, a.logits, a.pred = ptr(W["emb_w"]), ptr(emb_op), ptr(logits), ptr(pred)
+            keep += [we_pk, out_pk, emb_op]
+        _lib.check(_lib.lib().las_dec_fwd(ctypes.byref(a), _lib.stream_ptr()))
+        out_bf = cvt_bf16(W["out_w"])                                                 # [V, ZC]
+        if mode == 0:
+            logits = gemm(zc, ZC, 0, out_bf, ZC, 0, B * R, V, ZC, bias=W["out_b"]).view(B, R, V)
+        ctx.geom = (B, Te, H, Hd, O, A, V, E, C, K, L, mode, att_scaling, smooth_scaling)
+        ctx.saved = dict(enc_bf=enc_bf, Pm=Pm, mlp_enc_bf=mlp_enc_bf, wr_cat=wr_cat, ws=ws, zc=zc, cx=cx, dzf=dzf,
+                         gates=gates, csave=csave, conv_w=conv_w, mlp_att=mlp_att, gvec=gvec, emb_in=emb_in,
+                         out_bf=out_bf, ys_in=ys_in, keep=keep)
+        ctx.W = W
+        ctx.mark_non_differentiable(ws)
+        if pred is not None:
+            ctx.mark_non_differentiable(pred)
+            return logits, ws, pred
+        return logits, ws, None
+
+    @staticmethod
+    def backward(ctx, dlogits, _dws, _dpred):
+        B, Te, H, Hd, O, A, V, E, C, K, L, mode, att_scaling, smooth_scaling = ctx.geom
+        if mode != 0:
+            raise _lib.LasError("decoder backward is implemented for the teacher-forced mode only")
+        S, W = ctx.saved, ctx.W
+        dev = dlogits.device
+        R, ZC, Ep = L + 1, Hd + O, _r16(E)
+        f32 = dict(device=dev, dtype=torch.float32)
+        n = B * R
+        a, _ = _dec_common(S["enc_bf"].view(B, Te, H), W, L, K)
+        a.mode, a.att_scaling, a.smooth_scaling = mode, att_scaling, smooth_scaling
+        # output layer (model.py:293): dW = dlogits^T [z;c], d[z;c] = dlogits W
+        dl = dlogits.contiguous().view(n, V)
+        dl_bf = cvt_bf16(dl)                                                          # [n, Vp]
+        Vp = dl_bf.shape[1]
+        zc = S["zc"]
+        d_out_w = gemm(dl_bf, Vp, 1, zc, ZC, 1, V, ZC, n)
+        d_out_b = colsum(dl, V)
+        dzc_all = gemm(dl_bf, Vp, 0, S["out_bf"], ZC, 1, n, ZC, V)                    # f32 [n, ZC]
+        wrT_pk = pack_afrag(S["wr_cat"], 0, transposed=True)
+        mlp_oT_pk = pack_afrag(W["mlp_o_w"], 0, transposed=True)
+        mlp_decT_pk = pack_afrag(W["mlp_dec_w"], 0, transposed=True)
+        dcz_tot = torch.empty(B, ZC, **f32)
+        dcz_all = torch.zeros(n, ZC, device=dev, dtype=BF16)
+        dctx_all = torch.empty(B, L, H, **f32)
+        dw_buf = torch.empty(B, Te, **f32)
+        dattc_all = torch.empty(L, B, Te, C, **f32)
+        ddz_all = torch.zeros(n * A + 64, **f32)
+        dP = torch.zeros(B * Te, A, **f32)
+        att_part = torch.empty(((Te + 31) // 32) * B * 17 * ((A + 31) // 32 * 32), **f32)
+        dc_state = torch.empty(B, Hd, **f32)
+        dgates = torch.zeros(n, 4 * Hd, device=dev, dtype=BF16)
+        d_mlp_att = torch.zeros(A, C, **f32)
+        d_gvec = torch.zeros(A, **f32)
+        d_conv = torch.zeros(C, 2 * K + 1, **f32)
+        denc = torch.empty(B, Te, H, **f32)
+        a.enc_h, a.P = ptr(S["enc_bf"]), ptr(S["Pm"])
+        a.conv_w, a.mlp_att, a.gvec = ptr(S["conv_w"]), ptr(S["mlp_att"]), ptr(S["gvec"])
+        a.ws, a.zc, a.ctx, a.dzf = ptr(S["ws"]), ptr(zc), ptr(S["cx"]), ptr(S["dzf"])
+        a.gates_save, a.c_save = ptr(S["gates"]), ptr(S["csave"])
+        a.wrT_pk, a.mlp_oT_pk, a.mlp_decT_pk = ptr(wrT_pk), ptr(mlp_oT_pk), ptr(mlp_decT_pk)
+        a.dzc_all, a.dcz_tot, a.dcz_all, a.dctx_all, a.dw_buf = (ptr(dzc_all), ptr(dcz_tot), ptr(dcz_all),
+                                                                 ptr(dctx_all), ptr(dw_buf))
+        a.dattc_all, a.ddz_all, a.dP, a.att_part, a.dc_state = (ptr(dattc_all), ptr(ddz_all), ptr(dP),
+                                                                ptr(att_part), ptr(dc_state))
+        a.dgates, a.dmlp_att, a.dgvec, a.dconv_w, a.denc = (ptr(dgates), ptr(d_mlp_att), ptr(d_gvec), ptr(d_conv),
+                                                            ptr(denc))
+        a.denc_accumulate = 0
+        _lib.check(_lib.lib().las_dec_bwd(ctypes.byref(a), _lib.stream_ptr()))
+        # ---- weight gradients deferred out of the time loop, as dense contractions over all (b, t)
+        d_wr = gemm(dgates, 4 * Hd, 1, zc, ZC, 1, 4 * Hd, ZC, n)                      # [4Hd, Hd+O]
+        emb_in = S["emb_in"]
+        d_we = gemm(dgates, 4 * Hd, 1, emb_in, Ep, 1, 4 * Hd, Ep, n)                  # [4Hd, Ep]
+        d_w_ih = torch.cat([d_we[:, :E], d_wr[:, Hd:]], dim=1)
+        d_w_hh = d_wr[:, :Hd].contiguous()
+        d_b = colsum(dgates, 4 * Hd)
+        we_bf = cvt_bf16(W["w_ih"][:, :E], ld_dst=Ep)
+        demb_rows = gemm(dgates, 4 * Hd, 0, we_bf, Ep, 1, n, Ep, 4 * Hd)              # f32 [n, Ep]
+        d_emb = torch.zeros(V, E, **f32)
+        call("las_scatter_add_rows", ptr(demb_rows), Ep, E, ptr(S["ys_in"]), n, 0, ptr(d_emb))
+        dc_att = dcz_all[:, Hd:]                                                      # bf16 view, ld ZC
+        d_mlp_o_w = gemm(dc_att, ZC, 1, S["cx"], H, 1, O, H, n)
+        d_mlp_o_b = colsum(dc_att, O, ld=ZC, rows=n)
+        ddz_bf = cvt_bf16(ddz_all[:n * A].view(n, A))
+        d_mlp_dec = gemm(ddz_bf, ddz_bf.shape[1], 1, zc, ZC, 1, A, Hd, n)
+        dP_bf = cvt_bf16(dP)
+        Ap8 = dP_bf.shape[1]
+        d_mlp_enc_w = gemm(dP_bf, Ap8, 1, S["enc_bf"], H, 1, A, H, B * Te)
+        d_mlp_enc_b = colsum(dP, A)
+        gemm(dP_bf, Ap8, 0, S["mlp_enc_bf"], H, 1, B * Te, H, A, out=denc.view(B * Te, H), accumulate=True)
+        ctx.saved = None
+        grads = dict(emb_w=d_emb, w_ih=d_w_ih, w_hh=d_w_hh, b_ih=d_b, b_hh=d_b, out_w=d_out_w, out_b=d_out_b,
+                     mlp_enc_w=d_mlp_enc_w, mlp_enc_b=d_mlp_enc_b, mlp_dec_w=d_mlp_dec, mlp_att_w=d_mlp_att,
+                     conv_w=d_conv.view_as(W["conv_w"]), gvec_w=d_gvec.view_as(W["gvec_w"]), mlp_o_w=d_mlp_o_w,
+                     mlp_o_b=d_mlp_o_b)
+        return (denc, None, None, None, None, None, None, None, None, *[grads[k] for k in DEC_WEIGHTS])
+
+
+# --------------------------------------------------------------------------------------------
+# log-softmax + gather + unigram label smoothing (model.py:353-366, 523-530)
+# --------------------------------------------------------------------------------------------
+class CELabelSmoothFn(torch.autograd.Function):
+    """logits_alloc f32 [B, R, V]; rows r0..r0+L-1 of every utterance are scored against
+    targets [B, L] (None: each row's own argmax). Returns (logp [B, L], prob [B, L], pred [B, L])."""
+
+    @staticmethod
+    def forward(ctx, logits_alloc, targets, dist, ls, r0, L):
+        B, R, V = logits_alloc.shape
+        dev = logits_alloc.device
+        logp = torch.empty(B, L, device=dev, dtype=torch.float32)
+        prob = torch.empty(B, L, device=dev, dtype=torch.float32)
+        pred = torch.empty(B, L, device=dev, dtype=torch.int64)
+        base = logits_alloc.data_ptr() + r0 * V * 4
+        call("las_ce_ls_fwd", base, V, R * V, L, B * L, V, ptr(targets), ptr(dist), float(ls), ptr(logp), ptr(prob),
+             ptr(pred))
+        ctx.args = (logits_alloc, targets, dist, float(ls), r0, L)
+        ctx.mark_non_differentiable(pred)
+        return logp, prob, pred
+
+    @staticmethod
+    def backward(ctx, g_logp, g_prob, _g_pred):
+        logits_alloc, targets, dist, ls, r0, L = ctx.args
+        B, R, V = logits_alloc.shape
+        dl = torch.zeros_like(logits_alloc)
+        gl = g_logp.contiguous() if g_logp is not None else None
+        gp = g_prob.contiguous() if g_prob is not None else None
+        off = r0 * V * 4
+        call("las_ce_ls_bwd", logits_alloc.data_ptr() + off, V, R * V, L, B * L, V, ptr(targets), ptr(dist), ls,
+             ptr(gl), ptr(gp), dl.data_ptr() + off)
+        return dl, None, None, None, None, None
+
+
+# --------------------------------------------------------------------------------------------
+# LM "judge": embedding -> n-layer unidirectional LSTM -> Linear (model.py:492-532)
+# --------------------------------------------------------------------------------------------
+class LMFn(torch.autograd.Function):
+    """ys_in int64 [B, Lm] (device), lens int32 [B] (device) or None -> logits f32 [B, Lm, V].
+    weights: emb_w, then (w_ih, w_hh, b_ih, b_hh) per layer, then out_w, out_b."""
+
+    @staticmethod
+    def forward(ctx, ys_in, lens, n_layers, pad, *wts):
+        emb_w = wts[0]
+        out_w, out_b = wts[-2], wts[-1]
+        B, Lm = ys_in.shape
+        dev = emb_w.device
+        V, E = emb_w.shape
+        Ep = _r8(E)
+        n = B * Lm
+        xin = torch.empty(n, Ep, device=dev, dtype=BF16)
+        call("las_gather_rows_bf16", ptr(emb_w), E, ptr(ys_in), n, ptr(xin), Ep)
+        Dp = Ep
+        saved = []
+        for l in range(n_layers):
+            w_ih, w_hh, b_ih, b_hh = wts[1 + 4 * l:5 + 4 * l]
+            H = w_hh.shape[1]
+            w_bf = cvt_bf16(w_ih, ld_dst=Dp)
+            xproj = gemm(xin, Dp, 0, w_bf, Dp, 0, n, 4 * H, Dp, bias=(b_ih + b_hh))
+            whh_pk = pack_afrag(w_hh, 1, H)
+            y = torch.zeros(n, H, device=dev, dtype=BF16)
+            hprev = torch.empty(n, H, device=dev, dtype=BF16)
+            gates = torch.empty(1, B, Lm, H, 4, device=dev, dtype=torch.float16)
+            csave = torch.empty(1, B, Lm, H, device=dev, dtype=torch.float32)
+            ws = torch.empty(_lib.lib().las_lstm_ws_bytes(B, H, 1), device=dev, dtype=torch.uint8)
+            call("las_lstm_seq_fwd", ptr(xproj), ptr(whh_pk), ptr(lens), B, Lm, H, 1, ptr(y), Lm * H, H, 0,
+                 ptr(hprev), Lm * H, H, ptr(gates), ptr(csave), ptr(ws))
+            saved.append((xin, w_bf, hprev, gates, csave, Dp, H))
+            xin, Dp = y, H
+        out_bf = cvt_bf16(out_w)
+        logits = gemm(xin, Dp, 0, out_bf, Dp, 0, n, V, Dp, bias=out_b).view(B, Lm, V)
+        ctx.saved = (saved, xin, out_bf, ys_in, lens)
+        ctx.geom = (B, Lm, V, E, Ep, n_layers, pad)
+        ctx.wts = wts
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        saved, ylast, out_bf, ys_in, lens = ctx.saved
+        B, Lm, V, E, Ep, n_layers, pad = ctx.geom
+        wts = ctx.wts
+        dev = dlogits.device
+        n = B * Lm
+        dl = dlogits.contiguous().view(n, V)
+        dl_bf = cvt_bf16(dl)
+        Vp = dl_bf.shape[1]
+        Hl = ylast.shape[1]
+        d_out_w = gemm(dl_bf, Vp, 1, ylast, Hl, 1, V, Hl, n)
+        d_out_b = colsum(dl, V)
+        dy = gemm(dl_bf, Vp, 0, out_bf, Hl, 1, n, Hl, V)
+        grads = [None] * len(wts)
+        grads[-2], grads[-1] = d_out_w, d_out_b
+        for l in reversed(range(n_layers)):
+            xin, w_bf, hprev, gates, csave, Dp, H = saved[l]
+            w_ih, w_hh, b_ih, b_hh = wts[1 + 4 * l:5 + 4 * l]
+            whhT = pack_afrag(w_hh, 0, transposed=True)
+            dG = torch.empty(n, 4 * H, device=dev, dtype=BF16)
+            ws = torch.empty(B * H, device=dev, dtype=torch.float32)
+            call("las_lstm_seq_bwd", ptr(dy), Lm * H, H, 0, ptr(whhT), ptr(lens), B, Lm, H, 1, ptr(gates), ptr(csave),
+                 ptr(dG), Lm * 4 * H, 4 * H, ptr(ws))
+            d_w_ih = gemm(dG, 4 * H, 1, xin, Dp, 1, 4 * H, Dp, n)[:, :w_ih.shape[1]]
+            d_w_hh = gemm(dG, 4 * H, 1, hprev, H, 1, 4 * H, H, n)
+            d_b = colsum(dG, 4 * H)
+            grads[1 + 4 * l:5 + 4 * l] = [d_w_ih, d_w_hh, d_b, d_b]
+            dy = gemm(dG, 4 * H, 0, w_bf, Dp, 1, n, Dp, 4 * H)                       # f32 [n, Dp]
+        d_emb = torch.zeros(V, E, device=dev, dtype=torch.float32)
+        call("las_scatter_add_rows", ptr(dy), Ep, E, ptr(ys_in), n, pad, ptr(d_emb))
+        grads[0] = d_emb
+        ctx.saved = None
+        return (None, None, None, None, *grads)

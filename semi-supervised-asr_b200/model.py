@@ -1,0 +1,272 @@
+"""Drop-in modules for the reference's model.py (jjery2243542/semi-supervised-ASR):
+`pBLSTM`, `Encoder`, `AttLoc`, `Decoder`, `E2E`, `LM` with the same constructor arguments,
+`forward` signatures, return values and `state_dict` key names/shapes (so reference `.ckpt`
+files load unchanged), computing through the sm_100a kernels of liblas_b200.so.
+
+Parameters live in stock `torch.nn` containers (`nn.LSTM`, `nn.LSTMCell`, `nn.Linear`, `nn.Conv2d`,
+`nn.Embedding`) purely so that names, shapes and default initialisation match the reference; their
+`forward` methods are never called. There is no CPU path: inputs are moved to the CUDA device and
+the kernels raise if the extension is missing.
+"""
+import numpy as np
+import torch
+
+from . import functional as Fn
+from .utils import _seq_mask, cc, pad_list, weight_init
+
+
+class pBLSTM(torch.nn.Module):
+    """model.py:58-98."""
+
+    def __init__(self, input_dim, hidden_dim, n_layers, subsample, dropout_rate):
+        super().__init__()
+        layers, project_layers = [], []
+        for i in range(n_layers):
+            idim = input_dim if i == 0 else hidden_dim
+            project_dim = hidden_dim * 4 if subsample[i] > 1 else hidden_dim * 2
+            layers.append(torch.nn.LSTM(idim, hidden_dim, num_layers=1, bidirectional=True, batch_first=True))
+            project_layers.append(torch.nn.Linear(project_dim, hidden_dim))
+        self.layers = torch.nn.ModuleList(layers)
+        self.project_layers = torch.nn.ModuleList(project_layers)
+        self.dropout_layer = torch.nn.Dropout(p=dropout_rate)
+        self.subsample = subsample
+        self.dropout_rate = dropout_rate
+
+    def _weights(self):
+        w = []
+        for layer, proj in zip(self.layers, self.project_layers):
+            w += [layer.weight_ih_l0, layer.weight_hh_l0, layer.bias_ih_l0, layer.bias_hh_l0,
+                  layer.weight_ih_l0_reverse, layer.weight_hh_l0_reverse, layer.bias_ih_l0_reverse,
+                  layer.bias_hh_l0_reverse, proj.weight, proj.bias]
+        return w
+
+    def forward(self, xpad, ilens):
+        xpad = cc(xpad).float()
+        host_lens = [int(l) for l in (ilens.tolist() if torch.is_tensor(ilens) else ilens)]
+        T = max(host_lens)
+        xpad = xpad[:, :T].contiguous()                      # pad_packed_sequence trims to the longest
+        lens_dev = Fn.lens_tensor(host_lens, xpad.device)
+        if self.training and self.dropout_rate > 0:
+            raise NotImplementedError("dropout inside the fused encoder is not wired yet; use dropout_rate=0")
+        out = Fn.EncoderFn.apply(xpad, lens_dev, tuple(int(s) for s in self.subsample), *self._weights())
+        for sub in self.subsample:                            # model.py:92
+            if sub > 1:
+                host_lens = [(l + 1) // sub for l in host_lens]
+        return out, host_lens
+
+
+class Encoder(torch.nn.Module):
+    """model.py:100-112."""
+
+    def __init__(self, input_dim, hidden_dim, n_layers, subsample, dropout_rate, in_channel=1):
+        super().__init__()
+        self.enc2 = pBLSTM(input_dim=input_dim, hidden_dim=hidden_dim, n_layers=n_layers, subsample=subsample,
+                           dropout_rate=dropout_rate)
+
+    def forward(self, x, ilens):
+        return self.enc2(x, ilens)
+
+
+class AttLoc(torch.nn.Module):
+    """model.py:114-173. Parameter container + per-utterance cache semantics; the attention math
+    itself runs inside the fused decoder loop (functional.DecoderFn)."""
+
+    def __init__(self, encoder_dim, decoder_dim, att_dim, conv_channels, conv_kernel_size, att_odim):
+        super().__init__()
+        self.mlp_enc = torch.nn.Linear(encoder_dim, att_dim)
+        self.mlp_dec = torch.nn.Linear(decoder_dim, att_dim, bias=False)
+        self.mlp_att = torch.nn.Linear(conv_channels, att_dim, bias=False)
+        self.loc_conv = torch.nn.Conv2d(1, conv_channels, (1, 2 * conv_kernel_size + 1),
+                                        padding=(0, conv_kernel_size), bias=False)
+        self.gvec = torch.nn.Linear(att_dim, 1, bias=False)
+        self.mlp_o = torch.nn.Linear(encoder_dim, att_odim)
+        self.encoder_dim = encoder_dim
+        self.decoder_dim = decoder_dim
+        self.att_dim = att_dim
+        self.att_odim = att_odim
+        self.conv_channels = conv_channels
+        self.conv_kernel_size = conv_kernel_size
+        self.enc_length = None
+        self.enc_h = None
+        self.pre_compute_enc_h = None
+
+    def reset(self):
+        self.enc_length = None
+        self.enc_h = None
+        self.pre_compute_enc_h = None
+
+    def _weights(self):
+        return [self.mlp_enc.weight, self.mlp_enc.bias, self.mlp_dec.weight, self.mlp_att.weight,
+                self.loc_conv.weight, self.gvec.weight, self.mlp_o.weight, self.mlp_o.bias]
+
+
+class Decoder(torch.nn.Module):
+    """model.py:256-367."""
+
+    def __init__(self, output_dim, embedding_dim, hidden_dim, attention, att_odim, dropout_rate, bos, eos, pad,
+                 ls_weight=0, labeldist=None):
+        super().__init__()
+        self.bos, self.eos, self.pad = bos, eos, pad
+        self.embedding = torch.nn.Embedding(output_dim, embedding_dim, padding_idx=pad)
+        self.LSTMCell = torch.nn.LSTMCell(embedding_dim + att_odim, hidden_dim)
+        self.output_layer = torch.nn.Linear(hidden_dim + att_odim, output_dim)
+        self.dropout_layer = torch.nn.Dropout(p=dropout_rate)
+        self.attention = attention
+        self.hidden_dim = hidden_dim
+        self.att_odim = att_odim
+        self.dropout_rate = dropout_rate
+        self.ls_weight = ls_weight
+        self.labeldist = labeldist
+        self.vlabeldist = None
+        if labeldist is not None:
+            self.vlabeldist = cc(torch.from_numpy(np.array(labeldist, dtype=np.float32)))
+
+    def zero_state(self, enc_pad, dim=None):
+        return enc_pad.new_zeros(enc_pad.size(0), dim if dim else self.hidden_dim)
+
+    def _weights(self):
+        att = self.attention
+        return [self.embedding.weight, self.LSTMCell.weight_ih, self.LSTMCell.weight_hh, self.LSTMCell.bias_ih,
+                self.LSTMCell.bias_hh, self.output_layer.weight, self.output_layer.bias] + att._weights()
+
+    def forward(self, enc_pad, enc_len, ys=None, tf_rate=1.0, max_dec_timesteps=500, sample=False, smooth=False,
+                scaling=1.0, label_smoothing=True):
+        if sample:
+            raise NotImplementedError("Categorical sampling (model.py:350) is not used by any Solver path")
+        if self.training and self.dropout_rate > 0:
+            raise NotImplementedError("dropout inside the fused decoder is not wired yet; use dropout_rate=0")
+        dev = enc_pad.device
+        B = enc_pad.size(0)
+        self.attention.reset()
+        enc_lens_dev = Fn.lens_tensor(enc_len, dev)
+        teacher = ys is not None and len(ys) > 0
+        if teacher:
+            if tf_rate < 1.0:
+                raise NotImplementedError("scheduled sampling (tf_rate < 1) is not implemented; config pins 1.0")
+            ys_host = [y.detach().cpu().numpy().astype(np.int64) if torch.is_tensor(y) else np.asarray(y, np.int64)
+                       for y in ys]
+            L = max(len(y) for y in ys_host) + 1
+            ys_in = np.full((B, L + 1), self.eos, dtype=np.int64)          # model.py:303-306
+            ys_out = np.full((B, L), self.eos, dtype=np.int64)
+            for b, y in enumerate(ys_host):
+                ys_in[b, 0] = self.bos
+                ys_in[b, 1:1 + len(y)] = y
+                ys_out[b, :len(y)] = y
+            ys_in[:, L] = self.pad                                          # guard column (never consumed)
+            ys_in_dev = torch.from_numpy(ys_in).to(dev)
+            ys_out_dev = torch.from_numpy(ys_out).to(dev)
+            mode = 0
+        else:
+            L = int(max_dec_timesteps)
+            ys_in_dev, ys_out_dev = None, None
+            mode = 2 if smooth else 1
+        logits_alloc, ws_alloc, pred = Fn.DecoderFn.apply(
+            enc_pad.float().contiguous(), enc_lens_dev, ys_in_dev, L, mode, float(scaling), 2.0,
+            self.attention.conv_kernel_size, self.bos, *self._weights())
+        ls = self.ls_weight if (label_smoothing and self.ls_weight > 0 and self.training) else 0.0
+        dist = self.vlabeldist.to(dev) if ls > 0 else None
+        ys_log_probs, _, prediction = Fn.CELabelSmoothFn.apply(logits_alloc, ys_out_dev, dist, ls, 1, L)
+        return logits_alloc[:, 1:], ys_log_probs, prediction, ws_alloc[:, 1:]
+
+
+class E2E(torch.nn.Module):
+    """model.py:408-456."""
+
+    def __init__(self, input_dim, enc_hidden_dim, enc_n_layers, subsample, dropout_rate, dec_hidden_dim, att_dim,
+                 conv_channels, conv_kernel_size, att_odim, embedding_dim, output_dim, ls_weight, labeldist, pad=0,
+                 bos=1, eos=2):
+        super().__init__()
+        self.encoder = Encoder(input_dim=input_dim, hidden_dim=enc_hidden_dim, n_layers=enc_n_layers,
+                               subsample=subsample, dropout_rate=dropout_rate)
+        self.attention = AttLoc(encoder_dim=enc_hidden_dim, decoder_dim=dec_hidden_dim, att_dim=att_dim,
+                                conv_channels=conv_channels, conv_kernel_size=conv_kernel_size, att_odim=att_odim)
+        self.decoder = Decoder(output_dim=output_dim, hidden_dim=dec_hidden_dim, embedding_dim=embedding_dim,
+                               attention=self.attention, dropout_rate=dropout_rate, att_odim=att_odim,
+                               ls_weight=ls_weight, labeldist=labeldist, bos=bos, eos=eos, pad=pad)
+
+    def forward(self, data, ilens, ys=None, tf_rate=1.0, max_dec_timesteps=200, sample=False, smooth=False,
+                scaling=1.0, label_smoothing=True):
+        enc_h, enc_lens = self.encoder(data, ilens)
+        return self.decoder(enc_h, enc_lens, ys, tf_rate=tf_rate, max_dec_timesteps=max_dec_timesteps,
+                            sample=sample, smooth=smooth, scaling=scaling, label_smoothing=label_smoothing)
+
+    def mask_and_cal_loss(self, log_probs, ys, mask=None):
+        if mask is None:
+            seq_len = [y.size(0) + 1 for y in ys]
+            mask = _seq_mask(seq_len=seq_len, max_len=log_probs.size(1)).to(log_probs.device)
+        else:
+            seq_len = [y.size(0) for y in ys]
+        return -torch.sum(log_probs * mask) / sum(seq_len)
+
+
+class LM(torch.nn.Module):
+    """The "judge" language model, model.py:459-573."""
+
+    def __init__(self, output_dim, embedding_dim, hidden_dim, dropout_rate, n_layers, bos, eos, pad, ls_weight,
+                 labeldist):
+        super().__init__()
+        self.bos, self.eos, self.pad = bos, eos, pad
+        self.embedding = torch.nn.Embedding(output_dim, embedding_dim, padding_idx=pad)
+        self.LSTM = torch.nn.LSTM(embedding_dim, hidden_dim, num_layers=n_layers, batch_first=True,
+                                  dropout=dropout_rate if n_layers > 1 else 0)
+        weight_init(self.LSTM)
+        self.output_layer = torch.nn.Linear(hidden_dim, output_dim)
+        self.dropout_layer = torch.nn.Dropout(p=dropout_rate)
+        self.hidden_dim = hidden_dim
+        self.output_dim = output_dim
+        self.dropout_rate = dropout_rate
+        self.n_layers = n_layers
+        self.ls_weight = ls_weight
+        self.labeldist = labeldist
+        self.vlabeldist = None
+        if labeldist is not None:
+            self.vlabeldist = cc(torch.from_numpy(np.array(labeldist, dtype=np.float32)))
+
+    def zero_state(self, ref, dim=None):
+        return ref.new_zeros(self.n_layers, ref.size(0), dim if dim else self.hidden_dim)
+
+    def _weights(self):
+        w = [self.embedding.weight]
+        for l in range(self.n_layers):
+            w += [getattr(self.LSTM, f"weight_ih_l{l}"), getattr(self.LSTM, f"weight_hh_l{l}"),
+                  getattr(self.LSTM, f"bias_ih_l{l}"), getattr(self.LSTM, f"bias_hh_l{l}")]
+        return w + [self.output_layer.weight, self.output_layer.bias]
+
+    def forward(self, ys=None, discrete_input=True):
+        if self.training and self.dropout_rate > 0:
+            raise NotImplementedError("dropout inside the fused LM is not wired yet; use dropout_rate=0")
+        dev = self.embedding.weight.device
+        if discrete_input:
+            ys_host = [y.detach().cpu().numpy().astype(np.int64) if torch.is_tensor(y) else np.asarray(y, np.int64)
+                       for y in ys]
+            B = len(ys_host)
+            Lm = max(len(y) for y in ys_host) + 5                          # model.py:496-499
+            ys_in = np.full((B, Lm), self.eos, dtype=np.int64)
+            ys_out = np.full((B, Lm), self.eos, dtype=np.int64)
+            for b, y in enumerate(ys_host):
+                ys_in[b, 0] = self.bos
+                ys_in[b, 1:1 + len(y)] = y
+                ys_out[b, :len(y)] = y
+            lens = Fn.lens_tensor([len(y) + 5 for y in ys_host], dev)
+            ys_in_dev = torch.from_numpy(ys_in).to(dev)
+            ys_out_dev = torch.from_numpy(ys_out).to(dev)
+        else:
+            ys = ys.to(dev)
+            bos_seq = ys.new_zeros(ys.size(0), 1) + self.bos                # model.py:503-505
+            ys_in_dev = torch.cat([bos_seq, ys[:, :-1]], dim=1).contiguous()
+            ys_out_dev = ys.contiguous()
+            lens = None
+            Lm = ys.size(1)
+        logits = Fn.LMFn.apply(ys_in_dev, lens, self.n_layers, self.pad, *self._weights())
+        ls = self.ls_weight if (self.ls_weight > 0 and self.training) else 0.0
+        dist = self.vlabeldist.to(dev) if ls > 0 else None
+        ys_log_probs, ys_probs, predictions = Fn.CELabelSmoothFn.apply(logits, ys_out_dev, dist, ls, 0, Lm)
+        return ys_log_probs, ys_probs, predictions
+
+    def mask_and_cal_sum(self, log_probs, ys, mask=None):
+        if mask is None:
+            seq_len = [y.size(0) + 1 + 4 for y in ys]
+            mask = _seq_mask(seq_len=seq_len, max_len=log_probs.size(1)).to(log_probs.device)
+        else:
+            seq_len = [y.size(0) for y in ys]
+        return torch.sum(log_probs * mask) / sum(seq_len)

@@ -1,0 +1,75 @@
+"""Host-side helpers with the reference's names and semantics (utils.py of
+jjery2243542/semi-supervised-ASR): device placement, padding, masks, LSTM re-initialisation,
+learning-rate edits. Only what the hot path and its Solver entry points touch."""
+import numpy as np
+import torch
+from torch.nn import init
+
+
+def cc(net):
+    """utils.py:150-152."""
+    device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+    return net.to(device)
+
+
+def to_gpu(data):
+    """utils.py:154-158."""
+    xs, ilens, ys = data
+    return cc(xs), ilens, [cc(y) for y in ys]
+
+
+def pad_list(xs, pad_value=0):
+    """utils.py:173-179: right-pad a list of tensors to the longest."""
+    batch_size = len(xs)
+    max_length = max(x.size(0) for x in xs)
+    pad = xs[0].data.new(batch_size, max_length, *xs[0].size()[1:]).fill_(pad_value)
+    for i in range(batch_size):
+        pad[i, :xs[i].size(0)] = xs[i]
+    return pad
+
+
+def _seq_mask(seq_len, max_len, is_list=True):
+    """utils.py:181-190: mask[b, t] = 1.0 where t < seq_len[b]."""
+    if is_list:
+        seq_len = torch.from_numpy(np.array(seq_len))
+    seq_range = torch.arange(0, max_len).long().to(seq_len.device)
+    return (seq_range.unsqueeze(0) < seq_len.unsqueeze(1)).float()
+
+
+def weight_init(m):
+    """utils.py:97-103 as used by LM.__init__ (model.py:470): orthogonal matrices, normal biases."""
+    if isinstance(m, (torch.nn.LSTM, torch.nn.LSTMCell, torch.nn.GRU, torch.nn.GRUCell)):
+        for param in m.parameters():
+            if len(param.shape) >= 2:
+                init.orthogonal_(param.data)
+            else:
+                init.normal_(param.data)
+
+
+def adjust_learning_rate(optimizer, lr):
+    """utils.py:134-139."""
+    for param_group in optimizer.param_groups:
+        param_group["lr"] = lr
+    return lr
+
+
+def remove_pad_eos(sequences, eos=2):
+    """utils.py:192-201: cut every sequence at its first EOS."""
+    out = []
+    for sequence in sequences:
+        try:
+            eos_index = next(i for i, v in enumerate(sequence) if v == eos)
+        except StopIteration:
+            eos_index = len(sequence)
+        out.append(sequence[:eos_index])
+    return out
+
+
+def infinite_iter(iterable):
+    """utils.py:247-254."""
+    it = iter(iterable)
+    while True:
+        try:
+            yield next(it)
+        except StopIteration:
+            it = iter(iterable)

@@ -1,0 +1,154 @@
+"""GPU parity of the supervised LAS path (encoder, decoder, loss, gradients) against
+(a) golden fixtures produced by the reference itself, (b) the CPU oracle on seeded random cases.
+
+Tolerances (BASELINE.json north_star): masks / lengths / padding bit-exact; loss within 1e-3
+relative; parameter-gradient cosine >= 0.999 vs fp32. Activations are compared with a bf16-operand
+tolerance (3e-2 of the tensor's max magnitude)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import las_oracle as O
+from tests.util import cosine, e2e_from_golden, load_golden, pkg, rel_err
+
+pytestmark = pytest.mark.gpu
+SUP_CASES = ["sup_small_odd", "sup_sub1", "sup_b1_widekernel"]
+ACT_TOL = 3e-2
+
+
+def _run(m, g, G, train=True):
+    m.train(train)
+    x = torch.from_numpy(g["x"]).cuda()
+    ys = [torch.from_numpy(y).cuda() for y in G["ys"]]
+    return m(x, g["ilens"].tolist(), ys, tf_rate=1.0, sample=False)
+
+
+@pytest.mark.parametrize("name", SUP_CASES)
+def test_encoder_matches_reference(name):
+    G = load_golden(name)
+    g = G["raw"]
+    m = e2e_from_golden(G)
+    enc_h, enc_lens = m.encoder(torch.from_numpy(g["x"]).cuda(), g["ilens"].tolist())
+    assert enc_lens == g["enc_lens"].tolist()                       # integer: bit exact
+    assert tuple(enc_h.shape) == g["enc_h"].shape
+    assert rel_err(enc_h, g["enc_h"]) < ACT_TOL
+    # rows past the length are relu(bias) of the last projection (bit-exact in bf16)
+    n = len(g["subsample"])
+    rb = torch.relu(G["p0"][f"encoder.enc2.project_layers.{n - 1}.bias"]).to(torch.bfloat16).float()
+    for b, l in enumerate(enc_lens):
+        if l < enc_h.shape[1]:
+            assert torch.equal(enc_h[b, l:].cpu(), rb.expand(enc_h.shape[1] - l, -1))
+
+
+@pytest.mark.parametrize("name", SUP_CASES)
+def test_teacher_forced_forward_and_loss(name):
+    G = load_golden(name)
+    g = G["raw"]
+    m = e2e_from_golden(G)
+    logits, logp, pred, ws = _run(m, g, G)
+    assert tuple(logits.shape) == g["logits"].shape and tuple(ws.shape) == g["ws"].shape
+    assert rel_err(logits, g["logits"]) < ACT_TOL
+    assert rel_err(ws, g["ws"]) < ACT_TOL
+    assert rel_err(logp, g["log_probs"]) < ACT_TOL
+    loss = float(-logp.mean())
+    assert abs(loss - float(g["loss"])) < 1e-3 * abs(float(g["loss"]))
+    val = float(m.mask_and_cal_loss(logp, [torch.from_numpy(y) for y in G["ys"]]))
+    assert abs(val - float(g["val_loss"])) < 1e-3 * abs(float(g["val_loss"]))
+    # attention rows are normalised over ALL Te padded frames
+    s = ws.sum(-1)
+    assert torch.allclose(s, torch.ones_like(s), atol=1e-4)
+    # argmax must match wherever the reference's top-2 margin exceeds the activation tolerance
+    ref_l = torch.from_numpy(g["logits"])
+    top2 = ref_l.topk(2, dim=-1).values
+    safe = (top2[..., 0] - top2[..., 1]) > 2 * ACT_TOL * ref_l.abs().max()
+    assert torch.equal(pred.cpu()[safe], torch.from_numpy(g["prediction"])[safe])
+
+
+@pytest.mark.parametrize("name", SUP_CASES)
+def test_supervised_gradients(name):
+    G = load_golden(name)
+    g = G["raw"]
+    m = e2e_from_golden(G)
+    _, logp, _, _ = _run(m, g, G)
+    loss = -torch.mean(logp)
+    m.zero_grad()
+    loss.backward()
+    grads = {k: p.grad for k, p in m.named_parameters()}
+    assert set(grads) == set(G["g"])                                # same unique parameter names
+    bad = []
+    flat_a, flat_b = [], []
+    for k, gv in G["g"].items():
+        assert grads[k] is not None, k
+        c = cosine(grads[k], gv)
+        flat_a.append(grads[k].detach().cpu().flatten())
+        flat_b.append(gv.flatten())
+        if c < 0.999:
+            bad.append((k, c))
+    whole = cosine(torch.cat(flat_a), torch.cat(flat_b))
+    assert whole >= 0.999, whole
+    assert not bad, bad
+    norm = float(torch.cat(flat_a).double().norm())
+    assert abs(norm - float(g["grad_norm"])) < 1e-2 * float(g["grad_norm"])
+
+
+@pytest.mark.parametrize("name", SUP_CASES)
+def test_greedy_decode(name):
+    G = load_golden(name)
+    g = G["raw"]
+    m = e2e_from_golden(G)
+    m.eval()
+    with torch.no_grad():
+        logits, logp, pred, _ = m(torch.from_numpy(g["x"]).cuda(), g["ilens"].tolist(), ys=None, max_dec_timesteps=12)
+    assert tuple(pred.shape) == g["greedy_pred"].shape
+    ref_l = torch.from_numpy(g["greedy_logits"])
+    ref_p = torch.from_numpy(g["greedy_pred"])
+    # free-running: compare up to the first step whose reference top-2 margin is within tolerance
+    top2 = ref_l.topk(2, dim=-1).values
+    margin_ok = (top2[..., 0] - top2[..., 1]) > 2 * ACT_TOL * ref_l.abs().max()
+    for b in range(pred.shape[0]):
+        n = 0
+        while n < pred.shape[1] and bool(margin_ok[b, n]):
+            n += 1
+        assert torch.equal(pred[b, :n].cpu(), ref_p[b, :n]), (b, n)
+        if n > 0:
+            assert rel_err(logits[b, :n], ref_l[b, :n]) < ACT_TOL
+
+
+def _random_case(seed, B, T, D, H, sub, V, E, A, C, K, ls):
+    M = pkg("model")
+    torch.manual_seed(seed)
+    rng = np.random.RandomState(seed)
+    lens = sorted([T] + [int(rng.randint(int(0.4 * T), T + 1)) for _ in range(B - 1)], reverse=True)
+    x = np.zeros((B, T, D), dtype=np.float32)
+    ys = []
+    for b, l in enumerate(lens):
+        x[b, :l] = rng.randn(l, D).astype(np.float32)
+        ys.append(rng.randint(3, V, size=max(2, int(round(0.125 * l)))).astype(np.int64))
+    labeldist = O.label_distribution(ys, V)
+    m = M.E2E(input_dim=D, enc_hidden_dim=H, enc_n_layers=len(sub), subsample=sub, dropout_rate=0.0,
+              dec_hidden_dim=H, att_dim=A, conv_channels=C, conv_kernel_size=K, att_odim=H, embedding_dim=E,
+              output_dim=V, ls_weight=ls, labeldist=labeldist)
+    P = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    return m.cuda(), P, x, lens, ys, labeldist
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(seed=3, B=5, T=61, D=40, H=64, sub=[2, 2, 2], V=20, E=32, A=48, C=5, K=7, ls=0.05),
+    dict(seed=4, B=9, T=48, D=249, H=32, sub=[1, 2, 2], V=34, E=16, A=32, C=10, K=20, ls=0.0),
+])
+def test_random_case_against_oracle(cfg):
+    m, P, x, lens, ys, labeldist = _random_case(**cfg)
+    loss_o, grads_o, norm_o, _ = O.supervised_step(torch.from_numpy(x), lens, ys, P, {}, cfg["sub"], cfg["ls"],
+                                                   labeldist, fast=True)
+    m.train()
+    _, logp, _, _ = m(torch.from_numpy(x).cuda(), lens, [torch.from_numpy(y).cuda() for y in ys])
+    loss = -torch.mean(logp)
+    m.zero_grad()
+    loss.backward()
+    assert abs(float(loss) - loss_o) < 1e-3 * abs(loss_o)
+    a, b = [], []
+    for k, p in m.named_parameters():
+        a.append(p.grad.detach().cpu().flatten())
+        b.append(grads_o[k].flatten())
+        assert cosine(p.grad, grads_o[k]) >= 0.999, (k, cosine(p.grad, grads_o[k]))
+    assert cosine(torch.cat(a), torch.cat(b)) >= 0.999

@@ -1,10 +1,17 @@
-"""Shared helpers for the test-suite (golden loading, comparison metrics)."""
+"""Shared helpers for the test-suite (golden loading, comparison metrics, package import)."""
+import importlib
 import os
 
 import numpy as np
 import torch
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+PKG_NAME = "semi-supervised-asr_b200"
+
+
+def pkg(sub=None):
+    """The product package (its directory name has a hyphen, so no plain `import`)."""
+    return importlib.import_module(PKG_NAME + ("." + sub if sub else ""))
 
 
 def load_golden(name):
@@ -21,8 +28,8 @@ def load_golden(name):
 
 
 def cosine(a, b):
-    a = torch.as_tensor(a).double().flatten()
-    b = torch.as_tensor(b).double().flatten()
+    a = torch.as_tensor(a).detach().cpu().double().flatten()
+    b = torch.as_tensor(b).detach().cpu().double().flatten()
     na, nb = a.norm(), b.norm()
     if na == 0 and nb == 0:
         return 1.0
@@ -30,6 +37,25 @@ def cosine(a, b):
 
 
 def rel_err(a, b):
-    a = torch.as_tensor(a).double()
-    b = torch.as_tensor(b).double()
+    a = torch.as_tensor(a).detach().cpu().double()
+    b = torch.as_tensor(b).detach().cpu().double()
     return float((a - b).abs().max() / (b.abs().max() + 1e-12))
+
+
+def e2e_from_golden(G, dropout_rate=0.0):
+    """Build the product E2E with the golden case's hyper-parameters and load its p0 state_dict."""
+    M = pkg("model")
+    g, p0 = G["raw"], G["p0"]
+    sub = g["subsample"].tolist()
+    H = p0["encoder.enc2.layers.0.weight_hh_l0"].shape[1]
+    D = p0["encoder.enc2.layers.0.weight_ih_l0"].shape[1]
+    V, E = p0["decoder.embedding.weight"].shape
+    A = p0["attention.mlp_enc.weight"].shape[0]
+    C, _, _, ksz = p0["attention.loc_conv.weight"].shape
+    Hd = p0["decoder.LSTMCell.weight_hh"].shape[1]
+    O = p0["attention.mlp_o.weight"].shape[0]
+    m = M.E2E(input_dim=D, enc_hidden_dim=H, enc_n_layers=len(sub), subsample=sub, dropout_rate=dropout_rate,
+              dec_hidden_dim=Hd, att_dim=A, conv_channels=C, conv_kernel_size=(ksz - 1) // 2, att_odim=O,
+              embedding_dim=E, output_dim=V, ls_weight=float(g["ls_weight"]), labeldist=g["labeldist"])
+    missing = m.load_state_dict(p0, strict=True)
+    return m.cuda()
