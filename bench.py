@@ -1,0 +1,359 @@
+"""bench.py — train utterances/sec of the LAS supervised train step (BASELINE.json config 2:
+si284-shaped, batch 32 per GPU, T~1000 frames, bf16 MMA operands / f32 state) on N B200s.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          our CUDA path (one rank per GPU)
+  python bench.py --impl reference ...                         the reference's CPU path (oracle port)
+
+A "step" = forward + loss + backward + clip + AMSGrad on one synthetic WSJ-shaped batch
+(SURVEY.md §8(d)). `value`: inputs already resident in HBM (graph replay only); `e2e`: the same
+step through SupervisedTrainer.step() with pinned-host inputs, H2D copies and a loss read-back
+inside the timed region. Prints ONE JSON line on rank 0.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+PKG = "semi-supervised-asr_b200"
+
+CFG = dict(input_dim=249, enc_hidden_dim=320, enc_n_layers=3, subsample=[2, 2, 2], dec_hidden_dim=320, att_dim=320,
+           conv_channels=10, conv_kernel_size=100, att_odim=320, embedding_dim=128, ls_weight=0.05, V=34,
+           lr=5e-4, weight_decay=1e-6, max_grad_norm=5.0)
+# algorithmic work per utterance-step, SURVEY.md §8(d) / BASELINE.md §4 (config 2)
+FLOP_PER_UTT = 19.81e9
+HBM_BYTES_PER_UTT = 51e6
+
+
+def synth_batch(rng, B, Tmax, D, V):
+    """T_b ~ U[0.4 Tmax, Tmax], T_0 = Tmax, sorted descending; x ~ N(0,1), zeros
+    past T_b; L_b = clip(round(0.125 T_b), 2, 250), tokens ~ U[3, V)."""
+    lens = sorted([Tmax] + [int(rng.randint(int(0.4 * Tmax), Tmax + 1)) for _ in range(B - 1)], reverse=True)
+    x = np.zeros((B, Tmax, D), dtype=np.float32)
+    ys = []
+    for b, l in enumerate(lens):
+        x[b, :l] = rng.standard_normal((l, D)).astype(np.float32)
+        L = int(np.clip(round(0.125 * l), 2, 250))
+        ys.append(rng.randint(3, V, size=L).astype(np.int64))
+    return x, lens, ys
+
+
+def labeldist_of(ys, V):
+    cnt = np.zeros(V)
+    for y in ys:
+        for t in y:
+            cnt[t] += 1
+    cnt[2] += len(ys)
+    cnt[0] = cnt[1] = 0
+    return cnt / cnt.sum()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for n, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference_run(steps, warmup, threads, B=8, Tmax=1000):
+    """The reference's CPU path for the same step (oracle port: same torch CPU ops as model.py /
+    solver.py:375-385, incl. torch's packed CPU LSTM), on a bounded sample: batches of B=8."""
+    from oracle import las_oracle as O
+    torch.set_num_threads(threads)
+    rng = np.random.RandomState(1234)
+    M = importlib.import_module(PKG + ".model")
+    x, lens, ys = synth_batch(rng, B, Tmax, CFG["input_dim"], CFG["V"])
+    ld = labeldist_of(ys, CFG["V"])
+    torch.manual_seed(1234)
+    m = M.E2E(input_dim=CFG["input_dim"], enc_hidden_dim=CFG["enc_hidden_dim"], enc_n_layers=CFG["enc_n_layers"],
+              subsample=CFG["subsample"], dropout_rate=0.0, dec_hidden_dim=CFG["dec_hidden_dim"],
+              att_dim=CFG["att_dim"], conv_channels=CFG["conv_channels"], conv_kernel_size=CFG["conv_kernel_size"],
+              att_odim=CFG["att_odim"], embedding_dim=CFG["embedding_dim"], output_dim=CFG["V"],
+              ls_weight=CFG["ls_weight"], labeldist=ld)
+    P = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    state = {}
+    xt = torch.from_numpy(x)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        _, _, _, new = O.supervised_step(xt, lens, ys, P, state, CFG["subsample"], CFG["ls_weight"], ld,
+                                         lr=CFG["lr"], weight_decay=CFG["weight_decay"],
+                                         max_grad_norm=CFG["max_grad_norm"], fast=True)
+        for k in new:
+            P[k] = new[k]
+            if k.startswith("attention."):
+                P["decoder." + k] = new[k]
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return B * len(times) / sum(times), float(np.mean(times)), f"B={B} utterances, Tmax={Tmax}, {len(times)} step(s)"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--tmax", type=int, default=1000)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-step", action="store_true", help="run ONE eager step between cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cores = os.cpu_count() or 1
+    workload = f"supervised LAS train step, si284-shaped synthetic, B={args.batch}/GPU, Tmax={args.tmax}, 3xpBLSTM-320 [2,2,2], V=34"
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps = max(1, min(args.steps, 3))
+        v, sec, sample = cpu_reference_run(steps, min(args.warmup, 1), cores)
+        print(json.dumps({
+            "impl": "reference", "metric": "train utterances/sec", "value": v, "unit": "utt/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload, "sample": sample},
+            "cpu_baseline": {"value": v, "unit": "utt/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device: the product path has no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    M = importlib.import_module(PKG + ".model")
+    E = importlib.import_module(PKG + ".engine")
+    OPT = importlib.import_module(PKG + ".optim")
+    LIB = importlib.import_module(PKG + "._lib")
+
+    rng = np.random.RandomState(1234 + rank)
+    nb = 4                                             # distinct synthetic batches, cycled
+    batches = [synth_batch(rng, args.batch, args.tmax, CFG["input_dim"], CFG["V"]) for _ in range(nb)]
+    # one geometry for all batches (graph replay): pad label lists to a common Lmax via the longest utterance
+    ld = labeldist_of([y for b in batches for y in b[2]], CFG["V"])
+    torch.manual_seed(1234)
+    m = M.E2E(input_dim=CFG["input_dim"], enc_hidden_dim=CFG["enc_hidden_dim"], enc_n_layers=CFG["enc_n_layers"],
+              subsample=CFG["subsample"], dropout_rate=0.0, dec_hidden_dim=CFG["dec_hidden_dim"],
+              att_dim=CFG["att_dim"], conv_channels=CFG["conv_channels"], conv_kernel_size=CFG["conv_kernel_size"],
+              att_odim=CFG["att_odim"], embedding_dim=CFG["embedding_dim"], output_dim=CFG["V"],
+              ls_weight=CFG["ls_weight"], labeldist=ld).to(dev)
+    if world > 1:                                      # identical initial weights on every rank
+        for p in m.parameters():
+            torch.distributed.broadcast(p.data, 0)
+    opt = OPT.FusedAdam(m.parameters(), lr=CFG["lr"], weight_decay=CFG["weight_decay"], amsgrad=True)
+    tr = E.SupervisedTrainer(m, opt, max_grad_norm=CFG["max_grad_norm"], use_graph=not args.no_graph)
+    pinned = [(torch.from_numpy(x).pin_memory(), lens, [torch.from_numpy(y) for y in ys]) for x, lens, ys in batches]
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (first step of a geometry is eager, second captures the graph)
+    W = max(args.warmup, 3)
+    losses = []
+    for i in range(W):
+        loss, _ = tr.step(*pinned[i % nb])
+        losses.append(float(loss))
+    if args.profile_step:
+        tr.use_graph = False
+        key = tr.stage(*pinned[0])
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        tr.run(key)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        print(json.dumps({"profile_step": "done", "loss": losses}))
+        return
+    c0 = LIB.lib().las_launch_count()
+    key = tr.stage(*pinned[0])
+    if args.no_graph:
+        tr.run(key)
+        launches = int(LIB.lib().las_launch_count() - c0)
+    else:
+        launches = None
+
+    # ---- device-resident timing: inputs staged once per distinct batch, then replay only
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    keys = [tr.stage(*p) for p in pinned]              # all batches share one geometry only if shapes agree
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(args.steps):
+        tr.run(keys[i % nb])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    # ---- end-to-end timing: pinned host inputs, H2D + step + loss read-back every step
+    barrier()
+    t0 = time.perf_counter()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for i in range(args.steps):
+        loss, _ = tr.step(*pinned[i % nb])
+        losses.append(loss.item())
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3)
+    clocks = sampler.stop()
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    x0, _, ys0 = pinned[0]
+    Lmax = max(len(y) for y in ys0) + 1
+    h2d = x0.numel() * 4 + args.batch * 4 + args.batch * (2 * Lmax + 1) * 8
+    utt = args.batch * world * args.steps
+    value = utt / (ms * 1e-3)
+    e2e = utt / (ms_e2e * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+    # launches per step (ours): measured with graphs off on one extra eager step
+    if launches is None:
+        tr2_graph = tr.use_graph
+        tr.use_graph = False
+        c0 = LIB.lib().las_launch_count()
+        tr.run(keys[0])
+        torch.cuda.synchronize()
+        launches = int(LIB.lib().las_launch_count() - c0)
+        tr.use_graph = tr2_graph
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    roof = kernel_roofline(dev, hbm_peak, "measured" if peaks else "fallback")
+    out = {
+        "metric": "train utterances/sec", "value": value, "unit": "utt/s", "n_gpus": world, "steps": args.steps,
+        "warmup": W, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": workload, "global_batch": args.batch * world, "parallelism": f"dp{world}",
+                   "precision": "bf16 MMA operands, f32 accumulate/state/master weights", "dropout": 0.0,
+                   "cuda_graph": not args.no_graph,
+                   "l2": "working set per step (>1 GB of saved activations) exceeds the 126 MB L2; no flush"},
+        "e2e": {"value": e2e, "unit": "utt/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": 4},
+        "gpu_launches": launches * args.steps,
+        "gpu_launches_per_step": launches,
+        "clocks": clocks,
+        "step_roofline": {"algorithmic_tflops": FLOP_PER_UTT * args.batch / (ms / args.steps * 1e-3) / 1e12,
+                          "frac_of_bf16_sustained": FLOP_PER_UTT * args.batch / (ms / args.steps * 1e-3) / 1e12 / tf_peak,
+                          "algorithmic_hbm_gbs": HBM_BYTES_PER_UTT * args.batch / (ms / args.steps * 1e-3) / 1e9},
+        "roofline": roof,
+        "loss_first_last": [losses[0], losses[-1]],
+    }
+    if not args.no_cpu_baseline:
+        v, sec, sample = cpu_reference_run(2, 1, cores)
+        out["cpu_baseline"] = {"value": v, "unit": "utt/s", "cores": cores, "kind": "port", "sample": sample,
+                               "s_per_step": sec}
+    print(json.dumps(out))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def kernel_roofline(dev, hbm_peak, which):
+    """Dominant kernel = the cluster-persistent BLSTM recurrence of encoder layer 0 (longest serial
+    chain of the step). Timed live with CUDA events around las_lstm_seq_fwd on the current stream."""
+    Fn = importlib.import_module(PKG + ".functional")
+    LIB = importlib.import_module(PKG + "._lib")
+    B, T, H = 32, 1000, CFG["enc_hidden_dim"]
+    torch.manual_seed(0)
+    xproj = torch.randn(B * T, 8 * H, device=dev) * 0.1
+    w = [torch.randn(4 * H, H, device=dev) * 0.05 for _ in range(2)]
+    whh = torch.cat([Fn.pack_afrag(w[0], 1, H), Fn.pack_afrag(w[1], 1, H)])
+    lens = torch.full((B,), T, device=dev, dtype=torch.int32)
+    y = torch.zeros(B, T, 2 * H, device=dev, dtype=torch.bfloat16)
+    hprev = torch.empty_like(y)
+    gates = torch.empty(2, B, T, H, 4, device=dev, dtype=torch.float16)
+    cs = torch.empty(2, B, T, H, device=dev, dtype=torch.float32)
+    ws = torch.empty(LIB.lib().las_lstm_ws_bytes(B, H, 2), device=dev, dtype=torch.uint8)
+
+    def run():
+        Fn.call("las_lstm_seq_fwd", Fn.ptr(xproj), Fn.ptr(whh), Fn.ptr(lens), B, T, H, 2, Fn.ptr(y), T * 2 * H, 2 * H, 0,
+                Fn.ptr(hprev), T * 2 * H, 2 * H, Fn.ptr(gates), Fn.ptr(cs), Fn.ptr(ws))
+    g = torch.cuda.CUDAGraph()
+    run()
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g):
+        run()
+    for _ in range(2):
+        g.replay()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(3):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / 3            # one launch = the whole T-step sequence, both directions
+    # algorithmic HBM bytes of one launch (DESIGN.md "kernels"): W_hh fragments once (2*4H*H*2 B), per (b, t):
+    # xproj row 8H*4 B read; y 2H*2 B, hprev 2H*2 B, gates (4 x f16) 2H*8 B and c (f32) 2H*4 B written.
+    bytes_per_launch = 2 * 4 * H * H * 2 + B * T * (8 * H * 4 + 2 * H * 2 + 2 * H * 2 + 2 * H * 8 + 2 * H * 4)
+    ach = bytes_per_launch / (us * 1e-6) / 1e9
+    return {"kernel": "lstm_persist_fwd_kernel (BLSTM layer 0: T=1000 timesteps, both directions, one launch)",
+            "bound": "hbm", "achieved": ach, "peak": hbm_peak, "peak_source": which, "unit": "GB/s",
+            "frac": ach / hbm_peak, "traffic": None, "us_per_launch": us, "us_per_timestep": us / T,
+            "algorithmic_bytes_per_launch": bytes_per_launch,
+            "note": "latency-bound serial recurrence: the binding resource is the per-timestep DSMEM exchange, not HBM"}
+
+
+if __name__ == "__main__":
+    main()

@@ -31,6 +31,8 @@ extern "C" {
 const char* las_last_error(void);
 int las_version(void);
 int las_num_sms(void);
+/* kernels launched by this library since load (host counter; bench.py reports the per-step delta) */
+unsigned long long las_launch_count(void);
 
 /* Dense contraction D[m,n] = sum_k A[m,k]*B[n,k] (+bias[n]) (relu) (+=C) on tcgen05 tensor
  * cores, bf16 operands, f32 accumulation, operands fetched by TMA.
@@ -109,9 +111,18 @@ int las_lstm_seq_fwd(const float* xproj, const void* whh_pk, const int32_t* lens
                      int64_t hp_ld_b, int64_t hp_ld_t, void* gates_save, float* c_save, void* ws,
                      void* stream);
 int las_lstm_seq_bwd(const float* dy, int64_t dy_ld_b, int64_t dy_ld_t, int rep_row,
-                     const void* whhT_pk, const int32_t* lens, int B, int T, int H, int ndir,
-                     const void* gates_save, const float* c_save, void* dG, int64_t dg_ld_b,
+                     const void* whhT_pk, int whhT_layout, const int32_t* lens, int B, int T, int H,
+                     int ndir, const void* gates_save, const float* c_save, void* dG, int64_t dg_ld_b,
                      int64_t dg_ld_t, void* ws, void* stream);
+/* Cluster-persistent recurrence (one launch per layer and pass): returns 1 and the cluster size /
+ * units per CTA when hidden size H is served by it (las_lstm_seq_fwd then uses it automatically;
+ * las_lstm_seq_bwd uses it when whhT_layout == 1, i.e. W_hh^T packed by las_pack_whhT_owner). */
+int las_lstm_persistent_geometry(int H, int* cs, int* upc);
+/* switch between the cluster-persistent and the per-timestep kernels (returns the previous setting;
+ * default on, or off with LAS_DISABLE_PERSISTENT=1 in the environment) */
+int las_set_persistent(int on);
+int64_t las_whhT_owner_bytes(int H);
+int las_pack_whhT_owner(const float* W_hh, int H, void* out, void* stream);
 /* lens_out[b] = (lens_in[b] + 1) / sub   (model.py:92) */
 int las_pyramid_lens(const int32_t* lens_in, int B, int sub, int32_t* lens_out, void* stream);
 

@@ -38,6 +38,7 @@ SIGNATURES = {
     "las_last_error": (c_char_p, []),
     "las_version": (c_int, []),
     "las_num_sms": (c_int, []),
+    "las_launch_count": (ctypes.c_ulonglong, []),
     "las_gemm_bf16": (c_int, [P, L, I, P, L, I, P, L, I, P, I, I, I, I, I, P]),
     "las_cvt_pad_bf16": (c_int, [P, L, L, I, P, L, P]),
     "las_add2": (c_int, [P, P, P, L, P]),
@@ -54,7 +55,11 @@ SIGNATURES = {
     "las_smallmm": (c_int, [P, I, I, P, I, L, I, P, P, L, P, L, P, L, P]),
     "las_lstm_ws_bytes": (c_int64, [I, I, I]),
     "las_lstm_seq_fwd": (c_int, [P, P, P, I, I, I, I, P, L, L, I, P, L, L, P, P, P, P]),
-    "las_lstm_seq_bwd": (c_int, [P, L, L, I, P, P, I, I, I, I, P, P, P, L, L, P, P]),
+    "las_lstm_seq_bwd": (c_int, [P, L, L, I, P, I, P, I, I, I, I, P, P, P, L, L, P, P]),
+    "las_lstm_persistent_geometry": (c_int, [I, P, P]),
+    "las_set_persistent": (c_int, [I]),
+    "las_whhT_owner_bytes": (c_int64, [I]),
+    "las_pack_whhT_owner": (c_int, [P, I, P, P]),
     "las_pyramid_lens": (c_int, [P, I, I, P, P]),
     "las_att_init": (c_int, [P, I, I, P, L, P]),
     "las_dec_fwd": (c_int, [ctypes.POINTER(DecArgs), P]),

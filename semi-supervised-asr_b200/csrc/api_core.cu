@@ -10,6 +10,7 @@
 namespace las {
 
 static thread_local char g_err[512] = "";
+unsigned long long g_launches = 0;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -44,6 +45,8 @@ const char* las_last_error(void) { return las::g_err; }
 int las_version(void) { return LAS_B200_VERSION; }
 
 int las_num_sms(void) { return las::num_sms(); }
+
+unsigned long long las_launch_count(void) { return las::g_launches; }
 
 int las_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb,
                   int b_mn_major, void* C, int64_t ldc, int c_is_bf16, const float* bias, int M,

@@ -1,0 +1,577 @@
+// Persistent LSTM recurrence for the pyramidal BLSTM listener (model.py:67, 79-81): ONE launch runs
+// all T timesteps of a layer. A thread-block cluster of CS CTAs serves one (direction, group of 8
+// utterances); every CTA keeps its slice of the recurrent weights resident in REGISTERS as
+// mma.m16n8k16 A fragments for the whole sequence, the cell state lives in registers, and the only
+// per-step communication is the exchange of the new hidden state through distributed shared memory:
+//
+//   forward : all-gather of h_t. Each lane transposes its 8x8 (unit x utterance) tile with movmatrix
+//             so that it holds exactly one B-fragment word of the NEXT step's MMA, and pushes it to
+//             every CTA of the cluster with st.async (data + mbarrier complete_tx in one message; no
+//             fence, no separate flag). A CTA starts step t+1 when its mbarrier has counted all bytes.
+//   backward: reduce-scatter of dh_t. A CTA multiplies W_hh^T restricted to ITS OWN gate rows with
+//             its own gate gradients (no gather needed), pushes the f32 partial sums to the CTAs that
+//             own the units, and each owner adds the CS partials before the gate-derivative math.
+//
+// Timesteps are therefore synchronised by mbarrier transaction counts fed by remote stores, not by
+// kernel boundaries: per step one DSMEM hop instead of a launch + L2 round trips.
+#include <cooperative_groups.h>
+#include <stdlib.h>
+#include "common.cuh"
+#include "las_internal.h"
+#include "../../include/las_b200.h"
+
+namespace cg = cooperative_groups;
+
+namespace las {
+
+namespace {
+
+constexpr int kMaxUGC = 5;   // unit groups (8 hidden units) per CTA
+constexpr int kMaxKTW = 10;  // k-tiles (16) per warp in the forward kernel
+constexpr int kNB = 8;       // utterances per cluster (one MMA n-tile)
+
+struct Geom {
+  int UG, CS, UGC, KT, KS, KTW, JT, MTW;
+};
+
+bool geom_for(int H, Geom& g) {
+  if (H % 8 != 0 || H < 8 || H > 8 * 8 * kMaxUGC) return false;
+  g.UG = H / 8;
+  const int cs0 = g.UG < 8 ? g.UG : 8;
+  g.UGC = (g.UG + cs0 - 1) / cs0;
+  g.CS = (g.UG + g.UGC - 1) / g.UGC;
+  g.KT = (H + 15) / 16;
+  g.KS = g.KT > kMaxKTW ? 2 : 1;
+  g.KTW = (g.KT + g.KS - 1) / g.KS;
+  g.JT = (H + 15) / 16;
+  const int W = 2 * g.UGC;
+  g.MTW = (g.JT + W - 1) / W;
+  return g.MTW <= 2 && g.KTW <= kMaxKTW && g.UGC <= kMaxUGC;
+}
+
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_async_b32(uint32_t addr, uint32_t v, uint32_t mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+               ::"r"(addr), "r"(v), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void st_async_v2(uint32_t addr, uint32_t v0, uint32_t v1, uint32_t mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];"
+               ::"r"(addr), "r"(v0), "r"(v1), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ uint32_t movmatrix_trans(uint32_t a) {
+  uint32_t d;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
+  return d;
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must trap, not hang the GPU box.
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (++spins > (1u << 24)) {
+      printf("las: persistent LSTM barrier timeout (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y,
+             blockIdx.z, threadIdx.x);
+      __trap();
+    }
+  }
+}
+
+struct FwdP {
+  const float* xproj; int64_t xp_ld_b, xp_ld_t;
+  const uint32_t* whh_pk;      // [ndir][2*UG][KT][32][4]
+  const int32_t* lens;
+  __nv_bfloat16* y; int64_t y_ld_b, y_ld_t;
+  __nv_bfloat16* hprev; int64_t hp_ld_b, hp_ld_t;
+  __half* gates_save; float* c_save;
+  int B, T, H, rep_row;
+  int UG, UGC, KS, KTW, KT;
+};
+
+// grid (CS, ceil(B/8), ndir), cluster (CS,1,1), block 32*UGC*KS. warp = ks*UGC + ugl.
+__global__ void __launch_bounds__(320, 1) lstm_persist_fwd_kernel(FwdP p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);                    // [2]
+  uint32_t* hs = reinterpret_cast<uint32_t*>(smem + 16);                 // [2][KT][32][2]
+  float* red = reinterpret_cast<float*>(smem + 16 + 2 * p.KT * 256);     // [UGC][32][8]
+  cg::cluster_group cluster = cg::this_cluster();
+  const uint32_t rank = cluster.block_rank(), CS = cluster.num_blocks();
+  const int grp = blockIdx.y, dir = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tig = lane & 3;
+  const int ugl = warp % p.UGC, ks = warp / p.UGC;
+  const int ug = rank * p.UGC + ugl;
+  const bool ug_ok = ug < p.UG;
+  const uint32_t tx_bytes = static_cast<uint32_t>(p.UG) * 128u;
+  const int T = p.T, H = p.H;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    fence_mbar_init();
+  }
+  for (int i = threadIdx.x; i < 2 * p.KT * 64; i += blockDim.x) hs[i] = 0u;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (T > 1) mbar_arrive_expect_tx(&full[1], tx_bytes);   // h_0 -> consumed by step 1
+    if (T > 2) mbar_arrive_expect_tx(&full[0], tx_bytes);   // h_1 -> consumed by step 2
+  }
+  cluster.sync();   // every CTA's barriers are armed before any remote store can arrive
+
+  // resident recurrent weights: A fragments of this warp's unit group and k-range
+  uint4 A[2][kMaxKTW];
+  {
+    const int64_t a_dir = static_cast<int64_t>(2) * p.UG * p.KT * 128;
+#pragma unroll
+    for (int half = 0; half < 2; ++half)
+#pragma unroll
+      for (int j = 0; j < kMaxKTW; ++j) {
+        const int kt = ks * p.KTW + j;
+        if (ug_ok && j < p.KTW && kt < p.KT)
+          A[half][j] = __ldg(reinterpret_cast<const uint4*>(p.whh_pk + dir * a_dir) +
+                             (static_cast<int64_t>(2 * ug + half) * p.KT + kt) * 32 + lane);
+        else
+          A[half][j] = make_uint4(0u, 0u, 0u, 0u);
+      }
+  }
+
+  // per-lane recurrent state (epilogue warps): unit u, utterances n[0], n[1]
+  const int u = 8 * ug + g;
+  const bool epi = (ks == 0) && ug_ok;
+  int n[2], len[2];
+  float c_st[2] = {0.f, 0.f};
+  __nv_bfloat16 h_st[2];
+  float xp[2][4];
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    n[e] = grp * kNB + 2 * tig + e;
+    len[e] = (epi && n[e] < p.B) ? (p.lens ? p.lens[n[e]] : T) : 0;
+    h_st[e] = __float2bfloat16(0.f);
+  }
+  auto load_xp = [&](int s, float (&dst)[2][4]) {
+    const int t = (dir == 0) ? s : (T - 1 - s);
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      if (epi && t < len[e]) {
+        const float* q = p.xproj + n[e] * p.xp_ld_b + t * p.xp_ld_t + static_cast<int64_t>(dir) * 4 * H + u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dst[e][k] = __ldg(q + k * H);
+      }
+    }
+  };
+  load_xp(0, xp);
+
+  for (int s = 0; s < T; ++s) {
+    const int t = (dir == 0) ? s : (T - 1 - s);
+    float xn[2][4];
+    if (s + 1 < T) load_xp(s + 1, xn);   // prefetch: DRAM latency hidden behind this step
+
+    float acc[2][2][4];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
+
+    if (s > 0) {
+      const int buf = s & 1;
+      mbar_wait_cluster(&full[buf], ((s - 1) >> 1) & 1);
+      if (threadIdx.x == 0 && s + 2 < T) mbar_arrive_expect_tx(&full[buf], tx_bytes);  // re-arm for step s+2
+      const uint2* hb = reinterpret_cast<const uint2*>(hs + buf * p.KT * 64) + lane;
+#pragma unroll
+      for (int j = 0; j < kMaxKTW; ++j) {
+        const int kt = ks * p.KTW + j;
+        if (j < p.KTW && kt < p.KT) {
+          const uint2 b = hb[kt * 32];
+          const uint32_t A0[4] = {A[0][j].x, A[0][j].y, A[0][j].z, A[0][j].w};
+          const uint32_t A1[4] = {A[1][j].x, A[1][j].y, A[1][j].z, A[1][j].w};
+          mma_bf16_16816(acc[0][j & 1], A0, b.x, b.y);
+          mma_bf16_16816(acc[1][j & 1], A1, b.x, b.y);
+        }
+      }
+    }
+    float gsum[2][4];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) gsum[a][c] = acc[a][0][c] + acc[a][1][c];
+    if (p.KS == 2) {
+      float* r = red + (ugl * 32 + lane) * 8;
+      if (ks == 1) {
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) r[a * 4 + c] = gsum[a][c];
+      }
+      __syncthreads();
+      if (ks == 0) {
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) gsum[a][c] += r[a * 4 + c];
+      }
+    }
+    if (epi) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const bool inb = n[e] < p.B;
+        const bool active = t < len[e];
+        const __nv_bfloat16 h_old = h_st[e];
+        if (active) {
+          const float gi = gsum[0][e] + xp[e][0];
+          const float gf = gsum[0][2 + e] + xp[e][1];
+          const float gg = gsum[1][e] + xp[e][2];
+          const float go = gsum[1][2 + e] + xp[e][3];
+          const float i = sigmoid_acc(gi), f = sigmoid_acc(gf), gc = tanh_acc(gg), o = sigmoid_acc(go);
+          const float c = f * c_st[e] + i * gc;
+          const float h = o * tanh_acc(c);
+          c_st[e] = c;
+          h_st[e] = __float2bfloat16(h);
+          const int64_t sv = ((static_cast<int64_t>(dir) * p.B + n[e]) * T + t) * H + u;
+          if (p.gates_save) {
+            __half2 lo = __floats2half2_rn(i, f), hi = __floats2half2_rn(gc, o);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&lo);
+            pk.y = *reinterpret_cast<uint32_t*>(&hi);
+            reinterpret_cast<uint2*>(p.gates_save)[sv] = pk;
+          }
+          if (p.c_save) p.c_save[sv] = c;
+          const int64_t yo = n[e] * p.y_ld_b + t * p.y_ld_t + static_cast<int64_t>(dir) * H + u;
+          p.y[yo] = h_st[e];
+          if (p.rep_row && t == T - 1) p.y[yo + p.y_ld_t] = h_st[e];
+        }
+        if (inb && p.hprev) p.hprev[n[e] * p.hp_ld_b + t * p.hp_ld_t + static_cast<int64_t>(dir) * H + u] = h_old;
+      }
+      if (s + 1 < T) {
+        // lane (unit g, utterances 2tig, 2tig+1) -> after the 8x8 transpose: (utterance g, units 2tig, 2tig+1)
+        __nv_bfloat162 hv;
+        hv.x = h_st[0];
+        hv.y = h_st[1];
+        const uint32_t w = movmatrix_trans(*reinterpret_cast<uint32_t*>(&hv));
+        const int nbuf = (s + 1) & 1;
+        const uint32_t dst = smem_u32(hs + ((nbuf * p.KT + (ug >> 1)) * 32 + lane) * 2 + (ug & 1));
+        const uint32_t bar = smem_u32(&full[nbuf]);
+        for (uint32_t peer = 0; peer < CS; ++peer) st_async_b32(mapa_u32(dst, peer), w, mapa_u32(bar, peer));
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 2; ++e)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) xp[e][k] = xn[e][k];
+  }
+  cluster.sync();   // nobody exits while remote stores may still target its shared memory
+}
+
+struct BwdP {
+  const float* dy; int64_t dy_ld_b, dy_ld_t;
+  const uint32_t* wT_pk;       // owner-ordered W_hh^T fragments [ndir][JT][CS*KTC][32][4]
+  const int32_t* lens;
+  const __half* gates_save; const float* c_save;
+  __nv_bfloat16* dG; int64_t dg_ld_b, dg_ld_t;
+  int B, T, H, rep_row;
+  int UGC, JT, MTW, CSn;
+};
+
+// grid (CS, ceil(B/8), ndir), cluster (CS,1,1), block 64*UGC (= 8 utterances x UPC units).
+__global__ void __launch_bounds__(320, 1) lstm_persist_bwd_kernel(BwdP p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int UPC = 8 * p.UGC, KTC = 2 * p.UGC;
+  uint64_t* pfull = reinterpret_cast<uint64_t*>(smem);                   // [2]
+  float* part = reinterpret_cast<float*>(smem + 16);                     // [2][CS][UPC*8]
+  uint32_t* dgs = reinterpret_cast<uint32_t*>(smem + 16 + 2 * p.CSn * UPC * 8 * 4);   // [KTC][32][2]
+  cg::cluster_group cluster = cg::this_cluster();
+  const uint32_t rank = cluster.block_rank(), CS = cluster.num_blocks();
+  const int grp = blockIdx.y, dir = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tig = lane & 3;
+  const int T = p.T, H = p.H;
+  const int vu = max(0, min(UPC, H - static_cast<int>(rank) * UPC));     // valid units owned by this CTA
+  const uint32_t tx_bytes = CS * static_cast<uint32_t>(vu) * 32u;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&pfull[0], 1);
+    mbar_init(&pfull[1], 1);
+    fence_mbar_init();
+  }
+  for (int i = threadIdx.x; i < KTC * 64; i += blockDim.x) dgs[i] = 0u;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (T > 1) mbar_arrive_expect_tx(&pfull[1], tx_bytes);
+    if (T > 2) mbar_arrive_expect_tx(&pfull[0], tx_bytes);
+  }
+  cluster.sync();
+
+  // resident W_hh^T fragments: rows = this warp's 16-unit tiles, K = this CTA's own gate rows
+  uint4 A[2][kMaxKTW];
+  {
+    const int KTtot = p.CSn * KTC;
+    const int64_t a_dir = static_cast<int64_t>(p.JT) * KTtot * 128;
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int kc = 0; kc < kMaxKTW; ++kc) {
+        const int mt = warp * p.MTW + m;
+        if (m < p.MTW && mt < p.JT && kc < KTC)
+          A[m][kc] = __ldg(reinterpret_cast<const uint4*>(p.wT_pk + dir * a_dir) +
+                           (static_cast<int64_t>(mt) * KTtot + rank * KTC + kc) * 32 + lane);
+        else
+          A[m][kc] = make_uint4(0u, 0u, 0u, 0u);
+      }
+  }
+
+  // element owned by this thread in the pointwise phase: local unit ul, utterance row nr
+  const int ul = threadIdx.x >> 3, nr = threadIdx.x & 7;
+  const int uo = rank * UPC + ul;
+  const int nb = grp * kNB + nr;
+  const bool own = (uo < H) && (nb < p.B);
+  const int len = own ? (p.lens ? p.lens[nb] : T) : 0;
+  float dc_st = 0.f;
+
+  for (int s = 0; s < T; ++s) {
+    const int t = (dir == 0) ? (T - 1 - s) : s;
+    const bool active = t < len;
+    // operands of the gate-derivative math, fetched now and used after the exchange
+    uint2 gpk = make_uint2(0u, 0u);
+    float c_cur = 0.f, c_prev = 0.f, dyv = 0.f;
+    if (active) {
+      const int64_t sv = ((static_cast<int64_t>(dir) * p.B + nb) * T + t) * H + uo;
+      gpk = reinterpret_cast<const uint2*>(p.gates_save)[sv];
+      c_cur = p.c_save[sv];
+      if (dir == 0) { if (t > 0) c_prev = p.c_save[sv - H]; }
+      else          { if (t + 1 < len) c_prev = p.c_save[sv + H]; }
+      if (p.dy) {
+        const float* dyp = p.dy + nb * p.dy_ld_b + t * p.dy_ld_t + static_cast<int64_t>(dir) * H + uo;
+        dyv = dyp[0];
+        if (p.rep_row && t == T - 1) dyv += dyp[p.dy_ld_t];
+      }
+    }
+    float dh = dyv;
+    if (s > 0) {
+      const int buf = s & 1;
+      // partial dh for this warp's unit tiles from this CTA's own gate gradients of the previous step
+      float acc[2][2][4];
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
+      const uint2* db = reinterpret_cast<const uint2*>(dgs) + lane;
+#pragma unroll
+      for (int kc = 0; kc < kMaxKTW; ++kc) {
+        if (kc < KTC) {
+          const uint2 b = db[kc * 32];
+#pragma unroll
+          for (int m = 0; m < 2; ++m) {
+            const uint32_t Af[4] = {A[m][kc].x, A[m][kc].y, A[m][kc].z, A[m][kc].w};
+            mma_bf16_16816(acc[m][kc & 1], Af, b.x, b.y);
+          }
+        }
+      }
+      // scatter the partial sums to the CTAs that own the units
+      const uint32_t part_base = smem_u32(part + (static_cast<int64_t>(buf) * p.CSn + rank) * UPC * 8);
+      const uint32_t bar = smem_u32(&pfull[buf]);
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        const int mt = warp * p.MTW + m;
+        if (m < p.MTW && mt < p.JT) {
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int j = 16 * mt + g + 8 * hh;
+            if (j < H) {
+              const uint32_t owner = j / UPC;
+              const int jl = j - owner * UPC;
+              const float v0 = acc[m][0][2 * hh] + acc[m][1][2 * hh];
+              const float v1 = acc[m][0][2 * hh + 1] + acc[m][1][2 * hh + 1];
+              st_async_v2(mapa_u32(part_base + (jl * 8 + 2 * tig) * 4, owner), __float_as_uint(v0),
+                          __float_as_uint(v1), mapa_u32(bar, owner));
+            }
+          }
+        }
+      }
+      mbar_wait_cluster(&pfull[buf], ((s - 1) >> 1) & 1);
+      if (threadIdx.x == 0 && s + 2 < T) mbar_arrive_expect_tx(&pfull[buf], tx_bytes);
+      const float* pp = part + static_cast<int64_t>(buf) * p.CSn * UPC * 8 + threadIdx.x;
+      for (uint32_t src = 0; src < CS; ++src) dh += pp[src * UPC * 8];
+    }
+    // gate derivatives (same math as cell_bwd_kernel)
+    float d4[4] = {0.f, 0.f, 0.f, 0.f};
+    if (active) {
+      const float2 if_ = __half22float2(*reinterpret_cast<const __half2*>(&gpk.x));
+      const float2 go_ = __half22float2(*reinterpret_cast<const __half2*>(&gpk.y));
+      const float i = if_.x, f = if_.y, gc = go_.x, o = go_.y;
+      const float tc = tanh_acc(c_cur);
+      const float dc = dh * o * (1.f - tc * tc) + dc_st;
+      dc_st = dc * f;
+      d4[0] = dc * gc * i * (1.f - i);
+      d4[1] = dc * c_prev * f * (1.f - f);
+      d4[2] = dc * i * (1.f - gc * gc);
+      d4[3] = dh * tc * o * (1.f - o);
+    }
+    if (own) {
+      __nv_bfloat16* dgp = p.dG + nb * p.dg_ld_b + t * p.dg_ld_t + static_cast<int64_t>(dir) * 4 * H + uo;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) dgp[q * H] = __float2bfloat16(d4[q]);
+    }
+    if (s + 1 < T && uo < H) {
+      // B fragments of the next step's MMA: K index k = gate*UPC + ul within this CTA
+      __nv_bfloat16* d16 = reinterpret_cast<__nv_bfloat16*>(dgs);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int k = q * UPC + ul;
+        const int kt = k >> 4, kk = k & 15;
+        d16[((kt * 32 + nr * 4 + ((kk & 7) >> 1)) * 2 + (kk >> 3)) * 2 + (kk & 1)] = __float2bfloat16(d4[q]);
+      }
+    }
+    __syncthreads();
+  }
+  cluster.sync();
+}
+
+// owner-ordered packing of W_hh^T: logical A[j][k], k = r*4*UPC + gate*UPC + ul  <->  W[gate*H + r*UPC + ul][j]
+__global__ void pack_whhT_owner_kernel(const float* __restrict__ W, int H, int CS, int UPC, int JT,
+                                       uint32_t* __restrict__ out) {
+  const int KTtot = CS * UPC / 4;
+  const int64_t total = static_cast<int64_t>(JT) * KTtot * 128;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int jj = idx & 3;
+    const int lane = (idx >> 2) & 31;
+    const int64_t tk = idx >> 7;
+    const int kt = tk % KTtot;
+    const int tile = tk / KTtot;
+    const int g = lane >> 2, tig = lane & 3;
+    const int j = 16 * tile + g + 8 * (jj & 1);
+    const int k0 = 16 * kt + 2 * tig + 8 * (jj >> 1);
+    float v[2] = {0.f, 0.f};
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int k = k0 + q;
+      const int r = k / (4 * UPC), rem = k % (4 * UPC);
+      const int gate = rem / UPC, ulq = rem % UPC;
+      const int uq = r * UPC + ulq;
+      if (j < H && uq < H) v[q] = W[(static_cast<int64_t>(gate) * H + uq) * H + j];
+    }
+    out[idx] = pack_bf16x2(v[0], v[1]);
+  }
+}
+
+int g_persist = -1;   // -1: take the default from the environment (LAS_DISABLE_PERSISTENT=1 turns it off)
+bool persist_enabled() {
+  if (g_persist < 0) {
+    const char* e = getenv("LAS_DISABLE_PERSISTENT");
+    g_persist = (e && e[0] == '1') ? 0 : 1;
+  }
+  return g_persist == 1;
+}
+
+template <typename Kern, typename P>
+int launch_cluster(Kern kern, const P& p, int CS, int NG, int ndir, int threads, size_t smem, cudaStream_t stream) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(CS, NG, ndir);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CS;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  LAS_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+  ++g_launches;
+  return 0;
+}
+
+}  // namespace
+
+int persist_supported(int H) {
+  Geom g;
+  return persist_enabled() && geom_for(H, g) ? 1 : 0;
+}
+
+int persist_lstm_fwd(const float* xproj, const void* whh_pk, const int32_t* lens, int B, int T, int H, int ndir,
+                     void* y, int64_t y_ld_b, int64_t y_ld_t, int rep_row, void* hprev, int64_t hp_ld_b,
+                     int64_t hp_ld_t, void* gates_save, float* c_save, cudaStream_t stream) {
+  Geom g;
+  LAS_REQUIRE(geom_for(H, g), "persistent LSTM: hidden size %d unsupported", H);
+  FwdP p;
+  p.xproj = xproj; p.xp_ld_t = static_cast<int64_t>(ndir) * 4 * H; p.xp_ld_b = p.xp_ld_t * T;
+  p.whh_pk = static_cast<const uint32_t*>(whh_pk); p.lens = lens;
+  p.y = static_cast<__nv_bfloat16*>(y); p.y_ld_b = y_ld_b; p.y_ld_t = y_ld_t;
+  p.hprev = static_cast<__nv_bfloat16*>(hprev); p.hp_ld_b = hp_ld_b; p.hp_ld_t = hp_ld_t;
+  p.gates_save = static_cast<__half*>(gates_save); p.c_save = c_save;
+  p.B = B; p.T = T; p.H = H; p.rep_row = rep_row;
+  p.UG = g.UG; p.UGC = g.UGC; p.KS = g.KS; p.KTW = g.KTW; p.KT = g.KT;
+  const size_t smem = 16 + static_cast<size_t>(2) * g.KT * 256 + static_cast<size_t>(g.UGC) * 32 * 8 * 4;
+  return launch_cluster(lstm_persist_fwd_kernel, p, g.CS, (B + kNB - 1) / kNB, ndir, 32 * g.UGC * g.KS, smem, stream);
+}
+
+int persist_lstm_bwd(const float* dy, int64_t dy_ld_b, int64_t dy_ld_t, int rep_row, const void* wT_owner_pk,
+                     const int32_t* lens, int B, int T, int H, int ndir, const void* gates_save,
+                     const float* c_save, void* dG, int64_t dg_ld_b, int64_t dg_ld_t, cudaStream_t stream) {
+  Geom g;
+  LAS_REQUIRE(geom_for(H, g), "persistent LSTM: hidden size %d unsupported", H);
+  BwdP p;
+  p.dy = dy; p.dy_ld_b = dy_ld_b; p.dy_ld_t = dy_ld_t; p.rep_row = rep_row;
+  p.wT_pk = static_cast<const uint32_t*>(wT_owner_pk); p.lens = lens;
+  p.gates_save = static_cast<const __half*>(gates_save); p.c_save = c_save;
+  p.dG = static_cast<__nv_bfloat16*>(dG); p.dg_ld_b = dg_ld_b; p.dg_ld_t = dg_ld_t;
+  p.B = B; p.T = T; p.H = H;
+  p.UGC = g.UGC; p.JT = g.JT; p.MTW = g.MTW; p.CSn = g.CS;
+  const int UPC = 8 * g.UGC;
+  const size_t smem = 16 + static_cast<size_t>(2) * g.CS * UPC * 8 * 4 + static_cast<size_t>(2 * g.UGC) * 256;
+  return launch_cluster(lstm_persist_bwd_kernel, p, g.CS, (B + kNB - 1) / kNB, ndir, 64 * g.UGC, smem, stream);
+}
+
+}  // namespace las
+
+using namespace las;
+
+extern "C" {
+
+int las_set_persistent(int on) {
+  const int prev = persist_enabled() ? 1 : 0;
+  g_persist = on ? 1 : 0;
+  return prev;
+}
+
+int las_lstm_persistent_geometry(int H, int* cs, int* upc) {
+  Geom g;
+  if (!persist_enabled() || !geom_for(H, g)) return 0;
+  if (cs) *cs = g.CS;
+  if (upc) *upc = 8 * g.UGC;
+  return 1;
+}
+
+int64_t las_whhT_owner_bytes(int H) {
+  Geom g;
+  if (!geom_for(H, g)) return 0;
+  return static_cast<int64_t>(g.JT) * (g.CS * 2 * g.UGC) * 128 * 4;
+}
+
+int las_pack_whhT_owner(const float* W, int H, void* out, void* stream) {
+  Geom g;
+  LAS_REQUIRE(geom_for(H, g), "pack_whhT_owner: hidden size %d unsupported", H);
+  const int64_t total = static_cast<int64_t>(g.JT) * (g.CS * 2 * g.UGC) * 128;
+  int blocks = static_cast<int>((total + 255) / 256);
+  if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
+  pack_whhT_owner_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(W, H, g.CS, 8 * g.UGC, g.JT,
+                                                                                  static_cast<uint32_t*>(out));
+  ++g_launches;
+  LAS_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

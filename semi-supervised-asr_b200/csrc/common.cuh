@@ -13,6 +13,7 @@ namespace las {
 // error plumbing (C-ABI returns int; message retrievable with las_last_error())
 // ----------------------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
+extern unsigned long long g_launches;  // kernels launched by this library (las_launch_count())
 int check_cuda(cudaError_t e, const char* what);
 
 #define LAS_CUDA(expr)                                   \
@@ -219,7 +220,7 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_ma
 // ----------------------------------------------------------------------------------------
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0,
                                                uint32_t b1) {
-  asm volatile(
+  asm(
       "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 "
       "{%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])

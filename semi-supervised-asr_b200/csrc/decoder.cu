@@ -33,6 +33,33 @@ __device__ __forceinline__ float block_reduce_max(float v, float* red, int nwarp
   return t;
 }
 
+// Sum 16 per-lane values across the warp with 16 shuffles (instead of 16 x 5): each halving step
+// keeps half of the values and exchanges the other half with the partner lane. On return, lane l
+// holds the warp total of value index ((l>>4)&1)*8 + ((l>>3)&1)*4 + ((l>>2)&1)*2 + ((l>>1)&1).
+__device__ __forceinline__ float warp_multi_reduce16(const float (&v)[16], int lane) {
+  float a[8], b[4], c[2];
+  const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float mine = h16 ? v[8 + i] : v[i], other = h16 ? v[i] : v[8 + i];
+    a[i] = mine + __shfl_xor_sync(0xffffffffu, other, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float mine = h8 ? a[4 + i] : a[i], other = h8 ? a[i] : a[4 + i];
+    b[i] = mine + __shfl_xor_sync(0xffffffffu, other, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float mine = h4 ? b[2 + i] : b[i], other = h4 ? b[i] : b[2 + i];
+    c[i] = mine + __shfl_xor_sync(0xffffffffu, other, 4);
+  }
+  const float mine = h2 ? c[1] : c[0], other = h2 ? c[0] : c[1];
+  float r = mine + __shfl_xor_sync(0xffffffffu, other, 2);
+  r += __shfl_xor_sync(0xffffffffu, r, 1);
+  return r;
+}
+
 struct AttGeom {
   int B, Te, A, C, K;  // K = conv_kernel_size (taps = 2K+1)
   int H;               // encoder feature dim
@@ -344,12 +371,17 @@ __global__ void __launch_bounds__(512) att_energy_bwd_kernel(EnergyBwdParams p) 
     dgv = fmaf(de, s, dgv);
     ddz += ds;
     if (a < g.A) p.dP[pb + static_cast<int64_t>(tl) * g.A] += ds;
+    float prod[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) prod[c] = 0.f;
 #pragma unroll
     for (int c = 0; c < CM; ++c) {
       dmatt[c] = fmaf(ds, conv[tl * CM + c], dmatt[c]);
-      const float v = warp_sum(ds * matt[c]);
-      if (lane == 0) red2[(warp * kTT + tl) * CM + c] = v;
+      prod[c] = ds * matt[c];
     }
+    const float tot = warp_multi_reduce16(prod, lane);
+    const int ci = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+    if ((lane & 1) == 0 && ci < CM) red2[(warp * kTT + tl) * CM + ci] = tot;
   }
   __syncthreads();
   for (int i = threadIdx.x; i < ntl * g.C; i += blockDim.x) {
@@ -457,7 +489,7 @@ extern "C" {
 
 int las_att_init(const int32_t* enc_lens, int B, int Te, float* w, int64_t w_ld, void* stream) {
   if (B == 0) return 0;
-  att_init_kernel<<<B, 128, 0, static_cast<cudaStream_t>(stream)>>>(enc_lens, B, Te, w, w_ld);
+  att_init_kernel<<<B, 128, 0, static_cast<cudaStream_t>(stream)>>>(enc_lens, B, Te, w, w_ld); ++g_launches;
   LAS_LAUNCH_CHECK();
   return 0;
 }
@@ -520,10 +552,11 @@ int las_dec_fwd(const las_dec_args* a, void* stream_) {
     ep.wprev = a->ws + static_cast<int64_t>(t) * Te;
     if (CM == 4) att_energy_fwd_kernel<4><<<egrid, ethreads, esmem, stream>>>(ep);
     else att_energy_fwd_kernel<16><<<egrid, ethreads, esmem, stream>>>(ep);
+    ++g_launches;
     // (4) w = softmax(scaling * e) over all Te, context = w @ enc_h   (model.py:167-171)
     xp.w_out = a->ws + static_cast<int64_t>(t + 1) * Te;
     xp.ctx = ctx + static_cast<int64_t>(t + 1) * a->H;
-    att_ctx_fwd_kernel<<<cgrid, 256, csmem, stream>>>(xp);
+    att_ctx_fwd_kernel<<<cgrid, 256, csmem, stream>>>(xp); ++g_launches;
     // (5) c_t = mlp_o(context)   (model.py:172) -> second half of zc row t+1
     smallmm(static_cast<const uint32_t*>(a->mlp_o_pk), O, a->H, ctx + static_cast<int64_t>(t + 1) * a->H, 0, R * a->H, B,
             a->mlp_o_b, nullptr, 0, nullptr, 0, zc + static_cast<int64_t>(t + 1) * ZC + Hd, R * ZC, stream);
@@ -537,7 +570,7 @@ int las_dec_fwd(const las_dec_args* a, void* stream_) {
       np.scaling = a->smooth_scaling; np.smooth = (a->mode == 2);
       np.pred = a->pred + t; np.pred_ld = L;
       np.emb_out = emb_op + static_cast<int64_t>(t + 1) * Ep; np.eo_ld = R * Ep;
-      next_emb_kernel<<<(B + 3) / 4, 128, 0, stream>>>(np);
+      next_emb_kernel<<<(B + 3) / 4, 128, 0, stream>>>(np); ++g_launches;
     }
   }
   LAS_LAUNCH_CHECK();
@@ -597,7 +630,7 @@ int las_dec_bwd(const las_dec_args* a, void* stream_) {
     // (3) dw_t = <dcontext, enc_h> + conv-input gradient of step t+1
     wp.dctx = dctx_t;
     wp.dattc_next = (t + 1 < L) ? a->dattc_all + static_cast<int64_t>(t + 1) * B * Te * a->C : nullptr;
-    att_dw_kernel<<<egrid, 256, dsmem, stream>>>(wp);
+    att_dw_kernel<<<egrid, 256, dsmem, stream>>>(wp); ++g_launches;
     // (4) softmax + energy backward (tanh recomputed)
     ep.dz = a->dzf + static_cast<int64_t>(t) * A;
     ep.wprev = a->ws + static_cast<int64_t>(t) * Te;
@@ -606,6 +639,7 @@ int las_dec_bwd(const las_dec_args* a, void* stream_) {
     ep.dattc = a->dattc_all + static_cast<int64_t>(t) * B * Te * a->C;
     if (CM == 4) att_energy_bwd_kernel<4><<<egrid, ethreads, esmem, stream>>>(ep);
     else att_energy_bwd_kernel<16><<<egrid, ethreads, esmem, stream>>>(ep);
+    ++g_launches;
     // (5) dz_t += mlp_dec^T ddz ; LSTMCell backward -> dgates_t
     cb.step = L - 1 - t;
     cb.v = a->ddz_all; cb.v_t_fwd = t + 1;
@@ -613,9 +647,9 @@ int las_dec_bwd(const las_dec_args* a, void* stream_) {
   }
   // reductions that were deferred out of the loop
   att_part_reduce_kernel<<<((a->C + 1) * A + 255) / 256, 256, 0, stream>>>(a->att_part, ncta, CM, Ap, A, a->C,
-                                                                             a->dmlp_att, a->dgvec);
-  att_dconv_kernel<<<ksz, 256, 0, stream>>>(a->dattc_all, a->ws, L, B, Te, a->C, a->K, a->dconv_w);
-  att_denc_kernel<<<dim3(Te, B), 256, 0, stream>>>(a->ws, a->dctx_all, L, B, Te, a->H, a->denc, a->denc_accumulate);
+                                                                             a->dmlp_att, a->dgvec); ++g_launches;
+  att_dconv_kernel<<<ksz, 256, 0, stream>>>(a->dattc_all, a->ws, L, B, Te, a->C, a->K, a->dconv_w); ++g_launches;
+  att_denc_kernel<<<dim3(Te, B), 256, 0, stream>>>(a->ws, a->dctx_all, L, B, Te, a->H, a->denc, a->denc_accumulate); ++g_launches;
   LAS_LAUNCH_CHECK();
   return 0;
 }

@@ -283,7 +283,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cu
   }
   const int tiles = ((p.M + BLOCK_M - 1) / BLOCK_M) * ((p.N + BN - 1) / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, kThreads, L::kTotal, stream>>>(ta, tb, p);
+  kern<<<grid, kThreads, L::kTotal, stream>>>(ta, tb, p); ++g_launches;
   LAS_LAUNCH_CHECK();
   return 0;
 }

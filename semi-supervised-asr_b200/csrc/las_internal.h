@@ -15,6 +15,15 @@ int gemm_bf16(const void* A, int64_t lda, bool a_mn, const void* B, int64_t ldb,
               int64_t ldc, bool c_bf16, const float* bias, int M, int N, int K, bool relu,
               bool accumulate, cudaStream_t stream);
 
+// cluster-persistent recurrence (blstm_persistent.cu)
+int persist_supported(int H);
+int persist_lstm_fwd(const float* xproj, const void* whh_pk, const int32_t* lens, int B, int T, int H, int ndir,
+                     void* y, int64_t y_ld_b, int64_t y_ld_t, int rep_row, void* hprev, int64_t hp_ld_b,
+                     int64_t hp_ld_t, void* gates_save, float* c_save, cudaStream_t stream);
+int persist_lstm_bwd(const float* dy, int64_t dy_ld_b, int64_t dy_ld_t, int rep_row, const void* wT_owner_pk,
+                     const int32_t* lens, int B, int T, int H, int ndir, const void* gates_save,
+                     const float* c_save, void* dG, int64_t dg_ld_b, int64_t dg_ld_t, cudaStream_t stream);
+
 #ifdef __CUDACC__
 }  // namespace las
 #include <cuda_bf16.h>
@@ -45,6 +54,7 @@ struct CellFwdParams {
   __half* gates_save;                  // [ndir][B][T][H][4] or nullptr
   float* c_save;                       // [ndir][B][T][H] or nullptr
   int B, T, H, ndir, UG;
+  int NT, KS;                          // warp layout, filled by launch_cell_fwd
   int step;                            // 0..T-1 (the reverse direction processes t = T-1-step)
   int rep_row;                         // 1: the value at t == T-1 is also written to row T
 };
@@ -68,6 +78,7 @@ struct CellBwdParams {
   int64_t dg_ld_b, dg_ld_t;
   float* dc_state;                     // [ndir][B][H]
   int B, T, H, ndir;
+  int NT, KS;                          // warp layout, filled by launch_cell_bwd
   int step;
   int rep_row;
 };
@@ -85,10 +96,11 @@ struct SmallMMParams {
   __nv_bfloat16* out_bf16;             // [N, ld_outb] or nullptr
   int64_t ld_outb;
   int M, N, MT, KT;
+  int NT, KS;
 };
 
-int launch_cell_fwd(const CellFwdParams& p, cudaStream_t stream);
-int launch_cell_bwd(const CellBwdParams& p, cudaStream_t stream);
+int launch_cell_fwd(CellFwdParams& p, cudaStream_t stream);
+int launch_cell_bwd(CellBwdParams& p, cudaStream_t stream);
 int pack_afrag(const float* W, int64_t ld, int rows, int cols, int col_offset, int mode, int H,
                bool transposed, int tiles, int KT, uint32_t* out, cudaStream_t stream);
 // out[n, m] = sum_k A[m,k] v[n,k] (+bias[m]) (+add[n,m]); A pre-packed by pack_afrag (mode 0).

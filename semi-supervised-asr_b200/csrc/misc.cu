@@ -269,14 +269,14 @@ int las_cvt_pad_bf16(const float* src, int64_t ld_src, int64_t rows, int cols, v
   LAS_REQUIRE(ld_dst % 2 == 0 && ld_dst >= cols, "cvt_pad: bad ld_dst");
   if (rows == 0) return 0;
   cvt_pad_bf16_kernel<<<grid_for(rows * (ld_dst / 2)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      src, ld_src, rows, cols, static_cast<__nv_bfloat16*>(dst), ld_dst);
+      src, ld_src, rows, cols, static_cast<__nv_bfloat16*>(dst), ld_dst); ++g_launches;
   LAS_LAUNCH_CHECK();
   return 0;
 }
 
 int las_add2(const float* a, const float* b, float* out, int64_t n, void* stream) {
   if (n == 0) return 0;
-  add2_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, b, out, n);
+  add2_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, b, out, n); ++g_launches;
   LAS_LAUNCH_CHECK();
   return 0;
 }
@@ -284,7 +284,7 @@ int las_add2(const float* a, const float* b, float* out, int64_t n, void* stream
 int las_relu_bwd(const float* dout, const void* out, int out_is_bf16, void* dz, int64_t n, void* stream) {
   if (n == 0) return 0;
   relu_bwd_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      dout, out, out_is_bf16, static_cast<__nv_bfloat16*>(dz), n);
+      dout, out, out_is_bf16, static_cast<__nv_bfloat16*>(dz), n); ++g_launches;
   LAS_LAUNCH_CHECK();
   return 0;
 }
@@ -299,6 +299,7 @@ int las_colsum(const void* x, int x_is_bf16, int64_t ld, int64_t rows, int cols,
   else
     colsum_kernel<float><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const float*>(x), ld, rows, cols, out, rows_per_cta);
+  ++g_launches;
   LAS_LAUNCH_CHECK();
   return 0;
 }
@@ -307,7 +308,7 @@ int las_gather_rows_bf16(const float* table, int dim, const int64_t* idx, int64_
                          int64_t ld_out, void* stream) {
   if (n == 0) return 0;
   gather_rows_bf16_kernel<<<static_cast<int>(n < 4096 ? n : 4096), 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      table, dim, idx, n, static_cast<__nv_bfloat16*>(out), ld_out);
+      table, dim, idx, n, static_cast<__nv_bfloat16*>(out), ld_out); ++g_launches;
   LAS_LAUNCH_CHECK();
   return 0;
 }
@@ -316,7 +317,7 @@ int las_scatter_add_rows(const float* d, int64_t ld, int dim, const int64_t* idx
                          float* dtable, void* stream) {
   if (n == 0) return 0;
   scatter_add_rows_kernel<<<static_cast<int>(n < 4096 ? n : 4096), 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      d, ld, dim, idx, n, pad, dtable);
+      d, ld, dim, idx, n, pad, dtable); ++g_launches;
   LAS_LAUNCH_CHECK();
   return 0;
 }
@@ -327,7 +328,7 @@ int las_ce_ls_fwd(const float* logits, int64_t ld, int64_t ld_b, int64_t rows_pe
   if (rows == 0) return 0;
   const int wpb = 8;
   ce_ls_fwd_kernel<<<static_cast<unsigned>((rows + wpb - 1) / wpb), wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-      logits, ld, ld_b, rows_per_b, rows, V, targets, dist, ls, out_logp, out_prob, out_pred);
+      logits, ld, ld_b, rows_per_b, rows, V, targets, dist, ls, out_logp, out_prob, out_pred); ++g_launches;
   LAS_LAUNCH_CHECK();
   return 0;
 }
@@ -338,7 +339,7 @@ int las_ce_ls_bwd(const float* logits, int64_t ld, int64_t ld_b, int64_t rows_pe
   if (rows == 0) return 0;
   const int wpb = 8;
   ce_ls_bwd_kernel<<<static_cast<unsigned>((rows + wpb - 1) / wpb), wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-      logits, ld, ld_b, rows_per_b, rows, V, targets, dist, ls, g_logp, g_prob, dlogits);
+      logits, ld, ld_b, rows_per_b, rows, V, targets, dist, ls, g_logp, g_prob, dlogits); ++g_launches;
   LAS_LAUNCH_CHECK();
   return 0;
 }
@@ -351,7 +352,7 @@ __global__ void pyramid_lens_kernel(const int32_t* __restrict__ in, int B, int s
 int las_pyramid_lens(const int32_t* lens_in, int B, int sub, int32_t* lens_out, void* stream) {
   if (B == 0) return 0;
   LAS_REQUIRE(sub >= 1, "pyramid_lens: subsample factor must be >= 1");
-  pyramid_lens_kernel<<<(B + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(lens_in, B, sub, lens_out);
+  pyramid_lens_kernel<<<(B + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(lens_in, B, sub, lens_out); ++g_launches;
   LAS_LAUNCH_CHECK();
   return 0;
 }
@@ -359,8 +360,8 @@ int las_pyramid_lens(const int32_t* lens_in, int B, int sub, int32_t* lens_out, 
 int las_grad_norm(const float* g, int64_t n, void* partials_ws, float* out_norm, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int np = 256;
-  sqnorm_partial_kernel<<<np, 256, 0, stream>>>(g, n, static_cast<double*>(partials_ws));
-  sqnorm_final_kernel<<<1, 32, 0, stream>>>(static_cast<const double*>(partials_ws), np, out_norm);
+  sqnorm_partial_kernel<<<np, 256, 0, stream>>>(g, n, static_cast<double*>(partials_ws)); ++g_launches;
+  sqnorm_final_kernel<<<1, 32, 0, stream>>>(static_cast<const double*>(partials_ws), np, out_norm); ++g_launches;
   LAS_LAUNCH_CHECK();
   return 0;
 }
@@ -372,7 +373,7 @@ int las_adam_step(float* p, const float* g, float* m, float* v, float* vmax, int
   LAS_REQUIRE(step_dev != nullptr, "adam: step_dev must point to the device step counter");
   adam_step_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       p, g, m, v, vmax, n, lr, beta1, beta2, eps, weight_decay, step_dev, max_norm, norm_ptr,
-      grad_scale);
+      grad_scale); ++g_launches;
   LAS_LAUNCH_CHECK();
   return 0;
 }

@@ -73,7 +73,7 @@ int pack_afrag(const float* W, int64_t ld, int rows, int cols, int col_offset, i
   int blocks = static_cast<int>((total + 255) / 256);
   if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
   pack_afrag_kernel<<<blocks, 256, 0, stream>>>(W, ld, rows, cols, col_offset, mode, H,
-                                                transposed ? 1 : 0, tiles, KT, out);
+                                                transposed ? 1 : 0, tiles, KT, out); ++g_launches;
   LAS_LAUNCH_CHECK();
   return 0;
 }
@@ -89,63 +89,124 @@ __device__ __forceinline__ uint32_t ldb_frag(const void* v, int is_f32, int64_t 
 }
 
 // ------------------------------------------------------------------------------------------
+// shared MMA machinery of the step kernels
+// ------------------------------------------------------------------------------------------
+// A CTA is (32 lanes) x NT batch tiles (8 rows each) x KS K-splits: warp = ks * NT + nt. Every
+// warp accumulates its K-range with all loads of a chunk issued before the first MMA of the chunk
+// (the step kernels are latency-bound: one L2 round trip per chunk instead of one per k-tile),
+// K-splits > 0 park their partial sums in shared memory and split 0 finishes.
+constexpr int kChunk = 8;
+constexpr int kMaxWarps = 16;
+
+// acc[m] += A[m-th tile][k-range] * v^T for NM row tiles sharing one B operand.
+template <int NM>
+__device__ __forceinline__ void mma_span(const uint4* __restrict__ a, int64_t tile_stride, const void* v,
+                                         int v_f32, int64_t voff, int kbeg, int kend, float (&acc)[NM][4]) {
+  for (int k0 = kbeg; k0 < kend; k0 += kChunk) {
+    uint4 A[NM][kChunk];
+    uint32_t B0[kChunk], B1[kChunk];
+#pragma unroll
+    for (int j = 0; j < kChunk; ++j) {
+      if (k0 + j < kend) {
+#pragma unroll
+        for (int m = 0; m < NM; ++m) A[m][j] = __ldg(a + m * tile_stride + static_cast<int64_t>(k0 + j) * 32);
+        B0[j] = ldb_frag(v, v_f32, voff + 16 * (k0 + j));
+        B1[j] = ldb_frag(v, v_f32, voff + 16 * (k0 + j) + 8);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kChunk; ++j) {
+      if (k0 + j < kend) {
+#pragma unroll
+        for (int m = 0; m < NM; ++m) {
+          const uint32_t Af[4] = {A[m][j].x, A[m][j].y, A[m][j].z, A[m][j].w};
+          mma_bf16_16816(acc[m], Af, B0[j], B1[j]);
+        }
+      }
+    }
+  }
+}
+
+// Sum the partial accumulators of the K-splits into split 0. Returns false for warps that are done.
+template <int NM>
+__device__ __forceinline__ bool ksplit_reduce(float (&acc)[NM][4], float* red, int nt, int ks, int NT, int KS,
+                                              int lane) {
+  if (KS == 1) return true;
+  if (ks > 0) {
+    float* r = red + ((static_cast<int64_t>(ks - 1) * NT + nt) * 32 + lane) * (NM * 4);
+#pragma unroll
+    for (int m = 0; m < NM; ++m)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) r[m * 4 + c] = acc[m][c];
+  }
+  __syncthreads();
+  if (ks > 0) return false;
+  for (int k = 1; k < KS; ++k) {
+    const float* r = red + ((static_cast<int64_t>(k - 1) * NT + nt) * 32 + lane) * (NM * 4);
+#pragma unroll
+    for (int m = 0; m < NM; ++m)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[m][c] += r[m * 4 + c];
+  }
+  return true;
+}
+
+struct WarpShape { int NT, KS; };
+// batch tiles per CTA and K-splits for an operand of KT k-tiles
+static inline WarpShape warp_shape(int N, int KT) {
+  WarpShape w;
+  w.NT = N >= 32 ? 4 : (N + 7) / 8;
+  if (w.NT < 1) w.NT = 1;
+  int ks = (KT + 9) / 10;
+  const int cap = kMaxWarps / w.NT;
+  if (ks > cap) ks = cap;
+  if (ks > KT) ks = KT;
+  if (ks < 1) ks = 1;
+  w.KS = ks;
+  return w;
+}
+
+// ------------------------------------------------------------------------------------------
 // forward LSTM cell step
 // ------------------------------------------------------------------------------------------
-// grid (UG, ceil(B/32), ndir), 4 warps; warp w owns batch rows 32*blockIdx.y + 8w .. +7 and the
-// 8 hidden units of unit-group blockIdx.x (all four gates -> the cell update is thread-local).
-__global__ void __launch_bounds__(128) cell_fwd_kernel(CellFwdParams p) {
+// grid (UG, ceil(B/(8*NT)), ndir); a CTA owns the 8 hidden units of unit-group blockIdx.x (all
+// four gates -> the cell update is thread-local) for 8*NT batch rows.
+__global__ void __launch_bounds__(512) cell_fwd_kernel(CellFwdParams p) {
+  __shared__ float red[(kMaxWarps - 1) * 32 * 8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, tig = lane & 3;
+  const int nt = warp % p.NT, ks = warp / p.NT;
   const int ug = blockIdx.x;
-  const int n0 = (blockIdx.y * 4 + warp) * 8;
+  const int n0 = (blockIdx.y * p.NT + nt) * 8;
   const int dir = blockIdx.z;
-  if (n0 >= p.B) return;
   const int t = (dir == 0) ? p.step : (p.T - 1 - p.step);
   const int nb = min(n0 + g, p.B - 1);  // clamp the operand row; results of rows >= B are dropped
 
-  float acc[2][2][4];
+  float acc[2][4];
 #pragma unroll
   for (int a = 0; a < 2; ++a)
 #pragma unroll
-    for (int b = 0; b < 2; ++b)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
+    for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
 
-  if (p.KT1 > 0) {
-    const uint4* a_if = reinterpret_cast<const uint4*>(p.a1 + dir * p.a_dir) +
-                        static_cast<int64_t>(2 * ug) * p.KT1 * 32 + lane;
-    const uint4* a_go = a_if + static_cast<int64_t>(p.KT1) * 32;
-    const __nv_bfloat16* vin = p.v1 + dir * p.v1_dir + nb * p.v1_ld + 2 * tig;
-#pragma unroll 4
-    for (int kt = 0; kt < p.KT1; ++kt) {
-      const uint4 aif = __ldg(a_if + kt * 32);
-      const uint4 ago = __ldg(a_go + kt * 32);
-      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(vin + 16 * kt);
-      const uint32_t b1 = *reinterpret_cast<const uint32_t*>(vin + 16 * kt + 8);
-      const uint32_t A0[4] = {aif.x, aif.y, aif.z, aif.w};
-      const uint32_t A1[4] = {ago.x, ago.y, ago.z, ago.w};
-      mma_bf16_16816(acc[0][kt & 1], A0, b0, b1);
-      mma_bf16_16816(acc[1][kt & 1], A1, b0, b1);
+  // the two operand segments form one K range of KT1 + KT2 tiles, split evenly over the KS warps
+  const int KT = p.KT1 + p.KT2;
+  const int per = (KT + p.KS - 1) / p.KS;
+  const int kb = ks * per, ke = min(KT, kb + per);
+  if (n0 < p.B) {
+    if (kb < p.KT1) {
+      const uint4* a = reinterpret_cast<const uint4*>(p.a1 + dir * p.a_dir) + static_cast<int64_t>(2 * ug) * p.KT1 * 32 + lane;
+      mma_span<2>(a, static_cast<int64_t>(p.KT1) * 32, p.v1, 0, dir * p.v1_dir + nb * p.v1_ld + 2 * tig, kb,
+                  min(ke, p.KT1), acc);
+    }
+    if (ke > p.KT1) {
+      const uint4* a = reinterpret_cast<const uint4*>(p.a2) + static_cast<int64_t>(2 * ug) * p.KT2 * 32 + lane;
+      mma_span<2>(a, static_cast<int64_t>(p.KT2) * 32, p.v2, 0, nb * p.v2_ld + 2 * tig, max(kb, p.KT1) - p.KT1,
+                  ke - p.KT1, acc);
     }
   }
-  if (p.KT2 > 0) {
-    const uint4* a_if = reinterpret_cast<const uint4*>(p.a2) + static_cast<int64_t>(2 * ug) * p.KT2 * 32 + lane;
-    const uint4* a_go = a_if + static_cast<int64_t>(p.KT2) * 32;
-    const __nv_bfloat16* vin = p.v2 + nb * p.v2_ld + 2 * tig;
-#pragma unroll 4
-    for (int kt = 0; kt < p.KT2; ++kt) {
-      const uint4 aif = __ldg(a_if + kt * 32);
-      const uint4 ago = __ldg(a_go + kt * 32);
-      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(vin + 16 * kt);
-      const uint32_t b1 = *reinterpret_cast<const uint32_t*>(vin + 16 * kt + 8);
-      const uint32_t A0[4] = {aif.x, aif.y, aif.z, aif.w};
-      const uint32_t A1[4] = {ago.x, ago.y, ago.z, ago.w};
-      mma_bf16_16816(acc[0][kt & 1], A0, b0, b1);
-      mma_bf16_16816(acc[1][kt & 1], A1, b0, b1);
-    }
-  }
+  if (!ksplit_reduce<2>(acc, red, nt, ks, p.NT, p.KS, lane)) return;
   const int u = 8 * ug + g;
-  if (u >= p.H) return;
+  if (u >= p.H || n0 >= p.B) return;
 #pragma unroll
   for (int e = 0; e < 2; ++e) {
     const int n = n0 + 2 * tig + e;
@@ -159,10 +220,10 @@ __global__ void __launch_bounds__(128) cell_fwd_kernel(CellFwdParams p) {
     __nv_bfloat16 y_val = __float2bfloat16(0.f);
     if (active) {
       const float* xp = p.xproj + n * p.xp_ld_b + t * p.xp_ld_t + dir * p.xp_ld_dir + u;
-      const float gi = acc[0][0][e] + acc[0][1][e] + xp[0];
-      const float gf = acc[0][0][2 + e] + acc[0][1][2 + e] + xp[p.H];
-      const float gg = acc[1][0][e] + acc[1][1][e] + xp[2 * p.H];
-      const float go = acc[1][0][2 + e] + acc[1][1][2 + e] + xp[3 * p.H];
+      const float gi = acc[0][e] + xp[0];
+      const float gf = acc[0][2 + e] + xp[p.H];
+      const float gg = acc[1][e] + xp[2 * p.H];
+      const float go = acc[1][2 + e] + xp[3 * p.H];
       const float i = sigmoid_acc(gi), f = sigmoid_acc(gf), gc = tanh_acc(gg), o = sigmoid_acc(go);
       const float c = f * p.c_state[st] + i * gc;
       const float h = o * tanh_acc(c);
@@ -189,49 +250,43 @@ __global__ void __launch_bounds__(128) cell_fwd_kernel(CellFwdParams p) {
   }
 }
 
-int launch_cell_fwd(const CellFwdParams& p, cudaStream_t stream) {
-  dim3 grid(p.UG, (p.B + 31) / 32, p.ndir);
-  cell_fwd_kernel<<<grid, 128, 0, stream>>>(p);
+int launch_cell_fwd(CellFwdParams& p, cudaStream_t stream) {
+  const WarpShape w = warp_shape(p.B, p.KT1 + p.KT2);
+  p.NT = w.NT; p.KS = w.KS;
+  dim3 grid(p.UG, (p.B + 8 * w.NT - 1) / (8 * w.NT), p.ndir);
+  cell_fwd_kernel<<<grid, 32 * w.NT * w.KS, 0, stream>>>(p); ++g_launches;
   return 0;
 }
 
 // ------------------------------------------------------------------------------------------
 // backward LSTM cell step
 // ------------------------------------------------------------------------------------------
-// grid (ceil(H/16), ceil(B/32), ndir), 4 warps. dh[n, j] = sum_k A[j, k] v[n, k] + dy + extra;
+// grid (ceil(H/16), ceil(B/(8*NT)), ndir). dh[n, j] = sum_k A[j, k] v[n, k] + dy + extra;
 // A = W_hh^T (encoder/LM; v = gate gradients of the step that consumed h_t) or mlp_dec^T
 // (decoder; v = gradient of the attention's decoder-state projection).
-__global__ void __launch_bounds__(128) cell_bwd_kernel(CellBwdParams p) {
+__global__ void __launch_bounds__(512) cell_bwd_kernel(CellBwdParams p) {
+  __shared__ float red[(kMaxWarps - 1) * 32 * 4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, tig = lane & 3;
+  const int nt = warp % p.NT, ks = warp / p.NT;
   const int jt = blockIdx.x;
-  const int n0 = (blockIdx.y * 4 + warp) * 8;
+  const int n0 = (blockIdx.y * p.NT + nt) * 8;
   const int dir = blockIdx.z;
-  if (n0 >= p.B) return;
   // BPTT order: forward direction walks t = T-1..0, reverse direction walks t = 0..T-1.
   const int t = (dir == 0) ? (p.T - 1 - p.step) : p.step;
 
-  float acc[4][4];
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
-
-  if (p.v != nullptr && p.KT > 0) {
-    const uint4* aT = reinterpret_cast<const uint4*>(p.a_pk + dir * p.a_dir) +
-                      static_cast<int64_t>(jt) * p.KT * 32 + lane;
+  float acc[1][4] = {{0.f, 0.f, 0.f, 0.f}};
+  if (p.v != nullptr && p.KT > 0 && n0 < p.B) {
+    const uint4* aT = reinterpret_cast<const uint4*>(p.a_pk + dir * p.a_dir) + static_cast<int64_t>(jt) * p.KT * 32 + lane;
     const int nb = min(n0 + g, p.B - 1);
     const int t_src = (dir == 0) ? p.v_t_fwd : p.v_t_rev;  // the step that consumed h_t
     const int64_t off = dir * p.v_dir + nb * p.v_ld + t_src * p.v_ld_t + 2 * tig;
-#pragma unroll 4
-    for (int kt = 0; kt < p.KT; ++kt) {
-      const uint4 a = __ldg(aT + kt * 32);
-      const uint32_t b0 = ldb_frag(p.v, p.v_f32, off + 16 * kt);
-      const uint32_t b1 = ldb_frag(p.v, p.v_f32, off + 16 * kt + 8);
-      const uint32_t A[4] = {a.x, a.y, a.z, a.w};
-      mma_bf16_16816(acc[kt & 3], A, b0, b1);
-    }
+    const int per = (p.KT + p.KS - 1) / p.KS;
+    const int kb = ks * per, ke = min(p.KT, kb + per);
+    mma_span<1>(aT, 0, p.v, p.v_f32, off, kb, ke, acc);
   }
+  if (!ksplit_reduce<1>(acc, red, nt, ks, p.NT, p.KS, lane)) return;
+  if (n0 >= p.B) return;
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
     const int j = 16 * jt + g + 8 * (e >> 1);
@@ -255,7 +310,7 @@ __global__ void __launch_bounds__(128) cell_bwd_kernel(CellBwdParams p) {
     float c_prev = 0.f;
     if (dir == 0) { if (t > 0) c_prev = p.c_save[sv - p.H]; }
     else          { if (t + 1 < len) c_prev = p.c_save[sv + p.H]; }
-    float dh = acc[0][e] + acc[1][e] + acc[2][e] + acc[3][e];
+    float dh = acc[0][e];
     if (p.dy) {
       const float* dyp = p.dy + n * p.dy_ld_b + t * p.dy_ld_t + static_cast<int64_t>(dir) * p.H + j;
       dh += dyp[0];
@@ -272,42 +327,40 @@ __global__ void __launch_bounds__(128) cell_bwd_kernel(CellBwdParams p) {
   }
 }
 
-int launch_cell_bwd(const CellBwdParams& p, cudaStream_t stream) {
-  dim3 grid((p.H + 15) / 16, (p.B + 31) / 32, p.ndir);
-  cell_bwd_kernel<<<grid, 128, 0, stream>>>(p);
+int launch_cell_bwd(CellBwdParams& p, cudaStream_t stream) {
+  const WarpShape w = warp_shape(p.B, p.v ? p.KT : 1);
+  p.NT = w.NT; p.KS = w.KS;
+  dim3 grid((p.H + 15) / 16, (p.B + 8 * w.NT - 1) / (8 * w.NT), p.ndir);
+  cell_bwd_kernel<<<grid, 32 * w.NT * w.KS, 0, stream>>>(p); ++g_launches;
   return 0;
 }
 
 // ------------------------------------------------------------------------------------------
 // small batched mat-vec: out[n, m] = sum_k A[m, k] * v[n, k] (+ bias[m]) (+ add[n, m])
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) smallmm_kernel(SmallMMParams p) {
+__global__ void __launch_bounds__(512) smallmm_kernel(SmallMMParams p) {
+  __shared__ float red[(kMaxWarps - 1) * 32 * 4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, tig = lane & 3;
+  const int nt = warp % p.NT, ks = warp / p.NT;
   const int mt = blockIdx.x;
-  const int n0 = (blockIdx.y * 4 + warp) * 8;
-  if (n0 >= p.N) return;
-  const uint4* a = reinterpret_cast<const uint4*>(p.a_pk) + static_cast<int64_t>(mt) * p.KT * 32 + lane;
-  const int64_t off = static_cast<int64_t>(min(n0 + g, p.N - 1)) * p.ldv + 2 * tig;
-  float acc[4][4];
-#pragma unroll
-  for (int x = 0; x < 4; ++x)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) acc[x][c] = 0.f;
-#pragma unroll 4
-  for (int kt = 0; kt < p.KT; ++kt) {
-    const uint4 av = __ldg(a + kt * 32);
-    const uint32_t b0 = ldb_frag(p.v, p.v_f32, off + 16 * kt);
-    const uint32_t b1 = ldb_frag(p.v, p.v_f32, off + 16 * kt + 8);
-    const uint32_t A[4] = {av.x, av.y, av.z, av.w};
-    mma_bf16_16816(acc[kt & 3], A, b0, b1);
+  const int n0 = (blockIdx.y * p.NT + nt) * 8;
+  float acc[1][4] = {{0.f, 0.f, 0.f, 0.f}};
+  if (n0 < p.N) {
+    const uint4* a = reinterpret_cast<const uint4*>(p.a_pk) + static_cast<int64_t>(mt) * p.KT * 32 + lane;
+    const int64_t off = static_cast<int64_t>(min(n0 + g, p.N - 1)) * p.ldv + 2 * tig;
+    const int per = (p.KT + p.KS - 1) / p.KS;
+    const int kb = ks * per, ke = min(p.KT, kb + per);
+    mma_span<1>(a, 0, p.v, p.v_f32, off, kb, ke, acc);
   }
+  if (!ksplit_reduce<1>(acc, red, nt, ks, p.NT, p.KS, lane)) return;
+  if (n0 >= p.N) return;
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
     const int m = 16 * mt + g + 8 * (e >> 1);
     const int n = n0 + 2 * tig + (e & 1);
     if (m >= p.M || n >= p.N) continue;
-    float r = acc[0][e] + acc[1][e] + acc[2][e] + acc[3][e];
+    float r = acc[0][e];
     if (p.bias) r += p.bias[m];
     if (p.add) r += p.add[n * p.ld_add + m];
     if (p.out_f32) p.out_f32[n * p.ld_out + m] = r;
@@ -323,8 +376,10 @@ int smallmm(const uint32_t* a_pk, int M, int K, const void* v, int v_f32, int64_
   p.a_pk = a_pk; p.v = v; p.v_f32 = v_f32; p.ldv = ldv; p.bias = bias; p.add = add; p.ld_add = ld_add;
   p.out_f32 = out_f32; p.ld_out = ld_out; p.out_bf16 = out_bf16; p.ld_outb = ld_outb;
   p.M = M; p.N = N; p.MT = (M + 15) / 16; p.KT = (K + 15) / 16;
-  dim3 grid(p.MT, (N + 31) / 32);
-  smallmm_kernel<<<grid, 128, 0, stream>>>(p);
+  const WarpShape w = warp_shape(N, p.KT);
+  p.NT = w.NT; p.KS = w.KS;
+  dim3 grid(p.MT, (N + 8 * w.NT - 1) / (8 * w.NT));
+  smallmm_kernel<<<grid, 32 * w.NT * w.KS, 0, stream>>>(p); ++g_launches;
   return 0;
 }
 
@@ -385,6 +440,9 @@ int las_lstm_seq_fwd(const float* xproj, const void* whh_pk, const int32_t* lens
   LAS_REQUIRE(H % 8 == 0, "lstm: hidden size %d must be a multiple of 8", H);
   LAS_REQUIRE(ndir == 1 || ndir == 2, "lstm: ndir must be 1 or 2");
   if (B == 0 || T == 0) return 0;
+  if (persist_supported(H))   // one cluster-persistent launch for the whole sequence (blstm_persistent.cu)
+    return persist_lstm_fwd(xproj, whh_pk, lens, B, T, H, ndir, y, y_ld_b, y_ld_t, rep_row, hprev, hp_ld_b,
+                            hp_ld_t, gates_save, c_save, stream);
   const int KT = (H + 15) / 16;
   const int64_t Kp = KT * 16 + 16;
   CellFwdParams p = {};
@@ -417,14 +475,20 @@ int las_lstm_seq_fwd(const float* xproj, const void* whh_pk, const int32_t* lens
 
 // BPTT through one LSTM layer. dy f32 indexed like y (may be NULL); dG bf16 out,
 // dG[b*dg_ld_b + t*dg_ld_t + dir*4H + gate*H + u] (zeros past the length); whhT_pk = fragments of
-// W_hh^T per direction (las_pack_afrag mode 0, transposed). ws: f32 [ndir, B, H] scratch.
+// W_hh^T per direction: whhT_layout 0 = las_pack_afrag mode 0, transposed (per-timestep kernels);
+// 1 = las_pack_whhT_owner (cluster-persistent kernel). ws: f32 [ndir, B, H] scratch.
 int las_lstm_seq_bwd(const float* dy, int64_t dy_ld_b, int64_t dy_ld_t, int rep_row,
-                     const void* whhT_pk, const int32_t* lens, int B, int T, int H, int ndir,
-                     const void* gates_save, const float* c_save, void* dG, int64_t dg_ld_b,
+                     const void* whhT_pk, int whhT_layout, const int32_t* lens, int B, int T, int H,
+                     int ndir, const void* gates_save, const float* c_save, void* dG, int64_t dg_ld_b,
                      int64_t dg_ld_t, void* ws, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   LAS_REQUIRE(H % 8 == 0, "lstm: hidden size %d must be a multiple of 8", H);
   if (B == 0 || T == 0) return 0;
+  if (whhT_layout == 1) {
+    LAS_REQUIRE(persist_supported(H), "lstm bwd: owner-ordered weights given but H=%d has no persistent kernel", H);
+    return persist_lstm_bwd(dy, dy_ld_b, dy_ld_t, rep_row, whhT_pk, lens, B, T, H, ndir, gates_save, c_save, dG,
+                            dg_ld_b, dg_ld_t, stream);
+  }
   CellBwdParams p = {};
   p.dy = dy; p.dy_ld_b = dy_ld_b; p.dy_ld_t = dy_ld_t; p.rep_row = rep_row;
   p.dh_extra = nullptr; p.dhx_ld = 0;

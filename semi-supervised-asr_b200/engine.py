@@ -1,0 +1,119 @@
+"""Train-step engines behind `Solver.sup_train_one_epoch` (solver.py:360-393): forward, loss =
+-mean(log_probs), backward, clip_grad_norm_(max_grad_norm), Adam(amsgrad) step — with the whole
+step (several thousand per-timestep launches) captured into one CUDA graph per batch geometry
+(B, Tmax, Lmax) and replayed.
+
+Data parallelism (one process per GPU): every rank runs the same step on its shard; the flat
+gradient buffer is summed with ONE NCCL all-reduce between backward and the optimiser, and the
+update uses grad_scale = 1/world_size (DDP averaging). There is no other exchange on this path.
+"""
+import numpy as np
+import torch
+
+from . import functional as Fn
+
+
+def build_targets(ys, bos, eos, pad):
+    """model.py:301-306: ys_in = [BOS, y], ys_out = [y, EOS], both EOS-padded; plus one guard
+    column (PAD) so that every per-step buffer has L+1 rows. Returns (ys_in [B, L+1], ys_out [B, L])."""
+    ys_host = [y.detach().cpu().numpy().astype(np.int64) if torch.is_tensor(y) else np.asarray(y, np.int64)
+               for y in ys]
+    B = len(ys_host)
+    L = max(len(y) for y in ys_host) + 1
+    ys_in = np.full((B, L + 1), eos, dtype=np.int64)
+    ys_out = np.full((B, L), eos, dtype=np.int64)
+    for b, y in enumerate(ys_host):
+        ys_in[b, 0] = bos
+        ys_in[b, 1:1 + len(y)] = y
+        ys_out[b, :len(y)] = y
+    ys_in[:, L] = pad
+    return ys_in, ys_out
+
+
+class _Static:
+    """Device + pinned-host staging buffers of one batch geometry, and its captured graph."""
+
+    def __init__(self, B, T, D, L, dev):
+        self.x = torch.zeros(B, T, D, device=dev, dtype=torch.float32)
+        self.lens = torch.zeros(B, device=dev, dtype=torch.int32)
+        self.ys_in = torch.zeros(B, L + 1, device=dev, dtype=torch.int64)
+        self.ys_out = torch.zeros(B, L, device=dev, dtype=torch.int64)
+        self.h_lens = torch.zeros(B, dtype=torch.int32).pin_memory()
+        self.h_ys_in = torch.zeros(B, L + 1, dtype=torch.int64).pin_memory()
+        self.h_ys_out = torch.zeros(B, L, dtype=torch.int64).pin_memory()
+        self.graph = None
+        self.loss = None
+        self.norm = None
+        self.seen = 0
+
+
+class SupervisedTrainer:
+    def __init__(self, model, optimizer, max_grad_norm=5.0, use_graph=True, process_group=None):
+        self.model = model
+        self.opt = optimizer
+        self.max_grad_norm = max_grad_norm
+        self.use_graph = use_graph
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        self.static = {}
+        self.launches_per_step = None
+
+    # ---- the step body: everything below runs on the current stream, no host sync
+    def _body(self, st, L):
+        m = self.model
+        enc = m.encoder.enc2
+        enc_h = enc.forward_dev(st.x, st.lens)
+        enc_lens = enc.out_lens_dev(st.lens)
+        _, logp, _, _ = m.decoder.forward_dev(enc_h, enc_lens, st.ys_in, st.ys_out, L, 0)
+        loss = -torch.mean(logp)                                   # solver.py:377 (ALL B x (Lmax+1) positions)
+        self.opt.zero_grad()
+        loss.backward()
+        if self.world > 1:
+            torch.distributed.all_reduce(self.opt.flat_grad, group=self.pg)
+        norm = self.opt.clip_and_step(self.max_grad_norm, grad_scale=1.0 / self.world)
+        return loss.detach(), norm
+
+    def stage(self, xs, ilens, ys):
+        """Host -> device copies of one batch into the static buffers of its geometry."""
+        m = self.model
+        dev = next(m.parameters()).device
+        host_lens = [int(l) for l in (ilens.tolist() if torch.is_tensor(ilens) else ilens)]
+        T = max(host_lens)
+        ys_in, ys_out = build_targets(ys, m.decoder.bos, m.decoder.eos, m.decoder.pad)
+        B, L = ys_out.shape
+        key = (B, T, xs.shape[2], L)
+        st = self.static.get(key)
+        if st is None:
+            st = self.static[key] = _Static(B, T, xs.shape[2], L, dev)
+        st.x.copy_(xs[:, :T], non_blocking=True)
+        st.h_lens.copy_(torch.tensor(host_lens, dtype=torch.int32))
+        st.h_ys_in.copy_(torch.from_numpy(ys_in))
+        st.h_ys_out.copy_(torch.from_numpy(ys_out))
+        st.lens.copy_(st.h_lens, non_blocking=True)
+        st.ys_in.copy_(st.h_ys_in, non_blocking=True)
+        st.ys_out.copy_(st.h_ys_out, non_blocking=True)
+        return key
+
+    def run(self, key):
+        """One train step on the batch currently staged for `key`. Returns (loss, grad_norm) device tensors."""
+        st = self.static[key]
+        L = key[3]
+        self.model.train()
+        if not self.use_graph:
+            return self._body(st, L)
+        if st.graph is None:
+            if st.seen == 0:                       # first sight of a geometry: eager (also warms lazy init)
+                st.seen = 1
+                return self._body(st, L)
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g):
+                st.loss, st.norm = self._body(st, L)
+            st.graph = g
+        st.graph.replay()
+        return st.loss, st.norm
+
+    def step(self, xs, ilens, ys):
+        return self.run(self.stage(xs, ilens, ys))

@@ -12,7 +12,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import DecArgs, call, ptr
+from ._lib import DecArgs, call, ptr  # noqa: F401  (re-exported for the modules)
 
 BF16 = torch.bfloat16
 
@@ -68,6 +68,17 @@ def pack_afrag(W, mode, H=0, transposed=False, col_offset=0, cols=None):
     out = torch.empty(nbytes // 4, device=W.device, dtype=torch.int32)
     call("las_pack_afrag", ptr(W), W.stride(0), rows_arg, cols_arg, col_offset, mode, H, int(transposed), ptr(out))
     return out
+
+
+def pack_whhT(w_hh):
+    """W_hh^T fragments for the BPTT kernels. Returns (packed, layout): layout 1 = owner-ordered for
+    the cluster-persistent kernel when it serves this hidden size, 0 = plain transposed."""
+    H = w_hh.shape[1]
+    if _lib.lib().las_lstm_persistent_geometry(H, None, None):
+        out = torch.empty(_lib.lib().las_whhT_owner_bytes(H) // 4, device=w_hh.device, dtype=torch.int32)
+        call("las_pack_whhT_owner", ptr(w_hh.contiguous()), H, ptr(out))
+        return out, 1
+    return pack_afrag(w_hh, 0, transposed=True), 0
 
 
 def colsum(x, cols, out=None, ld=None, rows=None):
@@ -159,10 +170,12 @@ class EncoderFn(torch.autograd.Function):
             d_proj_b = colsum(dz, Ho)
             dy = gemm(dz, Ho, 0, wp, Kp, 1, n, Kp, Ho)                               # f32 [B, Tp, 2H] view
             # recurrence
-            whhT = torch.cat([pack_afrag(w_hh, 0, transposed=True), pack_afrag(w_hh_r, 0, transposed=True)])
+            wf, layout = pack_whhT(w_hh)
+            wr, _ = pack_whhT(w_hh_r)
+            whhT = torch.cat([wf, wr])
             dG = torch.empty(B * T, 8 * H, device=dev, dtype=BF16)
             ws = torch.empty(2 * B * H, device=dev, dtype=torch.float32)
-            call("las_lstm_seq_bwd", ptr(dy), Tp * 2 * H, 2 * H, rep, ptr(whhT), ptr(lens_i), B, T, H, 2,
+            call("las_lstm_seq_bwd", ptr(dy), Tp * 2 * H, 2 * H, rep, ptr(whhT), layout, ptr(lens_i), B, T, H, 2,
                  ptr(gates), ptr(csave), ptr(dG), T * 8 * H, 8 * H, ptr(ws))
             del dy
             # weight gradients as dense contractions over all (b, t)
@@ -451,10 +464,10 @@ class LMFn(torch.autograd.Function):
         for l in reversed(range(n_layers)):
             xin, w_bf, hprev, gates, csave, Dp, H = saved[l]
             w_ih, w_hh, b_ih, b_hh = wts[1 + 4 * l:5 + 4 * l]
-            whhT = pack_afrag(w_hh, 0, transposed=True)
+            whhT, layout = pack_whhT(w_hh)
             dG = torch.empty(n, 4 * H, device=dev, dtype=BF16)
             ws = torch.empty(B * H, device=dev, dtype=torch.float32)
-            call("las_lstm_seq_bwd", ptr(dy), Lm * H, H, 0, ptr(whhT), ptr(lens), B, Lm, H, 1, ptr(gates), ptr(csave),
+            call("las_lstm_seq_bwd", ptr(dy), Lm * H, H, 0, ptr(whhT), layout, ptr(lens), B, Lm, H, 1, ptr(gates), ptr(csave),
                  ptr(dG), Lm * 4 * H, 4 * H, ptr(ws))
             d_w_ih = gemm(dG, 4 * H, 1, xin, Dp, 1, 4 * H, Dp, n)[:, :w_ih.shape[1]]
             d_w_hh = gemm(dG, 4 * H, 1, hprev, H, 1, 4 * H, H, n)

@@ -46,13 +46,28 @@ class pBLSTM(torch.nn.Module):
         T = max(host_lens)
         xpad = xpad[:, :T].contiguous()                      # pad_packed_sequence trims to the longest
         lens_dev = Fn.lens_tensor(host_lens, xpad.device)
-        if self.training and self.dropout_rate > 0:
-            raise NotImplementedError("dropout inside the fused encoder is not wired yet; use dropout_rate=0")
-        out = Fn.EncoderFn.apply(xpad, lens_dev, tuple(int(s) for s in self.subsample), *self._weights())
+        out = self.forward_dev(xpad, lens_dev)
         for sub in self.subsample:                            # model.py:92
             if sub > 1:
                 host_lens = [(l + 1) // sub for l in host_lens]
         return out, host_lens
+
+    def forward_dev(self, xpad, lens_dev):
+        """Device-resident variant (no host work; CUDA-graph capturable): x f32 [B, T, D] with T the
+        longest length, lens int32 [B] on the device. Returns enc_h only."""
+        if self.training and self.dropout_rate > 0:
+            raise NotImplementedError("dropout inside the fused encoder is not wired yet; use dropout_rate=0")
+        return Fn.EncoderFn.apply(xpad, lens_dev, tuple(int(s) for s in self.subsample), *self._weights())
+
+    def out_lens_dev(self, lens_dev):
+        """(len + 1) // sub per pyramid level, on the device (model.py:92)."""
+        cur = lens_dev
+        for sub in self.subsample:
+            if sub > 1:
+                nl = torch.empty_like(cur)
+                Fn.call("las_pyramid_lens", Fn.ptr(cur), cur.numel(), int(sub), Fn.ptr(nl))
+                cur = nl
+        return cur
 
 
 class Encoder(torch.nn.Module):
@@ -133,8 +148,6 @@ class Decoder(torch.nn.Module):
                 scaling=1.0, label_smoothing=True):
         if sample:
             raise NotImplementedError("Categorical sampling (model.py:350) is not used by any Solver path")
-        if self.training and self.dropout_rate > 0:
-            raise NotImplementedError("dropout inside the fused decoder is not wired yet; use dropout_rate=0")
         dev = enc_pad.device
         B = enc_pad.size(0)
         self.attention.reset()
@@ -160,6 +173,14 @@ class Decoder(torch.nn.Module):
             L = int(max_dec_timesteps)
             ys_in_dev, ys_out_dev = None, None
             mode = 2 if smooth else 1
+        return self.forward_dev(enc_pad, enc_lens_dev, ys_in_dev, ys_out_dev, L, mode, scaling, label_smoothing)
+
+    def forward_dev(self, enc_pad, enc_lens_dev, ys_in_dev, ys_out_dev, L, mode, scaling=1.0, label_smoothing=True):
+        """Device-resident variant (CUDA-graph capturable). ys_in_dev int64 [B, L+1] = [BOS, y, EOS.., PAD],
+        ys_out_dev int64 [B, L] = [y, EOS..]; mode 0 teacher forcing, 1 greedy, 2 smooth free-run."""
+        if self.training and self.dropout_rate > 0:
+            raise NotImplementedError("dropout inside the fused decoder is not wired yet; use dropout_rate=0")
+        dev = enc_pad.device
         logits_alloc, ws_alloc, pred = Fn.DecoderFn.apply(
             enc_pad.float().contiguous(), enc_lens_dev, ys_in_dev, L, mode, float(scaling), 2.0,
             self.attention.conv_kernel_size, self.bos, *self._weights())

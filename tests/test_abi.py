@@ -16,7 +16,7 @@ HEADER = os.path.join(ROOT, "include", "las_b200.h")
 def declared_functions():
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(las_[a-z0-9_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(las_[A-Za-z0-9_]+)\s*\(", src)))
 
 
 def test_library_exports_every_declared_symbol():
