@@ -121,6 +121,8 @@ int las_lstm_persistent_geometry(int H, int* cs, int* upc);
 /* switch between the cluster-persistent and the per-timestep kernels (returns the previous setting;
  * default on, or off with LAS_DISABLE_PERSISTENT=1 in the environment) */
 int las_set_persistent(int on);
+/* development aid: device buffer of 128 int64 receiving a clock64() phase trace of the persistent kernels */
+int las_set_debug_buffer(void* dev_int64_x128);
 int64_t las_whhT_owner_bytes(int H);
 int las_pack_whhT_owner(const float* W_hh, int H, void* out, void* stream);
 /* lens_out[b] = (lens_in[b] + 1) / sub   (model.py:92) */

@@ -58,6 +58,7 @@ SIGNATURES = {
     "las_lstm_seq_bwd": (c_int, [P, L, L, I, P, I, P, I, I, I, I, P, P, P, L, L, P, P]),
     "las_lstm_persistent_geometry": (c_int, [I, P, P]),
     "las_set_persistent": (c_int, [I]),
+    "las_set_debug_buffer": (c_int, [P]),
     "las_whhT_owner_bytes": (c_int64, [I]),
     "las_pack_whhT_owner": (c_int, [P, I, P, P]),
     "las_pyramid_lens": (c_int, [P, I, I, P, P]),

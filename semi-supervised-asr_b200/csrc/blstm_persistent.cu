@@ -29,6 +29,7 @@ namespace {
 constexpr int kMaxUGC = 5;   // unit groups (8 hidden units) per CTA
 constexpr int kMaxKTW = 10;  // k-tiles (16) per warp in the forward kernel
 constexpr int kNB = 8;       // utterances per cluster (one MMA n-tile)
+constexpr int kPF = 8;       // timesteps of global-memory prefetch distance (cp.async ring in shared memory)
 
 struct Geom {
   int UG, CS, UGC, KT, KS, KTW, JT, MTW;
@@ -62,16 +63,31 @@ __device__ __forceinline__ void st_async_v2(uint32_t addr, uint32_t v0, uint32_t
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];"
                ::"r"(addr), "r"(v0), "r"(v1), "r"(mbar) : "memory");
 }
+// Asynchronous global->shared copies (LDGSTS): the per-timestep operands are prefetched kPF steps
+// ahead without occupying registers or the load scoreboard (a register ring made every branch of
+// the step loop wait for DRAM: profiles/r01_persist_v2_stalls.txt).
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 __device__ __forceinline__ uint32_t movmatrix_trans(uint32_t a) {
   uint32_t d;
   asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
   return d;
 }
+// The payload lands in THIS CTA's shared memory together with its complete_tx (st.async), so the
+// default (CTA-scope) wait is enough; a cluster-scope acquire makes ptxas emit CCTL.IVALL (L1
+// invalidate) after every wait, which also drains the global prefetch loads: 37 % of all stall
+// samples in the first version of this kernel (profiles/r01_persist_v1_stalls.txt).
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
@@ -97,6 +113,7 @@ struct FwdP {
   __half* gates_save; float* c_save;
   int B, T, H, rep_row;
   int UG, UGC, KS, KTW, KT;
+  long long* dbg;              // optional clock64() trace of cluster (0,0,0) (las_set_debug_buffer)
 };
 
 // grid (CS, ceil(B/8), ndir), cluster (CS,1,1), block 32*UGC*KS. warp = ks*UGC + ugl.
@@ -105,6 +122,7 @@ __global__ void __launch_bounds__(320, 1) lstm_persist_fwd_kernel(FwdP p) {
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);                    // [2]
   uint32_t* hs = reinterpret_cast<uint32_t*>(smem + 16);                 // [2][KT][32][2]
   float* red = reinterpret_cast<float*>(smem + 16 + 2 * p.KT * 256);     // [UGC][32][8]
+  float* xring = red + p.UGC * 32 * 8;                                   // [kPF][UGC][32][8]
   cg::cluster_group cluster = cg::this_cluster();
   const uint32_t rank = cluster.block_rank(), CS = cluster.num_blocks();
   const int grp = blockIdx.y, dir = blockIdx.z;
@@ -151,30 +169,37 @@ __global__ void __launch_bounds__(320, 1) lstm_persist_fwd_kernel(FwdP p) {
   int n[2], len[2];
   float c_st[2] = {0.f, 0.f};
   __nv_bfloat16 h_st[2];
-  float xp[2][4];
 #pragma unroll
   for (int e = 0; e < 2; ++e) {
     n[e] = grp * kNB + 2 * tig + e;
     len[e] = (epi && n[e] < p.B) ? (p.lens ? p.lens[n[e]] : T) : 0;
     h_st[e] = __float2bfloat16(0.f);
   }
-  auto load_xp = [&](int s, float (&dst)[2][4]) {
-    const int t = (dir == 0) ? s : (T - 1 - s);
+  // xproj ring: slot s % kPF holds this lane's 2 x 4 gate pre-activations of step s (thread-private)
+  float* xslot = xring + (static_cast<int64_t>(ugl) * 32 + lane) * 8;
+  const int ring_stride = p.UGC * 32 * 8;
+  auto prefetch_xp = [&](int s) {
+    if (epi && s < T) {
+      const int t = (dir == 0) ? s : (T - 1 - s);
+      float* dst = xslot + (s % kPF) * ring_stride;
 #pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      if (epi && t < len[e]) {
-        const float* q = p.xproj + n[e] * p.xp_ld_b + t * p.xp_ld_t + static_cast<int64_t>(dir) * 4 * H + u;
+      for (int e = 0; e < 2; ++e) {
+        if (t < len[e]) {
+          const float* q = p.xproj + n[e] * p.xp_ld_b + t * p.xp_ld_t + static_cast<int64_t>(dir) * 4 * H + u;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) dst[e][k] = __ldg(q + k * H);
+          for (int k = 0; k < 4; ++k) cp_async<4>(dst + e * 4 + k, q + k * H);
+        }
       }
     }
+    cp_async_commit();
   };
-  load_xp(0, xp);
+  for (int i = 0; i < kPF; ++i) prefetch_xp(i);
 
+  const bool trace = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0;
+#define LAS_TRACE(slot) do { if (trace && s >= 64 && s < 72) p.dbg[(s - 64) * 8 + (slot)] = clock64(); } while (0)
   for (int s = 0; s < T; ++s) {
     const int t = (dir == 0) ? s : (T - 1 - s);
-    float xn[2][4];
-    if (s + 1 < T) load_xp(s + 1, xn);   // prefetch: DRAM latency hidden behind this step
+    LAS_TRACE(0);
 
     float acc[2][2][4];
 #pragma unroll
@@ -187,6 +212,7 @@ __global__ void __launch_bounds__(320, 1) lstm_persist_fwd_kernel(FwdP p) {
     if (s > 0) {
       const int buf = s & 1;
       mbar_wait_cluster(&full[buf], ((s - 1) >> 1) & 1);
+      LAS_TRACE(1);
       if (threadIdx.x == 0 && s + 2 < T) mbar_arrive_expect_tx(&full[buf], tx_bytes);  // re-arm for step s+2
       const uint2* hb = reinterpret_cast<const uint2*>(hs + buf * p.KT * 64) + lane;
 #pragma unroll
@@ -206,6 +232,7 @@ __global__ void __launch_bounds__(320, 1) lstm_persist_fwd_kernel(FwdP p) {
     for (int a = 0; a < 2; ++a)
 #pragma unroll
       for (int c = 0; c < 4; ++c) gsum[a][c] = acc[a][0][c] + acc[a][1][c];
+    LAS_TRACE(2);
     if (p.KS == 2) {
       float* r = red + (ugl * 32 + lane) * 8;
       if (ks == 1) {
@@ -222,7 +249,16 @@ __global__ void __launch_bounds__(320, 1) lstm_persist_fwd_kernel(FwdP p) {
           for (int c = 0; c < 4; ++c) gsum[a][c] += r[a * 4 + c];
       }
     }
+    LAS_TRACE(3);
+    cp_async_wait<kPF - 1>();   // this step's xproj values have landed in the ring
+    LAS_TRACE(4);
     if (epi) {
+      const float* xs = xslot + (s % kPF) * ring_stride;
+      float xp[2][4];
+#pragma unroll
+      for (int e = 0; e < 2; ++e)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) xp[e][k] = xs[e * 4 + k];
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const bool inb = n[e] < p.B;
@@ -253,6 +289,7 @@ __global__ void __launch_bounds__(320, 1) lstm_persist_fwd_kernel(FwdP p) {
         }
         if (inb && p.hprev) p.hprev[n[e] * p.hp_ld_b + t * p.hp_ld_t + static_cast<int64_t>(dir) * H + u] = h_old;
       }
+      LAS_TRACE(5);
       if (s + 1 < T) {
         // lane (unit g, utterances 2tig, 2tig+1) -> after the 8x8 transpose: (utterance g, units 2tig, 2tig+1)
         __nv_bfloat162 hv;
@@ -265,11 +302,11 @@ __global__ void __launch_bounds__(320, 1) lstm_persist_fwd_kernel(FwdP p) {
         for (uint32_t peer = 0; peer < CS; ++peer) st_async_b32(mapa_u32(dst, peer), w, mapa_u32(bar, peer));
       }
     }
-#pragma unroll
-    for (int e = 0; e < 2; ++e)
-#pragma unroll
-      for (int k = 0; k < 4; ++k) xp[e][k] = xn[e][k];
+    LAS_TRACE(6);
+    prefetch_xp(s + kPF);   // refill this ring slot: DRAM latency hidden behind kPF timesteps
+    LAS_TRACE(7);
   }
+#undef LAS_TRACE
   cluster.sync();   // nobody exits while remote stores may still target its shared memory
 }
 
@@ -281,6 +318,7 @@ struct BwdP {
   __nv_bfloat16* dG; int64_t dg_ld_b, dg_ld_t;
   int B, T, H, rep_row;
   int UGC, JT, MTW, CSn;
+  long long* dbg;
 };
 
 // grid (CS, ceil(B/8), ndir), cluster (CS,1,1), block 64*UGC (= 8 utterances x UPC units).
@@ -290,6 +328,7 @@ __global__ void __launch_bounds__(320, 1) lstm_persist_bwd_kernel(BwdP p) {
   uint64_t* pfull = reinterpret_cast<uint64_t*>(smem);                   // [2]
   float* part = reinterpret_cast<float*>(smem + 16);                     // [2][CS][UPC*8]
   uint32_t* dgs = reinterpret_cast<uint32_t*>(smem + 16 + 2 * p.CSn * UPC * 8 * 4);   // [KTC][32][2]
+  float* pring = reinterpret_cast<float*>(dgs + KTC * 64);                             // [kPF][threads][8]
   cg::cluster_group cluster = cg::this_cluster();
   const uint32_t rank = cluster.block_rank(), CS = cluster.num_blocks();
   const int grp = blockIdx.y, dir = blockIdx.z;
@@ -337,25 +376,36 @@ __global__ void __launch_bounds__(320, 1) lstm_persist_bwd_kernel(BwdP p) {
   const int len = own ? (p.lens ? p.lens[nb] : T) : 0;
   float dc_st = 0.f;
 
+  // operands of the gate-derivative math: thread-private cp.async ring, fetched kPF timesteps ahead
+  //   slot layout (8 floats): [0..1] gates (4 x f16), [2] c_t, [3] c_prev, [4] dy, [5] dy of the replicated row
+  float* pslot = pring + static_cast<int64_t>(threadIdx.x) * 8;
+  const int ring_stride = blockDim.x * 8;
+  auto prefetch = [&](int s) {
+    const int t = (dir == 0) ? (T - 1 - s) : s;
+    if (s < T && t < len) {
+      float* dst = pslot + (s % kPF) * ring_stride;
+      const int64_t sv = ((static_cast<int64_t>(dir) * p.B + nb) * T + t) * H + uo;
+      cp_async<8>(dst, reinterpret_cast<const uint2*>(p.gates_save) + sv);
+      cp_async<4>(dst + 2, p.c_save + sv);
+      if (dir == 0) { if (t > 0) cp_async<4>(dst + 3, p.c_save + sv - H); }
+      else          { if (t + 1 < len) cp_async<4>(dst + 3, p.c_save + sv + H); }
+      if (p.dy) {
+        const float* dyp = p.dy + nb * p.dy_ld_b + t * p.dy_ld_t + static_cast<int64_t>(dir) * H + uo;
+        cp_async<4>(dst + 4, dyp);
+        if (p.rep_row && t == T - 1) cp_async<4>(dst + 5, dyp + p.dy_ld_t);
+      }
+    }
+    cp_async_commit();
+  };
+  for (int i = 0; i < kPF; ++i) prefetch(i);
+
+  const bool trace = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0;
+#define LAS_TRACE(slot) do { if (trace && s >= 64 && s < 72) p.dbg[64 + (s - 64) * 8 + (slot)] = clock64(); } while (0)
   for (int s = 0; s < T; ++s) {
     const int t = (dir == 0) ? (T - 1 - s) : s;
     const bool active = t < len;
-    // operands of the gate-derivative math, fetched now and used after the exchange
-    uint2 gpk = make_uint2(0u, 0u);
-    float c_cur = 0.f, c_prev = 0.f, dyv = 0.f;
-    if (active) {
-      const int64_t sv = ((static_cast<int64_t>(dir) * p.B + nb) * T + t) * H + uo;
-      gpk = reinterpret_cast<const uint2*>(p.gates_save)[sv];
-      c_cur = p.c_save[sv];
-      if (dir == 0) { if (t > 0) c_prev = p.c_save[sv - H]; }
-      else          { if (t + 1 < len) c_prev = p.c_save[sv + H]; }
-      if (p.dy) {
-        const float* dyp = p.dy + nb * p.dy_ld_b + t * p.dy_ld_t + static_cast<int64_t>(dir) * H + uo;
-        dyv = dyp[0];
-        if (p.rep_row && t == T - 1) dyv += dyp[p.dy_ld_t];
-      }
-    }
-    float dh = dyv;
+    LAS_TRACE(0);
+    float dh = 0.f;
     if (s > 0) {
       const int buf = s & 1;
       // partial dh for this warp's unit tiles from this CTA's own gate gradients of the previous step
@@ -378,6 +428,7 @@ __global__ void __launch_bounds__(320, 1) lstm_persist_bwd_kernel(BwdP p) {
           }
         }
       }
+      LAS_TRACE(1);
       // scatter the partial sums to the CTAs that own the units
       const uint32_t part_base = smem_u32(part + (static_cast<int64_t>(buf) * p.CSn + rank) * UPC * 8);
       const uint32_t bar = smem_u32(&pfull[buf]);
@@ -399,14 +450,28 @@ __global__ void __launch_bounds__(320, 1) lstm_persist_bwd_kernel(BwdP p) {
           }
         }
       }
+      LAS_TRACE(2);
       mbar_wait_cluster(&pfull[buf], ((s - 1) >> 1) & 1);
+      LAS_TRACE(3);
       if (threadIdx.x == 0 && s + 2 < T) mbar_arrive_expect_tx(&pfull[buf], tx_bytes);
       const float* pp = part + static_cast<int64_t>(buf) * p.CSn * UPC * 8 + threadIdx.x;
       for (uint32_t src = 0; src < CS; ++src) dh += pp[src * UPC * 8];
     }
     // gate derivatives (same math as cell_bwd_kernel)
     float d4[4] = {0.f, 0.f, 0.f, 0.f};
+    LAS_TRACE(4);
+    cp_async_wait<kPF - 1>();
     if (active) {
+      const float* q = pslot + (s % kPF) * ring_stride;
+      const uint2 gpk = *reinterpret_cast<const uint2*>(q);
+      const float c_cur = q[2];
+      float c_prev = 0.f;
+      if (dir == 0) { if (t > 0) c_prev = q[3]; }
+      else          { if (t + 1 < len) c_prev = q[3]; }
+      if (p.dy) {
+        dh += q[4];
+        if (p.rep_row && t == T - 1) dh += q[5];
+      }
       const float2 if_ = __half22float2(*reinterpret_cast<const __half2*>(&gpk.x));
       const float2 go_ = __half22float2(*reinterpret_cast<const __half2*>(&gpk.y));
       const float i = if_.x, f = if_.y, gc = go_.x, o = go_.y;
@@ -433,8 +498,13 @@ __global__ void __launch_bounds__(320, 1) lstm_persist_bwd_kernel(BwdP p) {
         d16[((kt * 32 + nr * 4 + ((kk & 7) >> 1)) * 2 + (kk >> 3)) * 2 + (kk & 1)] = __float2bfloat16(d4[q]);
       }
     }
+    LAS_TRACE(5);
+    prefetch(s + kPF);
+    LAS_TRACE(6);
     __syncthreads();
+    LAS_TRACE(7);
   }
+#undef LAS_TRACE
   cluster.sync();
 }
 
@@ -466,6 +536,7 @@ __global__ void pack_whhT_owner_kernel(const float* __restrict__ W, int H, int C
   }
 }
 
+void* g_dbg_buf = nullptr;   // las_set_debug_buffer: >= 128 int64 of device memory, or null
 int g_persist = -1;   // -1: take the default from the environment (LAS_DISABLE_PERSISTENT=1 turns it off)
 bool persist_enabled() {
   if (g_persist < 0) {
@@ -477,6 +548,12 @@ bool persist_enabled() {
 
 template <typename Kern, typename P>
 int launch_cluster(Kern kern, const P& p, int CS, int NG, int ndir, int threads, size_t smem, cudaStream_t stream) {
+  static bool attr_set = false;   // one instance per kernel (template instantiation)
+  if (!attr_set) {
+    LAS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  LAS_REQUIRE(smem <= 200 * 1024, "persistent LSTM: %zu bytes of shared memory needed", smem);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(CS, NG, ndir);
   cfg.blockDim = dim3(threads);
@@ -514,7 +591,8 @@ int persist_lstm_fwd(const float* xproj, const void* whh_pk, const int32_t* lens
   p.gates_save = static_cast<__half*>(gates_save); p.c_save = c_save;
   p.B = B; p.T = T; p.H = H; p.rep_row = rep_row;
   p.UG = g.UG; p.UGC = g.UGC; p.KS = g.KS; p.KTW = g.KTW; p.KT = g.KT;
-  const size_t smem = 16 + static_cast<size_t>(2) * g.KT * 256 + static_cast<size_t>(g.UGC) * 32 * 8 * 4;
+  p.dbg = static_cast<long long*>(g_dbg_buf);
+  const size_t smem = 16 + static_cast<size_t>(2) * g.KT * 256 + static_cast<size_t>(1 + kPF) * g.UGC * 32 * 8 * 4;
   return launch_cluster(lstm_persist_fwd_kernel, p, g.CS, (B + kNB - 1) / kNB, ndir, 32 * g.UGC * g.KS, smem, stream);
 }
 
@@ -530,8 +608,10 @@ int persist_lstm_bwd(const float* dy, int64_t dy_ld_b, int64_t dy_ld_t, int rep_
   p.dG = static_cast<__nv_bfloat16*>(dG); p.dg_ld_b = dg_ld_b; p.dg_ld_t = dg_ld_t;
   p.B = B; p.T = T; p.H = H;
   p.UGC = g.UGC; p.JT = g.JT; p.MTW = g.MTW; p.CSn = g.CS;
+  p.dbg = static_cast<long long*>(g_dbg_buf);
   const int UPC = 8 * g.UGC;
-  const size_t smem = 16 + static_cast<size_t>(2) * g.CS * UPC * 8 * 4 + static_cast<size_t>(2 * g.UGC) * 256;
+  const size_t smem = 16 + static_cast<size_t>(2) * g.CS * UPC * 8 * 4 + static_cast<size_t>(2 * g.UGC) * 256 +
+                      static_cast<size_t>(kPF) * 64 * g.UGC * 8 * 4;
   return launch_cluster(lstm_persist_bwd_kernel, p, g.CS, (B + kNB - 1) / kNB, ndir, 64 * g.UGC, smem, stream);
 }
 
@@ -540,6 +620,13 @@ int persist_lstm_bwd(const float* dy, int64_t dy_ld_b, int64_t dy_ld_t, int rep_
 using namespace las;
 
 extern "C" {
+
+/* development aid: clock64() phase trace of timesteps 64..71 of cluster (0,0,0): 8 slots per step,
+ * forward kernel in entries [0,64), backward kernel in [64,128) */
+int las_set_debug_buffer(void* dev_int64_x128) {
+  g_dbg_buf = dev_int64_x128;
+  return 0;
+}
 
 int las_set_persistent(int on) {
   const int prev = persist_enabled() ? 1 : 0;
