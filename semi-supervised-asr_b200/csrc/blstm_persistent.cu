@@ -178,22 +178,54 @@ __global__ void __launch_bounds__(320, 1) lstm_persist_fwd_kernel(FwdP p) {
   // xproj ring: slot s % kPF holds this lane's 2 x 4 gate pre-activations of step s (thread-private)
   float* xslot = xring + (static_cast<int64_t>(ugl) * 32 + lane) * 8;
   const int ring_stride = p.UGC * 32 * 8;
-  auto prefetch_xp = [&](int s) {
-    if (epi && s < T) {
-      const int t = (dir == 0) ? s : (T - 1 - s);
-      float* dst = xslot + (s % kPF) * ring_stride;
+  // running source pointers of the prefetch (no 64-bit index arithmetic inside the step loop)
+  const int64_t xstep = (dir == 0) ? p.xp_ld_t : -p.xp_ld_t;
+  const float* xsrc[2];
+#pragma unroll
+  for (int e = 0; e < 2; ++e)
+    xsrc[e] = p.xproj + n[e] * p.xp_ld_b + static_cast<int64_t>(dir == 0 ? 0 : T - 1) * p.xp_ld_t +
+              static_cast<int64_t>(dir) * 4 * H + u;
+  int pf_s = 0;   // next step to prefetch
+  auto prefetch_xp = [&]() {
+    if (epi && pf_s < T) {
+      const int t = (dir == 0) ? pf_s : (T - 1 - pf_s);
+      float* dst = xslot + (pf_s % kPF) * ring_stride;
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         if (t < len[e]) {
-          const float* q = p.xproj + n[e] * p.xp_ld_b + t * p.xp_ld_t + static_cast<int64_t>(dir) * 4 * H + u;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) cp_async<4>(dst + e * 4 + k, q + k * H);
+          for (int k = 0; k < 4; ++k) cp_async<4>(dst + e * 4 + k, xsrc[e] + k * H);
         }
+        xsrc[e] += xstep;
       }
     }
+    ++pf_s;
     cp_async_commit();
   };
-  for (int i = 0; i < kPF; ++i) prefetch_xp(i);
+  for (int i = 0; i < kPF; ++i) prefetch_xp();
+
+  // running global offsets of this lane's two elements (start at the first processed timestep)
+  const int t0 = (dir == 0) ? 0 : T - 1;
+  const int64_t sv_step = (dir == 0) ? H : -H;
+  const int64_t y_step = (dir == 0) ? p.y_ld_t : -p.y_ld_t;
+  const int64_t hp_step = (dir == 0) ? p.hp_ld_t : -p.hp_ld_t;
+  int64_t sv_off[2], y_off[2], hp_off[2];
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    sv_off[e] = ((static_cast<int64_t>(dir) * p.B + n[e]) * T + t0) * H + u;
+    y_off[e] = n[e] * p.y_ld_b + t0 * p.y_ld_t + static_cast<int64_t>(dir) * H + u;
+    hp_off[e] = n[e] * p.hp_ld_b + t0 * p.hp_ld_t + static_cast<int64_t>(dir) * H + u;
+  }
+  // cluster-mapped destinations of this lane's B-fragment word and of the peers' barriers
+  // (buffer 0; buffer 1 lies hs_buf_bytes / 8 bytes further inside the same CTA window)
+  uint32_t hs_remote[8], bar_remote[8];
+  const uint32_t hs_buf_bytes = static_cast<uint32_t>(p.KT) * 256u;
+#pragma unroll
+  for (int peer = 0; peer < 8; ++peer) {
+    const uint32_t pr = peer < static_cast<int>(CS) ? peer : 0;
+    hs_remote[peer] = mapa_u32(smem_u32(hs + (((ug >> 1)) * 32 + lane) * 2 + (ug & 1)), pr);
+    bar_remote[peer] = mapa_u32(smem_u32(&full[0]), pr);
+  }
 
   const bool trace = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0;
 #define LAS_TRACE(slot) do { if (trace && s >= 64 && s < 72) p.dbg[(s - 64) * 8 + (slot)] = clock64(); } while (0)
@@ -259,12 +291,14 @@ __global__ void __launch_bounds__(320, 1) lstm_persist_fwd_kernel(FwdP p) {
       for (int e = 0; e < 2; ++e)
 #pragma unroll
         for (int k = 0; k < 4; ++k) xp[e][k] = xs[e * 4 + k];
+      float sv_i[2], sv_f[2], sv_g[2], sv_o[2];
+      __nv_bfloat16 h_old[2];
+      bool act[2];
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const bool inb = n[e] < p.B;
-        const bool active = t < len[e];
-        const __nv_bfloat16 h_old = h_st[e];
-        if (active) {
+        act[e] = t < len[e];
+        h_old[e] = h_st[e];
+        if (act[e]) {
           const float gi = gsum[0][e] + xp[e][0];
           const float gf = gsum[0][2 + e] + xp[e][1];
           const float gg = gsum[1][e] + xp[e][2];
@@ -274,22 +308,11 @@ __global__ void __launch_bounds__(320, 1) lstm_persist_fwd_kernel(FwdP p) {
           const float h = o * tanh_acc(c);
           c_st[e] = c;
           h_st[e] = __float2bfloat16(h);
-          const int64_t sv = ((static_cast<int64_t>(dir) * p.B + n[e]) * T + t) * H + u;
-          if (p.gates_save) {
-            __half2 lo = __floats2half2_rn(i, f), hi = __floats2half2_rn(gc, o);
-            uint2 pk;
-            pk.x = *reinterpret_cast<uint32_t*>(&lo);
-            pk.y = *reinterpret_cast<uint32_t*>(&hi);
-            reinterpret_cast<uint2*>(p.gates_save)[sv] = pk;
-          }
-          if (p.c_save) p.c_save[sv] = c;
-          const int64_t yo = n[e] * p.y_ld_b + t * p.y_ld_t + static_cast<int64_t>(dir) * H + u;
-          p.y[yo] = h_st[e];
-          if (p.rep_row && t == T - 1) p.y[yo + p.y_ld_t] = h_st[e];
+          sv_i[e] = i; sv_f[e] = f; sv_g[e] = gc; sv_o[e] = o;
         }
-        if (inb && p.hprev) p.hprev[n[e] * p.hp_ld_b + t * p.hp_ld_t + static_cast<int64_t>(dir) * H + u] = h_old;
       }
       LAS_TRACE(5);
+      // critical path first: the new state goes to the peers before anything is written to HBM
       if (s + 1 < T) {
         // lane (unit g, utterances 2tig, 2tig+1) -> after the 8x8 transpose: (utterance g, units 2tig, 2tig+1)
         __nv_bfloat162 hv;
@@ -297,13 +320,31 @@ __global__ void __launch_bounds__(320, 1) lstm_persist_fwd_kernel(FwdP p) {
         hv.y = h_st[1];
         const uint32_t w = movmatrix_trans(*reinterpret_cast<uint32_t*>(&hv));
         const int nbuf = (s + 1) & 1;
-        const uint32_t dst = smem_u32(hs + ((nbuf * p.KT + (ug >> 1)) * 32 + lane) * 2 + (ug & 1));
-        const uint32_t bar = smem_u32(&full[nbuf]);
-        for (uint32_t peer = 0; peer < CS; ++peer) st_async_b32(mapa_u32(dst, peer), w, mapa_u32(bar, peer));
+#pragma unroll
+        for (int peer = 0; peer < 8; ++peer)
+          if (peer < static_cast<int>(CS)) st_async_b32(hs_remote[peer] + nbuf * hs_buf_bytes, w, bar_remote[peer] + nbuf * 8u);
+      }
+      // saved activations (BPTT operands) and the layer output
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        if (act[e]) {
+          if (p.gates_save) {
+            __half2 lo = __floats2half2_rn(sv_i[e], sv_f[e]), hi = __floats2half2_rn(sv_g[e], sv_o[e]);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&lo);
+            pk.y = *reinterpret_cast<uint32_t*>(&hi);
+            reinterpret_cast<uint2*>(p.gates_save)[sv_off[e]] = pk;
+          }
+          if (p.c_save) p.c_save[sv_off[e]] = c_st[e];
+          p.y[y_off[e]] = h_st[e];
+          if (p.rep_row && t == T - 1) p.y[y_off[e] + p.y_ld_t] = h_st[e];
+        }
+        if (n[e] < p.B && p.hprev) p.hprev[hp_off[e]] = h_old[e];
+        sv_off[e] += sv_step; y_off[e] += y_step; hp_off[e] += hp_step;
       }
     }
     LAS_TRACE(6);
-    prefetch_xp(s + kPF);   // refill this ring slot: DRAM latency hidden behind kPF timesteps
+    prefetch_xp();   // refill this ring slot (step s + kPF): DRAM latency hidden behind kPF timesteps
     LAS_TRACE(7);
   }
 #undef LAS_TRACE
@@ -380,24 +421,51 @@ __global__ void __launch_bounds__(320, 1) lstm_persist_bwd_kernel(BwdP p) {
   //   slot layout (8 floats): [0..1] gates (4 x f16), [2] c_t, [3] c_prev, [4] dy, [5] dy of the replicated row
   float* pslot = pring + static_cast<int64_t>(threadIdx.x) * 8;
   const int ring_stride = blockDim.x * 8;
-  auto prefetch = [&](int s) {
-    const int t = (dir == 0) ? (T - 1 - s) : s;
-    if (s < T && t < len) {
-      float* dst = pslot + (s % kPF) * ring_stride;
-      const int64_t sv = ((static_cast<int64_t>(dir) * p.B + nb) * T + t) * H + uo;
-      cp_async<8>(dst, reinterpret_cast<const uint2*>(p.gates_save) + sv);
-      cp_async<4>(dst + 2, p.c_save + sv);
-      if (dir == 0) { if (t > 0) cp_async<4>(dst + 3, p.c_save + sv - H); }
-      else          { if (t + 1 < len) cp_async<4>(dst + 3, p.c_save + sv + H); }
-      if (p.dy) {
-        const float* dyp = p.dy + nb * p.dy_ld_b + t * p.dy_ld_t + static_cast<int64_t>(dir) * H + uo;
-        cp_async<4>(dst + 4, dyp);
-        if (p.rep_row && t == T - 1) cp_async<4>(dst + 5, dyp + p.dy_ld_t);
+  // running source offsets (first processed timestep: t = T-1 for the forward direction, 0 for the reverse)
+  const int tb0 = (dir == 0) ? T - 1 : 0;
+  const int64_t sv_step = (dir == 0) ? -H : H;
+  const int64_t dy_step = (dir == 0) ? -p.dy_ld_t : p.dy_ld_t;
+  int64_t sv_run = ((static_cast<int64_t>(dir) * p.B + nb) * T + tb0) * H + uo;
+  const float* dy_run = p.dy ? p.dy + nb * p.dy_ld_b + tb0 * p.dy_ld_t + static_cast<int64_t>(dir) * H + uo : nullptr;
+  const int64_t dg_step = (dir == 0) ? -p.dg_ld_t : p.dg_ld_t;
+  __nv_bfloat16* dg_run = p.dG + nb * p.dg_ld_b + tb0 * p.dg_ld_t + static_cast<int64_t>(dir) * 4 * H + uo;
+  int pf_s = 0;
+  auto prefetch = [&]() {
+    const int t = (dir == 0) ? (T - 1 - pf_s) : pf_s;
+    if (pf_s < T && t < len) {
+      float* dst = pslot + (pf_s % kPF) * ring_stride;
+      cp_async<8>(dst, reinterpret_cast<const uint2*>(p.gates_save) + sv_run);
+      cp_async<4>(dst + 2, p.c_save + sv_run);
+      if (dir == 0) { if (t > 0) cp_async<4>(dst + 3, p.c_save + sv_run - H); }
+      else          { if (t + 1 < len) cp_async<4>(dst + 3, p.c_save + sv_run + H); }
+      if (dy_run) {
+        cp_async<4>(dst + 4, dy_run);
+        if (p.rep_row && t == T - 1) cp_async<4>(dst + 5, dy_run + p.dy_ld_t);
       }
     }
+    ++pf_s;
+    sv_run += sv_step;
+    if (dy_run) dy_run += dy_step;
     cp_async_commit();
   };
-  for (int i = 0; i < kPF; ++i) prefetch(i);
+  for (int i = 0; i < kPF; ++i) prefetch();
+
+  // reduce-scatter destinations of this lane's partial sums (buffer 0; buffer 1 is part_buf_bytes further)
+  uint32_t sc_dst[2][2], sc_bar[2][2];
+  bool sc_ok[2][2];
+  const uint32_t part_buf_bytes = static_cast<uint32_t>(p.CSn) * UPC * 8 * 4;
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const int mt = warp * p.MTW + m;
+      const int j = 16 * mt + g + 8 * hh;
+      sc_ok[m][hh] = m < p.MTW && mt < p.JT && j < H;
+      const uint32_t owner = sc_ok[m][hh] ? j / UPC : 0;
+      const int jl = sc_ok[m][hh] ? j - owner * UPC : 0;
+      sc_dst[m][hh] = mapa_u32(smem_u32(part + static_cast<int64_t>(rank) * UPC * 8 + jl * 8 + 2 * tig), owner);
+      sc_bar[m][hh] = mapa_u32(smem_u32(&pfull[0]), owner);
+    }
 
   const bool trace = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0;
 #define LAS_TRACE(slot) do { if (trace && s >= 64 && s < 72) p.dbg[64 + (s - 64) * 8 + (slot)] = clock64(); } while (0)
@@ -430,26 +498,16 @@ __global__ void __launch_bounds__(320, 1) lstm_persist_bwd_kernel(BwdP p) {
       }
       LAS_TRACE(1);
       // scatter the partial sums to the CTAs that own the units
-      const uint32_t part_base = smem_u32(part + (static_cast<int64_t>(buf) * p.CSn + rank) * UPC * 8);
-      const uint32_t bar = smem_u32(&pfull[buf]);
 #pragma unroll
-      for (int m = 0; m < 2; ++m) {
-        const int mt = warp * p.MTW + m;
-        if (m < p.MTW && mt < p.JT) {
+      for (int m = 0; m < 2; ++m)
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            const int j = 16 * mt + g + 8 * hh;
-            if (j < H) {
-              const uint32_t owner = j / UPC;
-              const int jl = j - owner * UPC;
-              const float v0 = acc[m][0][2 * hh] + acc[m][1][2 * hh];
-              const float v1 = acc[m][0][2 * hh + 1] + acc[m][1][2 * hh + 1];
-              st_async_v2(mapa_u32(part_base + (jl * 8 + 2 * tig) * 4, owner), __float_as_uint(v0),
-                          __float_as_uint(v1), mapa_u32(bar, owner));
-            }
+        for (int hh = 0; hh < 2; ++hh)
+          if (sc_ok[m][hh]) {
+            const float v0 = acc[m][0][2 * hh] + acc[m][1][2 * hh];
+            const float v1 = acc[m][0][2 * hh + 1] + acc[m][1][2 * hh + 1];
+            st_async_v2(sc_dst[m][hh] + buf * part_buf_bytes, __float_as_uint(v0), __float_as_uint(v1),
+                        sc_bar[m][hh] + buf * 8u);
           }
-        }
-      }
       LAS_TRACE(2);
       mbar_wait_cluster(&pfull[buf], ((s - 1) >> 1) & 1);
       LAS_TRACE(3);
@@ -484,10 +542,10 @@ __global__ void __launch_bounds__(320, 1) lstm_persist_bwd_kernel(BwdP p) {
       d4[3] = dh * tc * o * (1.f - o);
     }
     if (own) {
-      __nv_bfloat16* dgp = p.dG + nb * p.dg_ld_b + t * p.dg_ld_t + static_cast<int64_t>(dir) * 4 * H + uo;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) dgp[q * H] = __float2bfloat16(d4[q]);
+      for (int q = 0; q < 4; ++q) dg_run[q * H] = __float2bfloat16(d4[q]);
     }
+    dg_run += dg_step;
     if (s + 1 < T && uo < H) {
       // B fragments of the next step's MMA: K index k = gate*UPC + ul within this CTA
       __nv_bfloat16* d16 = reinterpret_cast<__nv_bfloat16*>(dgs);
@@ -499,7 +557,7 @@ __global__ void __launch_bounds__(320, 1) lstm_persist_bwd_kernel(BwdP p) {
       }
     }
     LAS_TRACE(5);
-    prefetch(s + kPF);
+    prefetch();
     LAS_TRACE(6);
     __syncthreads();
     LAS_TRACE(7);

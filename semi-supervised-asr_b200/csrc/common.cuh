@@ -43,11 +43,13 @@ __device__ __forceinline__ float tanh_fast(float x) {
   return y;
 }
 // Accurate variants (used wherever the result feeds a long recurrence).
-__device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + __expf(-x)); }
+// ex2.approx + rcp.approx (~2 + 1 ulp): no IEEE-division slow path on the serial critical path.
+__device__ __forceinline__ float sigmoid_acc(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float tanh_acc(float x) {
-  // tanh(x) = 1 - 2/(exp(2x)+1); __expf relative error ~2 ulp, saturates cleanly.
-  float e = __expf(2.0f * x);
-  return 1.0f - 2.0f / (e + 1.0f);
+  // tanh(x) = 1 - 2/(exp(2x)+1); saturates cleanly (e = inf -> 1, e = 0 -> -1). The clamp keeps
+  // e + 1 below 2^126, where __fdividef would flush the quotient to zero anyway.
+  float e = __expf(2.0f * fminf(x, 40.0f));
+  return 1.0f - __fdividef(2.0f, e + 1.0f);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
