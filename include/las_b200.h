@@ -97,7 +97,7 @@ int las_adam_step(float* p, const float* g, float* m, float* v, float* vmax, int
  * recurrences (model.py:67, 79-81 packed BLSTM; model.py:466, 515-517 LM LSTM)
  * ---------------------------------------------------------------------------------------- */
 /* f32 weight matrix -> bf16 mma A-fragments. mode 0: rows in order; mode 1: LSTM gate-interleaved
- * (rows = 4H, logical row gate*H + unit). transposed: logical A[r][c] = W[c*ld + col_offset + r]. */
+ * (rows = 4H, logical row gate*H + unit; tile = 8 units x 2 gates); mode 2: tile = 4 units x 4 gates. transposed: logical A[r][c] = W[c*ld + col_offset + r]. */
 int las_pack_afrag(const float* W, int64_t ld, int rows, int cols, int col_offset, int mode, int H,
                    int transposed, void* out, void* stream);
 int64_t las_afrag_bytes(int rows, int cols, int mode, int H);
@@ -190,9 +190,36 @@ typedef struct las_dec_args {
   float* dgvec;              /* += [A]                                                          */
   float* dconv_w;            /* += [C, 2K+1]                                                    */
   float* denc;               /* f32 [B, Te, H] gradient through the context (see denc_accumulate) */
+  /* cluster-persistent decoder (teacher-forced mode; used when las_dec_persistent_supported() != 0) */
+  const void* Q;             /* bf16 [B, Te, O] = enc_h @ mlp_o.weight^T (no bias)               */
+  const void* wr2_pk;        /* fragments (mode 2: 4 units x 4 gates per tile) of [W_hh | W_ih[:, E:]] */
+  float* cpre;               /* f32 [B, L, O]: c_t before the mlp_o bias                        */
+  float* conv_save;          /* f32 [B, L, Te, 16]: location-conv features of every step        */
+  const void* wrT2_pk;       /* backward: las_dec_persistent_pack(0, [W_hh | W_ih[:, E:]])      */
+  const void* mlp_decT2_pk;  /* backward: las_dec_persistent_pack(1, mlp_dec.weight)            */
+  float* de_all;             /* backward out: f32 [B, L, Te] energy gradients                   */
+  float* dc_all;             /* backward out: f32 [B, L, O] total gradient of c_t               */
 } las_dec_args;
 
 int las_att_init(const int32_t* enc_lens, int B, int Te, float* w, int64_t w_ld, void* stream);
+/* 1 when las_dec_fwd / las_dec_bwd will run this problem (sizes, mode, Q and wr2_pk set) as ONE
+ * cluster-persistent launch instead of per-step launches */
+int las_dec_persistent_supported(const las_dec_args* args_host);
+/* weight fragments of the cluster-persistent backward kernel (which: 0 = [W_hh | W_ih[:, E:]]^T from the
+ * f32 [4Hd, Hd+O] matrix, 1 = mlp_dec.weight^T from the f32 [A, Hd] matrix) */
+int64_t las_dec_persistent_pack_bytes(int which, int Hd, int O, int A);
+int las_dec_persistent_pack(int which, const float* W, int64_t ld, int Hd, int O, int A, void* out, void* stream);
+/* Post-loop reductions of the persistent backward (parallel over utterances / frames):
+ *   dQ[b,te,o] = sum_t ws[b,t+1,te] dc[b,t,o]                       (las_att_dq)
+ *   dP[b,te,a], dmlp_att[a,c] (+=), dgvec[a] (+=) from de, conv, dz, P with tanh recomputed (las_att_param_grads) */
+int las_att_dq(const float* ws_alloc, const float* dc_all, int L, int B, int Te, int O, float* dQ, void* stream);
+/* dconv_w[c,k] += sum_{t,b,te} dattc[t,b,te,c] * ws[b,t,te+k-K]   (loc_conv.weight gradient) */
+int las_att_dconv(const float* dattc_all, const float* ws_alloc, int L, int B, int Te, int C, int K, float* dconv_w,
+                  void* stream);
+int las_att_param_grads(const float* P, const float* dzf, const float* conv_save, const float* de_all,
+                        const float* mlp_att, const float* gvec, int B, int L, int Te, int A, int C, float* dP,
+                        float* part_ws /* scratch f32 [ceil(Te/32)*B, 17, roundup32(A)] */, float* dmlp_att,
+                        float* dgvec, void* stream);
 int las_dec_fwd(const las_dec_args* args_host, void* stream);
 int las_dec_bwd(const las_dec_args* args_host, void* stream);
 

@@ -28,7 +28,7 @@ class DecArgs(ctypes.Structure):
             "ws", "zc", "ctx", "c_state", "emb_op", "logits", "pred", "e_buf", "dzf", "gates_save", "c_save",
             "wrT_pk", "mlp_oT_pk", "mlp_decT_pk", "dzc_all", "dcz_tot", "dcz_all", "dctx_all", "dw_buf",
             "dattc_all", "ddz_all", "dP", "att_part", "dc_state", "dgates", "dmlp_att", "dgvec", "dconv_w",
-            "denc")]
+            "denc", "Q", "wr2_pk", "cpre", "conv_save", "wrT2_pk", "mlp_decT2_pk", "de_all", "dc_all")]
     )
 
 
@@ -63,6 +63,12 @@ SIGNATURES = {
     "las_pack_whhT_owner": (c_int, [P, I, P, P]),
     "las_pyramid_lens": (c_int, [P, I, I, P, P]),
     "las_att_init": (c_int, [P, I, I, P, L, P]),
+    "las_dec_persistent_supported": (c_int, [ctypes.POINTER(DecArgs)]),
+    "las_dec_persistent_pack_bytes": (c_int64, [I, I, I, I]),
+    "las_dec_persistent_pack": (c_int, [I, P, L, I, I, I, P, P]),
+    "las_att_dq": (c_int, [P, P, I, I, I, I, P, P]),
+    "las_att_dconv": (c_int, [P, P, I, I, I, I, I, P, P]),
+    "las_att_param_grads": (c_int, [P, P, P, P, P, P, I, I, I, I, I, P, P, P, P, P]),
     "las_dec_fwd": (c_int, [ctypes.POINTER(DecArgs), P]),
     "las_dec_bwd": (c_int, [ctypes.POINTER(DecArgs), P]),
 }

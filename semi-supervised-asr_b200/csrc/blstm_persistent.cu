@@ -631,6 +631,8 @@ int launch_cluster(Kern kern, const P& p, int CS, int NG, int ndir, int threads,
 
 }  // namespace
 
+void* g_dbg_buf_shared = nullptr;
+
 int persist_supported(int H) {
   Geom g;
   return persist_enabled() && geom_for(H, g) ? 1 : 0;
@@ -683,6 +685,7 @@ extern "C" {
  * forward kernel in entries [0,64), backward kernel in [64,128) */
 int las_set_debug_buffer(void* dev_int64_x128) {
   g_dbg_buf = dev_int64_x128;
+  las::g_dbg_buf_shared = dev_int64_x128;
   return 0;
 }
 

@@ -456,6 +456,63 @@ __global__ void __launch_bounds__(256) att_denc_kernel(const float* __restrict__
   }
 }
 
+// Post-loop parameter gradients of the energy MLP for the persistent backward: every (b, te, a) is
+// independent, so nothing of this sits in the serial loop. For its frame tile a CTA walks all steps t
+// and recomputes s = tanh(P + dz_t + mlp_att conv_t) from the saved conv features and energy gradients:
+//   dP[b,te,a] = sum_t ds,  part[cta][c][a] = sum ds*conv[c],  part[cta][CM][a] = sum de*s,  ds = de gv (1 - s^2)
+// grid (ceil(Te/kTT), B), block = A rounded up to a warp multiple.
+template <int CM>
+__global__ void __launch_bounds__(512) att_param_grad_kernel(const float* __restrict__ P, const float* __restrict__ dzf,
+                                                             const float* __restrict__ conv_save,
+                                                             const float* __restrict__ de_all,
+                                                             const float* __restrict__ mlp_att,
+                                                             const float* __restrict__ gvec, int B, int L, int Te, int A,
+                                                             int C, int Ap, float* __restrict__ dP,
+                                                             float* __restrict__ part) {
+  const int b = blockIdx.y, te0 = blockIdx.x * kTT, a = threadIdx.x;
+  const bool ok = a < A;
+  float matt[CM], dmatt[CM];
+#pragma unroll
+  for (int c = 0; c < CM; ++c) {
+    matt[c] = (ok && c < C) ? mlp_att[a * C + c] : 0.f;
+    dmatt[c] = 0.f;
+  }
+  const float gv = ok ? gvec[a] : 0.f;
+  float dgv = 0.f;
+  const int ntl = min(kTT, Te - te0);
+  for (int tl = 0; tl < ntl; ++tl) {
+    const int te = te0 + tl;
+    const float pv = ok ? P[(static_cast<int64_t>(b) * Te + te) * A + a] : 0.f;
+    float dp = 0.f;
+    for (int t = 0; t < L; ++t) {
+      const float de = __ldg(de_all + (static_cast<int64_t>(b) * L + t) * Te + te);
+      const float4* cv = reinterpret_cast<const float4*>(conv_save + ((static_cast<int64_t>(b) * L + t) * Te + te) * 16);
+      float conv[CM];
+#pragma unroll
+      for (int c4 = 0; c4 < CM / 4; ++c4) {
+        const float4 v = __ldg(cv + c4);
+        conv[4 * c4] = v.x; conv[4 * c4 + 1] = v.y; conv[4 * c4 + 2] = v.z; conv[4 * c4 + 3] = v.w;
+      }
+      float x = pv + (ok ? dzf[(static_cast<int64_t>(b) * L + t) * A + a] : 0.f);
+#pragma unroll
+      for (int c = 0; c < CM; ++c) x = fmaf(matt[c], conv[c], x);
+      const float s = tanh_fast(x);
+      const float ds = de * gv * (1.f - s * s);
+      dp += ds;
+      dgv = fmaf(de, s, dgv);
+#pragma unroll
+      for (int c = 0; c < CM; ++c) dmatt[c] = fmaf(ds, conv[c], dmatt[c]);
+    }
+    if (ok) dP[(static_cast<int64_t>(b) * Te + te) * A + a] = dp;
+  }
+  if (ok) {
+    float* pp = part + static_cast<int64_t>(blockIdx.y * gridDim.x + blockIdx.x) * (CM + 1) * Ap + a;
+#pragma unroll
+    for (int c = 0; c < CM; ++c) pp[c * Ap] = dmatt[c];
+    pp[CM * Ap] = dgv;
+  }
+}
+
 static size_t energy_smem(const las_dec_args* a, int CM, int nwarps, bool bwd) {
   const int ksz = 2 * a->K + 1;
   size_t f = a->Te + 2 * a->K + static_cast<size_t>(a->C) * ksz + kTT * CM;
@@ -494,9 +551,51 @@ int las_att_init(const int32_t* enc_lens, int B, int Te, float* w, int64_t w_ld,
   return 0;
 }
 
+int las_dec_persistent_supported(const las_dec_args* a) { return dec_persist_supported(a); }
+
+int64_t las_dec_persistent_pack_bytes(int which, int Hd, int O, int A) { return dec_persist_pack_bytes(which, Hd, O, A); }
+
+int las_dec_persistent_pack(int which, const float* W, int64_t ld, int Hd, int O, int A, void* out, void* stream) {
+  return dec_persist_pack(which, W, ld, Hd, O, A, out, static_cast<cudaStream_t>(stream));
+}
+
+int las_att_dq(const float* ws_alloc, const float* dc_all, int L, int B, int Te, int O, float* dQ, void* stream) {
+  if (B == 0 || Te == 0) return 0;
+  att_denc_kernel<<<dim3(Te, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(ws_alloc, dc_all, L, B, Te, O, dQ, 0); ++g_launches;
+  LAS_LAUNCH_CHECK();
+  return 0;
+}
+
+int las_att_dconv(const float* dattc_all, const float* ws_alloc, int L, int B, int Te, int C, int K, float* dconv_w,
+                  void* stream) {
+  LAS_REQUIRE(C >= 1 && C <= 16, "att_dconv: conv_channels %d out of range [1,16]", C);
+  if (B == 0 || Te == 0 || L == 0) return 0;
+  att_dconv_kernel<<<2 * K + 1, 256, 0, static_cast<cudaStream_t>(stream)>>>(dattc_all, ws_alloc, L, B, Te, C, K, dconv_w); ++g_launches;
+  LAS_LAUNCH_CHECK();
+  return 0;
+}
+
+int las_att_param_grads(const float* P, const float* dzf, const float* conv_save, const float* de_all,
+                        const float* mlp_att, const float* gvec, int B, int L, int Te, int A, int C, float* dP,
+                        float* part_ws, float* dmlp_att, float* dgvec, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  LAS_REQUIRE(A >= 1 && A <= 512 && C >= 1 && C <= 16, "att_param_grads: att_dim / conv_channels out of range");
+  if (B == 0 || Te == 0 || L == 0) return 0;
+  const int CM = (C <= 4) ? 4 : 16;
+  const int threads = (A + 31) / 32 * 32;
+  const dim3 grid((Te + kTT - 1) / kTT, B);
+  if (CM == 4) att_param_grad_kernel<4><<<grid, threads, 0, stream>>>(P, dzf, conv_save, de_all, mlp_att, gvec, B, L, Te, A, C, threads, dP, part_ws);
+  else att_param_grad_kernel<16><<<grid, threads, 0, stream>>>(P, dzf, conv_save, de_all, mlp_att, gvec, B, L, Te, A, C, threads, dP, part_ws);
+  ++g_launches;
+  att_part_reduce_kernel<<<((C + 1) * A + 255) / 256, 256, 0, stream>>>(part_ws, grid.x * grid.y, CM, threads, A, C, dmlp_att, dgvec); ++g_launches;
+  LAS_LAUNCH_CHECK();
+  return 0;
+}
+
 int las_dec_fwd(const las_dec_args* a, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (int rc = check_args(a)) return rc;
+  if (dec_persist_supported(a)) return dec_persist_fwd(a, stream);   // one cluster-persistent launch
   const int B = a->B, L = a->L, Te = a->Te, Hd = a->Hd, O = a->O, A = a->A, V = a->V, E = a->E;
   const int ZC = Hd + O;
   const int64_t R = L + 1;  // rows per utterance in the per-step buffers
@@ -581,6 +680,7 @@ int las_dec_bwd(const las_dec_args* a, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (int rc = check_args(a)) return rc;
   LAS_REQUIRE(a->mode == 0, "decoder backward: only the teacher-forced mode is implemented here");
+  if (dec_persist_supported(a)) return dec_persist_bwd(a, stream);   // one cluster-persistent launch
   const int B = a->B, L = a->L, Te = a->Te, Hd = a->Hd, O = a->O, A = a->A;
   const int ZC = Hd + O;
   const int64_t R = L + 1;

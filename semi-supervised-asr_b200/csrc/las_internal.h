@@ -24,6 +24,17 @@ int persist_lstm_bwd(const float* dy, int64_t dy_ld_b, int64_t dy_ld_t, int rep_
                      const int32_t* lens, int B, int T, int H, int ndir, const void* gates_save,
                      const float* c_save, void* dG, int64_t dg_ld_b, int64_t dg_ld_t, cudaStream_t stream);
 
+// cluster-persistent attention decoder (decoder_persistent.cu)
+}  // namespace las
+struct las_dec_args;
+namespace las {
+extern void* g_dbg_buf_shared;   // las_set_debug_buffer (development aid)
+int dec_persist_supported(const las_dec_args* a);
+int dec_persist_fwd(const las_dec_args* a, cudaStream_t stream);
+int dec_persist_bwd(const las_dec_args* a, cudaStream_t stream);
+int64_t dec_persist_pack_bytes(int which, int Hd, int O, int A);
+int dec_persist_pack(int which, const float* W, int64_t ld, int Hd, int O, int A, void* out, cudaStream_t stream);
+
 #ifdef __CUDACC__
 }  // namespace las
 #include <cuda_bf16.h>

@@ -26,6 +26,7 @@ namespace las {
 // ------------------------------------------------------------------------------------------
 // out[((tile*KT + kt)*32 + lane)*4 + j]: j&1 -> row +8, j>>1 -> col +8 (mma.m16n8k16 A layout).
 // mode 0: tile rows are 16 consecutive logical rows.
+// mode 2: tile = 4 hidden units x 4 gates: row rl -> gate rl>>2 of unit 4*tile + (rl&3).
 // mode 1: LSTM gate interleave: tile = 2*ug + half; rows 0-7 -> gate 2*half of units 8ug..8ug+7,
 //         rows 8-15 -> gate 2*half+1 of the same units (logical row = gate*H + unit).
 // transposed != 0: logical A[row][col] = W[col][row].
@@ -46,6 +47,10 @@ __global__ void pack_afrag_kernel(const float* __restrict__ W, int64_t ld, int r
     int row;
     if (mode == 0) {
       row = 16 * tile + rl;
+    } else if (mode == 2) {
+      const int unit = 4 * tile + (rl & 3);
+      const int gate = rl >> 2;
+      row = (unit < H) ? gate * H + unit : rows;
     } else {
       const int ug = tile >> 1, half = tile & 1;
       const int unit = 8 * ug + (rl & 7);
@@ -394,14 +399,14 @@ extern "C" {
 
 int las_pack_afrag(const float* W, int64_t ld, int rows, int cols, int col_offset, int mode, int H,
                    int transposed, void* out, void* stream) {
-  const int tiles = (mode == 1) ? 2 * ((H + 7) / 8) : (rows + 15) / 16;
+  const int tiles = (mode == 1) ? 2 * ((H + 7) / 8) : (mode == 2) ? (H + 3) / 4 : (rows + 15) / 16;
   const int KT = (cols + 15) / 16;
   return pack_afrag(W, ld, rows, cols, col_offset, mode, H, transposed != 0, tiles, KT,
                     static_cast<uint32_t*>(out), static_cast<cudaStream_t>(stream));
 }
 
 int64_t las_afrag_bytes(int rows, int cols, int mode, int H) {
-  const int64_t tiles = (mode == 1) ? 2 * ((H + 7) / 8) : (rows + 15) / 16;
+  const int64_t tiles = (mode == 1) ? 2 * ((H + 7) / 8) : (mode == 2) ? (H + 3) / 4 : (rows + 15) / 16;
   const int64_t KT = (cols + 15) / 16;
   return tiles * KT * 128 * 4;
 }

@@ -8,6 +8,7 @@ Precision: bf16 MMA operands, f32 accumulation, f32 recurrent cell state, f32 ma
 gradients.
 """
 import ctypes
+import os
 
 import torch
 
@@ -15,6 +16,8 @@ from . import _lib
 from ._lib import DecArgs, call, ptr  # noqa: F401  (re-exported for the modules)
 
 BF16 = torch.bfloat16
+# cluster-persistent attention decoder (csrc/decoder_persistent.cu); LAS_DEC_PERSIST=0 selects the per-step kernels
+DEC_PERSISTENT = os.environ.get("LAS_DEC_PERSIST", "1") == "1"
 
 
 def _r8(n):
@@ -275,6 +278,21 @@ class DecoderFn(torch.autograd.Function):
             a.cell_bias, a.we_pk, a.out_pk, a.out_b = ptr(cell_bias), ptr(we_pk), ptr(out_pk), ptr(W["out_b"])
             a.emb_w, a.emb_op, a.logits, a.pred = ptr(W["emb_w"]), ptr(emb_op), ptr(logits), ptr(pred)
             keep += [we_pk, out_pk, emb_op]
+        persist, pers = False, None
+        if mode == 0 and DEC_PERSISTENT:
+            # cluster-persistent decoder: c_t = w_t @ Q + bias with Q = enc_h @ mlp_o.weight^T
+            mlp_o_bf = cvt_bf16(W["mlp_o_w"])
+            Qm = gemm(enc_bf, H, 0, mlp_o_bf, H, 0, B * Te, O, H, out_bf16=True)
+            wr2_pk = pack_afrag(wr_cat, 2, Hd)
+            a.Q, a.wr2_pk = ptr(Qm), ptr(wr2_pk)
+            persist = bool(_lib.lib().las_dec_persistent_supported(ctypes.byref(a)))
+            if persist:
+                cpre = torch.empty(B, L, O, **f32)
+                conv_save = torch.empty(B, L, Te, 16, **f32)
+                a.cpre, a.conv_save = ptr(cpre), ptr(conv_save)
+                pers = dict(Qm=Qm, wr2_pk=wr2_pk, cpre=cpre, conv_save=conv_save, mlp_o_bf=mlp_o_bf)
+            else:
+                a.Q, a.wr2_pk = None, None
         _lib.check(_lib.lib().las_dec_fwd(ctypes.byref(a), _lib.stream_ptr()))
         out_bf = cvt_bf16(W["out_w"])                                                 # [V, ZC]
         if mode == 0:
@@ -282,7 +300,7 @@ class DecoderFn(torch.autograd.Function):
         ctx.geom = (B, Te, H, Hd, O, A, V, E, C, K, L, mode, att_scaling, smooth_scaling)
         ctx.saved = dict(enc_bf=enc_bf, Pm=Pm, mlp_enc_bf=mlp_enc_bf, wr_cat=wr_cat, ws=ws, zc=zc, cx=cx, dzf=dzf,
                          gates=gates, csave=csave, conv_w=conv_w, mlp_att=mlp_att, gvec=gvec, emb_in=emb_in,
-                         out_bf=out_bf, ys_in=ys_in, keep=keep)
+                         out_bf=out_bf, ys_in=ys_in, keep=keep, pers=pers)
         ctx.W = W
         ctx.mark_non_differentiable(ws)
         if pred is not None:
@@ -339,7 +357,29 @@ class DecoderFn(torch.autograd.Function):
         a.dgates, a.dmlp_att, a.dgvec, a.dconv_w, a.denc = (ptr(dgates), ptr(d_mlp_att), ptr(d_gvec), ptr(d_conv),
                                                             ptr(denc))
         a.denc_accumulate = 0
+        pers = S["pers"]
+        if pers is not None:
+            # cluster-persistent backward: the serial loop only produces per-step gradients; every
+            # parameter gradient is reduced afterwards by the GEMMs / parallel kernels below
+            L_ = _lib.lib()
+            wrT2 = torch.empty(L_.las_dec_persistent_pack_bytes(0, Hd, O, A) // 4, device=dev, dtype=torch.int32)
+            call("las_dec_persistent_pack", 0, ptr(S["wr_cat"]), ZC, Hd, O, A, ptr(wrT2))
+            mlp_dec_w = W["mlp_dec_w"].contiguous()
+            decT2 = torch.empty(L_.las_dec_persistent_pack_bytes(1, Hd, O, A) // 4, device=dev, dtype=torch.int32)
+            call("las_dec_persistent_pack", 1, ptr(mlp_dec_w), Hd, Hd, O, A, ptr(decT2))
+            de_all = torch.zeros(B, L, Te, **f32)
+            dc_all = torch.zeros(B, L, O, **f32)
+            a.Q, a.wr2_pk, a.cpre, a.conv_save = ptr(pers["Qm"]), ptr(pers["wr2_pk"]), ptr(pers["cpre"]), ptr(pers["conv_save"])
+            a.wrT2_pk, a.mlp_decT2_pk, a.de_all, a.dc_all = ptr(wrT2), ptr(decT2), ptr(de_all), ptr(dc_all)
         _lib.check(_lib.lib().las_dec_bwd(ctypes.byref(a), _lib.stream_ptr()))
+        if pers is not None:
+            call("las_att_param_grads", ptr(S["Pm"]), ptr(S["dzf"]), ptr(pers["conv_save"]), ptr(de_all), ptr(S["mlp_att"]),
+                 ptr(S["gvec"]), B, L, Te, A, C, ptr(dP), ptr(att_part), ptr(d_mlp_att), ptr(d_gvec))
+            d_conv_t = torch.zeros(C, 2 * K + 1, **f32)
+            call("las_att_dconv", ptr(dattc_all), ptr(S["ws"]), L, B, Te, C, K, ptr(d_conv_t))
+            d_conv = d_conv_t
+            dQ = torch.empty(B * Te, O, **f32)
+            call("las_att_dq", ptr(S["ws"]), ptr(dc_all), L, B, Te, O, ptr(dQ))
         # ---- weight gradients deferred out of the time loop, as dense contractions over all (b, t)
         d_wr = gemm(dgates, 4 * Hd, 1, zc, ZC, 1, 4 * Hd, ZC, n)                      # [4Hd, Hd+O]
         emb_in = S["emb_in"]
@@ -352,7 +392,13 @@ class DecoderFn(torch.autograd.Function):
         d_emb = torch.zeros(V, E, **f32)
         call("las_scatter_add_rows", ptr(demb_rows), Ep, E, ptr(S["ys_in"]), n, 0, ptr(d_emb))
         dc_att = dcz_all[:, Hd:]                                                      # bf16 view, ld ZC
-        d_mlp_o_w = gemm(dc_att, ZC, 1, S["cx"], H, 1, O, H, n)
+        if pers is not None:
+            # c_t = w_t @ Q + b, Q = enc_h @ mlp_o.weight^T: d mlp_o.weight = dQ^T enc_h, d enc_h = dQ mlp_o.weight
+            dQ_bf = cvt_bf16(dQ)
+            d_mlp_o_w = gemm(dQ_bf, dQ_bf.shape[1], 1, S["enc_bf"], H, 1, O, H, B * Te)
+            gemm(dQ_bf, dQ_bf.shape[1], 0, pers["mlp_o_bf"], H, 1, B * Te, H, O, out=denc.view(B * Te, H))
+        else:
+            d_mlp_o_w = gemm(dc_att, ZC, 1, S["cx"], H, 1, O, H, n)
         d_mlp_o_b = colsum(dc_att, O, ld=ZC, rows=n)
         ddz_bf = cvt_bf16(ddz_all[:n * A].view(n, A))
         d_mlp_dec = gemm(ddz_bf, ddz_bf.shape[1], 1, zc, ZC, 1, A, Hd, n)
