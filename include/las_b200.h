@@ -183,7 +183,7 @@ typedef struct las_dec_args {
   float* dattc_all;          /* f32 [L, B, Te, C]                                               */
   float* ddz_all;            /* f32 [B, L+1, A] (+64 slack), zeroed                             */
   float* dP;                 /* f32 [B, Te, A], zeroed                                          */
-  float* att_part;           /* scratch f32 [ceil(Te/32)*B, 17, roundup32(A)]                   */
+  float* att_part;           /* scratch f32, las_att_scratch_floats() elements                  */
   float* dc_state;           /* scratch f32 [B, Hd]                                             */
   void* dgates;              /* bf16 [B, L+1, 4Hd], zeroed (row L stays zero)                   */
   float* dmlp_att;           /* += [A, C]                                                       */
@@ -191,14 +191,16 @@ typedef struct las_dec_args {
   float* dconv_w;            /* += [C, 2K+1]                                                    */
   float* denc;               /* f32 [B, Te, H] gradient through the context (see denc_accumulate) */
   /* cluster-persistent decoder (teacher-forced mode; used when las_dec_persistent_supported() != 0) */
-  const void* Q;             /* bf16 [B, Te, O] = enc_h @ mlp_o.weight^T (no bias)               */
+  const void* Q;             /* bf16 [B, Te, O] = enc_h @ mlp_o.weight^T, centred over the frames of each utterance */
   const void* wr2_pk;        /* fragments (mode 2: 4 units x 4 gates per tile) of [W_hh | W_ih[:, E:]] */
-  float* cpre;               /* f32 [B, L, O]: c_t before the mlp_o bias                        */
+  float* cpre;               /* f32 [B, L, O]: c_t - cbias = sum_te w_t[te] Q[te]                */
   float* conv_save;          /* f32 [B, L, Te, 16]: location-conv features of every step        */
   const void* wrT2_pk;       /* backward: las_dec_persistent_pack(0, [W_hh | W_ih[:, E:]])      */
   const void* mlp_decT2_pk;  /* backward: las_dec_persistent_pack(1, mlp_dec.weight)            */
   float* de_all;             /* backward out: f32 [B, L, Te] energy gradients                   */
   float* dc_all;             /* backward out: f32 [B, L, O] total gradient of c_t               */
+  const float* cbias;        /* f32 [B, O]: mlp_o.bias + the frame mean removed from Q          */
+  const float* pbar;         /* f32 [B, A]: frame mean removed from P (then P holds P - pbar and dzf = mlp_dec(z_t) + pbar) */
 } las_dec_args;
 
 int las_att_init(const int32_t* enc_lens, int B, int Te, float* w, int64_t w_ld, void* stream);
@@ -215,10 +217,12 @@ int las_dec_persistent_pack(int which, const float* W, int64_t ld, int Hd, int O
 int las_att_dq(const float* ws_alloc, const float* dc_all, int L, int B, int Te, int O, float* dQ, void* stream);
 /* dconv_w[c,k] += sum_{t,b,te} dattc[t,b,te,c] * ws[b,t,te+k-K]   (loc_conv.weight gradient) */
 int las_att_dconv(const float* dattc_all, const float* ws_alloc, int L, int B, int Te, int C, int K, float* dconv_w,
-                  void* stream);
+                  float* scratch, void* stream);
+/* floats of scratch (las_dec_args.att_part, las_att_dconv, las_att_param_grads part_ws) for these sizes */
+int64_t las_att_scratch_floats(int B, int L, int Te, int A, int C, int K);
 int las_att_param_grads(const float* P, const float* dzf, const float* conv_save, const float* de_all,
                         const float* mlp_att, const float* gvec, int B, int L, int Te, int A, int C, float* dP,
-                        float* part_ws /* scratch f32 [ceil(Te/32)*B, 17, roundup32(A)] */, float* dmlp_att,
+                        float* part_ws /* scratch: las_att_scratch_floats() */, float* dmlp_att,
                         float* dgvec, void* stream);
 int las_dec_fwd(const las_dec_args* args_host, void* stream);
 int las_dec_bwd(const las_dec_args* args_host, void* stream);

@@ -28,7 +28,7 @@ class DecArgs(ctypes.Structure):
             "ws", "zc", "ctx", "c_state", "emb_op", "logits", "pred", "e_buf", "dzf", "gates_save", "c_save",
             "wrT_pk", "mlp_oT_pk", "mlp_decT_pk", "dzc_all", "dcz_tot", "dcz_all", "dctx_all", "dw_buf",
             "dattc_all", "ddz_all", "dP", "att_part", "dc_state", "dgates", "dmlp_att", "dgvec", "dconv_w",
-            "denc", "Q", "wr2_pk", "cpre", "conv_save", "wrT2_pk", "mlp_decT2_pk", "de_all", "dc_all")]
+            "denc", "Q", "wr2_pk", "cpre", "conv_save", "wrT2_pk", "mlp_decT2_pk", "de_all", "dc_all", "cbias", "pbar")]
     )
 
 
@@ -67,7 +67,8 @@ SIGNATURES = {
     "las_dec_persistent_pack_bytes": (c_int64, [I, I, I, I]),
     "las_dec_persistent_pack": (c_int, [I, P, L, I, I, I, P, P]),
     "las_att_dq": (c_int, [P, P, I, I, I, I, P, P]),
-    "las_att_dconv": (c_int, [P, P, I, I, I, I, I, P, P]),
+    "las_att_dconv": (c_int, [P, P, I, I, I, I, I, P, P, P]),
+    "las_att_scratch_floats": (c_int64, [I, I, I, I, I, I]),
     "las_att_param_grads": (c_int, [P, P, P, P, P, P, I, I, I, I, I, P, P, P, P, P]),
     "las_dec_fwd": (c_int, [ctypes.POINTER(DecArgs), P]),
     "las_dec_bwd": (c_int, [ctypes.POINTER(DecArgs), P]),

@@ -413,33 +413,64 @@ __global__ void att_part_reduce_kernel(const float* __restrict__ part, int ncta,
   else dgvec[a] += s;
 }
 
-// dconv_w[c, k] += sum_{t, b, te} dattc[t, b, te, c] * w_{t-1}[b, te + k - K]
-// (w_{t-1} = ws_alloc row t). grid (2K+1), block 256; every thread strides over (t, b, te).
-__global__ void __launch_bounds__(256) att_dconv_kernel(const float* __restrict__ dattc_all, const float* __restrict__ ws_alloc,
-                                                        int L, int B, int Te, int C, int K, float* __restrict__ dconv_w) {
-  __shared__ float red[8];
-  const int k = blockIdx.x;
+// dconv_w[c, k] += sum_{t, b, te} dattc[t, b, te, c] * w_{t-1}[b, te + k - K]   (w_{t-1} = ws_alloc row t).
+// Pass 1: grid (ceil(L/kDT), B), block 256 (thread = tap k): partial[cta][c][k] over kDT steps of one
+// utterance, operands staged in shared memory. Pass 2: deterministic sum over the CTAs.
+constexpr int kDT = 8;
+__global__ void __launch_bounds__(256) att_dconv_partial_kernel(const float* __restrict__ dattc_all,
+                                                                const float* __restrict__ ws_alloc, int L, int B, int Te,
+                                                                int C, int K, float* __restrict__ partial) {
+  extern __shared__ float sm[];
+  float* wp = sm;                       // [Te + 2K] zero padded alignment
+  float* d = wp + Te + 2 * K;           // [Te][C]
   const int ksz = 2 * K + 1;
+  const int b = blockIdx.y, t0 = blockIdx.x * kDT;
   float acc[16];
 #pragma unroll
   for (int c = 0; c < 16; ++c) acc[c] = 0.f;
-  const int64_t total = static_cast<int64_t>(L) * B * Te;
-  for (int64_t i = threadIdx.x; i < total; i += 256) {
-    const int te = i % Te;
-    const int64_t tb = i / Te;
-    const int b = tb % B, t = tb / B;
-    const int j = te + k - K;
-    if (j < 0 || j >= Te) continue;
-    const float w = ws_alloc[(static_cast<int64_t>(b) * (L + 1) + t) * Te + j];
-    const float* d = dattc_all + i * C;
+  for (int t = t0; t < min(L, t0 + kDT); ++t) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < Te + 2 * K; i += 256) {
+      const int j = i - K;
+      wp[i] = (j >= 0 && j < Te) ? ws_alloc[(static_cast<int64_t>(b) * (L + 1) + t) * Te + j] : 0.f;
+    }
+    const float* src = dattc_all + (static_cast<int64_t>(t) * B + b) * Te * C;
+    for (int i = threadIdx.x; i < Te * C; i += 256) d[i] = src[i];
+    __syncthreads();
+    for (int k = threadIdx.x; k < ksz; k += 256) {
+      const float* wk = wp + k;           // wk[te] = w[te + k - K]
+      for (int te = 0; te < Te; ++te) {
+        const float w = wk[te];
+        const float* dr = d + te * C;
+#pragma unroll
+        for (int c = 0; c < 16; ++c)
+          if (c < C) acc[c] = fmaf(dr[c], w, acc[c]);
+      }
+    }
+  }
+  float* out = partial + static_cast<int64_t>(blockIdx.y * gridDim.x + blockIdx.x) * C * ksz;
+  for (int k = threadIdx.x; k < ksz; k += 256)
 #pragma unroll
     for (int c = 0; c < 16; ++c)
-      if (c < C) acc[c] = fmaf(d[c], w, acc[c]);
-  }
-  for (int c = 0; c < C; ++c) {
-    const float s = block_reduce_sum(acc[c], red, 8);
-    if (threadIdx.x == 0) dconv_w[c * ksz + k] += s;
-  }
+      if (c < C) out[c * ksz + k] = acc[c];
+}
+__global__ void att_dconv_reduce_kernel(const float* __restrict__ partial, int ncta, int n, float* __restrict__ dconv_w) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int k = 0; k < ncta; ++k) s += partial[static_cast<int64_t>(k) * n + i];
+  dconv_w[i] += s;
+}
+static int launch_att_dconv(const float* dattc_all, const float* ws_alloc, int L, int B, int Te, int C, int K,
+                            float* dconv_w, float* partial_ws, cudaStream_t stream) {
+  const int ksz = 2 * K + 1;
+  LAS_REQUIRE(ksz <= 256, "att_dconv: conv kernel of %d taps is wider than 256", ksz);
+  const dim3 grid((L + kDT - 1) / kDT, B);
+  const size_t smem = (Te + 2 * K + static_cast<size_t>(Te) * C) * sizeof(float);
+  LAS_REQUIRE(smem <= 48 * 1024, "att_dconv: %zu bytes of shared memory needed", smem);
+  att_dconv_partial_kernel<<<grid, 256, smem, stream>>>(dattc_all, ws_alloc, L, B, Te, C, K, partial_ws); ++g_launches;
+  att_dconv_reduce_kernel<<<(C * ksz + 255) / 256, 256, 0, stream>>>(partial_ws, grid.x * grid.y, C * ksz, dconv_w); ++g_launches;
+  return 0;
 }
 
 // denc[b, te, h] (+)= sum_t ws[b, t, te] * dctx[b, t, h]     (gradient of the context bmm)
@@ -460,7 +491,8 @@ __global__ void __launch_bounds__(256) att_denc_kernel(const float* __restrict__
 // independent, so nothing of this sits in the serial loop. For its frame tile a CTA walks all steps t
 // and recomputes s = tanh(P + dz_t + mlp_att conv_t) from the saved conv features and energy gradients:
 //   dP[b,te,a] = sum_t ds,  part[cta][c][a] = sum ds*conv[c],  part[cta][CM][a] = sum de*s,  ds = de gv (1 - s^2)
-// grid (ceil(Te/kTT), B), block = A rounded up to a warp multiple.
+// grid (ceil(Te/kPG), B), block = A rounded up to a warp multiple.
+constexpr int kPG = 8;   // frames per CTA: small tiles keep ~4 CTAs per SM in flight (the loop is latency-bound)
 template <int CM>
 __global__ void __launch_bounds__(512) att_param_grad_kernel(const float* __restrict__ P, const float* __restrict__ dzf,
                                                              const float* __restrict__ conv_save,
@@ -469,7 +501,7 @@ __global__ void __launch_bounds__(512) att_param_grad_kernel(const float* __rest
                                                              const float* __restrict__ gvec, int B, int L, int Te, int A,
                                                              int C, int Ap, float* __restrict__ dP,
                                                              float* __restrict__ part) {
-  const int b = blockIdx.y, te0 = blockIdx.x * kTT, a = threadIdx.x;
+  const int b = blockIdx.y, te0 = blockIdx.x * kPG, a = threadIdx.x;
   const bool ok = a < A;
   float matt[CM], dmatt[CM];
 #pragma unroll
@@ -479,7 +511,7 @@ __global__ void __launch_bounds__(512) att_param_grad_kernel(const float* __rest
   }
   const float gv = ok ? gvec[a] : 0.f;
   float dgv = 0.f;
-  const int ntl = min(kTT, Te - te0);
+  const int ntl = min(kPG, Te - te0);
   for (int tl = 0; tl < ntl; ++tl) {
     const int te = te0 + tl;
     const float pv = ok ? P[(static_cast<int64_t>(b) * Te + te) * A + a] : 0.f;
@@ -566,11 +598,21 @@ int las_att_dq(const float* ws_alloc, const float* dc_all, int L, int B, int Te,
   return 0;
 }
 
+int64_t las_att_scratch_floats(int B, int L, int Te, int A, int C, int K) {
+  // shared scratch of the attention backward: per-CTA partial sums of (a) the energy-MLP parameter
+  // gradients, (b) the conv-weight gradient
+  const int64_t Ap = (A + 31) / 32 * 32;
+  const int64_t a = static_cast<int64_t>((Te + kPG - 1) / kPG) * B * 17 * Ap;
+  const int64_t b = static_cast<int64_t>((L + kDT - 1) / kDT) * B * C * (2 * K + 1);
+  const int64_t c = static_cast<int64_t>((Te + kTT - 1) / kTT) * B * 17 * Ap;
+  return (a > b ? (a > c ? a : c) : (b > c ? b : c)) + 64;
+}
+
 int las_att_dconv(const float* dattc_all, const float* ws_alloc, int L, int B, int Te, int C, int K, float* dconv_w,
-                  void* stream) {
+                  float* scratch, void* stream) {
   LAS_REQUIRE(C >= 1 && C <= 16, "att_dconv: conv_channels %d out of range [1,16]", C);
   if (B == 0 || Te == 0 || L == 0) return 0;
-  att_dconv_kernel<<<2 * K + 1, 256, 0, static_cast<cudaStream_t>(stream)>>>(dattc_all, ws_alloc, L, B, Te, C, K, dconv_w); ++g_launches;
+  if (int rc = launch_att_dconv(dattc_all, ws_alloc, L, B, Te, C, K, dconv_w, scratch, static_cast<cudaStream_t>(stream))) return rc;
   LAS_LAUNCH_CHECK();
   return 0;
 }
@@ -583,7 +625,7 @@ int las_att_param_grads(const float* P, const float* dzf, const float* conv_save
   if (B == 0 || Te == 0 || L == 0) return 0;
   const int CM = (C <= 4) ? 4 : 16;
   const int threads = (A + 31) / 32 * 32;
-  const dim3 grid((Te + kTT - 1) / kTT, B);
+  const dim3 grid((Te + kPG - 1) / kPG, B);
   if (CM == 4) att_param_grad_kernel<4><<<grid, threads, 0, stream>>>(P, dzf, conv_save, de_all, mlp_att, gvec, B, L, Te, A, C, threads, dP, part_ws);
   else att_param_grad_kernel<16><<<grid, threads, 0, stream>>>(P, dzf, conv_save, de_all, mlp_att, gvec, B, L, Te, A, C, threads, dP, part_ws);
   ++g_launches;
@@ -748,7 +790,7 @@ int las_dec_bwd(const las_dec_args* a, void* stream_) {
   // reductions that were deferred out of the loop
   att_part_reduce_kernel<<<((a->C + 1) * A + 255) / 256, 256, 0, stream>>>(a->att_part, ncta, CM, Ap, A, a->C,
                                                                              a->dmlp_att, a->dgvec); ++g_launches;
-  att_dconv_kernel<<<ksz, 256, 0, stream>>>(a->dattc_all, a->ws, L, B, Te, a->C, a->K, a->dconv_w); ++g_launches;
+  if (int rc = launch_att_dconv(a->dattc_all, a->ws, L, B, Te, a->C, a->K, a->dconv_w, a->att_part, stream)) return rc;
   att_denc_kernel<<<dim3(Te, B), 256, 0, stream>>>(a->ws, a->dctx_all, L, B, Te, a->H, a->denc, a->denc_accumulate); ++g_launches;
   LAS_LAUNCH_CHECK();
   return 0;

@@ -159,7 +159,8 @@ struct DecFwdP {
   const float* embx;             // [B, L+1, 4Hd]
   const uint32_t* wr_pk;         // [Hd/4][KTg][32][4]  (pack mode 2)
   const uint32_t* dec_pk;        // [AT][KTd][32][4]    (pack mode 0)
-  const float* mlp_o_b;
+  const float* cbias;            // [B, O] mlp_o.bias + frame mean of the uncentred Q
+  const float* pbar;             // [B, A] frame mean removed from P: added to dz before it is sent / saved
   const float* conv_w;
   const float* mlp_att;
   const float* gvec;
@@ -306,6 +307,7 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
   const bool depi_ok = depi && a_d < A && (cl * NB + n_d) < p.B;
   const int d_w0 = (al >> 4) * g.KSd;
   float* dzf_ptr = p.dzf + static_cast<int64_t>(depi_ok ? cl * NB + n_d : 0) * L * A + (depi_ok ? a_d : 0);
+  const float pbar_d = depi_ok ? p.pbar[static_cast<int64_t>(cl * NB + n_d) * A + a_d] : 0.f;
   // P3: (frame tile, attention-dim slice) of this warp
   const int e_tt = warp / g.WPT, e_wi = warp % g.WPT;
   const bool e_act = warp < g.TT * g.WPT && ntl > 0;
@@ -434,7 +436,7 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
     }
     __syncthreads();
     if (depi_ok) {
-      const float v = red_gather(red, d_w0, g.KSd, al & 15, n_d);
+      const float v = red_gather(red, d_w0, g.KSd, al & 15, n_d) + pbar_d;
       dzf_ptr[0] = v;
       const uint32_t off = dzv_base + 4u * a_d;
       for (int qq = 0; qq < G; ++qq) st_remote_f32(mapa(off, n_d * G + qq), v);
@@ -563,12 +565,12 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
         __nv_bfloat16* zrow = p.zc + (static_cast<int64_t>(b_own) * R + t + 1) * ZC + Hd;
         if (va) {
           if (p.cpre) p.cpre[(static_cast<int64_t>(b_own) * L + t) * O + oa] = ca;
-          ha = __float2bfloat16(ca + p.mlp_o_b[oa]);
+          ha = __float2bfloat16(ca + p.cbias[static_cast<int64_t>(b_own) * O + oa]);
           zrow[oa] = ha;
         }
         if (vb) {
           if (p.cpre) p.cpre[(static_cast<int64_t>(b_own) * L + t) * O + ob] = cb;
-          hb = __float2bfloat16(cb + p.mlp_o_b[ob]);
+          hb = __float2bfloat16(cb + p.cbias[static_cast<int64_t>(b_own) * O + ob]);
           zrow[ob] = hb;
         }
         // pair (o, o+1): the partner is the lane 4 further (gq + 1)
@@ -664,7 +666,7 @@ bool dec_bgeom(const las_dec_args* a, int NB, BGeom& g) {
   g.o_matt2 = take(g.KTa * 2 * 32 * 8);
   g.o_cwB2 = take(g.NT8 * 32 * 16);
   g.o_dwnrx = take(2 * g.G * Te * 4);
-  g.o_ddzrx = take(g.G * NB * A * 2);
+  g.o_ddzrx = take(g.G * NB * A * 4);
   g.o_ddzB = take(g.KTap * 256);
   g.o_wt = take(Te * 4);
   g.o_cpre = take(O * 4);
@@ -725,7 +727,7 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
   uint2* mattB2 = reinterpret_cast<uint2*>(smem + g.o_matt2);      // [KTa][2][32]   k = attention dim, n = channel
   uint4* cwB2 = reinterpret_cast<uint4*>(smem + g.o_cwB2);         // [NT8][32]      k = channel, n = tap
   float* dwn_rx = reinterpret_cast<float*>(smem + g.o_dwnrx);      // [2][G][Te]
-  uint32_t* ddz_rx = reinterpret_cast<uint32_t*>(smem + g.o_ddzrx);   // [G][NB][A/2] bf16 pairs
+  float* ddz_rx = reinterpret_cast<float*>(smem + g.o_ddzrx);      // [G][NB][A] f32 partials (owner partials cancel: bf16 is not enough)
   uint32_t* ddzB = reinterpret_cast<uint32_t*>(smem + g.o_ddzB);   // [KTap][32][2]
   float* wt_s = reinterpret_cast<float*>(smem + g.o_wt);           // [Te] w_t
   float* cpre_s = reinterpret_cast<float*>(smem + g.o_cpre);       // [O]
@@ -782,7 +784,7 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
   for (int i = tid; i < g.KSb * g.FB * 64; i += kBT) dgB[i] = 0u;
   for (int i = tid; i < g.KTap * 64; i += kBT) ddzB[i] = 0u;
   for (int i = tid; i < 2 * G * Te; i += kBT) dwn_rx[i] = 0.f;
-  for (int i = tid; i < G * NB * A2; i += kBT) ddz_rx[i] = 0u;
+  for (int i = tid; i < G * NB * A; i += kBT) ddz_rx[i] = 0.f;
   for (int i = tid; i < g.TT * 16 * 16; i += kBT) conv_s[i] = 0.f;
   for (int i = tid; i < g.TT * 16; i += kBT) de_s[i] = 0.f;
   for (int i = tid; i < A; i += kBT) gv_s[i] = p.gvec[i];
@@ -1037,7 +1039,7 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
     }
     __syncthreads();
     DTRACE(4);
-    // B4: ddz partial -> all CTAs (bf16 pairs); conv-input gradient of my frames for step t-1
+    // B4: ddz partial -> all CTAs (f32); conv-input gradient of my frames for step t-1
     if (own_ok) {
       for (int ap = tid; ap < A2; ap += kBT) {
         float v0 = 0.f, v1 = 0.f;
@@ -1046,10 +1048,13 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
             const float2 v = *reinterpret_cast<const float2*>(ddz_part + tt * A + 2 * ap);
             v0 += v.x; v1 += v.y;
           }
-        const uint32_t word = pack_bf16x2(v0, v1);
-        const uint32_t off = ddzrx_base + 4u * ((q * NB + n_own) * A2 + ap);
+        const uint32_t off = ddzrx_base + 4u * ((q * NB + n_own) * A + 2 * ap);
 #pragma unroll
-        for (int r = 0; r < kCS; ++r) st_remote_u32(mapa(off, r), word);
+        for (int r = 0; r < kCS; ++r) {
+          const uint32_t ra = mapa(off, r);
+          st_remote_f32(ra, v0);
+          st_remote_f32(ra + 4u, v1);
+        }
       }
     }
     if (e_act) {
@@ -1116,7 +1121,7 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
       const int n = idx / A2, ap = idx - n * A2;
       float v0 = 0.f, v1 = 0.f;
       for (int qq = 0; qq < G; ++qq) {
-        const float2 v = unpack_bf16x2(ddz_rx[(qq * NB + n) * A2 + ap]);
+        const float2 v = *reinterpret_cast<const float2*>(ddz_rx + (qq * NB + n) * A + 2 * ap);
         v0 += v.x; v1 += v.y;
       }
       ddzB[bfrag_word(2 * ap, n)] = pack_bf16x2(v0, v1);
@@ -1224,7 +1229,7 @@ static int pick_nb(const las_dec_args* a, DGeom& g, BGeom& bg) {
 }
 
 int dec_persist_supported(const las_dec_args* a) {
-  if (a->mode != 0 || a->Q == nullptr || a->wr2_pk == nullptr) return 0;
+  if (a->mode != 0 || a->Q == nullptr || a->wr2_pk == nullptr || a->cbias == nullptr || a->pbar == nullptr) return 0;
   DGeom g;
   BGeom bg;
   if (pick_nb(a, g, bg) == 0) return 0;
@@ -1341,7 +1346,7 @@ int dec_persist_fwd(const las_dec_args* a, cudaStream_t stream) {
   p.g = g;
   p.P = a->P; p.Q = static_cast<const __nv_bfloat16*>(a->Q); p.embx = a->embx;
   p.wr_pk = static_cast<const uint32_t*>(a->wr2_pk); p.dec_pk = static_cast<const uint32_t*>(a->mlp_dec_pk);
-  p.mlp_o_b = a->mlp_o_b; p.conv_w = a->conv_w; p.mlp_att = a->mlp_att; p.gvec = a->gvec;
+  p.cbias = a->cbias; p.pbar = a->pbar; p.conv_w = a->conv_w; p.mlp_att = a->mlp_att; p.gvec = a->gvec;
   p.ws = a->ws; p.zc = static_cast<__nv_bfloat16*>(a->zc); p.dzf = a->dzf;
   p.gates_save = static_cast<__half*>(a->gates_save); p.c_save = a->c_save;
   p.cpre = a->cpre; p.conv_save = a->conv_save;

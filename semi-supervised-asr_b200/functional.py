@@ -281,18 +281,28 @@ class DecoderFn(torch.autograd.Function):
         persist, pers = False, None
         if mode == 0 and DEC_PERSISTENT:
             # cluster-persistent decoder: c_t = w_t @ Q + bias with Q = enc_h @ mlp_o.weight^T
+            # Q is stored centred over the frames of each utterance (the mean goes into a per-utterance
+            # bias): bf16 rounding then applies to the deviations, which is what the softmax backward
+            # (dw - <w, dw>, a cancellation when the alignment is flat) actually consumes
             mlp_o_bf = cvt_bf16(W["mlp_o_w"])
-            Qm = gemm(enc_bf, H, 0, mlp_o_bf, H, 0, B * Te, O, H, out_bf16=True)
+            Qf = gemm(enc_bf, H, 0, mlp_o_bf, H, 0, B * Te, O, H).view(B, Te, O)
+            Qbar = Qf.mean(dim=1, keepdim=True)
+            Qm = (Qf - Qbar).to(BF16).view(B * Te, O)
+            cbias = (Qbar.view(B, O) + W["mlp_o_b"]).contiguous()
+            # likewise P = mlp_enc(enc_h): the kernels hold P - mean_te(P) in bf16 and add the mean to dz in f32
+            Pbar = Pm.view(B, Te, A).mean(dim=1)
+            Pc = (Pm.view(B, Te, A) - Pbar.unsqueeze(1)).contiguous()
             wr2_pk = pack_afrag(wr_cat, 2, Hd)
-            a.Q, a.wr2_pk = ptr(Qm), ptr(wr2_pk)
+            a.Q, a.wr2_pk, a.cbias, a.pbar = ptr(Qm), ptr(wr2_pk), ptr(cbias), ptr(Pbar)
             persist = bool(_lib.lib().las_dec_persistent_supported(ctypes.byref(a)))
             if persist:
                 cpre = torch.empty(B, L, O, **f32)
                 conv_save = torch.empty(B, L, Te, 16, **f32)
                 a.cpre, a.conv_save = ptr(cpre), ptr(conv_save)
-                pers = dict(Qm=Qm, wr2_pk=wr2_pk, cpre=cpre, conv_save=conv_save, mlp_o_bf=mlp_o_bf)
+                a.P = ptr(Pc)
+                pers = dict(Qm=Qm, wr2_pk=wr2_pk, cpre=cpre, conv_save=conv_save, mlp_o_bf=mlp_o_bf, cbias=cbias, Pc=Pc, Pbar=Pbar)
             else:
-                a.Q, a.wr2_pk = None, None
+                a.Q, a.wr2_pk, a.cbias, a.pbar = None, None, None, None
         _lib.check(_lib.lib().las_dec_fwd(ctypes.byref(a), _lib.stream_ptr()))
         out_bf = cvt_bf16(W["out_w"])                                                 # [V, ZC]
         if mode == 0:
@@ -338,7 +348,7 @@ class DecoderFn(torch.autograd.Function):
         dattc_all = torch.empty(L, B, Te, C, **f32)
         ddz_all = torch.zeros(n * A + 64, **f32)
         dP = torch.zeros(B * Te, A, **f32)
-        att_part = torch.empty(((Te + 31) // 32) * B * 17 * ((A + 31) // 32 * 32), **f32)
+        att_part = torch.empty(_lib.lib().las_att_scratch_floats(B, L, Te, A, C, K), **f32)
         dc_state = torch.empty(B, Hd, **f32)
         dgates = torch.zeros(n, 4 * Hd, device=dev, dtype=BF16)
         d_mlp_att = torch.zeros(A, C, **f32)
@@ -371,12 +381,15 @@ class DecoderFn(torch.autograd.Function):
             dc_all = torch.zeros(B, L, O, **f32)
             a.Q, a.wr2_pk, a.cpre, a.conv_save = ptr(pers["Qm"]), ptr(pers["wr2_pk"]), ptr(pers["cpre"]), ptr(pers["conv_save"])
             a.wrT2_pk, a.mlp_decT2_pk, a.de_all, a.dc_all = ptr(wrT2), ptr(decT2), ptr(de_all), ptr(dc_all)
+            a.cbias, a.pbar, a.P = ptr(pers["cbias"]), ptr(pers["Pbar"]), ptr(pers["Pc"])
+            if not L_.las_dec_persistent_supported(ctypes.byref(a)):
+                raise _lib.LasError("decoder backward: the forward ran the persistent kernel but the backward would not")
         _lib.check(_lib.lib().las_dec_bwd(ctypes.byref(a), _lib.stream_ptr()))
         if pers is not None:
-            call("las_att_param_grads", ptr(S["Pm"]), ptr(S["dzf"]), ptr(pers["conv_save"]), ptr(de_all), ptr(S["mlp_att"]),
+            call("las_att_param_grads", ptr(pers["Pc"]), ptr(S["dzf"]), ptr(pers["conv_save"]), ptr(de_all), ptr(S["mlp_att"]),
                  ptr(S["gvec"]), B, L, Te, A, C, ptr(dP), ptr(att_part), ptr(d_mlp_att), ptr(d_gvec))
             d_conv_t = torch.zeros(C, 2 * K + 1, **f32)
-            call("las_att_dconv", ptr(dattc_all), ptr(S["ws"]), L, B, Te, C, K, ptr(d_conv_t))
+            call("las_att_dconv", ptr(dattc_all), ptr(S["ws"]), L, B, Te, C, K, ptr(d_conv_t), ptr(att_part))
             d_conv = d_conv_t
             dQ = torch.empty(B * Te, O, **f32)
             call("las_att_dq", ptr(S["ws"]), ptr(dc_all), L, B, Te, O, ptr(dQ))
