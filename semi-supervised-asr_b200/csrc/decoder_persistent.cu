@@ -618,6 +618,7 @@ constexpr int kBT = 384;
 constexpr int kBW = 12;
 constexpr int kMaxFB = 20;     // Wr^T fragments per warp
 constexpr int kMaxFD2 = 4;     // mlp_dec^T fragments per warp
+constexpr int kCwLd = 20;      // row stride (floats) of the transposed conv weights: conflict-free LDS.128 over 8 consecutive taps
 
 struct BGeom {
   int NB, G, UPC, OPC, RPC;    // utterances per cluster, owners per utterance, z units / c dims / rows per CTA
@@ -627,7 +628,7 @@ struct BGeom {
   int KTo, AT8, NC, NT8;       // O/16; A/8; conv channel n-tiles; 8-wide tiles over the conv taps
   int Pld, Qld;
   int o_dgB, o_red, o_dcbuf, o_P, o_Q, o_matt, o_matt2, o_cwB2, o_dwnrx, o_ddzrx, o_ddzB, o_wt, o_cpre, o_dzv,
-      o_conv, o_de, o_dwpart, o_dwns, o_dwnout, o_gv, o_wred, o_scratch;
+      o_conv, o_de, o_dwpart, o_dwns, o_dwnout, o_dwnpart, o_gv, o_wred, o_scratch;
   int smem;
 };
 
@@ -664,7 +665,7 @@ bool dec_bgeom(const las_dec_args* a, int NB, BGeom& g) {
   g.o_Q = take(g.TT * 16 * g.Qld * 2);
   g.o_matt = take(g.AT8 * 32 * 16);
   g.o_matt2 = take(g.KTa * 2 * 32 * 8);
-  g.o_cwB2 = take(g.NT8 * 32 * 16);
+  g.o_cwB2 = take(ksz * kCwLd * 4);
   g.o_dwnrx = take(2 * g.G * Te * 4);
   g.o_ddzrx = take(g.G * NB * A * 4);
   g.o_ddzB = take(g.KTap * 256);
@@ -676,6 +677,7 @@ bool dec_bgeom(const las_dec_args* a, int NB, BGeom& g) {
   g.o_dwpart = take(g.WPT * g.TT * 16 * 4);
   g.o_dwns = take(Te * 4);
   g.o_dwnout = take(Te * 4);
+  g.o_dwnpart = take((kBT / Te > 0 ? kBT / Te : 1) * Te * 4);
   g.o_gv = take(A * 4);
   g.o_wred = take(kBW * 4);
   // phase-B scratch: ddz partials [TT][A] f32 + dconv partial accumulators [12 warps][2][32] float4
@@ -725,7 +727,8 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
   __nv_bfloat16* Q_s = reinterpret_cast<__nv_bfloat16*>(smem + g.o_Q);   // [TT*16][Qld] my frames of Q
   uint4* mattB = reinterpret_cast<uint4*>(smem + g.o_matt);        // [AT8][32]      k = channel, n = attention dim
   uint2* mattB2 = reinterpret_cast<uint2*>(smem + g.o_matt2);      // [KTa][2][32]   k = attention dim, n = channel
-  uint4* cwB2 = reinterpret_cast<uint4*>(smem + g.o_cwB2);         // [NT8][32]      k = channel, n = tap
+  float* cw_t = reinterpret_cast<float*>(smem + g.o_cwB2);         // [2K+1][kCwLd] transposed conv weights (channels padded to 16)
+  float* dwn_part = reinterpret_cast<float*>(smem + g.o_dwnpart);  // [kBT/Te][Te]
   float* dwn_rx = reinterpret_cast<float*>(smem + g.o_dwnrx);      // [2][G][Te]
   float* ddz_rx = reinterpret_cast<float*>(smem + g.o_ddzrx);      // [G][NB][A] f32 partials (owner partials cancel: bf16 is not enough)
   uint32_t* ddzB = reinterpret_cast<uint32_t*>(smem + g.o_ddzB);   // [KTap][32][2]
@@ -812,19 +815,9 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
     }
     mattB2[i] = make_uint2(pack_bf16x2(m[0], m[1]), pack_bf16x2(m[2], m[3]));
   }
-  for (int i = tid; i < g.NT8 * 32; i += kBT) {
-    // k = channel, n = tap 8*nt + (l >> 2)
-    const int nt = i >> 5, l = i & 31, kk = 8 * nt + (l >> 2), c0 = 2 * (l & 3);
-    float m[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int c = c0 + (k & 1) + 8 * (k >> 1);
-      m[k] = (c < C && kk < ksz) ? p.conv_w[c * ksz + kk] : 0.f;
-    }
-    uint4 v;
-    split_bf16x2(m[0], m[1], v.x, v.z);
-    split_bf16x2(m[2], m[3], v.y, v.w);
-    cwB2[i] = v;
+  for (int i = tid; i < ksz * kCwLd; i += kBT) {
+    const int k = i / kCwLd, c = i % kCwLd;
+    cw_t[i] = (c < C) ? p.conv_w[c * ksz + k] : 0.f;
   }
   for (int i = tid; i < g.TT * 16 * g.Pld; i += kBT) {
     const int r = i / g.Pld, a = i % g.Pld;
@@ -926,7 +919,6 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
 
     // ================= phase B: attention backward for my frames =================
     // B1: dw = Q dc (tensor cores, K split over the warps of a frame tile); softmax dot product
-    if (tid < Te) dwn_out[tid] = 0.f;
     {
       float part = 0.f;
       if (own_ok) {
@@ -1057,59 +1049,75 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
         }
       }
     }
-    if (e_act) {
-      // dconv of my frame tile in A-fragment position (sum of the partials of the WPT warps)
+    if (e_act && e_wi == 0) {
+      // dconv of my frame tile: sum of the partials of the WPT warps -> conv_s (reused) and dattc_all
       float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int w = 0; w < g.WPT; ++w) {
         const float4 a = dcred[((e_tt * g.WPT + w) * 2) * 32 + lane], b = dcred[((e_tt * g.WPT + w) * 2 + 1) * 32 + lane];
         s0.x += a.x; s0.y += a.y; s0.z += a.z; s0.w += a.w;
         s1.x += b.x; s1.y += b.y; s1.z += b.z; s1.w += b.w;
       }
-      if (e_wi == 0) {
-        // dattc_all[t][b][te][c] for the conv-weight gradient (post-loop kernel)
-        float* drow = p.dattc_all + ((static_cast<int64_t>(t) * p.B + b_own) * Te + cm) * C;
-        const int c0 = 2 * tig;
-        if (gq + 16 * e_tt < ntl) {
-          if (c0 < C) drow[gq * C + c0] = s0.x;
-          if (c0 + 1 < C) drow[gq * C + c0 + 1] = s0.y;
-          if (c0 + 8 < C) drow[gq * C + c0 + 8] = s1.x;
-          if (c0 + 9 < C) drow[gq * C + c0 + 9] = s1.y;
+      const int r0 = 16 * e_tt + gq, r1 = r0 + 8, c0 = 2 * tig;
+      *reinterpret_cast<float2*>(conv_s + r0 * 16 + c0) = make_float2(s0.x, s0.y);
+      *reinterpret_cast<float2*>(conv_s + r1 * 16 + c0) = make_float2(s0.z, s0.w);
+      *reinterpret_cast<float2*>(conv_s + r0 * 16 + 8 + c0) = make_float2(s1.x, s1.y);
+      *reinterpret_cast<float2*>(conv_s + r1 * 16 + 8 + c0) = make_float2(s1.z, s1.w);
+      // dattc_all[t][b][te][c] for the conv-weight gradient (post-loop kernel)
+      float* drow = p.dattc_all + ((static_cast<int64_t>(t) * p.B + b_own) * Te + cm) * C;
+      if (r0 < ntl) {
+        if (c0 < C) drow[gq * C + c0] = s0.x;
+        if (c0 + 1 < C) drow[gq * C + c0 + 1] = s0.y;
+        if (c0 + 8 < C) drow[gq * C + c0 + 8] = s1.x;
+        if (c0 + 9 < C) drow[gq * C + c0 + 9] = s1.y;
+      }
+      if (r1 < ntl) {
+        if (c0 < C) drow[(gq + 8) * C + c0] = s0.z;
+        if (c0 + 1 < C) drow[(gq + 8) * C + c0 + 1] = s0.w;
+        if (c0 + 8 < C) drow[(gq + 8) * C + c0 + 8] = s1.z;
+        if (c0 + 9 < C) drow[(gq + 8) * C + c0 + 9] = s1.w;
+      }
+    }
+    __syncthreads();
+    // conv-input gradient of my frames for step t-1: dwn[j] = sum_{tl,c} dconv[tl][c] cw[c][j - te + K].
+    // thread -> (output frame j, frame residue); deterministic two-stage sum (no shared-memory float atomics)
+    const int ngrp = max(1, kBT / Te);
+    if (own_ok && t > 0 && tid < ngrp * Te) {
+      const int gi = tid / Te, j = tid - gi * Te;
+      float acc[12];
+#pragma unroll
+      for (int c = 0; c < 12; ++c) acc[c] = 0.f;
+      float acc2[4] = {0.f, 0.f, 0.f, 0.f};
+      const int nc4 = (C + 3) >> 2;
+      for (int tl = gi; tl < ntl; tl += ngrp) {
+        const int k = j - (te0 + tl) + K;
+        if (k < 0 || k > 2 * K) continue;
+        const float4* dr = reinterpret_cast<const float4*>(conv_s + tl * 16);
+        const float4* cr = reinterpret_cast<const float4*>(cw_t + k * kCwLd);
+        const float4 d0 = dr[0], d1 = dr[1], w0 = cr[0], w1 = cr[1];
+        acc[0] = fmaf(d0.x, w0.x, acc[0]); acc[1] = fmaf(d0.y, w0.y, acc[1]); acc[2] = fmaf(d0.z, w0.z, acc[2]); acc[3] = fmaf(d0.w, w0.w, acc[3]);
+        acc[4] = fmaf(d1.x, w1.x, acc[4]); acc[5] = fmaf(d1.y, w1.y, acc[5]); acc[6] = fmaf(d1.z, w1.z, acc[6]); acc[7] = fmaf(d1.w, w1.w, acc[7]);
+        if (nc4 > 2) {
+          const float4 d2 = dr[2], w2 = cr[2];
+          acc[8] = fmaf(d2.x, w2.x, acc[8]); acc[9] = fmaf(d2.y, w2.y, acc[9]); acc[10] = fmaf(d2.z, w2.z, acc[10]); acc[11] = fmaf(d2.w, w2.w, acc[11]);
         }
-        if (gq + 8 + 16 * e_tt < ntl) {
-          if (c0 < C) drow[(gq + 8) * C + c0] = s0.z;
-          if (c0 + 1 < C) drow[(gq + 8) * C + c0 + 1] = s0.w;
-          if (c0 + 8 < C) drow[(gq + 8) * C + c0 + 8] = s1.z;
-          if (c0 + 9 < C) drow[(gq + 8) * C + c0 + 9] = s1.w;
+        if (nc4 > 3) {
+          const float4 d3 = dr[3], w3 = cr[3];
+          acc2[0] = fmaf(d3.x, w3.x, acc2[0]); acc2[1] = fmaf(d3.y, w3.y, acc2[1]); acc2[2] = fmaf(d3.z, w3.z, acc2[2]); acc2[3] = fmaf(d3.w, w3.w, acc2[3]);
         }
       }
-      if (t > 0) {
-        uint32_t Dh[4], Dl[4];
-        split_bf16x2(s0.x, s0.y, Dh[0], Dl[0]);
-        split_bf16x2(s0.z, s0.w, Dh[1], Dl[1]);
-        split_bf16x2(s1.x, s1.y, Dh[2], Dl[2]);
-        split_bf16x2(s1.z, s1.w, Dh[3], Dl[3]);
-        // G[i][k] = sum_c dconv[i][c] cw[c][k]; dwn[j] += G[i][k] with j = i + k - K
-        const int k_lo = max(0, K - (cm + 15)), k_hi = min(2 * K, K + Te - 1 - cm);
-        for (int nt = (k_lo >> 3) + e_wi; nt <= (k_hi >> 3); nt += g.WPT) {
-          const uint4 b = cwB2[nt * 32 + lane];
-          float acc[4] = {0.f, 0.f, 0.f, 0.f};
-          mma_bf16_16816(acc, Dh, b.x, b.y);
-          mma_bf16_16816(acc, Dl, b.x, b.y);
-          mma_bf16_16816(acc, Dh, b.z, b.w);
-          const int j0 = cm + gq + 8 * nt + 2 * tig - K;   // row gq, column 2*tig
-          if (j0 >= 0 && j0 < Te) atomicAdd(dwn_out + j0, acc[0]);
-          if (j0 + 1 >= 0 && j0 + 1 < Te) atomicAdd(dwn_out + j0 + 1, acc[1]);
-          if (j0 + 8 >= 0 && j0 + 8 < Te) atomicAdd(dwn_out + j0 + 8, acc[2]);
-          if (j0 + 9 >= 0 && j0 + 9 < Te) atomicAdd(dwn_out + j0 + 9, acc[3]);
-        }
-      }
+      float sacc = (acc2[0] + acc2[1]) + (acc2[2] + acc2[3]);
+#pragma unroll
+      for (int c = 0; c < 12; ++c) sacc += acc[c];
+      dwn_part[gi * Te + j] = sacc;
     }
     __syncthreads();
     if (own_ok && t > 0) {
       // partial conv-input gradient -> every owner of this utterance (slot q, parity of step t-1)
-      for (int i = tid; i < Te * G; i += kBT) {
-        const int qq = i / Te, j = i - qq * Te;
-        st_remote_f32(mapa(dwnrx_base + 4u * (((par ^ 1) * G + q) * Te + j), n_own * G + qq), dwn_out[j]);
+      for (int j = tid; j < Te; j += kBT) {
+        float v = 0.f;
+        for (int gi = 0; gi < ngrp; ++gi) v += dwn_part[gi * Te + j];
+        for (int qq = 0; qq < G; ++qq)
+          st_remote_f32(mapa(dwnrx_base + 4u * (((par ^ 1) * G + q) * Te + j), n_own * G + qq), v);
       }
     }
     DTRACE(5);

@@ -47,3 +47,28 @@ else:
     run(3, 40, 64, 48, 5, 7, 32, 20, 12)
     run(9, 37, 128, 64, 10, 20, 16, 34, 11)
     run(32, 125, 320, 320, 10, 100, 128, 34, 126)
+
+if os.environ.get("LAS_TRACE"):
+    LIB = pkg("_lib")
+    torch.manual_seed(0)
+    dev = torch.device("cuda")
+    B, Te, Hd, A, C, K, E, V, L = 32, 125, 320, 320, 10, 100, 128, 34, 126
+    att = M.AttLoc(Hd, Hd, A, C, K, Hd)
+    dec = M.Decoder(V, E, Hd, att, Hd, 0.0, 1, 2, 0).to(dev)
+    enc_h = torch.relu(torch.randn(B, Te, Hd, device=dev)).requires_grad_(True)
+    lens = torch.full((B,), Te, dtype=torch.int32, device=dev)
+    ys_in = torch.randint(3, V, (B, L + 1), device=dev)
+    ys_out = torch.randint(3, V, (B, L), device=dev)
+    Fn.DEC_PERSISTENT = True
+    dbg = torch.zeros(256, device=dev, dtype=torch.int64)
+    LIB.lib().las_set_debug_buffer(dbg.data_ptr())
+    logits, logp, pred, ws = dec.forward_dev(enc_h, lens, ys_in, ys_out, L, 0)
+    (-logp.mean()).backward()
+    torch.cuda.synchronize()
+    LIB.lib().las_set_debug_buffer(None)
+    d = dbg.cpu()[64:128].view(4, 16)
+    names = ["A:mma+epi", "BAR_A", "B1-2:dw,de", "B3:energy", "B4:ddz,dwn", "BAR_B", "C:cell", "BAR_C"]
+    print(" ".join(f"{n:>11s}" for n in names))
+    for s_ in range(4):
+        row = d[s_]
+        print(" ".join(f"{int(row[i + 1] - row[i]):11d}" for i in range(8)), "| step", int(d[s_ + 1, 0] - row[0]) if s_ < 3 else "")
