@@ -200,6 +200,13 @@ typedef struct las_dec_args {
   float* de_all;             /* backward out: f32 [B, L, Te] energy gradients                   */
   float* dc_all;             /* backward out: f32 [B, L, O] total gradient of c_t               */
   const float* cbias;        /* f32 [B, O]: mlp_o.bias + the frame mean removed from Q          */
+  /* backward of the free-running smooth mode (mode 2: the gradient of logit_t also arrives through the next
+   * input embedding, so the output layer's backward runs inside the loop; dzc_all is then an output) */
+  const void* weT_pk;        /* fragments (mode 0, transposed) of W_ih[:, :E]  ([Ep, 4Hd])      */
+  const void* outT_pk;       /* fragments (mode 0, transposed) of output_layer.weight ([Hd+O, V]) */
+  const float* dlogits;      /* f32 [B, L+1, V] loss gradient of the logits                     */
+  float* dl_tot;             /* out: f32 [B, L+1, Vq] (+64 slack), Vq = V rounded up to 4, zeroed: total gradient of the logits */
+  float* demb_buf;           /* scratch f32 [B, Ep]                                             */
   const float* pbar;         /* f32 [B, A]: frame mean removed from P (then P holds P - pbar and dzf = mlp_dec(z_t) + pbar) */
 } las_dec_args;
 

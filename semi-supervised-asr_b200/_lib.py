@@ -28,7 +28,7 @@ class DecArgs(ctypes.Structure):
             "ws", "zc", "ctx", "c_state", "emb_op", "logits", "pred", "e_buf", "dzf", "gates_save", "c_save",
             "wrT_pk", "mlp_oT_pk", "mlp_decT_pk", "dzc_all", "dcz_tot", "dcz_all", "dctx_all", "dw_buf",
             "dattc_all", "ddz_all", "dP", "att_part", "dc_state", "dgates", "dmlp_att", "dgvec", "dconv_w",
-            "denc", "Q", "wr2_pk", "cpre", "conv_save", "wrT2_pk", "mlp_decT2_pk", "de_all", "dc_all", "cbias", "pbar")]
+            "denc", "Q", "wr2_pk", "cpre", "conv_save", "wrT2_pk", "mlp_decT2_pk", "de_all", "dc_all", "cbias", "weT_pk", "outT_pk", "dlogits", "dl_tot", "demb_buf", "pbar")]
     )
 
 

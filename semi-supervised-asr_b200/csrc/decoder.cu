@@ -247,6 +247,46 @@ __global__ void __launch_bounds__(128) next_emb_kernel(NextEmbParams p) {
   }
 }
 
+// Backward of the smooth input embedding emb_{t+1} = softmax(s * logit_t) @ E (model.py:341): adds
+// s * p * (dp - <p, dp>), dp[v] = <E[v, :], demb_{t+1}>, to the loss gradient of logit_t. One warp
+// per utterance; V <= 1024.
+struct SmoothBwdParams {
+  int B, V, E;
+  float scaling;
+  const float* logits; int64_t lg_ld;     // logits_t rows
+  const float* demb; int64_t de_ld;       // [B] rows: W_ih[:, :E]^T dgates_{t+1}
+  const float* emb_w;                     // [V, E]
+  const float* dlogits; int64_t dl_ld;    // incoming gradient rows
+  float* dl_tot; int64_t dt_ld;           // out rows
+};
+__global__ void __launch_bounds__(128) smooth_dlogit_kernel(SmoothBwdParams p) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (b >= p.B) return;
+  const float* x = p.logits + b * p.lg_ld;
+  const float* de = p.demb + b * p.de_ld;
+  float mx = -INFINITY;
+  for (int v = lane; v < p.V; v += 32) mx = fmaxf(mx, x[v]);
+  mx = warp_max(mx);
+  float se = 0.f, pd = 0.f;
+  for (int v = lane; v < p.V; v += 32) {
+    const float pv = __expf(p.scaling * (x[v] - mx));
+    float dp = 0.f;
+    for (int j = 0; j < p.E; ++j) dp = fmaf(p.emb_w[v * p.E + j], de[j], dp);
+    se += pv;
+    pd = fmaf(pv, dp, pd);
+  }
+  se = warp_sum(se);
+  pd = warp_sum(pd);
+  const float inv = 1.f / se, dot = pd * inv;
+  for (int v = lane; v < p.V; v += 32) {
+    const float pv = __expf(p.scaling * (x[v] - mx)) * inv;
+    float dp = 0.f;
+    for (int j = 0; j < p.E; ++j) dp = fmaf(p.emb_w[v * p.E + j], de[j], dp);
+    p.dl_tot[b * p.dt_ld + v] = p.dlogits[b * p.dl_ld + v] + p.scaling * pv * (dp - dot);
+  }
+}
+
 // Initial alignment (model.py:151-153): 1/len over valid frames, exact zeros beyond.
 __global__ void att_init_kernel(const int32_t* __restrict__ enc_lens, int B, int Te, float* w, int64_t w_ld) {
   const int b = blockIdx.x;
@@ -721,8 +761,11 @@ int las_dec_fwd(const las_dec_args* a, void* stream_) {
 int las_dec_bwd(const las_dec_args* a, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (int rc = check_args(a)) return rc;
-  LAS_REQUIRE(a->mode == 0, "decoder backward: only the teacher-forced mode is implemented here");
   if (dec_persist_supported(a)) return dec_persist_bwd(a, stream);   // one cluster-persistent launch
+  const bool smooth = a->mode == 2;
+  if (smooth)
+    LAS_REQUIRE(a->weT_pk && a->outT_pk && a->dlogits && a->dl_tot && a->demb_buf && a->logits && a->emb_w,
+                "decoder backward (smooth free-run): missing buffers");
   const int B = a->B, L = a->L, Te = a->Te, Hd = a->Hd, O = a->O, A = a->A;
   const int ZC = Hd + O;
   const int64_t R = L + 1;
@@ -760,7 +803,30 @@ int las_dec_bwd(const las_dec_args* a, void* stream_) {
   cb.dG = dgates; cb.dg_ld_b = R * 4 * Hd; cb.dg_ld_t = 4 * Hd;
   cb.dc_state = a->dc_state; cb.B = B; cb.T = L; cb.H = Hd; cb.ndir = 1;
 
+  const int V = a->V, E = a->E, Ep = (E + 15) / 16 * 16;
+  const int64_t Vq = (V + 3) / 4 * 4;
   for (int t = L - 1; t >= 0; --t) {
+    if (smooth) {
+      // (0) free-running smooth mode: the gradient of logit_t also arrives through emb_{t+1}; only then
+      //     is the output layer's contribution to d[z_t; c_t] known
+      float* dlt = a->dl_tot + static_cast<int64_t>(t + 1) * Vq;   // rows padded to Vq floats: 8-byte aligned operand loads
+      if (t + 1 < L) {
+        smallmm(static_cast<const uint32_t*>(a->weT_pk), Ep, 4 * Hd, dgates + static_cast<int64_t>(t + 1) * 4 * Hd, 0,
+                R * 4 * Hd, B, nullptr, nullptr, 0, a->demb_buf, Ep, nullptr, 0, stream);
+        SmoothBwdParams sp = {};
+        sp.B = B; sp.V = V; sp.E = E; sp.scaling = a->smooth_scaling;
+        sp.logits = a->logits + static_cast<int64_t>(t + 1) * V; sp.lg_ld = R * V;
+        sp.demb = a->demb_buf; sp.de_ld = Ep; sp.emb_w = a->emb_w;
+        sp.dlogits = a->dlogits + static_cast<int64_t>(t + 1) * V; sp.dl_ld = R * V;
+        sp.dl_tot = dlt; sp.dt_ld = R * Vq;
+        smooth_dlogit_kernel<<<(B + 3) / 4, 128, 0, stream>>>(sp); ++g_launches;
+      } else {
+        LAS_CUDA(cudaMemcpy2DAsync(dlt, R * Vq * sizeof(float), a->dlogits + static_cast<int64_t>(t + 1) * V,
+                                   R * V * sizeof(float), V * sizeof(float), B, cudaMemcpyDeviceToDevice, stream));
+      }
+      smallmm(static_cast<const uint32_t*>(a->outT_pk), ZC, V, dlt, 1, R * Vq, B, nullptr, nullptr, 0,
+              const_cast<float*>(a->dzc_all) + static_cast<int64_t>(t + 1) * ZC, R * ZC, nullptr, 0, stream);
+    }
     // (1) d[z_t; c_t] = dzc_all (from the output layer) + Wr^T dgates_{t+1}  (row L of dgates is zero)
     smallmm(static_cast<const uint32_t*>(a->wrT_pk), ZC, 4 * Hd, dgates + static_cast<int64_t>(t + 1) * 4 * Hd, 0, R * 4 * Hd, B,
             nullptr, a->dzc_all + static_cast<int64_t>(t + 1) * ZC, R * ZC, a->dcz_tot, ZC,

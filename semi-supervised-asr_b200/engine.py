@@ -117,3 +117,73 @@ class SupervisedTrainer:
 
     def step(self, xs, ilens, ys):
         return self.run(self.stage(xs, ilens, ys))
+
+
+def _clip_and_step(opt, params, max_grad_norm):
+    """clip_grad_norm_ + optimizer.step for the fused optimiser or a stock torch optimiser."""
+    if hasattr(opt, "clip_and_step"):
+        return opt.clip_and_step(max_grad_norm)
+    norm = torch.nn.utils.clip_grad_norm_(params, max_norm=max_grad_norm)
+    opt.step()
+    return norm
+
+
+class SSLTrainer:
+    """`Solver.gen_train_one_iteration` (solver.py:460-495): free-running decode of the unpaired speech with the
+    smooth embedding, LM ("judge") probabilities of the decoded tokens as per-token weights, paired supervised
+    loss, loss = sup + unsup_weight * unsup, backward, clip, generator step.
+
+    The judge's output enters the loss only as a weight (its input is the discrete prediction), so
+    it is evaluated under no_grad here; the reference leaves it attached, which only fills the judge's unused
+    `.grad` fields (dis_opt never steps in this phase)."""
+
+    def __init__(self, model, judge, optimizer, max_grad_norm=5.0, unsup_weight=0.001, proportion=0.125,
+                 smooth=True, scaling=3.0):
+        self.model, self.judge, self.opt = model, judge, optimizer
+        self.max_grad_norm, self.unsup_weight, self.proportion = max_grad_norm, unsup_weight, proportion
+        self.smooth, self.scaling = smooth, scaling
+
+    def losses(self, lab, unlab):
+        m = self.model
+        (xs, ilens, ys), (uxs, uilens) = lab, unlab
+        Lu = int(uxs.size(1) * self.proportion)                                    # solver.py:469
+        _, u_logp, u_pred, _ = m(uxs, uilens, ys=None, sample=False, label_smoothing=False, max_dec_timesteps=Lu,
+                                 smooth=self.smooth, scaling=self.scaling)
+        with torch.no_grad():
+            _, lm_probs, _ = self.judge(ys=u_pred, discrete_input=False)           # solver.py:473
+        mask = (u_pred != m.decoder.eos).float()                                    # solver.py:477
+        unsup = -torch.sum(lm_probs * u_logp * mask) / torch.sum(mask)
+        _, logp, _, _ = m(xs, ilens, ys)
+        sup = -torch.mean(logp)                                                     # solver.py:482
+        return sup + self.unsup_weight * unsup, sup, unsup, (u_logp, u_pred, lm_probs)
+
+    def step(self, lab, unlab):
+        self.model.train()
+        self.judge.train()
+        loss, sup, unsup, _ = self.losses(lab, unlab)
+        self.opt.zero_grad()
+        loss.backward()
+        norm = _clip_and_step(self.opt, list(self.model.parameters()), self.max_grad_norm)
+        return loss.detach(), sup.detach(), unsup.detach(), norm
+
+
+class JudgeTrainer:
+    """`Solver.judge_train_one_iteration` (solver.py:288-301): masked LM loss over len+5 positions, backward,
+    clip, plain Adam step."""
+
+    def __init__(self, judge, optimizer, max_grad_norm=5.0):
+        self.judge, self.opt, self.max_grad_norm = judge, optimizer, max_grad_norm
+
+    def losses(self, ys):
+        log_probs, probs, _ = self.judge(ys)
+        loss = -self.judge.mask_and_cal_sum(log_probs, ys)
+        avg_prob = self.judge.mask_and_cal_sum(probs, ys)
+        return loss, avg_prob
+
+    def step(self, ys):
+        self.judge.train()
+        loss, avg_prob = self.losses(ys)
+        self.opt.zero_grad()
+        loss.backward()
+        norm = _clip_and_step(self.opt, list(self.judge.parameters()), self.max_grad_norm)
+        return loss.detach(), avg_prob.detach(), norm

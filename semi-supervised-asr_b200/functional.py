@@ -310,7 +310,9 @@ class DecoderFn(torch.autograd.Function):
         ctx.geom = (B, Te, H, Hd, O, A, V, E, C, K, L, mode, att_scaling, smooth_scaling)
         ctx.saved = dict(enc_bf=enc_bf, Pm=Pm, mlp_enc_bf=mlp_enc_bf, wr_cat=wr_cat, ws=ws, zc=zc, cx=cx, dzf=dzf,
                          gates=gates, csave=csave, conv_w=conv_w, mlp_att=mlp_att, gvec=gvec, emb_in=emb_in,
-                         out_bf=out_bf, ys_in=ys_in, keep=keep, pers=pers)
+                         out_bf=out_bf, ys_in=ys_in, keep=keep, pers=pers, bos=bos,
+                         logits=logits if mode != 0 else None,
+                         emb_op=(emb_op[:B * R * Ep].view(B * R, Ep) if mode != 0 else None))
         ctx.W = W
         ctx.mark_non_differentiable(ws)
         if pred is not None:
@@ -321,8 +323,6 @@ class DecoderFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dlogits, _dws, _dpred):
         B, Te, H, Hd, O, A, V, E, C, K, L, mode, att_scaling, smooth_scaling = ctx.geom
-        if mode != 0:
-            raise _lib.LasError("decoder backward is implemented for the teacher-forced mode only")
         S, W = ctx.saved, ctx.W
         dev = dlogits.device
         R, ZC, Ep = L + 1, Hd + O, _r16(E)
@@ -332,12 +332,25 @@ class DecoderFn(torch.autograd.Function):
         a.mode, a.att_scaling, a.smooth_scaling = mode, att_scaling, smooth_scaling
         # output layer (model.py:293): dW = dlogits^T [z;c], d[z;c] = dlogits W
         dl = dlogits.contiguous().view(n, V)
-        dl_bf = cvt_bf16(dl)                                                          # [n, Vp]
-        Vp = dl_bf.shape[1]
         zc = S["zc"]
-        d_out_w = gemm(dl_bf, Vp, 1, zc, ZC, 1, V, ZC, n)
-        d_out_b = colsum(dl, V)
-        dzc_all = gemm(dl_bf, Vp, 0, S["out_bf"], ZC, 1, n, ZC, V)                    # f32 [n, ZC]
+        dl_tot = None
+        if mode == 2:
+            # smooth free-run: d logit_t also arrives through emb_{t+1} = softmax(s logit_t) @ E, so the output
+            # layer's backward runs inside the time loop (las_dec_bwd fills dl_tot and dzc_all)
+            Vq = (V + 3) // 4 * 4
+            dl_tot = torch.zeros(n * Vq + 64, **f32)
+            dzc_all = torch.zeros(n, ZC, **f32)
+            weT_pk = pack_afrag(W["w_ih"][:, :E].contiguous(), 0, transposed=True)
+            outT_pk = pack_afrag(W["out_w"], 0, transposed=True)
+            demb_buf = torch.empty(B, Ep, **f32)
+            a.weT_pk, a.outT_pk, a.dlogits, a.dl_tot, a.demb_buf = ptr(weT_pk), ptr(outT_pk), ptr(dl), ptr(dl_tot), ptr(demb_buf)
+            a.logits, a.emb_w = ptr(S["logits"]), ptr(W["emb_w"])
+        else:
+            dl_bf = cvt_bf16(dl)                                                      # [n, Vp]
+            Vp = dl_bf.shape[1]
+            d_out_w = gemm(dl_bf, Vp, 1, zc, ZC, 1, V, ZC, n)
+            d_out_b = colsum(dl, V)
+            dzc_all = gemm(dl_bf, Vp, 0, S["out_bf"], ZC, 1, n, ZC, V)                # f32 [n, ZC]
         wrT_pk = pack_afrag(S["wr_cat"], 0, transposed=True)
         mlp_oT_pk = pack_afrag(W["mlp_o_w"], 0, transposed=True)
         mlp_decT_pk = pack_afrag(W["mlp_dec_w"], 0, transposed=True)
@@ -394,16 +407,35 @@ class DecoderFn(torch.autograd.Function):
             dQ = torch.empty(B * Te, O, **f32)
             call("las_att_dq", ptr(S["ws"]), ptr(dc_all), L, B, Te, O, ptr(dQ))
         # ---- weight gradients deferred out of the time loop, as dense contractions over all (b, t)
+        if mode == 2:
+            dlt = dl_tot[:n * Vq].view(n, Vq)[:, :V]
+            dlt_bf = cvt_bf16(dlt)
+            d_out_w = gemm(dlt_bf, dlt_bf.shape[1], 1, zc, ZC, 1, V, ZC, n)
+            d_out_b = colsum(dlt, V)
         d_wr = gemm(dgates, 4 * Hd, 1, zc, ZC, 1, 4 * Hd, ZC, n)                      # [4Hd, Hd+O]
-        emb_in = S["emb_in"]
+        emb_in = S["emb_in"] if mode == 0 else S["emb_op"]                            # bf16 [n, Ep] step inputs
         d_we = gemm(dgates, 4 * Hd, 1, emb_in, Ep, 1, 4 * Hd, Ep, n)                  # [4Hd, Ep]
         d_w_ih = torch.cat([d_we[:, :E], d_wr[:, Hd:]], dim=1)
         d_w_hh = d_wr[:, :Hd].contiguous()
         d_b = colsum(dgates, 4 * Hd)
         we_bf = cvt_bf16(W["w_ih"][:, :E], ld_dst=Ep)
         demb_rows = gemm(dgates, 4 * Hd, 0, we_bf, Ep, 1, n, Ep, 4 * Hd)              # f32 [n, Ep]
-        d_emb = torch.zeros(V, E, **f32)
-        call("las_scatter_add_rows", ptr(demb_rows), Ep, E, ptr(S["ys_in"]), n, 0, ptr(d_emb))
+        if mode == 0:
+            d_emb = torch.zeros(V, E, **f32)
+            call("las_scatter_add_rows", ptr(demb_rows), Ep, E, ptr(S["ys_in"]), n, 0, ptr(d_emb))
+        else:
+            # emb_0 = E[BOS]; emb_{t+1} = p_t @ E with p_t = softmax(s logit_t) (smooth, model.py:341: a matmul,
+            # so every row of E receives gradient) or one-hot(argmax) (greedy): d E = sum_rows p^T demb
+            lg = S["logits"]                                                          # [B, R, V], row r = step r-1
+            if mode == 2:
+                p_all = torch.softmax(lg * smooth_scaling, dim=-1)
+            else:
+                p_all = torch.nn.functional.one_hot(lg.argmax(-1), V).float()
+            p_all = torch.cat([torch.nn.functional.one_hot(torch.full((B, 1), S["bos"], device=dev), V).float(),
+                               p_all[:, 1:]], dim=1)                                  # row r feeds step r
+            p_bf = cvt_bf16(p_all.reshape(n, V))
+            de_bf = cvt_bf16(demb_rows)
+            d_emb = gemm(p_bf, p_bf.shape[1], 1, de_bf, de_bf.shape[1], 1, V, Ep, n)[:, :E].contiguous()
         dc_att = dcz_all[:, Hd:]                                                      # bf16 view, ld ZC
         if pers is not None:
             # c_t = w_t @ Q + b, Q = enc_h @ mlp_o.weight^T: d mlp_o.weight = dQ^T enc_h, d enc_h = dQ mlp_o.weight
