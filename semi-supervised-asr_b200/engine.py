@@ -120,9 +120,20 @@ class SupervisedTrainer:
 
 
 def _clip_and_step(opt, params, max_grad_norm):
-    """clip_grad_norm_ + optimizer.step for the fused optimiser or a stock torch optimiser."""
+    """(data-parallel gradient all-reduce +) clip_grad_norm_ + optimizer.step, for the fused optimiser or a stock
+    torch optimiser."""
+    world = 1
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        world = torch.distributed.get_world_size()
     if hasattr(opt, "clip_and_step"):
-        return opt.clip_and_step(max_grad_norm)
+        if world > 1:
+            torch.distributed.all_reduce(opt.flat_grad)
+        return opt.clip_and_step(max_grad_norm, grad_scale=1.0 / world)
+    if world > 1:
+        for p in params:
+            if p.grad is not None:
+                torch.distributed.all_reduce(p.grad)
+                p.grad.div_(world)
     norm = torch.nn.utils.clip_grad_norm_(params, max_norm=max_grad_norm)
     opt.step()
     return norm

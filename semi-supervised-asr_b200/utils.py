@@ -73,3 +73,60 @@ def infinite_iter(iterable):
             yield next(it)
         except StopIteration:
             it = iter(iterable)
+
+
+def edit_distance(a, b):
+    """Levenshtein distance between two sequences (the reference delegates to the `editdistance` package,
+    utils.py:4, 225)."""
+    if len(a) < len(b):
+        a, b = b, a
+    prev = list(range(len(b) + 1))
+    for i, ca in enumerate(a, 1):
+        cur = [i]
+        for j, cb in enumerate(b, 1):
+            cur.append(min(prev[j] + 1, cur[j - 1] + 1, prev[j - 1] + (ca != cb)))
+        prev = cur
+    return prev[-1]
+
+
+def ind2character(sequences, non_lang_syms, vocab):
+    """utils.py:212-220: indices -> symbols, non-language symbols dropped."""
+    inv = {v: k for k, v in vocab.items()}
+    skip = {vocab[s] for s in non_lang_syms}
+    return [[inv[i] for i in seq if i not in skip] for seq in sequences]
+
+
+def char_list_to_str(char_lists):
+    """utils.py:230-235."""
+    return ["".join(" " if ch == "<space>" else ch for ch in chars) for chars in char_lists]
+
+
+def to_sents(ind_seq, vocab, non_lang_syms):
+    """utils.py:203-210."""
+    return char_list_to_str(ind2character(ind_seq, non_lang_syms, vocab))
+
+
+def calculate_cer(hyps, refs):
+    """utils.py:222-228: total edit distance / total reference length."""
+    dis = sum(edit_distance(h, r) for h, r in zip(hyps, refs))
+    return dis / max(1, sum(len(r) for r in refs))
+
+
+class Logger:
+    """utils.py:237-245 writes tensorboard events; here the same calls append JSON lines to `{logdir}/events.jsonl`
+    (tensorboardX is not a dependency of the hot path)."""
+
+    def __init__(self, logdir="./log"):
+        import json
+        import os
+        os.makedirs(logdir, exist_ok=True)
+        self._f = open(os.path.join(logdir, "events.jsonl"), "a")
+        self._json = json
+
+    def scalar_summary(self, tag, value, step):
+        self._f.write(self._json.dumps({"tag": tag, "value": float(value), "step": int(step)}) + "\n")
+        self._f.flush()
+
+    def text_summary(self, tag, value, step):
+        self._f.write(self._json.dumps({"tag": tag, "text": str(value), "step": int(step)}) + "\n")
+        self._f.flush()

@@ -179,9 +179,57 @@ def case_lm_and_ssl(ref, name, seed, B, Tmax, D, H, subsample, V, E, A, C, ksz, 
     print(name, "sup", sup.item(), "unsup", unsup.item(), "jloss", jloss.item())
 
 
+
+def case_host_plumbing(name, seed):
+    """Batch layout and host statistics straight from the reference's own functions: dataloader._collate_fn /
+    _speech_collate_fn / _text_collate_fn (dataloader.py:6-24), Solver.get_label_dist and
+    calculate_length_proportion (solver.py:69-85), utils.remove_pad_eos / ind2character (utils.py:192-220)."""
+    import dataloader as ref_dl
+    import solver as ref_solver
+    import utils as ref_utils
+    rng = np.random.RandomState(seed)
+    V = 12
+    vocab = {"<PAD>": 0, "<BOS>": 1, "<EOS>": 2, "<NOISE>": 3, "<space>": 4}
+    for i, ch in enumerate("ABCDEFG"):
+        vocab[ch] = 5 + i
+    non_lang = ["<NOISE>", "<PAD>", "<BOS>", "<EOS>"]
+    items = []
+    for i in range(9):
+        T = int(rng.randint(3, 15))
+        items.append((rng.randn(T, 5).astype(np.float32), [int(t) for t in rng.randint(3, V, size=int(rng.randint(1, 7)))]))
+    items[3] = (items[3][0][:items[1][0].shape[0]].copy() if items[3][0].shape[0] >= items[1][0].shape[0]
+                else np.concatenate([items[3][0], items[3][0]])[:items[1][0].shape[0]].copy(), items[3][1])   # a tie in length
+    out = {"n_items": len(items), "vocab_keys": np.array(list(vocab.keys())), "vocab_vals": np.array(list(vocab.values())),
+           "non_lang": np.array(non_lang)}
+    for i, (f, t) in enumerate(items):
+        out[f"feat_{i}"] = f
+        out[f"tok_{i}"] = np.array(t, dtype=np.int64)
+    padded, ilens, texts = ref_dl._collate_fn(list(items))
+    out["c_padded"], out["c_ilens"] = padded.numpy(), np.array(ilens)
+    for i, t in enumerate(texts):
+        out[f"c_text_{i}"] = t.numpy()
+    sp, sil = ref_dl._speech_collate_fn(list(items))
+    out["s_padded"], out["s_ilens"] = sp.numpy(), np.array(sil)
+    for i, t in enumerate(ref_dl._text_collate_fn(list(items))):
+        out[f"t_text_{i}"] = t.numpy()
+    fake = types.SimpleNamespace(vocab=vocab, train_lab_dataset=items)
+    out["labeldist"] = ref_solver.Solver.get_label_dist(fake, items)
+    out["proportion"] = np.float64(ref_solver.Solver.calculate_length_proportion(fake))
+    seqs = [[5, 6, 2, 7, 2], [2, 5], [5, 4, 6, 3, 7], []]
+    cut = ref_utils.remove_pad_eos(seqs, eos=2)
+    out["rpe"] = np.array([len(c) for c in cut])
+    chars = ref_utils.ind2character(cut, non_lang, vocab)
+    out["sents"] = np.array(ref_utils.char_list_to_str(chars))
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print("wrote", name)
+
+
 if __name__ == "__main__":
     ref = import_reference()
     torch.set_num_threads(4)
+    if os.environ.get("ONLY_HOST"):
+        case_host_plumbing("host_plumbing", seed=31)
+        sys.exit(0)
     # odd padded extents at every pyramid level, ragged lengths
     case_supervised(ref, "sup_small_odd", seed=11, B=4, Tmax=37, D=24, H=16, n_layers=3, subsample=[2, 2, 2],
                     V=12, E=8, A=16, C=3, ksz=5, ls=0.05)
@@ -191,5 +239,6 @@ if __name__ == "__main__":
     # kernel wider than Te, batch 1
     case_supervised(ref, "sup_b1_widekernel", seed=13, B=1, Tmax=19, D=16, H=8, n_layers=2, subsample=[2, 2],
                     V=9, E=8, A=8, C=2, ksz=10, ls=0.05)
+    case_host_plumbing("host_plumbing", seed=31)
     case_lm_and_ssl(ref, "ssl_small", seed=21, B=3, Tmax=30, D=16, H=16, subsample=[2, 2], V=11, E=8, A=16,
                     C=3, ksz=4, ls=0.05, JE=8, JH=24)

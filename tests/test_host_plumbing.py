@@ -1,0 +1,140 @@
+"""CPU tests of the host side: batch layout bit-exact against the reference's own collate functions (golden
+fixture made by tests/golden/make_golden.py from /root/reference), label statistics, text post-processing, the
+data-parallel dealing of batches (incl. a world_size-2 gloo run), and optimiser checkpoint format."""
+import os
+import pickle
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from tests.util import GOLDEN_DIR, pkg
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _golden():
+    z = np.load(os.path.join(GOLDEN_DIR, "host_plumbing.npz"))
+    g = {k: z[k] for k in z.files}
+    items = [(g[f"feat_{i}"], g[f"tok_{i}"].tolist()) for i in range(int(g["n_items"]))]
+    vocab = {str(k): int(v) for k, v in zip(g["vocab_keys"], g["vocab_vals"])}
+    return g, items, vocab
+
+
+def test_collate_matches_reference_bit_exact():
+    D = pkg("data")
+    g, items, _ = _golden()
+    padded, ilens, texts = D.collate(list(items))
+    assert padded.dtype == torch.float32 and np.array_equal(padded.numpy(), g["c_padded"])     # zero padding, order
+    assert ilens == g["c_ilens"].tolist() and ilens == sorted(ilens, reverse=True)
+    assert all(t.dtype == torch.int64 and np.array_equal(t.numpy(), g[f"c_text_{i}"]) for i, t in enumerate(texts))
+    sp, sil = D.speech_collate(list(items))
+    assert np.array_equal(sp.numpy(), g["s_padded"]) and sil == g["s_ilens"].tolist()
+    for i, t in enumerate(D.text_collate(list(items))):
+        assert np.array_equal(t.numpy(), g[f"t_text_{i}"])
+
+
+def test_label_statistics_and_text_helpers_match_reference():
+    S, U = pkg("solver"), pkg("utils")
+    g, items, vocab = _golden()
+    fake = type("F", (), {"vocab": vocab, "train_lab_dataset": items})()
+    assert np.array_equal(S.Solver.get_label_dist(fake, items), g["labeldist"])
+    assert S.Solver.calculate_length_proportion(fake) == float(g["proportion"])
+    seqs = [[5, 6, 2, 7, 2], [2, 5], [5, 4, 6, 3, 7], []]
+    cut = U.remove_pad_eos(seqs, eos=2)
+    assert [len(c) for c in cut] == g["rpe"].tolist()
+    assert U.to_sents(cut, vocab, [str(s) for s in g["non_lang"]]) == [str(s) for s in g["sents"]]
+
+
+def test_edit_distance_and_cer_known_answers():
+    U = pkg("utils")
+    assert U.edit_distance("kitten", "sitting") == 3 and U.edit_distance("", "abc") == 3 and U.edit_distance("abc", "abc") == 0
+    assert U.edit_distance(list("flaw"), list("lawn")) == 2
+    assert U.calculate_cer(["abcd", "xy"], ["abed", "xyz"]) == pytest.approx(2 / 7)
+
+
+def test_seq_mask_and_pad_list_bit_exact():
+    U = pkg("utils")
+    m = U._seq_mask([3, 1, 0], 4)
+    assert m.dtype == torch.float32 and m.tolist() == [[1, 1, 1, 0], [1, 0, 0, 0], [0, 0, 0, 0]]
+    p = U.pad_list([torch.tensor([5, 6, 7]), torch.tensor([8])], 2)
+    assert p.tolist() == [[5, 6, 7], [8, 2, 2]]
+
+
+def test_pickle_dataset_filters_and_sorting(tmp_path):
+    D = pkg("data")
+    rng = np.random.RandomState(0)
+    data = {f"u{i}": {"feature": rng.randn(T, 3).astype(np.float32), "token_ids": list(range(3, 3 + L))}
+            for i, (T, L) in enumerate([(5, 2), (50, 4), (9, 1), (20, 30), (12, 3)])}
+    path = tmp_path / "set.pkl"
+    with open(path, "wb") as f:
+        pickle.dump(data, f)
+    cfg = dict(max_feature_length=40, min_feature_length=6, max_text_length=10, min_text_length=2)
+    ds = D.PickleDataset(str(path), config=cfg, sort=True)
+    assert [ds[i][0].shape[0] for i in range(len(ds))] == [12]       # only u4 passes all four filters
+    ds = D.PickleDataset(str(path), config=None, sort=True)
+    assert [ds[i][0].shape[0] for i in range(len(ds))] == [5, 9, 12, 20, 50]
+    assert [k for k in D.PickleDataset(str(path), sort=False).keys] == list(data)
+
+
+def test_batch_dealing_partitions_and_balances():
+    D = pkg("data")
+    rng = np.random.RandomState(1)
+    items = [(rng.randn(int(T), 2).astype(np.float32), [3] * 2) for T in rng.randint(10, 100, size=16)]
+    key = lambda it: it[0].shape[0]
+    shards = [D.shard_items(items, r, 4, key) for r in range(4)]
+    assert sorted(key(it) for s in shards for it in s) == sorted(key(it) for it in items)      # a partition
+    for s in shards:
+        lens = [key(it) for it in s]
+        assert lens == sorted(lens, reverse=True) and len(s) == 4
+    tot = [sum(key(it) for it in s) for s in shards]
+    assert max(tot) - min(tot) <= max(key(it) for it in items)          # round-robin keeps frame totals close
+    # loaders on two ranks draw the same global batches and split them
+    ds = items
+    la = list(D.BatchLoader(ds, 4, True, False, D.collate, rank=0, world=2, seed=7))
+    lb = list(D.BatchLoader(ds, 4, True, False, D.collate, rank=1, world=2, seed=7))
+    lg = list(D.BatchLoader(ds, 8, True, False, D.collate, rank=0, world=1, seed=7))
+    assert len(la) == len(lb) == len(lg) == 2
+    for (xa, ia, _), (xb, ib, _), (xg, ig, _) in zip(la, lb, lg):
+        assert sorted(ia + ib, reverse=True) == ig and ia == ig[0::2] and ib == ig[1::2]
+
+
+GLOO_WORKER = r"""
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import numpy as np, torch, torch.distributed as dist
+from tests.util import pkg
+dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+D = pkg("data")
+rank, world = dist.get_rank(), dist.get_world_size()
+rng = np.random.RandomState(3)
+items = [(rng.randn(int(T), 2).astype(np.float32), [3, 4]) for T in rng.randint(5, 60, size=12)]
+tot = torch.zeros(1, dtype=torch.float64)
+n = torch.zeros(1, dtype=torch.float64)
+for xs, ilens, ys in D.BatchLoader(items, 3, True, False, D.collate, rank=rank, world=world, seed=5):
+    assert ilens == sorted(ilens, reverse=True)
+    tot += float(xs.double().sum()); n += len(ilens)
+dist.all_reduce(tot); dist.all_reduce(n)
+ref = sum(float(torch.from_numpy(f).double().sum()) for f, _ in items)
+assert int(n) == len(items) and abs(float(tot) - ref) < 1e-9, (float(n), float(tot), ref)
+# gradient averaging as engine._clip_and_step does it for a stock optimiser
+p = torch.nn.Parameter(torch.zeros(4)); p.grad = torch.full((4,), float(rank + 1))
+opt = torch.optim.SGD([p], lr=1.0)
+E = pkg("engine")
+E._clip_and_step(opt, [p], max_grad_norm=1e9)
+assert torch.allclose(p.data, torch.full((4,), -(1 + world) / 2.0)), p.data
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_data_parallel_dealing_under_gloo_world2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(GLOO_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
