@@ -147,6 +147,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-step", action="store_true", help="run ONE eager step between cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
     args = ap.parse_args()
+    if os.environ.get("LAS_BENCH_WATCHDOG"):       # stack dump + exit if a (multi-rank) run stops making progress
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["LAS_BENCH_WATCHDOG"]), exit=True)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -260,11 +263,8 @@ def main():
     value = utt / (ms * 1e-3)
     e2e = utt / (ms_e2e * 1e-3)
 
-    if rank != 0:
-        if world > 1:
-            torch.distributed.destroy_process_group()
-        return
-    # launches per step (ours): measured with graphs off on one extra eager step
+    # launches per step (ours): measured with graphs off on one extra eager step (every rank runs it: the
+    # step contains the gradient all-reduce)
     if launches is None:
         tr2_graph = tr.use_graph
         tr.use_graph = False
@@ -273,6 +273,10 @@ def main():
         torch.cuda.synchronize()
         launches = int(LIB.lib().las_launch_count() - c0)
         tr.use_graph = tr2_graph
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

@@ -59,9 +59,10 @@ class SupervisedTrainer:
             self.world = torch.distributed.get_world_size(process_group)
         self.static = {}
         self.launches_per_step = None
+        self.update_graph, self.update_norm = None, None
 
     # ---- the step body: everything below runs on the current stream, no host sync
-    def _body(self, st, L):
+    def _fwd_bwd(self, st, L):
         m = self.model
         enc = m.encoder.enc2
         enc_h = enc.forward_dev(st.x, st.lens)
@@ -70,10 +71,16 @@ class SupervisedTrainer:
         loss = -torch.mean(logp)                                   # solver.py:377 (ALL B x (Lmax+1) positions)
         self.opt.zero_grad()
         loss.backward()
+        return loss.detach()
+
+    def _update(self):
+        return self.opt.clip_and_step(self.max_grad_norm, grad_scale=1.0 / self.world)
+
+    def _body(self, st, L):
+        loss = self._fwd_bwd(st, L)
         if self.world > 1:
             torch.distributed.all_reduce(self.opt.flat_grad, group=self.pg)
-        norm = self.opt.clip_and_step(self.max_grad_norm, grad_scale=1.0 / self.world)
-        return loss.detach(), norm
+        return loss, self._update()
 
     def stage(self, xs, ilens, ys):
         """Host -> device copies of one batch into the static buffers of its geometry."""
@@ -97,7 +104,12 @@ class SupervisedTrainer:
         return key
 
     def run(self, key):
-        """One train step on the batch currently staged for `key`. Returns (loss, grad_norm) device tensors."""
+        """One train step on the batch currently staged for `key`. Returns (loss, grad_norm) device tensors.
+
+        Single GPU: the whole step is one CUDA graph. Data parallel: forward+backward is one graph and the
+        optimiser another, with the NCCL all-reduce of the flat gradient issued eagerly between them (a
+        collective recorded inside a capture is not executed at capture time, which would desynchronise ranks
+        that meet a new batch geometry at different steps)."""
         st = self.static[key]
         L = key[3]
         self.model.train()
@@ -110,10 +122,25 @@ class SupervisedTrainer:
             g = torch.cuda.CUDAGraph()
             torch.cuda.synchronize()
             with torch.cuda.graph(g):
-                st.loss, st.norm = self._body(st, L)
+                if self.world == 1:
+                    st.loss, st.norm = self._body(st, L)
+                else:
+                    st.loss = self._fwd_bwd(st, L)
             st.graph = g
+            if self.world > 1 and self.update_graph is None:
+                torch.cuda.synchronize()
+                gu = torch.cuda.CUDAGraph()
+                step0 = self.opt.step_dev.clone()
+                with torch.cuda.graph(gu):
+                    self.update_norm = self._update()
+                self.update_graph = gu
+                self.opt.step_dev.copy_(step0)     # nothing ran during capture, but keep the counter explicit
         st.graph.replay()
-        return st.loss, st.norm
+        if self.world == 1:
+            return st.loss, st.norm
+        torch.distributed.all_reduce(self.opt.flat_grad, group=self.pg)
+        self.update_graph.replay()
+        return st.loss, self.update_norm
 
     def step(self, xs, ilens, ys):
         return self.run(self.stage(xs, ilens, ys))
