@@ -143,6 +143,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--tmax", type=int, default=1000)
+    ap.add_argument("--dropout", type=float, default=0.3, help="dropout_rate (config.yaml:30 of the reference: 0.3)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-step", action="store_true", help="run ONE eager step between cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
@@ -187,7 +188,7 @@ def main():
     ld = labeldist_of([y for b in batches for y in b[2]], CFG["V"])
     torch.manual_seed(1234)
     m = M.E2E(input_dim=CFG["input_dim"], enc_hidden_dim=CFG["enc_hidden_dim"], enc_n_layers=CFG["enc_n_layers"],
-              subsample=CFG["subsample"], dropout_rate=0.0, dec_hidden_dim=CFG["dec_hidden_dim"],
+              subsample=CFG["subsample"], dropout_rate=args.dropout, dec_hidden_dim=CFG["dec_hidden_dim"],
               att_dim=CFG["att_dim"], conv_channels=CFG["conv_channels"], conv_kernel_size=CFG["conv_kernel_size"],
               att_odim=CFG["att_odim"], embedding_dim=CFG["embedding_dim"], output_dim=CFG["V"],
               ls_weight=CFG["ls_weight"], labeldist=ld).to(dev)
@@ -290,7 +291,7 @@ def main():
         "warmup": W, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": workload, "global_batch": args.batch * world, "parallelism": f"dp{world}",
-                   "precision": "bf16 MMA operands, f32 accumulate/state/master weights", "dropout": 0.0,
+                   "precision": "bf16 MMA operands, f32 accumulate/state/master weights", "dropout": args.dropout,
                    "cuda_graph": not args.no_graph,
                    "l2": "working set per step (>1 GB of saved activations) exceeds the 126 MB L2; no flush"},
         "e2e": {"value": e2e, "unit": "utt/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": int(h2d),

@@ -56,6 +56,13 @@ int las_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int
 int las_cvt_pad_bf16(const float* src, int64_t ld_src, int64_t rows, int cols, void* dst,
                      int64_t ld_dst, void* stream);
 int las_add2(const float* a, const float* b, float* out, int64_t n, void* stream);
+/* Dropout (model.py:82, 95, 285, 512, 520; nn.LSTM inter-layer dropout), in place, on a strided [B, T(+rep_row), W]
+ * view: kept elements are scaled by 1/(1-p). The mask is a pure function of (*seed_dev, site, element index)
+ * (Philox4x32-10), so the backward pass applies the same call to the gradient instead of storing masks; seed_dev
+ * is a device uint64 the caller advances once per training step (CUDA-graph replay safe). rep_row = 1: row T
+ * (the replicated row of an odd pyramid extent) shares the mask of row T-1. */
+int las_dropout(void* x, int x_is_bf16, int64_t B, int64_t T, int W, int64_t ld_b, int64_t ld_t, int rep_row, float p,
+                const void* seed_dev, uint32_t site, void* stream);
 /* ReLU backward of model.py:94: dz = dout * (out > 0), dz in bf16 */
 int las_relu_bwd(const float* dout, const void* out, int out_is_bf16, void* dz, int64_t n, void* stream);
 /* out[c] += sum_r x[r, c] (bias gradients) */
@@ -207,6 +214,12 @@ typedef struct las_dec_args {
   const float* dlogits;      /* f32 [B, L+1, V] loss gradient of the logits                     */
   float* dl_tot;             /* out: f32 [B, L+1, Vq] (+64 slack), Vq = V rounded up to 4, zeroed: total gradient of the logits */
   float* demb_buf;           /* scratch f32 [B, Ep]                                             */
+  /* cell-input dropout (model.py:285): mask element (b*(L+1) + r)*O + o of site drop_site for c_{r-1} as input of
+   * step r, element (b*(L+1) + r)*E + j of site drop_site + 1 for the step-r embedding (see las_dropout) */
+  float drop_p;              /* 0 = off                                                         */
+  uint32_t drop_site;
+  const void* seed_dev;      /* device uint64                                                   */
+  void* zcd;                 /* per-step path: bf16 [B, L+1, Hd+O] (+64 slack), zeroed: [z | drop(c)] */
   const float* pbar;         /* f32 [B, A]: frame mean removed from P (then P holds P - pbar and dzf = mlp_dec(z_t) + pbar) */
 } las_dec_args;
 

@@ -28,7 +28,9 @@ class DecArgs(ctypes.Structure):
             "ws", "zc", "ctx", "c_state", "emb_op", "logits", "pred", "e_buf", "dzf", "gates_save", "c_save",
             "wrT_pk", "mlp_oT_pk", "mlp_decT_pk", "dzc_all", "dcz_tot", "dcz_all", "dctx_all", "dw_buf",
             "dattc_all", "ddz_all", "dP", "att_part", "dc_state", "dgates", "dmlp_att", "dgvec", "dconv_w",
-            "denc", "Q", "wr2_pk", "cpre", "conv_save", "wrT2_pk", "mlp_decT2_pk", "de_all", "dc_all", "cbias", "weT_pk", "outT_pk", "dlogits", "dl_tot", "demb_buf", "pbar")]
+            "denc", "Q", "wr2_pk", "cpre", "conv_save", "wrT2_pk", "mlp_decT2_pk", "de_all", "dc_all", "cbias", "weT_pk", "outT_pk", "dlogits", "dl_tot", "demb_buf")]
+        + [("drop_p", c_float), ("drop_site", ctypes.c_uint32)]
+        + [(n, c_void_p) for n in ("seed_dev", "zcd", "pbar")]
     )
 
 
@@ -42,6 +44,7 @@ SIGNATURES = {
     "las_gemm_bf16": (c_int, [P, L, I, P, L, I, P, L, I, P, I, I, I, I, I, P]),
     "las_cvt_pad_bf16": (c_int, [P, L, L, I, P, L, P]),
     "las_add2": (c_int, [P, P, P, L, P]),
+    "las_dropout": (c_int, [P, I, L, L, I, L, L, I, F, P, ctypes.c_uint32, P]),
     "las_relu_bwd": (c_int, [P, P, I, P, L, P]),
     "las_colsum": (c_int, [P, I, L, L, I, P, P]),
     "las_gather_rows_bf16": (c_int, [P, I, P, L, P, L, P]),

@@ -73,6 +73,31 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
 }
 
 // ----------------------------------------------------------------------------------------
+// dropout: counter-based RNG (Philox4x32-10), so the backward pass recomputes the mask instead of
+// storing it. Element `idx` of dropout site `site` at the step whose seed is `seed` is kept iff
+// its uniform variate is >= p (torch.nn.Dropout semantics: kept values are scaled by 1/(1-p)).
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint2 key, uint4 ctr) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u;
+    key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+__device__ __forceinline__ bool dropout_keep(unsigned long long seed, uint32_t site, unsigned long long idx, float p) {
+  const unsigned long long blk = idx >> 2;
+  const uint4 r = philox4x32_10(make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)),
+                                make_uint4(static_cast<uint32_t>(blk), static_cast<uint32_t>(blk >> 32), site, 0x4c41535fu));
+  const uint32_t sel = static_cast<uint32_t>(idx) & 3u;
+  const uint32_t v = sel == 0 ? r.x : (sel == 1 ? r.y : (sel == 2 ? r.z : r.w));
+  return static_cast<float>(v >> 8) * (1.0f / 16777216.0f) >= p;
+}
+
+// ----------------------------------------------------------------------------------------
 // shared-memory addressing, mbarrier, fences
 // ----------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

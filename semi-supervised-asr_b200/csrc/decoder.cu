@@ -207,6 +207,7 @@ __global__ void __launch_bounds__(256) att_ctx_fwd_kernel(CtxFwdParams p) {
 // Next input embedding in free-running modes (model.py:331-341): argmax token, then either its
 // embedding row (greedy) or softmax(scaling * logit) @ E (smooth). One warp per utterance.
 struct NextEmbParams {
+  float drop_p; const unsigned long long* seed_dev; uint32_t site; int64_t R, row;   // cell-input dropout of the embedding
   int B, V, E;
   const float* logits; int64_t lg_ld;   // row b at logits + b*lg_ld
   const float* emb_w;                   // [V, E]
@@ -232,8 +233,14 @@ __global__ void __launch_bounds__(128) next_emb_kernel(NextEmbParams p) {
     if (om > mx || (om == mx && oa < amax)) { mx = om; amax = oa; }
   }
   if (lane == 0) p.pred[b * p.pred_ld] = amax;
+  const unsigned long long seed = p.drop_p > 0.f ? *p.seed_dev : 0ull;
+  auto drop = [&](float v, int j) {
+    if (p.drop_p <= 0.f) return v;
+    return dropout_keep(seed, p.site, (static_cast<unsigned long long>(b) * p.R + p.row) * p.E + j, p.drop_p)
+               ? v / (1.f - p.drop_p) : 0.f;
+  };
   if (!p.smooth) {
-    for (int j = lane; j < p.E; j += 32) p.emb_out[b * p.eo_ld + j] = __float2bfloat16(p.emb_w[amax * p.E + j]);
+    for (int j = lane; j < p.E; j += 32) p.emb_out[b * p.eo_ld + j] = __float2bfloat16(drop(p.emb_w[amax * p.E + j], j));
     return;
   }
   float se = 0.f;
@@ -243,7 +250,7 @@ __global__ void __launch_bounds__(128) next_emb_kernel(NextEmbParams p) {
   for (int j = lane; j < p.E; j += 32) {
     float s = 0.f;
     for (int v = 0; v < p.V; ++v) s = fmaf(__expf(p.scaling * (x[v] - mx)) * inv, p.emb_w[v * p.E + j], s);
-    p.emb_out[b * p.eo_ld + j] = __float2bfloat16(s);
+    p.emb_out[b * p.eo_ld + j] = __float2bfloat16(drop(s, j));
   }
 }
 
@@ -251,6 +258,7 @@ __global__ void __launch_bounds__(128) next_emb_kernel(NextEmbParams p) {
 // s * p * (dp - <p, dp>), dp[v] = <E[v, :], demb_{t+1}>, to the loss gradient of logit_t. One warp
 // per utterance; V <= 1024.
 struct SmoothBwdParams {
+  float drop_p; const unsigned long long* seed_dev; uint32_t site; int64_t R, row;   // dropout mask of emb_{t+1}
   int B, V, E;
   float scaling;
   const float* logits; int64_t lg_ld;     // logits_t rows
@@ -264,7 +272,14 @@ __global__ void __launch_bounds__(128) smooth_dlogit_kernel(SmoothBwdParams p) {
   const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (b >= p.B) return;
   const float* x = p.logits + b * p.lg_ld;
-  const float* de = p.demb + b * p.de_ld;
+  float* de = const_cast<float*>(p.demb) + b * p.de_ld;
+  if (p.drop_p > 0.f) {   // gradient w.r.t. the un-dropped embedding (each warp owns its row of the scratch)
+    const unsigned long long seed = *p.seed_dev;
+    for (int j = lane; j < p.E; j += 32)
+      de[j] = dropout_keep(seed, p.site, (static_cast<unsigned long long>(b) * p.R + p.row) * p.E + j, p.drop_p)
+                  ? de[j] / (1.f - p.drop_p) : 0.f;
+    __syncwarp();
+  }
   float mx = -INFINITY;
   for (int v = lane; v < p.V; v += 32) mx = fmaxf(mx, x[v]);
   mx = warp_max(mx);
@@ -285,6 +300,47 @@ __global__ void __launch_bounds__(128) smooth_dlogit_kernel(SmoothBwdParams p) {
     for (int j = 0; j < p.E; ++j) dp = fmaf(p.emb_w[v * p.E + j], de[j], dp);
     p.dl_tot[b * p.dt_ld + v] = p.dlogits[b * p.dl_ld + v] + p.scaling * pv * (dp - dot);
   }
+}
+
+// Decoder cell-input dropout (model.py:285) for the per-step path. The mask of c_t as an input of step t+1 is
+// element (b*R + t+1)*O + o of site `site`; of the step-(t+1) embedding, element (b*R + t+1)*E + j of site + 1.
+// forward : zcd row = [z_t | drop(c_t)]  (the undropped [z_t | c_t] still feeds the output layer)
+// backward: dcz_tot = [dz | drop'(dc)] + dzc_all row, also stored as bf16
+struct DropRowParams {
+  int B, Hd, O;
+  int64_t R, row;
+  float p;
+  const unsigned long long* seed_dev;
+  uint32_t site;
+  const __nv_bfloat16* zc; __nv_bfloat16* zcd;     // forward: rows at b*R*ZC + row*ZC
+  float* dcz_tot; const float* dzc_row; __nv_bfloat16* dcz_row; int64_t d_ld;   // backward
+};
+__global__ void dec_drop_fwd_kernel(DropRowParams p) {
+  const int ZC = p.Hd + p.O;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.B * ZC) return;
+  const int b = i / ZC, j = i % ZC;
+  const int64_t off = (static_cast<int64_t>(b) * p.R + p.row) * ZC + j;
+  __nv_bfloat16 v = p.zc[off];
+  if (j >= p.Hd) {
+    const bool keep = dropout_keep(*p.seed_dev, p.site, (static_cast<unsigned long long>(b) * p.R + p.row) * p.O + (j - p.Hd), p.p);
+    v = keep ? __float2bfloat16(__bfloat162float(v) / (1.f - p.p)) : __float2bfloat16(0.f);
+  }
+  p.zcd[off] = v;
+}
+__global__ void dec_drop_bwd_kernel(DropRowParams p) {
+  const int ZC = p.Hd + p.O;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.B * ZC) return;
+  const int b = i / ZC, j = i % ZC;
+  float v = p.dcz_tot[b * ZC + j];
+  if (j >= p.Hd) {
+    const bool keep = dropout_keep(*p.seed_dev, p.site, (static_cast<unsigned long long>(b) * p.R + p.row) * p.O + (j - p.Hd), p.p);
+    v = keep ? v / (1.f - p.p) : 0.f;
+  }
+  v += p.dzc_row[b * p.d_ld + j];
+  p.dcz_tot[b * ZC + j] = v;
+  p.dcz_row[b * p.d_ld + j] = __float2bfloat16(v);
 }
 
 // Initial alignment (model.py:151-153): 1/len over valid frames, exact zeros beyond.
@@ -689,6 +745,9 @@ int las_dec_fwd(const las_dec_args* a, void* stream_) {
   const size_t csmem = (Te + 2 + 8 + 8 * 32 * 2) * sizeof(float);
   if (int rc = ensure_smem(att_ctx_fwd_kernel, csmem)) return rc;
   const bool free_run = a->mode != 0;
+  const bool drop = a->drop_p > 0.f;
+  if (drop) LAS_REQUIRE(a->seed_dev && a->zcd, "decoder: dropout needs seed_dev and the zcd buffer");
+  __nv_bfloat16* zcd = static_cast<__nv_bfloat16*>(a->zcd);
   __nv_bfloat16* zc = static_cast<__nv_bfloat16*>(a->zc);
   __nv_bfloat16* ctx = static_cast<__nv_bfloat16*>(a->ctx);
   __nv_bfloat16* emb_op = static_cast<__nv_bfloat16*>(a->emb_op);
@@ -720,7 +779,7 @@ int las_dec_fwd(const las_dec_args* a, void* stream_) {
   for (int t = 0; t < L; ++t) {
     // (1) LSTMCell: gates = W [emb; c_{t-1}; z_{t-1}] + b   (model.py:284-286)
     cp.step = t;
-    cp.v1 = zc + static_cast<int64_t>(t) * ZC;
+    cp.v1 = (drop ? zcd : zc) + static_cast<int64_t>(t) * ZC;      // cell input: c_{t-1} after dropout (model.py:285)
     cp.hout = zc + static_cast<int64_t>(t + 1) * ZC;
     if (free_run) cp.v2 = emb_op + static_cast<int64_t>(t) * Ep;
     launch_cell_fwd(cp, stream);
@@ -741,12 +800,21 @@ int las_dec_fwd(const las_dec_args* a, void* stream_) {
     // (5) c_t = mlp_o(context)   (model.py:172) -> second half of zc row t+1
     smallmm(static_cast<const uint32_t*>(a->mlp_o_pk), O, a->H, ctx + static_cast<int64_t>(t + 1) * a->H, 0, R * a->H, B,
             a->mlp_o_b, nullptr, 0, nullptr, 0, zc + static_cast<int64_t>(t + 1) * ZC + Hd, R * ZC, stream);
+    if (drop) {
+      DropRowParams dp = {};
+      dp.B = B; dp.Hd = Hd; dp.O = O; dp.R = R; dp.row = t + 1; dp.p = a->drop_p;
+      dp.seed_dev = static_cast<const unsigned long long*>(a->seed_dev); dp.site = a->drop_site;
+      dp.zc = zc; dp.zcd = zcd;
+      dec_drop_fwd_kernel<<<(B * ZC + 255) / 256, 256, 0, stream>>>(dp); ++g_launches;
+    }
     if (free_run) {
       // (6) logit_t = output_layer([z_t; c_t]) (model.py:290-293), (7) next input embedding
       float* lg = a->logits + static_cast<int64_t>(t + 1) * V;
       smallmm(static_cast<const uint32_t*>(a->out_pk), V, ZC, zc + static_cast<int64_t>(t + 1) * ZC, 0, R * ZC, B,
               a->out_b, nullptr, 0, lg, R * V, nullptr, 0, stream);
       NextEmbParams np = {};
+      np.drop_p = a->drop_p; np.seed_dev = static_cast<const unsigned long long*>(a->seed_dev);
+      np.site = a->drop_site + 1; np.R = R; np.row = t + 1;
       np.B = B; np.V = V; np.E = E; np.logits = lg; np.lg_ld = R * V; np.emb_w = a->emb_w;
       np.scaling = a->smooth_scaling; np.smooth = (a->mode == 2);
       np.pred = a->pred + t; np.pred_ld = L;
@@ -763,6 +831,8 @@ int las_dec_bwd(const las_dec_args* a, void* stream_) {
   if (int rc = check_args(a)) return rc;
   if (dec_persist_supported(a)) return dec_persist_bwd(a, stream);   // one cluster-persistent launch
   const bool smooth = a->mode == 2;
+  const bool drop = a->drop_p > 0.f;
+  if (drop) LAS_REQUIRE(a->seed_dev, "decoder backward: dropout needs seed_dev");
   if (smooth)
     LAS_REQUIRE(a->weT_pk && a->outT_pk && a->dlogits && a->dl_tot && a->demb_buf && a->logits && a->emb_w,
                 "decoder backward (smooth free-run): missing buffers");
@@ -814,6 +884,8 @@ int las_dec_bwd(const las_dec_args* a, void* stream_) {
         smallmm(static_cast<const uint32_t*>(a->weT_pk), Ep, 4 * Hd, dgates + static_cast<int64_t>(t + 1) * 4 * Hd, 0,
                 R * 4 * Hd, B, nullptr, nullptr, 0, a->demb_buf, Ep, nullptr, 0, stream);
         SmoothBwdParams sp = {};
+        sp.drop_p = a->drop_p; sp.seed_dev = static_cast<const unsigned long long*>(a->seed_dev);
+        sp.site = a->drop_site + 1; sp.R = R; sp.row = t + 1;
         sp.B = B; sp.V = V; sp.E = E; sp.scaling = a->smooth_scaling;
         sp.logits = a->logits + static_cast<int64_t>(t + 1) * V; sp.lg_ld = R * V;
         sp.demb = a->demb_buf; sp.de_ld = Ep; sp.emb_w = a->emb_w;
@@ -828,9 +900,21 @@ int las_dec_bwd(const las_dec_args* a, void* stream_) {
               const_cast<float*>(a->dzc_all) + static_cast<int64_t>(t + 1) * ZC, R * ZC, nullptr, 0, stream);
     }
     // (1) d[z_t; c_t] = dzc_all (from the output layer) + Wr^T dgates_{t+1}  (row L of dgates is zero)
-    smallmm(static_cast<const uint32_t*>(a->wrT_pk), ZC, 4 * Hd, dgates + static_cast<int64_t>(t + 1) * 4 * Hd, 0, R * 4 * Hd, B,
-            nullptr, a->dzc_all + static_cast<int64_t>(t + 1) * ZC, R * ZC, a->dcz_tot, ZC,
-            dcz_all + static_cast<int64_t>(t + 1) * ZC, R * ZC, stream);
+    if (!drop) {
+      smallmm(static_cast<const uint32_t*>(a->wrT_pk), ZC, 4 * Hd, dgates + static_cast<int64_t>(t + 1) * 4 * Hd, 0, R * 4 * Hd, B,
+              nullptr, a->dzc_all + static_cast<int64_t>(t + 1) * ZC, R * ZC, a->dcz_tot, ZC,
+              dcz_all + static_cast<int64_t>(t + 1) * ZC, R * ZC, stream);
+    } else {
+      // the path through the cell input of step t+1 carries that step's dropout mask on its c part
+      smallmm(static_cast<const uint32_t*>(a->wrT_pk), ZC, 4 * Hd, dgates + static_cast<int64_t>(t + 1) * 4 * Hd, 0, R * 4 * Hd, B,
+              nullptr, nullptr, 0, a->dcz_tot, ZC, nullptr, 0, stream);
+      DropRowParams dp = {};
+      dp.B = B; dp.Hd = Hd; dp.O = O; dp.R = R; dp.row = t + 1; dp.p = a->drop_p;
+      dp.seed_dev = static_cast<const unsigned long long*>(a->seed_dev); dp.site = a->drop_site;
+      dp.dcz_tot = a->dcz_tot; dp.dzc_row = a->dzc_all + static_cast<int64_t>(t + 1) * ZC;
+      dp.dcz_row = dcz_all + static_cast<int64_t>(t + 1) * ZC; dp.d_ld = R * ZC;
+      dec_drop_bwd_kernel<<<(B * ZC + 255) / 256, 256, 0, stream>>>(dp); ++g_launches;
+    }
     // (2) dcontext = mlp_o^T dc_t
     float* dctx_t = a->dctx_all + static_cast<int64_t>(t) * a->H;
     smallmm(static_cast<const uint32_t*>(a->mlp_oT_pk), a->H, O, dcz_all + static_cast<int64_t>(t + 1) * ZC + Hd, 0, R * ZC, B,

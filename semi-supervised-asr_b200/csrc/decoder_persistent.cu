@@ -171,6 +171,7 @@ struct DecFwdP {
   float* c_save;                 // [B, L, Hd]
   float* cpre;                   // [B, L, O]  context term before the bias
   float* conv_save;              // [B, L, Te, 16] location-conv features (C padded to 16)
+  float drop_p; uint32_t drop_site; const unsigned long long* seed_dev;   // cell-input dropout of c_t (model.py:285)
   long long* dbg;                // optional clock64() phase trace (las_set_debug_buffer)
 };
 
@@ -323,6 +324,7 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
   // cluster-mapped base addresses
   const uint32_t zB_base = smem_u32(zB), dzv_base = smem_u32(dzv), eall_base = smem_u32(e_all);
   const float scal = p.att_scaling;
+  const bool drop_on = p.drop_p > 0.f;
 
   cluster_barrier();   // every CTA's shared memory is initialised before any remote store
   const bool trace = p.dbg != nullptr && blockIdx.y == 0 && rank == 0 && tid == 0;
@@ -573,6 +575,13 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
           hb = __float2bfloat16(cb + p.cbias[static_cast<int64_t>(b_own) * O + ob]);
           zrow[ob] = hb;
         }
+        if (drop_on) {
+          // what the NEXT step's gates see is dropout(c_t); the output layer (zc in global memory) sees c_t
+          const unsigned long long seed = *p.seed_dev, base = (static_cast<unsigned long long>(b_own) * R + t + 1) * O;
+          const float sc = 1.f / (1.f - p.drop_p);
+          if (va) ha = dropout_keep(seed, p.drop_site, base + oa, p.drop_p) ? __float2bfloat16(__bfloat162float(ha) * sc) : __float2bfloat16(0.f);
+          if (vb) hb = dropout_keep(seed, p.drop_site, base + ob, p.drop_p) ? __float2bfloat16(__bfloat162float(hb) * sc) : __float2bfloat16(0.f);
+        }
         // pair (o, o+1): the partner is the lane 4 further (gq + 1)
         const uint32_t wa = __bfloat16_as_ushort(ha), wb = __bfloat16_as_ushort(hb);
         const uint32_t ua = __shfl_down_sync(0xffffffffu, wa, 4), ub = __shfl_down_sync(0xffffffffu, wb, 4);
@@ -702,6 +711,7 @@ struct DecBwdP {
   float* ddz_all;                // [B, L+1, A] (row t+1)
   float* de_all;                 // [B, L, Te]
   float* dattc_all;              // [L, B, Te, C]
+  float drop_p; uint32_t drop_site; const unsigned long long* seed_dev;
   long long* dbg;
 };
 
@@ -901,7 +911,11 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
     }
     __syncthreads();
     if (epi_ok) {
-      const float v = red_gather(red, a_w0, g.KSb, row_l & 15, n_e) + dzc_v;
+      float mm = red_gather(red, a_w0, g.KSb, row_l & 15, n_e);
+      if (p.drop_p > 0.f && !is_z)   // the path through the cell input of step t+1 carries that step's dropout mask
+        mm = dropout_keep(*p.seed_dev, p.drop_site, (static_cast<unsigned long long>(b_e) * R + t + 1) * O + o_e, p.drop_p)
+                 ? mm / (1.f - p.drop_p) : 0.f;
+      const float v = mm + dzc_v;
       if (is_z) {
         dz_acc = v;
       } else {
@@ -1238,6 +1252,7 @@ static int pick_nb(const las_dec_args* a, DGeom& g, BGeom& bg) {
 
 int dec_persist_supported(const las_dec_args* a) {
   if (a->mode != 0 || a->Q == nullptr || a->wr2_pk == nullptr || a->cbias == nullptr || a->pbar == nullptr) return 0;
+  if (a->drop_p > 0.f && a->seed_dev == nullptr) return 0;
   DGeom g;
   BGeom bg;
   if (pick_nb(a, g, bg) == 0) return 0;
@@ -1305,6 +1320,7 @@ int dec_persist_bwd(const las_dec_args* a, cudaStream_t stream) {
   p.cpre = a->cpre; p.conv_save = a->conv_save; p.dzc_all = a->dzc_all;
   p.dgates = static_cast<__nv_bfloat16*>(a->dgates); p.dcz_all = static_cast<__nv_bfloat16*>(a->dcz_all);
   p.dc_all = a->dc_all; p.ddz_all = a->ddz_all; p.de_all = a->de_all; p.dattc_all = a->dattc_all;
+  p.drop_p = a->drop_p; p.drop_site = a->drop_site; p.seed_dev = static_cast<const unsigned long long*>(a->seed_dev);
   p.dbg = static_cast<long long*>(g_dbg_buf_shared);
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute at[1];
@@ -1358,6 +1374,7 @@ int dec_persist_fwd(const las_dec_args* a, cudaStream_t stream) {
   p.ws = a->ws; p.zc = static_cast<__nv_bfloat16*>(a->zc); p.dzf = a->dzf;
   p.gates_save = static_cast<__half*>(a->gates_save); p.c_save = a->c_save;
   p.cpre = a->cpre; p.conv_save = a->conv_save;
+  p.drop_p = a->drop_p; p.drop_site = a->drop_site; p.seed_dev = static_cast<const unsigned long long*>(a->seed_dev);
   p.dbg = static_cast<long long*>(g_dbg_buf_shared);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(kCS, (a->B + nb - 1) / nb, 1);

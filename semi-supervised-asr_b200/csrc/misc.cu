@@ -258,6 +258,27 @@ __global__ void adam_step_kernel(float* __restrict__ p, const float* __restrict_
   }
 }
 
+// x[b, t, c] *= keep(seed, site, (b*T + min(t, T-1))*W + c) / (1 - p), t < T + rep_row: the replicated row of
+// an odd pyramid extent (model.py:88-89 pads AFTER the dropout of model.py:82) shares the mask of row T-1.
+template <typename T>
+__global__ void dropout_kernel(T* __restrict__ x, int64_t B, int64_t Tn, int W, int64_t ld_b, int64_t ld_t, int rep_row,
+                               float p, const unsigned long long* __restrict__ seed_dev, uint32_t site) {
+  const unsigned long long seed = *seed_dev;
+  const float scale = 1.0f / (1.0f - p);
+  const int64_t rows = Tn + rep_row, total = B * rows * W;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % W);
+    const int64_t bt = i / W, t = bt % rows, b = bt / rows;
+    const int64_t tm = t < Tn ? t : Tn - 1;
+    T* q = x + b * ld_b + t * ld_t + c;
+    const bool keep = dropout_keep(seed, site, static_cast<unsigned long long>((b * Tn + tm) * W + c), p);
+    if constexpr (sizeof(T) == 2) *q = keep ? __float2bfloat16(__bfloat162float(*q) * scale) : __float2bfloat16(0.f);
+    else *q = keep ? *q * scale : 0.f;
+  }
+}
+
+
 }  // namespace las
 
 using namespace las;
@@ -277,6 +298,22 @@ int las_cvt_pad_bf16(const float* src, int64_t ld_src, int64_t rows, int cols, v
 int las_add2(const float* a, const float* b, float* out, int64_t n, void* stream) {
   if (n == 0) return 0;
   add2_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, b, out, n); ++g_launches;
+  LAS_LAUNCH_CHECK();
+  return 0;
+}
+
+int las_dropout(void* x, int x_is_bf16, int64_t B, int64_t T, int W, int64_t ld_b, int64_t ld_t, int rep_row, float p,
+                const void* seed_dev, uint32_t site, void* stream) {
+  LAS_REQUIRE(p >= 0.f && p < 1.f, "dropout: rate %f out of range [0, 1)", p);
+  if (p == 0.f || B * T * W == 0) return 0;
+  const int64_t n = B * (T + rep_row) * W;
+  if (x_is_bf16)
+    dropout_kernel<__nv_bfloat16><<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<__nv_bfloat16*>(x), B, T, W, ld_b, ld_t, rep_row, p, static_cast<const unsigned long long*>(seed_dev), site);
+  else
+    dropout_kernel<float><<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<float*>(x), B, T, W, ld_b, ld_t, rep_row, p, static_cast<const unsigned long long*>(seed_dev), site);
+  ++g_launches;
   LAS_LAUNCH_CHECK();
   return 0;
 }

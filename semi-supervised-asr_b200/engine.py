@@ -163,6 +163,7 @@ def _clip_and_step(opt, params, max_grad_norm):
                 p.grad.div_(world)
     norm = torch.nn.utils.clip_grad_norm_(params, max_norm=max_grad_norm)
     opt.step()
+    Fn.advance_dropout_seed()
     return norm
 
 

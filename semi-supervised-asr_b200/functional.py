@@ -20,6 +20,39 @@ BF16 = torch.bfloat16
 DEC_PERSISTENT = os.environ.get("LAS_DEC_PERSIST", "1") == "1"
 
 
+# --------------------------------------------------------------------------------------------
+# dropout: masks are a function of (device seed, site id, element index) -- see las_dropout. The seed advances
+# once per optimiser step (FusedAdam / the trainers call advance_dropout_seed()); every Function.forward call
+# inside a step draws fresh site ids, so two forwards of the same module in one step use different masks.
+# --------------------------------------------------------------------------------------------
+_DROP = {"seed": None, "calls": 0}
+
+
+def dropout_seed(device):
+    if _DROP["seed"] is None or _DROP["seed"].device != device:
+        _DROP["seed"] = torch.tensor([torch.initial_seed() & 0x7FFFFFFFFFFF], device=device, dtype=torch.int64)
+    return _DROP["seed"]
+
+
+def advance_dropout_seed():
+    """New masks from the next forward on. Call once per training step (after backward)."""
+    if _DROP["seed"] is not None:
+        _DROP["seed"] += 1
+    _DROP["calls"] = 0
+
+
+def new_sites(n=64):
+    """Base site id for one Function.forward call (n consecutive ids reserved)."""
+    _DROP["calls"] += 1
+    return (_DROP["calls"] * n) & 0x7FFFFFFF
+
+
+def dropout_(x, B, T, W, ld_b, ld_t, rep, p, site):
+    """In-place dropout on a strided [B, T(+rep), W] view of a bf16 or f32 tensor."""
+    call("las_dropout", ptr(x), int(x.dtype == BF16), B, T, W, ld_b, ld_t, int(rep), float(p),
+         ptr(dropout_seed(x.device)), int(site))
+
+
 def _r8(n):
     return (n + 7) // 8 * 8
 
@@ -109,8 +142,9 @@ class EncoderFn(torch.autograd.Function):
     b_hh_r, proj_w, proj_b."""
 
     @staticmethod
-    def forward(ctx, x, lens, subsample, *weights):
+    def forward(ctx, x, lens, subsample, p_drop, *weights):
         B, T, D = x.shape
+        site0 = new_sites() if p_drop > 0 else 0
         dev = x.device
         n_layers = len(subsample)
         assert len(weights) == 10 * n_layers
@@ -135,12 +169,16 @@ class EncoderFn(torch.autograd.Function):
             call("las_lstm_seq_fwd", ptr(xproj), ptr(whh_pk), ptr(cur_lens), B, T, H, 2, ptr(y), Tp * 2 * H, 2 * H,
                  rep, ptr(hprev), T * 2 * H, 2 * H, ptr(gates), ptr(csave), ptr(ws))
             del xproj
+            if p_drop > 0:      # model.py:82 (before the replicate pad of an odd extent: the extra row shares its mask)
+                dropout_(y, B, T, 2 * H, Tp * 2 * H, 2 * H, rep, p_drop, site0 + 2 * i)
             if sub > 1:
                 T2, Kp = Tp // 2, 4 * H
             else:
                 T2, Kp = T, 2 * H
             wp = cvt_bf16(proj_w)                                                   # [H, Kp]
             out = gemm(y, Kp, 0, wp, Kp, 0, B * T2, proj_w.shape[0], Kp, out_bf16=True, bias=proj_b, relu=True)
+            if p_drop > 0:      # model.py:95 (all rows, incl. the relu(bias) rows past each length)
+                dropout_(out, B * T2, 1, proj_w.shape[0], proj_w.shape[0], proj_w.shape[0], 0, p_drop, site0 + 2 * i + 1)
             saved.append((xin, wcat, y, hprev, gates, csave, out, wp, cur_lens, T, Tp, T2, Dp, H, rep))
             if sub > 1:
                 nl = torch.empty_like(cur_lens)
@@ -149,6 +187,7 @@ class EncoderFn(torch.autograd.Function):
             xin, T, Dp = out, T2, proj_w.shape[0]
         ctx.saved = saved
         ctx.subsample = list(subsample)
+        ctx.drop = (float(p_drop), site0)
         ctx.B = B
         ctx.weights = weights
         ctx.D = D
@@ -159,19 +198,26 @@ class EncoderFn(torch.autograd.Function):
         B = ctx.B
         n_layers = len(ctx.subsample)
         grads = [None] * (10 * n_layers)
+        p_drop, site0 = ctx.drop
         dout = denc.contiguous().float()
+        if p_drop > 0:
+            dout = dout.clone()                       # masked in place below
         for i in reversed(range(n_layers)):
             xin, wcat, y, hprev, gates, csave, out, wp, lens_i, T, Tp, T2, Dp, H, rep = ctx.saved[i]
             w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r, proj_w, proj_b = ctx.weights[10 * i:10 * i + 10]
             dev = dout.device
             Ho, Kp = proj_w.shape
             n = B * T2
+            if p_drop > 0:
+                dropout_(dout, n, 1, Ho, Ho, Ho, 0, p_drop, site0 + 2 * i + 1)
             dz = torch.empty(n, Ho, device=dev, dtype=BF16)
             call("las_relu_bwd", ptr(dout), ptr(out), 1, ptr(dz), n * Ho)
             # projection: dW = dz^T yview, db = colsum(dz), dy = dz W
             d_proj_w = gemm(dz, Ho, 1, y, Kp, 1, Ho, Kp, n)
             d_proj_b = colsum(dz, Ho)
             dy = gemm(dz, Ho, 0, wp, Kp, 1, n, Kp, Ho)                               # f32 [B, Tp, 2H] view
+            if p_drop > 0:
+                dropout_(dy, B, T, 2 * H, Tp * 2 * H, 2 * H, rep, p_drop, site0 + 2 * i)
             # recurrence
             wf, layout = pack_whhT(w_hh)
             wr, _ = pack_whhT(w_hh_r)
@@ -193,7 +239,7 @@ class EncoderFn(torch.autograd.Function):
             if i > 0:
                 dout = gemm(dG, 8 * H, 0, wcat, Dp, 1, B * T, Dp, 8 * H)             # f32 [B*T, H_prev]
         ctx.saved = None
-        return (None, None, None, *grads)
+        return (None, None, None, None, *grads)
 
 
 # --------------------------------------------------------------------------------------------
@@ -220,14 +266,17 @@ class DecoderFn(torch.autograd.Function):
     unused), ws_alloc f32 [B, L+1, Te] (row 0 = initial alignment), pred int64 [B, L] or None)."""
 
     @staticmethod
-    def forward(ctx, enc_h, enc_lens, ys_in, L, mode, smooth_scaling, att_scaling, K, bos, *wts):
+    def forward(ctx, enc_h, enc_lens, ys_in, L, mode, smooth_scaling, att_scaling, K, bos, p_drop, *wts):
         W = dict(zip(DEC_WEIGHTS, wts))
         dev = enc_h.device
+        site0 = new_sites() if p_drop > 0 else 0
         a, (B, Te, H, Hd, O, A, V, E, C) = _dec_common(enc_h, W, L, K)
         R, ZC, Ep = L + 1, Hd + O, _r16(E)
         a.mode, a.att_scaling, a.smooth_scaling = mode, att_scaling, smooth_scaling
         f32 = dict(device=dev, dtype=torch.float32)
         keep = []  # keep tensors referenced by raw pointers alive until the launches are enqueued
+        if p_drop > 0:                                 # cell-input dropout (model.py:285)
+            a.drop_p, a.drop_site, a.seed_dev = float(p_drop), site0, ptr(dropout_seed(dev))
 
         enc_bf = cvt_bf16(enc_h.reshape(B * Te, H))
         mlp_enc_bf = cvt_bf16(W["mlp_enc_w"])
@@ -262,6 +311,8 @@ class DecoderFn(torch.autograd.Function):
             # teacher forcing: the embedding half of the LSTMCell input projection for all steps at once
             emb_in = torch.empty(B * R, Ep, device=dev, dtype=BF16)
             call("las_gather_rows_bf16", ptr(W["emb_w"]), E, ptr(ys_in), B * R, ptr(emb_in), Ep)
+            if p_drop > 0:
+                dropout_(emb_in, B, R, E, R * Ep, Ep, 0, p_drop, site0 + 1)
             we_bf = cvt_bf16(we, ld_dst=Ep)
             embx = gemm(emb_in, Ep, 0, we_bf, Ep, 0, B * R, 4 * Hd, Ep, bias=cell_bias)
             a.embx = ptr(embx)
@@ -273,6 +324,8 @@ class DecoderFn(torch.autograd.Function):
             bos_row = torch.zeros(Ep, **f32)
             bos_row[:E] = W["emb_w"][bos]
             emb_op[:B * R * Ep].view(B, R, Ep)[:, 0, :] = bos_row.to(BF16)
+            if p_drop > 0:                             # row 0 now; later rows are masked as the kernels write them
+                dropout_(emb_op, B, R, E, R * Ep, Ep, 0, p_drop, site0 + 1)
             logits = torch.zeros(B, R, V, **f32)
             pred = torch.zeros(B, L, device=dev, dtype=torch.int64)
             a.cell_bias, a.we_pk, a.out_pk, a.out_b = ptr(cell_bias), ptr(we_pk), ptr(out_pk), ptr(W["out_b"])
@@ -303,11 +356,16 @@ class DecoderFn(torch.autograd.Function):
                 pers = dict(Qm=Qm, wr2_pk=wr2_pk, cpre=cpre, conv_save=conv_save, mlp_o_bf=mlp_o_bf, cbias=cbias, Pc=Pc, Pbar=Pbar)
             else:
                 a.Q, a.wr2_pk, a.cbias, a.pbar = None, None, None, None
+        if p_drop > 0 and not persist:
+            zcd = torch.zeros(B * R * ZC + 64, device=dev, dtype=BF16)
+            a.zcd = ptr(zcd)
+            keep.append(zcd)
         _lib.check(_lib.lib().las_dec_fwd(ctypes.byref(a), _lib.stream_ptr()))
         out_bf = cvt_bf16(W["out_w"])                                                 # [V, ZC]
         if mode == 0:
             logits = gemm(zc, ZC, 0, out_bf, ZC, 0, B * R, V, ZC, bias=W["out_b"]).view(B, R, V)
         ctx.geom = (B, Te, H, Hd, O, A, V, E, C, K, L, mode, att_scaling, smooth_scaling)
+        ctx.drop = (float(p_drop), site0)
         ctx.saved = dict(enc_bf=enc_bf, Pm=Pm, mlp_enc_bf=mlp_enc_bf, wr_cat=wr_cat, ws=ws, zc=zc, cx=cx, dzf=dzf,
                          gates=gates, csave=csave, conv_w=conv_w, mlp_att=mlp_att, gvec=gvec, emb_in=emb_in,
                          out_bf=out_bf, ys_in=ys_in, keep=keep, pers=pers, bos=bos,
@@ -330,6 +388,9 @@ class DecoderFn(torch.autograd.Function):
         n = B * R
         a, _ = _dec_common(S["enc_bf"].view(B, Te, H), W, L, K)
         a.mode, a.att_scaling, a.smooth_scaling = mode, att_scaling, smooth_scaling
+        p_drop, site0 = ctx.drop
+        if p_drop > 0:
+            a.drop_p, a.drop_site, a.seed_dev = p_drop, site0, ptr(dropout_seed(dev))
         # output layer (model.py:293): dW = dlogits^T [z;c], d[z;c] = dlogits W
         dl = dlogits.contiguous().view(n, V)
         zc = S["zc"]
@@ -412,7 +473,11 @@ class DecoderFn(torch.autograd.Function):
             dlt_bf = cvt_bf16(dlt)
             d_out_w = gemm(dlt_bf, dlt_bf.shape[1], 1, zc, ZC, 1, V, ZC, n)
             d_out_b = colsum(dlt, V)
-        d_wr = gemm(dgates, 4 * Hd, 1, zc, ZC, 1, 4 * Hd, ZC, n)                      # [4Hd, Hd+O]
+        zc_in = zc
+        if p_drop > 0:                                 # the cell saw [z_{t-1} | dropout(c_{t-1})]
+            zc_in = zc.clone()
+            dropout_(zc_in[Hd:], B, R, O, R * ZC, ZC, 0, p_drop, site0)
+        d_wr = gemm(dgates, 4 * Hd, 1, zc_in, ZC, 1, 4 * Hd, ZC, n)                   # [4Hd, Hd+O]
         emb_in = S["emb_in"] if mode == 0 else S["emb_op"]                            # bf16 [n, Ep] step inputs
         d_we = gemm(dgates, 4 * Hd, 1, emb_in, Ep, 1, 4 * Hd, Ep, n)                  # [4Hd, Ep]
         d_w_ih = torch.cat([d_we[:, :E], d_wr[:, Hd:]], dim=1)
@@ -420,6 +485,8 @@ class DecoderFn(torch.autograd.Function):
         d_b = colsum(dgates, 4 * Hd)
         we_bf = cvt_bf16(W["w_ih"][:, :E], ld_dst=Ep)
         demb_rows = gemm(dgates, 4 * Hd, 0, we_bf, Ep, 1, n, Ep, 4 * Hd)              # f32 [n, Ep]
+        if p_drop > 0:                                 # gradient w.r.t. the un-dropped step embeddings
+            dropout_(demb_rows, B, R, E, R * Ep, Ep, 0, p_drop, site0 + 1)
         if mode == 0:
             d_emb = torch.zeros(V, E, **f32)
             call("las_scatter_add_rows", ptr(demb_rows), Ep, E, ptr(S["ys_in"]), n, 0, ptr(d_emb))
@@ -457,7 +524,7 @@ class DecoderFn(torch.autograd.Function):
                      mlp_enc_w=d_mlp_enc_w, mlp_enc_b=d_mlp_enc_b, mlp_dec_w=d_mlp_dec, mlp_att_w=d_mlp_att,
                      conv_w=d_conv.view_as(W["conv_w"]), gvec_w=d_gvec.view_as(W["gvec_w"]), mlp_o_w=d_mlp_o_w,
                      mlp_o_b=d_mlp_o_b)
-        return (denc, None, None, None, None, None, None, None, None, *[grads[k] for k in DEC_WEIGHTS])
+        return (denc, None, None, None, None, None, None, None, None, None, *[grads[k] for k in DEC_WEIGHTS])
 
 
 # --------------------------------------------------------------------------------------------
@@ -502,7 +569,8 @@ class LMFn(torch.autograd.Function):
     weights: emb_w, then (w_ih, w_hh, b_ih, b_hh) per layer, then out_w, out_b."""
 
     @staticmethod
-    def forward(ctx, ys_in, lens, n_layers, pad, *wts):
+    def forward(ctx, ys_in, lens, n_layers, pad, p_drop, *wts):
+        site0 = new_sites() if p_drop > 0 else 0
         emb_w = wts[0]
         out_w, out_b = wts[-2], wts[-1]
         B, Lm = ys_in.shape
@@ -512,6 +580,8 @@ class LMFn(torch.autograd.Function):
         n = B * Lm
         xin = torch.empty(n, Ep, device=dev, dtype=BF16)
         call("las_gather_rows_bf16", ptr(emb_w), E, ptr(ys_in), n, ptr(xin), Ep)
+        if p_drop > 0:                                # model.py:512
+            dropout_(xin, n, 1, E, Ep, Ep, 0, p_drop, site0)
         Dp = Ep
         saved = []
         for l in range(n_layers):
@@ -528,11 +598,14 @@ class LMFn(torch.autograd.Function):
             call("las_lstm_seq_fwd", ptr(xproj), ptr(whh_pk), ptr(lens), B, Lm, H, 1, ptr(y), Lm * H, H, 0,
                  ptr(hprev), Lm * H, H, ptr(gates), ptr(csave), ptr(ws))
             saved.append((xin, w_bf, hprev, gates, csave, Dp, H))
+            if p_drop > 0:                            # nn.LSTM(dropout=p) between layers (model.py:466) and model.py:520 on top
+                dropout_(y, n, 1, H, H, H, 0, p_drop, site0 + 1 + l)
             xin, Dp = y, H
         out_bf = cvt_bf16(out_w)
         logits = gemm(xin, Dp, 0, out_bf, Dp, 0, n, V, Dp, bias=out_b).view(B, Lm, V)
         ctx.saved = (saved, xin, out_bf, ys_in, lens)
         ctx.geom = (B, Lm, V, E, Ep, n_layers, pad)
+        ctx.drop = (float(p_drop), site0)
         ctx.wts = wts
         return logits
 
@@ -550,11 +623,14 @@ class LMFn(torch.autograd.Function):
         d_out_w = gemm(dl_bf, Vp, 1, ylast, Hl, 1, V, Hl, n)
         d_out_b = colsum(dl, V)
         dy = gemm(dl_bf, Vp, 0, out_bf, Hl, 1, n, Hl, V)
+        p_drop, site0 = ctx.drop
         grads = [None] * len(wts)
         grads[-2], grads[-1] = d_out_w, d_out_b
         for l in reversed(range(n_layers)):
             xin, w_bf, hprev, gates, csave, Dp, H = saved[l]
             w_ih, w_hh, b_ih, b_hh = wts[1 + 4 * l:5 + 4 * l]
+            if p_drop > 0:                            # gradient of this layer's (dropped-out) output
+                dropout_(dy, n, 1, H, dy.stride(0), dy.stride(0), 0, p_drop, site0 + 1 + l)
             whhT, layout = pack_whhT(w_hh)
             dG = torch.empty(n, 4 * H, device=dev, dtype=BF16)
             ws = torch.empty(B * H, device=dev, dtype=torch.float32)
@@ -565,8 +641,10 @@ class LMFn(torch.autograd.Function):
             d_b = colsum(dG, 4 * H)
             grads[1 + 4 * l:5 + 4 * l] = [d_w_ih, d_w_hh, d_b, d_b]
             dy = gemm(dG, 4 * H, 0, w_bf, Dp, 1, n, Dp, 4 * H)                       # f32 [n, Dp]
+        if p_drop > 0:
+            dropout_(dy, n, 1, E, Ep, Ep, 0, p_drop, site0)
         d_emb = torch.zeros(V, E, device=dev, dtype=torch.float32)
         call("las_scatter_add_rows", ptr(dy), Ep, E, ptr(ys_in), n, pad, ptr(d_emb))
         grads[0] = d_emb
         ctx.saved = None
-        return (None, None, None, None, *grads)
+        return (None, None, None, None, None, *grads)

@@ -55,9 +55,8 @@ class pBLSTM(torch.nn.Module):
     def forward_dev(self, xpad, lens_dev):
         """Device-resident variant (no host work; CUDA-graph capturable): x f32 [B, T, D] with T the
         longest length, lens int32 [B] on the device. Returns enc_h only."""
-        if self.training and self.dropout_rate > 0:
-            raise NotImplementedError("dropout inside the fused encoder is not wired yet; use dropout_rate=0")
-        return Fn.EncoderFn.apply(xpad, lens_dev, tuple(int(s) for s in self.subsample), *self._weights())
+        p = float(self.dropout_rate) if self.training else 0.0
+        return Fn.EncoderFn.apply(xpad, lens_dev, tuple(int(s) for s in self.subsample), p, *self._weights())
 
     def out_lens_dev(self, lens_dev):
         """(len + 1) // sub per pyramid level, on the device (model.py:92)."""
@@ -178,12 +177,11 @@ class Decoder(torch.nn.Module):
     def forward_dev(self, enc_pad, enc_lens_dev, ys_in_dev, ys_out_dev, L, mode, scaling=1.0, label_smoothing=True):
         """Device-resident variant (CUDA-graph capturable). ys_in_dev int64 [B, L+1] = [BOS, y, EOS.., PAD],
         ys_out_dev int64 [B, L] = [y, EOS..]; mode 0 teacher forcing, 1 greedy, 2 smooth free-run."""
-        if self.training and self.dropout_rate > 0:
-            raise NotImplementedError("dropout inside the fused decoder is not wired yet; use dropout_rate=0")
         dev = enc_pad.device
+        p = float(self.dropout_rate) if self.training else 0.0
         logits_alloc, ws_alloc, pred = Fn.DecoderFn.apply(
             enc_pad.float().contiguous(), enc_lens_dev, ys_in_dev, L, mode, float(scaling), 2.0,
-            self.attention.conv_kernel_size, self.bos, *self._weights())
+            self.attention.conv_kernel_size, self.bos, p, *self._weights())
         ls = self.ls_weight if (label_smoothing and self.ls_weight > 0 and self.training) else 0.0
         dist = self.vlabeldist.to(dev) if ls > 0 else None
         ys_log_probs, _, prediction = Fn.CELabelSmoothFn.apply(logits_alloc, ys_out_dev, dist, ls, 1, L)
@@ -254,8 +252,6 @@ class LM(torch.nn.Module):
         return w + [self.output_layer.weight, self.output_layer.bias]
 
     def forward(self, ys=None, discrete_input=True):
-        if self.training and self.dropout_rate > 0:
-            raise NotImplementedError("dropout inside the fused LM is not wired yet; use dropout_rate=0")
         dev = self.embedding.weight.device
         if discrete_input:
             ys_host = [y.detach().cpu().numpy().astype(np.int64) if torch.is_tensor(y) else np.asarray(y, np.int64)
@@ -278,7 +274,8 @@ class LM(torch.nn.Module):
             ys_out_dev = ys.contiguous()
             lens = None
             Lm = ys.size(1)
-        logits = Fn.LMFn.apply(ys_in_dev, lens, self.n_layers, self.pad, *self._weights())
+        p = float(self.dropout_rate) if self.training else 0.0
+        logits = Fn.LMFn.apply(ys_in_dev, lens, self.n_layers, self.pad, p, *self._weights())
         ls = self.ls_weight if (self.ls_weight > 0 and self.training) else 0.0
         dist = self.vlabeldist.to(dev) if ls > 0 else None
         ys_log_probs, ys_probs, predictions = Fn.CELabelSmoothFn.apply(logits, ys_out_dev, dist, ls, 0, Lm)

@@ -10,6 +10,7 @@ checkpoints load unchanged.
 import torch
 
 from ._lib import call, ptr
+from .functional import advance_dropout_seed
 
 
 class FusedAdam:
@@ -54,6 +55,7 @@ class FusedAdam:
              ptr(self.max_exp_avg_sq), n, float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),
              float(g["weight_decay"]), ptr(self.step_dev), float(max_norm if max_norm else 0.0), ptr(self.norm_dev),
              float(grad_scale))
+        advance_dropout_seed()                         # the next forward draws new dropout masks
         return self.norm_dev
 
     def step(self):

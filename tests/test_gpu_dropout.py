@@ -1,0 +1,148 @@
+"""Dropout on the CUDA path (model.py:82, 95, 285, 512, 520; config dropout_rate 0.3 / dis_dropout_rate 0.5).
+Bit parity with PyTorch's RNG stream is impossible, so these tests check what can be checked:
+mask statistics and scaling, mask consistency between forward and backward (the backward RECOMPUTES the mask),
+eval mode being dropout-free, fresh masks per step, and agreement between the cluster-persistent and the
+per-step decoder under the same masks."""
+import numpy as np
+import pytest
+import torch
+
+from tests.util import cosine, pkg, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def test_dropout_kernel_statistics_and_replicated_row():
+    Fn = pkg("functional")
+    dev = torch.device("cuda")
+    B, T, W, p = 7, 33, 96, 0.3
+    x = torch.ones(B, T + 1, W, device=dev, dtype=torch.bfloat16)
+    Fn.dropout_(x, B, T, W, (T + 1) * W, W, 1, p, 12345)
+    y = x.float()
+    kept = (y != 0)
+    assert abs(float(kept[:, :T].float().mean()) - (1 - p)) < 0.02
+    assert torch.allclose(y[kept], torch.full_like(y[kept], 1 / (1 - p)), rtol=1e-2)     # bf16(1/(1-p))
+    assert torch.equal(y[:, T], y[:, T - 1])                                             # model.py:88-89 after :82
+    x2 = torch.ones(B, T + 1, W, device=dev, dtype=torch.float32)
+    Fn.dropout_(x2, B, T, W, (T + 1) * W, W, 1, p, 12345)
+    assert torch.equal(x2 != 0, kept)                                                    # same mask for gradients
+    x3 = torch.ones(B, T + 1, W, device=dev, dtype=torch.float32)
+    Fn.dropout_(x3, B, T, W, (T + 1) * W, W, 1, p, 12346)
+    assert not torch.equal(x3 != 0, kept)                                                # another site, another mask
+    Fn.advance_dropout_seed()
+    x4 = torch.ones(B, T + 1, W, device=dev, dtype=torch.float32)
+    Fn.dropout_(x4, B, T, W, (T + 1) * W, W, 1, p, 12345)
+    assert not torch.equal(x4 != 0, kept)                                                # next step, another mask
+
+
+def _model(p, H=64, seed=0):
+    M = pkg("model")
+    torch.manual_seed(seed)
+    rng = np.random.RandomState(seed)
+    B, T, D, V = 6, 41, 24, 17
+    lens = sorted([T] + [int(rng.randint(20, T + 1)) for _ in range(B - 1)], reverse=True)
+    x = np.zeros((B, T, D), dtype=np.float32)
+    ys = []
+    for b, l in enumerate(lens):
+        x[b, :l] = rng.randn(l, D)
+        ys.append(torch.from_numpy(rng.randint(3, V, size=max(2, l // 7)).astype(np.int64)).cuda())
+    ld = np.ones(V) / V
+    m = M.E2E(input_dim=D, enc_hidden_dim=H, enc_n_layers=2, subsample=[2, 2], dropout_rate=p, dec_hidden_dim=H,
+              att_dim=48, conv_channels=5, conv_kernel_size=7, att_odim=H, embedding_dim=32, output_dim=V,
+              ls_weight=0.05, labeldist=ld).cuda()
+    return m, torch.from_numpy(x).cuda(), lens, ys
+
+
+def test_eval_mode_has_no_dropout_and_train_mode_is_stochastic_per_step():
+    Fn = pkg("functional")
+    m, x, lens, ys = _model(0.3)
+    m.eval()
+    with torch.no_grad():
+        a = m(x, lens, ys)[1]
+        b = m(x, lens, ys)[1]
+    assert torch.equal(a, b)
+    m0, _, _, _ = _model(0.0)
+    m0.load_state_dict(m.state_dict())
+    m0.eval()
+    with torch.no_grad():
+        assert torch.equal(m0(x, lens, ys)[1], a)              # eval == the p = 0 model
+    m.train()
+    with torch.no_grad():
+        t1 = m(x, lens, ys)[1]
+        t2 = m(x, lens, ys)[1]                                  # second forward of the same step: other sites
+        Fn.advance_dropout_seed()
+        t3 = m(x, lens, ys)[1]
+    assert not torch.equal(t1, a) and not torch.equal(t1, t2) and not torch.equal(t1, t3)
+    assert abs(float(t1.mean()) - float(a.mean())) < 0.5 * abs(float(a.mean()))      # same scale in expectation
+
+
+def test_backward_recomputes_the_forward_masks():
+    """Directional finite difference of the train-mode loss under FIXED masks (same seed, same site ids):
+    if the backward applied different masks than the forward, the analytic derivative would not match."""
+    Fn = pkg("functional")
+    m, x, lens, ys = _model(0.3, seed=1)
+    m.train()
+
+    def loss_at():
+        Fn._DROP["calls"] = 0                                    # same site ids -> same masks (seed not advanced)
+        return -m(x, lens, ys)[1].mean()
+
+    loss = loss_at()
+    m.zero_grad()
+    loss.backward()
+    names = ["decoder.LSTMCell.weight_ih", "encoder.enc2.project_layers.1.weight", "decoder.embedding.weight",
+             "encoder.enc2.layers.1.weight_hh_l0"]
+    params = dict(m.named_parameters())
+    for k in names:
+        p = params[k]
+        g = p.grad.detach().clone()
+        d = g / (g.norm() + 1e-20)
+        eps = 2e-2
+        with torch.no_grad():
+            p.add_(eps * d)
+            lp = float(loss_at())
+            p.sub_(2 * eps * d)
+            lm = float(loss_at())
+            p.add_(eps * d)
+        fd = (lp - lm) / (2 * eps)
+        an = float((g * d).sum())
+        assert abs(fd - an) < 0.15 * abs(an) + 1e-4, (k, fd, an)
+
+
+def test_persistent_and_per_step_decoder_agree_under_dropout():
+    Fn = pkg("functional")
+    m, x, lens, ys = _model(0.3, seed=2)
+    m.train()
+    outs = []
+    for flag in (True, False):
+        Fn.DEC_PERSISTENT = flag
+        Fn._DROP["calls"] = 0
+        m.zero_grad()
+        logits, logp, _, ws = m(x, lens, ys)
+        (-logp.mean()).backward()
+        outs.append((logits.detach().clone(), ws.detach().clone(), {k: p.grad.detach().clone() for k, p in m.named_parameters()}))
+    Fn.DEC_PERSISTENT = True
+    (l0, w0, g0), (l1, w1, g1) = outs
+    assert rel_err(l0, l1) < 3e-2 and rel_err(w0, w1) < 3e-2
+    for k in g0:
+        assert cosine(g0[k], g1[k]) >= 0.995, (k, cosine(g0[k], g1[k]))
+
+
+def test_lm_dropout_and_ssl_step_run_in_train_mode():
+    M, E = pkg("model"), pkg("engine")
+    m, x, lens, ys = _model(0.3, seed=3)
+    V = m.decoder.output_layer.weight.shape[0]
+    lm = M.LM(output_dim=V, embedding_dim=16, hidden_dim=32, dropout_rate=0.5, n_layers=2, bos=1, eos=2, pad=0,
+              ls_weight=0.05, labeldist=np.ones(V) / V).cuda()
+    opt = pkg("optim").FusedAdam(m.parameters(), lr=1e-3, weight_decay=1e-6, amsgrad=True)
+    tr = E.SSLTrainer(m, lm, opt, proportion=0.2)
+    l1 = tr.step((x, lens, ys), (x, lens))
+    l2 = tr.step((x, lens, ys), (x, lens))
+    assert all(torch.isfinite(t).all() for t in l1[:3] + l2[:3])
+    jt = E.JudgeTrainer(lm, pkg("optim").FusedAdam(lm.parameters(), lr=2e-4))
+    j1 = jt.step(ys)
+    assert torch.isfinite(j1[0])
+    lm.train()
+    a = lm(ys)[0]
+    b = lm(ys)[0]
+    assert not torch.equal(a, b)

@@ -38,7 +38,7 @@ def _run_gpu(x, lens, P, H, persistent):
         proj_w = (torch.randn(H, 4 * H) * 0.2).to(dev).requires_grad_(True)
         proj_b = (torch.randn(H) * 0.1).to(dev).requires_grad_(True)
         lens_dev = Fn.lens_tensor(lens, dev)
-        out = Fn.EncoderFn.apply(x.to(dev), lens_dev, (2,), *w, proj_w, proj_b)
+        out = Fn.EncoderFn.apply(x.to(dev), lens_dev, (2,), 0.0, *w, proj_w, proj_b)
         torch.manual_seed(7)
         gout = torch.randn(out.shape).to(dev)
         (out * gout).sum().backward()
