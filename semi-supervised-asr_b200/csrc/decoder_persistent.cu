@@ -121,6 +121,12 @@ __device__ __forceinline__ void st_remote_u32(uint32_t addr, uint32_t v) {
 __device__ __forceinline__ void st_remote_f32(uint32_t addr, float v) {
   asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
+__device__ __forceinline__ void st_remote_v4_f32(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void st_remote_v4_u32(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 // Release/acquire barrier over all threads of the cluster: remote stores issued before it are
 // visible to every CTA after it.
 __device__ __forceinline__ void cluster_barrier() {
@@ -1047,20 +1053,16 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
     DTRACE(4);
     // B4: ddz partial -> all CTAs (f32); conv-input gradient of my frames for step t-1
     if (own_ok) {
-      for (int ap = tid; ap < A2; ap += kBT) {
-        float v0 = 0.f, v1 = 0.f;
+      for (int aq = tid; aq < (A >> 2); aq += kBT) {      // 4 attention dims per thread: 16-byte remote stores
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (ntl > 0)
           for (int tt = 0; tt < g.TT; ++tt) {
-            const float2 v = *reinterpret_cast<const float2*>(ddz_part + tt * A + 2 * ap);
-            v0 += v.x; v1 += v.y;
+            const float4 x = *reinterpret_cast<const float4*>(ddz_part + tt * A + 4 * aq);
+            v.x += x.x; v.y += x.y; v.z += x.z; v.w += x.w;
           }
-        const uint32_t off = ddzrx_base + 4u * ((q * NB + n_own) * A + 2 * ap);
+        const uint32_t off = ddzrx_base + 4u * ((q * NB + n_own) * A + 4 * aq);
 #pragma unroll
-        for (int r = 0; r < kCS; ++r) {
-          const uint32_t ra = mapa(off, r);
-          st_remote_f32(ra, v0);
-          st_remote_f32(ra + 4u, v1);
-        }
+        for (int r = 0; r < kCS; ++r) st_remote_v4_f32(mapa(off, r), v.x, v.y, v.z, v.w);
       }
     }
     if (e_act && e_wi == 0) {
@@ -1186,15 +1188,16 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
         }
       }
       if (warp < (RPC * NB + 31) / 32) {
+        // K order of the gathered gate gradients (must match the Wr^T fragments, pack_rowsel_kernel kperm):
+        // k-tile = 4 hidden units; the 4 gate values of a unit pair are 4 consecutive fragment words
+        uint32_t wd[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint32_t up = __shfl_down_sync(0xffffffffu, w4[k], 1);
-          if (epi && is_z && (row_l & 1) == 0) {
-            const uint32_t word = w4[k] | (up << 16);
-            const uint32_t off = dgB_base + 4u * static_cast<uint32_t>(bfrag_word(k * Hd + u_e, n_e));
+        for (int k = 0; k < 4; ++k) wd[k] = w4[k] | (__shfl_down_sync(0xffffffffu, w4[k], 1) << 16);
+        if (epi && is_z && (row_l & 1) == 0) {
+          const int kt = u_e >> 2, pp = (u_e >> 1) & 1;
+          const uint32_t off = dgB_base + 4u * static_cast<uint32_t>((kt * 32 + n_e * 4 + 2 * pp) * 2);
 #pragma unroll
-            for (int r = 0; r < kCS; ++r) st_remote_u32(mapa(off, r), word);
-          }
+          for (int r = 0; r < kCS; ++r) st_remote_v4_u32(mapa(off, r), wd[0], wd[1], wd[2], wd[3]);
         }
       }
     }
@@ -1209,8 +1212,11 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
 // A[row i][k] = W[k*ld + col(i)] for the rows a CTA owns in the backward kernel:
 // i < UPC -> col = col_z0 + r*UPC + i; UPC <= i < UPC+OPC -> col = col_c0 + r*OPC + (i - UPC); else zero.
 // out: [16][MT][KT][32][4] mma A fragments.
+// kperm != 0 (Wr^T): fragment column k' of k-tile kt stands for W row gate*Hd + unit with unit = 4*kt + 2*pp + j and
+// k' - 16*kt = 4*pp + j + (gate & 1 ? 8 : 0) + (gate & 2 ? 2 : 0)  (so that a unit pair's four gate gradients are four
+// consecutive B-fragment words: one 16-byte DSMEM store in the backward kernel).
 __global__ void pack_rowsel_kernel(const float* __restrict__ W, int64_t ld, int Ktot, int MT, int KT, int UPC, int OPC,
-                                   int col_z0, int col_c0, uint32_t* __restrict__ out) {
+                                   int col_z0, int col_c0, int kperm, int Hd, uint32_t* __restrict__ out) {
   const int64_t total = static_cast<int64_t>(kCS) * MT * KT * 128;
   for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -1227,8 +1233,18 @@ __global__ void pack_rowsel_kernel(const float* __restrict__ W, int64_t ld, int 
     else if (i < UPC + OPC) col = col_c0 + r * OPC + (i - UPC);
     float v0 = 0.f, v1 = 0.f;
     if (col >= 0) {
-      if (k0 < Ktot) v0 = W[static_cast<int64_t>(k0) * ld + col];
-      if (k0 + 1 < Ktot) v1 = W[static_cast<int64_t>(k0 + 1) * ld + col];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        int k = k0 + e;
+        if (kperm) {
+          const int kk = k & 15, ktile = k >> 4;
+          const int gate = ((kk >> 3) & 1) | (((kk >> 1) & 1) << 1);
+          const int unit = 4 * ktile + 2 * ((kk >> 2) & 1) + (kk & 1);
+          k = (unit < Hd) ? gate * Hd + unit : Ktot;
+        }
+        const float v = (k < Ktot) ? W[static_cast<int64_t>(k) * ld + col] : 0.f;
+        if (e == 0) v0 = v; else v1 = v;
+      }
     }
     out[idx] = pack_bf16x2(v0, v1);
   }
@@ -1347,7 +1363,8 @@ int dec_persist_pack(int which, const float* W, int64_t ld, int Hd, int O, int A
   const int64_t total = static_cast<int64_t>(kCS) * MT * KT * 128;
   int blocks = static_cast<int>((total + 255) / 256);
   if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
-  pack_rowsel_kernel<<<blocks, 256, 0, stream>>>(W, ld, Ktot, MT, KT, UPC, opc, cz, cc, static_cast<uint32_t*>(out));
+  pack_rowsel_kernel<<<blocks, 256, 0, stream>>>(W, ld, Ktot, MT, KT, UPC, opc, cz, cc, which == 0 ? 1 : 0, Hd,
+                                                 static_cast<uint32_t*>(out));
   ++g_launches;
   LAS_LAUNCH_CHECK();
   return 0;
