@@ -48,6 +48,13 @@ int las_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int
                   int b_mn_major, void* C, int64_t ldc, int c_is_bf16, const float* bias, int M,
                   int N, int K, int relu, int accumulate, void* stream);
 
+/* Same contraction with a caller workspace (f32, ws_bytes): shapes with few output tiles and a long K (the
+ * weight-gradient GEMMs: K = all frames of the batch) are split along K over the idle SMs, partial tiles go to
+ * the workspace and are summed in a fixed order (deterministic). Falls back to the plain path otherwise. */
+int las_gemm_bf16_ws(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb,
+                     int b_mn_major, void* C, int64_t ldc, int c_is_bf16, const float* bias, int M,
+                     int N, int K, int relu, int accumulate, void* ws, int64_t ws_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * element-wise / reduction helpers (HBM-bound)
  * ---------------------------------------------------------------------------------------- */

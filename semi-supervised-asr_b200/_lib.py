@@ -42,6 +42,7 @@ SIGNATURES = {
     "las_num_sms": (c_int, []),
     "las_launch_count": (ctypes.c_ulonglong, []),
     "las_gemm_bf16": (c_int, [P, L, I, P, L, I, P, L, I, P, I, I, I, I, I, P]),
+    "las_gemm_bf16_ws": (c_int, [P, L, I, P, L, I, P, L, I, P, I, I, I, I, I, P, L, P]),
     "las_cvt_pad_bf16": (c_int, [P, L, L, I, P, L, P]),
     "las_add2": (c_int, [P, P, P, L, P]),
     "las_dropout": (c_int, [P, I, L, L, I, L, L, I, F, P, ctypes.c_uint32, P]),

@@ -56,4 +56,12 @@ int las_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int
                         static_cast<cudaStream_t>(stream));
 }
 
+int las_gemm_bf16_ws(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb,
+                     int b_mn_major, void* C, int64_t ldc, int c_is_bf16, const float* bias, int M,
+                     int N, int K, int relu, int accumulate, void* ws, int64_t ws_bytes, void* stream) {
+  return las::gemm_bf16(A, lda, a_mn_major != 0, B, ldb, b_mn_major != 0, C, ldc, c_is_bf16 != 0,
+                        bias, M, N, K, relu != 0, accumulate != 0,
+                        static_cast<cudaStream_t>(stream), ws, ws_bytes);
+}
+
 }  // extern "C"

@@ -40,6 +40,7 @@ struct GemmParams {
   int M, N, K;
   int relu;
   int accumulate;
+  int ksplit;        // > 1: work item = (tile, K slice); C is then the f32 workspace [ksplit][M][N] (ldc = N)
 };
 
 template <int BN, bool A_MN, bool B_MN, typename OutT>
@@ -63,6 +64,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   const int n_blocks = (p.N + BN - 1) / BN;
   const int k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
   const int num_tiles = m_blocks * n_blocks;
+  const int kb_per = (k_blocks + p.ksplit - 1) / p.ksplit;
+  const int num_items = num_tiles * p.ksplit;      // host guarantees that every K slice is non-empty
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -89,10 +92,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     // ===================== TMA producer =====================
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const int tile = item % num_tiles, split = item / num_tiles;
       const int m0 = (tile / n_blocks) * BLOCK_M;
       const int n0 = (tile % n_blocks) * BN;
-      for (int kb = 0; kb < k_blocks; ++kb) {
+      const int kb0 = split * kb_per, kb1 = min(k_blocks, kb0 + kb_per);
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * L::kStageBytes;
         uint8_t* sb = sa + L::kABytes;
@@ -122,11 +127,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const int split = item / num_tiles;
+      const int kb0 = split * kb_per, kb1 = min(k_blocks, kb0 + kb_per);
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BN;
-      for (int kb = 0; kb < k_blocks; ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
@@ -139,10 +146,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                                       : make_smem_desc_sw128(sa + k * (UMMA_K * 2), 16, 1024);
           const uint64_t bdesc = B_MN ? make_smem_desc_sw128(sb + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
                                       : make_smem_desc_sw128(sb + k * (UMMA_K * 2), 16, 1024);
-          umma_bf16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
+          umma_bf16(d_tmem, adesc, bdesc, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
         }
         umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
-        if (kb == k_blocks - 1) umma_commit(&tfull_bar[acc]);
+        if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
@@ -152,8 +159,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     const int q = warp & 3;  // TMEM lane quadrant this warp may touch
     int acc = 0;
     uint32_t acc_phase = 0;
-    OutT* Cout = reinterpret_cast<OutT*>(p.C);
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const int tile = item % num_tiles, split = item / num_tiles;
+      OutT* Cout = reinterpret_cast<OutT*>(p.C) + static_cast<int64_t>(split) * p.M * p.N;   // split > 0 only with ldc == N
       const int m0 = (tile / n_blocks) * BLOCK_M;
       const int n0 = (tile % n_blocks) * BN;
       mbar_wait(&tfull_bar[acc], acc_phase);
@@ -235,6 +243,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   }
 }
 
+// Deterministic split-K reduction: C[m, n] = (accumulate ? C : 0) + sum_s ws[s][m][n] (+ bias[n]) (relu).
+template <typename OutT>
+__global__ void splitk_reduce_kernel(const float* __restrict__ ws, int ksplit, int M, int N, OutT* __restrict__ C,
+                                     int64_t ldc, const float* __restrict__ bias, int relu, int accumulate) {
+  const int64_t total = static_cast<int64_t>(M) * N;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int m = static_cast<int>(i / N), n = static_cast<int>(i % N);
+    float v = 0.f;
+    for (int s = 0; s < ksplit; ++s) v += ws[s * total + i];
+    if (bias != nullptr) v += bias[n];
+    if (relu) v = fmaxf(v, 0.f);
+    OutT* c = C + m * ldc + n;
+    if constexpr (sizeof(OutT) == 4) *c = accumulate ? *c + v : v;
+    else *c = __float2bfloat16(accumulate ? __bfloat162float(*c) + v : v);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -281,7 +307,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cu
     LAS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     configured = true;
   }
-  const int tiles = ((p.M + BLOCK_M - 1) / BLOCK_M) * ((p.N + BN - 1) / BN);
+  const int tiles = ((p.M + BLOCK_M - 1) / BLOCK_M) * ((p.N + BN - 1) / BN) * p.ksplit;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   kern<<<grid, kThreads, L::kTotal, stream>>>(ta, tb, p); ++g_launches;
   LAS_LAUNCH_CHECK();
@@ -301,7 +327,7 @@ int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMa
 
 int gemm_bf16(const void* A, int64_t lda, bool a_mn, const void* B, int64_t ldb, bool b_mn, void* C,
               int64_t ldc, bool c_bf16, const float* bias, int M, int N, int K, bool relu,
-              bool accumulate, cudaStream_t stream) {
+              bool accumulate, cudaStream_t stream, void* ws, int64_t ws_bytes) {
   if (M == 0 || N == 0) return 0;
   LAS_REQUIRE(K > 0, "gemm: K must be positive");
   int rc = get_encode();
@@ -315,7 +341,38 @@ int gemm_bf16(const void* A, int64_t lda, bool a_mn, const void* B, int64_t ldb,
   if (!b_mn) rc = make_tmap(&tb, B, N, K, ldb, BLOCK_K, BN);
   else       rc = make_tmap(&tb, B, K, N, ldb, 64, BLOCK_K);
   if (rc) return rc;
-  GemmParams p{C, bias, ldc, M, N, K, relu ? 1 : 0, accumulate ? 1 : 0};
+  // Split-K for the weight-gradient shapes (few output tiles, K = all frames of the batch): the K slices
+  // go to otherwise idle SMs, partial tiles land in the caller's workspace and are summed in a fixed order.
+  const int tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + BN - 1) / BN);
+  const int k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
+  int ksplit = 1;
+  if (ws != nullptr && tiles * 2 <= num_sms() && k_blocks >= 32) {
+    ksplit = num_sms() / tiles;
+    if (ksplit > k_blocks / 8) ksplit = k_blocks / 8;
+    if (ksplit > 16) ksplit = 16;
+    while (ksplit > 1 && static_cast<int64_t>(ksplit) * M * N * 4 > ws_bytes) --ksplit;
+    const int per = (k_blocks + ksplit - 1) / ksplit;
+    ksplit = (k_blocks + per - 1) / per;            // no empty slice
+  }
+  if (ksplit > 1) {
+    GemmParams p{ws, nullptr, N, M, N, K, 0, 0, ksplit};
+    rc = (BN == 64) ? dispatch_major<64, float>(a_mn, b_mn, ta, tb, p, stream)
+                    : dispatch_major<128, float>(a_mn, b_mn, ta, tb, p, stream);
+    if (rc) return rc;
+    const int64_t total = static_cast<int64_t>(M) * N;
+    int blocks = static_cast<int>((total + 255) / 256);
+    if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
+    if (c_bf16)
+      splitk_reduce_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(static_cast<const float*>(ws), ksplit, M, N,
+                                                                      static_cast<__nv_bfloat16*>(C), ldc, bias, relu, accumulate);
+    else
+      splitk_reduce_kernel<float><<<blocks, 256, 0, stream>>>(static_cast<const float*>(ws), ksplit, M, N,
+                                                              static_cast<float*>(C), ldc, bias, relu, accumulate);
+    ++g_launches;
+    LAS_LAUNCH_CHECK();
+    return 0;
+  }
+  GemmParams p{C, bias, ldc, M, N, K, relu ? 1 : 0, accumulate ? 1 : 0, 1};
   if (BN == 64) {
     return c_bf16 ? dispatch_major<64, __nv_bfloat16>(a_mn, b_mn, ta, tb, p, stream)
                   : dispatch_major<64, float>(a_mn, b_mn, ta, tb, p, stream);

@@ -13,7 +13,7 @@ int num_sms();
 //   a_mn == true  : A is row-major [K, M] with leading dimension lda   (same for B / N)
 int gemm_bf16(const void* A, int64_t lda, bool a_mn, const void* B, int64_t ldb, bool b_mn, void* C,
               int64_t ldc, bool c_bf16, const float* bias, int M, int N, int K, bool relu,
-              bool accumulate, cudaStream_t stream);
+              bool accumulate, cudaStream_t stream, void* ws = nullptr, int64_t ws_bytes = 0);
 
 // cluster-persistent recurrence (blstm_persistent.cu)
 int persist_supported(int H);

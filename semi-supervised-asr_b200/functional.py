@@ -64,6 +64,17 @@ def _r16(n):
 # --------------------------------------------------------------------------------------------
 # thin op wrappers
 # --------------------------------------------------------------------------------------------
+_GEMM_WS = {}
+
+
+def _gemm_workspace(device):
+    """Split-K workspace (32 MiB of f32, one per device; stream-ordered use only)."""
+    ws = _GEMM_WS.get(device)
+    if ws is None:
+        ws = _GEMM_WS[device] = torch.empty(8 << 20, device=device, dtype=torch.float32)
+    return ws
+
+
 def gemm(A, lda, a_mn, Bm, ldb, b_mn, M, N, K, out=None, out_bf16=False, bias=None, relu=False,
          accumulate=False, ldc=None):
     """D[m,n] = sum_k A[m,k] B[n,k] (+bias[n]) (relu) (+=D). A/Bm: bf16 tensors (base pointers)."""
@@ -71,8 +82,9 @@ def gemm(A, lda, a_mn, Bm, ldb, b_mn, M, N, K, out=None, out_bf16=False, bias=No
         out = torch.empty(M, N, device=A.device, dtype=BF16 if out_bf16 else torch.float32)
     if ldc is None:
         ldc = N
-    call("las_gemm_bf16", ptr(A), lda, int(a_mn), ptr(Bm), ldb, int(b_mn), ptr(out), ldc, int(out.dtype == BF16),
-         ptr(bias), M, N, K, int(relu), int(accumulate))
+    ws = _gemm_workspace(A.device)
+    call("las_gemm_bf16_ws", ptr(A), lda, int(a_mn), ptr(Bm), ldb, int(b_mn), ptr(out), ldc, int(out.dtype == BF16),
+         ptr(bias), M, N, K, int(relu), int(accumulate), ptr(ws), ws.numel() * 4)
     return out
 
 
