@@ -88,6 +88,14 @@ __device__ __forceinline__ uint4 philox4x32_10(uint2 key, uint4 ctr) {
   }
   return ctr;
 }
+// keep decisions of the 4 elements 4*blk .. 4*blk+3 (one Philox call): bit i of the result = element 4*blk + i
+__device__ __forceinline__ uint32_t dropout_keep4(unsigned long long seed, uint32_t site, unsigned long long blk, float p) {
+  const uint4 r = philox4x32_10(make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)),
+                                make_uint4(static_cast<uint32_t>(blk), static_cast<uint32_t>(blk >> 32), site, 0x4c41535fu));
+  const float s = 1.0f / 16777216.0f;
+  return (static_cast<float>(r.x >> 8) * s >= p ? 1u : 0u) | (static_cast<float>(r.y >> 8) * s >= p ? 2u : 0u) |
+         (static_cast<float>(r.z >> 8) * s >= p ? 4u : 0u) | (static_cast<float>(r.w >> 8) * s >= p ? 8u : 0u);
+}
 __device__ __forceinline__ bool dropout_keep(unsigned long long seed, uint32_t site, unsigned long long idx, float p) {
   const unsigned long long blk = idx >> 2;
   const uint4 r = philox4x32_10(make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)),

@@ -589,6 +589,7 @@ __global__ void __launch_bounds__(256) att_denc_kernel(const float* __restrict__
 //   dP[b,te,a] = sum_t ds,  part[cta][c][a] = sum ds*conv[c],  part[cta][CM][a] = sum de*s,  ds = de gv (1 - s^2)
 // grid (ceil(Te/kPG), B), block = A rounded up to a warp multiple.
 constexpr int kPG = 8;   // frames per CTA: small tiles keep ~4 CTAs per SM in flight (the loop is latency-bound)
+constexpr int kPGT = 16;   // decoder steps per shared-memory chunk
 template <int CM>
 __global__ void __launch_bounds__(512) att_param_grad_kernel(const float* __restrict__ P, const float* __restrict__ dzf,
                                                              const float* __restrict__ conv_save,
@@ -597,8 +598,13 @@ __global__ void __launch_bounds__(512) att_param_grad_kernel(const float* __rest
                                                              const float* __restrict__ gvec, int B, int L, int Te, int A,
                                                              int C, int Ap, float* __restrict__ dP,
                                                              float* __restrict__ part) {
+  // step-major loop: dz_t is read once per step, the conv features / energy gradients of the tile's frames are
+  // staged per chunk of kPGT steps with cp.async (double buffered), P and the accumulators live in registers
+  __shared__ __align__(16) float conv_s[2][kPGT][kPG][16];
+  __shared__ float de_s[2][kPGT][kPG];
   const int b = blockIdx.y, te0 = blockIdx.x * kPG, a = threadIdx.x;
   const bool ok = a < A;
+  const int ntl = min(kPG, Te - te0);
   float matt[CM], dmatt[CM];
 #pragma unroll
   for (int c = 0; c < CM; ++c) {
@@ -606,34 +612,76 @@ __global__ void __launch_bounds__(512) att_param_grad_kernel(const float* __rest
     dmatt[c] = 0.f;
   }
   const float gv = ok ? gvec[a] : 0.f;
-  float dgv = 0.f;
-  const int ntl = min(kPG, Te - te0);
-  for (int tl = 0; tl < ntl; ++tl) {
-    const int te = te0 + tl;
-    const float pv = ok ? P[(static_cast<int64_t>(b) * Te + te) * A + a] : 0.f;
-    float dp = 0.f;
-    for (int t = 0; t < L; ++t) {
-      const float de = __ldg(de_all + (static_cast<int64_t>(b) * L + t) * Te + te);
-      const float4* cv = reinterpret_cast<const float4*>(conv_save + ((static_cast<int64_t>(b) * L + t) * Te + te) * 16);
-      float conv[CM];
+  float dgv = 0.f, pv[kPG], dp[kPG];
 #pragma unroll
-      for (int c4 = 0; c4 < CM / 4; ++c4) {
-        const float4 v = __ldg(cv + c4);
-        conv[4 * c4] = v.x; conv[4 * c4 + 1] = v.y; conv[4 * c4 + 2] = v.z; conv[4 * c4 + 3] = v.w;
+  for (int f = 0; f < kPG; ++f) {
+    pv[f] = (ok && f < ntl) ? P[(static_cast<int64_t>(b) * Te + te0 + f) * A + a] : 0.f;
+    dp[f] = 0.f;
+  }
+  auto stage = [&](int chunk, int buf) {
+    const int t0 = chunk * kPGT;
+    // conv rows: kPGT x ntl x 16 floats in 16-byte pieces; energy gradients: kPGT x ntl floats
+    for (int i = threadIdx.x; i < kPGT * kPG * 4; i += blockDim.x) {
+      const int q4 = i & 3, f = (i >> 2) % kPG, tt = i / (4 * kPG);
+      const int t = t0 + tt;
+      float* dst = &conv_s[buf][tt][f][4 * q4];
+      if (t < L && f < ntl) {
+        const float* src = conv_save + ((static_cast<int64_t>(b) * L + t) * Te + te0 + f) * 16 + 4 * q4;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+      } else {
+        *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      float x = pv + (ok ? dzf[(static_cast<int64_t>(b) * L + t) * A + a] : 0.f);
-#pragma unroll
-      for (int c = 0; c < CM; ++c) x = fmaf(matt[c], conv[c], x);
-      const float s = tanh_fast(x);
-      const float ds = de * gv * (1.f - s * s);
-      dp += ds;
-      dgv = fmaf(de, s, dgv);
-#pragma unroll
-      for (int c = 0; c < CM; ++c) dmatt[c] = fmaf(ds, conv[c], dmatt[c]);
     }
-    if (ok) dP[(static_cast<int64_t>(b) * Te + te) * A + a] = dp;
+    for (int i = threadIdx.x; i < kPGT * kPG; i += blockDim.x) {
+      const int f = i % kPG, tt = i / kPG, t = t0 + tt;
+      float* dst = &de_s[buf][tt][f];
+      if (t < L && f < ntl) {
+        const float* src = de_all + (static_cast<int64_t>(b) * L + t) * Te + te0 + f;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+      } else {
+        *dst = 0.f;
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  const int nchunks = (L + kPGT - 1) / kPGT;
+  stage(0, 0);
+  for (int ch = 0; ch < nchunks; ++ch) {
+    const int buf = ch & 1;
+    if (ch + 1 < nchunks) stage(ch + 1, buf ^ 1);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncthreads();
+    const int tn = min(kPGT, L - ch * kPGT);
+    for (int tt = 0; tt < tn; ++tt) {
+      const float dz = ok ? __ldg(dzf + (static_cast<int64_t>(b) * L + ch * kPGT + tt) * A + a) : 0.f;
+#pragma unroll
+      for (int f = 0; f < kPG; ++f) {
+        const float4* cv = reinterpret_cast<const float4*>(&conv_s[buf][tt][f][0]);
+        float conv[CM];
+#pragma unroll
+        for (int c4 = 0; c4 < CM / 4; ++c4) {
+          const float4 v = cv[c4];
+          conv[4 * c4] = v.x; conv[4 * c4 + 1] = v.y; conv[4 * c4 + 2] = v.z; conv[4 * c4 + 3] = v.w;
+        }
+        const float de = de_s[buf][tt][f];
+        float x = pv[f] + dz;
+#pragma unroll
+        for (int c = 0; c < CM; ++c) x = fmaf(matt[c], conv[c], x);
+        const float sx = tanh_fast(x);
+        const float ds = de * gv * (1.f - sx * sx);
+        dp[f] += ds;
+        dgv = fmaf(de, sx, dgv);
+#pragma unroll
+        for (int c = 0; c < CM; ++c) dmatt[c] = fmaf(ds, conv[c], dmatt[c]);
+      }
+    }
+    __syncthreads();
   }
   if (ok) {
+#pragma unroll
+    for (int f = 0; f < kPG; ++f)
+      if (f < ntl) dP[(static_cast<int64_t>(b) * Te + te0 + f) * A + a] = dp[f];
     float* pp = part + static_cast<int64_t>(blockIdx.y * gridDim.x + blockIdx.x) * (CM + 1) * Ap + a;
 #pragma unroll
     for (int c = 0; c < CM; ++c) pp[c * Ap] = dmatt[c];

@@ -302,11 +302,57 @@ int las_add2(const float* a, const float* b, float* out, int64_t n, void* stream
   return 0;
 }
 
+}  // extern "C"
+namespace las {
+// W % 4 == 0 and 4-element-aligned rows: one thread = 4 consecutive elements = one Philox call, vector access.
+template <typename T>
+__global__ void dropout4_kernel(T* __restrict__ x, int64_t B, int64_t Tn, int W, int64_t ld_b, int64_t ld_t, int rep_row,
+                                float p, const unsigned long long* __restrict__ seed_dev, uint32_t site) {
+  const unsigned long long seed = *seed_dev;
+  const float scale = 1.0f / (1.0f - p);
+  const int W4 = W >> 2;
+  const int64_t rows = Tn + rep_row, total = B * rows * W4;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c4 = static_cast<int>(i % W4);
+    const int64_t bt = i / W4, t = bt % rows, b = bt / rows;
+    const int64_t tm = t < Tn ? t : Tn - 1;
+    const uint32_t k = dropout_keep4(seed, site, static_cast<unsigned long long>(((b * Tn + tm) * W + 4 * c4) >> 2), p);
+    T* q = x + b * ld_b + t * ld_t + 4 * c4;
+    if constexpr (sizeof(T) == 2) {
+      uint2 v = *reinterpret_cast<uint2*>(q);
+      const float2 a = unpack_bf16x2(v.x), c = unpack_bf16x2(v.y);
+      v.x = pack_bf16x2((k & 1u) ? a.x * scale : 0.f, (k & 2u) ? a.y * scale : 0.f);
+      v.y = pack_bf16x2((k & 4u) ? c.x * scale : 0.f, (k & 8u) ? c.y * scale : 0.f);
+      *reinterpret_cast<uint2*>(q) = v;
+    } else {
+      float4 v = *reinterpret_cast<float4*>(q);
+      v.x = (k & 1u) ? v.x * scale : 0.f; v.y = (k & 2u) ? v.y * scale : 0.f;
+      v.z = (k & 4u) ? v.z * scale : 0.f; v.w = (k & 8u) ? v.w * scale : 0.f;
+      *reinterpret_cast<float4*>(q) = v;
+    }
+  }
+}
+}  // namespace las
+extern "C" {
+
 int las_dropout(void* x, int x_is_bf16, int64_t B, int64_t T, int W, int64_t ld_b, int64_t ld_t, int rep_row, float p,
                 const void* seed_dev, uint32_t site, void* stream) {
   LAS_REQUIRE(p >= 0.f && p < 1.f, "dropout: rate %f out of range [0, 1)", p);
   if (p == 0.f || B * T * W == 0) return 0;
   const int64_t n = B * (T + rep_row) * W;
+  const int esz = x_is_bf16 ? 2 : 4;
+  if (W % 4 == 0 && ld_b % 4 == 0 && ld_t % 4 == 0 && (reinterpret_cast<uintptr_t>(x) % (4 * esz)) == 0) {
+    if (x_is_bf16)
+      dropout4_kernel<__nv_bfloat16><<<grid_for(n / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+          static_cast<__nv_bfloat16*>(x), B, T, W, ld_b, ld_t, rep_row, p, static_cast<const unsigned long long*>(seed_dev), site);
+    else
+      dropout4_kernel<float><<<grid_for(n / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+          static_cast<float*>(x), B, T, W, ld_b, ld_t, rep_row, p, static_cast<const unsigned long long*>(seed_dev), site);
+    ++g_launches;
+    LAS_LAUNCH_CHECK();
+    return 0;
+  }
   if (x_is_bf16)
     dropout_kernel<__nv_bfloat16><<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<__nv_bfloat16*>(x), B, T, W, ld_b, ld_t, rep_row, p, static_cast<const unsigned long long*>(seed_dev), site);
