@@ -323,17 +323,15 @@ def kernel_roofline(dev, hbm_peak, which):
     torch.manual_seed(0)
     xproj = torch.randn(B * T, 8 * H, device=dev) * 0.1
     w = [torch.randn(4 * H, H, device=dev) * 0.05 for _ in range(2)]
-    whh = torch.cat([Fn.pack_afrag(w[0], 1, H), Fn.pack_afrag(w[1], 1, H)])
+    whh = torch.cat([Fn.pack_afrag(w[0], 3, H), Fn.pack_afrag(w[1], 3, H)])
     lens = torch.full((B,), T, device=dev, dtype=torch.int32)
     y = torch.zeros(B, T, 2 * H, device=dev, dtype=torch.bfloat16)
     hprev = torch.empty_like(y)
-    gates = torch.empty(2, B, T, H, 4, device=dev, dtype=torch.float16)
-    cs = torch.empty(2, B, T, H, device=dev, dtype=torch.float32)
-    ws = torch.empty(LIB.lib().las_lstm_ws_bytes(B, H, 2), device=dev, dtype=torch.uint8)
+    rec = torch.empty(2 * B * T * H, 4, device=dev, dtype=torch.int32)
 
     def run():
-        Fn.call("las_lstm_seq_fwd", Fn.ptr(xproj), Fn.ptr(whh), Fn.ptr(lens), B, T, H, 2, Fn.ptr(y), T * 2 * H, 2 * H, 0,
-                Fn.ptr(hprev), T * 2 * H, 2 * H, Fn.ptr(gates), Fn.ptr(cs), Fn.ptr(ws))
+        Fn.call("las_lstm_persist_fwd", Fn.ptr(xproj), Fn.ptr(whh), Fn.ptr(lens), B, T, H, 2, Fn.ptr(y), T * 2 * H, 2 * H,
+                0, Fn.ptr(hprev), T * 2 * H, 2 * H, Fn.ptr(rec))
     g = torch.cuda.CUDAGraph()
     run()
     torch.cuda.synchronize()
@@ -350,8 +348,9 @@ def kernel_roofline(dev, hbm_peak, which):
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / 3            # one launch = the whole T-step sequence, both directions
     # algorithmic HBM bytes of one launch (DESIGN.md "kernels"): W_hh fragments once (2*4H*H*2 B), per (b, t):
-    # xproj row 8H*4 B read; y 2H*2 B, hprev 2H*2 B, gates (4 x f16) 2H*8 B and c (f32) 2H*4 B written.
-    bytes_per_launch = 2 * 4 * H * H * 2 + B * T * (8 * H * 4 + 2 * H * 2 + 2 * H * 2 + 2 * H * 8 + 2 * H * 4)
+    # xproj row 8H*4 B read; y 2H*2 B, hprev 2H*2 B and the 16-byte activation records (gates 4 x f16, c, tanh c:
+    # 2H*16 B) written.
+    bytes_per_launch = 2 * 4 * H * H * 2 + B * T * (8 * H * 4 + 2 * H * 2 + 2 * H * 2 + 2 * H * 16)
     ach = bytes_per_launch / (us * 1e-6) / 1e9
     return {"kernel": "lstm_persist_fwd_kernel (BLSTM layer 0: T=1000 timesteps, both directions, one launch)",
             "bound": "hbm", "achieved": ach, "peak": hbm_peak, "peak_source": which, "unit": "GB/s",

@@ -111,7 +111,7 @@ int las_adam_step(float* p, const float* g, float* m, float* v, float* vmax, int
  * recurrences (model.py:67, 79-81 packed BLSTM; model.py:466, 515-517 LM LSTM)
  * ---------------------------------------------------------------------------------------- */
 /* f32 weight matrix -> bf16 mma A-fragments. mode 0: rows in order; mode 1: LSTM gate-interleaved
- * (rows = 4H, logical row gate*H + unit; tile = 8 units x 2 gates); mode 2: tile = 4 units x 4 gates. transposed: logical A[r][c] = W[c*ld + col_offset + r]. */
+ * (rows = 4H, logical row gate*H + unit; tile = 8 units x 2 gates); mode 2: tile = 4 units x 4 gates; mode 3: mode 2 with the K positions of each k-tile quad-permuted (persistent LSTM forward). transposed: logical A[r][c] = W[c*ld + col_offset + r]. */
 int las_pack_afrag(const float* W, int64_t ld, int rows, int cols, int col_offset, int mode, int H,
                    int transposed, void* out, void* stream);
 int64_t las_afrag_bytes(int rows, int cols, int mode, int H);
@@ -128,10 +128,20 @@ int las_lstm_seq_bwd(const float* dy, int64_t dy_ld_b, int64_t dy_ld_t, int rep_
                      const void* whhT_pk, int whhT_layout, const int32_t* lens, int B, int T, int H,
                      int ndir, const void* gates_save, const float* c_save, void* dG, int64_t dg_ld_b,
                      int64_t dg_ld_t, void* ws, void* stream);
-/* Cluster-persistent recurrence (one launch per layer and pass): returns 1 and the cluster size /
- * units per CTA when hidden size H is served by it (las_lstm_seq_fwd then uses it automatically;
- * las_lstm_seq_bwd uses it when whhT_layout == 1, i.e. W_hh^T packed by las_pack_whhT_owner). */
+/* Cluster-persistent recurrence (one launch per layer and pass). las_lstm_persistent_geometry returns 1 (and
+ * the backward kernel's cluster size / units per CTA) when hidden size H is served by it. Its operand layouts
+ * differ from the per-timestep pair above so that every thread moves 8-16 bytes per access:
+ *   xproj, dG  columns are gate-minor: [dir*4H + 4*unit + gate] (permute the rows of W_ih / the bias accordingly)
+ *   whh_pk     las_pack_afrag mode 2 per direction; whhT_owner_pk from las_pack_whhT_owner
+ *   rec        [ndir, B, T, H] records of 16 bytes: (i,f) f16x2 | (g,o) f16x2 | c f32 | tanh(c) f32
+ * y / hprev / dy / lens / rep_row as in las_lstm_seq_{fwd,bwd}. */
 int las_lstm_persistent_geometry(int H, int* cs, int* upc);
+int las_lstm_persist_fwd(const float* xproj, const void* whh_pk, const int32_t* lens, int B, int T, int H,
+                         int ndir, void* y, int64_t y_ld_b, int64_t y_ld_t, int rep_row, void* hprev,
+                         int64_t hp_ld_b, int64_t hp_ld_t, void* rec, void* stream);
+int las_lstm_persist_bwd(const float* dy, int64_t dy_ld_b, int64_t dy_ld_t, int rep_row,
+                         const void* whhT_owner_pk, const int32_t* lens, int B, int T, int H, int ndir,
+                         const void* rec, void* dG, int64_t dg_ld_b, int64_t dg_ld_t, void* stream);
 /* switch between the cluster-persistent and the per-timestep kernels (returns the previous setting;
  * default on, or off with LAS_DISABLE_PERSISTENT=1 in the environment) */
 int las_set_persistent(int on);

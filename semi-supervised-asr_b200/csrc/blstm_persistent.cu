@@ -27,13 +27,28 @@ namespace las {
 namespace {
 
 constexpr int kMaxUGC = 5;   // unit groups (8 hidden units) per CTA
-constexpr int kMaxKTW = 10;  // k-tiles (16) per warp in the forward kernel
+constexpr int kMaxKTW = 10;  // k-tiles (16) per warp in the backward kernel (= 2 * kMaxUGC)
+constexpr int kMaxKT = 20;   // k-tiles (16) of the forward kernel: the whole hidden size
 constexpr int kNB = 8;       // utterances per cluster (one MMA n-tile)
 constexpr int kPF = 8;       // timesteps of global-memory prefetch distance (cp.async ring in shared memory)
 
 struct Geom {
   int UG, CS, UGC, KT, KS, KTW, JT, MTW;
 };
+
+// forward kernel: Q quads of 4 hidden units, WPC quads (= warps) per CTA, CS CTAs per cluster
+struct FGeom {
+  int Q, CS, WPC, KT;
+};
+bool fgeom_for(int H, FGeom& g) {
+  if (H % 8 != 0 || H < 8) return false;
+  g.Q = H / 4;
+  const int cs0 = g.Q < 8 ? g.Q : 8;
+  g.WPC = (g.Q + cs0 - 1) / cs0;
+  g.CS = (g.Q + g.WPC - 1) / g.WPC;
+  g.KT = (H + 15) / 16;
+  return g.WPC <= 10 && g.KT <= kMaxKT;
+}
 
 bool geom_for(int H, Geom& g) {
   if (H % 8 != 0 || H < 8 || H > 8 * 8 * kMaxUGC) return false;
@@ -58,6 +73,10 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void st_async_b32(uint32_t addr, uint32_t v, uint32_t mbar) {
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
                ::"r"(addr), "r"(v), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void st_async_v4(uint32_t addr, uint4 v, uint32_t mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+               ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(mbar) : "memory");
 }
 __device__ __forceinline__ void st_async_v2(uint32_t addr, uint32_t v0, uint32_t v1, uint32_t mbar) {
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];"
@@ -105,32 +124,37 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
 }
 
 struct FwdP {
-  const float* xproj; int64_t xp_ld_b, xp_ld_t;
-  const uint32_t* whh_pk;      // [ndir][2*UG][KT][32][4]
+  const float* xproj; int64_t xp_ld_b, xp_ld_t;   // gate-minor columns: [dir*4H + 4*u + gate]
+  const uint32_t* whh_pk;      // [ndir][Q][KT][32][4] (las_pack_afrag mode 3: tile = 4 units x 4 gates, quad-permuted K)
   const int32_t* lens;
   __nv_bfloat16* y; int64_t y_ld_b, y_ld_t;
   __nv_bfloat16* hprev; int64_t hp_ld_b, hp_ld_t;
-  __half* gates_save; float* c_save;
+  uint4* rec;                  // [ndir][B][T][H] x 16 B: (i,f) f16x2 | (g,o) f16x2 | c f32 | tanh(c) f32
   int B, T, H, rep_row;
-  int UG, UGC, KS, KTW, KT;
+  int Q, WPC, KT;
   long long* dbg;              // optional clock64() trace of cluster (0,0,0) (las_set_debug_buffer)
 };
 
-// grid (CS, ceil(B/8), ndir), cluster (CS,1,1), block 32*UGC*KS. warp = ks*UGC + ugl.
+// grid (CS, ceil(B/8), ndir), cluster (CS,1,1), block 32*WPC. Warp w of CTA `rank` owns the 4 hidden units of
+// quad rank*WPC + w: its m16 tile holds their 16 gate rows, K = all of H, so a warp needs no partial-sum
+// exchange with other warps and the step loop contains no block-wide barrier: warps are paced only by the
+// mbarrier that counts the bytes of h_t arriving from the cluster.
 __global__ void __launch_bounds__(320, 1) lstm_persist_fwd_kernel(FwdP p) {
   extern __shared__ __align__(16) uint8_t smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);                    // [2]
-  uint32_t* hs = reinterpret_cast<uint32_t*>(smem + 16);                 // [2][KT][32][2]
-  float* red = reinterpret_cast<float*>(smem + 16 + 2 * p.KT * 256);     // [UGC][32][8]
-  float* xring = red + p.UGC * 32 * 8;                                   // [kPF][UGC][32][8]
+  // h_t as B fragments, [2][KT][4 quads][8 utterances][2 words]: the K positions of a k-tile are permuted so that
+  // quad q's four units are exactly the (b0, b1) words of the lanes with tig == q. A warp's output (4 units x 8
+  // utterances) is then one contiguous 64-byte run, pushed to each peer as 16-byte st.async vectors. The utterance
+  // index of quads 2, 3 is XORed with 4 so that a half-warp's 8-byte fragment loads hit 32 distinct banks.
+  uint32_t* hs = reinterpret_cast<uint32_t*>(smem + 16);
+  float4* xring = reinterpret_cast<float4*>(smem + 16 + 2 * p.KT * 256); // [kPF][threads]
   cg::cluster_group cluster = cg::this_cluster();
   const uint32_t rank = cluster.block_rank(), CS = cluster.num_blocks();
   const int grp = blockIdx.y, dir = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tig = lane & 3;
-  const int ugl = warp % p.UGC, ks = warp / p.UGC;
-  const int ug = rank * p.UGC + ugl;
-  const bool ug_ok = ug < p.UG;
-  const uint32_t tx_bytes = static_cast<uint32_t>(p.UG) * 128u;
+  const int quad = rank * p.WPC + warp;
+  const bool quad_ok = quad < p.Q;
+  const uint32_t tx_bytes = static_cast<uint32_t>(p.H) * 16u;
   const int T = p.T, H = p.H;
 
   if (threadIdx.x == 0) {
@@ -146,208 +170,152 @@ __global__ void __launch_bounds__(320, 1) lstm_persist_fwd_kernel(FwdP p) {
   }
   cluster.sync();   // every CTA's barriers are armed before any remote store can arrive
 
-  // resident recurrent weights: A fragments of this warp's unit group and k-range
-  uint4 A[2][kMaxKTW];
-  {
-    const int64_t a_dir = static_cast<int64_t>(2) * p.UG * p.KT * 128;
+  if (quad_ok) {
+    // resident recurrent weights: A fragments of this warp's quad over the whole K range
+    uint4 A[kMaxKT];
+    {
+      const uint4* src = reinterpret_cast<const uint4*>(p.whh_pk) +
+                         (static_cast<int64_t>(dir) * p.Q + quad) * p.KT * 32 + lane;
 #pragma unroll
-    for (int half = 0; half < 2; ++half)
-#pragma unroll
-      for (int j = 0; j < kMaxKTW; ++j) {
-        const int kt = ks * p.KTW + j;
-        if (ug_ok && j < p.KTW && kt < p.KT)
-          A[half][j] = __ldg(reinterpret_cast<const uint4*>(p.whh_pk + dir * a_dir) +
-                             (static_cast<int64_t>(2 * ug + half) * p.KT + kt) * 32 + lane);
-        else
-          A[half][j] = make_uint4(0u, 0u, 0u, 0u);
-      }
-  }
-
-  // per-lane recurrent state (epilogue warps): unit u, utterances n[0], n[1]
-  const int u = 8 * ug + g;
-  const bool epi = (ks == 0) && ug_ok;
-  int n[2], len[2];
-  float c_st[2] = {0.f, 0.f};
-  __nv_bfloat16 h_st[2];
-#pragma unroll
-  for (int e = 0; e < 2; ++e) {
-    n[e] = grp * kNB + 2 * tig + e;
-    len[e] = (epi && n[e] < p.B) ? (p.lens ? p.lens[n[e]] : T) : 0;
-    h_st[e] = __float2bfloat16(0.f);
-  }
-  // xproj ring: slot s % kPF holds this lane's 2 x 4 gate pre-activations of step s (thread-private)
-  float* xslot = xring + (static_cast<int64_t>(ugl) * 32 + lane) * 8;
-  const int ring_stride = p.UGC * 32 * 8;
-  // running source pointers of the prefetch (no 64-bit index arithmetic inside the step loop)
-  const int64_t xstep = (dir == 0) ? p.xp_ld_t : -p.xp_ld_t;
-  const float* xsrc[2];
-#pragma unroll
-  for (int e = 0; e < 2; ++e)
-    xsrc[e] = p.xproj + n[e] * p.xp_ld_b + static_cast<int64_t>(dir == 0 ? 0 : T - 1) * p.xp_ld_t +
-              static_cast<int64_t>(dir) * 4 * H + u;
-  int pf_s = 0;   // next step to prefetch
-  auto prefetch_xp = [&]() {
-    if (epi && pf_s < T) {
-      const int t = (dir == 0) ? pf_s : (T - 1 - pf_s);
-      float* dst = xslot + (pf_s % kPF) * ring_stride;
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        if (t < len[e]) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) cp_async<4>(dst + e * 4 + k, xsrc[e] + k * H);
-        }
-        xsrc[e] += xstep;
-      }
+      for (int kt = 0; kt < kMaxKT; ++kt) A[kt] = kt < p.KT ? __ldg(src + kt * 32) : make_uint4(0u, 0u, 0u, 0u);
     }
-    ++pf_s;
-    cp_async_commit();
-  };
-  for (int i = 0; i < kPF; ++i) prefetch_xp();
+    // element owned by this lane after the in-warp gate exchange: unit u, utterance n
+    const int gl = g >> 2, ul = g & 3;
+    const int u = 4 * quad + ul;
+    const int n_loc = 2 * tig + gl;
+    const int n = grp * kNB + n_loc;
+    const int len = n < p.B ? (p.lens ? p.lens[n] : T) : 0;
+    float c_st = 0.f;
+    uint32_t h_bits = 0u;
+    uint2 quad_prev = make_uint2(0u, 0u);
 
-  // running global offsets of this lane's two elements (start at the first processed timestep)
-  const int t0 = (dir == 0) ? 0 : T - 1;
-  const int64_t sv_step = (dir == 0) ? H : -H;
-  const int64_t y_step = (dir == 0) ? p.y_ld_t : -p.y_ld_t;
-  const int64_t hp_step = (dir == 0) ? p.hp_ld_t : -p.hp_ld_t;
-  int64_t sv_off[2], y_off[2], hp_off[2];
-#pragma unroll
-  for (int e = 0; e < 2; ++e) {
-    sv_off[e] = ((static_cast<int64_t>(dir) * p.B + n[e]) * T + t0) * H + u;
-    y_off[e] = n[e] * p.y_ld_b + t0 * p.y_ld_t + static_cast<int64_t>(dir) * H + u;
-    hp_off[e] = n[e] * p.hp_ld_b + t0 * p.hp_ld_t + static_cast<int64_t>(dir) * H + u;
-  }
-  // cluster-mapped destinations of this lane's B-fragment word and of the peers' barriers
-  // (buffer 0; buffer 1 lies hs_buf_bytes / 8 bytes further inside the same CTA window)
-  uint32_t hs_remote[8], bar_remote[8];
-  const uint32_t hs_buf_bytes = static_cast<uint32_t>(p.KT) * 256u;
-#pragma unroll
-  for (int peer = 0; peer < 8; ++peer) {
-    const uint32_t pr = peer < static_cast<int>(CS) ? peer : 0;
-    hs_remote[peer] = mapa_u32(smem_u32(hs + (((ug >> 1)) * 32 + lane) * 2 + (ug & 1)), pr);
-    bar_remote[peer] = mapa_u32(smem_u32(&full[0]), pr);
-  }
+    // xproj ring: slot s % kPF holds this lane's 4 gate pre-activations of step s (thread-private, one 16-byte copy)
+    float4* xslot = xring + threadIdx.x;
+    const int ring_stride = blockDim.x;
+    const int64_t xstep = (dir == 0) ? p.xp_ld_t : -p.xp_ld_t;
+    const float* xsrc = p.xproj + n * p.xp_ld_b + static_cast<int64_t>(dir == 0 ? 0 : T - 1) * p.xp_ld_t +
+                        static_cast<int64_t>(dir) * 4 * H + 4 * u;
+    int pf_s = 0;   // next step to prefetch
+    auto prefetch_xp = [&]() {
+      if (pf_s < T) {
+        const int t = (dir == 0) ? pf_s : (T - 1 - pf_s);
+        if (t < len) cp_async<16>(xslot + (pf_s % kPF) * ring_stride, xsrc);
+        xsrc += xstep;
+      }
+      ++pf_s;
+      cp_async_commit();
+    };
+    for (int i = 0; i < kPF; ++i) prefetch_xp();
 
-  const bool trace = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0;
+    // running global pointers (start at the first processed timestep)
+    const int t0 = (dir == 0) ? 0 : T - 1;
+    const int64_t rec_step = (dir == 0) ? H : -H;
+    const int64_t y_step = (dir == 0) ? p.y_ld_t : -p.y_ld_t;
+    const int64_t hp_step = (dir == 0) ? p.hp_ld_t : -p.hp_ld_t;
+    uint4* rec_run = p.rec + ((static_cast<int64_t>(dir) * p.B + n) * T + t0) * H + u;
+    // the layer output and the entering state are written as 8-byte words (the quad's 4 units of one utterance):
+    // lane ul == 0 writes y, lane ul == 1 writes hprev
+    __nv_bfloat16* y_run = p.y + n * p.y_ld_b + t0 * p.y_ld_t + static_cast<int64_t>(dir) * H + 4 * quad;
+    __nv_bfloat16* hp_run = p.hprev ? p.hprev + n * p.hp_ld_b + t0 * p.hp_ld_t + static_cast<int64_t>(dir) * H + 4 * quad : nullptr;
+    // after the in-warp gather the 8 lanes sharing `tig` hold the same 16 bytes (utterances 2tig, 2tig+1 of the
+    // quad); lane g pushes them to peer g. Cluster-mapped destination (buffer 0; buffer 1 lies hs_buf_bytes
+    // further) and the peer's barrier:
+    const uint32_t hs_buf_bytes = static_cast<uint32_t>(p.KT) * 256u;
+    const bool peer_ok = static_cast<uint32_t>(g) < CS;
+    const uint32_t hs_remote = mapa_u32(smem_u32(hs + (quad * 8 + ((2 * tig) ^ (((quad & 3) >> 1) << 2))) * 2), peer_ok ? g : 0);
+    const uint32_t bar_remote = mapa_u32(smem_u32(&full[0]), peer_ok ? g : 0);
+
+    const bool trace = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0;
 #define LAS_TRACE(slot) do { if (trace && s >= 64 && s < 72) p.dbg[(s - 64) * 8 + (slot)] = clock64(); } while (0)
-  for (int s = 0; s < T; ++s) {
-    const int t = (dir == 0) ? s : (T - 1 - s);
-    LAS_TRACE(0);
-
-    float acc[2][2][4];
+    for (int s = 0; s < T; ++s) {
+      const int t = (dir == 0) ? s : (T - 1 - s);
+      LAS_TRACE(0);
+      float acc[4][4];
 #pragma unroll
-    for (int a = 0; a < 2; ++a)
+      for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int b = 0; b < 2; ++b)
+        for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
+      if (s > 0) {
+        const int buf = s & 1;
+        mbar_wait_cluster(&full[buf], ((s - 1) >> 1) & 1);
+        LAS_TRACE(1);
+        if (threadIdx.x == 0 && s + 2 < T) mbar_arrive_expect_tx(&full[buf], tx_bytes);  // re-arm for step s+2
+        const uint2* hb = reinterpret_cast<const uint2*>(hs + buf * p.KT * 64) + tig * 8 + (g ^ ((tig >> 1) << 2));
 #pragma unroll
-        for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
-
-    if (s > 0) {
-      const int buf = s & 1;
-      mbar_wait_cluster(&full[buf], ((s - 1) >> 1) & 1);
-      LAS_TRACE(1);
-      if (threadIdx.x == 0 && s + 2 < T) mbar_arrive_expect_tx(&full[buf], tx_bytes);  // re-arm for step s+2
-      const uint2* hb = reinterpret_cast<const uint2*>(hs + buf * p.KT * 64) + lane;
-#pragma unroll
-      for (int j = 0; j < kMaxKTW; ++j) {
-        const int kt = ks * p.KTW + j;
-        if (j < p.KTW && kt < p.KT) {
-          const uint2 b = hb[kt * 32];
-          const uint32_t A0[4] = {A[0][j].x, A[0][j].y, A[0][j].z, A[0][j].w};
-          const uint32_t A1[4] = {A[1][j].x, A[1][j].y, A[1][j].z, A[1][j].w};
-          mma_bf16_16816(acc[0][j & 1], A0, b.x, b.y);
-          mma_bf16_16816(acc[1][j & 1], A1, b.x, b.y);
-        }
-      }
-    }
-    float gsum[2][4];
-#pragma unroll
-    for (int a = 0; a < 2; ++a)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) gsum[a][c] = acc[a][0][c] + acc[a][1][c];
-    LAS_TRACE(2);
-    if (p.KS == 2) {
-      float* r = red + (ugl * 32 + lane) * 8;
-      if (ks == 1) {
-#pragma unroll
-        for (int a = 0; a < 2; ++a)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) r[a * 4 + c] = gsum[a][c];
-      }
-      __syncthreads();
-      if (ks == 0) {
-#pragma unroll
-        for (int a = 0; a < 2; ++a)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) gsum[a][c] += r[a * 4 + c];
-      }
-    }
-    LAS_TRACE(3);
-    cp_async_wait<kPF - 1>();   // this step's xproj values have landed in the ring
-    LAS_TRACE(4);
-    if (epi) {
-      const float* xs = xslot + (s % kPF) * ring_stride;
-      float xp[2][4];
-#pragma unroll
-      for (int e = 0; e < 2; ++e)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) xp[e][k] = xs[e * 4 + k];
-      float sv_i[2], sv_f[2], sv_g[2], sv_o[2];
-      __nv_bfloat16 h_old[2];
-      bool act[2];
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        act[e] = t < len[e];
-        h_old[e] = h_st[e];
-        if (act[e]) {
-          const float gi = gsum[0][e] + xp[e][0];
-          const float gf = gsum[0][2 + e] + xp[e][1];
-          const float gg = gsum[1][e] + xp[e][2];
-          const float go = gsum[1][2 + e] + xp[e][3];
-          const float i = sigmoid_acc(gi), f = sigmoid_acc(gf), gc = tanh_acc(gg), o = sigmoid_acc(go);
-          const float c = f * c_st[e] + i * gc;
-          const float h = o * tanh_acc(c);
-          c_st[e] = c;
-          h_st[e] = __float2bfloat16(h);
-          sv_i[e] = i; sv_f[e] = f; sv_g[e] = gc; sv_o[e] = o;
-        }
-      }
-      LAS_TRACE(5);
-      // critical path first: the new state goes to the peers before anything is written to HBM
-      if (s + 1 < T) {
-        // lane (unit g, utterances 2tig, 2tig+1) -> after the 8x8 transpose: (utterance g, units 2tig, 2tig+1)
-        __nv_bfloat162 hv;
-        hv.x = h_st[0];
-        hv.y = h_st[1];
-        const uint32_t w = movmatrix_trans(*reinterpret_cast<uint32_t*>(&hv));
-        const int nbuf = (s + 1) & 1;
-#pragma unroll
-        for (int peer = 0; peer < 8; ++peer)
-          if (peer < static_cast<int>(CS)) st_async_b32(hs_remote[peer] + nbuf * hs_buf_bytes, w, bar_remote[peer] + nbuf * 8u);
-      }
-      // saved activations (BPTT operands) and the layer output
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        if (act[e]) {
-          if (p.gates_save) {
-            __half2 lo = __floats2half2_rn(sv_i[e], sv_f[e]), hi = __floats2half2_rn(sv_g[e], sv_o[e]);
-            uint2 pk;
-            pk.x = *reinterpret_cast<uint32_t*>(&lo);
-            pk.y = *reinterpret_cast<uint32_t*>(&hi);
-            reinterpret_cast<uint2*>(p.gates_save)[sv_off[e]] = pk;
+        for (int kt = 0; kt < kMaxKT; ++kt) {
+          if (kt < p.KT) {
+            const uint2 b = hb[kt * 32];
+            const uint32_t Af[4] = {A[kt].x, A[kt].y, A[kt].z, A[kt].w};
+            mma_bf16_16816(acc[kt & 3], Af, b.x, b.y);
           }
-          if (p.c_save) p.c_save[sv_off[e]] = c_st[e];
-          p.y[y_off[e]] = h_st[e];
-          if (p.rep_row && t == T - 1) p.y[y_off[e] + p.y_ld_t] = h_st[e];
         }
-        if (n[e] < p.B && p.hprev) p.hprev[hp_off[e]] = h_old[e];
-        sv_off[e] += sv_step; y_off[e] += y_step; hp_off[e] += hp_step;
       }
+      LAS_TRACE(2);
+      // C fragment: c0/c1 = row g (gate gl of unit ul), c2/c3 = row g+8 (gate 2+gl), utterances 2tig / 2tig+1.
+      // Lanes g and g^4 trade halves so that each ends up with all four gates of (unit ul, utterance 2tig+gl).
+      float cf[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) cf[c] = (acc[0][c] + acc[1][c]) + (acc[2][c] + acc[3][c]);
+      const float r0 = __shfl_xor_sync(0xffffffffu, gl ? cf[0] : cf[1], 16);
+      const float r1 = __shfl_xor_sync(0xffffffffu, gl ? cf[2] : cf[3], 16);
+      cp_async_wait<kPF - 1>();   // this step's xproj values have landed in the ring
+      const bool act = t < len;
+      float sv_i = 0.f, sv_f = 0.f, sv_g = 0.f, sv_o = 0.f, tc = 0.f;
+      if (act) {
+        const float4 xp = xslot[(s % kPF) * ring_stride];
+        const float gi = (gl ? r0 : cf[0]) + xp.x;
+        const float gf = (gl ? cf[1] : r0) + xp.y;
+        const float gg = (gl ? r1 : cf[2]) + xp.z;
+        const float go = (gl ? cf[3] : r1) + xp.w;
+        sv_i = sigmoid_acc(gi); sv_f = sigmoid_acc(gf); sv_g = tanh_acc(gg); sv_o = sigmoid_acc(go);
+        c_st = sv_f * c_st + sv_i * sv_g;
+        tc = tanh_acc(c_st);
+        const __nv_bfloat16 hb16 = __float2bfloat16(sv_o * tc);
+        h_bits = static_cast<uint32_t>(*reinterpret_cast<const unsigned short*>(&hb16));
+      }
+      LAS_TRACE(3);
+      // gather: (units 0,1 | 2,3) words of this lane's utterance, then the neighbour utterance's
+      const uint32_t other = __shfl_xor_sync(0xffffffffu, h_bits, 4);
+      const uint32_t wp = (ul & 1) ? (other | (h_bits << 16)) : (h_bits | (other << 16));
+      const uint32_t wo = __shfl_xor_sync(0xffffffffu, wp, 8);
+      const uint2 qw = (ul & 2) ? make_uint2(wo, wp) : make_uint2(wp, wo);
+      const uint32_t x0 = __shfl_xor_sync(0xffffffffu, qw.x, 16);
+      const uint32_t x1 = __shfl_xor_sync(0xffffffffu, qw.y, 16);
+      // critical path first: the new state goes to the peers before anything is written to HBM
+      if (s + 1 < T && peer_ok) {
+        const int nbuf = (s + 1) & 1;
+        const uint4 v = gl ? make_uint4(x0, x1, qw.x, qw.y) : make_uint4(qw.x, qw.y, x0, x1);
+        st_async_v4(hs_remote + nbuf * hs_buf_bytes, v, bar_remote + nbuf * 8u);
+      }
+      LAS_TRACE(4);
+      // saved activations (BPTT operands) and the layer output
+      if (act) {
+        const __half2 lo = __floats2half2_rn(sv_i, sv_f), hi = __floats2half2_rn(sv_g, sv_o);
+        uint4 r;
+        r.x = *reinterpret_cast<const uint32_t*>(&lo);
+        r.y = *reinterpret_cast<const uint32_t*>(&hi);
+        r.z = __float_as_uint(c_st);
+        r.w = __float_as_uint(tc);
+        *rec_run = r;
+      }
+      if (ul == 0) {
+        if (act) {
+          *reinterpret_cast<uint2*>(y_run) = qw;
+          if (p.rep_row && t == T - 1) *reinterpret_cast<uint2*>(y_run + p.y_ld_t) = qw;
+        }
+      } else if (ul == 1 && hp_run && n < p.B) {
+        *reinterpret_cast<uint2*>(hp_run) = quad_prev;
+      }
+      quad_prev = qw;
+      rec_run += rec_step; y_run += y_step;
+      if (hp_run) hp_run += hp_step;
+      LAS_TRACE(5);
+      prefetch_xp();   // refill this ring slot (step s + kPF): DRAM latency hidden behind kPF timesteps
+      LAS_TRACE(6);
+      LAS_TRACE(7);
     }
-    LAS_TRACE(6);
-    prefetch_xp();   // refill this ring slot (step s + kPF): DRAM latency hidden behind kPF timesteps
-    LAS_TRACE(7);
-  }
 #undef LAS_TRACE
+  }
   cluster.sync();   // nobody exits while remote stores may still target its shared memory
 }
 
@@ -355,8 +323,9 @@ struct BwdP {
   const float* dy; int64_t dy_ld_b, dy_ld_t;
   const uint32_t* wT_pk;       // owner-ordered W_hh^T fragments [ndir][JT][CS*KTC][32][4]
   const int32_t* lens;
-  const __half* gates_save; const float* c_save;
-  __nv_bfloat16* dG; int64_t dg_ld_b, dg_ld_t;
+  const uint4* rec;            // records written by lstm_persist_fwd_kernel
+  __nv_bfloat16* dG;           // gate-minor columns: [dir*4H + 4*u + gate]
+  int64_t dg_ld_b, dg_ld_t;
   int B, T, H, rep_row;
   int UGC, JT, MTW, CSn;
   long long* dbg;
@@ -418,7 +387,8 @@ __global__ void __launch_bounds__(320, 1) lstm_persist_bwd_kernel(BwdP p) {
   float dc_st = 0.f;
 
   // operands of the gate-derivative math: thread-private cp.async ring, fetched kPF timesteps ahead
-  //   slot layout (8 floats): [0..1] gates (4 x f16), [2] c_t, [3] c_prev, [4] dy, [5] dy of the replicated row
+  //   slot layout (8 floats): [0..3] the forward record (gates 4 x f16, c_t, tanh c_t), [4] dy, [5] dy of the
+  //   replicated row. c_prev is the c_t field of the NEXT processed step's slot (already in flight).
   float* pslot = pring + static_cast<int64_t>(threadIdx.x) * 8;
   const int ring_stride = blockDim.x * 8;
   // running source offsets (first processed timestep: t = T-1 for the forward direction, 0 for the reverse)
@@ -428,16 +398,13 @@ __global__ void __launch_bounds__(320, 1) lstm_persist_bwd_kernel(BwdP p) {
   int64_t sv_run = ((static_cast<int64_t>(dir) * p.B + nb) * T + tb0) * H + uo;
   const float* dy_run = p.dy ? p.dy + nb * p.dy_ld_b + tb0 * p.dy_ld_t + static_cast<int64_t>(dir) * H + uo : nullptr;
   const int64_t dg_step = (dir == 0) ? -p.dg_ld_t : p.dg_ld_t;
-  __nv_bfloat16* dg_run = p.dG + nb * p.dg_ld_b + tb0 * p.dg_ld_t + static_cast<int64_t>(dir) * 4 * H + uo;
+  __nv_bfloat16* dg_run = p.dG + nb * p.dg_ld_b + tb0 * p.dg_ld_t + static_cast<int64_t>(dir) * 4 * H + 4 * uo;
   int pf_s = 0;
   auto prefetch = [&]() {
     const int t = (dir == 0) ? (T - 1 - pf_s) : pf_s;
     if (pf_s < T && t < len) {
       float* dst = pslot + (pf_s % kPF) * ring_stride;
-      cp_async<8>(dst, reinterpret_cast<const uint2*>(p.gates_save) + sv_run);
-      cp_async<4>(dst + 2, p.c_save + sv_run);
-      if (dir == 0) { if (t > 0) cp_async<4>(dst + 3, p.c_save + sv_run - H); }
-      else          { if (t + 1 < len) cp_async<4>(dst + 3, p.c_save + sv_run + H); }
+      cp_async<16>(dst, p.rec + sv_run);
       if (dy_run) {
         cp_async<4>(dst + 4, dy_run);
         if (p.rep_row && t == T - 1) cp_async<4>(dst + 5, dy_run + p.dy_ld_t);
@@ -451,21 +418,22 @@ __global__ void __launch_bounds__(320, 1) lstm_persist_bwd_kernel(BwdP p) {
   for (int i = 0; i < kPF; ++i) prefetch();
 
   // reduce-scatter destinations of this lane's partial sums (buffer 0; buffer 1 is part_buf_bytes further)
-  uint32_t sc_dst[2][2], sc_bar[2][2];
-  bool sc_ok[2][2];
+  // Lanes tig and tig^1 trade halves of their C fragments so that each holds 4 consecutive utterances of ONE unit
+  // (even tig: row g, odd tig: row g+8) and sends them as one 16-byte st.async.
+  uint32_t sc_dst[2], sc_bar[2];
+  bool sc_ok[2];
   const uint32_t part_buf_bytes = static_cast<uint32_t>(p.CSn) * UPC * 8 * 4;
+  const int hh_own = tig & 1;
 #pragma unroll
-  for (int m = 0; m < 2; ++m)
-#pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
-      const int mt = warp * p.MTW + m;
-      const int j = 16 * mt + g + 8 * hh;
-      sc_ok[m][hh] = m < p.MTW && mt < p.JT && j < H;
-      const uint32_t owner = sc_ok[m][hh] ? j / UPC : 0;
-      const int jl = sc_ok[m][hh] ? j - owner * UPC : 0;
-      sc_dst[m][hh] = mapa_u32(smem_u32(part + static_cast<int64_t>(rank) * UPC * 8 + jl * 8 + 2 * tig), owner);
-      sc_bar[m][hh] = mapa_u32(smem_u32(&pfull[0]), owner);
-    }
+  for (int m = 0; m < 2; ++m) {
+    const int mt = warp * p.MTW + m;
+    const int j = 16 * mt + g + 8 * hh_own;
+    sc_ok[m] = m < p.MTW && mt < p.JT && j < H;
+    const uint32_t owner = sc_ok[m] ? j / UPC : 0;
+    const int jl = sc_ok[m] ? j - owner * UPC : 0;
+    sc_dst[m] = mapa_u32(smem_u32(part + static_cast<int64_t>(rank) * UPC * 8 + jl * 8 + 2 * (tig & ~1)), owner);
+    sc_bar[m] = mapa_u32(smem_u32(&pfull[0]), owner);
+  }
 
   const bool trace = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0;
 #define LAS_TRACE(slot) do { if (trace && s >= 64 && s < 72) p.dbg[64 + (s - 64) * 8 + (slot)] = clock64(); } while (0)
@@ -499,15 +467,19 @@ __global__ void __launch_bounds__(320, 1) lstm_persist_bwd_kernel(BwdP p) {
       LAS_TRACE(1);
       // scatter the partial sums to the CTAs that own the units
 #pragma unroll
-      for (int m = 0; m < 2; ++m)
+      for (int m = 0; m < 2; ++m) {
+        float v[4];
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh)
-          if (sc_ok[m][hh]) {
-            const float v0 = acc[m][0][2 * hh] + acc[m][1][2 * hh];
-            const float v1 = acc[m][0][2 * hh + 1] + acc[m][1][2 * hh + 1];
-            st_async_v2(sc_dst[m][hh] + buf * part_buf_bytes, __float_as_uint(v0), __float_as_uint(v1),
-                        sc_bar[m][hh] + buf * 8u);
-          }
+        for (int c = 0; c < 4; ++c) v[c] = acc[m][0][c] + acc[m][1][c];
+        // give away the row this lane does not send (even tig keeps row g = v[0..1], odd tig keeps row g+8 = v[2..3])
+        const float r0 = __shfl_xor_sync(0xffffffffu, hh_own ? v[0] : v[2], 1);
+        const float r1 = __shfl_xor_sync(0xffffffffu, hh_own ? v[1] : v[3], 1);
+        if (sc_ok[m]) {
+          const uint4 q = hh_own ? make_uint4(__float_as_uint(r0), __float_as_uint(r1), __float_as_uint(v[2]), __float_as_uint(v[3]))
+                                 : make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(r0), __float_as_uint(r1));
+          st_async_v4(sc_dst[m] + buf * part_buf_bytes, q, sc_bar[m] + buf * 8u);
+        }
+      }
       LAS_TRACE(2);
       mbar_wait_cluster(&pfull[buf], ((s - 1) >> 1) & 1);
       LAS_TRACE(3);
@@ -518,14 +490,16 @@ __global__ void __launch_bounds__(320, 1) lstm_persist_bwd_kernel(BwdP p) {
     // gate derivatives (same math as cell_bwd_kernel)
     float d4[4] = {0.f, 0.f, 0.f, 0.f};
     LAS_TRACE(4);
-    cp_async_wait<kPF - 1>();
+    cp_async_wait<kPF - 2>();   // this step's and the next step's operands have landed
     if (active) {
       const float* q = pslot + (s % kPF) * ring_stride;
-      const uint2 gpk = *reinterpret_cast<const uint2*>(q);
-      const float c_cur = q[2];
+      const float4 rc = *reinterpret_cast<const float4*>(q);
+      const uint2 gpk = make_uint2(__float_as_uint(rc.x), __float_as_uint(rc.y));
+      const float tc = rc.w;
       float c_prev = 0.f;
-      if (dir == 0) { if (t > 0) c_prev = q[3]; }
-      else          { if (t + 1 < len) c_prev = q[3]; }
+      const float* qn = pslot + ((s + 1) % kPF) * ring_stride;
+      if (dir == 0) { if (t > 0) c_prev = qn[2]; }
+      else          { if (t + 1 < len) c_prev = qn[2]; }
       if (p.dy) {
         dh += q[4];
         if (p.rep_row && t == T - 1) dh += q[5];
@@ -533,7 +507,6 @@ __global__ void __launch_bounds__(320, 1) lstm_persist_bwd_kernel(BwdP p) {
       const float2 if_ = __half22float2(*reinterpret_cast<const __half2*>(&gpk.x));
       const float2 go_ = __half22float2(*reinterpret_cast<const __half2*>(&gpk.y));
       const float i = if_.x, f = if_.y, gc = go_.x, o = go_.y;
-      const float tc = tanh_acc(c_cur);
       const float dc = dh * o * (1.f - tc * tc) + dc_st;
       dc_st = dc * f;
       d4[0] = dc * gc * i * (1.f - i);
@@ -542,8 +515,10 @@ __global__ void __launch_bounds__(320, 1) lstm_persist_bwd_kernel(BwdP p) {
       d4[3] = dh * tc * o * (1.f - o);
     }
     if (own) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) dg_run[q * H] = __float2bfloat16(d4[q]);
+      uint2 pk;
+      pk.x = pack_bf16x2(d4[0], d4[1]);
+      pk.y = pack_bf16x2(d4[2], d4[3]);
+      *reinterpret_cast<uint2*>(dg_run) = pk;
     }
     dg_run += dg_step;
     if (s + 1 < T && uo < H) {
@@ -635,36 +610,46 @@ void* g_dbg_buf_shared = nullptr;
 
 int persist_supported(int H) {
   Geom g;
-  return persist_enabled() && geom_for(H, g) ? 1 : 0;
+  FGeom f;
+  return persist_enabled() && geom_for(H, g) && fgeom_for(H, f) ? 1 : 0;
 }
 
 int persist_lstm_fwd(const float* xproj, const void* whh_pk, const int32_t* lens, int B, int T, int H, int ndir,
                      void* y, int64_t y_ld_b, int64_t y_ld_t, int rep_row, void* hprev, int64_t hp_ld_b,
-                     int64_t hp_ld_t, void* gates_save, float* c_save, cudaStream_t stream) {
-  Geom g;
-  LAS_REQUIRE(geom_for(H, g), "persistent LSTM: hidden size %d unsupported", H);
+                     int64_t hp_ld_t, void* rec, cudaStream_t stream) {
+  FGeom g;
+  LAS_REQUIRE(fgeom_for(H, g), "persistent LSTM: hidden size %d unsupported", H);
+  LAS_REQUIRE(y_ld_b % 4 == 0 && y_ld_t % 4 == 0 && hp_ld_b % 4 == 0 && hp_ld_t % 4 == 0 &&
+                  reinterpret_cast<uintptr_t>(y) % 8 == 0 && reinterpret_cast<uintptr_t>(hprev) % 8 == 0,
+              "persistent LSTM: y / hprev must be 8-byte aligned with strides that are multiples of 4");
+  LAS_REQUIRE(reinterpret_cast<uintptr_t>(xproj) % 16 == 0 && reinterpret_cast<uintptr_t>(rec) % 16 == 0,
+              "persistent LSTM: xproj / rec must be 16-byte aligned");
   FwdP p;
   p.xproj = xproj; p.xp_ld_t = static_cast<int64_t>(ndir) * 4 * H; p.xp_ld_b = p.xp_ld_t * T;
   p.whh_pk = static_cast<const uint32_t*>(whh_pk); p.lens = lens;
   p.y = static_cast<__nv_bfloat16*>(y); p.y_ld_b = y_ld_b; p.y_ld_t = y_ld_t;
   p.hprev = static_cast<__nv_bfloat16*>(hprev); p.hp_ld_b = hp_ld_b; p.hp_ld_t = hp_ld_t;
-  p.gates_save = static_cast<__half*>(gates_save); p.c_save = c_save;
+  p.rec = static_cast<uint4*>(rec);
   p.B = B; p.T = T; p.H = H; p.rep_row = rep_row;
-  p.UG = g.UG; p.UGC = g.UGC; p.KS = g.KS; p.KTW = g.KTW; p.KT = g.KT;
+  p.Q = g.Q; p.WPC = g.WPC; p.KT = g.KT;
   p.dbg = static_cast<long long*>(g_dbg_buf);
-  const size_t smem = 16 + static_cast<size_t>(2) * g.KT * 256 + static_cast<size_t>(1 + kPF) * g.UGC * 32 * 8 * 4;
-  return launch_cluster(lstm_persist_fwd_kernel, p, g.CS, (B + kNB - 1) / kNB, ndir, 32 * g.UGC * g.KS, smem, stream);
+  const int threads = 32 * g.WPC;
+  const size_t smem = 16 + static_cast<size_t>(2) * g.KT * 256 + static_cast<size_t>(kPF) * threads * 16;
+  return launch_cluster(lstm_persist_fwd_kernel, p, g.CS, (B + kNB - 1) / kNB, ndir, threads, smem, stream);
 }
 
 int persist_lstm_bwd(const float* dy, int64_t dy_ld_b, int64_t dy_ld_t, int rep_row, const void* wT_owner_pk,
-                     const int32_t* lens, int B, int T, int H, int ndir, const void* gates_save,
-                     const float* c_save, void* dG, int64_t dg_ld_b, int64_t dg_ld_t, cudaStream_t stream) {
+                     const int32_t* lens, int B, int T, int H, int ndir, const void* rec, void* dG, int64_t dg_ld_b,
+                     int64_t dg_ld_t, cudaStream_t stream) {
   Geom g;
   LAS_REQUIRE(geom_for(H, g), "persistent LSTM: hidden size %d unsupported", H);
+  LAS_REQUIRE(dg_ld_b % 4 == 0 && dg_ld_t % 4 == 0 && reinterpret_cast<uintptr_t>(dG) % 8 == 0 &&
+                  reinterpret_cast<uintptr_t>(rec) % 16 == 0,
+              "persistent LSTM: dG must be 8-byte aligned with strides that are multiples of 4, rec 16-byte aligned");
   BwdP p;
   p.dy = dy; p.dy_ld_b = dy_ld_b; p.dy_ld_t = dy_ld_t; p.rep_row = rep_row;
   p.wT_pk = static_cast<const uint32_t*>(wT_owner_pk); p.lens = lens;
-  p.gates_save = static_cast<const __half*>(gates_save); p.c_save = c_save;
+  p.rec = static_cast<const uint4*>(rec);
   p.dG = static_cast<__nv_bfloat16*>(dG); p.dg_ld_b = dg_ld_b; p.dg_ld_t = dg_ld_t;
   p.B = B; p.T = T; p.H = H;
   p.UGC = g.UGC; p.JT = g.JT; p.MTW = g.MTW; p.CSn = g.CS;

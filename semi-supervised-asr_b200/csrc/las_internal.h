@@ -19,10 +19,10 @@ int gemm_bf16(const void* A, int64_t lda, bool a_mn, const void* B, int64_t ldb,
 int persist_supported(int H);
 int persist_lstm_fwd(const float* xproj, const void* whh_pk, const int32_t* lens, int B, int T, int H, int ndir,
                      void* y, int64_t y_ld_b, int64_t y_ld_t, int rep_row, void* hprev, int64_t hp_ld_b,
-                     int64_t hp_ld_t, void* gates_save, float* c_save, cudaStream_t stream);
+                     int64_t hp_ld_t, void* rec, cudaStream_t stream);
 int persist_lstm_bwd(const float* dy, int64_t dy_ld_b, int64_t dy_ld_t, int rep_row, const void* wT_owner_pk,
-                     const int32_t* lens, int B, int T, int H, int ndir, const void* gates_save,
-                     const float* c_save, void* dG, int64_t dg_ld_b, int64_t dg_ld_t, cudaStream_t stream);
+                     const int32_t* lens, int B, int T, int H, int ndir, const void* rec, void* dG,
+                     int64_t dg_ld_b, int64_t dg_ld_t, cudaStream_t stream);
 
 // cluster-persistent attention decoder (decoder_persistent.cu)
 }  // namespace las

@@ -43,11 +43,15 @@ __global__ void pack_afrag_kernel(const float* __restrict__ W, int64_t ld, int r
     const int tile = tk / KT;
     const int g = lane >> 2, tig = lane & 3;
     const int rl = g + 8 * (j & 1);
-    const int c0 = 16 * kt + 2 * tig + 8 * (j >> 1);
+    int c0 = 16 * kt + 2 * tig + 8 * (j >> 1);
     int row;
+    if (mode == 3) {   // mode 2 rows; K positions of each k-tile permuted: quad q = units 4q..4q+3 at {2q, 2q+1, 2q+8, 2q+9}
+      const int p0 = 2 * tig + 8 * (j >> 1);
+      c0 = 16 * kt + 4 * ((p0 & 7) >> 1) + 2 * (p0 >> 3);
+    }
     if (mode == 0) {
       row = 16 * tile + rl;
-    } else if (mode == 2) {
+    } else if (mode == 2 || mode == 3) {
       const int unit = 4 * tile + (rl & 3);
       const int gate = rl >> 2;
       row = (unit < H) ? gate * H + unit : rows;
@@ -399,14 +403,14 @@ extern "C" {
 
 int las_pack_afrag(const float* W, int64_t ld, int rows, int cols, int col_offset, int mode, int H,
                    int transposed, void* out, void* stream) {
-  const int tiles = (mode == 1) ? 2 * ((H + 7) / 8) : (mode == 2) ? (H + 3) / 4 : (rows + 15) / 16;
+  const int tiles = (mode == 1) ? 2 * ((H + 7) / 8) : (mode == 2 || mode == 3) ? (H + 3) / 4 : (rows + 15) / 16;
   const int KT = (cols + 15) / 16;
   return pack_afrag(W, ld, rows, cols, col_offset, mode, H, transposed != 0, tiles, KT,
                     static_cast<uint32_t*>(out), static_cast<cudaStream_t>(stream));
 }
 
 int64_t las_afrag_bytes(int rows, int cols, int mode, int H) {
-  const int64_t tiles = (mode == 1) ? 2 * ((H + 7) / 8) : (mode == 2) ? (H + 3) / 4 : (rows + 15) / 16;
+  const int64_t tiles = (mode == 1) ? 2 * ((H + 7) / 8) : (mode == 2 || mode == 3) ? (H + 3) / 4 : (rows + 15) / 16;
   const int64_t KT = (cols + 15) / 16;
   return tiles * KT * 128 * 4;
 }
@@ -445,9 +449,6 @@ int las_lstm_seq_fwd(const float* xproj, const void* whh_pk, const int32_t* lens
   LAS_REQUIRE(H % 8 == 0, "lstm: hidden size %d must be a multiple of 8", H);
   LAS_REQUIRE(ndir == 1 || ndir == 2, "lstm: ndir must be 1 or 2");
   if (B == 0 || T == 0) return 0;
-  if (persist_supported(H))   // one cluster-persistent launch for the whole sequence (blstm_persistent.cu)
-    return persist_lstm_fwd(xproj, whh_pk, lens, B, T, H, ndir, y, y_ld_b, y_ld_t, rep_row, hprev, hp_ld_b,
-                            hp_ld_t, gates_save, c_save, stream);
   const int KT = (H + 15) / 16;
   const int64_t Kp = KT * 16 + 16;
   CellFwdParams p = {};
@@ -489,11 +490,7 @@ int las_lstm_seq_bwd(const float* dy, int64_t dy_ld_b, int64_t dy_ld_t, int rep_
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   LAS_REQUIRE(H % 8 == 0, "lstm: hidden size %d must be a multiple of 8", H);
   if (B == 0 || T == 0) return 0;
-  if (whhT_layout == 1) {
-    LAS_REQUIRE(persist_supported(H), "lstm bwd: owner-ordered weights given but H=%d has no persistent kernel", H);
-    return persist_lstm_bwd(dy, dy_ld_b, dy_ld_t, rep_row, whhT_pk, lens, B, T, H, ndir, gates_save, c_save, dG,
-                            dg_ld_b, dg_ld_t, stream);
-  }
+  LAS_REQUIRE(whhT_layout == 0, "lstm bwd: owner-ordered weights belong to las_lstm_persist_bwd");
   CellBwdParams p = {};
   p.dy = dy; p.dy_ld_b = dy_ld_b; p.dy_ld_t = dy_ld_t; p.rep_row = rep_row;
   p.dh_extra = nullptr; p.dhx_ld = 0;
@@ -516,6 +513,31 @@ int las_lstm_seq_bwd(const float* dy, int64_t dy_ld_b, int64_t dy_ld_t, int rep_
     p.v_ld_t = dg_ld_t;
     launch_cell_bwd(p, stream);
   }
+  LAS_LAUNCH_CHECK();
+  return 0;
+}
+
+int las_lstm_persist_fwd(const float* xproj, const void* whh_pk, const int32_t* lens, int B, int T, int H,
+                         int ndir, void* y, int64_t y_ld_b, int64_t y_ld_t, int rep_row, void* hprev,
+                         int64_t hp_ld_b, int64_t hp_ld_t, void* rec, void* stream) {
+  LAS_REQUIRE(persist_supported(H), "persistent LSTM: hidden size %d unsupported (or switched off)", H);
+  LAS_REQUIRE(ndir == 1 || ndir == 2, "lstm: ndir must be 1 or 2");
+  if (B == 0 || T == 0) return 0;
+  int rc = persist_lstm_fwd(xproj, whh_pk, lens, B, T, H, ndir, y, y_ld_b, y_ld_t, rep_row, hprev, hp_ld_b, hp_ld_t,
+                            rec, static_cast<cudaStream_t>(stream));
+  if (rc) return rc;
+  LAS_LAUNCH_CHECK();
+  return 0;
+}
+
+int las_lstm_persist_bwd(const float* dy, int64_t dy_ld_b, int64_t dy_ld_t, int rep_row,
+                         const void* whhT_owner_pk, const int32_t* lens, int B, int T, int H, int ndir,
+                         const void* rec, void* dG, int64_t dg_ld_b, int64_t dg_ld_t, void* stream) {
+  LAS_REQUIRE(persist_supported(H), "persistent LSTM: hidden size %d unsupported (or switched off)", H);
+  if (B == 0 || T == 0) return 0;
+  int rc = persist_lstm_bwd(dy, dy_ld_b, dy_ld_t, rep_row, whhT_owner_pk, lens, B, T, H, ndir, rec, dG, dg_ld_b,
+                            dg_ld_t, static_cast<cudaStream_t>(stream));
+  if (rc) return rc;
   LAS_LAUNCH_CHECK();
   return 0;
 }

@@ -146,6 +146,89 @@ def lens_tensor(lens, device):
 
 
 # --------------------------------------------------------------------------------------------
+# one LSTM layer over padded sequences (shared by the listener and the LM)
+# --------------------------------------------------------------------------------------------
+_GATE_PERM = {}
+
+
+def gate_perm(H, ndir, device):
+    """Row permutation between torch's gate-major order [dir][gate][unit] and the gate-minor order
+    [dir][unit][gate] of the cluster-persistent kernels. Returns (perm, inv): X_minor = X_major[perm],
+    X_major = X_minor[inv]."""
+    key = (H, ndir, device)
+    pi = _GATE_PERM.get(key)
+    if pi is None:
+        perm = torch.arange(ndir * 4 * H, device=device).view(ndir, 4, H).permute(0, 2, 1).reshape(-1).contiguous()
+        inv = torch.empty_like(perm)
+        inv[perm] = torch.arange(ndir * 4 * H, device=device)
+        pi = _GATE_PERM[key] = (perm, inv)
+    return pi
+
+
+def lstm_layer_fwd(xin, Dp, w_ih, w_hh, bias, lens, B, T, Tp, rep):
+    """xin bf16 [B*T, Dp]; w_ih / w_hh / bias: per-direction lists (bias = b_ih + b_hh). Returns
+    (y bf16 [B, Tp, ndir*H], zero past each length, `rep` replicated row written; saved state for lstm_layer_bwd)."""
+    dev = xin.device
+    ndir = len(w_hh)
+    H = w_hh[0].shape[1]
+    persist = bool(_lib.lib().las_lstm_persistent_geometry(H, None, None))
+    wcat = torch.cat(w_ih, dim=0) if ndir > 1 else w_ih[0]
+    bcat = torch.cat(bias) if ndir > 1 else bias[0]
+    if persist:
+        perm, _ = gate_perm(H, ndir, dev)
+        wcat, bcat = wcat.index_select(0, perm), bcat.index_select(0, perm)
+    wcat_bf = cvt_bf16(wcat, ld_dst=Dp)                                            # [ndir*4H, Dp]
+    xproj = gemm(xin, Dp, 0, wcat_bf, Dp, 0, B * T, ndir * 4 * H, Dp, bias=bcat)   # f32 [B*T, ndir*4H]
+    y = torch.zeros(B, Tp, ndir * H, device=dev, dtype=BF16)
+    hprev = torch.empty(B, T, ndir * H, device=dev, dtype=BF16)
+    if persist:
+        whh_pk = torch.cat([pack_afrag(w, 3, H) for w in w_hh])
+        rec = torch.empty(ndir * B * T * H, 4, device=dev, dtype=torch.int32)
+        call("las_lstm_persist_fwd", ptr(xproj), ptr(whh_pk), ptr(lens), B, T, H, ndir, ptr(y), Tp * ndir * H, ndir * H,
+             rep, ptr(hprev), T * ndir * H, ndir * H, ptr(rec))
+        act = (rec,)
+    else:
+        whh_pk = torch.cat([pack_afrag(w, 1, H) for w in w_hh])
+        gates = torch.empty(ndir, B, T, H, 4, device=dev, dtype=torch.float16)
+        csave = torch.empty(ndir, B, T, H, device=dev, dtype=torch.float32)
+        ws = torch.empty(_lib.lib().las_lstm_ws_bytes(B, H, ndir), device=dev, dtype=torch.uint8)
+        call("las_lstm_seq_fwd", ptr(xproj), ptr(whh_pk), ptr(lens), B, T, H, ndir, ptr(y), Tp * ndir * H, ndir * H,
+             rep, ptr(hprev), T * ndir * H, ndir * H, ptr(gates), ptr(csave), ptr(ws))
+        act = (gates, csave)
+    return y, (xin, wcat_bf, hprev, act, persist, lens, B, T, Tp, rep, Dp, H, ndir)
+
+
+def lstm_layer_bwd(saved, w_hh, dy, need_dx=True):
+    """dy f32 [B, Tp, ndir*H]. Returns (dx f32 [B*T, Dp] or None, d_w_ih [ndir*4H, Dp], d_w_hh list, d_bias
+    [ndir*4H]) in torch's gate-major row order."""
+    xin, wcat_bf, hprev, act, persist, lens, B, T, Tp, rep, Dp, H, ndir = saved
+    dev = dy.device
+    G = ndir * 4 * H
+    dG = torch.empty(B * T, G, device=dev, dtype=BF16)
+    if persist:
+        whhT = torch.cat([pack_whhT(w)[0] for w in w_hh])
+        call("las_lstm_persist_bwd", ptr(dy), Tp * ndir * H, ndir * H, rep, ptr(whhT), ptr(lens), B, T, H, ndir,
+             ptr(act[0]), ptr(dG), T * G, G)
+    else:
+        whhT = torch.cat([pack_afrag(w, 0, transposed=True) for w in w_hh])
+        ws = torch.empty(ndir * B * H, device=dev, dtype=torch.float32)
+        call("las_lstm_seq_bwd", ptr(dy), Tp * ndir * H, ndir * H, rep, ptr(whhT), 0, ptr(lens), B, T, H, ndir,
+             ptr(act[0]), ptr(act[1]), ptr(dG), T * G, G, ptr(ws))
+    # weight gradients as dense contractions over all (b, t)
+    d_wcat = gemm(dG, G, 1, xin, Dp, 1, G, Dp, B * T)                                # [ndir*4H, Dp]
+    d_bcat = colsum(dG, G)
+    hp2 = hprev.view(B * T, ndir * H)
+    d_whh = [gemm(dG[:, 4 * H * d:], G, 1, hp2[:, H * d:], ndir * H, 1, 4 * H, H, B * T) for d in range(ndir)]
+    if persist:
+        _, inv = gate_perm(H, ndir, dev)
+        _, inv1 = gate_perm(H, 1, dev)
+        d_wcat, d_bcat = d_wcat.index_select(0, inv), d_bcat.index_select(0, inv)
+        d_whh = [g.index_select(0, inv1) for g in d_whh]
+    dx = gemm(dG, G, 0, wcat_bf, Dp, 1, B * T, Dp, G) if need_dx else None           # f32 [B*T, Dp]
+    return dx, d_wcat, d_whh, d_bcat
+
+
+# --------------------------------------------------------------------------------------------
 # pyramidal BLSTM encoder (model.py:58-98)
 # --------------------------------------------------------------------------------------------
 class EncoderFn(torch.autograd.Function):
@@ -167,20 +250,10 @@ class EncoderFn(torch.autograd.Function):
         for i, sub in enumerate(subsample):
             w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r, proj_w, proj_b = weights[10 * i:10 * i + 10]
             H = w_hh.shape[1]
-            wcat = cvt_bf16(torch.cat([w_ih, w_ih_r], dim=0), ld_dst=Dp)           # [8H, Dp]
-            bcat = torch.cat([b_ih + b_hh, b_ih_r + b_hh_r])
-            xproj = gemm(xin, Dp, 0, wcat, Dp, 0, B * T, 8 * H, Dp, bias=bcat)      # f32 [B*T, 8H]
-            whh_pk = torch.cat([pack_afrag(w_hh, 1, H), pack_afrag(w_hh_r, 1, H)])
             Tp = T + (T % 2) if sub > 1 else T
-            y = torch.zeros(B, Tp, 2 * H, device=dev, dtype=BF16)
-            hprev = torch.empty(B, T, 2 * H, device=dev, dtype=BF16)
-            gates = torch.empty(2, B, T, H, 4, device=dev, dtype=torch.float16)
-            csave = torch.empty(2, B, T, H, device=dev, dtype=torch.float32)
-            ws = torch.empty(_lib.lib().las_lstm_ws_bytes(B, H, 2), device=dev, dtype=torch.uint8)
             rep = int(sub > 1 and T % 2 == 1)
-            call("las_lstm_seq_fwd", ptr(xproj), ptr(whh_pk), ptr(cur_lens), B, T, H, 2, ptr(y), Tp * 2 * H, 2 * H,
-                 rep, ptr(hprev), T * 2 * H, 2 * H, ptr(gates), ptr(csave), ptr(ws))
-            del xproj
+            y, lsaved = lstm_layer_fwd(xin, Dp, [w_ih, w_ih_r], [w_hh, w_hh_r], [b_ih + b_hh, b_ih_r + b_hh_r], cur_lens,
+                                       B, T, Tp, rep)
             if p_drop > 0:      # model.py:82 (before the replicate pad of an odd extent: the extra row shares its mask)
                 dropout_(y, B, T, 2 * H, Tp * 2 * H, 2 * H, rep, p_drop, site0 + 2 * i)
             if sub > 1:
@@ -191,7 +264,7 @@ class EncoderFn(torch.autograd.Function):
             out = gemm(y, Kp, 0, wp, Kp, 0, B * T2, proj_w.shape[0], Kp, out_bf16=True, bias=proj_b, relu=True)
             if p_drop > 0:      # model.py:95 (all rows, incl. the relu(bias) rows past each length)
                 dropout_(out, B * T2, 1, proj_w.shape[0], proj_w.shape[0], proj_w.shape[0], 0, p_drop, site0 + 2 * i + 1)
-            saved.append((xin, wcat, y, hprev, gates, csave, out, wp, cur_lens, T, Tp, T2, Dp, H, rep))
+            saved.append((lsaved, y, out, wp, T, Tp, T2, Dp, H, rep))
             if sub > 1:
                 nl = torch.empty_like(cur_lens)
                 call("las_pyramid_lens", ptr(cur_lens), B, sub, ptr(nl))
@@ -215,7 +288,7 @@ class EncoderFn(torch.autograd.Function):
         if p_drop > 0:
             dout = dout.clone()                       # masked in place below
         for i in reversed(range(n_layers)):
-            xin, wcat, y, hprev, gates, csave, out, wp, lens_i, T, Tp, T2, Dp, H, rep = ctx.saved[i]
+            lsaved, y, out, wp, T, Tp, T2, Dp, H, rep = ctx.saved[i]
             w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r, proj_w, proj_b = ctx.weights[10 * i:10 * i + 10]
             dev = dout.device
             Ho, Kp = proj_w.shape
@@ -230,26 +303,14 @@ class EncoderFn(torch.autograd.Function):
             dy = gemm(dz, Ho, 0, wp, Kp, 1, n, Kp, Ho)                               # f32 [B, Tp, 2H] view
             if p_drop > 0:
                 dropout_(dy, B, T, 2 * H, Tp * 2 * H, 2 * H, rep, p_drop, site0 + 2 * i)
-            # recurrence
-            wf, layout = pack_whhT(w_hh)
-            wr, _ = pack_whhT(w_hh_r)
-            whhT = torch.cat([wf, wr])
-            dG = torch.empty(B * T, 8 * H, device=dev, dtype=BF16)
-            ws = torch.empty(2 * B * H, device=dev, dtype=torch.float32)
-            call("las_lstm_seq_bwd", ptr(dy), Tp * 2 * H, 2 * H, rep, ptr(whhT), layout, ptr(lens_i), B, T, H, 2,
-                 ptr(gates), ptr(csave), ptr(dG), T * 8 * H, 8 * H, ptr(ws))
+            dx, d_wcat, d_whh, d_bcat = lstm_layer_bwd(lsaved, [w_hh, w_hh_r], dy, need_dx=i > 0)
             del dy
-            # weight gradients as dense contractions over all (b, t)
-            d_wcat = gemm(dG, 8 * H, 1, xin, Dp, 1, 8 * H, Dp, B * T)                # [8H, Dp]
-            d_bcat = colsum(dG, 8 * H)
             Din = w_ih.shape[1]
-            d_whh = gemm(dG, 8 * H, 1, hprev, 2 * H, 1, 4 * H, H, B * T)
-            d_whh_r = gemm(dG[:, 4 * H:], 8 * H, 1, hprev.view(B * T, 2 * H)[:, H:], 2 * H, 1, 4 * H, H, B * T)
-            grads[10 * i:10 * i + 10] = [d_wcat[:4 * H, :Din], d_whh, d_bcat[:4 * H], d_bcat[:4 * H],
-                                         d_wcat[4 * H:, :Din], d_whh_r, d_bcat[4 * H:], d_bcat[4 * H:],
+            grads[10 * i:10 * i + 10] = [d_wcat[:4 * H, :Din], d_whh[0], d_bcat[:4 * H], d_bcat[:4 * H],
+                                         d_wcat[4 * H:, :Din], d_whh[1], d_bcat[4 * H:], d_bcat[4 * H:],
                                          d_proj_w, d_proj_b]
             if i > 0:
-                dout = gemm(dG, 8 * H, 0, wcat, Dp, 1, B * T, Dp, 8 * H)             # f32 [B*T, H_prev]
+                dout = dx
         ctx.saved = None
         return (None, None, None, None, *grads)
 
@@ -599,17 +660,9 @@ class LMFn(torch.autograd.Function):
         for l in range(n_layers):
             w_ih, w_hh, b_ih, b_hh = wts[1 + 4 * l:5 + 4 * l]
             H = w_hh.shape[1]
-            w_bf = cvt_bf16(w_ih, ld_dst=Dp)
-            xproj = gemm(xin, Dp, 0, w_bf, Dp, 0, n, 4 * H, Dp, bias=(b_ih + b_hh))
-            whh_pk = pack_afrag(w_hh, 1, H)
-            y = torch.zeros(n, H, device=dev, dtype=BF16)
-            hprev = torch.empty(n, H, device=dev, dtype=BF16)
-            gates = torch.empty(1, B, Lm, H, 4, device=dev, dtype=torch.float16)
-            csave = torch.empty(1, B, Lm, H, device=dev, dtype=torch.float32)
-            ws = torch.empty(_lib.lib().las_lstm_ws_bytes(B, H, 1), device=dev, dtype=torch.uint8)
-            call("las_lstm_seq_fwd", ptr(xproj), ptr(whh_pk), ptr(lens), B, Lm, H, 1, ptr(y), Lm * H, H, 0,
-                 ptr(hprev), Lm * H, H, ptr(gates), ptr(csave), ptr(ws))
-            saved.append((xin, w_bf, hprev, gates, csave, Dp, H))
+            y, lsaved = lstm_layer_fwd(xin, Dp, [w_ih], [w_hh], [b_ih + b_hh], lens, B, Lm, Lm, 0)
+            y = y.view(n, H)
+            saved.append(lsaved)
             if p_drop > 0:                            # nn.LSTM(dropout=p) between layers (model.py:466) and model.py:520 on top
                 dropout_(y, n, 1, H, H, H, 0, p_drop, site0 + 1 + l)
             xin, Dp = y, H
@@ -639,20 +692,12 @@ class LMFn(torch.autograd.Function):
         grads = [None] * len(wts)
         grads[-2], grads[-1] = d_out_w, d_out_b
         for l in reversed(range(n_layers)):
-            xin, w_bf, hprev, gates, csave, Dp, H = saved[l]
             w_ih, w_hh, b_ih, b_hh = wts[1 + 4 * l:5 + 4 * l]
+            H = w_hh.shape[1]
             if p_drop > 0:                            # gradient of this layer's (dropped-out) output
                 dropout_(dy, n, 1, H, dy.stride(0), dy.stride(0), 0, p_drop, site0 + 1 + l)
-            whhT, layout = pack_whhT(w_hh)
-            dG = torch.empty(n, 4 * H, device=dev, dtype=BF16)
-            ws = torch.empty(B * H, device=dev, dtype=torch.float32)
-            call("las_lstm_seq_bwd", ptr(dy), Lm * H, H, 0, ptr(whhT), layout, ptr(lens), B, Lm, H, 1, ptr(gates), ptr(csave),
-                 ptr(dG), Lm * 4 * H, 4 * H, ptr(ws))
-            d_w_ih = gemm(dG, 4 * H, 1, xin, Dp, 1, 4 * H, Dp, n)[:, :w_ih.shape[1]]
-            d_w_hh = gemm(dG, 4 * H, 1, hprev, H, 1, 4 * H, H, n)
-            d_b = colsum(dG, 4 * H)
-            grads[1 + 4 * l:5 + 4 * l] = [d_w_ih, d_w_hh, d_b, d_b]
-            dy = gemm(dG, 4 * H, 0, w_bf, Dp, 1, n, Dp, 4 * H)                       # f32 [n, Dp]
+            dy, d_w_ih, d_w_hh, d_b = lstm_layer_bwd(saved[l], [w_hh], dy)
+            grads[1 + 4 * l:5 + 4 * l] = [d_w_ih[:, :w_ih.shape[1]], d_w_hh[0], d_b, d_b]
         if p_drop > 0:
             dropout_(dy, n, 1, E, Ep, Ep, 0, p_drop, site0)
         d_emb = torch.zeros(V, E, device=dev, dtype=torch.float32)

@@ -9,23 +9,20 @@ dev = torch.device("cuda")
 torch.manual_seed(0)
 xproj = torch.randn(B * T, 8 * H, device=dev) * 0.1
 w = [torch.randn(4 * H, H, device=dev) * 0.05 for _ in range(2)]
-whh = torch.cat([Fn.pack_afrag(w[0], 1, H), Fn.pack_afrag(w[1], 1, H)])
+whh = torch.cat([Fn.pack_afrag(w[0], 3, H), Fn.pack_afrag(w[1], 3, H)])
 wT = torch.cat([Fn.pack_whhT(w[0])[0], Fn.pack_whhT(w[1])[0]])
 lens = torch.full((B,), T, device=dev, dtype=torch.int32)
 y = torch.zeros(B, T, 2 * H, device=dev, dtype=torch.bfloat16)
 hprev = torch.empty_like(y)
-gates = torch.empty(2, B, T, H, 4, device=dev, dtype=torch.float16)
-cs = torch.empty(2, B, T, H, device=dev, dtype=torch.float32)
-ws = torch.empty(LIB.lib().las_lstm_ws_bytes(B, H, 2), device=dev, dtype=torch.uint8)
+rec = torch.empty(2 * B * T * H, 4, device=dev, dtype=torch.int32)
 dy = torch.randn(B, T, 2 * H, device=dev) * 0.01
 dG = torch.empty(B * T, 8 * H, device=dev, dtype=torch.bfloat16)
-ws2 = torch.empty(2 * B * H, device=dev, dtype=torch.float32)
 def fwd():
-    Fn.call("las_lstm_seq_fwd", Fn.ptr(xproj), Fn.ptr(whh), Fn.ptr(lens), B, T, H, 2, Fn.ptr(y), T * 2 * H, 2 * H, 0,
-            Fn.ptr(hprev), T * 2 * H, 2 * H, Fn.ptr(gates), Fn.ptr(cs), Fn.ptr(ws))
+    Fn.call("las_lstm_persist_fwd", Fn.ptr(xproj), Fn.ptr(whh), Fn.ptr(lens), B, T, H, 2, Fn.ptr(y), T * 2 * H, 2 * H, 0,
+            Fn.ptr(hprev), T * 2 * H, 2 * H, Fn.ptr(rec))
 def bwd():
-    Fn.call("las_lstm_seq_bwd", Fn.ptr(dy), T * 2 * H, 2 * H, 0, Fn.ptr(wT), 1, Fn.ptr(lens), B, T, H, 2, Fn.ptr(gates),
-            Fn.ptr(cs), Fn.ptr(dG), T * 8 * H, 8 * H, Fn.ptr(ws2))
+    Fn.call("las_lstm_persist_bwd", Fn.ptr(dy), T * 2 * H, 2 * H, 0, Fn.ptr(wT), Fn.ptr(lens), B, T, H, 2, Fn.ptr(rec),
+            Fn.ptr(dG), T * 8 * H, 8 * H)
 for _ in range(2):
     fwd(); bwd()
 torch.cuda.synchronize()
