@@ -60,6 +60,7 @@ class SupervisedTrainer:
         self.static = {}
         self.launches_per_step = None
         self.update_graph, self.update_norm = None, None
+        self.cap_stream = None
 
     # ---- the step body: everything below runs on the current stream, no host sync
     def _fwd_bwd(self, st, L):
@@ -70,7 +71,8 @@ class SupervisedTrainer:
         _, logp, _, _ = m.decoder.forward_dev(enc_h, enc_lens, st.ys_in, st.ys_out, L, 0)
         loss = -torch.mean(logp)                                   # solver.py:377 (ALL B x (Lmax+1) positions)
         self.opt.zero_grad()
-        loss.backward()
+        with Fn.deferred_wgrad():      # weight-gradient contractions run on a side stream, joined on exit
+            loss.backward()
         return loss.detach()
 
     def _update(self):
@@ -120,8 +122,13 @@ class SupervisedTrainer:
                 st.seen = 1
                 return self._body(st, L)
             g = torch.cuda.CUDAGraph()
+            Fn.warm_deferred(st.x.device)       # side stream + its workspace exist before the capture
             torch.cuda.synchronize()
-            with torch.cuda.graph(g):
+            if self.cap_stream is None:
+                # the critical path is captured on a high-priority stream: when both are pending, its CTAs are
+                # scheduled before those of the (default-priority) weight-gradient side stream
+                self.cap_stream = torch.cuda.Stream(device=st.x.device, priority=-1)
+            with torch.cuda.graph(g, stream=self.cap_stream):
                 if self.world == 1:
                     st.loss, st.norm = self._body(st, L)
                 else:
@@ -201,7 +208,8 @@ class SSLTrainer:
         self.judge.train()
         loss, sup, unsup, _ = self.losses(lab, unlab)
         self.opt.zero_grad()
-        loss.backward()
+        with Fn.deferred_wgrad():
+            loss.backward()
         norm = _clip_and_step(self.opt, list(self.model.parameters()), self.max_grad_norm)
         return loss.detach(), sup.detach(), unsup.detach(), norm
 
@@ -223,6 +231,7 @@ class JudgeTrainer:
         self.judge.train()
         loss, avg_prob = self.losses(ys)
         self.opt.zero_grad()
-        loss.backward()
+        with Fn.deferred_wgrad():
+            loss.backward()
         norm = _clip_and_step(self.opt, list(self.judge.parameters()), self.max_grad_norm)
         return loss.detach(), avg_prob.detach(), norm

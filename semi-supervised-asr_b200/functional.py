@@ -68,11 +68,90 @@ _GEMM_WS = {}
 
 
 def _gemm_workspace(device):
-    """Split-K workspace (32 MiB of f32, one per device; stream-ordered use only)."""
-    ws = _GEMM_WS.get(device)
+    """Split-K workspace (32 MiB of f32, one per device and stream; stream-ordered use only)."""
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    ws = _GEMM_WS.get(key)
     if ws is None:
-        ws = _GEMM_WS[device] = torch.empty(8 << 20, device=device, dtype=torch.float32)
+        ws = _GEMM_WS[key] = torch.empty(8 << 20, device=device, dtype=torch.float32)
     return ws
+
+
+# --------------------------------------------------------------------------------------------
+# deferred weight gradients: the serial kernels of the backward pass (BPTT recurrences, decoder loop) occupy
+# at most 64 of the 148 SMs, and every parameter gradient is a dense contraction that nothing on that
+# critical path waits for. Inside `with deferred_wgrad():` the Functions below fork those contractions onto a
+# side stream, accumulate them straight into `param.grad` there and hand autograd `None`; leaving the context
+# joins the side stream. Only trainers whose optimiser pre-allocates `.grad` (optim.FusedAdam) use it; a bare
+# `loss.backward()` keeps the ordinary single-stream behaviour.
+# --------------------------------------------------------------------------------------------
+_DEFER = {"on": False, "streams": {}, "keep": [], "used": False}
+
+
+class deferred_wgrad:
+    def __enter__(self):
+        _DEFER["on"] = True
+        return self
+
+    def __exit__(self, *exc):
+        _DEFER["on"] = False
+        join_deferred()
+        return False
+
+
+def join_deferred():
+    """The current stream waits for every weight-gradient kernel forked so far."""
+    if _DEFER["used"]:
+        for dev, side in _DEFER["streams"].items():
+            torch.cuda.current_stream(dev).wait_stream(side)
+        _DEFER["used"] = False
+    _DEFER["keep"].clear()
+
+
+def warm_deferred(device):
+    """Create the side stream and its GEMM workspace outside any graph capture."""
+    side = _DEFER["streams"].get(device)
+    if side is None:
+        side = _DEFER["streams"][device] = torch.cuda.Stream(device=device)
+    with torch.cuda.stream(side):
+        _gemm_workspace(device)
+    return side
+
+
+class wgrad_scope:
+    """`with wgrad_scope(weights, keep...) as sc:` runs its body on the side stream when deferral is active for
+    these weights; `sc.deliver(grads)` then either accumulates into `.grad` (returning Nones) or passes through."""
+
+    def __init__(self, weights, *keep):
+        self.weights = weights
+        self.deferred = _DEFER["on"] and all(
+            (not w.requires_grad) or (isinstance(w, torch.nn.Parameter) and w.grad is not None) for w in weights)
+        self.keep = keep
+        self.cm = None
+
+    def __enter__(self):
+        if self.deferred:
+            dev = self.weights[0].device
+            side = warm_deferred(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            _DEFER["keep"].append(self.keep)      # operands allocated on the main stream stay alive until the join
+            _DEFER["used"] = True
+            self.cm = torch.cuda.stream(side)
+            self.cm.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.cm is not None:
+            self.cm.__exit__(*exc)
+        return False
+
+    def deliver(self, grads):
+        if not self.deferred:
+            return list(grads)
+        for w, g in zip(self.weights, grads):
+            if g is not None and w.requires_grad:
+                w.grad.add_(g.reshape(w.grad.shape) if g.shape != w.grad.shape else g)
+        _DEFER["keep"].append(list(grads))
+        return [None] * len(grads)
 
 
 def gemm(A, lda, a_mn, Bm, ldb, b_mn, M, N, K, out=None, out_bf16=False, bias=None, relu=False,
@@ -199,8 +278,8 @@ def lstm_layer_fwd(xin, Dp, w_ih, w_hh, bias, lens, B, T, Tp, rep):
 
 
 def lstm_layer_bwd(saved, w_hh, dy, need_dx=True):
-    """dy f32 [B, Tp, ndir*H]. Returns (dx f32 [B*T, Dp] or None, d_w_ih [ndir*4H, Dp], d_w_hh list, d_bias
-    [ndir*4H]) in torch's gate-major row order."""
+    """BPTT of one layer (the critical path). dy f32 [B, Tp, ndir*H]. Returns (dx f32 [B*T, Dp] or None, dG bf16
+    [B*T, ndir*4H] for lstm_layer_wgrad)."""
     xin, wcat_bf, hprev, act, persist, lens, B, T, Tp, rep, Dp, H, ndir = saved
     dev = dy.device
     G = ndir * 4 * H
@@ -214,7 +293,16 @@ def lstm_layer_bwd(saved, w_hh, dy, need_dx=True):
         ws = torch.empty(ndir * B * H, device=dev, dtype=torch.float32)
         call("las_lstm_seq_bwd", ptr(dy), Tp * ndir * H, ndir * H, rep, ptr(whhT), 0, ptr(lens), B, T, H, ndir,
              ptr(act[0]), ptr(act[1]), ptr(dG), T * G, G, ptr(ws))
-    # weight gradients as dense contractions over all (b, t)
+    dx = gemm(dG, G, 0, wcat_bf, Dp, 1, B * T, Dp, G) if need_dx else None           # f32 [B*T, Dp]
+    return dx, dG
+
+
+def lstm_layer_wgrad(saved, dG):
+    """Weight gradients of one LSTM layer as dense contractions over all (b, t) (off the critical path: call it
+    inside a wgrad_scope). Returns (d_w_ih [ndir*4H, Dp], d_w_hh list, d_bias [ndir*4H]) in torch's gate-major order."""
+    xin, wcat_bf, hprev, act, persist, lens, B, T, Tp, rep, Dp, H, ndir = saved
+    dev = dG.device
+    G = ndir * 4 * H
     d_wcat = gemm(dG, G, 1, xin, Dp, 1, G, Dp, B * T)                                # [ndir*4H, Dp]
     d_bcat = colsum(dG, G)
     hp2 = hprev.view(B * T, ndir * H)
@@ -224,8 +312,7 @@ def lstm_layer_bwd(saved, w_hh, dy, need_dx=True):
         _, inv1 = gate_perm(H, 1, dev)
         d_wcat, d_bcat = d_wcat.index_select(0, inv), d_bcat.index_select(0, inv)
         d_whh = [g.index_select(0, inv1) for g in d_whh]
-    dx = gemm(dG, G, 0, wcat_bf, Dp, 1, B * T, Dp, G) if need_dx else None           # f32 [B*T, Dp]
-    return dx, d_wcat, d_whh, d_bcat
+    return d_wcat, d_whh, d_bcat
 
 
 # --------------------------------------------------------------------------------------------
@@ -289,7 +376,8 @@ class EncoderFn(torch.autograd.Function):
             dout = dout.clone()                       # masked in place below
         for i in reversed(range(n_layers)):
             lsaved, y, out, wp, T, Tp, T2, Dp, H, rep = ctx.saved[i]
-            w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r, proj_w, proj_b = ctx.weights[10 * i:10 * i + 10]
+            lw = ctx.weights[10 * i:10 * i + 10]
+            w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r, proj_w, proj_b = lw
             dev = dout.device
             Ho, Kp = proj_w.shape
             n = B * T2
@@ -297,18 +385,21 @@ class EncoderFn(torch.autograd.Function):
                 dropout_(dout, n, 1, Ho, Ho, Ho, 0, p_drop, site0 + 2 * i + 1)
             dz = torch.empty(n, Ho, device=dev, dtype=BF16)
             call("las_relu_bwd", ptr(dout), ptr(out), 1, ptr(dz), n * Ho)
-            # projection: dW = dz^T yview, db = colsum(dz), dy = dz W
-            d_proj_w = gemm(dz, Ho, 1, y, Kp, 1, Ho, Kp, n)
-            d_proj_b = colsum(dz, Ho)
+            # critical path: dy = dz W_proj -> BPTT -> dx
             dy = gemm(dz, Ho, 0, wp, Kp, 1, n, Kp, Ho)                               # f32 [B, Tp, 2H] view
             if p_drop > 0:
                 dropout_(dy, B, T, 2 * H, Tp * 2 * H, 2 * H, rep, p_drop, site0 + 2 * i)
-            dx, d_wcat, d_whh, d_bcat = lstm_layer_bwd(lsaved, [w_hh, w_hh_r], dy, need_dx=i > 0)
+            dx, dG = lstm_layer_bwd(lsaved, [w_hh, w_hh_r], dy, need_dx=i > 0)
             del dy
-            Din = w_ih.shape[1]
-            grads[10 * i:10 * i + 10] = [d_wcat[:4 * H, :Din], d_whh[0], d_bcat[:4 * H], d_bcat[:4 * H],
-                                         d_wcat[4 * H:, :Din], d_whh[1], d_bcat[4 * H:], d_bcat[4 * H:],
-                                         d_proj_w, d_proj_b]
+            # parameter gradients: projection dW = dz^T yview, db = colsum(dz); LSTM weights from dG
+            with wgrad_scope(lw, dz, y, dG, lsaved) as sc:
+                d_proj_w = gemm(dz, Ho, 1, y, Kp, 1, Ho, Kp, n)
+                d_proj_b = colsum(dz, Ho)
+                d_wcat, d_whh, d_bcat = lstm_layer_wgrad(lsaved, dG)
+                Din = w_ih.shape[1]
+                grads[10 * i:10 * i + 10] = sc.deliver([d_wcat[:4 * H, :Din], d_whh[0], d_bcat[:4 * H], d_bcat[:4 * H],
+                                                        d_wcat[4 * H:, :Din], d_whh[1], d_bcat[4 * H:], d_bcat[4 * H:],
+                                                        d_proj_w, d_proj_b])
             if i > 0:
                 dout = dx
         ctx.saved = None
@@ -445,6 +536,7 @@ class DecoderFn(torch.autograd.Function):
                          logits=logits if mode != 0 else None,
                          emb_op=(emb_op[:B * R * Ep].view(B * R, Ep) if mode != 0 else None))
         ctx.W = W
+        ctx.wts = wts
         ctx.mark_non_differentiable(ws)
         if pred is not None:
             ctx.mark_non_differentiable(pred)
@@ -482,8 +574,6 @@ class DecoderFn(torch.autograd.Function):
         else:
             dl_bf = cvt_bf16(dl)                                                      # [n, Vp]
             Vp = dl_bf.shape[1]
-            d_out_w = gemm(dl_bf, Vp, 1, zc, ZC, 1, V, ZC, n)
-            d_out_b = colsum(dl, V)
             dzc_all = gemm(dl_bf, Vp, 0, S["out_bf"], ZC, 1, n, ZC, V)                # f32 [n, ZC]
         wrT_pk = pack_afrag(S["wr_cat"], 0, transposed=True)
         mlp_oT_pk = pack_afrag(W["mlp_o_w"], 0, transposed=True)
@@ -532,72 +622,82 @@ class DecoderFn(torch.autograd.Function):
             if not L_.las_dec_persistent_supported(ctypes.byref(a)):
                 raise _lib.LasError("decoder backward: the forward ran the persistent kernel but the backward would not")
         _lib.check(_lib.lib().las_dec_bwd(ctypes.byref(a), _lib.stream_ptr()))
+        # ---- critical path: gradient w.r.t. the encoder states
+        dP_bf = None
         if pers is not None:
             call("las_att_param_grads", ptr(pers["Pc"]), ptr(S["dzf"]), ptr(pers["conv_save"]), ptr(de_all), ptr(S["mlp_att"]),
                  ptr(S["gvec"]), B, L, Te, A, C, ptr(dP), ptr(att_part), ptr(d_mlp_att), ptr(d_gvec))
-            d_conv_t = torch.zeros(C, 2 * K + 1, **f32)
-            call("las_att_dconv", ptr(dattc_all), ptr(S["ws"]), L, B, Te, C, K, ptr(d_conv_t), ptr(att_part))
-            d_conv = d_conv_t
             dQ = torch.empty(B * Te, O, **f32)
             call("las_att_dq", ptr(S["ws"]), ptr(dc_all), L, B, Te, O, ptr(dQ))
-        # ---- weight gradients deferred out of the time loop, as dense contractions over all (b, t)
-        if mode == 2:
-            dlt = dl_tot[:n * Vq].view(n, Vq)[:, :V]
-            dlt_bf = cvt_bf16(dlt)
-            d_out_w = gemm(dlt_bf, dlt_bf.shape[1], 1, zc, ZC, 1, V, ZC, n)
-            d_out_b = colsum(dlt, V)
-        zc_in = zc
-        if p_drop > 0:                                 # the cell saw [z_{t-1} | dropout(c_{t-1})]
-            zc_in = zc.clone()
-            dropout_(zc_in[Hd:], B, R, O, R * ZC, ZC, 0, p_drop, site0)
-        d_wr = gemm(dgates, 4 * Hd, 1, zc_in, ZC, 1, 4 * Hd, ZC, n)                   # [4Hd, Hd+O]
-        emb_in = S["emb_in"] if mode == 0 else S["emb_op"]                            # bf16 [n, Ep] step inputs
-        d_we = gemm(dgates, 4 * Hd, 1, emb_in, Ep, 1, 4 * Hd, Ep, n)                  # [4Hd, Ep]
-        d_w_ih = torch.cat([d_we[:, :E], d_wr[:, Hd:]], dim=1)
-        d_w_hh = d_wr[:, :Hd].contiguous()
-        d_b = colsum(dgates, 4 * Hd)
-        we_bf = cvt_bf16(W["w_ih"][:, :E], ld_dst=Ep)
-        demb_rows = gemm(dgates, 4 * Hd, 0, we_bf, Ep, 1, n, Ep, 4 * Hd)              # f32 [n, Ep]
-        if p_drop > 0:                                 # gradient w.r.t. the un-dropped step embeddings
-            dropout_(demb_rows, B, R, E, R * Ep, Ep, 0, p_drop, site0 + 1)
-        if mode == 0:
-            d_emb = torch.zeros(V, E, **f32)
-            call("las_scatter_add_rows", ptr(demb_rows), Ep, E, ptr(S["ys_in"]), n, 0, ptr(d_emb))
-        else:
-            # emb_0 = E[BOS]; emb_{t+1} = p_t @ E with p_t = softmax(s logit_t) (smooth, model.py:341: a matmul,
-            # so every row of E receives gradient) or one-hot(argmax) (greedy): d E = sum_rows p^T demb
-            lg = S["logits"]                                                          # [B, R, V], row r = step r-1
-            if mode == 2:
-                p_all = torch.softmax(lg * smooth_scaling, dim=-1)
-            else:
-                p_all = torch.nn.functional.one_hot(lg.argmax(-1), V).float()
-            p_all = torch.cat([torch.nn.functional.one_hot(torch.full((B, 1), S["bos"], device=dev), V).float(),
-                               p_all[:, 1:]], dim=1)                                  # row r feeds step r
-            p_bf = cvt_bf16(p_all.reshape(n, V))
-            de_bf = cvt_bf16(demb_rows)
-            d_emb = gemm(p_bf, p_bf.shape[1], 1, de_bf, de_bf.shape[1], 1, V, Ep, n)[:, :E].contiguous()
-        dc_att = dcz_all[:, Hd:]                                                      # bf16 view, ld ZC
-        if pers is not None:
-            # c_t = w_t @ Q + b, Q = enc_h @ mlp_o.weight^T: d mlp_o.weight = dQ^T enc_h, d enc_h = dQ mlp_o.weight
+            # c_t = w_t @ Q + b, Q = enc_h @ mlp_o.weight^T: d enc_h = dQ mlp_o.weight (+ dP mlp_enc.weight below)
             dQ_bf = cvt_bf16(dQ)
-            d_mlp_o_w = gemm(dQ_bf, dQ_bf.shape[1], 1, S["enc_bf"], H, 1, O, H, B * Te)
             gemm(dQ_bf, dQ_bf.shape[1], 0, pers["mlp_o_bf"], H, 1, B * Te, H, O, out=denc.view(B * Te, H))
-        else:
-            d_mlp_o_w = gemm(dc_att, ZC, 1, S["cx"], H, 1, O, H, n)
-        d_mlp_o_b = colsum(dc_att, O, ld=ZC, rows=n)
-        ddz_bf = cvt_bf16(ddz_all[:n * A].view(n, A))
-        d_mlp_dec = gemm(ddz_bf, ddz_bf.shape[1], 1, zc, ZC, 1, A, Hd, n)
         dP_bf = cvt_bf16(dP)
         Ap8 = dP_bf.shape[1]
-        d_mlp_enc_w = gemm(dP_bf, Ap8, 1, S["enc_bf"], H, 1, A, H, B * Te)
-        d_mlp_enc_b = colsum(dP, A)
         gemm(dP_bf, Ap8, 0, S["mlp_enc_bf"], H, 1, B * Te, H, A, out=denc.view(B * Te, H), accumulate=True)
+        # ---- weight gradients deferred out of the time loop, as dense contractions over all (b, t); nothing on
+        # the critical path (the encoder's backward) waits for them
+        with wgrad_scope(ctx.wts, S, dl, dlogits, dl_tot, dgates, dcz_all, ddz_all, dP, dP_bf, dattc_all, att_part,
+                         (dQ_bf if pers is not None else None), d_mlp_att, d_gvec) as sc:
+            if pers is not None:
+                d_conv_t = torch.zeros(C, 2 * K + 1, **f32)
+                call("las_att_dconv", ptr(dattc_all), ptr(S["ws"]), L, B, Te, C, K, ptr(d_conv_t), ptr(att_part))
+                d_conv = d_conv_t
+            if mode == 2:
+                dlt = dl_tot[:n * Vq].view(n, Vq)[:, :V]
+                dlt_bf = cvt_bf16(dlt)
+                d_out_w = gemm(dlt_bf, dlt_bf.shape[1], 1, zc, ZC, 1, V, ZC, n)
+                d_out_b = colsum(dlt, V)
+            else:
+                d_out_w = gemm(dl_bf, Vp, 1, zc, ZC, 1, V, ZC, n)
+                d_out_b = colsum(dl, V)
+            zc_in = zc
+            if p_drop > 0:                                 # the cell saw [z_{t-1} | dropout(c_{t-1})]
+                zc_in = zc.clone()
+                dropout_(zc_in[Hd:], B, R, O, R * ZC, ZC, 0, p_drop, site0)
+            d_wr = gemm(dgates, 4 * Hd, 1, zc_in, ZC, 1, 4 * Hd, ZC, n)                   # [4Hd, Hd+O]
+            emb_in = S["emb_in"] if mode == 0 else S["emb_op"]                            # bf16 [n, Ep] step inputs
+            d_we = gemm(dgates, 4 * Hd, 1, emb_in, Ep, 1, 4 * Hd, Ep, n)                  # [4Hd, Ep]
+            d_w_ih = torch.cat([d_we[:, :E], d_wr[:, Hd:]], dim=1)
+            d_w_hh = d_wr[:, :Hd].contiguous()
+            d_b = colsum(dgates, 4 * Hd)
+            we_bf = cvt_bf16(W["w_ih"][:, :E], ld_dst=Ep)
+            demb_rows = gemm(dgates, 4 * Hd, 0, we_bf, Ep, 1, n, Ep, 4 * Hd)              # f32 [n, Ep]
+            if p_drop > 0:                                 # gradient w.r.t. the un-dropped step embeddings
+                dropout_(demb_rows, B, R, E, R * Ep, Ep, 0, p_drop, site0 + 1)
+            if mode == 0:
+                d_emb = torch.zeros(V, E, **f32)
+                call("las_scatter_add_rows", ptr(demb_rows), Ep, E, ptr(S["ys_in"]), n, 0, ptr(d_emb))
+            else:
+                # emb_0 = E[BOS]; emb_{t+1} = p_t @ E with p_t = softmax(s logit_t) (smooth, model.py:341: a matmul,
+                # so every row of E receives gradient) or one-hot(argmax) (greedy): d E = sum_rows p^T demb
+                lg = S["logits"]                                                          # [B, R, V], row r = step r-1
+                if mode == 2:
+                    p_all = torch.softmax(lg * smooth_scaling, dim=-1)
+                else:
+                    p_all = torch.nn.functional.one_hot(lg.argmax(-1), V).float()
+                p_all = torch.cat([torch.nn.functional.one_hot(torch.full((B, 1), S["bos"], device=dev), V).float(),
+                                   p_all[:, 1:]], dim=1)                                  # row r feeds step r
+                p_bf = cvt_bf16(p_all.reshape(n, V))
+                de_bf = cvt_bf16(demb_rows)
+                d_emb = gemm(p_bf, p_bf.shape[1], 1, de_bf, de_bf.shape[1], 1, V, Ep, n)[:, :E].contiguous()
+            dc_att = dcz_all[:, Hd:]                                                      # bf16 view, ld ZC
+            if pers is not None:
+                d_mlp_o_w = gemm(dQ_bf, dQ_bf.shape[1], 1, S["enc_bf"], H, 1, O, H, B * Te)   # d mlp_o.weight = dQ^T enc_h
+            else:
+                d_mlp_o_w = gemm(dc_att, ZC, 1, S["cx"], H, 1, O, H, n)
+            d_mlp_o_b = colsum(dc_att, O, ld=ZC, rows=n)
+            ddz_bf = cvt_bf16(ddz_all[:n * A].view(n, A))
+            d_mlp_dec = gemm(ddz_bf, ddz_bf.shape[1], 1, zc, ZC, 1, A, Hd, n)
+            d_mlp_enc_w = gemm(dP_bf, Ap8, 1, S["enc_bf"], H, 1, A, H, B * Te)
+            d_mlp_enc_b = colsum(dP, A)
+            grads = dict(emb_w=d_emb, w_ih=d_w_ih, w_hh=d_w_hh, b_ih=d_b, b_hh=d_b, out_w=d_out_w, out_b=d_out_b,
+                         mlp_enc_w=d_mlp_enc_w, mlp_enc_b=d_mlp_enc_b, mlp_dec_w=d_mlp_dec, mlp_att_w=d_mlp_att,
+                         conv_w=d_conv.view_as(W["conv_w"]), gvec_w=d_gvec.view_as(W["gvec_w"]), mlp_o_w=d_mlp_o_w,
+                         mlp_o_b=d_mlp_o_b)
+            glist = sc.deliver([grads[k] for k in DEC_WEIGHTS])
         ctx.saved = None
-        grads = dict(emb_w=d_emb, w_ih=d_w_ih, w_hh=d_w_hh, b_ih=d_b, b_hh=d_b, out_w=d_out_w, out_b=d_out_b,
-                     mlp_enc_w=d_mlp_enc_w, mlp_enc_b=d_mlp_enc_b, mlp_dec_w=d_mlp_dec, mlp_att_w=d_mlp_att,
-                     conv_w=d_conv.view_as(W["conv_w"]), gvec_w=d_gvec.view_as(W["gvec_w"]), mlp_o_w=d_mlp_o_w,
-                     mlp_o_b=d_mlp_o_b)
-        return (denc, None, None, None, None, None, None, None, None, None, *[grads[k] for k in DEC_WEIGHTS])
+        return (denc, None, None, None, None, None, None, None, None, None, *glist)
 
 
 # --------------------------------------------------------------------------------------------
@@ -696,8 +796,10 @@ class LMFn(torch.autograd.Function):
             H = w_hh.shape[1]
             if p_drop > 0:                            # gradient of this layer's (dropped-out) output
                 dropout_(dy, n, 1, H, dy.stride(0), dy.stride(0), 0, p_drop, site0 + 1 + l)
-            dy, d_w_ih, d_w_hh, d_b = lstm_layer_bwd(saved[l], [w_hh], dy)
-            grads[1 + 4 * l:5 + 4 * l] = [d_w_ih[:, :w_ih.shape[1]], d_w_hh[0], d_b, d_b]
+            dy, dG = lstm_layer_bwd(saved[l], [w_hh], dy)
+            with wgrad_scope(wts[1 + 4 * l:5 + 4 * l], dG, saved[l]) as sc:
+                d_w_ih, d_w_hh, d_b = lstm_layer_wgrad(saved[l], dG)
+                grads[1 + 4 * l:5 + 4 * l] = sc.deliver([d_w_ih[:, :w_ih.shape[1]], d_w_hh[0], d_b, d_b])
         if p_drop > 0:
             dropout_(dy, n, 1, E, Ep, Ep, 0, p_drop, site0)
         d_emb = torch.zeros(V, E, device=dev, dtype=torch.float32)
