@@ -22,14 +22,16 @@ constexpr int BLOCK_K = 64;   // 64 bf16 = 128 bytes = one swizzle atom row
 constexpr int UMMA_K = 16;
 constexpr int kStages = 6;
 constexpr int kAccStages = 2;
-constexpr int kThreads = 256;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps4-7 epilogue
+constexpr int kThreads = 384;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps4-11 epilogue (two per TMEM lane quadrant)
+constexpr int kEpiWarps = 8;
 
 template <int BN>
 struct SmemLayout {
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
   static constexpr int kBBytes = BN * BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kBarOffset = kStages * kStageBytes;
+  static constexpr int kEpiOffset = kStages * kStageBytes;          // per epilogue warp: a (32 rows x 32 f32) transpose tile
+  static constexpr int kBarOffset = kEpiOffset + kEpiWarps * 4096;
   static constexpr int kTotal = kBarOffset + 256 + 1024;  // barriers + alignment slack
 };
 
@@ -78,7 +80,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
     for (int s = 0; s < kAccStages; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[s], kEpiWarps);  // one arrive per epilogue warp
     }
     fence_mbar_init();
   }
@@ -157,6 +159,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   } else if (warp >= 4) {
     // ===================== epilogue: TMEM -> registers -> global =====================
     const int q = warp & 3;  // TMEM lane quadrant this warp may touch
+    const int half = (warp - 4) >> 2;   // column half of the tile served by this warp
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
@@ -166,67 +169,80 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const int n0 = (tile % n_blocks) * BN;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const int row = m0 + q * 32 + lane;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+      // Each lane reads one accumulator ROW from TMEM; the 32x32 chunk is transposed through a swizzled
+      // shared-memory tile so that global stores are row-contiguous (a quarter warp writes one full 128-byte
+      // line of an f32 row) instead of 32 scattered 16-byte pieces per instruction.
+      float4* xt = reinterpret_cast<float4*>(smem + L::kEpiOffset + (warp - 4) * 4096);
+      const int row_base = m0 + q * 32;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
         uint32_t v[32];
         tmem_ld_32x32(taddr + c0, v);
         tmem_ld_wait();
         const int col0 = n0 + c0;
-        if (row < p.M && col0 < p.N) {
-          OutT* crow = Cout + static_cast<int64_t>(row) * p.ldc + col0;
-          const int ncols = min(32, p.N - col0);
-          float f[32];
+        if (col0 >= p.N || row_base >= p.M) continue;      // warp-uniform
+        const int ncols = min(32, p.N - col0);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float x = __uint_as_float(v[j]);
-            if (p.bias != nullptr && j < ncols) x += __ldg(p.bias + col0 + j);
-            if (p.relu) x = fmaxf(x, 0.0f);
-            f[j] = x;
-          }
+        for (int j = 0; j < 8; ++j) {
+          float4 o;
+          o.x = __uint_as_float(v[4 * j]); o.y = __uint_as_float(v[4 * j + 1]);
+          o.z = __uint_as_float(v[4 * j + 2]); o.w = __uint_as_float(v[4 * j + 3]);
+          xt[lane * 8 + (j ^ (lane & 7))] = o;
+        }
+        __syncwarp();
+        // lane -> (row sub-index rs = lane >> 3, float4 column jj = lane & 7); 8 passes of 4 rows
+        const int jj = lane & 7, rs = lane >> 3;
+        const int cbase = col0 + 4 * jj;
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias != nullptr) {
+          if (cbase + 0 < p.N) bv.x = __ldg(p.bias + cbase + 0);
+          if (cbase + 1 < p.N) bv.y = __ldg(p.bias + cbase + 1);
+          if (cbase + 2 < p.N) bv.z = __ldg(p.bias + cbase + 2);
+          if (cbase + 3 < p.N) bv.w = __ldg(p.bias + cbase + 3);
+        }
+        const bool vec_ok = (ncols == 32);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rl = 4 * i + rs;
+          const int row = row_base + rl;
+          float4 o = xt[rl * 8 + (jj ^ (rl & 7))];
+          o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+          if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+          if (row >= p.M) continue;
+          OutT* cptr = Cout + static_cast<int64_t>(row) * p.ldc + cbase;
           if constexpr (sizeof(OutT) == 4) {
-            const bool vec = (ncols == 32) && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0);
-            if (vec) {
-              float4* c4 = reinterpret_cast<float4*>(crow);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float4 o = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-                if (p.accumulate) {
-                  float4 old = c4[j];
-                  o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-                }
-                c4[j] = o;
+            if (vec_ok && (reinterpret_cast<uintptr_t>(cptr) & 15) == 0) {
+              float4* c4 = reinterpret_cast<float4*>(cptr);
+              if (p.accumulate) {
+                const float4 old = *c4;
+                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
               }
+              *c4 = o;
             } else {
-              for (int j = 0; j < ncols; ++j) {
-                float o = f[j];
-                if (p.accumulate) o += crow[j];
-                crow[j] = o;
-              }
+              const float f[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (cbase + e < p.N) cptr[e] = p.accumulate ? cptr[e] + f[e] : f[e];
             }
           } else {
-            const bool vec = (ncols == 32) && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0);
-            if (vec && !p.accumulate) {
-              uint4* c4 = reinterpret_cast<uint4*>(crow);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                uint4 o;
-                o.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
-                o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
-                o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
-                o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
-                c4[j] = o;
-              }
+            if (vec_ok && !p.accumulate && (reinterpret_cast<uintptr_t>(cptr) & 7) == 0) {
+              uint2 pk;
+              pk.x = pack_bf16x2(o.x, o.y);
+              pk.y = pack_bf16x2(o.z, o.w);
+              *reinterpret_cast<uint2*>(cptr) = pk;
             } else {
-              for (int j = 0; j < ncols; ++j) {
-                float o = f[j];
-                if (p.accumulate) o += __bfloat162float(crow[j]);
-                crow[j] = __float2bfloat16(o);
-              }
+              const float f[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (cbase + e < p.N) {
+                  const float x = p.accumulate ? f[e] + __bfloat162float(cptr[e]) : f[e];
+                  cptr[e] = __float2bfloat16(x);
+                }
             }
           }
         }
+        __syncwarp();      // the tile is rewritten by the next chunk
       }
       tc_fence_before();
       __syncwarp();

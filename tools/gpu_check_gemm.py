@@ -47,9 +47,9 @@ def run(M, N, K, a_mn, b_mn, c_bf16, bias, relu, acc):
         Bst[:, :K] = B
         ldb = Kp
     C = (C0.to(torch.bfloat16) if c_bf16 else C0.clone()).contiguous()
-    L.call("las_gemm_bf16", L.ptr(Ast), L.i64(lda), L.i32(a_mn), L.ptr(Bst), L.i64(ldb), L.i32(b_mn),
-           L.ptr(C), L.i64(N), L.i32(c_bf16), L.ptr(bias_t), L.i32(M), L.i32(N), L.i32(K), L.i32(relu),
-           L.i32(acc), L.stream_ptr())
+    L.call("las_gemm_bf16", L.ptr(Ast), int(lda), int(a_mn), L.ptr(Bst), int(ldb), int(b_mn),
+           L.ptr(C), int(N), int(c_bf16), L.ptr(bias_t), int(M), int(N), int(K), int(relu),
+           int(acc))
     torch.cuda.synchronize()
     err = (C.float() - ref).abs().max().item()
     scale = ref.abs().max().item() + 1e-6
@@ -81,15 +81,15 @@ def main():
     C = torch.empty(M, N, device="cuda")
     for c_bf16, Ct in ((0, C), (1, C.to(torch.bfloat16))):
         for _ in range(3):
-            L.call("las_gemm_bf16", L.ptr(A), L.i64(K), L.i32(0), L.ptr(B), L.i64(K), L.i32(0), L.ptr(Ct),
-                   L.i64(N), L.i32(c_bf16), L.ptr(None), L.i32(M), L.i32(N), L.i32(K), L.i32(0), L.i32(0),
+            L.call("las_gemm_bf16", L.ptr(A), int(K), int(0), L.ptr(B), int(K), int(0), L.ptr(Ct),
+                   int(N), int(c_bf16), L.ptr(None), int(M), int(N), int(K), int(0), int(0),
                    L.stream_ptr())
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(10):
-            L.call("las_gemm_bf16", L.ptr(A), L.i64(K), L.i32(0), L.ptr(B), L.i64(K), L.i32(0), L.ptr(Ct),
-                   L.i64(N), L.i32(c_bf16), L.ptr(None), L.i32(M), L.i32(N), L.i32(K), L.i32(0), L.i32(0),
+            L.call("las_gemm_bf16", L.ptr(A), int(K), int(0), L.ptr(B), int(K), int(0), L.ptr(Ct),
+                   int(N), int(c_bf16), L.ptr(None), int(M), int(N), int(K), int(0), int(0),
                    L.stream_ptr())
         e1.record()
         torch.cuda.synchronize()
@@ -106,14 +106,14 @@ def main():
     B = torch.randn(N, K, device="cuda").to(torch.bfloat16)
     C = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
     for _ in range(3):
-        L.call("las_gemm_bf16", L.ptr(A), L.i64(K), L.i32(0), L.ptr(B), L.i64(K), L.i32(0), L.ptr(C),
-               L.i64(N), L.i32(1), L.ptr(None), L.i32(M), L.i32(N), L.i32(K), L.i32(0), L.i32(0), L.stream_ptr())
+        L.call("las_gemm_bf16", L.ptr(A), int(K), int(0), L.ptr(B), int(K), int(0), L.ptr(C),
+               int(N), int(1), L.ptr(None), int(M), int(N), int(K), int(0), int(0), L.stream_ptr())
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(10):
-        L.call("las_gemm_bf16", L.ptr(A), L.i64(K), L.i32(0), L.ptr(B), L.i64(K), L.i32(0), L.ptr(C),
-               L.i64(N), L.i32(1), L.ptr(None), L.i32(M), L.i32(N), L.i32(K), L.i32(0), L.i32(0), L.stream_ptr())
+        L.call("las_gemm_bf16", L.ptr(A), int(K), int(0), L.ptr(B), int(K), int(0), L.ptr(C),
+               int(N), int(1), L.ptr(None), int(M), int(N), int(K), int(0), int(0), L.stream_ptr())
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
