@@ -246,8 +246,9 @@ def main():
     t0 = time.perf_counter()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
-    for i in range(args.steps):
-        loss, _ = tr.step(*pinned[i % nb])
+    # public API: SupervisedTrainer.steps() over host batches -- the H2D copy of batch i+1 is issued while step i
+    # runs; every step's loss is read back to the host
+    for loss, _ in tr.steps(pinned[i % nb] for i in range(args.steps)):
         losses.append(loss.item())
     e3.record()
     barrier()

@@ -45,6 +45,20 @@ class _Static:
         self.loss = None
         self.norm = None
         self.seen = 0
+        self.slots = [None, None]          # double-buffered upload targets of the pipelined path (steps())
+
+
+class _Slot:
+    """One upload target: device copies of a batch plus the pinned host staging of its small integer tensors."""
+
+    def __init__(self, st):
+        self.x = torch.empty_like(st.x)
+        self.lens, self.ys_in, self.ys_out = torch.empty_like(st.lens), torch.empty_like(st.ys_in), torch.empty_like(st.ys_out)
+        self.h_lens = torch.zeros_like(st.h_lens).pin_memory()
+        self.h_ys_in = torch.zeros_like(st.h_ys_in).pin_memory()
+        self.h_ys_out = torch.zeros_like(st.h_ys_out).pin_memory()
+        self.ready = torch.cuda.Event()    # upload finished (recorded on the copy stream)
+        self.consumed = None               # device copy into the static buffers finished (recorded on the main stream)
 
 
 class SupervisedTrainer:
@@ -61,6 +75,7 @@ class SupervisedTrainer:
         self.launches_per_step = None
         self.update_graph, self.update_norm = None, None
         self.cap_stream = None
+        self.copy_stream = None
 
     # ---- the step body: everything below runs on the current stream, no host sync
     def _fwd_bwd(self, st, L):
@@ -151,6 +166,72 @@ class SupervisedTrainer:
 
     def step(self, xs, ilens, ys):
         return self.run(self.stage(xs, ilens, ys))
+
+    # ---- pipelined epoch: the host->device copy of batch i+1 overlaps the train step of batch i
+    def _geometry(self, xs, ilens, ys):
+        m = self.model
+        dev = next(m.parameters()).device
+        host_lens = [int(l) for l in (ilens.tolist() if torch.is_tensor(ilens) else ilens)]
+        T = max(host_lens)
+        ys_in, ys_out = build_targets(ys, m.decoder.bos, m.decoder.eos, m.decoder.pad)
+        B, L = ys_out.shape
+        key = (B, T, xs.shape[2], L)
+        st = self.static.get(key)
+        if st is None:
+            st = self.static[key] = _Static(B, T, xs.shape[2], L, dev)
+        return key, st, host_lens, T, ys_in, ys_out
+
+    def upload(self, xs, ilens, ys, slot):
+        """Start the H2D copies of one batch into upload slot `slot` (0/1) on the copy stream. Returns a handle."""
+        key, st, host_lens, T, ys_in, ys_out = self._geometry(xs, ilens, ys)
+        if self.copy_stream is None:
+            self.copy_stream = torch.cuda.Stream(device=st.x.device)
+        sl = st.slots[slot]
+        if sl is None:
+            sl = st.slots[slot] = _Slot(st)
+        else:
+            sl.ready.synchronize()                     # the previous upload from these pinned buffers has left the host
+        sl.h_lens.copy_(torch.tensor(host_lens, dtype=torch.int32))
+        sl.h_ys_in.copy_(torch.from_numpy(ys_in))
+        sl.h_ys_out.copy_(torch.from_numpy(ys_out))
+        cs = self.copy_stream
+        if sl.consumed is not None:
+            cs.wait_event(sl.consumed)                 # the step that used this slot has copied it out
+        with torch.cuda.stream(cs):
+            sl.x.copy_(xs[:, :T], non_blocking=True)
+            sl.lens.copy_(sl.h_lens, non_blocking=True)
+            sl.ys_in.copy_(sl.h_ys_in, non_blocking=True)
+            sl.ys_out.copy_(sl.h_ys_out, non_blocking=True)
+            sl.ready.record(cs)
+        return key, slot
+
+    def run_uploaded(self, handle):
+        key, slot = handle
+        st = self.static[key]
+        sl = st.slots[slot]
+        main = torch.cuda.current_stream(st.x.device)
+        main.wait_event(sl.ready)
+        st.x.copy_(sl.x, non_blocking=True)            # device-to-device: ~10 us for 32 MB
+        st.lens.copy_(sl.lens, non_blocking=True)
+        st.ys_in.copy_(sl.ys_in, non_blocking=True)
+        st.ys_out.copy_(sl.ys_out, non_blocking=True)
+        sl.consumed = torch.cuda.Event()
+        sl.consumed.record(main)
+        return self.run(key)
+
+    def steps(self, batches):
+        """Train on an iterable of host batches (xs [B, T, D] ideally pinned, ilens, ys); yields (loss, grad_norm)
+        device tensors per batch. While step i runs on the GPU the inputs of batch i+1 are already being copied."""
+        it = iter(batches)
+        nxt = next(it, None)
+        k = 0
+        handle = self.upload(*nxt, k) if nxt is not None else None
+        while handle is not None:
+            out = self.run_uploaded(handle)            # asynchronous: returns as soon as the step is enqueued
+            nxt = next(it, None)
+            k ^= 1
+            handle = self.upload(*nxt, k) if nxt is not None else None
+            yield out
 
 
 def _clip_and_step(opt, params, max_grad_norm):

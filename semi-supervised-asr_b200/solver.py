@@ -230,10 +230,14 @@ class Solver(object):
         c, tag = self.config, self.config["tag"]
         steps = len(self.train_lab_loader)
         total = torch.zeros((), device=next(self.model.parameters()).device)
-        for i, (xs, ilens, ys) in enumerate(self.train_lab_loader):
-            if c["add_gaussian"] and epoch >= c["gaussian_epoch"]:               # solver.py:370-373 (host noise)
-                xs = xs + torch.from_numpy(np.random.normal(0, c["gaussian_std"], tuple(xs.shape)).astype(np.float32))
-            loss, _ = self.sup_trainer.step(xs, ilens, ys)                        # no per-step .item(): no sync
+        def batches():
+            for xs, ilens, ys in self.train_lab_loader:
+                if c["add_gaussian"] and epoch >= c["gaussian_epoch"]:           # solver.py:370-373 (host noise)
+                    xs = xs + torch.from_numpy(np.random.normal(0, c["gaussian_std"], tuple(xs.shape)).astype(np.float32))
+                yield xs, ilens, ys
+
+        # pipelined: the H2D copy of batch i+1 overlaps step i; no per-step .item(), so no host sync either
+        for i, (loss, _) in enumerate(self.sup_trainer.steps(batches())):
             total += loss
             if self.logger is not None and (i + 1) % max(1, c.get("log_every", 50)) == 0:
                 self.log("scalar_summary", f"{tag}/train_loss", loss.item(), epoch * steps + i + 1)
