@@ -31,6 +31,9 @@ CFG = dict(input_dim=249, enc_hidden_dim=320, enc_n_layers=3, subsample=[2, 2, 2
 # algorithmic work per utterance-step, SURVEY.md §8(d) / BASELINE.md §4 (config 2)
 FLOP_PER_UTT = 19.81e9
 HBM_BYTES_PER_UTT = 51e6
+# dram__bytes_read.sum + dram__bytes_write.sum of one lstm_persist_fwd_kernel launch (B=32, T=1000, H=320, both
+# directions) from the committed `ncu --set full` capture
+NCU_TRAFFIC_BYTES = 693971200
 
 
 def synth_batch(rng, B, Tmax, D, V):
@@ -355,7 +358,8 @@ def kernel_roofline(dev, hbm_peak, which):
     ach = bytes_per_launch / (us * 1e-6) / 1e9
     return {"kernel": "lstm_persist_fwd_kernel (BLSTM layer 0: T=1000 timesteps, both directions, one launch)",
             "bound": "hbm", "achieved": ach, "peak": hbm_peak, "peak_source": which, "unit": "GB/s",
-            "frac": ach / hbm_peak, "traffic": None, "us_per_launch": us, "us_per_timestep": us / T,
+            "frac": ach / hbm_peak, "traffic": NCU_TRAFFIC_BYTES, "traffic_source": "profiles/r01n_ncu_full_summary.txt (dram read 329.4 MB + write 364.6 MB per launch)",
+            "us_per_launch": us, "us_per_timestep": us / T,
             "algorithmic_bytes_per_launch": bytes_per_launch,
             "note": "latency-bound serial recurrence: the binding resource is the per-timestep DSMEM exchange, not HBM"}
 
