@@ -637,7 +637,7 @@ class DecoderFn(torch.autograd.Function):
         gemm(dP_bf, Ap8, 0, S["mlp_enc_bf"], H, 1, B * Te, H, A, out=denc.view(B * Te, H), accumulate=True)
         # ---- weight gradients deferred out of the time loop, as dense contractions over all (b, t); nothing on
         # the critical path (the encoder's backward) waits for them
-        with wgrad_scope(ctx.wts, S, dl, dlogits, dl_tot, dgates, dcz_all, ddz_all, dP, dP_bf, dattc_all, att_part,
+        with wgrad_scope(ctx.wts, S, dl, (dl_bf if mode != 2 else None), dlogits, dl_tot, dgates, dcz_all, ddz_all, dP, dP_bf, dattc_all, att_part,
                          (dQ_bf if pers is not None else None), d_mlp_att, d_gvec) as sc:
             if pers is not None:
                 d_conv_t = torch.zeros(C, 2 * K + 1, **f32)

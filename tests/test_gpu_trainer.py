@@ -74,3 +74,39 @@ def test_pipelined_steps_equal_step():
     _, _, tr_b = _trainer(G1, True)
     got = [float(loss) for loss, _ in tr_b.steps(seq)]
     assert np.allclose(ref, got, rtol=2e-3), (ref, got)
+
+
+def test_graph_replay_equals_eager_at_config2_layer_sizes():
+    """Same check at BASELINE config-2 layer sizes (H=320, att 320, conv 10x201, V=34; B=8, T=400), where the
+    captured step's allocation pattern (buffers freed on the main stream while the weight-gradient side stream
+    still reads them) differs from the toy fixtures."""
+    M, E, OPT = pkg("model"), pkg("engine"), pkg("optim")
+    rng = np.random.RandomState(7)
+    B, T, D, V = 8, 400, 249, 34
+    lens = sorted([T] + [int(rng.randint(T // 2, T + 1)) for _ in range(B - 1)], reverse=True)
+    x = np.zeros((B, T, D), dtype=np.float32)
+    ys = []
+    for b, l in enumerate(lens):
+        x[b, :l] = rng.standard_normal((l, D)).astype(np.float32)
+        ys.append(torch.from_numpy(rng.randint(3, V, size=max(2, l // 8)).astype(np.int64)))
+    cnt = np.bincount(np.concatenate([y.numpy() for y in ys] + [np.full(B, 2)]), minlength=V).astype(np.float64)
+    cnt[:2] = 0
+    ld = cnt / cnt.sum()
+    batch = (torch.from_numpy(x).pin_memory(), lens, ys)
+    traj = {}
+    for use_graph in (False, True):
+        torch.manual_seed(11)
+        m = M.E2E(input_dim=D, enc_hidden_dim=320, enc_n_layers=3, subsample=[2, 2, 2], dropout_rate=0.0, dec_hidden_dim=320,
+                  att_dim=320, conv_channels=10, conv_kernel_size=100, att_odim=320, embedding_dim=128, output_dim=V,
+                  ls_weight=0.05, labeldist=ld).cuda()
+        opt = OPT.FusedAdam(m.parameters(), lr=5e-4, weight_decay=1e-6, amsgrad=True)
+        tr = E.SupervisedTrainer(m, opt, max_grad_norm=5.0, use_graph=use_graph)
+        out = []
+        for _ in range(12):
+            loss, norm = tr.step(*batch)
+            out.append((float(loss), float(norm)))                   # graph mode returns the SAME static tensors each step
+        traj[use_graph] = (np.array([l for l, _ in out]), np.array([n for _, n in out]))
+    (la, na), (lb, nb) = traj[False], traj[True]
+    assert la[-1] < la[0] - 0.2, la                                  # 12 steps on one batch: it must be learning
+    assert np.allclose(la, lb, rtol=5e-3), (la, lb)
+    assert np.allclose(na, nb, rtol=0.1), (na, nb)

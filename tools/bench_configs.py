@@ -1,0 +1,143 @@
+"""BASELINE.json configs 4 and 5 on one B200; bench.py stays the config-2/3 contract line.
+
+  config 4  semi-supervised generator step (solver.py:460-495): paired B=32,Tmax=1000 + unpaired speech
+            B=32,Tmax=1000 (Lu=125 free-running steps, smooth embedding, scaling 3) through ASR + LM judge;
+            plus the judge pre-train step (solver.py:288-301) on a text batch of 32
+  config 5a supervised train step at B=64, Tmax=2000, 4-layer pBLSTM subsample [1,2,2,2] (Te=250, L<=250)
+  config 5b greedy decode (Solver.test semantics, eval mode, 230 steps/utterance): batch 1 and batch 32
+
+Prints one JSON line per measurement. Timing: CUDA events around K steps after W warm-up steps, inputs resident."""
+import argparse
+import importlib
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench as BN  # noqa: E402
+
+PKG = BN.PKG
+M = importlib.import_module(PKG + ".model")
+E = importlib.import_module(PKG + ".engine")
+OPT = importlib.import_module(PKG + ".optim")
+
+
+def make_e2e(cfg, ld, dropout, dev):
+    return M.E2E(input_dim=cfg["input_dim"], enc_hidden_dim=cfg["enc_hidden_dim"], enc_n_layers=cfg["enc_n_layers"],
+                 subsample=cfg["subsample"], dropout_rate=dropout, dec_hidden_dim=cfg["dec_hidden_dim"],
+                 att_dim=cfg["att_dim"], conv_channels=cfg["conv_channels"], conv_kernel_size=cfg["conv_kernel_size"],
+                 att_odim=cfg["att_odim"], embedding_dim=cfg["embedding_dim"], output_dim=cfg["V"],
+                 ls_weight=cfg["ls_weight"], labeldist=ld).to(dev)
+
+
+def timed(fn, steps, warmup):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def config4(args, dev):
+    cfg = dict(BN.CFG)
+    rng = np.random.RandomState(1234)
+    x, lens, ys = BN.synth_batch(rng, 32, 1000, cfg["input_dim"], cfg["V"])
+    rng_u = np.random.RandomState(2234)
+    ux, ulens, _ = BN.synth_batch(rng_u, 32, 1000, cfg["input_dim"], cfg["V"])
+    ld = BN.labeldist_of(ys, cfg["V"])
+    torch.manual_seed(1234)
+    m = make_e2e(cfg, ld, args.dropout, dev)
+    lm = M.LM(output_dim=cfg["V"], embedding_dim=256, hidden_dim=640, dropout_rate=0.5 if args.dropout > 0 else 0.0,
+              n_layers=2, bos=1, eos=2, pad=0, ls_weight=cfg["ls_weight"], labeldist=ld).to(dev)
+    gen_opt = OPT.FusedAdam(m.parameters(), lr=1e-4, weight_decay=1e-6, amsgrad=True)
+    dis_opt = OPT.FusedAdam(lm.parameters(), lr=2e-4)
+    ssl = E.SSLTrainer(m, lm, gen_opt, max_grad_norm=5.0, unsup_weight=0.001, proportion=0.125, smooth=True, scaling=3.0)
+    jt = E.JudgeTrainer(lm, dis_opt, max_grad_norm=5.0)
+    lab = (torch.from_numpy(x).to(dev), lens, [torch.from_numpy(y).to(dev) for y in ys])
+    unlab = (torch.from_numpy(ux).to(dev), ulens)
+    text = sorted([torch.from_numpy(y).to(dev) for y in ys], key=len, reverse=True)
+    ms_j = timed(lambda: jt.step(text), args.steps, args.warmup)
+    # the reference enters ssl_train with a pre-trained generator (solver.py:516-); from random weights the greedy
+    # free-run collapses onto one token, and if that token is <EOS> the mask sum -- the loss denominator of
+    # solver.py:478 -- is zero. A few supervised steps first, as the reference's own flow does.
+    sup_tr = E.SupervisedTrainer(m, gen_opt, max_grad_norm=5.0)
+    pinned = (torch.from_numpy(x).pin_memory(), lens, [torch.from_numpy(y) for y in ys])
+    for _ in range(args.pretrain):
+        sup_tr.step(*pinned)
+    m.train(); lm.train()
+    with torch.no_grad():
+        l0, s0, u0, (u_logp, u_pred, lm_probs) = ssl.losses(lab, unlab)
+    diag = {"non_eos_tokens": int((u_pred != 2).sum()), "tokens": int(u_pred.numel()),
+            "nan_u_logp": bool(torch.isnan(u_logp).any()), "nan_lm_probs": bool(torch.isnan(lm_probs).any())}
+    ms = timed(lambda: ssl.step(lab, unlab), args.steps, args.warmup)
+    loss, sup, unsup, _ = ssl.step(lab, unlab)
+    return [
+        {"config": 4, "workload": "semi-supervised generator step: paired B=32 + unpaired speech B=32, Tmax=1000, Lu=125 smooth free-run, LM judge 2x640",
+         "ms_per_step": ms, "utt_per_s_paired_plus_unpaired": 64 / (ms * 1e-3), "utt_per_s_paired": 32 / (ms * 1e-3),
+         "loss": float(loss), "sup": float(sup), "unsup": float(unsup), "steps": args.steps, "dropout": args.dropout,
+         "supervised_pretrain_steps": args.pretrain, "free_run_diag": diag, "cuda_graph": False},
+        {"config": 4, "workload": "judge (LM 2x640) pre-train step on a text batch of 32 (L<=125+5)", "ms_per_step": ms_j,
+         "texts_per_s": 32 / (ms_j * 1e-3), "steps": args.steps, "cuda_graph": False},
+    ]
+
+
+def config5(args, dev):
+    cfg = dict(BN.CFG)
+    cfg.update(enc_n_layers=4, subsample=[1, 2, 2, 2])
+    rng = np.random.RandomState(1234)
+    x, lens, ys = BN.synth_batch(rng, 64, 2000, cfg["input_dim"], cfg["V"])
+    ld = BN.labeldist_of(ys, cfg["V"])
+    torch.manual_seed(1234)
+    m = make_e2e(cfg, ld, args.dropout, dev)
+    opt = OPT.FusedAdam(m.parameters(), lr=cfg["lr"], weight_decay=cfg["weight_decay"], amsgrad=True)
+    tr = E.SupervisedTrainer(m, opt, max_grad_norm=5.0)
+    batch = (torch.from_numpy(x).pin_memory(), lens, [torch.from_numpy(y) for y in ys])
+    losses = [float(tr.step(*batch)[0]) for _ in range(3)]
+    key = tr.stage(*batch)
+    ms = timed(lambda: tr.run(key), args.steps, 2)
+    out = [{"config": "5a", "workload": "supervised train step B=64, Tmax=2000, 4xpBLSTM-320 subsample [1,2,2,2], Te=250, L+1=251",
+            "ms_per_step": ms, "utt_per_s": 64 / (ms * 1e-3), "loss_first_steps": losses, "steps": args.steps,
+            "dropout": args.dropout, "cuda_graph": True,
+            "algorithmic_tflops": 62.82e9 * 64 / (ms * 1e-3) / 1e12}]
+    # 5b: greedy decode, eval mode, 230 steps per utterance, no early stop (solver.py:244-286)
+    m.eval()
+    xd = torch.from_numpy(x).to(dev)
+    with torch.no_grad():
+        for B in (1, 32):
+            xb, lb = xd[:B, :lens[0] if B > 1 else lens[0]], lens[:B]
+            ms_d = timed(lambda: m(xb, lb, ys=None, max_dec_timesteps=230), max(3, args.steps // 2), 2)
+            out.append({"config": "5b", "workload": f"greedy decode, eval mode, 230 steps, batch {B}, T={lens[0]} frames, 4-layer encoder",
+                        "ms_per_batch": ms_d, "utt_per_s": B / (ms_d * 1e-3)})
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--dropout", type=float, default=0.3)
+    ap.add_argument("--only", default="4,5")
+    ap.add_argument("--pretrain", type=int, default=30)
+    args = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    res = []
+    if "4" in args.only:
+        res += config4(args, dev)
+    if "5" in args.only:
+        res += config5(args, dev)
+    for r in res:
+        print(json.dumps(r))
+
+
+if __name__ == "__main__":
+    main()
