@@ -372,8 +372,69 @@ int las_relu_bwd(const float* dout, const void* out, int out_is_bf16, void* dz, 
   return 0;
 }
 
+}  // extern "C"
+namespace las {
+// Vector path: a thread owns EPT = 16 bytes / sizeof(T) consecutive columns, a warp 32*EPT columns of one row (512
+// contiguous bytes), the 8 warps of a CTA walk rows r0+w, r0+w+8, ...; one atomicAdd per column per CTA.
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ x, int64_t ld, int64_t rows, int cols,
+                                                         float* __restrict__ out, int rows_per_cta) {
+  constexpr int EPT = 16 / sizeof(T);
+  __shared__ float red[8][32 * EPT + 1];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c0 = (blockIdx.x * 32 + lane) * EPT;
+  const int64_t r0 = static_cast<int64_t>(blockIdx.y) * rows_per_cta;
+  const int64_t r1 = min(rows, r0 + rows_per_cta);
+  float s[EPT];
+#pragma unroll
+  for (int e = 0; e < EPT; ++e) s[e] = 0.f;
+  if (c0 < cols) {      // cols % EPT == 0: the whole vector is in range
+    for (int64_t r = r0 + w; r < r1; r += 8) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + r * ld + c0));
+      if constexpr (sizeof(T) == 2) {
+        const float2 a = unpack_bf16x2(v.x), b = unpack_bf16x2(v.y), c = unpack_bf16x2(v.z), d = unpack_bf16x2(v.w);
+        s[0] += a.x; s[1] += a.y; s[2] += b.x; s[3] += b.y; s[4] += c.x; s[5] += c.y; s[6] += d.x; s[7] += d.y;
+      } else {
+        s[0] += __uint_as_float(v.x); s[1] += __uint_as_float(v.y); s[2] += __uint_as_float(v.z); s[3] += __uint_as_float(v.w);
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < EPT; ++e) red[w][lane * EPT + e] = s[e];
+  __syncthreads();
+  for (int i = threadIdx.x; i < 32 * EPT; i += 256) {
+    const int c = blockIdx.x * 32 * EPT + i;
+    if (c < cols) {
+      float t = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t += red[k][i];
+      atomicAdd(out + c, t);
+    }
+  }
+}
+}  // namespace las
+extern "C" {
+
 int las_colsum(const void* x, int x_is_bf16, int64_t ld, int64_t rows, int cols, float* out, void* stream) {
   if (rows == 0 || cols == 0) return 0;
+  const int ept = x_is_bf16 ? 8 : 4;
+  if (cols % ept == 0 && ld % ept == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0) {
+    const int xb = (cols + 32 * ept - 1) / (32 * ept);
+    // ~4 CTAs per SM in total, at least 64 rows each
+    int64_t chunks = (4LL * num_sms() + xb - 1) / xb;
+    int64_t rpc = (rows + chunks - 1) / chunks;
+    if (rpc < 64) rpc = 64;
+    dim3 grid(xb, static_cast<unsigned>((rows + rpc - 1) / rpc));
+    if (x_is_bf16)
+      colsum_vec_kernel<__nv_bfloat16><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+          static_cast<const __nv_bfloat16*>(x), ld, rows, cols, out, static_cast<int>(rpc));
+    else
+      colsum_vec_kernel<float><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+          static_cast<const float*>(x), ld, rows, cols, out, static_cast<int>(rpc));
+    ++g_launches;
+    LAS_LAUNCH_CHECK();
+    return 0;
+  }
   const int rows_per_cta = 512;
   dim3 grid((cols + 31) / 32, static_cast<unsigned>((rows + rows_per_cta - 1) / rows_per_cta));
   if (x_is_bf16)

@@ -66,25 +66,20 @@ def config4(args, dev):
     unlab = (torch.from_numpy(ux).to(dev), ulens)
     text = sorted([torch.from_numpy(y).to(dev) for y in ys], key=len, reverse=True)
     ms_j = timed(lambda: jt.step(text), args.steps, args.warmup)
-    # the reference enters ssl_train with a pre-trained generator (solver.py:516-); from random weights the greedy
-    # free-run collapses onto one token, and if that token is <EOS> the mask sum -- the loss denominator of
-    # solver.py:478 -- is zero. A few supervised steps first, as the reference's own flow does.
-    sup_tr = E.SupervisedTrainer(m, gen_opt, max_grad_norm=5.0)
-    pinned = (torch.from_numpy(x).pin_memory(), lens, [torch.from_numpy(y) for y in ys])
-    for _ in range(args.pretrain):
-        sup_tr.step(*pinned)
     m.train(); lm.train()
-    with torch.no_grad():
-        l0, s0, u0, (u_logp, u_pred, lm_probs) = ssl.losses(lab, unlab)
-    diag = {"non_eos_tokens": int((u_pred != 2).sum()), "tokens": int(u_pred.numel()),
-            "nan_u_logp": bool(torch.isnan(u_logp).any()), "nan_lm_probs": bool(torch.isnan(lm_probs).any())}
+    first = [float(v) for v in ssl.step(lab, unlab)[:3]]          # loss, sup, unsup of the first step
     ms = timed(lambda: ssl.step(lab, unlab), args.steps, args.warmup)
-    loss, sup, unsup, _ = ssl.step(lab, unlab)
+    with torch.no_grad():
+        _, _, _, (_, u_pred, _) = ssl.losses(lab, unlab)
+    diag = {"non_eos_tokens_after_timing": int((u_pred != 2).sum()), "tokens": int(u_pred.numel()),
+            "note": "on synthetic random text the generator collapses onto <EOS> (the most frequent target, ys_out is "
+                    "EOS-padded) within ~8 steps; the reference's unsup loss (solver.py:478) is then 0/0 -- values below are "
+                    "from the FIRST step"}
     return [
         {"config": 4, "workload": "semi-supervised generator step: paired B=32 + unpaired speech B=32, Tmax=1000, Lu=125 smooth free-run, LM judge 2x640",
          "ms_per_step": ms, "utt_per_s_paired_plus_unpaired": 64 / (ms * 1e-3), "utt_per_s_paired": 32 / (ms * 1e-3),
-         "loss": float(loss), "sup": float(sup), "unsup": float(unsup), "steps": args.steps, "dropout": args.dropout,
-         "supervised_pretrain_steps": args.pretrain, "free_run_diag": diag, "cuda_graph": False},
+         "loss": first[0], "sup": first[1], "unsup": first[2], "steps": args.steps, "dropout": args.dropout,
+         "free_run_diag": diag, "cuda_graph": False},
         {"config": 4, "workload": "judge (LM 2x640) pre-train step on a text batch of 32 (L<=125+5)", "ms_per_step": ms_j,
          "texts_per_s": 32 / (ms_j * 1e-3), "steps": args.steps, "cuda_graph": False},
     ]
@@ -126,7 +121,6 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--dropout", type=float, default=0.3)
     ap.add_argument("--only", default="4,5")
-    ap.add_argument("--pretrain", type=int, default=30)
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)

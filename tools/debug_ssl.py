@@ -47,3 +47,24 @@ with torch.no_grad():
     bad = (~torch.isfinite(logits)).nonzero()
     if len(bad):
         print("first non-finite logits at", bad[:5].tolist())
+if os.environ.get("SSL"):
+    lm = M.LM(output_dim=34, embedding_dim=256, hidden_dim=640, dropout_rate=0.5 if drop > 0 else 0.0, n_layers=2, bos=1, eos=2, pad=0,
+              ls_weight=0.05, labeldist=ld).to(dev)
+    gen_opt = OPT.FusedAdam(m.parameters(), lr=1e-4, weight_decay=1e-6, amsgrad=True)
+    ssl = E.SSLTrainer(m, lm, gen_opt, max_grad_norm=5.0, unsup_weight=0.001, proportion=0.125, smooth=True, scaling=3.0)
+    lab = (torch.from_numpy(x).to(dev), lens, [torch.from_numpy(y).to(dev) for y in ys])
+    unlab = (uxd, ulens)
+    for i in range(int(os.environ["SSL"])):
+        m.train(); lm.train()
+        loss, sup, unsup, (u_logp, u_pred, lm_probs) = ssl.losses(lab, unlab)
+        gen_opt.zero_grad()
+        loss.backward()
+        torch.cuda.synchronize()
+        gn = {k: float(p.grad.norm()) for k, p in m.named_parameters()}
+        badk = [k for k, v in gn.items() if not np.isfinite(v)]
+        tot = float(torch.cat([p.grad.flatten() for p in m.parameters()]).double().norm())
+        print(f"step {i}: loss {float(loss):.5f} sup {float(sup):.5f} unsup {float(unsup):.5f} non-eos {int((u_pred != 2).sum())} "
+              f"gradnorm {tot:.4f} nonfinite grads: {badk[:6]}", flush=True)
+        if i == 0:
+            print("  top grad norms:", sorted(gn.items(), key=lambda kv: -kv[1] if np.isfinite(kv[1]) else -1e30)[:5])
+        gen_opt.clip_and_step(5.0)

@@ -12,7 +12,10 @@ rng = np.random.RandomState(1234)
 B, T = int(os.environ.get("B", 32)), int(os.environ.get("T", 1000))
 x, lens, ys = BN.synth_batch(rng, B, T, 249, 34)
 ld = BN.labeldist_of(ys, 34)
-C = BN.CFG
+C = dict(BN.CFG)
+if os.environ.get("SUB"):
+    C["subsample"] = [int(v) for v in os.environ["SUB"].split(",")]
+    C["enc_n_layers"] = len(C["subsample"])
 torch.manual_seed(1234)
 m = M.E2E(input_dim=C["input_dim"], enc_hidden_dim=C["enc_hidden_dim"], enc_n_layers=C["enc_n_layers"], subsample=C["subsample"],
           dropout_rate=0.3, dec_hidden_dim=C["dec_hidden_dim"], att_dim=C["att_dim"], conv_channels=C["conv_channels"],
