@@ -81,6 +81,11 @@ class SupervisedTrainer:
     def _fwd_bwd(self, st, L):
         m = self.model
         enc = m.encoder.enc2
+        # bf16 copies / fragment packs of all weights: on the side stream, so that only layer 0's stay on the
+        # critical path and the rest overlaps the first recurrence
+        jobs = enc.prep_jobs() + m.decoder.prep_jobs(0)
+        jobs.sort(key=lambda j: "bwd" in j[0])          # stable: forward operands first, in order of use
+        Fn.prepare_ahead(jobs)
         enc_h = enc.forward_dev(st.x, st.lens)
         enc_lens = enc.out_lens_dev(st.lens)
         _, logp, _, _ = m.decoder.forward_dev(enc_h, enc_lens, st.ys_in, st.ys_out, L, 0)

@@ -105,6 +105,7 @@ def join_deferred():
             torch.cuda.current_stream(dev).wait_stream(side)
         _DEFER["used"] = False
     _DEFER["keep"].clear()
+    _PREP.clear()
 
 
 def warm_deferred(device):
@@ -225,6 +226,79 @@ def lens_tensor(lens, device):
 
 
 # --------------------------------------------------------------------------------------------
+# weight preparation ahead of use: the bf16 copies / MMA fragment packs / permutations of the parameters are pure
+# functions of the weights (~110 small kernels per step). The Functions obtain them through `_prep(kind, tensors,
+# builder)`; a trainer may run the same builders at the very beginning of the step on the side stream
+# (`prepare_ahead(jobs)`), so that only layer 0's preparation stays on the critical path and the rest overlaps
+# the first recurrence. Without `prepare_ahead` every builder simply runs inline.
+# --------------------------------------------------------------------------------------------
+_PREP = {}
+
+
+def _prep_key(kind, tensors):
+    return (kind,) + tuple(id(t) for t in tensors)
+
+
+def _prep(kind, tensors, builder):
+    ent = _PREP.get(_prep_key(kind, tensors))
+    if ent is None:
+        return builder()
+    val, ev = ent
+    torch.cuda.current_stream(tensors[0].device).wait_event(ev)
+    return val
+
+
+def prepare_ahead(jobs):
+    """jobs: iterable of (kind, tensors, builder) in the order the step needs them. Runs the builders on the side
+    stream; the results are handed to the matching `_prep` calls of this step. `join_deferred()` (end of the
+    backward pass) joins the stream and drops the cache."""
+    jobs = list(jobs)
+    if not jobs:
+        return
+    dev = jobs[0][1][0].device
+    side = warm_deferred(dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    _DEFER["used"] = True
+    with torch.cuda.stream(side):
+        for kind, tensors, builder in jobs:
+            val = builder()
+            ev = torch.cuda.Event()
+            ev.record(side)
+            _PREP[_prep_key(kind, tensors)] = (val, ev)
+
+
+def _build_lstm_fwd(w_ih, w_hh, b_ih, b_hh, Dp):
+    """-> (persist, wcat_bf [ndir*4H, Dp] bf16, bcat [ndir*4H] f32, whh_pk) for one LSTM layer."""
+    dev = w_hh[0].device
+    ndir = len(w_hh)
+    H = w_hh[0].shape[1]
+    persist = bool(_lib.lib().las_lstm_persistent_geometry(H, None, None))
+    wcat = torch.cat(w_ih, dim=0) if ndir > 1 else w_ih[0]
+    bias = [bi + bh for bi, bh in zip(b_ih, b_hh)]
+    bcat = torch.cat(bias) if ndir > 1 else bias[0]
+    if persist:
+        perm, _ = gate_perm(H, ndir, dev)
+        wcat, bcat = wcat.index_select(0, perm), bcat.index_select(0, perm)
+    wcat_bf = cvt_bf16(wcat, ld_dst=Dp)
+    whh_pk = torch.cat([pack_afrag(w, 3 if persist else 1, H) for w in w_hh])
+    return persist, wcat_bf, bcat, whh_pk
+
+
+def _build_lstm_bwd(w_hh):
+    H = w_hh[0].shape[1]
+    if _lib.lib().las_lstm_persistent_geometry(H, None, None):
+        return torch.cat([pack_whhT(w)[0] for w in w_hh])
+    return torch.cat([pack_afrag(w, 0, transposed=True) for w in w_hh])
+
+
+def lstm_prep_jobs(w_ih, w_hh, b_ih, b_hh, Dp):
+    """The prepare_ahead jobs of one LSTM layer (forward and backward packs)."""
+    w_ih, w_hh, b_ih, b_hh = list(w_ih), list(w_hh), list(b_ih), list(b_hh)
+    return [("lstm_fwd", w_ih + w_hh + b_ih + b_hh, lambda: _build_lstm_fwd(w_ih, w_hh, b_ih, b_hh, Dp)),
+            ("lstm_bwd", w_hh, lambda: _build_lstm_bwd(w_hh))]
+
+
+# --------------------------------------------------------------------------------------------
 # one LSTM layer over padded sequences (shared by the listener and the LM)
 # --------------------------------------------------------------------------------------------
 _GATE_PERM = {}
@@ -244,30 +318,25 @@ def gate_perm(H, ndir, device):
     return pi
 
 
-def lstm_layer_fwd(xin, Dp, w_ih, w_hh, bias, lens, B, T, Tp, rep):
-    """xin bf16 [B*T, Dp]; w_ih / w_hh / bias: per-direction lists (bias = b_ih + b_hh). Returns
-    (y bf16 [B, Tp, ndir*H], zero past each length, `rep` replicated row written; saved state for lstm_layer_bwd)."""
+def lstm_layer_fwd(xin, Dp, w_ih, w_hh, b_ih, b_hh, lens, B, T, Tp, rep):
+    """xin bf16 [B*T, Dp]; w_ih / w_hh / b_ih / b_hh: per-direction lists. Returns (y bf16 [B, Tp, ndir*H], zero
+    past each length, `rep` replicated row written; saved state for lstm_layer_bwd)."""
     dev = xin.device
     ndir = len(w_hh)
     H = w_hh[0].shape[1]
-    persist = bool(_lib.lib().las_lstm_persistent_geometry(H, None, None))
-    wcat = torch.cat(w_ih, dim=0) if ndir > 1 else w_ih[0]
-    bcat = torch.cat(bias) if ndir > 1 else bias[0]
-    if persist:
-        perm, _ = gate_perm(H, ndir, dev)
-        wcat, bcat = wcat.index_select(0, perm), bcat.index_select(0, perm)
-    wcat_bf = cvt_bf16(wcat, ld_dst=Dp)                                            # [ndir*4H, Dp]
+    w_ih, w_hh, b_ih, b_hh = list(w_ih), list(w_hh), list(b_ih), list(b_hh)
+    persist, wcat_bf, bcat, whh_pk = _prep("lstm_fwd", w_ih + w_hh + b_ih + b_hh,
+                                           lambda: _build_lstm_fwd(w_ih, w_hh, b_ih, b_hh, Dp))
+    assert wcat_bf.shape[1] == Dp
     xproj = gemm(xin, Dp, 0, wcat_bf, Dp, 0, B * T, ndir * 4 * H, Dp, bias=bcat)   # f32 [B*T, ndir*4H]
     y = torch.zeros(B, Tp, ndir * H, device=dev, dtype=BF16)
     hprev = torch.empty(B, T, ndir * H, device=dev, dtype=BF16)
     if persist:
-        whh_pk = torch.cat([pack_afrag(w, 3, H) for w in w_hh])
         rec = torch.empty(ndir * B * T * H, 4, device=dev, dtype=torch.int32)
         call("las_lstm_persist_fwd", ptr(xproj), ptr(whh_pk), ptr(lens), B, T, H, ndir, ptr(y), Tp * ndir * H, ndir * H,
              rep, ptr(hprev), T * ndir * H, ndir * H, ptr(rec))
         act = (rec,)
     else:
-        whh_pk = torch.cat([pack_afrag(w, 1, H) for w in w_hh])
         gates = torch.empty(ndir, B, T, H, 4, device=dev, dtype=torch.float16)
         csave = torch.empty(ndir, B, T, H, device=dev, dtype=torch.float32)
         ws = torch.empty(_lib.lib().las_lstm_ws_bytes(B, H, ndir), device=dev, dtype=torch.uint8)
@@ -284,12 +353,12 @@ def lstm_layer_bwd(saved, w_hh, dy, need_dx=True):
     dev = dy.device
     G = ndir * 4 * H
     dG = torch.empty(B * T, G, device=dev, dtype=BF16)
+    w_hh = list(w_hh)
+    whhT = _prep("lstm_bwd", w_hh, lambda: _build_lstm_bwd(w_hh))
     if persist:
-        whhT = torch.cat([pack_whhT(w)[0] for w in w_hh])
         call("las_lstm_persist_bwd", ptr(dy), Tp * ndir * H, ndir * H, rep, ptr(whhT), ptr(lens), B, T, H, ndir,
              ptr(act[0]), ptr(dG), T * G, G)
     else:
-        whhT = torch.cat([pack_afrag(w, 0, transposed=True) for w in w_hh])
         ws = torch.empty(ndir * B * H, device=dev, dtype=torch.float32)
         call("las_lstm_seq_bwd", ptr(dy), Tp * ndir * H, ndir * H, rep, ptr(whhT), 0, ptr(lens), B, T, H, ndir,
              ptr(act[0]), ptr(act[1]), ptr(dG), T * G, G, ptr(ws))
@@ -339,7 +408,7 @@ class EncoderFn(torch.autograd.Function):
             H = w_hh.shape[1]
             Tp = T + (T % 2) if sub > 1 else T
             rep = int(sub > 1 and T % 2 == 1)
-            y, lsaved = lstm_layer_fwd(xin, Dp, [w_ih, w_ih_r], [w_hh, w_hh_r], [b_ih + b_hh, b_ih_r + b_hh_r], cur_lens,
+            y, lsaved = lstm_layer_fwd(xin, Dp, [w_ih, w_ih_r], [w_hh, w_hh_r], [b_ih, b_ih_r], [b_hh, b_hh_r], cur_lens,
                                        B, T, Tp, rep)
             if p_drop > 0:      # model.py:82 (before the replicate pad of an odd extent: the extra row shares its mask)
                 dropout_(y, B, T, 2 * H, Tp * 2 * H, 2 * H, rep, p_drop, site0 + 2 * i)
@@ -347,7 +416,7 @@ class EncoderFn(torch.autograd.Function):
                 T2, Kp = Tp // 2, 4 * H
             else:
                 T2, Kp = T, 2 * H
-            wp = cvt_bf16(proj_w)                                                   # [H, Kp]
+            wp = _prep("cvt", [proj_w], lambda: cvt_bf16(proj_w))                   # [H, Kp]
             out = gemm(y, Kp, 0, wp, Kp, 0, B * T2, proj_w.shape[0], Kp, out_bf16=True, bias=proj_b, relu=True)
             if p_drop > 0:      # model.py:95 (all rows, incl. the relu(bias) rows past each length)
                 dropout_(out, B * T2, 1, proj_w.shape[0], proj_w.shape[0], proj_w.shape[0], 0, p_drop, site0 + 2 * i + 1)
@@ -425,6 +494,75 @@ def _dec_common(enc_h, W, L, K):
     return a, (B, Te, H, Hd, O, A, V, E, C)
 
 
+def _build_dec_fwd(W, mode):
+    """Weight-only operands of the decoder forward (see prepare_ahead)."""
+    V, E = W["emb_w"].shape
+    Hd = W["w_hh"].shape[1]
+    C = W["conv_w"].shape[0]
+    Ep = _r16(E)
+    d = {}
+    d["mlp_enc_bf"] = cvt_bf16(W["mlp_enc_w"])
+    d["wr_cat"] = torch.cat([W["w_hh"], W["w_ih"][:, E:]], dim=1).contiguous()      # [4Hd, Hd+O]
+    d["wr_pk"] = pack_afrag(d["wr_cat"], 1, Hd)
+    d["mlp_dec_pk"] = pack_afrag(W["mlp_dec_w"], 0)
+    d["mlp_o_pk"] = pack_afrag(W["mlp_o_w"], 0)
+    d["cell_bias"] = (W["b_ih"] + W["b_hh"]).contiguous()
+    d["conv_w"] = W["conv_w"].reshape(C, -1).contiguous()
+    d["mlp_att"] = W["mlp_att_w"].contiguous()
+    d["gvec"] = W["gvec_w"].reshape(-1).contiguous()
+    we = W["w_ih"][:, :E]
+    d["we_bf"] = cvt_bf16(we, ld_dst=Ep)
+    if mode != 0:
+        d["we_pk"] = pack_afrag(we.contiguous(), 1, Hd)
+        d["out_pk"] = pack_afrag(W["out_w"], 0)
+    elif DEC_PERSISTENT:
+        d["mlp_o_bf"] = cvt_bf16(W["mlp_o_w"])
+        d["wr2_pk"] = pack_afrag(d["wr_cat"], 2, Hd)
+    d["out_bf"] = cvt_bf16(W["out_w"])
+    return d
+
+
+def _build_dec_bwd(W, mode, wr_cat, persistent):
+    """Weight-only operands of the decoder backward."""
+    V, E = W["emb_w"].shape
+    Hd = W["w_hh"].shape[1]
+    O, A = W["mlp_o_w"].shape[0], W["mlp_enc_w"].shape[0]
+    dev = wr_cat.device
+    d = {}
+    d["wrT_pk"] = pack_afrag(wr_cat, 0, transposed=True)
+    d["mlp_oT_pk"] = pack_afrag(W["mlp_o_w"], 0, transposed=True)
+    d["mlp_decT_pk"] = pack_afrag(W["mlp_dec_w"], 0, transposed=True)
+    if mode == 2:
+        d["weT_pk"] = pack_afrag(W["w_ih"][:, :E].contiguous(), 0, transposed=True)
+        d["outT_pk"] = pack_afrag(W["out_w"], 0, transposed=True)
+    if persistent:
+        L_ = _lib.lib()
+        ZC = Hd + O
+        wrT2 = torch.empty(L_.las_dec_persistent_pack_bytes(0, Hd, O, A) // 4, device=dev, dtype=torch.int32)
+        call("las_dec_persistent_pack", 0, ptr(wr_cat), ZC, Hd, O, A, ptr(wrT2))
+        mlp_dec_w = W["mlp_dec_w"].contiguous()
+        decT2 = torch.empty(L_.las_dec_persistent_pack_bytes(1, Hd, O, A) // 4, device=dev, dtype=torch.int32)
+        call("las_dec_persistent_pack", 1, ptr(mlp_dec_w), Hd, Hd, O, A, ptr(decT2))
+        d["wrT2"], d["decT2"] = wrT2, decT2
+    return d
+
+
+def decoder_prep_jobs(wts, mode):
+    """prepare_ahead jobs of the decoder: forward operands; backward packs for the teacher-forced persistent path."""
+    wts = list(wts)
+    W = dict(zip(DEC_WEIGHTS, wts))
+    jobs = [("dec_fwd%d" % mode, wts, lambda: _build_dec_fwd(W, mode))]
+    Hd, O, A = W["w_hh"].shape[1], W["mlp_o_w"].shape[0], W["mlp_enc_w"].shape[0]
+    L_ = _lib.lib()
+    packable = L_.las_dec_persistent_pack_bytes(0, Hd, O, A) > 0 and L_.las_dec_persistent_pack_bytes(1, Hd, O, A) > 0
+    if mode == 0 and DEC_PERSISTENT and packable:
+        def bwd():
+            wr_cat = torch.cat([W["w_hh"], W["w_ih"][:, W["emb_w"].shape[1]:]], dim=1).contiguous()
+            return _build_dec_bwd(W, mode, wr_cat, True), wr_cat
+        jobs.append(("dec_bwd%d_p" % mode, wts, bwd))
+    return jobs
+
+
 class DecoderFn(torch.autograd.Function):
     """Runs all L decoder steps. Returns (logits_alloc f32 [B, L+1, V] (row r = step r-1; row 0
     unused), ws_alloc f32 [B, L+1, Te] (row 0 = initial alignment), pred int64 [B, L] or None)."""
@@ -442,15 +580,13 @@ class DecoderFn(torch.autograd.Function):
         if p_drop > 0:                                 # cell-input dropout (model.py:285)
             a.drop_p, a.drop_site, a.seed_dev = float(p_drop), site0, ptr(dropout_seed(dev))
 
+        wts = list(wts)
+        Pk = _prep("dec_fwd%d" % mode, wts, lambda: _build_dec_fwd(W, mode))
         enc_bf = cvt_bf16(enc_h.reshape(B * Te, H))
-        mlp_enc_bf = cvt_bf16(W["mlp_enc_w"])
+        mlp_enc_bf = Pk["mlp_enc_bf"]
         Pm = gemm(enc_bf, H, 0, mlp_enc_bf, H, 0, B * Te, A, H, bias=W["mlp_enc_b"])
-        wr_cat = torch.cat([W["w_hh"], W["w_ih"][:, E:]], dim=1).contiguous()        # [4Hd, Hd+O]
-        wr_pk = pack_afrag(wr_cat, 1, Hd)
-        mlp_dec_pk = pack_afrag(W["mlp_dec_w"], 0)
-        mlp_o_pk = pack_afrag(W["mlp_o_w"], 0)
-        cell_bias = (W["b_ih"] + W["b_hh"]).contiguous()
-        we = W["w_ih"][:, :E]
+        wr_cat, wr_pk, mlp_dec_pk, mlp_o_pk = Pk["wr_cat"], Pk["wr_pk"], Pk["mlp_dec_pk"], Pk["mlp_o_pk"]
+        cell_bias = Pk["cell_bias"]
         ws = torch.zeros(B, R, Te, **f32)
         call("las_att_init", ptr(enc_lens), B, Te, ptr(ws), R * Te)
         zc = torch.zeros(B * R * ZC + 64, device=dev, dtype=BF16)
@@ -460,9 +596,7 @@ class DecoderFn(torch.autograd.Function):
         dzf = torch.empty(B, L, A, **f32)
         gates = torch.empty(B, L, Hd, 4, device=dev, dtype=torch.float16)
         csave = torch.empty(B, L, Hd, **f32)
-        conv_w = W["conv_w"].reshape(C, -1).contiguous()
-        mlp_att = W["mlp_att_w"].contiguous()
-        gvec = W["gvec_w"].reshape(-1).contiguous()
+        conv_w, mlp_att, gvec = Pk["conv_w"], Pk["mlp_att"], Pk["gvec"]
         a.enc_h, a.P = ptr(enc_bf), ptr(Pm)
         a.wr_pk, a.mlp_dec_pk, a.mlp_o_pk, a.mlp_o_b = ptr(wr_pk), ptr(mlp_dec_pk), ptr(mlp_o_pk), ptr(W["mlp_o_b"])
         a.conv_w, a.mlp_att, a.gvec = ptr(conv_w), ptr(mlp_att), ptr(gvec)
@@ -477,13 +611,12 @@ class DecoderFn(torch.autograd.Function):
             call("las_gather_rows_bf16", ptr(W["emb_w"]), E, ptr(ys_in), B * R, ptr(emb_in), Ep)
             if p_drop > 0:
                 dropout_(emb_in, B, R, E, R * Ep, Ep, 0, p_drop, site0 + 1)
-            we_bf = cvt_bf16(we, ld_dst=Ep)
+            we_bf = Pk["we_bf"]
             embx = gemm(emb_in, Ep, 0, we_bf, Ep, 0, B * R, 4 * Hd, Ep, bias=cell_bias)
             a.embx = ptr(embx)
             keep += [embx, we_bf]
         else:
-            we_pk = pack_afrag(we.contiguous(), 1, Hd)
-            out_pk = pack_afrag(W["out_w"], 0)
+            we_pk, out_pk = Pk["we_pk"], Pk["out_pk"]
             emb_op = torch.zeros(B * R * Ep + 64, device=dev, dtype=BF16)
             bos_row = torch.zeros(Ep, **f32)
             bos_row[:E] = W["emb_w"][bos]
@@ -501,7 +634,7 @@ class DecoderFn(torch.autograd.Function):
             # Q is stored centred over the frames of each utterance (the mean goes into a per-utterance
             # bias): bf16 rounding then applies to the deviations, which is what the softmax backward
             # (dw - <w, dw>, a cancellation when the alignment is flat) actually consumes
-            mlp_o_bf = cvt_bf16(W["mlp_o_w"])
+            mlp_o_bf = Pk["mlp_o_bf"]
             Qf = gemm(enc_bf, H, 0, mlp_o_bf, H, 0, B * Te, O, H).view(B, Te, O)
             Qbar = Qf.mean(dim=1, keepdim=True)
             Qm = (Qf - Qbar).to(BF16).view(B * Te, O)
@@ -509,7 +642,7 @@ class DecoderFn(torch.autograd.Function):
             # likewise P = mlp_enc(enc_h): the kernels hold P - mean_te(P) in bf16 and add the mean to dz in f32
             Pbar = Pm.view(B, Te, A).mean(dim=1)
             Pc = (Pm.view(B, Te, A) - Pbar.unsqueeze(1)).contiguous()
-            wr2_pk = pack_afrag(wr_cat, 2, Hd)
+            wr2_pk = Pk["wr2_pk"]
             a.Q, a.wr2_pk, a.cbias, a.pbar = ptr(Qm), ptr(wr2_pk), ptr(cbias), ptr(Pbar)
             persist = bool(_lib.lib().las_dec_persistent_supported(ctypes.byref(a)))
             if persist:
@@ -525,14 +658,14 @@ class DecoderFn(torch.autograd.Function):
             a.zcd = ptr(zcd)
             keep.append(zcd)
         _lib.check(_lib.lib().las_dec_fwd(ctypes.byref(a), _lib.stream_ptr()))
-        out_bf = cvt_bf16(W["out_w"])                                                 # [V, ZC]
+        out_bf = Pk["out_bf"]                                                         # [V, ZC]
         if mode == 0:
             logits = gemm(zc, ZC, 0, out_bf, ZC, 0, B * R, V, ZC, bias=W["out_b"]).view(B, R, V)
         ctx.geom = (B, Te, H, Hd, O, A, V, E, C, K, L, mode, att_scaling, smooth_scaling)
         ctx.drop = (float(p_drop), site0)
         ctx.saved = dict(enc_bf=enc_bf, Pm=Pm, mlp_enc_bf=mlp_enc_bf, wr_cat=wr_cat, ws=ws, zc=zc, cx=cx, dzf=dzf,
                          gates=gates, csave=csave, conv_w=conv_w, mlp_att=mlp_att, gvec=gvec, emb_in=emb_in,
-                         out_bf=out_bf, ys_in=ys_in, keep=keep, pers=pers, bos=bos,
+                         out_bf=out_bf, ys_in=ys_in, keep=keep, pers=pers, bos=bos, we_bf=Pk["we_bf"], Pk=Pk,
                          logits=logits if mode != 0 else None,
                          emb_op=(emb_op[:B * R * Ep].view(B * R, Ep) if mode != 0 else None))
         ctx.W = W
@@ -566,18 +699,22 @@ class DecoderFn(torch.autograd.Function):
             Vq = (V + 3) // 4 * 4
             dl_tot = torch.zeros(n * Vq + 64, **f32)
             dzc_all = torch.zeros(n, ZC, **f32)
-            weT_pk = pack_afrag(W["w_ih"][:, :E].contiguous(), 0, transposed=True)
-            outT_pk = pack_afrag(W["out_w"], 0, transposed=True)
             demb_buf = torch.empty(B, Ep, **f32)
-            a.weT_pk, a.outT_pk, a.dlogits, a.dl_tot, a.demb_buf = ptr(weT_pk), ptr(outT_pk), ptr(dl), ptr(dl_tot), ptr(demb_buf)
+            a.dlogits, a.dl_tot, a.demb_buf = ptr(dl), ptr(dl_tot), ptr(demb_buf)
             a.logits, a.emb_w = ptr(S["logits"]), ptr(W["emb_w"])
         else:
             dl_bf = cvt_bf16(dl)                                                      # [n, Vp]
             Vp = dl_bf.shape[1]
             dzc_all = gemm(dl_bf, Vp, 0, S["out_bf"], ZC, 1, n, ZC, V)                # f32 [n, ZC]
-        wrT_pk = pack_afrag(S["wr_cat"], 0, transposed=True)
-        mlp_oT_pk = pack_afrag(W["mlp_o_w"], 0, transposed=True)
-        mlp_decT_pk = pack_afrag(W["mlp_dec_w"], 0, transposed=True)
+        pers = S["pers"]
+        wts = list(ctx.wts)
+        if mode == 0 and pers is not None:
+            Bk, _ = _prep("dec_bwd%d_p" % mode, wts, lambda: (_build_dec_bwd(W, mode, S["wr_cat"], True), S["wr_cat"]))
+        else:
+            Bk = _build_dec_bwd(W, mode, S["wr_cat"], pers is not None)
+        wrT_pk, mlp_oT_pk, mlp_decT_pk = Bk["wrT_pk"], Bk["mlp_oT_pk"], Bk["mlp_decT_pk"]
+        if mode == 2:
+            a.weT_pk, a.outT_pk = ptr(Bk["weT_pk"]), ptr(Bk["outT_pk"])
         dcz_tot = torch.empty(B, ZC, **f32)
         dcz_all = torch.zeros(n, ZC, device=dev, dtype=BF16)
         dctx_all = torch.empty(B, L, H, **f32)
@@ -604,16 +741,11 @@ class DecoderFn(torch.autograd.Function):
         a.dgates, a.dmlp_att, a.dgvec, a.dconv_w, a.denc = (ptr(dgates), ptr(d_mlp_att), ptr(d_gvec), ptr(d_conv),
                                                             ptr(denc))
         a.denc_accumulate = 0
-        pers = S["pers"]
         if pers is not None:
             # cluster-persistent backward: the serial loop only produces per-step gradients; every
             # parameter gradient is reduced afterwards by the GEMMs / parallel kernels below
             L_ = _lib.lib()
-            wrT2 = torch.empty(L_.las_dec_persistent_pack_bytes(0, Hd, O, A) // 4, device=dev, dtype=torch.int32)
-            call("las_dec_persistent_pack", 0, ptr(S["wr_cat"]), ZC, Hd, O, A, ptr(wrT2))
-            mlp_dec_w = W["mlp_dec_w"].contiguous()
-            decT2 = torch.empty(L_.las_dec_persistent_pack_bytes(1, Hd, O, A) // 4, device=dev, dtype=torch.int32)
-            call("las_dec_persistent_pack", 1, ptr(mlp_dec_w), Hd, Hd, O, A, ptr(decT2))
+            wrT2, decT2 = Bk["wrT2"], Bk["decT2"]
             de_all = torch.zeros(B, L, Te, **f32)
             dc_all = torch.zeros(B, L, O, **f32)
             a.Q, a.wr2_pk, a.cpre, a.conv_save = ptr(pers["Qm"]), ptr(pers["wr2_pk"]), ptr(pers["cpre"]), ptr(pers["conv_save"])
@@ -661,7 +793,7 @@ class DecoderFn(torch.autograd.Function):
             d_w_ih = torch.cat([d_we[:, :E], d_wr[:, Hd:]], dim=1)
             d_w_hh = d_wr[:, :Hd].contiguous()
             d_b = colsum(dgates, 4 * Hd)
-            we_bf = cvt_bf16(W["w_ih"][:, :E], ld_dst=Ep)
+            we_bf = S["we_bf"]
             demb_rows = gemm(dgates, 4 * Hd, 0, we_bf, Ep, 1, n, Ep, 4 * Hd)              # f32 [n, Ep]
             if p_drop > 0:                                 # gradient w.r.t. the un-dropped step embeddings
                 dropout_(demb_rows, B, R, E, R * Ep, Ep, 0, p_drop, site0 + 1)
@@ -760,7 +892,7 @@ class LMFn(torch.autograd.Function):
         for l in range(n_layers):
             w_ih, w_hh, b_ih, b_hh = wts[1 + 4 * l:5 + 4 * l]
             H = w_hh.shape[1]
-            y, lsaved = lstm_layer_fwd(xin, Dp, [w_ih], [w_hh], [b_ih + b_hh], lens, B, Lm, Lm, 0)
+            y, lsaved = lstm_layer_fwd(xin, Dp, [w_ih], [w_hh], [b_ih], [b_hh], lens, B, Lm, Lm, 0)
             y = y.view(n, H)
             saved.append(lsaved)
             if p_drop > 0:                            # nn.LSTM(dropout=p) between layers (model.py:466) and model.py:520 on top

@@ -40,6 +40,17 @@ class pBLSTM(torch.nn.Module):
                   layer.bias_hh_l0_reverse, proj.weight, proj.bias]
         return w
 
+    def prep_jobs(self):
+        """Weight-preparation jobs of this encoder for functional.prepare_ahead, in the order the step needs them."""
+        w = self._weights()
+        jobs = []
+        for i in range(len(self.layers)):
+            w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r, proj_w, _ = w[10 * i:10 * i + 10]
+            Dp = (w_ih.shape[1] + 7) // 8 * 8
+            jobs += Fn.lstm_prep_jobs([w_ih, w_ih_r], [w_hh, w_hh_r], [b_ih, b_ih_r], [b_hh, b_hh_r], Dp)
+            jobs.append(("cvt", [proj_w], (lambda pw: (lambda: Fn.cvt_bf16(pw)))(proj_w)))
+        return jobs
+
     def forward(self, xpad, ilens):
         xpad = cc(xpad).float()
         host_lens = [int(l) for l in (ilens.tolist() if torch.is_tensor(ilens) else ilens)]
@@ -173,6 +184,9 @@ class Decoder(torch.nn.Module):
             ys_in_dev, ys_out_dev = None, None
             mode = 2 if smooth else 1
         return self.forward_dev(enc_pad, enc_lens_dev, ys_in_dev, ys_out_dev, L, mode, scaling, label_smoothing)
+
+    def prep_jobs(self, mode=0):
+        return Fn.decoder_prep_jobs(self._weights(), mode)
 
     def forward_dev(self, enc_pad, enc_lens_dev, ys_in_dev, ys_out_dev, L, mode, scaling=1.0, label_smoothing=True):
         """Device-resident variant (CUDA-graph capturable). ys_in_dev int64 [B, L+1] = [BOS, y, EOS.., PAD],
