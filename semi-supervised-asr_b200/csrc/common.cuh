@@ -52,6 +52,31 @@ __device__ __forceinline__ float tanh_acc(float x) {
   return 1.0f - __fdividef(2.0f, e + 1.0f);
 }
 
+// argmax with torch.argmax's conventions: first maximal index; NaN counts as the maximum (first NaN wins). Always
+// returns an index in [0, V): an all-NaN row (a diverged model) must not turn into an out-of-range token id.
+__device__ __forceinline__ bool argmax_better(float av, int ai, float bv, int bi) {
+  const bool an = av != av, bn = bv != bv;
+  if (an != bn) return an;
+  if (an) return ai < bi;
+  return av > bv || (av == bv && ai < bi);
+}
+__device__ __forceinline__ int warp_argmax(const float* __restrict__ x, int V, int lane, float* max_out) {
+  float mx = -INFINITY;
+  int amax = 0x7fffffff;
+  for (int v = lane; v < V; v += 32) {
+    const float xv = x[v];
+    if (argmax_better(xv, v, mx, amax)) { mx = xv; amax = v; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, amax, o);
+    if (argmax_better(om, oa, mx, amax)) { mx = om; amax = oa; }
+  }
+  if (max_out) *max_out = mx;
+  return amax < V ? amax : 0;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

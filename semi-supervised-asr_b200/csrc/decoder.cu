@@ -220,18 +220,8 @@ __global__ void __launch_bounds__(128) next_emb_kernel(NextEmbParams p) {
   const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (b >= p.B) return;
   const float* x = p.logits + b * p.lg_ld;
-  float mx = -INFINITY;
-  int amax = 0x7fffffff;
-  for (int v = lane; v < p.V; v += 32) {
-    const float xv = x[v];
-    if (xv > mx) { mx = xv; amax = v; }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float om = __shfl_xor_sync(0xffffffffu, mx, o);
-    const int oa = __shfl_xor_sync(0xffffffffu, amax, o);
-    if (om > mx || (om == mx && oa < amax)) { mx = om; amax = oa; }
-  }
+  float mx;
+  const int amax = warp_argmax(x, p.V, lane, &mx);
   if (lane == 0) p.pred[b * p.pred_ld] = amax;
   const unsigned long long seed = p.drop_p > 0.f ? *p.seed_dev : 0ull;
   auto drop = [&](float v, int j) {
@@ -557,9 +547,93 @@ __global__ void att_dconv_reduce_kernel(const float* __restrict__ partial, int n
   for (int k = 0; k < ncta; ++k) s += partial[static_cast<int64_t>(k) * n + i];
   dconv_w[i] += s;
 }
+// Tensor-core variant: for one (t, b) the conv-weight gradient is D[c][k] = sum_te X[te][c] w[te + k - K], i.e.
+// A = X^T (16 channels x Te) times the Toeplitz matrix of the alignment. A CTA walks (t, b) pairs, stages X^T and the
+// zero-padded alignment as bf16 in shared memory (the alignment twice, once shifted by one element, so that the
+// two consecutive taps of a B-fragment word are one aligned 32-bit load for either parity), and keeps D in the
+// accumulators of its 8 warps (warp w owns the 8-tap tiles w, w+8, ...). partial[cta][c][k] is reduced afterwards
+// in a fixed order (att_dconv_reduce_kernel). bf16 operands, f32 accumulation.
+__global__ void __launch_bounds__(256) att_dconv_mma_kernel(const float* __restrict__ dattc_all,
+                                                            const float* __restrict__ ws_alloc, int L, int B, int Te,
+                                                            int C, int K, int KT, int NT, float* __restrict__ partial) {
+  extern __shared__ __align__(16) uint8_t dsm[];
+  const int a_ld = KT * 16 + 8;                                  // bf16 elements per channel row (word stride = 4 mod 32)
+  const int wlen = KT * 16 + NT * 8 + 16;                        // padded alignment, wpad[i] = w[i - K]
+  const int wwords = (wlen / 2 + 31) / 32 * 32 + 16;             // second array lands 16 banks away from the first
+  __nv_bfloat16* A_s = reinterpret_cast<__nv_bfloat16*>(dsm);    // [16][a_ld]
+  uint32_t* wE = reinterpret_cast<uint32_t*>(dsm + 16 * a_ld * 2);   // wE[m] = (wpad[2m], wpad[2m+1])
+  uint32_t* wO = wE + wwords;                                        // wO[m] = (wpad[2m+1], wpad[2m+2])
+  const int ksz = 2 * K + 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tig = lane & 3;
+  float acc[4][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[j][c] = 0.f;
+  for (int i = threadIdx.x; i < 16 * a_ld; i += 256) A_s[i] = __float2bfloat16(0.f);
+  const uint32_t* wl = ((g & 1) ? wO : wE) + ((2 * tig + g - (g & 1)) >> 1);
+  const uint32_t* a0p = reinterpret_cast<const uint32_t*>(A_s + g * a_ld) + tig;
+  const uint32_t* a1p = reinterpret_cast<const uint32_t*>(A_s + (g + 8) * a_ld) + tig;
+  const int n_items = L * B;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int t = item / B, b = item - t * B;
+    __syncthreads();                                               // previous item's fragments are consumed
+    const float* src = dattc_all + (static_cast<int64_t>(t) * B + b) * Te * C;
+    for (int i = threadIdx.x; i < Te * C; i += 256) {
+      const int te = i / C, c = i - te * C;
+      A_s[c * a_ld + te] = __float2bfloat16(src[i]);
+    }
+    const float* wrow = ws_alloc + (static_cast<int64_t>(b) * (L + 1) + t) * Te;
+    for (int m = threadIdx.x; m < wlen / 2; m += 256) {
+      float v[3];
+#pragma unroll
+      for (int e = 0; e < 3; ++e) {
+        const int j = 2 * m + e - K;
+        v[e] = (j >= 0 && j < Te) ? wrow[j] : 0.f;
+      }
+      wE[m] = pack_bf16x2(v[0], v[1]);
+      wO[m] = pack_bf16x2(v[1], v[2]);
+    }
+    __syncthreads();
+    for (int kt = 0; kt < KT; ++kt) {
+      const uint32_t Af[4] = {a0p[8 * kt], a1p[8 * kt], a0p[8 * kt + 4], a1p[8 * kt + 4]};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int nt = warp + 8 * j;
+        if (nt < NT) mma_bf16_16816(acc[j], Af, wl[8 * kt + 4 * nt], wl[8 * kt + 4 * nt + 4]);
+      }
+    }
+  }
+  float* out = partial + static_cast<int64_t>(blockIdx.x) * C * ksz;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int nt = warp + 8 * j;
+    if (nt >= NT) continue;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int c = g + 8 * (e >> 1), k = 8 * nt + 2 * tig + (e & 1);
+      if (c < C && k < ksz) out[c * ksz + k] = acc[j][e];
+    }
+  }
+}
+
 static int launch_att_dconv(const float* dattc_all, const float* ws_alloc, int L, int B, int Te, int C, int K,
                             float* dconv_w, float* partial_ws, cudaStream_t stream) {
   const int ksz = 2 * K + 1;
+  {
+    const int KT = (Te + 15) / 16, NT = (ksz + 7) / 8;
+    const int a_ld = KT * 16 + 8, wlen = KT * 16 + NT * 8 + 16, wwords = (wlen / 2 + 31) / 32 * 32 + 16;
+    const size_t smem = static_cast<size_t>(16) * a_ld * 2 + static_cast<size_t>(2) * wwords * 4;
+    if (NT <= 32 && smem <= 48 * 1024) {
+      // as many partial slots as the scratch was sized for (las_att_scratch_floats): ceil(L/kDT) * B
+      int ncta = ((L + kDT - 1) / kDT) * B;
+      if (ncta > L * B) ncta = L * B;
+      if (ncta > 4 * num_sms()) ncta = 4 * num_sms();
+      att_dconv_mma_kernel<<<ncta, 256, smem, stream>>>(dattc_all, ws_alloc, L, B, Te, C, K, KT, NT, partial_ws); ++g_launches;
+      att_dconv_reduce_kernel<<<(C * ksz + 255) / 256, 256, 0, stream>>>(partial_ws, ncta, C * ksz, dconv_w); ++g_launches;
+      return 0;
+    }
+  }
   LAS_REQUIRE(ksz <= 256, "att_dconv: conv kernel of %d taps is wider than 256", ksz);
   const dim3 grid((L + kDT - 1) / kDT, B);
   const size_t smem = (Te + 2 * K + static_cast<size_t>(Te) * C) * sizeof(float);

@@ -117,18 +117,8 @@ __global__ void ce_ls_fwd_kernel(const float* __restrict__ logits, int64_t ld, i
   const int64_t r = blockIdx.x * static_cast<int64_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= rows) return;
   const float* x = logits + (r / rows_per_b) * ld_b + (r % rows_per_b) * ld;
-  float mx = -INFINITY;
-  int amax = 0x7fffffff;
-  for (int v = lane; v < V; v += 32) {
-    const float xv = x[v];
-    if (xv > mx) { mx = xv; amax = v; }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float om = __shfl_xor_sync(0xffffffffu, mx, o);
-    const int oa = __shfl_xor_sync(0xffffffffu, amax, o);
-    if (om > mx || (om == mx && oa < amax)) { mx = om; amax = oa; }
-  }
+  float mx;
+  const int amax = warp_argmax(x, V, lane, &mx);
   float se = 0.f;
   for (int v = lane; v < V; v += 32) se += expf(x[v] - mx);
   se = warp_sum(se);
@@ -172,12 +162,7 @@ __global__ void ce_ls_bwd_kernel(const float* __restrict__ logits, int64_t ld, i
   if (targets) {
     y = targets[r];
   } else {  // free-running decode gathers at the row's own argmax (first maximal index)
-    int amax = 0x7fffffff;
-    for (int v = lane; v < V; v += 32)
-      if (x[v] == mx && v < amax) amax = v;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) amax = min(amax, __shfl_xor_sync(0xffffffffu, amax, o));
-    y = amax;
+    y = warp_argmax(x, V, lane, nullptr);
   }
   const float g = g_logp ? g_logp[r] : 0.f;
   const float py = expf(x[y] - mx) * inv;

@@ -7,6 +7,8 @@ Data parallelism (one process per GPU): every rank runs the same step on its sha
 gradient buffer is summed with ONE NCCL all-reduce between backward and the optimiser, and the
 update uses grad_scale = 1/world_size (DDP averaging). There is no other exchange on this path.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -66,7 +68,7 @@ class SupervisedTrainer:
         self.model = model
         self.opt = optimizer
         self.max_grad_norm = max_grad_norm
-        self.use_graph = use_graph
+        self.use_graph = use_graph and os.environ.get("LAS_NO_GRAPH", "0") != "1"   # debugging switch
         self.pg = process_group
         self.world = 1
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
@@ -76,6 +78,7 @@ class SupervisedTrainer:
         self.update_graph, self.update_norm = None, None
         self.cap_stream = None
         self.copy_stream = None
+        self.rb_dev, self.rb_host = None, None
 
     # ---- the step body: everything below runs on the current stream, no host sync
     def _fwd_bwd(self, st, L):
@@ -224,19 +227,53 @@ class SupervisedTrainer:
         sl.consumed.record(main)
         return self.run(key)
 
-    def steps(self, batches):
+    def _readback(self, out, k):
+        """Snapshot (loss, grad_norm) of the step just enqueued and start their D2H copy on the copy stream.
+        Returns (host_pair [2] pinned f32, event)."""
+        loss, norm = out
+        dev = loss.device
+        if self.rb_dev is None:
+            self.rb_dev = torch.zeros(4, 2, device=dev, dtype=torch.float32)
+            self.rb_host = torch.zeros(4, 2, dtype=torch.float32).pin_memory()
+        main = torch.cuda.current_stream(dev)
+        self.rb_dev[k, 0].copy_(loss.reshape(()), non_blocking=True)   # the static outputs are overwritten by the next replay
+        self.rb_dev[k, 1].copy_(torch.as_tensor(norm, device=dev).reshape(()).float(), non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(main)
+        cs = self.copy_stream
+        cs.wait_event(done)
+        with torch.cuda.stream(cs):
+            self.rb_host[k].copy_(self.rb_dev[k], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(cs)
+        return self.rb_host[k], ev
+
+    def steps(self, batches, lag=1):
         """Train on an iterable of host batches (xs [B, T, D] ideally pinned, ilens, ys); yields (loss, grad_norm)
-        device tensors per batch. While step i runs on the GPU the inputs of batch i+1 are already being copied."""
+        per batch as HOST scalars (0-dim CPU tensors), in order. Two overlaps: the host->device copy of batch i+1
+        runs during step i, and the results of step i are read back on the copy stream and handed out only after
+        step i+`lag` has been enqueued, so the GPU never waits for the host between steps."""
+        import collections
         it = iter(batches)
         nxt = next(it, None)
-        k = 0
+        k, n = 0, 0
         handle = self.upload(*nxt, k) if nxt is not None else None
+        pending = collections.deque()
         while handle is not None:
             out = self.run_uploaded(handle)            # asynchronous: returns as soon as the step is enqueued
+            pending.append(self._readback(out, n % 4))
+            n += 1
             nxt = next(it, None)
             k ^= 1
             handle = self.upload(*nxt, k) if nxt is not None else None
-            yield out
+            if len(pending) > lag:
+                host, ev = pending.popleft()
+                ev.synchronize()
+                yield host[0].clone(), host[1].clone()
+        while pending:
+            host, ev = pending.popleft()
+            ev.synchronize()
+            yield host[0].clone(), host[1].clone()
 
 
 def _clip_and_step(opt, params, max_grad_norm):
@@ -270,7 +307,8 @@ class SSLTrainer:
     `.grad` fields (dis_opt never steps in this phase)."""
 
     def __init__(self, model, judge, optimizer, max_grad_norm=5.0, unsup_weight=0.001, proportion=0.125,
-                 smooth=True, scaling=3.0):
+                 smooth=True, scaling=3.0, guard_empty_mask=True):
+        self.guard_empty_mask = guard_empty_mask
         self.model, self.judge, self.opt = model, judge, optimizer
         self.max_grad_norm, self.unsup_weight, self.proportion = max_grad_norm, unsup_weight, proportion
         self.smooth, self.scaling = smooth, scaling
@@ -279,12 +317,30 @@ class SSLTrainer:
         m = self.model
         (xs, ilens, ys), (uxs, uilens) = lab, unlab
         Lu = int(uxs.size(1) * self.proportion)                                    # solver.py:469
+        if os.environ.get("LAS_DEBUG_SSL"):
+            torch.cuda.synchronize()
+            print(f"[ssl] lab x {tuple(xs.shape)} ilens {list(ilens)} ylens {[len(y) for y in ys]} | unlab x {tuple(uxs.shape)} "
+                  f"uilens {list(uilens)} Lu {Lu}", flush=True)
         _, u_logp, u_pred, _ = m(uxs, uilens, ys=None, sample=False, label_smoothing=False, max_dec_timesteps=Lu,
                                  smooth=self.smooth, scaling=self.scaling)
+        dbg = os.environ.get("LAS_DEBUG_SSL")
+        if dbg:
+            torch.cuda.synchronize()
+            print(f"[ssl] free-run ok: pred range {int(u_pred.min())}..{int(u_pred.max())} shape {tuple(u_pred.shape)} "
+                  f"logp finite {bool(torch.isfinite(u_logp).all())}", flush=True)
         with torch.no_grad():
             _, lm_probs, _ = self.judge(ys=u_pred, discrete_input=False)           # solver.py:473
+        if dbg:
+            torch.cuda.synchronize()
+            print(f"[ssl] judge ok: finite {bool(torch.isfinite(lm_probs).all())}", flush=True)
         mask = (u_pred != m.decoder.eos).float()                                    # solver.py:477
-        unsup = -torch.sum(lm_probs * u_logp * mask) / torch.sum(mask)
+        denom = torch.sum(mask)
+        if self.guard_empty_mask:
+            # solver.py:478 divides by sum(mask); when every free-run token is <EOS> that is 0/0 = NaN, which the
+            # reference then back-propagates into every generator weight. Here the term is 0 in that case (the only
+            # inputs on which the two differ are those where the reference's step is NaN).
+            denom = denom.clamp_min(1.0)
+        unsup = -torch.sum(lm_probs * u_logp * mask) / denom
         _, logp, _, _ = m(xs, ilens, ys)
         sup = -torch.mean(logp)                                                     # solver.py:482
         return sup + self.unsup_weight * unsup, sup, unsup, (u_logp, u_pred, lm_probs)

@@ -89,7 +89,7 @@ _DEFER = {"on": False, "streams": {}, "keep": [], "used": False}
 
 class deferred_wgrad:
     def __enter__(self):
-        _DEFER["on"] = True
+        _DEFER["on"] = os.environ.get("LAS_NO_DEFER", "0") != "1"     # debugging switch: single-stream backward
         return self
 
     def __exit__(self, *exc):
@@ -253,7 +253,7 @@ def prepare_ahead(jobs):
     stream; the results are handed to the matching `_prep` calls of this step. `join_deferred()` (end of the
     backward pass) joins the stream and drops the cache."""
     jobs = list(jobs)
-    if not jobs:
+    if not jobs or os.environ.get("LAS_NO_PREP", "0") == "1":        # debugging switch: build everything inline
         return
     dev = jobs[0][1][0].device
     side = warm_deferred(dev)
@@ -458,17 +458,17 @@ class EncoderFn(torch.autograd.Function):
             dy = gemm(dz, Ho, 0, wp, Kp, 1, n, Kp, Ho)                               # f32 [B, Tp, 2H] view
             if p_drop > 0:
                 dropout_(dy, B, T, 2 * H, Tp * 2 * H, 2 * H, rep, p_drop, site0 + 2 * i)
+            # projection gradients dW = dz^T yview, db = colsum(dz) need only dz: forked BEFORE this layer's BPTT
+            with wgrad_scope(lw[8:10], dz, y) as sc:
+                grads[10 * i + 8:10 * i + 10] = sc.deliver([gemm(dz, Ho, 1, y, Kp, 1, Ho, Kp, n), colsum(dz, Ho)])
             dx, dG = lstm_layer_bwd(lsaved, [w_hh, w_hh_r], dy, need_dx=i > 0)
             del dy
-            # parameter gradients: projection dW = dz^T yview, db = colsum(dz); LSTM weights from dG
-            with wgrad_scope(lw, dz, y, dG, lsaved) as sc:
-                d_proj_w = gemm(dz, Ho, 1, y, Kp, 1, Ho, Kp, n)
-                d_proj_b = colsum(dz, Ho)
+            # LSTM weight gradients from dG (overlap the next layer's BPTT; layer 0's are the exposed tail)
+            with wgrad_scope(lw[:8], dG, lsaved) as sc:
                 d_wcat, d_whh, d_bcat = lstm_layer_wgrad(lsaved, dG)
                 Din = w_ih.shape[1]
-                grads[10 * i:10 * i + 10] = sc.deliver([d_wcat[:4 * H, :Din], d_whh[0], d_bcat[:4 * H], d_bcat[:4 * H],
-                                                        d_wcat[4 * H:, :Din], d_whh[1], d_bcat[4 * H:], d_bcat[4 * H:],
-                                                        d_proj_w, d_proj_b])
+                grads[10 * i:10 * i + 8] = sc.deliver([d_wcat[:4 * H, :Din], d_whh[0], d_bcat[:4 * H], d_bcat[:4 * H],
+                                                       d_wcat[4 * H:, :Din], d_whh[1], d_bcat[4 * H:], d_bcat[4 * H:]])
             if i > 0:
                 dout = dx
         ctx.saved = None

@@ -229,16 +229,17 @@ class Solver(object):
             raise NotImplementedError("scheduled sampling (tf_rate < 1) is not implemented; config.yaml pins 1.0")
         c, tag = self.config, self.config["tag"]
         steps = len(self.train_lab_loader)
-        total = torch.zeros((), device=next(self.model.parameters()).device)
+        total = 0.0
         def batches():
             for xs, ilens, ys in self.train_lab_loader:
                 if c["add_gaussian"] and epoch >= c["gaussian_epoch"]:           # solver.py:370-373 (host noise)
                     xs = xs + torch.from_numpy(np.random.normal(0, c["gaussian_std"], tuple(xs.shape)).astype(np.float32))
                 yield xs, ilens, ys
 
-        # pipelined: the H2D copy of batch i+1 overlaps step i; no per-step .item(), so no host sync either
+        # pipelined: the H2D copy of batch i+1 overlaps step i; losses arrive as host scalars one step late, so
+        # the GPU never waits for the host
         for i, (loss, _) in enumerate(self.sup_trainer.steps(batches())):
-            total += loss
+            total += float(loss)
             if self.logger is not None and (i + 1) % max(1, c.get("log_every", 50)) == 0:
                 self.log("scalar_summary", f"{tag}/train_loss", loss.item(), epoch * steps + i + 1)
         return float(total) / max(1, steps)

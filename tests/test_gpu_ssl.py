@@ -113,3 +113,44 @@ def test_smooth_mode_gradient_reaches_earlier_steps():
     for k in ("decoder.output_layer.bias", "decoder.embedding.weight", "decoder.LSTMCell.weight_ih"):
         p = dict(m.named_parameters())[k]
         assert cosine(p.grad, leaves[k].grad) >= 0.999, (k, cosine(p.grad, leaves[k].grad))
+
+
+def test_diverged_model_cannot_produce_out_of_range_tokens():
+    """torch.argmax conventions (first maximal index, NaN counts as the maximum): an all-NaN logit row -- a
+    diverged generator -- must give a token id in [0, V), not an out-of-range embedding index (this used to be an
+    illegal memory access in the free-running decoder)."""
+    G = load_golden("ssl_small")
+    g = G["raw"]
+    m = e2e_from_golden(G).train()
+    with torch.no_grad():
+        m.decoder.output_layer.bias.fill_(float("nan"))
+    ux = torch.from_numpy(g["ux"]).cuda()
+    Lu = int(ux.shape[1] * float(g["proportion"]))
+    _, u_logp, u_pred, _ = m(ux, g["uilens"].tolist(), ys=None, label_smoothing=False, max_dec_timesteps=Lu,
+                             smooth=True, scaling=3.0)
+    torch.cuda.synchronize()
+    V = m.decoder.output_layer.bias.numel()
+    assert int(u_pred.min()) >= 0 and int(u_pred.max()) < V
+    assert int(u_pred.max()) == 0                                   # first NaN index, as torch.argmax
+
+
+def test_all_eos_free_run_does_not_poison_the_generator():
+    """solver.py:478 divides by sum(pred != EOS); with every free-run token == EOS that is 0/0. The trainer's
+    guard makes the unsupervised term 0 there (guard_empty_mask=False keeps the reference's NaN)."""
+    G = load_golden("ssl_small")
+    g = G["raw"]
+    E = pkg("engine")
+    lab = (torch.from_numpy(g["x"]).cuda(), g["ilens"].tolist(), [torch.from_numpy(y).cuda() for y in G["ys"]])
+    unlab = (torch.from_numpy(g["ux"]).cuda(), g["uilens"].tolist())
+    for guard in (True, False):
+        m = e2e_from_golden(G).train()
+        lm = lm_from_golden(G).train()
+        with torch.no_grad():
+            m.decoder.output_layer.bias[2] += 50.0                  # <EOS> wins every argmax
+        tr = E.SSLTrainer(m, lm, None, proportion=float(g["proportion"]), guard_empty_mask=guard)
+        loss, sup, unsup, (_, u_pred, _) = tr.losses(lab, unlab)
+        assert bool((u_pred == 2).all())
+        if guard:
+            assert float(unsup) == 0.0 and bool(torch.isfinite(loss))
+        else:
+            assert bool(torch.isnan(unsup))
