@@ -78,7 +78,7 @@ class SupervisedTrainer:
         self.update_graph, self.update_norm = None, None
         self.cap_stream = None
         self.copy_stream = None
-        self.rb_dev, self.rb_host = None, None
+        self.rb_dev, self.rb_host, self.rb_stream = None, None, None
 
     # ---- the step body: everything below runs on the current stream, no host sync
     def _fwd_bwd(self, st, L):
@@ -240,7 +240,9 @@ class SupervisedTrainer:
         self.rb_dev[k, 1].copy_(torch.as_tensor(norm, device=dev).reshape(()).float(), non_blocking=True)
         done = torch.cuda.Event()
         done.record(main)
-        cs = self.copy_stream
+        if self.rb_stream is None:     # NOT the upload stream: this one waits for the step, the uploads must not
+            self.rb_stream = torch.cuda.Stream(device=dev)
+        cs = self.rb_stream
         cs.wait_event(done)
         with torch.cuda.stream(cs):
             self.rb_host[k].copy_(self.rb_dev[k], non_blocking=True)
