@@ -441,6 +441,23 @@ __global__ void __launch_bounds__(320, 1) lstm_persist_bwd_kernel(BwdP p) {
     const int t = (dir == 0) ? (T - 1 - s) : s;
     const bool active = t < len;
     LAS_TRACE(0);
+    // operands of the gate-derivative math into registers, then the ring slot is refilled right away: the loads
+    // and the cp.async issue are hidden behind the MMA and the DSMEM round trip below instead of following them
+    cp_async_wait<kPF - 2>();   // this step's and the next step's operands have landed
+    float4 rc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float c_prev = 0.f, dy_in = 0.f;
+    if (active) {
+      const float* q = pslot + (s % kPF) * ring_stride;
+      rc = *reinterpret_cast<const float4*>(q);
+      const float* qn = pslot + ((s + 1) % kPF) * ring_stride;
+      if (dir == 0) { if (t > 0) c_prev = qn[2]; }
+      else          { if (t + 1 < len) c_prev = qn[2]; }
+      if (p.dy) {
+        dy_in = q[4];
+        if (p.rep_row && t == T - 1) dy_in += q[5];
+      }
+    }
+    prefetch();   // refills slot s % kPF (just read) with step s + kPF
     float dh = 0.f;
     if (s > 0) {
       const int buf = s & 1;
@@ -490,20 +507,10 @@ __global__ void __launch_bounds__(320, 1) lstm_persist_bwd_kernel(BwdP p) {
     // gate derivatives (same math as cell_bwd_kernel)
     float d4[4] = {0.f, 0.f, 0.f, 0.f};
     LAS_TRACE(4);
-    cp_async_wait<kPF - 2>();   // this step's and the next step's operands have landed
     if (active) {
-      const float* q = pslot + (s % kPF) * ring_stride;
-      const float4 rc = *reinterpret_cast<const float4*>(q);
       const uint2 gpk = make_uint2(__float_as_uint(rc.x), __float_as_uint(rc.y));
       const float tc = rc.w;
-      float c_prev = 0.f;
-      const float* qn = pslot + ((s + 1) % kPF) * ring_stride;
-      if (dir == 0) { if (t > 0) c_prev = qn[2]; }
-      else          { if (t + 1 < len) c_prev = qn[2]; }
-      if (p.dy) {
-        dh += q[4];
-        if (p.rep_row && t == T - 1) dh += q[5];
-      }
+      dh += dy_in;
       const float2 if_ = __half22float2(*reinterpret_cast<const __half2*>(&gpk.x));
       const float2 go_ = __half22float2(*reinterpret_cast<const __half2*>(&gpk.y));
       const float i = if_.x, f = if_.y, gc = go_.x, o = go_.y;
@@ -532,7 +539,6 @@ __global__ void __launch_bounds__(320, 1) lstm_persist_bwd_kernel(BwdP p) {
       }
     }
     LAS_TRACE(5);
-    prefetch();
     LAS_TRACE(6);
     __syncthreads();
     LAS_TRACE(7);

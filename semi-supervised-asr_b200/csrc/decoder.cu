@@ -841,10 +841,12 @@ int las_att_param_grads(const float* P, const float* dzf, const float* conv_save
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   LAS_REQUIRE(A >= 1 && A <= 512 && C >= 1 && C <= 16, "att_param_grads: att_dim / conv_channels out of range");
   if (B == 0 || Te == 0 || L == 0) return 0;
-  const int CM = (C <= 4) ? 4 : 16;
+  const int CM = (C + 3) / 4 * 4;          // channel count padded to whole float4 pieces: no FMAs on padding beyond that
   const int threads = (A + 31) / 32 * 32;
   const dim3 grid((Te + kPG - 1) / kPG, B);
   if (CM == 4) att_param_grad_kernel<4><<<grid, threads, 0, stream>>>(P, dzf, conv_save, de_all, mlp_att, gvec, B, L, Te, A, C, threads, dP, part_ws);
+  else if (CM == 8) att_param_grad_kernel<8><<<grid, threads, 0, stream>>>(P, dzf, conv_save, de_all, mlp_att, gvec, B, L, Te, A, C, threads, dP, part_ws);
+  else if (CM == 12) att_param_grad_kernel<12><<<grid, threads, 0, stream>>>(P, dzf, conv_save, de_all, mlp_att, gvec, B, L, Te, A, C, threads, dP, part_ws);
   else att_param_grad_kernel<16><<<grid, threads, 0, stream>>>(P, dzf, conv_save, de_all, mlp_att, gvec, B, L, Te, A, C, threads, dP, part_ws);
   ++g_launches;
   att_part_reduce_kernel<<<((C + 1) * A + 255) / 256, 256, 0, stream>>>(part_ws, grid.x * grid.y, CM, threads, A, C, dmlp_att, dgvec); ++g_launches;
