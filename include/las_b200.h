@@ -136,6 +136,8 @@ int las_lstm_seq_bwd(const float* dy, int64_t dy_ld_b, int64_t dy_ld_t, int rep_
  *   rec        [ndir, B, T, H] records of 16 bytes: (i,f) f16x2 | (g,o) f16x2 | c f32 | tanh(c) f32
  * y / hprev / dy / lens / rep_row as in las_lstm_seq_{fwd,bwd}. */
 int las_lstm_persistent_geometry(int H, int* cs, int* upc);
+/* development aid: resident-cluster capacity of the persistent LSTM kernels (which: 0 forward, 1 backward) */
+int las_lstm_persist_max_clusters(int which, int H);
 int las_lstm_persist_fwd(const float* xproj, const void* whh_pk, const int32_t* lens, int B, int T, int H,
                          int ndir, void* y, int64_t y_ld_b, int64_t y_ld_t, int rep_row, void* hprev,
                          int64_t hp_ld_b, int64_t hp_ld_t, void* rec, void* stream);

@@ -63,6 +63,7 @@ SIGNATURES = {
     "las_lstm_persist_fwd": (c_int, [P, P, P, I, I, I, I, P, L, L, I, P, L, L, P, P]),
     "las_lstm_persist_bwd": (c_int, [P, L, L, I, P, P, I, I, I, I, P, P, L, L, P]),
     "las_lstm_persistent_geometry": (c_int, [I, P, P]),
+    "las_lstm_persist_max_clusters": (c_int, [I, I]),
     "las_set_persistent": (c_int, [I]),
     "las_set_debug_buffer": (c_int, [P]),
     "las_whhT_owner_bytes": (c_int64, [I]),

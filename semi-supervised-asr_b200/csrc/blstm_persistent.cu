@@ -686,6 +686,38 @@ int las_set_persistent(int on) {
   return prev;
 }
 
+/* development aid: how many clusters of the persistent LSTM kernels (which = 0 forward, 1 backward) can be resident
+ * at once for hidden size H (cudaOccupancyMaxActiveClusters); more clusters than this run as a second wave */
+int las_lstm_persist_max_clusters(int which, int H) {
+  Geom g;
+  FGeom f;
+  if (!geom_for(H, g) || !fgeom_for(H, f)) return 0;
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (which == 0) {
+    const int threads = 32 * f.WPC;
+    cfg.gridDim = dim3(f.CS, 1, 1); cfg.blockDim = dim3(threads); at[0].val.clusterDim.x = f.CS;
+    cfg.dynamicSmemBytes = 16 + static_cast<size_t>(2) * f.KT * 256 + static_cast<size_t>(kPF) * threads * 16;
+    cudaFuncSetAttribute(lstm_persist_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (cudaOccupancyMaxActiveClusters(&n, lstm_persist_fwd_kernel, &cfg) != cudaSuccess) n = -1;
+  } else {
+    const int UPC = 8 * g.UGC;
+    cfg.gridDim = dim3(g.CS, 1, 1); cfg.blockDim = dim3(64 * g.UGC); at[0].val.clusterDim.x = g.CS;
+    cfg.dynamicSmemBytes = 16 + static_cast<size_t>(2) * g.CS * UPC * 8 * 4 + static_cast<size_t>(2 * g.UGC) * 256 +
+                           static_cast<size_t>(kPF) * 64 * g.UGC * 8 * 4;
+    cudaFuncSetAttribute(lstm_persist_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (cudaOccupancyMaxActiveClusters(&n, lstm_persist_bwd_kernel, &cfg) != cudaSuccess) n = -1;
+  }
+  (void)cudaGetLastError();
+  return n;
+}
+
 int las_lstm_persistent_geometry(int H, int* cs, int* upc) {
   Geom g;
   if (!persist_enabled() || !geom_for(H, g)) return 0;
