@@ -147,7 +147,18 @@ class wgrad_scope:
 
     def deliver(self, grads):
         if not self.deferred:
-            return list(grads)
+            # autograd may adopt a returned tensor as `.grad` without copying: two parameters that share one
+            # gradient (b_ih / b_hh) must not end up sharing its memory (clip_grad_norm_ would scale it twice,
+            # a second backward would add into it twice)
+            out, seen = [], set()
+            for g in grads:
+                if g is not None:
+                    key = (g.data_ptr(), tuple(g.shape), tuple(g.stride()))
+                    if key in seen:
+                        g = g.clone()
+                    seen.add(key)
+                out.append(g)
+            return out
         for w, g in zip(self.weights, grads):
             if g is not None and w.requires_grad:
                 w.grad.add_(g.reshape(w.grad.shape) if g.shape != w.grad.shape else g)

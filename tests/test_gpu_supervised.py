@@ -167,3 +167,23 @@ def test_random_case_against_oracle(cfg):
     loss.backward()
     assert abs(float(loss) - loss_o) < 1e-3 * abs(loss_o)
     _check_grads(list(m.named_parameters()), grads_o)
+
+
+def test_shared_bias_gradient_is_not_aliased():
+    """b_ih and b_hh of every LSTM receive the same gradient values; their `.grad` tensors must still be distinct
+    memory (autograd adopts returned tensors without copying): clip_grad_norm_ scales `.grad` in place per
+    parameter, and a second backward accumulates in place."""
+    G = load_golden("sup_small_odd")
+    g = G["raw"]
+    m = e2e_from_golden(G)
+    for rep in range(2):
+        _, logp, _, _ = _run(m, g, G)
+        if rep == 0:
+            m.zero_grad(set_to_none=True)
+        (-torch.mean(logp)).backward()
+    named = dict(m.named_parameters())
+    ptrs = [p.grad.data_ptr() for p in named.values()]
+    assert len(set(ptrs)) == len(ptrs)
+    for k, gv in G["g"].items():                                     # two accumulated passes == 2 x the golden gradient
+        assert cosine(named[k].grad, gv) >= 0.999, k
+        assert abs(float(named[k].grad.norm()) - 2 * float(gv.norm())) < 2e-2 * 2 * float(gv.norm()) + 1e-6, k
