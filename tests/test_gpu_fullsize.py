@@ -107,3 +107,86 @@ def test_full_size_gradient_accumulation_is_additive(case):
     # second pass adds the same gradient (the decoder backward's shared-memory atomics make the last bits vary)
     rel = float((g2 - 2 * g1).norm() / g1.norm())
     assert rel < 1e-4, rel
+
+
+# ---- BASELINE config 4 at the reference's layer sizes (judge = 2 x LSTM-640 over 256-dim embeddings) on a
+# CPU-affordable batch
+def _lm(V, seed, labeldist):
+    M = pkg("model")
+    torch.manual_seed(seed)
+    lm = M.LM(output_dim=V, embedding_dim=256, hidden_dim=640, dropout_rate=0.0, n_layers=2, bos=1, eos=2, pad=0,
+              ls_weight=0.05, labeldist=labeldist)
+    PJ = {k: v.detach().clone() for k, v in lm.state_dict().items()}
+    return lm.cuda(), PJ
+
+
+def test_judge_step_at_reference_layer_sizes():
+    rng = np.random.RandomState(21)
+    V = 34
+    ys = sorted([rng.randint(3, V, size=int(n)).astype(np.int64) for n in rng.randint(20, 126, size=8)], key=len, reverse=True)
+    ld = O.label_distribution(ys, V)
+    lm, PJ = _lm(V, 21, ld)
+    (loss_o, avg_o), grads_o, _, _ = O.judge_step(ys, PJ, {}, 0.05, ld)
+    E = pkg("engine")
+    tr = E.JudgeTrainer(lm.train(), None, max_grad_norm=5.0)
+    loss, avg = tr.losses([torch.from_numpy(y).cuda() for y in ys])
+    assert abs(float(loss) - loss_o) < 1e-3 * abs(loss_o)
+    assert abs(float(avg) - avg_o) < 1e-3
+    lm.zero_grad()
+    loss.backward()
+    _check_grads(list(lm.named_parameters()), grads_o)
+
+
+def test_ssl_generator_step_at_reference_layer_sizes():
+    cfg = dict(seed=23, B=4, T=320, D=249, H=320, sub=[2, 2, 2], V=34, E=128, A=320, C=10, K=100, ls=0.05)
+    m, P, x, lens, ys, labeldist = _random_case(**cfg)
+    # a freshly initialised output layer gives nearly flat logits, i.e. near-ties at every free-running step; a
+    # sharper one (same factor in the oracle's copy) makes the fp32 and bf16 hypotheses agree
+    with torch.no_grad():
+        for k in ("decoder.output_layer.weight", "decoder.output_layer.bias"):
+            P[k] = P[k] * 40.0
+        m.decoder.output_layer.weight.mul_(40.0)
+        m.decoder.output_layer.bias.mul_(40.0)
+    lab = (torch.from_numpy(x).cuda(), lens, [torch.from_numpy(y).cuda() for y in ys])
+    E = pkg("engine")
+    # smooth mode feeds softmax(3 logit) @ E back, not the argmax, so the trajectories stay comparable even where a
+    # token differs: every disagreement must sit at a step whose fp32 top-2 margin is inside the bf16 tolerance.
+    # Unpaired batches are drawn until the two hypotheses agree everywhere (then the unsupervised term and the
+    # gradient through the free run are compared too).
+    agreed = None
+    for useed in (24, 25, 26, 27, 28, 29):
+        rng = np.random.RandomState(useed)
+        ulens = sorted([320] + [int(rng.randint(160, 321)) for _ in range(3)], reverse=True)
+        ux = np.zeros((4, 320, 249), dtype=np.float32)
+        for b, l in enumerate(ulens):
+            ux[b, :l] = rng.standard_normal((l, 249)).astype(np.float32)
+        with torch.no_grad():
+            _, _, u_pred, _ = m.train()(torch.from_numpy(ux).cuda(), ulens, ys=None, label_smoothing=False,
+                                        max_dec_timesteps=40, smooth=True, scaling=3.0)
+            o_logits, _, o_pred, _ = O.e2e_forward(torch.from_numpy(ux), ulens, P, cfg["sub"], ys=None, max_dec_timesteps=40,
+                                                   smooth=True, scaling=3.0, label_smoothing=False, ls_weight=0.05,
+                                                   labeldist=labeldist, training=True, fast=True)
+        top2 = o_logits.topk(2, dim=-1).values
+        margin = top2[..., 0] - top2[..., 1]
+        diff = u_pred.cpu() != o_pred
+        tol = 2 * 3e-2 * float(o_logits.abs().max())
+        assert not bool((diff & (margin > tol)).any()), (useed, int(diff.sum()), float(margin[diff].max()), tol)
+        if not bool(diff.any()):
+            agreed = useed
+            break
+    if agreed is None:
+        pytest.skip("free-running hypotheses differed at near-ties for every unpaired batch tried")
+    lm, PJ = _lm(34, 25, labeldist)
+    (loss_o, sup_o, unsup_o), grads_o, _, _ = O.ssl_step((torch.from_numpy(x), lens, ys), (torch.from_numpy(ux), ulens),
+                                                        P, PJ, {}, cfg["sub"], 0.125, 0.05, labeldist, labeldist, fast=True)
+    tr = E.SSLTrainer(m.train(), lm.train(), None, unsup_weight=0.001, proportion=0.125, smooth=True, scaling=3.0,
+                      guard_empty_mask=False)
+    loss, sup, unsup, (u_logp, u_pred, _) = tr.losses(lab, (torch.from_numpy(ux).cuda(), ulens))
+    assert tuple(u_pred.shape) == (4, 40)                                     # Lu = int(320 * 0.125)
+    assert torch.equal(u_pred.cpu(), o_pred)
+    assert abs(float(sup) - sup_o) < 1e-3 * abs(sup_o)
+    assert abs(float(unsup) - unsup_o) < 5e-3 * abs(unsup_o)
+    assert abs(float(loss) - loss_o) < 1e-3 * abs(loss_o)
+    m.zero_grad()
+    loss.backward()
+    _check_grads(list(m.named_parameters()), grads_o)
