@@ -240,6 +240,10 @@ typedef struct las_dec_args {
   const void* seed_dev;      /* device uint64                                                   */
   void* zcd;                 /* per-step path: bf16 [B, L+1, Hd+O] (+64 slack), zeroed: [z | drop(c)] */
   const float* pbar;         /* f32 [B, A]: frame mean removed from P (then P holds P - pbar and dzf = mlp_dec(z_t) + pbar) */
+  /* las_dec_fwd, per-step path only: run steps [t_begin, t_end) of the L (t_end == 0: up to L). All state lives in
+   * the caller's buffers (c_state, rows of zc / ws / emb_op), so a forward can be issued in chunks -- greedy decoding
+   * that stops once every utterance has emitted <EOS> (Solver.test / validation, solver.py:212-286). */
+  int32_t t_begin, t_end;
 } las_dec_args;
 
 int las_att_init(const int32_t* enc_lens, int B, int Te, float* w, int64_t w_ld, void* stream);

@@ -857,7 +857,12 @@ int las_att_param_grads(const float* P, const float* dzf, const float* conv_save
 int las_dec_fwd(const las_dec_args* a, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (int rc = check_args(a)) return rc;
-  if (dec_persist_supported(a)) return dec_persist_fwd(a, stream);   // one cluster-persistent launch
+  const int t_begin = a->t_begin, t_end = (a->t_end > 0 && a->t_end < a->L) ? a->t_end : a->L;
+  LAS_REQUIRE(t_begin >= 0 && t_begin <= t_end, "decoder: step range [%d, %d) invalid", t_begin, t_end);
+  if (dec_persist_supported(a)) {
+    LAS_REQUIRE(t_begin == 0 && t_end == a->L, "decoder: the persistent kernel runs all steps in one launch");
+    return dec_persist_fwd(a, stream);   // one cluster-persistent launch
+  }
   const int B = a->B, L = a->L, Te = a->Te, Hd = a->Hd, O = a->O, A = a->A, V = a->V, E = a->E;
   const int ZC = Hd + O;
   const int64_t R = L + 1;  // rows per utterance in the per-step buffers
@@ -900,7 +905,7 @@ int las_dec_fwd(const las_dec_args* a, void* stream_) {
   xp.enc_h = static_cast<const __nv_bfloat16*>(a->enc_h); xp.w_ld = R * Te; xp.ctx_ld = R * a->H;
 
   const dim3 egrid((Te + kTT - 1) / kTT, B), cgrid(B, (a->H + 63) / 64);
-  for (int t = 0; t < L; ++t) {
+  for (int t = t_begin; t < t_end; ++t) {
     // (1) LSTMCell: gates = W [emb; c_{t-1}; z_{t-1}] + b   (model.py:284-286)
     cp.step = t;
     cp.v1 = (drop ? zcd : zc) + static_cast<int64_t>(t) * ZC;      // cell input: c_{t-1} after dropout (model.py:285)

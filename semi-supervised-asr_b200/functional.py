@@ -489,6 +489,9 @@ class EncoderFn(torch.autograd.Function):
 # --------------------------------------------------------------------------------------------
 # attention decoder (model.py:139-173, 283-367)
 # --------------------------------------------------------------------------------------------
+# Greedy decoding with an early stop (see DecoderFn.forward); switched on by Solver around its scoring loops.
+GREEDY_EARLY_STOP = {"on": False, "eos": 2, "chunk": 16, "last_steps": None}
+
 DEC_WEIGHTS = ("emb_w", "w_ih", "w_hh", "b_ih", "b_hh", "out_w", "out_b", "mlp_enc_w", "mlp_enc_b", "mlp_dec_w",
                "mlp_att_w", "conv_w", "gvec_w", "mlp_o_w", "mlp_o_b")
 
@@ -668,7 +671,21 @@ class DecoderFn(torch.autograd.Function):
             zcd = torch.zeros(B * R * ZC + 64, device=dev, dtype=BF16)
             a.zcd = ptr(zcd)
             keep.append(zcd)
-        _lib.check(_lib.lib().las_dec_fwd(ctypes.byref(a), _lib.stream_ptr()))
+        es = GREEDY_EARLY_STOP
+        if mode == 1 and es["on"] and not torch.is_grad_enabled():
+            # greedy decoding for scoring (Solver.test / validation): issue the steps in chunks and stop as soon as
+            # every utterance has emitted <EOS>. Rows after the stop keep their initial zeros; the hypotheses are
+            # identical after remove_pad_eos (utils.py:192-201), which cuts at the first <EOS>.
+            t0 = 0
+            while t0 < L:
+                a.t_begin, a.t_end = t0, min(L, t0 + es["chunk"])
+                _lib.check(_lib.lib().las_dec_fwd(ctypes.byref(a), _lib.stream_ptr()))
+                t0 = a.t_end
+                if t0 < L and bool((pred[:, :t0] == es["eos"]).any(dim=1).all()):     # one host sync per chunk
+                    break
+            es["last_steps"] = t0
+        else:
+            _lib.check(_lib.lib().las_dec_fwd(ctypes.byref(a), _lib.stream_ptr()))
         out_bf = Pk["out_bf"]                                                         # [V, ZC]
         if mode == 0:
             logits = gemm(zc, ZC, 0, out_bf, ZC, 0, B * R, V, ZC, bias=W["out_b"]).view(B, R, V)

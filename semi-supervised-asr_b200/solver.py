@@ -17,6 +17,7 @@ import numpy as np
 import torch
 
 from . import engine
+from . import functional as Fn
 from .data import BatchLoader, PickleDataset, collate, speech_collate, text_collate
 from .model import E2E, LM
 from .optim import FusedAdam
@@ -161,6 +162,15 @@ class Solver(object):
     def _decode_set(self, loader, with_loss):
         self.model.eval()
         preds, refs, total = [], [], 0.0
+        # hypotheses are cut at their first <EOS> (ind2sent -> remove_pad_eos): decode in chunks and stop once
+        # every utterance of the batch has produced one, instead of always running max_dec_timesteps steps
+        Fn.GREEDY_EARLY_STOP.update(on=bool(self.config.get("greedy_early_stop", True)), eos=self.vocab["<EOS>"])
+        try:
+            return self._decode_loop(loader, with_loss, preds, refs, total)
+        finally:
+            Fn.GREEDY_EARLY_STOP["on"] = False
+
+    def _decode_loop(self, loader, with_loss, preds, refs, total):
         for data in loader:
             xs, ilens, ys = to_gpu(data)
             if with_loss:
@@ -230,10 +240,13 @@ class Solver(object):
         c, tag = self.config, self.config["tag"]
         steps = len(self.train_lab_loader)
         total = 0.0
+        # solver.py:370-373: Gaussian input noise from `gaussian_epoch` on -- drawn on the device after the upload
+        # (same distribution; the reference draws 8 M numpy normals per batch on the host)
+        noisy = bool(c["add_gaussian"]) and epoch >= c["gaussian_epoch"]
+        self.sup_trainer.input_noise_std = float(c["gaussian_std"]) if noisy else 0.0
+
         def batches():
             for xs, ilens, ys in self.train_lab_loader:
-                if c["add_gaussian"] and epoch >= c["gaussian_epoch"]:           # solver.py:370-373 (host noise)
-                    xs = xs + torch.from_numpy(np.random.normal(0, c["gaussian_std"], tuple(xs.shape)).astype(np.float32))
                 yield xs, ilens, ys
 
         # pipelined: the H2D copy of batch i+1 overlaps step i; losses arrive as host scalars one step late, so

@@ -187,3 +187,27 @@ def test_shared_bias_gradient_is_not_aliased():
     for k, gv in G["g"].items():                                     # two accumulated passes == 2 x the golden gradient
         assert cosine(named[k].grad, gv) >= 0.999, k
         assert abs(float(named[k].grad.norm()) - 2 * float(gv.norm())) < 2e-2 * 2 * float(gv.norm()) + 1e-6, k
+
+
+def test_greedy_early_stop_gives_the_same_hypotheses():
+    """Solver.test / validation cut every hypothesis at its first <EOS> (utils.py:192-201); decoding in chunks and
+    stopping once every utterance has emitted one must give the same cut hypotheses, in fewer steps."""
+    G = load_golden("sup_small_odd")
+    g = G["raw"]
+    Fn, U = pkg("functional"), pkg("utils")
+    m = e2e_from_golden(G).eval()
+    with torch.no_grad():
+        m.decoder.output_layer.bias[2] += 0.8                      # make <EOS> likely early, but not immediate
+    x, lens = torch.from_numpy(g["x"]).cuda(), g["ilens"].tolist()
+    with torch.no_grad():
+        _, _, full, _ = m(x, lens, ys=None, max_dec_timesteps=64)
+        Fn.GREEDY_EARLY_STOP.update(on=True, eos=2, chunk=4)
+        try:
+            _, _, early, _ = m(x, lens, ys=None, max_dec_timesteps=64)
+        finally:
+            Fn.GREEDY_EARLY_STOP["on"] = False
+    cut = lambda p: U.remove_pad_eos(p.cpu().numpy().tolist(), eos=2)
+    assert cut(full) == cut(early)
+    has_eos = bool((full == 2).any(dim=1).all())
+    if has_eos:
+        assert Fn.GREEDY_EARLY_STOP["last_steps"] < 64             # it really stopped early

@@ -110,3 +110,18 @@ def test_graph_replay_equals_eager_at_config2_layer_sizes():
     assert la[-1] < la[0] - 0.2, la                                  # 12 steps on one batch: it must be learning
     assert np.allclose(la, lb, rtol=5e-3), (la, lb)
     assert np.allclose(na, nb, rtol=0.1), (na, nb)
+
+
+def test_on_device_input_noise():
+    """solver.py:370-373 (add_gaussian): N(0, std) added to the features, here on the device after the upload."""
+    G = load_golden("sup_small_odd")
+    batch = _batch(G)
+    _, _, tr = _trainer(G, use_graph=False)
+    key = tr.stage(*batch)
+    clean = tr.static[key].x.clone()
+    tr.input_noise_std = 0.5
+    key = tr.stage(*batch)
+    noise = (tr.static[key].x - clean).flatten()
+    assert abs(float(noise.mean())) < 0.05 and abs(float(noise.std()) - 0.5) < 0.05
+    loss, _ = tr.run(key)
+    assert bool(torch.isfinite(loss))
