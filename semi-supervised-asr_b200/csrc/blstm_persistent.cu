@@ -40,10 +40,10 @@ struct Geom {
 struct FGeom {
   int Q, CS, WPC, KT;
 };
-bool fgeom_for(int H, FGeom& g) {
+bool fgeom_for(int H, FGeom& g, int max_cs = 8) {
   if (H % 8 != 0 || H < 8) return false;
   g.Q = H / 4;
-  const int cs0 = g.Q < 8 ? g.Q : 8;
+  const int cs0 = g.Q < max_cs ? g.Q : max_cs;
   g.WPC = (g.Q + cs0 - 1) / cs0;
   g.CS = (g.Q + g.WPC - 1) / g.WPC;
   g.KT = (H + 15) / 16;
@@ -222,8 +222,13 @@ __global__ void __launch_bounds__(320, 1) lstm_persist_fwd_kernel(FwdP p) {
     // further) and the peer's barrier:
     const uint32_t hs_buf_bytes = static_cast<uint32_t>(p.KT) * 256u;
     const bool peer_ok = static_cast<uint32_t>(g) < CS;
-    const uint32_t hs_remote = mapa_u32(smem_u32(hs + (quad * 8 + ((2 * tig) ^ (((quad & 3) >> 1) << 2))) * 2), peer_ok ? g : 0);
+    const uint32_t hs_local = smem_u32(hs + (quad * 8 + ((2 * tig) ^ (((quad & 3) >> 1) << 2))) * 2);
+    const uint32_t hs_remote = mapa_u32(hs_local, peer_ok ? g : 0);
     const uint32_t bar_remote = mapa_u32(smem_u32(&full[0]), peer_ok ? g : 0);
+    // clusters of more than 8 CTAs (up to 16): lane g also serves peer 8 + g
+    const bool peer2_ok = static_cast<uint32_t>(g) + 8u < CS;
+    const uint32_t hs_remote2 = mapa_u32(hs_local, peer2_ok ? g + 8 : 0);
+    const uint32_t bar_remote2 = mapa_u32(smem_u32(&full[0]), peer2_ok ? g + 8 : 0);
 
     const bool trace = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0;
 #define LAS_TRACE(slot) do { if (trace && s >= 64 && s < 72) p.dbg[(s - 64) * 8 + (slot)] = clock64(); } while (0)
@@ -282,10 +287,11 @@ __global__ void __launch_bounds__(320, 1) lstm_persist_fwd_kernel(FwdP p) {
       const uint32_t x0 = __shfl_xor_sync(0xffffffffu, qw.x, 16);
       const uint32_t x1 = __shfl_xor_sync(0xffffffffu, qw.y, 16);
       // critical path first: the new state goes to the peers before anything is written to HBM
-      if (s + 1 < T && peer_ok) {
+      if (s + 1 < T) {
         const int nbuf = (s + 1) & 1;
         const uint4 v = gl ? make_uint4(x0, x1, qw.x, qw.y) : make_uint4(qw.x, qw.y, x0, x1);
-        st_async_v4(hs_remote + nbuf * hs_buf_bytes, v, bar_remote + nbuf * 8u);
+        if (peer_ok) st_async_v4(hs_remote + nbuf * hs_buf_bytes, v, bar_remote + nbuf * 8u);
+        if (peer2_ok) st_async_v4(hs_remote2 + nbuf * hs_buf_bytes, v, bar_remote2 + nbuf * 8u);
       }
       LAS_TRACE(4);
       // saved activations (BPTT operands) and the layer output
@@ -590,6 +596,7 @@ int launch_cluster(Kern kern, const P& p, int CS, int NG, int ndir, int threads,
   static bool attr_set = false;   // one instance per kernel (template instantiation)
   if (!attr_set) {
     LAS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    LAS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     attr_set = true;
   }
   LAS_REQUIRE(smem <= 200 * 1024, "persistent LSTM: %zu bytes of shared memory needed", smem);
@@ -614,6 +621,29 @@ int launch_cluster(Kern kern, const P& p, int CS, int NG, int ndir, int threads,
 
 void* g_dbg_buf_shared = nullptr;
 
+// resident-cluster capacity of the forward kernel for a geometry (cached per cluster size / block size)
+static int fwd_max_clusters(const FGeom& f) {
+  static int cache[17][11];   // [CS][WPC], 0 = unknown, -1 = failed
+  int& c = cache[f.CS][f.WPC];
+  if (c != 0) return c > 0 ? c : 0;
+  const int threads = 32 * f.WPC;
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = f.CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  cfg.gridDim = dim3(f.CS, 1, 1); cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = 16 + static_cast<size_t>(2) * f.KT * 256 + static_cast<size_t>(kPF) * threads * 16;
+  int n = 0;
+  if (cudaFuncSetAttribute(lstm_persist_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+      cudaFuncSetAttribute(lstm_persist_fwd_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
+      cudaOccupancyMaxActiveClusters(&n, lstm_persist_fwd_kernel, &cfg) != cudaSuccess)
+    n = -1;
+  (void)cudaGetLastError();
+  c = n > 0 ? n : -1;
+  return n > 0 ? n : 0;
+}
+
 int persist_supported(int H) {
   Geom g;
   FGeom f;
@@ -623,8 +653,15 @@ int persist_supported(int H) {
 int persist_lstm_fwd(const float* xproj, const void* whh_pk, const int32_t* lens, int B, int T, int H, int ndir,
                      void* y, int64_t y_ld_b, int64_t y_ld_t, int rep_row, void* hprev, int64_t hp_ld_b,
                      int64_t hp_ld_t, void* rec, cudaStream_t stream) {
+  // The forward fragments are packed per quad, so the cluster size is free at launch: fewer warps per CTA (two per
+  // scheduler instead of three at H = 320) shorten every phase of the step, as long as all clusters stay resident.
   FGeom g;
   LAS_REQUIRE(fgeom_for(H, g), "persistent LSTM: hidden size %d unsupported", H);
+  {
+    FGeom g10;
+    const int need = ((B + kNB - 1) / kNB) * ndir;
+    if (fgeom_for(H, g10, 10) && g10.CS > 8 && fwd_max_clusters(g10) >= need) g = g10;
+  }
   LAS_REQUIRE(y_ld_b % 4 == 0 && y_ld_t % 4 == 0 && hp_ld_b % 4 == 0 && hp_ld_t % 4 == 0 &&
                   reinterpret_cast<uintptr_t>(y) % 8 == 0 && reinterpret_cast<uintptr_t>(hprev) % 8 == 0,
               "persistent LSTM: y / hprev must be 8-byte aligned with strides that are multiples of 4");
