@@ -68,6 +68,8 @@ class ClockSampler:
         self.rows, self.proc, self.index = [], None, index
 
     def start(self):
+        if os.environ.get("LAS_BENCH_NO_SMI"):     # diagnosis only: is the sampler perturbing the host loop?
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
@@ -210,8 +212,9 @@ def main():
     # ---- warm-up (first step of a geometry is eager, second captures the graph)
     W = max(args.warmup, 3)
     losses = []
-    for i in range(W):
-        loss, _ = tr.step(*pinned[i % nb])
+    # through the same public API the end-to-end region uses (steps()): its upload slots, copy / read-back streams
+    # and pinned staging are created here, not inside a timed region
+    for loss, _ in tr.steps(pinned[i % nb] for i in range(W)):
         losses.append(float(loss))
     if args.profile_step:
         tr.use_graph = False

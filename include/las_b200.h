@@ -111,7 +111,7 @@ int las_adam_step(float* p, const float* g, float* m, float* v, float* vmax, int
  * recurrences (model.py:67, 79-81 packed BLSTM; model.py:466, 515-517 LM LSTM)
  * ---------------------------------------------------------------------------------------- */
 /* f32 weight matrix -> bf16 mma A-fragments. mode 0: rows in order; mode 1: LSTM gate-interleaved
- * (rows = 4H, logical row gate*H + unit; tile = 8 units x 2 gates); mode 2: tile = 4 units x 4 gates; mode 3: mode 2 with the K positions of each k-tile quad-permuted (persistent LSTM forward). transposed: logical A[r][c] = W[c*ld + col_offset + r]. */
+ * (rows = 4H, logical row gate*H + unit; tile = 8 units x 2 gates); mode 2: tile = 4 units x 4 gates; mode 3: mode 2 with the K positions of each k-tile quad-permuted (persistent LSTM / decoder forward); mode 4: mode 0 rows with the same K permutation. transposed: logical A[r][c] = W[c*ld + col_offset + r]. */
 int las_pack_afrag(const float* W, int64_t ld, int rows, int cols, int col_offset, int mode, int H,
                    int transposed, void* out, void* stream);
 int64_t las_afrag_bytes(int rows, int cols, int mode, int H);
@@ -244,6 +244,7 @@ typedef struct las_dec_args {
    * the caller's buffers (c_state, rows of zc / ws / emb_op), so a forward can be issued in chunks -- greedy decoding
    * that stops once every utterance has emitted <EOS> (Solver.test / validation, solver.py:212-286). */
   int32_t t_begin, t_end;
+  const void* mlp_dec_pk_p;  /* persistent forward: fragments (mode 4: rows in order, quad-permuted K) of mlp_dec.weight; wr2_pk is mode 3 */
 } las_dec_args;
 
 int las_att_init(const int32_t* enc_lens, int B, int Te, float* w, int64_t w_ld, void* stream);

@@ -31,7 +31,7 @@ class DecArgs(ctypes.Structure):
             "denc", "Q", "wr2_pk", "cpre", "conv_save", "wrT2_pk", "mlp_decT2_pk", "de_all", "dc_all", "cbias", "weT_pk", "outT_pk", "dlogits", "dl_tot", "demb_buf")]
         + [("drop_p", c_float), ("drop_site", ctypes.c_uint32)]
         + [(n, c_void_p) for n in ("seed_dev", "zcd", "pbar")]
-        + [("t_begin", c_int32), ("t_end", c_int32)]
+        + [("t_begin", c_int32), ("t_end", c_int32), ("mlp_dec_pk_p", c_void_p)]
     )
 
 

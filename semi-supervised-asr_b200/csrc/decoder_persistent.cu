@@ -68,6 +68,7 @@ bool dec_geom(const las_dec_args* a, int NB, DGeom& g) {
   if (g.FG > kMaxFG || g.FD > kMaxFD) return false;
   if (O % (2 * g.G) != 0) return false;
   g.OS = O / g.G;
+  if (g.OS % 16 != 0 || (Hd / kCS) % 4 != 0) return false;   // whole 16-dim context tiles / whole unit quads per CTA
   g.OTs = (g.OS + 15) / 16;
   g.TR = (Te + g.G - 1) / g.G;
   g.TT = (g.TR + 15) / 16;
@@ -141,6 +142,18 @@ __device__ __forceinline__ int bfrag_word(int k, int n) {
   return ((kt * 32 + n * 4 + ((kk & 7) >> 1)) * 2) + (kk >> 3);
 }
 
+// Forward state buffer: same [KT][32][2] fragment order, but the K positions of a k-tile are quad-permuted (A
+// fragments packed with las_pack_afrag modes 3 / 4), so that lane (n, q) holds units 4q..4q+3 of its k-tile: the 16
+// units of (k-tile, utterance) are 32 contiguous bytes in natural order and can be pushed as 8/16-byte remote stores.
+// Word (two consecutive units k, k+1, k even) of column n:
+__device__ __forceinline__ int qfrag_word(int k, int n) {
+  const int kt = k >> 4, kk = k & 15;
+  return (kt * 32 + n * 4 + (kk >> 2)) * 2 + ((kk >> 1) & 1);
+}
+__device__ __forceinline__ void st_remote_v2_u32(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared::cluster.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+
 // Element (row, col) of a 16x8 accumulator tile, summed over the KS K-split warps w0 .. w0+KS-1.
 __device__ __forceinline__ float red_gather(const float* red, int w0, int KS, int row, int col) {
   const float* r = red + (w0 * 32 + (row & 7) * 4 + (col >> 1)) * 4 + (row >> 3) * 2 + (col & 1);
@@ -163,8 +176,8 @@ struct DecFwdP {
   const float* P;                // [B, Te, A]
   const __nv_bfloat16* Q;        // [B, Te, O]
   const float* embx;             // [B, L+1, 4Hd]
-  const uint32_t* wr_pk;         // [Hd/4][KTg][32][4]  (pack mode 2)
-  const uint32_t* dec_pk;        // [AT][KTd][32][4]    (pack mode 0)
+  const uint32_t* wr_pk;         // [Hd/4][KTg][32][4]  (pack mode 3: quad tiles, quad-permuted K)
+  const uint32_t* dec_pk;        // [AT][KTd][32][4]    (pack mode 4: rows in order, quad-permuted K)
   const float* cbias;            // [B, O] mlp_o.bias + frame mean of the uncentred Q
   const float* pbar;             // [B, A] frame mean removed from P: added to dz before it is sent / saved
   const float* conv_w;
@@ -301,7 +314,7 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
   const int u_e = rank * UPC + ulc;                       // global hidden unit
   const int epi_warps = (UPC * NB + 31) / 32;
   const int e_w0 = (epi ? (ulc >> 2) : 0) * g.KSg;        // first contributing warp of my gate tile
-  const int z_word = bfrag_word(u_e, epi ? n_e : 0);
+  const int z_word = qfrag_word(u_e & ~3, epi ? n_e : 0);   // first word of my unit's quad
   float cell = 0.f;
   const float* ex_ptr = p.embx + static_cast<int64_t>(epi_ok ? b_e : 0) * R * 4 * Hd + u_e;
   int64_t sv_idx = static_cast<int64_t>(epi_ok ? b_e : 0) * L * Hd + u_e;
@@ -389,12 +402,16 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
           zc_z_ptr[0] = zb16;
         }
       }
-      const uint32_t up = __shfl_down_sync(0xffffffffu, zbits, 1);
-      if (epi && (ulc & 1) == 0) {
-        const uint32_t word = zbits | (up << 16);
+      // the 4 lanes of a quad (UPC % 4 == 0, so they are lanes 4j..4j+3) gather its two words; each then pushes
+      // the 8 bytes to a quarter of the cluster
+      const uint32_t nb = __shfl_xor_sync(0xffffffffu, zbits, 1);
+      const uint32_t wp = (ulc & 1) ? (nb | (zbits << 16)) : (zbits | (nb << 16));
+      const uint32_t wo = __shfl_xor_sync(0xffffffffu, wp, 2);
+      if (epi) {
+        const uint32_t w0 = (ulc & 2) ? wo : wp, w1 = (ulc & 2) ? wp : wo;
         const uint32_t off = zB_base + 4u * static_cast<uint32_t>(zb_nxt_w + z_word);
 #pragma unroll
-        for (int r = 0; r < kCS; ++r) st_remote_u32(mapa(off, r), word);
+        for (int i = 0; i < kCS / 4; ++i) st_remote_v2_u32(mapa(off, (ulc & 3) * (kCS / 4) + i), w0, w1);
       }
     }
     sv_idx += Hd; zc_z_ptr += ZC;
@@ -588,21 +605,28 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
           if (va) ha = dropout_keep(seed, p.drop_site, base + oa, p.drop_p) ? __float2bfloat16(__bfloat162float(ha) * sc) : __float2bfloat16(0.f);
           if (vb) hb = dropout_keep(seed, p.drop_site, base + ob, p.drop_p) ? __float2bfloat16(__bfloat162float(hb) * sc) : __float2bfloat16(0.f);
         }
-        // pair (o, o+1): the partner is the lane 4 further (gq + 1)
+        // The 8 lanes with tig == 0 hold dims gq (wa) and gq + 8 (wb) of this warp's 16-dim tile = one (k-tile,
+        // utterance) row of the state buffer, 32 contiguous bytes. Three xor-shuffle rounds give every one of them
+        // the whole row; lane gq pushes it to CTAs 2gq and 2gq+1 as two 16-byte stores each.
         const uint32_t wa = __bfloat16_as_ushort(ha), wb = __bfloat16_as_ushort(hb);
-        const uint32_t ua = __shfl_down_sync(0xffffffffu, wa, 4), ub = __shfl_down_sync(0xffffffffu, wb, 4);
-        if (tig == 0 && (gq & 1) == 0) {
-          if (va) {
-            const uint32_t off = zB_base + 4u * static_cast<uint32_t>(zb_nxt_w + bfrag_word(Hd + oa, n_own));
-            const uint32_t word = wa | (ua << 16);
+        const uint32_t a1 = __shfl_xor_sync(0xffffffffu, wa, 4), b1 = __shfl_xor_sync(0xffffffffu, wb, 4);
+        const uint32_t pa = (gq & 1) ? (a1 | (wa << 16)) : (wa | (a1 << 16));
+        const uint32_t pb = (gq & 1) ? (b1 | (wb << 16)) : (wb | (b1 << 16));
+        const uint32_t a2 = __shfl_xor_sync(0xffffffffu, pa, 8), b2 = __shfl_xor_sync(0xffffffffu, pb, 8);
+        const uint32_t qa0 = (gq & 2) ? a2 : pa, qa1 = (gq & 2) ? pa : a2;
+        const uint32_t qb0 = (gq & 2) ? b2 : pb, qb1 = (gq & 2) ? pb : b2;
+        const uint32_t xa0 = __shfl_xor_sync(0xffffffffu, qa0, 16), xa1 = __shfl_xor_sync(0xffffffffu, qa1, 16);
+        const uint32_t xb0 = __shfl_xor_sync(0xffffffffu, qb0, 16), xb1 = __shfl_xor_sync(0xffffffffu, qb1, 16);
+        if (tig == 0 && va) {     // OS % 16 == 0 on this path: every tile is full
+          const bool hi = (gq & 4) != 0;
+          const uint32_t A0 = hi ? xa0 : qa0, A1 = hi ? xa1 : qa1, A2 = hi ? qa0 : xa0, A3 = hi ? qa1 : xa1;
+          const uint32_t B0 = hi ? xb0 : qb0, B1 = hi ? xb1 : qb1, B2 = hi ? qb0 : xb0, B3 = hi ? qb1 : xb1;
+          const uint32_t off = zB_base + 4u * static_cast<uint32_t>(zb_nxt_w + qfrag_word(Hd + q * OS + 16 * c_mt, n_own));
 #pragma unroll
-            for (int r = 0; r < kCS; ++r) st_remote_u32(mapa(off, r), word);
-          }
-          if (vb) {
-            const uint32_t off = zB_base + 4u * static_cast<uint32_t>(zb_nxt_w + bfrag_word(Hd + ob, n_own));
-            const uint32_t word = wb | (ub << 16);
-#pragma unroll
-            for (int r = 0; r < kCS; ++r) st_remote_u32(mapa(off, r), word);
+          for (int i = 0; i < 2; ++i) {
+            const uint32_t dst = mapa(off, 2 * gq + i);
+            st_remote_v4_u32(dst, A0, A1, A2, A3);
+            st_remote_v4_u32(dst + 16u, B0, B1, B2, B3);
           }
         }
       }
@@ -1267,7 +1291,9 @@ static int pick_nb(const las_dec_args* a, DGeom& g, BGeom& bg) {
 }
 
 int dec_persist_supported(const las_dec_args* a) {
-  if (a->mode != 0 || a->Q == nullptr || a->wr2_pk == nullptr || a->cbias == nullptr || a->pbar == nullptr) return 0;
+  if (a->mode != 0 || a->Q == nullptr || a->wr2_pk == nullptr || a->mlp_dec_pk_p == nullptr || a->cbias == nullptr ||
+      a->pbar == nullptr)
+    return 0;
   if (a->drop_p > 0.f && a->seed_dev == nullptr) return 0;
   DGeom g;
   BGeom bg;
@@ -1386,7 +1412,7 @@ int dec_persist_fwd(const las_dec_args* a, cudaStream_t stream) {
   p.att_scaling = a->att_scaling;
   p.g = g;
   p.P = a->P; p.Q = static_cast<const __nv_bfloat16*>(a->Q); p.embx = a->embx;
-  p.wr_pk = static_cast<const uint32_t*>(a->wr2_pk); p.dec_pk = static_cast<const uint32_t*>(a->mlp_dec_pk);
+  p.wr_pk = static_cast<const uint32_t*>(a->wr2_pk); p.dec_pk = static_cast<const uint32_t*>(a->mlp_dec_pk_p);
   p.cbias = a->cbias; p.pbar = a->pbar; p.conv_w = a->conv_w; p.mlp_att = a->mlp_att; p.gvec = a->gvec;
   p.ws = a->ws; p.zc = static_cast<__nv_bfloat16*>(a->zc); p.dzf = a->dzf;
   p.gates_save = static_cast<__half*>(a->gates_save); p.c_save = a->c_save;

@@ -45,11 +45,11 @@ __global__ void pack_afrag_kernel(const float* __restrict__ W, int64_t ld, int r
     const int rl = g + 8 * (j & 1);
     int c0 = 16 * kt + 2 * tig + 8 * (j >> 1);
     int row;
-    if (mode == 3) {   // mode 2 rows; K positions of each k-tile permuted: quad q = units 4q..4q+3 at {2q, 2q+1, 2q+8, 2q+9}
+    if (mode == 3 || mode == 4) {   // mode 3: mode 2 rows, mode 4: mode 0 rows; K positions of each k-tile permuted: quad q = units 4q..4q+3 at {2q, 2q+1, 2q+8, 2q+9}
       const int p0 = 2 * tig + 8 * (j >> 1);
       c0 = 16 * kt + 4 * ((p0 & 7) >> 1) + 2 * (p0 >> 3);
     }
-    if (mode == 0) {
+    if (mode == 0 || mode == 4) {
       row = 16 * tile + rl;
     } else if (mode == 2 || mode == 3) {
       const int unit = 4 * tile + (rl & 3);

@@ -257,11 +257,12 @@ class SupervisedTrainer:
             ev.record(cs)
         return self.rb_host[k], ev
 
-    def steps(self, batches, lag=1):
+    def steps(self, batches, lag=2):
         """Train on an iterable of host batches (xs [B, T, D] ideally pinned, ilens, ys); yields (loss, grad_norm)
         per batch as HOST scalars (0-dim CPU tensors), in order. Two overlaps: the host->device copy of batch i+1
         runs during step i, and the results of step i are read back on the copy stream and handed out only after
-        step i+`lag` has been enqueued, so the GPU never waits for the host between steps."""
+        step i+`lag` has been enqueued, so the GPU never waits for the host between steps (lag 2 also rides out
+        host stalls of up to one step time: driver-lock contention, garbage collection)."""
         import collections
         it = iter(batches)
         nxt = next(it, None)

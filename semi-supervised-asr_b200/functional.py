@@ -531,7 +531,8 @@ def _build_dec_fwd(W, mode):
         d["out_pk"] = pack_afrag(W["out_w"], 0)
     elif DEC_PERSISTENT:
         d["mlp_o_bf"] = cvt_bf16(W["mlp_o_w"])
-        d["wr2_pk"] = pack_afrag(d["wr_cat"], 2, Hd)
+        d["wr2_pk"] = pack_afrag(d["wr_cat"], 3, Hd)               # quad tiles, quad-permuted K (persistent kernel)
+        d["mlp_dec_pk_p"] = pack_afrag(W["mlp_dec_w"], 4)
     d["out_bf"] = cvt_bf16(W["out_w"])
     return d
 
@@ -658,6 +659,7 @@ class DecoderFn(torch.autograd.Function):
             Pc = (Pm.view(B, Te, A) - Pbar.unsqueeze(1)).contiguous()
             wr2_pk = Pk["wr2_pk"]
             a.Q, a.wr2_pk, a.cbias, a.pbar = ptr(Qm), ptr(wr2_pk), ptr(cbias), ptr(Pbar)
+            a.mlp_dec_pk_p = ptr(Pk["mlp_dec_pk_p"])
             persist = bool(_lib.lib().las_dec_persistent_supported(ctypes.byref(a)))
             if persist:
                 cpre = torch.empty(B, L, O, **f32)
@@ -777,6 +779,7 @@ class DecoderFn(torch.autograd.Function):
             de_all = torch.zeros(B, L, Te, **f32)
             dc_all = torch.zeros(B, L, O, **f32)
             a.Q, a.wr2_pk, a.cpre, a.conv_save = ptr(pers["Qm"]), ptr(pers["wr2_pk"]), ptr(pers["cpre"]), ptr(pers["conv_save"])
+            a.mlp_dec_pk_p = ptr(S["Pk"]["mlp_dec_pk_p"])
             a.wrT2_pk, a.mlp_decT2_pk, a.de_all, a.dc_all = ptr(wrT2), ptr(decT2), ptr(de_all), ptr(dc_all)
             a.cbias, a.pbar, a.P = ptr(pers["cbias"]), ptr(pers["Pbar"]), ptr(pers["Pc"])
             if not L_.las_dec_persistent_supported(ctypes.byref(a)):
