@@ -662,10 +662,10 @@ __global__ void __launch_bounds__(256) att_denc_kernel(const float* __restrict__
 // and recomputes s = tanh(P + dz_t + mlp_att conv_t) from the saved conv features and energy gradients:
 //   dP[b,te,a] = sum_t ds,  part[cta][c][a] = sum ds*conv[c],  part[cta][CM][a] = sum de*s,  ds = de gv (1 - s^2)
 // grid (ceil(Te/kPG), B), block = A rounded up to a warp multiple.
-constexpr int kPG = 8;   // frames per CTA: small tiles keep ~4 CTAs per SM in flight (the loop is latency-bound)
+constexpr int kPG = 8;   // frames per CTA; blocks of <= 320 threads are compiled for two CTAs per SM (the loop is latency-bound)
 constexpr int kPGT = 16;   // decoder steps per shared-memory chunk
-template <int CM>
-__global__ void __launch_bounds__(512) att_param_grad_kernel(const float* __restrict__ P, const float* __restrict__ dzf,
+template <int CM, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) att_param_grad_kernel(const float* __restrict__ P, const float* __restrict__ dzf,
                                                              const float* __restrict__ conv_save,
                                                              const float* __restrict__ de_all,
                                                              const float* __restrict__ mlp_att,
@@ -844,10 +844,21 @@ int las_att_param_grads(const float* P, const float* dzf, const float* conv_save
   const int CM = (C + 3) / 4 * 4;          // channel count padded to whole float4 pieces: no FMAs on padding beyond that
   const int threads = (A + 31) / 32 * 32;
   const dim3 grid((Te + kPG - 1) / kPG, B);
-  if (CM == 4) att_param_grad_kernel<4><<<grid, threads, 0, stream>>>(P, dzf, conv_save, de_all, mlp_att, gvec, B, L, Te, A, C, threads, dP, part_ws);
-  else if (CM == 8) att_param_grad_kernel<8><<<grid, threads, 0, stream>>>(P, dzf, conv_save, de_all, mlp_att, gvec, B, L, Te, A, C, threads, dP, part_ws);
-  else if (CM == 12) att_param_grad_kernel<12><<<grid, threads, 0, stream>>>(P, dzf, conv_save, de_all, mlp_att, gvec, B, L, Te, A, C, threads, dP, part_ws);
-  else att_param_grad_kernel<16><<<grid, threads, 0, stream>>>(P, dzf, conv_save, de_all, mlp_att, gvec, B, L, Te, A, C, threads, dP, part_ws);
+  // blocks of <= 320 threads are compiled for two CTAs per SM (<= 102 registers): the loop is latency-bound
+#define LAS_APG(CMV)                                                                                                   \
+  do {                                                                                                                 \
+    if (threads <= 320)                                                                                                \
+      att_param_grad_kernel<CMV, 320, 2><<<grid, threads, 0, stream>>>(P, dzf, conv_save, de_all, mlp_att, gvec, B, L, \
+                                                                        Te, A, C, threads, dP, part_ws);                \
+    else                                                                                                               \
+      att_param_grad_kernel<CMV, 512, 1><<<grid, threads, 0, stream>>>(P, dzf, conv_save, de_all, mlp_att, gvec, B, L, \
+                                                                        Te, A, C, threads, dP, part_ws);                \
+  } while (0)
+  if (CM == 4) LAS_APG(4);
+  else if (CM == 8) LAS_APG(8);
+  else if (CM == 12) LAS_APG(12);
+  else LAS_APG(16);
+#undef LAS_APG
   ++g_launches;
   att_part_reduce_kernel<<<((C + 1) * A + 255) / 256, 256, 0, stream>>>(part_ws, grid.x * grid.y, CM, threads, A, C, dmlp_att, dgvec); ++g_launches;
   LAS_LAUNCH_CHECK();
