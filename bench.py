@@ -365,7 +365,7 @@ def kernel_roofline(dev, hbm_peak, which):
             "frac": ach / hbm_peak, "traffic": NCU_TRAFFIC_BYTES, "traffic_source": "profiles/r01z_ncu_full_summary.txt (dram read 329.3 MB + write 366.6 MB per launch)",
             "us_per_launch": us, "us_per_timestep": us / T,
             "algorithmic_bytes_per_launch": bytes_per_launch,
-            "note": "latency-bound serial recurrence: the binding resource is the per-timestep DSMEM exchange, not HBM"}
+            "note": "latency-bound serial recurrence: T dependent steps, each a per-warp chain MMA -> gate math -> DSMEM push (DESIGN.md 4b); HBM traffic equals the algorithmic bytes, the time does not"}
 
 
 if __name__ == "__main__":
