@@ -317,11 +317,19 @@ class SSLTrainer:
     `.grad` fields (dis_opt never steps in this phase)."""
 
     def __init__(self, model, judge, optimizer, max_grad_norm=5.0, unsup_weight=0.001, proportion=0.125,
-                 smooth=True, scaling=3.0, guard_empty_mask=True):
+                 smooth=True, scaling=3.0, guard_empty_mask=True, use_graph=False):
         self.guard_empty_mask = guard_empty_mask
         self.model, self.judge, self.opt = model, judge, optimizer
         self.max_grad_norm, self.unsup_weight, self.proportion = max_grad_norm, unsup_weight, proportion
         self.smooth, self.scaling = smooth, scaling
+        # graph mode (fused optimiser only): the whole generator step -- both encoder/decoder passes, the judge, the
+        # backward with its side-stream weight gradients, clip + AMSGrad -- is captured once per batch geometry
+        self.use_graph = use_graph and hasattr(optimizer, "clip_and_step") and os.environ.get("LAS_NO_GRAPH", "0") != "1"
+        self.static = {}
+        self.cap_stream = None
+        self.world = 1
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.world = torch.distributed.get_world_size()
 
     def losses(self, lab, unlab):
         m = self.model
@@ -355,7 +363,92 @@ class SSLTrainer:
         sup = -torch.mean(logp)                                                     # solver.py:482
         return sup + self.unsup_weight * unsup, sup, unsup, (u_logp, u_pred, lm_probs)
 
+    # ---- device-resident body (no host work; CUDA-graph capturable)
+    def _body_dev(self, st, L, Lu):
+        m = self.model
+        enc, dec = m.encoder.enc2, m.decoder
+        jobs = enc.prep_jobs() + dec.prep_jobs(2 if self.smooth else 1) + dec.prep_jobs(0)
+        jobs.sort(key=lambda j: "bwd" in j[0])
+        Fn.prepare_ahead(jobs)
+        u_enc = enc.forward_dev(st.ux, st.ulens)
+        _, u_logp, u_pred, _ = dec.forward_dev(u_enc, enc.out_lens_dev(st.ulens), None, None, Lu, 2 if self.smooth else 1,
+                                               self.scaling, False)
+        with torch.no_grad():
+            _, lm_probs, _ = self.judge(ys=u_pred, discrete_input=False)
+        mask = (u_pred != dec.eos).float()
+        denom = torch.sum(mask)
+        if self.guard_empty_mask:
+            denom = denom.clamp_min(1.0)
+        unsup = -torch.sum(lm_probs * u_logp * mask) / denom
+        enc_h = enc.forward_dev(st.x, st.lens)
+        _, logp, _, _ = dec.forward_dev(enc_h, enc.out_lens_dev(st.lens), st.ys_in, st.ys_out, L, 0)
+        sup = -torch.mean(logp)
+        loss = sup + self.unsup_weight * unsup
+        self.opt.zero_grad()
+        with Fn.deferred_wgrad():
+            loss.backward()
+        if self.world > 1:
+            return loss.detach(), sup.detach(), unsup.detach(), None
+        norm = self.opt.clip_and_step(self.max_grad_norm, grad_scale=1.0)
+        return loss.detach(), sup.detach(), unsup.detach(), norm
+
+    def stage(self, lab, unlab):
+        """Host -> device copies of one (paired, unpaired) batch pair into the static buffers of its geometry."""
+        (xs, ilens, ys), (uxs, uilens) = lab, unlab
+        m = self.model
+        dev = next(m.parameters()).device
+        host_lens = [int(l) for l in (ilens.tolist() if torch.is_tensor(ilens) else ilens)]
+        uhost = [int(l) for l in (uilens.tolist() if torch.is_tensor(uilens) else uilens)]
+        T, Tu = max(host_lens), max(uhost)
+        ys_in, ys_out = build_targets(ys, m.decoder.bos, m.decoder.eos, m.decoder.pad)
+        B, L = ys_out.shape
+        Lu = int(uxs.size(1) * self.proportion)                                    # solver.py:469 (padded extent as given)
+        key = (B, T, xs.shape[2], L, len(uhost), Tu, Lu)
+        st = self.static.get(key)
+        if st is None:
+            st = self.static[key] = _Static(B, T, xs.shape[2], L, dev)
+            st.ux = torch.zeros(len(uhost), Tu, xs.shape[2], device=dev, dtype=torch.float32)
+            st.ulens = torch.zeros(len(uhost), device=dev, dtype=torch.int32)
+            st.out = None
+        st.x.copy_(xs[:, :T], non_blocking=True)
+        st.ux.copy_(uxs[:, :Tu], non_blocking=True)
+        st.lens.copy_(torch.tensor(host_lens, dtype=torch.int32), non_blocking=True)
+        st.ulens.copy_(torch.tensor(uhost, dtype=torch.int32), non_blocking=True)
+        st.ys_in.copy_(torch.from_numpy(ys_in), non_blocking=True)
+        st.ys_out.copy_(torch.from_numpy(ys_out), non_blocking=True)
+        return key
+
+    def run(self, key):
+        st = self.static[key]
+        L, Lu = key[3], key[6]
+        self.model.train()
+        self.judge.train()
+        if st.graph is None:
+            if st.seen == 0:                       # first sight of a geometry: eager (also warms lazy init)
+                st.seen = 1
+                out = self._body_dev(st, L, Lu)
+                return self._finish(out)
+            g = torch.cuda.CUDAGraph()
+            Fn.warm_deferred(st.x.device)
+            torch.cuda.synchronize()
+            if self.cap_stream is None:
+                self.cap_stream = torch.cuda.Stream(device=st.x.device, priority=-1)
+            with torch.cuda.graph(g, stream=self.cap_stream):
+                st.out = self._body_dev(st, L, Lu)
+            st.graph = g
+        st.graph.replay()
+        return self._finish(st.out)
+
+    def _finish(self, out):
+        loss, sup, unsup, norm = out
+        if self.world > 1:                         # data parallel: all-reduce + update outside the captured part
+            torch.distributed.all_reduce(self.opt.flat_grad)
+            norm = self.opt.clip_and_step(self.max_grad_norm, grad_scale=1.0 / self.world)
+        return loss, sup, unsup, norm
+
     def step(self, lab, unlab):
+        if self.use_graph:
+            return self.run(self.stage(lab, unlab))
         self.model.train()
         self.judge.train()
         loss, sup, unsup, _ = self.losses(lab, unlab)

@@ -154,3 +154,28 @@ def test_all_eos_free_run_does_not_poison_the_generator():
             assert float(unsup) == 0.0 and bool(torch.isfinite(loss))
         else:
             assert bool(torch.isnan(unsup))
+
+
+def test_ssl_graph_step_equals_eager():
+    """The captured generator step (both passes, judge, backward with side-stream weight gradients, clip + AMSGrad
+    in one CUDA graph) follows the eager trainer's loss trajectory."""
+    G = load_golden("ssl_small")
+    g = G["raw"]
+    E, OPT = pkg("engine"), pkg("optim")
+    lab = (torch.from_numpy(g["x"]).cuda(), g["ilens"].tolist(), [torch.from_numpy(y).cuda() for y in G["ys"]])
+    unlab = (torch.from_numpy(g["ux"]).cuda(), g["uilens"].tolist())
+    traj = {}
+    for use_graph in (False, True):
+        m = e2e_from_golden(G).train()
+        lm = lm_from_golden(G).train()
+        opt = OPT.FusedAdam(m.parameters(), lr=1e-3, weight_decay=1e-6, amsgrad=True)
+        tr = E.SSLTrainer(m, lm, opt, proportion=float(g["proportion"]), use_graph=use_graph)
+        out = []
+        for _ in range(5):
+            loss, sup, unsup, norm = tr.step(lab, unlab)
+            out.append((float(loss), float(sup), float(unsup), float(norm)))     # graph mode reuses static outputs
+        traj[use_graph] = np.array(out)
+    a, b = traj[False], traj[True]
+    assert abs(a[0, 0] - float(g["loss"])) < 1e-3 * abs(float(g["loss"]))       # first step == the reference's
+    assert a[-1, 1] < a[0, 1]                                                  # the supervised loss goes down
+    assert np.allclose(a, b, rtol=5e-3, atol=1e-5), (a, b)

@@ -60,7 +60,8 @@ def config4(args, dev):
               n_layers=2, bos=1, eos=2, pad=0, ls_weight=cfg["ls_weight"], labeldist=ld).to(dev)
     gen_opt = OPT.FusedAdam(m.parameters(), lr=1e-4, weight_decay=1e-6, amsgrad=True)
     dis_opt = OPT.FusedAdam(lm.parameters(), lr=2e-4)
-    ssl = E.SSLTrainer(m, lm, gen_opt, max_grad_norm=5.0, unsup_weight=0.001, proportion=0.125, smooth=True, scaling=3.0)
+    ssl = E.SSLTrainer(m, lm, gen_opt, max_grad_norm=5.0, unsup_weight=0.001, proportion=0.125, smooth=True, scaling=3.0,
+                       use_graph=not args.no_graph)
     jt = E.JudgeTrainer(lm, dis_opt, max_grad_norm=5.0)
     lab = (torch.from_numpy(x).to(dev), lens, [torch.from_numpy(y).to(dev) for y in ys])
     unlab = (torch.from_numpy(ux).to(dev), ulens)
@@ -79,7 +80,7 @@ def config4(args, dev):
         {"config": 4, "workload": "semi-supervised generator step: paired B=32 + unpaired speech B=32, Tmax=1000, Lu=125 smooth free-run, LM judge 2x640",
          "ms_per_step": ms, "utt_per_s_paired_plus_unpaired": 64 / (ms * 1e-3), "utt_per_s_paired": 32 / (ms * 1e-3),
          "loss": first[0], "sup": first[1], "unsup": first[2], "steps": args.steps, "dropout": args.dropout,
-         "free_run_diag": diag, "cuda_graph": False},
+         "free_run_diag": diag, "cuda_graph": not args.no_graph},
         {"config": 4, "workload": "judge (LM 2x640) pre-train step on a text batch of 32 (L<=125+5)", "ms_per_step": ms_j,
          "texts_per_s": 32 / (ms_j * 1e-3), "steps": args.steps, "cuda_graph": False},
     ]
@@ -121,6 +122,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--dropout", type=float, default=0.3)
     ap.add_argument("--only", default="4,5")
+    ap.add_argument("--no-graph", action="store_true")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
