@@ -215,14 +215,22 @@ struct NextEmbParams {
   int64_t* pred; int64_t pred_ld;       // pred[b*pred_ld]
   __nv_bfloat16* emb_out; int64_t eo_ld;
 };
+// One CTA (4 warps) per utterance; dynamic shared memory: V floats (softmax numerators).
 __global__ void __launch_bounds__(128) next_emb_kernel(NextEmbParams p) {
-  const int lane = threadIdx.x & 31;
-  const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
-  if (b >= p.B) return;
+  extern __shared__ float ne_sm[];
+  __shared__ float s_mx, s_inv;
+  __shared__ int s_amax;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.x;
   const float* x = p.logits + b * p.lg_ld;
-  float mx;
-  const int amax = warp_argmax(x, p.V, lane, &mx);
-  if (lane == 0) p.pred[b * p.pred_ld] = amax;
+  if (warp == 0) {
+    float mx;
+    const int amax = warp_argmax(x, p.V, lane, &mx);
+    if (lane == 0) { s_mx = mx; s_amax = amax; p.pred[b * p.pred_ld] = amax; }
+  }
+  __syncthreads();
+  const float mx = s_mx;
+  const int amax = s_amax;
   const unsigned long long seed = p.drop_p > 0.f ? *p.seed_dev : 0ull;
   auto drop = [&](float v, int j) {
     if (p.drop_p <= 0.f) return v;
@@ -230,17 +238,24 @@ __global__ void __launch_bounds__(128) next_emb_kernel(NextEmbParams p) {
                ? v / (1.f - p.drop_p) : 0.f;
   };
   if (!p.smooth) {
-    for (int j = lane; j < p.E; j += 32) p.emb_out[b * p.eo_ld + j] = __float2bfloat16(drop(p.emb_w[amax * p.E + j], j));
+    for (int j = threadIdx.x; j < p.E; j += 128) p.emb_out[b * p.eo_ld + j] = __float2bfloat16(drop(p.emb_w[amax * p.E + j], j));
     return;
   }
-  float se = 0.f;
-  for (int v = lane; v < p.V; v += 32) se += __expf(p.scaling * (x[v] - mx));
-  se = warp_sum(se);
-  const float inv = 1.f / se;
-  for (int j = lane; j < p.E; j += 32) {
+  // softmax numerators once per utterance (not once per output dimension), then a V-term dot product per dimension
+  for (int v = threadIdx.x; v < p.V; v += 128) ne_sm[v] = __expf(p.scaling * (x[v] - mx));
+  __syncthreads();
+  if (warp == 0) {
+    float se = 0.f;
+    for (int v = lane; v < p.V; v += 32) se += ne_sm[v];
+    se = warp_sum(se);
+    if (lane == 0) s_inv = 1.f / se;
+  }
+  __syncthreads();
+  const float inv = s_inv;
+  for (int j = threadIdx.x; j < p.E; j += 128) {
     float s = 0.f;
-    for (int v = 0; v < p.V; ++v) s = fmaf(__expf(p.scaling * (x[v] - mx)) * inv, p.emb_w[v * p.E + j], s);
-    p.emb_out[b * p.eo_ld + j] = __float2bfloat16(drop(s, j));
+    for (int v = 0; v < p.V; ++v) s = fmaf(ne_sm[v], p.emb_w[v * p.E + j], s);
+    p.emb_out[b * p.eo_ld + j] = __float2bfloat16(drop(s * inv, j));
   }
 }
 
@@ -257,38 +272,51 @@ struct SmoothBwdParams {
   const float* dlogits; int64_t dl_ld;    // incoming gradient rows
   float* dl_tot; int64_t dt_ld;           // out rows
 };
+// One CTA (4 warps) per utterance; dynamic shared memory: E floats (demb) + V floats (dp).
 __global__ void __launch_bounds__(128) smooth_dlogit_kernel(SmoothBwdParams p) {
-  const int lane = threadIdx.x & 31;
-  const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
-  if (b >= p.B) return;
+  extern __shared__ float sd_sm[];
+  float* de_s = sd_sm;            // [E]
+  float* dp_s = sd_sm + p.E;      // [V]: dp[v] = <E[v, :], demb>
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.x;
   const float* x = p.logits + b * p.lg_ld;
   float* de = const_cast<float*>(p.demb) + b * p.de_ld;
-  if (p.drop_p > 0.f) {   // gradient w.r.t. the un-dropped embedding (each warp owns its row of the scratch)
-    const unsigned long long seed = *p.seed_dev;
-    for (int j = lane; j < p.E; j += 32)
-      de[j] = dropout_keep(seed, p.site, (static_cast<unsigned long long>(b) * p.R + p.row) * p.E + j, p.drop_p)
-                  ? de[j] / (1.f - p.drop_p) : 0.f;
-    __syncwarp();
+  {
+    const unsigned long long seed = p.drop_p > 0.f ? *p.seed_dev : 0ull;
+    for (int j = threadIdx.x; j < p.E; j += 128) {
+      float v = de[j];
+      if (p.drop_p > 0.f) {   // gradient w.r.t. the un-dropped embedding (kept in the scratch row as before)
+        v = dropout_keep(seed, p.site, (static_cast<unsigned long long>(b) * p.R + p.row) * p.E + j, p.drop_p)
+                ? v / (1.f - p.drop_p) : 0.f;
+        de[j] = v;
+      }
+      de_s[j] = v;
+    }
   }
+  __syncthreads();
+  for (int v = warp; v < p.V; v += 4) {   // a warp per vocabulary row: coalesced reads of E[v, :]
+    float dp = 0.f;
+    for (int j = lane; j < p.E; j += 32) dp = fmaf(p.emb_w[v * p.E + j], de_s[j], dp);
+    dp = warp_sum(dp);
+    if (lane == 0) dp_s[v] = dp;
+  }
+  __syncthreads();
+  if (warp != 0) return;
   float mx = -INFINITY;
   for (int v = lane; v < p.V; v += 32) mx = fmaxf(mx, x[v]);
   mx = warp_max(mx);
   float se = 0.f, pd = 0.f;
   for (int v = lane; v < p.V; v += 32) {
     const float pv = __expf(p.scaling * (x[v] - mx));
-    float dp = 0.f;
-    for (int j = 0; j < p.E; ++j) dp = fmaf(p.emb_w[v * p.E + j], de[j], dp);
     se += pv;
-    pd = fmaf(pv, dp, pd);
+    pd = fmaf(pv, dp_s[v], pd);
   }
   se = warp_sum(se);
   pd = warp_sum(pd);
   const float inv = 1.f / se, dot = pd * inv;
   for (int v = lane; v < p.V; v += 32) {
     const float pv = __expf(p.scaling * (x[v] - mx)) * inv;
-    float dp = 0.f;
-    for (int j = 0; j < p.E; ++j) dp = fmaf(p.emb_w[v * p.E + j], de[j], dp);
-    p.dl_tot[b * p.dt_ld + v] = p.dlogits[b * p.dl_ld + v] + p.scaling * pv * (dp - dot);
+    p.dl_tot[b * p.dt_ld + v] = p.dlogits[b * p.dl_ld + v] + p.scaling * pv * (dp_s[v] - dot);
   }
 }
 
@@ -959,7 +987,7 @@ int las_dec_fwd(const las_dec_args* a, void* stream_) {
       np.scaling = a->smooth_scaling; np.smooth = (a->mode == 2);
       np.pred = a->pred + t; np.pred_ld = L;
       np.emb_out = emb_op + static_cast<int64_t>(t + 1) * Ep; np.eo_ld = R * Ep;
-      next_emb_kernel<<<(B + 3) / 4, 128, 0, stream>>>(np); ++g_launches;
+      next_emb_kernel<<<B, 128, V * sizeof(float), stream>>>(np); ++g_launches;
     }
   }
   LAS_LAUNCH_CHECK();
@@ -1031,7 +1059,7 @@ int las_dec_bwd(const las_dec_args* a, void* stream_) {
         sp.demb = a->demb_buf; sp.de_ld = Ep; sp.emb_w = a->emb_w;
         sp.dlogits = a->dlogits + static_cast<int64_t>(t + 1) * V; sp.dl_ld = R * V;
         sp.dl_tot = dlt; sp.dt_ld = R * Vq;
-        smooth_dlogit_kernel<<<(B + 3) / 4, 128, 0, stream>>>(sp); ++g_launches;
+        smooth_dlogit_kernel<<<B, 128, (E + V) * sizeof(float), stream>>>(sp); ++g_launches;
       } else {
         LAS_CUDA(cudaMemcpy2DAsync(dlt, R * Vq * sizeof(float), a->dlogits + static_cast<int64_t>(t + 1) * V,
                                    R * V * sizeof(float), V * sizeof(float), B, cudaMemcpyDeviceToDevice, stream));
