@@ -6,7 +6,8 @@
   config 5a supervised train step at B=64, Tmax=2000, 4-layer pBLSTM subsample [1,2,2,2] (Te=250, L<=250)
   config 5b greedy decode (Solver.test semantics, eval mode, 230 steps/utterance): batch 1 and batch 32
 
-Prints one JSON line per measurement. Timing: CUDA events around K steps after W warm-up steps, inputs resident."""
+Prints one JSON line per measurement. Under torchrun (config 4 only) every rank trains on its own
+shard, gradients are all-reduced each step, and the line reports the aggregate. Timing: CUDA events around K steps after W warm-up steps, inputs resident."""
 import argparse
 import importlib
 import json
@@ -34,30 +35,47 @@ def make_e2e(cfg, ld, dropout, dev):
                  ls_weight=cfg["ls_weight"], labeldist=ld).to(dev)
 
 
+WORLD = int(os.environ.get("WORLD_SIZE", "1"))
+RANK = int(os.environ.get("RANK", "0"))
+
+
+def barrier():
+    if WORLD > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+
+
 def timed(fn, steps, warmup):
+    """ms per step, CUDA events, max over ranks (barrier + synchronize on both sides)."""
     for _ in range(warmup):
         fn()
-    torch.cuda.synchronize()
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
         fn()
     e1.record()
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / steps
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], device="cuda", dtype=torch.float64)
+    if WORLD > 1:
+        torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+    return float(ms)
 
 
 def config4(args, dev):
     cfg = dict(BN.CFG)
-    rng = np.random.RandomState(1234)
+    rng = np.random.RandomState(1234 + RANK)
     x, lens, ys = BN.synth_batch(rng, 32, 1000, cfg["input_dim"], cfg["V"])
-    rng_u = np.random.RandomState(2234)
+    rng_u = np.random.RandomState(2234 + RANK)
     ux, ulens, _ = BN.synth_batch(rng_u, 32, 1000, cfg["input_dim"], cfg["V"])
     ld = BN.labeldist_of(ys, cfg["V"])
     torch.manual_seed(1234)
     m = make_e2e(cfg, ld, args.dropout, dev)
     lm = M.LM(output_dim=cfg["V"], embedding_dim=256, hidden_dim=640, dropout_rate=0.5 if args.dropout > 0 else 0.0,
               n_layers=2, bos=1, eos=2, pad=0, ls_weight=cfg["ls_weight"], labeldist=ld).to(dev)
+    if WORLD > 1:                                      # identical initial weights on every rank
+        for p in list(m.parameters()) + list(lm.parameters()):
+            torch.distributed.broadcast(p.data, 0)
     gen_opt = OPT.FusedAdam(m.parameters(), lr=1e-4, weight_decay=1e-6, amsgrad=True)
     dis_opt = OPT.FusedAdam(lm.parameters(), lr=2e-4)
     ssl = E.SSLTrainer(m, lm, gen_opt, max_grad_norm=5.0, unsup_weight=0.001, proportion=0.125, smooth=True, scaling=3.0,
@@ -78,11 +96,12 @@ def config4(args, dev):
                     "from the FIRST step"}
     return [
         {"config": 4, "workload": "semi-supervised generator step: paired B=32 + unpaired speech B=32, Tmax=1000, Lu=125 smooth free-run, LM judge 2x640",
-         "ms_per_step": ms, "utt_per_s_paired_plus_unpaired": 64 / (ms * 1e-3), "utt_per_s_paired": 32 / (ms * 1e-3),
+         "n_gpus": WORLD, "ms_per_step": ms, "utt_per_s_paired_plus_unpaired": 64 * WORLD / (ms * 1e-3),
+         "utt_per_s_paired": 32 * WORLD / (ms * 1e-3),
          "loss": first[0], "sup": first[1], "unsup": first[2], "steps": args.steps, "dropout": args.dropout,
          "free_run_diag": diag, "cuda_graph": not args.no_graph},
         {"config": 4, "workload": "judge (LM 2x640) pre-train step on a text batch of 32 (L<=125+5)", "ms_per_step": ms_j,
-         "texts_per_s": 32 / (ms_j * 1e-3), "steps": args.steps, "cuda_graph": False},
+         "n_gpus": WORLD, "texts_per_s": 32 * WORLD / (ms_j * 1e-3), "steps": args.steps, "cuda_graph": False},
     ]
 
 
@@ -124,15 +143,20 @@ def main():
     ap.add_argument("--only", default="4,5")
     ap.add_argument("--no-graph", action="store_true")
     args = ap.parse_args()
-    dev = torch.device("cuda", 0)
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
     torch.cuda.set_device(dev)
+    if WORLD > 1:
+        torch.distributed.init_process_group("nccl", device_id=dev)
     res = []
     if "4" in args.only:
         res += config4(args, dev)
     if "5" in args.only:
         res += config5(args, dev)
-    for r in res:
-        print(json.dumps(r))
+    if RANK == 0:
+        for r in res:
+            print(json.dumps(r))
+    if WORLD > 1:
+        torch.distributed.destroy_process_group()
 
 
 if __name__ == "__main__":
