@@ -79,11 +79,11 @@ __device__ __forceinline__ void conv_tile(const AttGeom& g, const float* __restr
   }
   for (int i = threadIdx.x; i < g.C * ksz; i += blockDim.x) cw[i] = conv_w[i];
   __syncthreads();
-  for (int i = threadIdx.x; i < kTT * g.C; i += blockDim.x) {
-    const int tl = i / g.C, c = i % g.C;
+  for (int i = threadIdx.x; i < kTT * CM; i += blockDim.x) {
+    const int tl = i / CM, c = i % CM;      // padding channels c >= C are written as exact zeros (0 * garbage may be NaN)
     const int te = te0 + tl;
     float s = 0.f;
-    if (te < g.Te) {
+    if (te < g.Te && c < g.C) {
       const float* wrow = wp + te;  // wp[te + k] = wprev[te + k - K]
       const float* crow = cw + c * ksz;
       for (int k = 0; k < ksz; ++k) s = fmaf(wrow[k], crow[k], s);
@@ -905,11 +905,13 @@ int las_dec_fwd(const las_dec_args* a, void* stream_) {
   const int B = a->B, L = a->L, Te = a->Te, Hd = a->Hd, O = a->O, A = a->A, V = a->V, E = a->E;
   const int ZC = Hd + O;
   const int64_t R = L + 1;  // rows per utterance in the per-step buffers
-  const int CM = (a->C <= 4) ? 4 : 16;
+  const int CM = (a->C + 3) / 4 * 4;       // channels padded to whole float4 pieces
   const int ethreads = (A + 31) / 32 * 32, ewarps = ethreads / 32;
   const size_t esmem = energy_smem(a, CM, ewarps, false);
   if (CM == 4) { if (int rc = ensure_smem(att_energy_fwd_kernel<4>, esmem)) return rc; }
-  else         { if (int rc = ensure_smem(att_energy_fwd_kernel<16>, esmem)) return rc; }
+  else if (CM == 8) { if (int rc = ensure_smem(att_energy_fwd_kernel<8>, esmem)) return rc; }
+  else if (CM == 12) { if (int rc = ensure_smem(att_energy_fwd_kernel<12>, esmem)) return rc; }
+  else { if (int rc = ensure_smem(att_energy_fwd_kernel<16>, esmem)) return rc; }
   const size_t csmem = (Te + 2 + 8 + 8 * 32 * 2) * sizeof(float);
   if (int rc = ensure_smem(att_ctx_fwd_kernel, csmem)) return rc;
   const bool free_run = a->mode != 0;
@@ -959,6 +961,8 @@ int las_dec_fwd(const las_dec_args* a, void* stream_) {
     ep.dz = dz_t;
     ep.wprev = a->ws + static_cast<int64_t>(t) * Te;
     if (CM == 4) att_energy_fwd_kernel<4><<<egrid, ethreads, esmem, stream>>>(ep);
+    else if (CM == 8) att_energy_fwd_kernel<8><<<egrid, ethreads, esmem, stream>>>(ep);
+    else if (CM == 12) att_energy_fwd_kernel<12><<<egrid, ethreads, esmem, stream>>>(ep);
     else att_energy_fwd_kernel<16><<<egrid, ethreads, esmem, stream>>>(ep);
     ++g_launches;
     // (4) w = softmax(scaling * e) over all Te, context = w @ enc_h   (model.py:167-171)
@@ -1007,12 +1011,14 @@ int las_dec_bwd(const las_dec_args* a, void* stream_) {
   const int B = a->B, L = a->L, Te = a->Te, Hd = a->Hd, O = a->O, A = a->A;
   const int ZC = Hd + O;
   const int64_t R = L + 1;
-  const int CM = (a->C <= 4) ? 4 : 16;
+  const int CM = (a->C + 3) / 4 * 4;
   const int ethreads = (A + 31) / 32 * 32, ewarps = ethreads / 32;
   const int Ap = ethreads;
   const size_t esmem = energy_smem(a, CM, ewarps, true);
   if (CM == 4) { if (int rc = ensure_smem(att_energy_bwd_kernel<4>, esmem)) return rc; }
-  else         { if (int rc = ensure_smem(att_energy_bwd_kernel<16>, esmem)) return rc; }
+  else if (CM == 8) { if (int rc = ensure_smem(att_energy_bwd_kernel<8>, esmem)) return rc; }
+  else if (CM == 12) { if (int rc = ensure_smem(att_energy_bwd_kernel<12>, esmem)) return rc; }
+  else { if (int rc = ensure_smem(att_energy_bwd_kernel<16>, esmem)) return rc; }
   const int ksz = 2 * a->K + 1;
   const size_t dsmem = (a->H + static_cast<size_t>(a->C) * ksz) * sizeof(float);
   if (int rc = ensure_smem(att_dw_kernel, dsmem)) return rc;
@@ -1098,6 +1104,8 @@ int las_dec_bwd(const las_dec_args* a, void* stream_) {
     ep.ddz = a->ddz_all + static_cast<int64_t>(t + 1) * A;
     ep.dattc = a->dattc_all + static_cast<int64_t>(t) * B * Te * a->C;
     if (CM == 4) att_energy_bwd_kernel<4><<<egrid, ethreads, esmem, stream>>>(ep);
+    else if (CM == 8) att_energy_bwd_kernel<8><<<egrid, ethreads, esmem, stream>>>(ep);
+    else if (CM == 12) att_energy_bwd_kernel<12><<<egrid, ethreads, esmem, stream>>>(ep);
     else att_energy_bwd_kernel<16><<<egrid, ethreads, esmem, stream>>>(ep);
     ++g_launches;
     // (5) dz_t += mlp_dec^T ddz ; LSTMCell backward -> dgates_t
