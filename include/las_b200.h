@@ -268,6 +268,11 @@ int las_att_param_grads(const float* P, const float* dzf, const float* conv_save
                         const float* mlp_att, const float* gvec, int B, int L, int Te, int A, int C, float* dP,
                         float* part_ws /* scratch: las_att_scratch_floats() */, float* dmlp_att,
                         float* dgvec, void* stream);
+/* the same in two parts, so that only the part the encoder's backward waits for runs on the critical path:
+ * what = 1 writes dP only, what = 2 adds the parameter sums into dmlp_att / dgvec only, what = 3 does both */
+int las_att_param_grads_part(const float* P, const float* dzf, const float* conv_save, const float* de_all,
+                             const float* mlp_att, const float* gvec, int B, int L, int Te, int A, int C, int what,
+                             float* dP, float* part_ws, float* dmlp_att, float* dgvec, void* stream);
 int las_dec_fwd(const las_dec_args* args_host, void* stream);
 int las_dec_bwd(const las_dec_args* args_host, void* stream);
 

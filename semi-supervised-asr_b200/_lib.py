@@ -78,6 +78,7 @@ SIGNATURES = {
     "las_att_dconv": (c_int, [P, P, I, I, I, I, I, P, P, P]),
     "las_att_scratch_floats": (c_int64, [I, I, I, I, I, I]),
     "las_att_param_grads": (c_int, [P, P, P, P, P, P, I, I, I, I, I, P, P, P, P, P]),
+    "las_att_param_grads_part": (c_int, [P, P, P, P, P, P, I, I, I, I, I, I, P, P, P, P, P]),
     "las_dec_fwd": (c_int, [ctypes.POINTER(DecArgs), P]),
     "las_dec_bwd": (c_int, [ctypes.POINTER(DecArgs), P]),
 }

@@ -47,7 +47,7 @@ bool fgeom_for(int H, FGeom& g, int max_cs = 8) {
   g.WPC = (g.Q + cs0 - 1) / cs0;
   g.CS = (g.Q + g.WPC - 1) / g.WPC;
   g.KT = (H + 15) / 16;
-  return g.WPC <= 10 && g.KT <= kMaxKT;
+  return g.WPC <= 12 && g.KT <= kMaxKT;
 }
 
 bool geom_for(int H, Geom& g) {
@@ -139,7 +139,7 @@ struct FwdP {
 // quad rank*WPC + w: its m16 tile holds their 16 gate rows, K = all of H, so a warp needs no partial-sum
 // exchange with other warps and the step loop contains no block-wide barrier: warps are paced only by the
 // mbarrier that counts the bytes of h_t arriving from the cluster.
-__global__ void __launch_bounds__(320, 1) lstm_persist_fwd_kernel(FwdP p) {
+__global__ void __launch_bounds__(384, 1) lstm_persist_fwd_kernel(FwdP p) {
   extern __shared__ __align__(16) uint8_t smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);                    // [2]
   // h_t as B fragments, [2][KT][4 quads][8 utterances][2 words]: the K positions of a k-tile are permuted so that
@@ -623,7 +623,7 @@ void* g_dbg_buf_shared = nullptr;
 
 // resident-cluster capacity of the forward kernel for a geometry (cached per cluster size / block size)
 static int fwd_max_clusters(const FGeom& f) {
-  static int cache[17][11];   // [CS][WPC], 0 = unknown, -1 = failed
+  static int cache[17][13];   // [CS][WPC], 0 = unknown, -1 = failed
   int& c = cache[f.CS][f.WPC];
   if (c != 0) return c > 0 ? c : 0;
   const int threads = 32 * f.WPC;
@@ -655,12 +655,24 @@ int persist_lstm_fwd(const float* xproj, const void* whh_pk, const int32_t* lens
                      int64_t hp_ld_t, void* rec, cudaStream_t stream) {
   // The forward fragments are packed per quad, so the cluster size is free at launch: fewer warps per CTA (two per
   // scheduler instead of three at H = 320) shorten every phase of the step, as long as all clusters stay resident.
+  // Batches that need more 8-CTA clusters than the GPU holds (B = 64, both directions: 16 against 15 on a B200) take
+  // 7-CTA clusters of 12 warps instead of running one cluster as a second wave.
   FGeom g;
   LAS_REQUIRE(fgeom_for(H, g), "persistent LSTM: hidden size %d unsupported", H);
   {
-    FGeom g10;
     const int need = ((B + kNB - 1) / kNB) * ndir;
-    if (fgeom_for(H, g10, 10) && g10.CS > 8 && fwd_max_clusters(g10) >= need) g = g10;
+    const int prefs[3] = {10, 8, 7};
+    for (int i = 0; i < 3; ++i) {
+      FGeom c;
+      if (!fgeom_for(H, c, prefs[i])) continue;
+      if (i == 0 && c.CS <= 8) continue;
+      if (fwd_max_clusters(c) >= need) { g = c; break; }
+    }
+    static const char* force = getenv("LAS_FWD_CS");     // development aid: pin the forward cluster size
+    if (force) {
+      FGeom c;
+      if (fgeom_for(H, c, atoi(force))) g = c;
+    }
   }
   LAS_REQUIRE(y_ld_b % 4 == 0 && y_ld_t % 4 == 0 && hp_ld_b % 4 == 0 && hp_ld_t % 4 == 0 &&
                   reinterpret_cast<uintptr_t>(y) % 8 == 0 && reinterpret_cast<uintptr_t>(hprev) % 8 == 0,

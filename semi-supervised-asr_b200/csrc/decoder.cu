@@ -672,16 +672,54 @@ static int launch_att_dconv(const float* dattc_all, const float* ws_alloc, int L
 }
 
 // denc[b, te, h] (+)= sum_t ws[b, t, te] * dctx[b, t, h]     (gradient of the context bmm)
-__global__ void __launch_bounds__(256) att_denc_kernel(const float* __restrict__ ws_alloc, const float* __restrict__ dctx_all,
+// grid (ceil(Te/kDE), B): a CTA owns kDE frames of one utterance, so dctx[b] is streamed Te/kDE times instead of
+// Te times (one frame per CTA made this kernel L2-bound: 123 us at config 2); the alignment columns of the tile
+// are staged in shared memory per chunk of kDEC steps.
+constexpr int kDE = 8;
+constexpr int kDEC = 128;
+__global__ void __launch_bounds__(320) att_denc_kernel(const float* __restrict__ ws_alloc, const float* __restrict__ dctx_all,
                                                        int L, int B, int Te, int H, float* __restrict__ denc, int accumulate) {
-  const int b = blockIdx.y, te = blockIdx.x;
-  const float* w = ws_alloc + (static_cast<int64_t>(b) * (L + 1) + 1) * Te + te;
+  __shared__ __align__(16) float wt[kDEC][kDE];
+  const int b = blockIdx.y, te0 = blockIdx.x * kDE;
+  const int nte = min(kDE, Te - te0);
+  const float* w = ws_alloc + (static_cast<int64_t>(b) * (L + 1) + 1) * Te + te0;
   const float* d = dctx_all + static_cast<int64_t>(b) * L * H;
-  for (int h = threadIdx.x; h < H; h += 256) {
-    float s = 0.f;
-    for (int t = 0; t < L; ++t) s = fmaf(w[static_cast<int64_t>(t) * Te], d[static_cast<int64_t>(t) * H + h], s);
-    float* o = denc + (static_cast<int64_t>(b) * Te + te) * H + h;
-    *o = accumulate ? *o + s : s;
+  for (int hb = 0; hb < H; hb += blockDim.x) {
+    const int h = hb + threadIdx.x;
+    float acc[kDE];
+#pragma unroll
+    for (int f = 0; f < kDE; ++f) acc[f] = 0.f;
+    for (int t0 = 0; t0 < L; t0 += kDEC) {
+      const int tn = min(kDEC, L - t0);
+      __syncthreads();
+      for (int i = threadIdx.x; i < tn * kDE; i += blockDim.x) {
+        const int tt = i / kDE, f = i % kDE;
+        wt[tt][f] = f < nte ? w[static_cast<int64_t>(t0 + tt) * Te + f] : 0.f;
+      }
+      __syncthreads();
+      if (h < H) {
+        const float* dp = d + static_cast<int64_t>(t0) * H + h;
+#pragma unroll 4
+        for (int tt = 0; tt < tn; ++tt) {
+          const float dv = __ldg(dp + static_cast<int64_t>(tt) * H);
+          const float4 w0 = *reinterpret_cast<const float4*>(&wt[tt][0]);
+          const float4 w1 = *reinterpret_cast<const float4*>(&wt[tt][4]);
+          acc[0] = fmaf(w0.x, dv, acc[0]); acc[1] = fmaf(w0.y, dv, acc[1]);
+          acc[2] = fmaf(w0.z, dv, acc[2]); acc[3] = fmaf(w0.w, dv, acc[3]);
+          acc[4] = fmaf(w1.x, dv, acc[4]); acc[5] = fmaf(w1.y, dv, acc[5]);
+          acc[6] = fmaf(w1.z, dv, acc[6]); acc[7] = fmaf(w1.w, dv, acc[7]);
+        }
+      }
+    }
+    if (h < H) {
+#pragma unroll
+      for (int f = 0; f < kDE; ++f) {
+        if (f < nte) {
+          float* o = denc + (static_cast<int64_t>(b) * Te + te0 + f) * H + h;
+          *o = accumulate ? *o + acc[f] : acc[f];
+        }
+      }
+    }
   }
 }
 
@@ -690,9 +728,11 @@ __global__ void __launch_bounds__(256) att_denc_kernel(const float* __restrict__
 // and recomputes s = tanh(P + dz_t + mlp_att conv_t) from the saved conv features and energy gradients:
 //   dP[b,te,a] = sum_t ds,  part[cta][c][a] = sum ds*conv[c],  part[cta][CM][a] = sum de*s,  ds = de gv (1 - s^2)
 // grid (ceil(Te/kPG), B), block = A rounded up to a warp multiple.
+// WHAT selects the outputs: bit 0 = dP (the critical path: the encoder's backward waits for it), bit 1 = the
+// parameter partial sums (nothing waits for them: the trainers run that instance on the weight-gradient stream).
 constexpr int kPG = 8;   // frames per CTA; blocks of <= 320 threads are compiled for two CTAs per SM (the loop is latency-bound)
 constexpr int kPGT = 16;   // decoder steps per shared-memory chunk
-template <int CM, int MAXT, int MINB>
+template <int CM, int MAXT, int MINB, int WHAT>
 __global__ void __launch_bounds__(MAXT, MINB) att_param_grad_kernel(const float* __restrict__ P, const float* __restrict__ dzf,
                                                              const float* __restrict__ conv_save,
                                                              const float* __restrict__ de_all,
@@ -772,18 +812,22 @@ __global__ void __launch_bounds__(MAXT, MINB) att_param_grad_kernel(const float*
         for (int c = 0; c < CM; ++c) x = fmaf(matt[c], conv[c], x);
         const float sx = tanh_fast(x);
         const float ds = de * gv * (1.f - sx * sx);
-        dp[f] += ds;
-        dgv = fmaf(de, sx, dgv);
+        if (WHAT & 1) dp[f] += ds;
+        if (WHAT & 2) {
+          dgv = fmaf(de, sx, dgv);
 #pragma unroll
-        for (int c = 0; c < CM; ++c) dmatt[c] = fmaf(ds, conv[c], dmatt[c]);
+          for (int c = 0; c < CM; ++c) dmatt[c] = fmaf(ds, conv[c], dmatt[c]);
+        }
       }
     }
     __syncthreads();
   }
-  if (ok) {
+  if (ok && (WHAT & 1)) {
 #pragma unroll
     for (int f = 0; f < kPG; ++f)
       if (f < ntl) dP[(static_cast<int64_t>(b) * Te + te0 + f) * A + a] = dp[f];
+  }
+  if (ok && (WHAT & 2)) {
     float* pp = part + static_cast<int64_t>(blockIdx.y * gridDim.x + blockIdx.x) * (CM + 1) * Ap + a;
 #pragma unroll
     for (int c = 0; c < CM; ++c) pp[c * Ap] = dmatt[c];
@@ -839,7 +883,7 @@ int las_dec_persistent_pack(int which, const float* W, int64_t ld, int Hd, int O
 
 int las_att_dq(const float* ws_alloc, const float* dc_all, int L, int B, int Te, int O, float* dQ, void* stream) {
   if (B == 0 || Te == 0) return 0;
-  att_denc_kernel<<<dim3(Te, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(ws_alloc, dc_all, L, B, Te, O, dQ, 0); ++g_launches;
+  att_denc_kernel<<<dim3((Te + kDE - 1) / kDE, B), (O <= 256 ? 256 : 320), 0, static_cast<cudaStream_t>(stream)>>>(ws_alloc, dc_all, L, B, Te, O, dQ, 0); ++g_launches;
   LAS_LAUNCH_CHECK();
   return 0;
 }
@@ -863,34 +907,51 @@ int las_att_dconv(const float* dattc_all, const float* ws_alloc, int L, int B, i
   return 0;
 }
 
-int las_att_param_grads(const float* P, const float* dzf, const float* conv_save, const float* de_all,
-                        const float* mlp_att, const float* gvec, int B, int L, int Te, int A, int C, float* dP,
-                        float* part_ws, float* dmlp_att, float* dgvec, void* stream_) {
+int las_att_param_grads_part(const float* P, const float* dzf, const float* conv_save, const float* de_all,
+                             const float* mlp_att, const float* gvec, int B, int L, int Te, int A, int C, int what,
+                             float* dP, float* part_ws, float* dmlp_att, float* dgvec, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   LAS_REQUIRE(A >= 1 && A <= 512 && C >= 1 && C <= 16, "att_param_grads: att_dim / conv_channels out of range");
+  LAS_REQUIRE(what >= 1 && what <= 3, "att_param_grads: what = %d (1 = dP, 2 = parameter gradients, 3 = both)", what);
   if (B == 0 || Te == 0 || L == 0) return 0;
   const int CM = (C + 3) / 4 * 4;          // channel count padded to whole float4 pieces: no FMAs on padding beyond that
   const int threads = (A + 31) / 32 * 32;
   const dim3 grid((Te + kPG - 1) / kPG, B);
   // blocks of <= 320 threads are compiled for two CTAs per SM (<= 102 registers): the loop is latency-bound
-#define LAS_APG(CMV)                                                                                                   \
+#define LAS_APG2(CMV, W)                                                                                               \
   do {                                                                                                                 \
     if (threads <= 320)                                                                                                \
-      att_param_grad_kernel<CMV, 320, 2><<<grid, threads, 0, stream>>>(P, dzf, conv_save, de_all, mlp_att, gvec, B, L, \
-                                                                        Te, A, C, threads, dP, part_ws);                \
+      att_param_grad_kernel<CMV, 320, 2, W><<<grid, threads, 0, stream>>>(P, dzf, conv_save, de_all, mlp_att, gvec, B, \
+                                                                           L, Te, A, C, threads, dP, part_ws);          \
     else                                                                                                               \
-      att_param_grad_kernel<CMV, 512, 1><<<grid, threads, 0, stream>>>(P, dzf, conv_save, de_all, mlp_att, gvec, B, L, \
-                                                                        Te, A, C, threads, dP, part_ws);                \
+      att_param_grad_kernel<CMV, 512, 1, W><<<grid, threads, 0, stream>>>(P, dzf, conv_save, de_all, mlp_att, gvec, B, \
+                                                                           L, Te, A, C, threads, dP, part_ws);          \
+  } while (0)
+#define LAS_APG(CMV)                                                                                                   \
+  do {                                                                                                                 \
+    if (what == 1) LAS_APG2(CMV, 1);                                                                                   \
+    else if (what == 2) LAS_APG2(CMV, 2);                                                                              \
+    else LAS_APG2(CMV, 3);                                                                                             \
   } while (0)
   if (CM == 4) LAS_APG(4);
   else if (CM == 8) LAS_APG(8);
   else if (CM == 12) LAS_APG(12);
   else LAS_APG(16);
 #undef LAS_APG
+#undef LAS_APG2
   ++g_launches;
-  att_part_reduce_kernel<<<((C + 1) * A + 255) / 256, 256, 0, stream>>>(part_ws, grid.x * grid.y, CM, threads, A, C, dmlp_att, dgvec); ++g_launches;
+  if (what & 2) {
+    att_part_reduce_kernel<<<((C + 1) * A + 255) / 256, 256, 0, stream>>>(part_ws, grid.x * grid.y, CM, threads, A, C, dmlp_att, dgvec); ++g_launches;
+  }
   LAS_LAUNCH_CHECK();
   return 0;
+}
+
+int las_att_param_grads(const float* P, const float* dzf, const float* conv_save, const float* de_all,
+                        const float* mlp_att, const float* gvec, int B, int L, int Te, int A, int C, float* dP,
+                        float* part_ws, float* dmlp_att, float* dgvec, void* stream_) {
+  return las_att_param_grads_part(P, dzf, conv_save, de_all, mlp_att, gvec, B, L, Te, A, C, 3, dP, part_ws, dmlp_att,
+                                  dgvec, stream_);
 }
 
 int las_dec_fwd(const las_dec_args* a, void* stream_) {
@@ -1117,7 +1178,7 @@ int las_dec_bwd(const las_dec_args* a, void* stream_) {
   att_part_reduce_kernel<<<((a->C + 1) * A + 255) / 256, 256, 0, stream>>>(a->att_part, ncta, CM, Ap, A, a->C,
                                                                              a->dmlp_att, a->dgvec); ++g_launches;
   if (int rc = launch_att_dconv(a->dattc_all, a->ws, L, B, Te, a->C, a->K, a->dconv_w, a->att_part, stream)) return rc;
-  att_denc_kernel<<<dim3(Te, B), 256, 0, stream>>>(a->ws, a->dctx_all, L, B, Te, a->H, a->denc, a->denc_accumulate); ++g_launches;
+  att_denc_kernel<<<dim3((Te + kDE - 1) / kDE, B), (a->H <= 256 ? 256 : 320), 0, stream>>>(a->ws, a->dctx_all, L, B, Te, a->H, a->denc, a->denc_accumulate); ++g_launches;
   LAS_LAUNCH_CHECK();
   return 0;
 }

@@ -380,6 +380,12 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
     DTRACE(1);
     __syncthreads();
     DTRACE(2);
+    // Global stores of a phase's results are issued AFTER the phase's cluster barrier: the barrier's release is a
+    // memory fence that waits for every store the thread has in flight, and HBM/L2 write acknowledgements ahead of
+    // it were 12 % of this kernel's stall samples (ERRBAR, profiles/r01z_ncu_full_summary.txt). Stored after the
+    // barrier, they complete under the next phase.
+    uint2 sv_pk = make_uint2(0u, 0u);
+    __nv_bfloat16 sv_z = __float2bfloat16(0.f);
     if (warp < epi_warps) {
       uint32_t zbits = 0u;
       if (epi) {
@@ -392,15 +398,10 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
         cell = f * cell + i * gc;
         const __nv_bfloat16 zb16 = __float2bfloat16(o * tanh_acc(cell));
         zbits = epi_ok ? static_cast<uint32_t>(__bfloat16_as_ushort(zb16)) : 0u;
-        if (epi_ok) {
-          __half2 lo = __floats2half2_rn(i, f), hi = __floats2half2_rn(gc, o);
-          uint2 pk;
-          pk.x = *reinterpret_cast<uint32_t*>(&lo);
-          pk.y = *reinterpret_cast<uint32_t*>(&hi);
-          reinterpret_cast<uint2*>(p.gates_save)[sv_idx] = pk;
-          p.c_save[sv_idx] = cell;
-          zc_z_ptr[0] = zb16;
-        }
+        __half2 lo = __floats2half2_rn(i, f), hi = __floats2half2_rn(gc, o);
+        sv_pk.x = *reinterpret_cast<uint32_t*>(&lo);
+        sv_pk.y = *reinterpret_cast<uint32_t*>(&hi);
+        sv_z = zb16;
       }
       // the 4 lanes of a quad (UPC % 4 == 0, so they are lanes 4j..4j+3) gather its two words; each then pushes
       // the 8 bytes to a quarter of the cluster
@@ -414,10 +415,15 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
         for (int i = 0; i < kCS / 4; ++i) st_remote_v2_u32(mapa(off, (ulc & 3) * (kCS / 4) + i), w0, w1);
       }
     }
-    sv_idx += Hd; zc_z_ptr += ZC;
     DTRACE(3);
     cluster_barrier();
     DTRACE(4);
+    if (epi_ok) {
+      reinterpret_cast<uint2*>(p.gates_save)[sv_idx] = sv_pk;
+      p.c_save[sv_idx] = cell;
+      zc_z_ptr[0] = sv_z;
+    }
+    sv_idx += Hd; zc_z_ptr += ZC;
 
     // ================= P2: dz = mlp_dec z_t; location conv of w_{t-1} on tensor cores =================
     if (d_act) {
@@ -460,16 +466,17 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
       cred[(warp * 2 + 1) * 32 + lane] = make_float4(c1[0], c1[1], c1[2], c1[3]);
     }
     __syncthreads();
+    float dz_v = 0.f;
     if (depi_ok) {
-      const float v = red_gather(red, d_w0, g.KSd, al & 15, n_d) + pbar_d;
-      dzf_ptr[0] = v;
+      dz_v = red_gather(red, d_w0, g.KSd, al & 15, n_d) + pbar_d;
       const uint32_t off = dzv_base + 4u * a_d;
-      for (int qq = 0; qq < G; ++qq) st_remote_f32(mapa(off, n_d * G + qq), v);
+      for (int qq = 0; qq < G; ++qq) st_remote_f32(mapa(off, n_d * G + qq), dz_v);
     }
-    dzf_ptr += A;
     DTRACE(5);
     cluster_barrier();
     DTRACE(6);
+    if (depi_ok) dzf_ptr[0] = dz_v;
+    dzf_ptr += A;
 
     // ================= P3: energies of my frames -> all owners of the utterance =================
     if (e_act) {
@@ -542,6 +549,9 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
     DTRACE(10);
 
     // ================= P4: softmax over all Te frames (every owner), context slice, broadcast =================
+    float w_keep = 0.f, ca_keep = 0.f, cb_keep = 0.f;
+    __nv_bfloat16 ha_keep = __float2bfloat16(0.f), hb_keep = ha_keep;
+    bool va_keep = false, vb_keep = false;
     {
       const bool fr = own_ok && tid < Te;
       const float e = fr ? e_all[tid] : -INFINITY;
@@ -561,9 +571,8 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
       for (int w = 0; w < kWarps; ++w) S += wred[kWarps + w];
       const float invS = own_ok ? 1.f / S : 0.f;
       if (fr) {
-        const float w = pv * invS;
-        wbuf[K + tid] = w;
-        if (tid >= te0 && tid < te0 + ntl) ws_row[tid] = w;
+        w_keep = pv * invS;
+        wbuf[K + tid] = w_keep;
       }
       // context slice on tensor cores: c[o] = sum_te QT[o][te] p[te]  (M = my context dims, K = frames, N = column 0)
       if (own_ok && c_mt < g.OTs) {
@@ -587,17 +596,9 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
         const bool va = tig == 0 && o_l0 < OS, vb = tig == 0 && o_l0 + 8 < OS;
         const float ca = acc[0] * invS, cb = acc[2] * invS;
         __nv_bfloat16 ha = __float2bfloat16(0.f), hb = ha;
-        __nv_bfloat16* zrow = p.zc + (static_cast<int64_t>(b_own) * R + t + 1) * ZC + Hd;
-        if (va) {
-          if (p.cpre) p.cpre[(static_cast<int64_t>(b_own) * L + t) * O + oa] = ca;
-          ha = __float2bfloat16(ca + p.cbias[static_cast<int64_t>(b_own) * O + oa]);
-          zrow[oa] = ha;
-        }
-        if (vb) {
-          if (p.cpre) p.cpre[(static_cast<int64_t>(b_own) * L + t) * O + ob] = cb;
-          hb = __float2bfloat16(cb + p.cbias[static_cast<int64_t>(b_own) * O + ob]);
-          zrow[ob] = hb;
-        }
+        if (va) ha = __float2bfloat16(ca + p.cbias[static_cast<int64_t>(b_own) * O + oa]);
+        if (vb) hb = __float2bfloat16(cb + p.cbias[static_cast<int64_t>(b_own) * O + ob]);
+        va_keep = va; vb_keep = vb; ca_keep = ca; cb_keep = cb; ha_keep = ha; hb_keep = hb;
         if (drop_on) {
           // what the NEXT step's gates see is dropout(c_t); the output layer (zc in global memory) sees c_t
           const unsigned long long seed = *p.seed_dev, base = (static_cast<unsigned long long>(b_own) * R + t + 1) * O;
@@ -631,10 +632,26 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
         }
       }
     }
-    ws_row += Te;
     DTRACE(11);
     cluster_barrier();
     DTRACE(12);
+    if (own_ok) {
+      if (tid >= te0 && tid < te0 + ntl) ws_row[tid] = w_keep;      // tid < Te holds: te0 + ntl <= Te
+      if (va_keep | vb_keep) {
+        const int oa = q * OS + o_l0, ob = oa + 8;
+        __nv_bfloat16* zrow = p.zc + (static_cast<int64_t>(b_own) * R + t + 1) * ZC + Hd;
+        float* crow = p.cpre ? p.cpre + (static_cast<int64_t>(b_own) * L + t) * O : nullptr;
+        if (va_keep) {
+          if (crow) crow[oa] = ca_keep;
+          zrow[oa] = ha_keep;
+        }
+        if (vb_keep) {
+          if (crow) crow[ob] = cb_keep;
+          zrow[ob] = hb_keep;
+        }
+      }
+    }
+    ws_row += Te;
   }
 #undef DTRACE
 }
@@ -940,6 +957,7 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
           make_float4(acc0[0] + acc1[0], acc0[1] + acc1[1], acc0[2] + acc1[2], acc0[3] + acc1[3]);
     }
     __syncthreads();
+    float dc_keep = 0.f;
     if (epi_ok) {
       float mm = red_gather(red, a_w0, g.KSb, row_l & 15, n_e);
       if (p.drop_p > 0.f && !is_z)   // the path through the cell input of step t+1 carries that step's dropout mask
@@ -949,8 +967,7 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
       if (is_z) {
         dz_acc = v;
       } else {
-        p.dc_all[(static_cast<int64_t>(b_e) * L + t) * O + o_e] = v;
-        p.dcz_all[(static_cast<int64_t>(b_e) * R + t + 1) * ZC + Hd + o_e] = __float2bfloat16(v);
+        dc_keep = v;
         const uint32_t off = dcbuf_base + 4u * o_e;
         for (int qq = 0; qq < G; ++qq) st_remote_f32(mapa(off, n_e * G + qq), v);
       }
@@ -960,6 +977,11 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
     DTRACE(1);
     cluster_barrier();
     DTRACE(2);
+    // global stores follow the barrier (its release fence would wait for their acknowledgements; see the forward kernel)
+    if (epi_ok && !is_z) {
+      p.dc_all[(static_cast<int64_t>(b_e) * L + t) * O + o_e] = dc_keep;
+      p.dcz_all[(static_cast<int64_t>(b_e) * R + t + 1) * ZC + Hd + o_e] = __float2bfloat16(dc_keep);
+    }
 
     // ================= phase B: attention backward for my frames =================
     // B1: dw = Q dc (tensor cores, K split over the warps of a frame tile); softmax dot product
@@ -1192,8 +1214,8 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
       reinterpret_cast<float4*>(red)[warp * 32 + lane] = make_float4(acc[0], acc[1], acc[2], acc[3]);
     }
     __syncthreads();
+    uint32_t w4[4] = {0u, 0u, 0u, 0u};
     {
-      uint32_t w4[4] = {0u, 0u, 0u, 0u};
       if (epi_ok && is_z) {
         const float dh = dz_acc + red_gather(red, c_w0, g.KSd, row_l & 15, n_e);
         const float2 if_ = __half22float2(*reinterpret_cast<const __half2*>(&gpk.x));
@@ -1206,9 +1228,7 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
                              dh * tc * o * (1.f - o)};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const __nv_bfloat16 h = __float2bfloat16(d4[k]);
-          dg_ptr[k * Hd] = h;
-          w4[k] = __bfloat16_as_ushort(h);
+          w4[k] = __bfloat16_as_ushort(__float2bfloat16(d4[k]));
         }
       }
       if (warp < (RPC * NB + 31) / 32) {
@@ -1225,10 +1245,14 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
         }
       }
     }
-    sv_idx -= Hd; dg_ptr -= 4 * Hd;
     DTRACE(7);
     cluster_barrier();
     DTRACE(8);
+    if (epi_ok && is_z) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) dg_ptr[k * Hd] = __ushort_as_bfloat16(static_cast<unsigned short>(w4[k]));
+    }
+    sv_idx -= Hd; dg_ptr -= 4 * Hd;
   }
 #undef DTRACE
 }

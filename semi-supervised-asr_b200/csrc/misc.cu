@@ -50,6 +50,21 @@ __global__ void relu_bwd_kernel(const float* __restrict__ dout, const void* __re
   }
 }
 
+// the same, 4 elements per thread (n % 4 == 0, 16/8-byte aligned pointers, bf16 activations)
+__global__ void relu_bwd4_kernel(const float4* __restrict__ dout, const uint2* __restrict__ out, uint2* __restrict__ dz,
+                                 int64_t n4) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float4 d = __ldg(dout + i);
+    const uint2 o = __ldg(out + i);
+    const float2 a = unpack_bf16x2(o.x), b = unpack_bf16x2(o.y);
+    uint2 r;
+    r.x = pack_bf16x2(a.x > 0.f ? d.x : 0.f, a.y > 0.f ? d.y : 0.f);
+    r.y = pack_bf16x2(b.x > 0.f ? d.z : 0.f, b.y > 0.f ? d.w : 0.f);
+    dz[i] = r;
+  }
+}
+
 // Column sums of a [rows, cols] matrix (bf16 or f32) into out[cols] (+=): each CTA reduces a
 // 32-column x ROWS_PER_CTA-row slab, one atomicAdd per column per CTA.
 template <typename T>
@@ -182,12 +197,21 @@ __global__ void ce_ls_bwd_kernel(const float* __restrict__ logits, int64_t ld, i
 // ------------------------------------------------------------------------------------------
 __global__ void sqnorm_partial_kernel(const float* __restrict__ g, int64_t n, double* __restrict__ partials) {
   __shared__ double red[8];
-  double s = 0.0;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+  // 16-byte loads, four independent double accumulators per thread (fixed order: the result is deterministic)
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  const int64_t n4 = (reinterpret_cast<uintptr_t>(g) & 15) == 0 ? n >> 2 : 0;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(g) + i);
+    s0 += static_cast<double>(v.x) * v.x; s1 += static_cast<double>(v.y) * v.y;
+    s2 += static_cast<double>(v.z) * v.z; s3 += static_cast<double>(v.w) * v.w;
+  }
+  for (int64_t i = 4 * n4 + blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const double v = g[i];
-    s += v * v;
+    s0 += v * v;
   }
+  double s = (s0 + s1) + (s2 + s3);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
@@ -222,24 +246,46 @@ __global__ void adam_step_kernel(float* __restrict__ p, const float* __restrict_
     coef *= fminf(c, 1.f);
   }
   const float step_size = lr / bc1;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const float pi = p[i];
-    float gi = g[i] * coef;
+  auto elem = [&](float& pi, float gi, float& mi, float& vi, float& vm) {
+    gi *= coef;
     if (wd != 0.f) gi += wd * pi;
-    const float mi = b1 * m[i] + (1.f - b1) * gi;
-    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-    m[i] = mi;
-    v[i] = vi;
+    mi = b1 * mi + (1.f - b1) * gi;
+    vi = b2 * vi + (1.f - b2) * gi * gi;
     float denom;
     if (vmax) {
-      const float vm = fmaxf(vmax[i], vi);
-      vmax[i] = vm;
+      vm = fmaxf(vm, vi);
       denom = sqrtf(vm) / bc2_sqrt + eps;
     } else {
       denom = sqrtf(vi) / bc2_sqrt + eps;
     }
-    p[i] = pi - step_size * (mi / denom);
+    pi = pi - step_size * (mi / denom);
+  };
+  // 16-byte accesses over the aligned body (the flat buffers of optim.FusedAdam are 16-byte aligned), scalar tail
+  const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                     reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(vmax)) & 15) == 0;
+  const int64_t n4 = vec ? n >> 2 : 0;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float4 p4 = reinterpret_cast<float4*>(p)[i], m4 = reinterpret_cast<float4*>(m)[i], v4 = reinterpret_cast<float4*>(v)[i];
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(g) + i);
+    float4 x4 = vmax ? reinterpret_cast<float4*>(vmax)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    elem(p4.x, g4.x, m4.x, v4.x, x4.x);
+    elem(p4.y, g4.y, m4.y, v4.y, x4.y);
+    elem(p4.z, g4.z, m4.z, v4.z, x4.z);
+    elem(p4.w, g4.w, m4.w, v4.w, x4.w);
+    reinterpret_cast<float4*>(m)[i] = m4;
+    reinterpret_cast<float4*>(v)[i] = v4;
+    if (vmax) reinterpret_cast<float4*>(vmax)[i] = x4;
+    reinterpret_cast<float4*>(p)[i] = p4;
+  }
+  for (int64_t i = 4 * n4 + blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float pi = p[i], mi = m[i], vi = v[i], vm = vmax ? vmax[i] : 0.f;
+    elem(pi, g[i], mi, vi, vm);
+    m[i] = mi;
+    v[i] = vi;
+    if (vmax) vmax[i] = vm;
+    p[i] = pi;
   }
 }
 
@@ -299,8 +345,20 @@ __global__ void dropout4_kernel(T* __restrict__ x, int64_t B, int64_t Tn, int W,
   const int64_t rows = Tn + rep_row, total = B * rows * W4;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int c4 = static_cast<int>(i % W4);
-    const int64_t bt = i / W4, t = bt % rows, b = bt / rows;
+    int c4;
+    int64_t t, b;
+    if (total < (1ll << 31)) {      // 32-bit divisions: the 64-bit ones cost as much as the Philox rounds
+      const uint32_t i32 = static_cast<uint32_t>(i), bt = i32 / static_cast<uint32_t>(W4);
+      c4 = static_cast<int>(i32 - bt * static_cast<uint32_t>(W4));
+      const uint32_t b32 = bt / static_cast<uint32_t>(rows);
+      b = b32;
+      t = bt - b32 * static_cast<uint32_t>(rows);
+    } else {
+      c4 = static_cast<int>(i % W4);
+      const int64_t bt = i / W4;
+      t = bt % rows;
+      b = bt / rows;
+    }
     const int64_t tm = t < Tn ? t : Tn - 1;
     const uint32_t k = dropout_keep4(seed, site, static_cast<unsigned long long>(((b * Tn + tm) * W + 4 * c4) >> 2), p);
     T* q = x + b * ld_b + t * ld_t + 4 * c4;
@@ -351,6 +409,13 @@ int las_dropout(void* x, int x_is_bf16, int64_t B, int64_t T, int W, int64_t ld_
 
 int las_relu_bwd(const float* dout, const void* out, int out_is_bf16, void* dz, int64_t n, void* stream) {
   if (n == 0) return 0;
+  if (out_is_bf16 && n % 4 == 0 && reinterpret_cast<uintptr_t>(dout) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 8 == 0 &&
+      reinterpret_cast<uintptr_t>(dz) % 8 == 0) {
+    relu_bwd4_kernel<<<grid_for(n / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float4*>(dout), static_cast<const uint2*>(out), static_cast<uint2*>(dz), n / 4); ++g_launches;
+    LAS_LAUNCH_CHECK();
+    return 0;
+  }
   relu_bwd_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       dout, out, out_is_bf16, static_cast<__nv_bfloat16*>(dz), n); ++g_launches;
   LAS_LAUNCH_CHECK();
@@ -500,7 +565,7 @@ int las_adam_step(float* p, const float* g, float* m, float* v, float* vmax, int
                   float max_norm, const float* norm_ptr, float grad_scale, void* stream) {
   if (n == 0) return 0;
   LAS_REQUIRE(step_dev != nullptr, "adam: step_dev must point to the device step counter");
-  adam_step_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  adam_step_kernel<<<grid_for((n + 3) / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       p, g, m, v, vmax, n, lr, beta1, beta2, eps, weight_decay, step_dev, max_norm, norm_ptr,
       grad_scale); ++g_launches;
   LAS_LAUNCH_CHECK();

@@ -84,7 +84,7 @@ def _gemm_workspace(device):
 # joins the side stream. Only trainers whose optimiser pre-allocates `.grad` (optim.FusedAdam) use it; a bare
 # `loss.backward()` keeps the ordinary single-stream behaviour.
 # --------------------------------------------------------------------------------------------
-_DEFER = {"on": False, "streams": {}, "keep": [], "used": False}
+_DEFER = {"on": False, "streams": {}, "keep": [], "used": False, "late": []}
 
 
 class deferred_wgrad:
@@ -98,8 +98,23 @@ class deferred_wgrad:
         return False
 
 
+def run_late_jobs():
+    """Side-stream jobs that were parked until a long serial kernel occupies the main stream (DecoderFn.backward parks
+    the energy-MLP parameter sums; EncoderFn.backward releases them next to layer 0's BPTT). Call on the side stream."""
+    jobs, _DEFER["late"] = _DEFER["late"], []
+    for _, job in jobs:
+        job()
+
+
 def join_deferred():
     """The current stream waits for every weight-gradient kernel forked so far."""
+    if _DEFER["late"]:                    # nobody released them (no encoder backward followed): run them now
+        dev = _DEFER["late"][0][0]
+        side = warm_deferred(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        _DEFER["used"] = True
+        with torch.cuda.stream(side):
+            run_late_jobs()
     if _DEFER["used"]:
         for dev, side in _DEFER["streams"].items():
             torch.cuda.current_stream(dev).wait_stream(side)
@@ -472,6 +487,8 @@ class EncoderFn(torch.autograd.Function):
             # projection gradients dW = dz^T yview, db = colsum(dz) need only dz: forked BEFORE this layer's BPTT
             with wgrad_scope(lw[8:10], dz, y) as sc:
                 grads[10 * i + 8:10 * i + 10] = sc.deliver([gemm(dz, Ho, 1, y, Kp, 1, Ho, Kp, n), colsum(dz, Ho)])
+                if i == 0 and sc.deferred:
+                    run_late_jobs()           # parked side-stream work runs next to the longest BPTT kernel
             dx, dG = lstm_layer_bwd(lsaved, [w_hh, w_hh_r], dy, need_dx=i > 0)
             del dy
             # LSTM weight gradients from dG (overlap the next layer's BPTT; layer 0's are the exposed tail)
@@ -787,9 +804,16 @@ class DecoderFn(torch.autograd.Function):
         _lib.check(_lib.lib().las_dec_bwd(ctypes.byref(a), _lib.stream_ptr()))
         # ---- critical path: gradient w.r.t. the encoder states
         dP_bf = None
+        scope = wgrad_scope(ctx.wts, S, pers, (de_all if pers is not None else None), dl, (dl_bf if mode != 2 else None),
+                            dlogits, dl_tot, dgates, dcz_all, ddz_all, dP, dattc_all, att_part, d_mlp_att, d_gvec)
         if pers is not None:
-            call("las_att_param_grads", ptr(pers["Pc"]), ptr(S["dzf"]), ptr(pers["conv_save"]), ptr(de_all), ptr(S["mlp_att"]),
-                 ptr(S["gvec"]), B, L, Te, A, C, ptr(dP), ptr(att_part), ptr(d_mlp_att), ptr(d_gvec))
+            # dP is all the encoder's backward waits for; when the weight gradients are deferred, the energy-MLP
+            # parameter sums (the same walk over (b, t, te, a) again, tanh recomputed) run on the side stream
+            apg = (ptr(pers["Pc"]), ptr(S["dzf"]), ptr(pers["conv_save"]), ptr(de_all), ptr(S["mlp_att"]), ptr(S["gvec"]),
+                   B, L, Te, A, C)
+            apg_split = scope.deferred and os.environ.get("LAS_APG_SPLIT", "1") == "1"
+            call("las_att_param_grads_part", *apg, 1 if apg_split else 3, ptr(dP), ptr(att_part), ptr(d_mlp_att),
+                 ptr(d_gvec))
             dQ = torch.empty(B * Te, O, **f32)
             call("las_att_dq", ptr(S["ws"]), ptr(dc_all), L, B, Te, O, ptr(dQ))
             # c_t = w_t @ Q + b, Q = enc_h @ mlp_o.weight^T: d enc_h = dQ mlp_o.weight (+ dP mlp_enc.weight below)
@@ -800,8 +824,8 @@ class DecoderFn(torch.autograd.Function):
         gemm(dP_bf, Ap8, 0, S["mlp_enc_bf"], H, 1, B * Te, H, A, out=denc.view(B * Te, H), accumulate=True)
         # ---- weight gradients deferred out of the time loop, as dense contractions over all (b, t); nothing on
         # the critical path (the encoder's backward) waits for them
-        with wgrad_scope(ctx.wts, S, dl, (dl_bf if mode != 2 else None), dlogits, dl_tot, dgates, dcz_all, ddz_all, dP, dP_bf, dattc_all, att_part,
-                         (dQ_bf if pers is not None else None), d_mlp_att, d_gvec) as sc:
+        scope.keep = scope.keep + (dP_bf, (dQ_bf if pers is not None else None))
+        with scope as sc:
             if pers is not None:
                 d_conv_t = torch.zeros(C, 2 * K + 1, **f32)
                 call("las_att_dconv", ptr(dattc_all), ptr(S["ws"]), L, B, Te, C, K, ptr(d_conv_t), ptr(att_part))
@@ -858,6 +882,24 @@ class DecoderFn(torch.autograd.Function):
                          mlp_enc_w=d_mlp_enc_w, mlp_enc_b=d_mlp_enc_b, mlp_dec_w=d_mlp_dec, mlp_att_w=d_mlp_att,
                          conv_w=d_conv.view_as(W["conv_w"]), gvec_w=d_gvec.view_as(W["gvec_w"]), mlp_o_w=d_mlp_o_w,
                          mlp_o_b=d_mlp_o_b)
+            if pers is not None and apg_split:
+                # This kernel fills every free SM with 150 us CTAs; run right away it delays the small kernels between
+                # the BPTT launches (each finds no free CTA slot). It is parked until the encoder's layer-0 BPTT, the
+                # longest serial kernel of the step, has the main stream to itself.
+                w_matt, w_gvec = ctx.wts[DEC_WEIGHTS.index("mlp_att_w")], ctx.wts[DEC_WEIGHTS.index("gvec_w")]
+                hold = (pers["Pc"], S["dzf"], pers["conv_save"], de_all, S["mlp_att"], S["gvec"], dP, att_part)
+
+                def late(apg=apg, hold=hold, d_mlp_att=d_mlp_att, d_gvec=d_gvec, w_matt=w_matt, w_gvec=w_gvec):
+                    call("las_att_param_grads_part", *apg, 2, ptr(hold[6]), ptr(hold[7]), ptr(d_mlp_att), ptr(d_gvec))
+                    if w_matt.requires_grad:
+                        w_matt.grad.add_(d_mlp_att.view_as(w_matt.grad))
+                    if w_gvec.requires_grad:
+                        w_gvec.grad.add_(d_gvec.view_as(w_gvec.grad))
+                    _DEFER["keep"].append((hold, d_mlp_att, d_gvec))
+
+                _DEFER["late"].append((dev, late))
+                grads["mlp_att_w"] = None
+                grads["gvec_w"] = None
             glist = sc.deliver([grads[k] for k in DEC_WEIGHTS])
         ctx.saved = None
         return (denc, None, None, None, None, None, None, None, None, None, *glist)

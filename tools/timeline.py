@@ -64,3 +64,10 @@ for s, L in streams.items():
         continue
     for e in L:
         print(f"{(e['ts'] - t0) / 1e3:8.3f} ms  {e['dur']:8.1f} us  [s{s}] {e['name'][:90]}")
+head_us = float(os.environ.get("HEAD_US", 0))
+if head_us > 0:
+    print(f"---- every kernel of the first {head_us:.0f} us, all streams")
+    for e in ev:
+        if e["ts"] - t0 > head_us:
+            break
+        print(f"{(e['ts'] - t0):8.1f} us  {e['dur']:7.1f} us  [s{e['args']['stream']}] {e['name'][:100]}")
