@@ -134,9 +134,11 @@ int las_lstm_seq_bwd(const float* dy, int64_t dy_ld_b, int64_t dy_ld_t, int rep_
  *   xproj, dG  columns are gate-minor: [dir*4H + 4*unit + gate] (permute the rows of W_ih / the bias accordingly)
  *   whh_pk     las_pack_afrag mode 2 per direction; whhT_owner_pk from las_pack_whhT_owner
  *   rec        [ndir, B, T, H] records of 16 bytes: (i,f) f16x2 | (g,o) f16x2 | c f32 | tanh(c) f32
- * y / hprev / dy / lens / rep_row as in las_lstm_seq_{fwd,bwd}. */
+ * y / hprev / dy / lens / rep_row as in las_lstm_seq_{fwd,bwd}, except that the persistent forward writes EVERY row of y
+ * (zeros past each length), so y need not be cleared by the caller. */
 int las_lstm_persistent_geometry(int H, int* cs, int* upc);
-/* development aid: resident-cluster capacity of the persistent LSTM kernels (which: 0 forward, 1 backward) */
+/* development aid: resident-cluster capacity of the persistent LSTM kernels (which: 0 forward with the default 8-CTA
+ * clusters, 1 backward, 2 / 3 forward with 7-CTA / 10-CTA clusters) */
 int las_lstm_persist_max_clusters(int which, int H);
 int las_lstm_persist_fwd(const float* xproj, const void* whh_pk, const int32_t* lens, int B, int T, int H,
                          int ndir, void* y, int64_t y_ld_b, int64_t y_ld_t, int rep_row, void* hprev,

@@ -305,9 +305,12 @@ __global__ void __launch_bounds__(384, 1) lstm_persist_fwd_kernel(FwdP p) {
         *rec_run = r;
       }
       if (ul == 0) {
-        if (act) {
-          *reinterpret_cast<uint2*>(y_run) = qw;
-          if (p.rep_row && t == T - 1) *reinterpret_cast<uint2*>(y_run + p.y_ld_t) = qw;
+        // every row of y is written here, zeros past the utterance's length (pad_packed_sequence): the caller does
+        // not have to clear the buffer first
+        if (n < p.B) {
+          const uint2 yv = act ? qw : make_uint2(0u, 0u);
+          *reinterpret_cast<uint2*>(y_run) = yv;
+          if (p.rep_row && t == T - 1) *reinterpret_cast<uint2*>(y_run + p.y_ld_t) = yv;
         }
       } else if (ul == 1 && hp_run && n < p.B) {
         *reinterpret_cast<uint2*>(hp_run) = quad_prev;
@@ -655,19 +658,14 @@ int persist_lstm_fwd(const float* xproj, const void* whh_pk, const int32_t* lens
                      int64_t hp_ld_t, void* rec, cudaStream_t stream) {
   // The forward fragments are packed per quad, so the cluster size is free at launch: fewer warps per CTA (two per
   // scheduler instead of three at H = 320) shorten every phase of the step, as long as all clusters stay resident.
-  // Batches that need more 8-CTA clusters than the GPU holds (B = 64, both directions: 16 against 15 on a B200) take
-  // 7-CTA clusters of 12 warps instead of running one cluster as a second wave.
+  // (7-CTA clusters of 12 warps were measured as a way to keep B = 64 -- 16 clusters -- in one wave: a B200 holds 15
+  // of them, exactly as many as 8-CTA clusters, and the step is slower (1.26 vs 1.14 us), so they are not chosen.)
   FGeom g;
   LAS_REQUIRE(fgeom_for(H, g), "persistent LSTM: hidden size %d unsupported", H);
   {
     const int need = ((B + kNB - 1) / kNB) * ndir;
-    const int prefs[3] = {10, 8, 7};
-    for (int i = 0; i < 3; ++i) {
-      FGeom c;
-      if (!fgeom_for(H, c, prefs[i])) continue;
-      if (i == 0 && c.CS <= 8) continue;
-      if (fwd_max_clusters(c) >= need) { g = c; break; }
-    }
+    FGeom g10;
+    if (fgeom_for(H, g10, 10) && g10.CS > 8 && fwd_max_clusters(g10) >= need) g = g10;
     static const char* force = getenv("LAS_FWD_CS");     // development aid: pin the forward cluster size
     if (force) {
       FGeom c;
@@ -749,6 +747,10 @@ int las_lstm_persist_max_clusters(int which, int H) {
   cfg.attrs = at;
   cfg.numAttrs = 1;
   int n = 0;
+  if (which == 2 || which == 3) {          // forward kernel with 7-CTA / 10-CTA clusters
+    FGeom c;
+    return fgeom_for(H, c, which == 2 ? 7 : 10) ? fwd_max_clusters(c) : 0;
+  }
   if (which == 0) {
     const int threads = 32 * f.WPC;
     cfg.gridDim = dim3(f.CS, 1, 1); cfg.blockDim = dim3(threads); at[0].val.clusterDim.x = f.CS;

@@ -181,6 +181,18 @@ class wgrad_scope:
         return [None] * len(grads)
 
 
+def zeros_many(dev, specs):
+    """One zeroed allocation carved into tensors: specs = [(shape, dtype), ...] -> list of views (256-byte aligned).
+    One fill instead of one tiny kernel per buffer on the critical path."""
+    offs, total = [], 0
+    for shape, dtype in specs:
+        nbytes = int(torch.Size(shape).numel()) * torch.empty((), dtype=dtype).element_size()
+        offs.append((total, nbytes))
+        total += (nbytes + 255) // 256 * 256
+    buf = torch.zeros(total, device=dev, dtype=torch.uint8)
+    return [buf[o:o + nb].view(dtype).view(shape) for (o, nb), (shape, dtype) in zip(offs, specs)]
+
+
 def gemm(A, lda, a_mn, Bm, ldb, b_mn, M, N, K, out=None, out_bf16=False, bias=None, relu=False,
          accumulate=False, ldc=None):
     """D[m,n] = sum_k A[m,k] B[n,k] (+bias[n]) (relu) (+=D). A/Bm: bf16 tensors (base pointers)."""
@@ -355,8 +367,9 @@ def lstm_layer_fwd(xin, Dp, w_ih, w_hh, b_ih, b_hh, lens, B, T, Tp, rep):
                                            lambda: _build_lstm_fwd(w_ih, w_hh, b_ih, b_hh, Dp))
     assert wcat_bf.shape[1] == Dp
     xproj = gemm(xin, Dp, 0, wcat_bf, Dp, 0, B * T, ndir * 4 * H, Dp, bias=bcat)   # f32 [B*T, ndir*4H]
-    y = torch.zeros(B, Tp, ndir * H, device=dev, dtype=BF16)
     hprev = torch.empty(B, T, ndir * H, device=dev, dtype=BF16)
+    # the persistent kernel writes every row of y (zeros past each length); the per-timestep kernels write active rows only
+    y = (torch.empty if persist else torch.zeros)(B, Tp, ndir * H, device=dev, dtype=BF16)
     if persist:
         rec = torch.empty(ndir * B * T * H, 4, device=dev, dtype=torch.int32)
         call("las_lstm_persist_fwd", ptr(xproj), ptr(whh_pk), ptr(lens), B, T, H, ndir, ptr(y), Tp * ndir * H, ndir * H,
@@ -619,11 +632,9 @@ class DecoderFn(torch.autograd.Function):
         Pm = gemm(enc_bf, H, 0, mlp_enc_bf, H, 0, B * Te, A, H, bias=W["mlp_enc_b"])
         wr_cat, wr_pk, mlp_dec_pk, mlp_o_pk = Pk["wr_cat"], Pk["wr_pk"], Pk["mlp_dec_pk"], Pk["mlp_o_pk"]
         cell_bias = Pk["cell_bias"]
-        ws = torch.zeros(B, R, Te, **f32)
+        ws, zc, cx, c_state = zeros_many(dev, [((B, R, Te), torch.float32), ((B * R * ZC + 64,), BF16),
+                                               ((B * R * H + 64,), BF16), ((B, Hd), torch.float32)])
         call("las_att_init", ptr(enc_lens), B, Te, ptr(ws), R * Te)
-        zc = torch.zeros(B * R * ZC + 64, device=dev, dtype=BF16)
-        cx = torch.zeros(B * R * H + 64, device=dev, dtype=BF16)
-        c_state = torch.zeros(B, Hd, **f32)
         e_buf = torch.empty(B, Te, **f32)
         dzf = torch.empty(B, L, A, **f32)
         gates = torch.empty(B, L, Hd, 4, device=dev, dtype=torch.float16)
@@ -763,18 +774,18 @@ class DecoderFn(torch.autograd.Function):
         if mode == 2:
             a.weT_pk, a.outT_pk = ptr(Bk["weT_pk"]), ptr(Bk["outT_pk"])
         dcz_tot = torch.empty(B, ZC, **f32)
-        dcz_all = torch.zeros(n, ZC, device=dev, dtype=BF16)
         dctx_all = torch.empty(B, L, H, **f32)
         dw_buf = torch.empty(B, Te, **f32)
         dattc_all = torch.empty(L, B, Te, C, **f32)
-        ddz_all = torch.zeros(n * A + 64, **f32)
-        dP = torch.zeros(B * Te, A, **f32)
         att_part = torch.empty(_lib.lib().las_att_scratch_floats(B, L, Te, A, C, K), **f32)
         dc_state = torch.empty(B, Hd, **f32)
-        dgates = torch.zeros(n, 4 * Hd, device=dev, dtype=BF16)
-        d_mlp_att = torch.zeros(A, C, **f32)
-        d_gvec = torch.zeros(A, **f32)
-        d_conv = torch.zeros(C, 2 * K + 1, **f32)
+        F32 = torch.float32
+        zspecs = [((n, ZC), BF16), ((n * A + 64,), F32), ((B * Te, A), F32), ((n, 4 * Hd), BF16), ((A, C), F32), ((A,), F32),
+                  ((C, 2 * K + 1), F32)]
+        if pers is not None:
+            zspecs += [((B, L, Te), F32), ((B, L, O), F32)]
+        zb = zeros_many(dev, zspecs)
+        dcz_all, ddz_all, dP, dgates, d_mlp_att, d_gvec, d_conv = zb[:7]
         denc = torch.empty(B, Te, H, **f32)
         a.enc_h, a.P = ptr(S["enc_bf"]), ptr(S["Pm"])
         a.conv_w, a.mlp_att, a.gvec = ptr(S["conv_w"]), ptr(S["mlp_att"]), ptr(S["gvec"])
@@ -793,8 +804,7 @@ class DecoderFn(torch.autograd.Function):
             # parameter gradient is reduced afterwards by the GEMMs / parallel kernels below
             L_ = _lib.lib()
             wrT2, decT2 = Bk["wrT2"], Bk["decT2"]
-            de_all = torch.zeros(B, L, Te, **f32)
-            dc_all = torch.zeros(B, L, O, **f32)
+            de_all, dc_all = zb[7], zb[8]
             a.Q, a.wr2_pk, a.cpre, a.conv_save = ptr(pers["Qm"]), ptr(pers["wr2_pk"]), ptr(pers["cpre"]), ptr(pers["conv_save"])
             a.mlp_dec_pk_p = ptr(S["Pk"]["mlp_dec_pk_p"])
             a.wrT2_pk, a.mlp_decT2_pk, a.de_all, a.dc_all = ptr(wrT2), ptr(decT2), ptr(de_all), ptr(dc_all)

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from tests.util import pkg
 Fn = pkg("functional"); LIB = pkg("_lib")
-B, T, H = 32, int(sys.argv[1]) if len(sys.argv) > 1 else 1000, 320
+B, T, H = int(os.environ.get('B', 32)), int(sys.argv[1]) if len(sys.argv) > 1 else 1000, 320
 dev = torch.device("cuda")
 torch.manual_seed(0)
 xproj = torch.randn(B * T, 8 * H, device=dev) * 0.1
@@ -28,7 +28,9 @@ for _ in range(2):
 torch.cuda.synchronize()
 e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
 e[0].record(); fwd(); e[1].record(); bwd(); e[2].record(); torch.cuda.synchronize()
-print(f"fwd {e[0].elapsed_time(e[1])*1e3/T:.3f} us/step  bwd {e[1].elapsed_time(e[2])*1e3/T:.3f} us/step  (T={T})")
+print(f"fwd {e[0].elapsed_time(e[1])*1e3/T:.3f} us/step  bwd {e[1].elapsed_time(e[2])*1e3/T:.3f} us/step  (B={B}, T={T}, LAS_FWD_CS={os.environ.get('LAS_FWD_CS')}); "
+      f"resident clusters: fwd default {LIB.lib().las_lstm_persist_max_clusters(0, H)}, fwd 7-CTA {LIB.lib().las_lstm_persist_max_clusters(2, H)}, "
+      f"fwd 10-CTA {LIB.lib().las_lstm_persist_max_clusters(3, H)}, bwd {LIB.lib().las_lstm_persist_max_clusters(1, H)}")
 if os.environ.get("LAS_TRACE"):
     dbg = torch.zeros(128, device=dev, dtype=torch.int64)
     LIB.lib().las_set_debug_buffer(dbg.data_ptr())
