@@ -231,7 +231,13 @@ __global__ void __launch_bounds__(384, 1) lstm_persist_fwd_kernel(FwdP p) {
     const uint32_t bar_remote2 = mapa_u32(smem_u32(&full[0]), peer2_ok ? g + 8 : 0);
 
     const bool trace = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0;
+// the phase trace costs ~30 instructions per timestep in a loop that is bound by its own instruction stream: it is
+// compiled in only with `make TRACE=1` (-DLAS_PHASE_TRACE)
+#ifdef LAS_PHASE_TRACE
 #define LAS_TRACE(slot) do { if (trace && s >= 64 && s < 72) p.dbg[(s - 64) * 8 + (slot)] = clock64(); } while (0)
+#else
+#define LAS_TRACE(slot) do { (void)trace; } while (0)
+#endif
     for (int s = 0; s < T; ++s) {
       const int t = (dir == 0) ? s : (T - 1 - s);
       LAS_TRACE(0);
@@ -246,12 +252,21 @@ __global__ void __launch_bounds__(384, 1) lstm_persist_fwd_kernel(FwdP p) {
         LAS_TRACE(1);
         if (threadIdx.x == 0 && s + 2 < T) mbar_arrive_expect_tx(&full[buf], tx_bytes);  // re-arm for step s+2
         const uint2* hb = reinterpret_cast<const uint2*>(hs + buf * p.KT * 64) + tig * 8 + (g ^ ((tig >> 1) << 2));
+        if (p.KT == kMaxKT) {     // H = 320: no per-k-tile bound check in the instruction stream
 #pragma unroll
-        for (int kt = 0; kt < kMaxKT; ++kt) {
-          if (kt < p.KT) {
+          for (int kt = 0; kt < kMaxKT; ++kt) {
             const uint2 b = hb[kt * 32];
             const uint32_t Af[4] = {A[kt].x, A[kt].y, A[kt].z, A[kt].w};
             mma_bf16_16816(acc[kt & 3], Af, b.x, b.y);
+          }
+        } else {
+#pragma unroll
+          for (int kt = 0; kt < kMaxKT; ++kt) {
+            if (kt < p.KT) {
+              const uint2 b = hb[kt * 32];
+              const uint32_t Af[4] = {A[kt].x, A[kt].y, A[kt].z, A[kt].w};
+              mma_bf16_16816(acc[kt & 3], Af, b.x, b.y);
+            }
           }
         }
       }
@@ -445,7 +460,11 @@ __global__ void __launch_bounds__(320, 1) lstm_persist_bwd_kernel(BwdP p) {
   }
 
   const bool trace = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0;
+#ifdef LAS_PHASE_TRACE
 #define LAS_TRACE(slot) do { if (trace && s >= 64 && s < 72) p.dbg[64 + (s - 64) * 8 + (slot)] = clock64(); } while (0)
+#else
+#define LAS_TRACE(slot) do { (void)trace; } while (0)
+#endif
   for (int s = 0; s < T; ++s) {
     const int t = (dir == 0) ? (T - 1 - s) : s;
     const bool active = t < len;
@@ -479,14 +498,26 @@ __global__ void __launch_bounds__(320, 1) lstm_persist_bwd_kernel(BwdP p) {
 #pragma unroll
           for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
       const uint2* db = reinterpret_cast<const uint2*>(dgs) + lane;
+      if (KTC == kMaxKTW) {       // H = 320: no per-k-tile bound check in the instruction stream
 #pragma unroll
-      for (int kc = 0; kc < kMaxKTW; ++kc) {
-        if (kc < KTC) {
+        for (int kc = 0; kc < kMaxKTW; ++kc) {
           const uint2 b = db[kc * 32];
 #pragma unroll
           for (int m = 0; m < 2; ++m) {
             const uint32_t Af[4] = {A[m][kc].x, A[m][kc].y, A[m][kc].z, A[m][kc].w};
             mma_bf16_16816(acc[m][kc & 1], Af, b.x, b.y);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int kc = 0; kc < kMaxKTW; ++kc) {
+          if (kc < KTC) {
+            const uint2 b = db[kc * 32];
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+              const uint32_t Af[4] = {A[m][kc].x, A[m][kc].y, A[m][kc].z, A[m][kc].w};
+              mma_bf16_16816(acc[m][kc & 1], Af, b.x, b.y);
+            }
           }
         }
       }
@@ -511,7 +542,12 @@ __global__ void __launch_bounds__(320, 1) lstm_persist_bwd_kernel(BwdP p) {
       LAS_TRACE(3);
       if (threadIdx.x == 0 && s + 2 < T) mbar_arrive_expect_tx(&pfull[buf], tx_bytes);
       const float* pp = part + static_cast<int64_t>(buf) * p.CSn * UPC * 8 + threadIdx.x;
-      for (uint32_t src = 0; src < CS; ++src) dh += pp[src * UPC * 8];
+      // the CS <= 8 partial sums: all loads first, then a tree (a serial load-add chain was 15 % of this kernel's
+      // stall samples, profiles/r02_ncu_full_summary.txt)
+      float pv[8];
+#pragma unroll
+      for (uint32_t src = 0; src < 8; ++src) pv[src] = src < CS ? pp[src * UPC * 8] : 0.f;
+      dh = ((pv[0] + pv[1]) + (pv[2] + pv[3])) + ((pv[4] + pv[5]) + (pv[6] + pv[7]));
     }
     // gate derivatives (same math as cell_bwd_kernel)
     float d4[4] = {0.f, 0.f, 0.f, 0.f};
