@@ -42,7 +42,8 @@ __device__ __forceinline__ float tanh_fast(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// Accurate variants (used wherever the result feeds a long recurrence).
+// Accurate variants (per-timestep kernels, decoder cell; the persistent BLSTM forward uses the MUFU.TANH forms, see
+// persist_lstm_fwd for the parity measurement).
 // ex2.approx + rcp.approx (~2 + 1 ulp): no IEEE-division slow path on the serial critical path.
 __device__ __forceinline__ float sigmoid_acc(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float tanh_acc(float x) {
