@@ -114,21 +114,25 @@ __device__ __forceinline__ uint4 philox4x32_10(uint2 key, uint4 ctr) {
   }
   return ctr;
 }
-// keep decisions of the 4 elements 4*blk .. 4*blk+3 (one Philox call): bit i of the result = element 4*blk + i
-__device__ __forceinline__ uint32_t dropout_keep4(unsigned long long seed, uint32_t site, unsigned long long blk, float p) {
+// One Philox call decides 8 elements: element idx uses the 16-bit lane (idx & 7) of block (idx >> 3) and is kept iff
+// that lane, as a fraction of 65536, is >= p (the rate is realised to 2^-16). Every mask on the path -- the vector and
+// scalar dropout kernels, the decoder's in-kernel cell-input dropout, forward and backward -- goes through these helpers.
+__device__ __forceinline__ uint32_t dropout_thresh16(float p) { return static_cast<uint32_t>(ceilf(p * 65536.0f)); }
+// keep decisions of the 8 elements 8*blk .. 8*blk+7: bit i of the result = element 8*blk + i
+__device__ __forceinline__ uint32_t dropout_keep8(unsigned long long seed, uint32_t site, unsigned long long blk, float p) {
   const uint4 r = philox4x32_10(make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)),
                                 make_uint4(static_cast<uint32_t>(blk), static_cast<uint32_t>(blk >> 32), site, 0x4c41535fu));
-  const float s = 1.0f / 16777216.0f;
-  return (static_cast<float>(r.x >> 8) * s >= p ? 1u : 0u) | (static_cast<float>(r.y >> 8) * s >= p ? 2u : 0u) |
-         (static_cast<float>(r.z >> 8) * s >= p ? 4u : 0u) | (static_cast<float>(r.w >> 8) * s >= p ? 8u : 0u);
+  const uint32_t t = dropout_thresh16(p);
+  return ((r.x & 0xffffu) >= t ? 1u : 0u) | ((r.x >> 16) >= t ? 2u : 0u) | ((r.y & 0xffffu) >= t ? 4u : 0u) |
+         ((r.y >> 16) >= t ? 8u : 0u) | ((r.z & 0xffffu) >= t ? 16u : 0u) | ((r.z >> 16) >= t ? 32u : 0u) |
+         ((r.w & 0xffffu) >= t ? 64u : 0u) | ((r.w >> 16) >= t ? 128u : 0u);
+}
+// keep decisions of the 4 elements 4*blk4 .. 4*blk4+3: bit i of the result = element 4*blk4 + i
+__device__ __forceinline__ uint32_t dropout_keep4(unsigned long long seed, uint32_t site, unsigned long long blk4, float p) {
+  return (dropout_keep8(seed, site, blk4 >> 1, p) >> (4u * (static_cast<uint32_t>(blk4) & 1u))) & 15u;
 }
 __device__ __forceinline__ bool dropout_keep(unsigned long long seed, uint32_t site, unsigned long long idx, float p) {
-  const unsigned long long blk = idx >> 2;
-  const uint4 r = philox4x32_10(make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)),
-                                make_uint4(static_cast<uint32_t>(blk), static_cast<uint32_t>(blk >> 32), site, 0x4c41535fu));
-  const uint32_t sel = static_cast<uint32_t>(idx) & 3u;
-  const uint32_t v = sel == 0 ? r.x : (sel == 1 ? r.y : (sel == 2 ? r.z : r.w));
-  return static_cast<float>(v >> 8) * (1.0f / 16777216.0f) >= p;
+  return ((dropout_keep8(seed, site, idx >> 3, p) >> (static_cast<uint32_t>(idx) & 7u)) & 1u) != 0u;
 }
 
 // ----------------------------------------------------------------------------------------

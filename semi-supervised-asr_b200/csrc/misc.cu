@@ -376,6 +376,55 @@ __global__ void dropout4_kernel(T* __restrict__ x, int64_t B, int64_t Tn, int W,
     }
   }
 }
+// W % 8 == 0 and 8-element-aligned rows: one thread = 8 consecutive elements = ONE Philox call, 16-byte accesses
+// (the 4-wide kernel above spends two calls on them, and the Philox rounds are what this kernel's time is made of).
+template <typename T>
+__global__ void dropout8_kernel(T* __restrict__ x, int64_t B, int64_t Tn, int W, int64_t ld_b, int64_t ld_t, int rep_row,
+                                float p, const unsigned long long* __restrict__ seed_dev, uint32_t site) {
+  const unsigned long long seed = *seed_dev;
+  const float scale = 1.0f / (1.0f - p);
+  const int W8 = W >> 3;
+  const int64_t rows = Tn + rep_row, total = B * rows * W8;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    int c8;
+    int64_t t, b;
+    if (total < (1ll << 31)) {
+      const uint32_t i32 = static_cast<uint32_t>(i), bt = i32 / static_cast<uint32_t>(W8);
+      c8 = static_cast<int>(i32 - bt * static_cast<uint32_t>(W8));
+      const uint32_t b32 = bt / static_cast<uint32_t>(rows);
+      b = b32;
+      t = bt - b32 * static_cast<uint32_t>(rows);
+    } else {
+      c8 = static_cast<int>(i % W8);
+      const int64_t bt = i / W8;
+      t = bt % rows;
+      b = bt / rows;
+    }
+    const int64_t tm = t < Tn ? t : Tn - 1;
+    const uint32_t k = dropout_keep8(seed, site, static_cast<unsigned long long>(((b * Tn + tm) * W + 8 * c8) >> 3), p);
+    T* q = x + b * ld_b + t * ld_t + 8 * c8;
+    if constexpr (sizeof(T) == 2) {
+      uint4 v = *reinterpret_cast<uint4*>(q);
+      uint32_t* w = &v.x;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 a = unpack_bf16x2(w[j]);
+        w[j] = pack_bf16x2((k >> (2 * j)) & 1u ? a.x * scale : 0.f, (k >> (2 * j + 1)) & 1u ? a.y * scale : 0.f);
+      }
+      *reinterpret_cast<uint4*>(q) = v;
+    } else {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float4 v = *reinterpret_cast<float4*>(q + 4 * h);
+        const uint32_t kk = k >> (4 * h);
+        v.x = (kk & 1u) ? v.x * scale : 0.f; v.y = (kk & 2u) ? v.y * scale : 0.f;
+        v.z = (kk & 4u) ? v.z * scale : 0.f; v.w = (kk & 8u) ? v.w * scale : 0.f;
+        *reinterpret_cast<float4*>(q + 4 * h) = v;
+      }
+    }
+  }
+}
 }  // namespace las
 extern "C" {
 
@@ -385,6 +434,17 @@ int las_dropout(void* x, int x_is_bf16, int64_t B, int64_t T, int W, int64_t ld_
   if (p == 0.f || B * T * W == 0) return 0;
   const int64_t n = B * (T + rep_row) * W;
   const int esz = x_is_bf16 ? 2 : 4;
+  if (W % 8 == 0 && ld_b % 8 == 0 && ld_t % 8 == 0 && (reinterpret_cast<uintptr_t>(x) % 16) == 0) {
+    if (x_is_bf16)
+      dropout8_kernel<__nv_bfloat16><<<grid_for(n / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+          static_cast<__nv_bfloat16*>(x), B, T, W, ld_b, ld_t, rep_row, p, static_cast<const unsigned long long*>(seed_dev), site);
+    else
+      dropout8_kernel<float><<<grid_for(n / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+          static_cast<float*>(x), B, T, W, ld_b, ld_t, rep_row, p, static_cast<const unsigned long long*>(seed_dev), site);
+    ++g_launches;
+    LAS_LAUNCH_CHECK();
+    return 0;
+  }
   if (W % 4 == 0 && ld_b % 4 == 0 && ld_t % 4 == 0 && (reinterpret_cast<uintptr_t>(x) % (4 * esz)) == 0) {
     if (x_is_bf16)
       dropout4_kernel<__nv_bfloat16><<<grid_for(n / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
