@@ -33,7 +33,7 @@ FLOP_PER_UTT = 19.81e9
 HBM_BYTES_PER_UTT = 51e6
 # dram__bytes_read.sum + dram__bytes_write.sum of one lstm_persist_fwd_kernel launch (B=32, T=1000, H=320, both
 # directions) from the committed `ncu --set full` capture
-NCU_TRAFFIC_BYTES = 329340416 + 364328960
+NCU_TRAFFIC_BYTES = 329358848 + 366706176
 
 
 def synth_batch(rng, B, Tmax, D, V):
@@ -362,7 +362,7 @@ def kernel_roofline(dev, hbm_peak, which):
     ach = bytes_per_launch / (us * 1e-6) / 1e9
     return {"kernel": "lstm_persist_fwd_kernel (BLSTM layer 0: T=1000 timesteps, both directions, one launch)",
             "bound": "hbm", "achieved": ach, "peak": hbm_peak, "peak_source": which, "unit": "GB/s",
-            "frac": ach / hbm_peak, "traffic": NCU_TRAFFIC_BYTES, "traffic_source": "profiles/r02_ncu_full_summary.txt (dram read 329.3 MB + write 364.3 MB per launch)",
+            "frac": ach / hbm_peak, "traffic": NCU_TRAFFIC_BYTES, "traffic_source": "profiles/r03_ncu_full_summary.txt (dram read 329.4 MB + write 366.7 MB per launch)",
             "us_per_launch": us, "us_per_timestep": us / T,
             "algorithmic_bytes_per_launch": bytes_per_launch,
             "note": "latency-bound serial recurrence: T dependent steps, each a per-warp chain MMA -> gate math -> DSMEM push (DESIGN.md 4b); HBM traffic equals the algorithmic bytes, the time does not"}

@@ -730,7 +730,7 @@ __global__ void __launch_bounds__(320) att_denc_kernel(const float* __restrict__
 // grid (ceil(Te/kPG), B), block = A rounded up to a warp multiple.
 // WHAT selects the outputs: bit 0 = dP (the critical path: the encoder's backward waits for it), bit 1 = the
 // parameter partial sums (nothing waits for them: the trainers run that instance on the weight-gradient stream).
-constexpr int kPG = 8;   // frames per CTA; blocks of <= 320 threads are compiled for two CTAs per SM (the loop is latency-bound)
+constexpr int kPG = 7;   // frames per CTA (Te = 125: 18 x 32 = 576 CTAs = 1.95 waves of the 296 two-per-SM slots; 8 frames gave 1.73 waves for the price of 2); blocks of <= 320 threads are compiled for two CTAs per SM
 constexpr int kPGT = 16;   // decoder steps per shared-memory chunk
 template <int CM, int MAXT, int MINB, int WHAT>
 __global__ void __launch_bounds__(MAXT, MINB) att_param_grad_kernel(const float* __restrict__ P, const float* __restrict__ dzf,
