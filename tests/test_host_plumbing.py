@@ -138,3 +138,20 @@ def test_data_parallel_dealing_under_gloo_world2(tmp_path):
                               stderr=subprocess.STDOUT, text=True) for r in range(2)]
     outs = [p.communicate(timeout=120)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
+
+
+def test_zeros_many_carves_aligned_zeroed_views():
+    """functional.zeros_many: one zeroed allocation, disjoint 256-byte-spaced views of the requested shapes/dtypes."""
+    Fn = pkg("functional")
+    specs = [((3, 5), torch.bfloat16), ((7,), torch.float32), ((2, 2, 2), torch.float32), ((1,), torch.int32)]
+    views = Fn.zeros_many("cpu", specs)
+    assert [tuple(v.shape) for v in views] == [s for s, _ in specs]
+    assert [v.dtype for v in views] == [d for _, d in specs]
+    base = views[0].data_ptr()
+    offs = [v.data_ptr() - base for v in views]
+    assert all(o % 256 == 0 for o in offs) and offs == sorted(offs) and len(set(offs)) == len(offs)
+    for i, v in enumerate(views):
+        assert not v.any()
+        v.fill_(i + 1)                       # writing one view must not leak into another
+    for i, v in enumerate(views):
+        assert bool((v == i + 1).all())
