@@ -34,6 +34,17 @@ def dropout_seed(device):
     return _DROP["seed"]
 
 
+def set_dropout_seed(value, device):
+    """Restore the device seed (resume): written INTO the existing tensor, whose address captured graphs hold."""
+    dropout_seed(device).fill_(int(value) & 0x7FFFFFFFFFFF)
+    _DROP["calls"] = 0
+
+
+def current_dropout_seed():
+    """Host copy of the device seed (None before the first dropout call). Synchronises; checkpoint time only."""
+    return None if _DROP["seed"] is None else int(_DROP["seed"].item())
+
+
 def advance_dropout_seed():
     """New masks from the next forward on. Call once per training step (after backward)."""
     if _DROP["seed"] is not None:

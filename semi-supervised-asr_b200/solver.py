@@ -21,7 +21,8 @@ from . import functional as Fn
 from .data import BatchLoader, PickleDataset, collate, speech_collate, text_collate
 from .model import E2E, LM
 from .optim import FusedAdam
-from .utils import Logger, adjust_learning_rate, calculate_cer, cc, infinite_iter, remove_pad_eos, to_gpu, to_sents
+from .utils import (Logger, adjust_learning_rate, calculate_cer, cc, infinite_iter, load_resume_state, remove_pad_eos,
+                    save_resume_state, to_gpu, to_sents)
 
 
 def _dist():
@@ -55,6 +56,10 @@ class Solver(object):
         if self.rank == 0:
             torch.save(self.model.state_dict(), f"{model_path}.ckpt")
             torch.save(self.gen_opt.state_dict(), f"{model_path}.opt")
+            try:      # the sidecar is an addition to the reference's two files; it must never cost a checkpoint
+                save_resume_state(f"{model_path}.resume", getattr(self, "progress", {}), Fn.current_dropout_seed())
+            except Exception as e:      # noqa: BLE001
+                self.say(f"warning: resume sidecar not written ({e})")
 
     def save_judge(self, model_path):
         if self.rank == 0:
@@ -71,6 +76,13 @@ class Solver(object):
         self.model.load_state_dict(torch.load(f"{model_path}.ckpt"))
         if load_optimizer:
             self.gen_opt.load_state_dict(torch.load(f"{model_path}.opt"))
+            # continuing a run (not just initialising from weights): counters and random streams from the sidecar,
+            # when there is one (checkpoints written by the reference have none)
+            state = load_resume_state(f"{model_path}.resume")
+            if state is not None:
+                self.progress = dict(state["progress"])
+                if state.get("dropout_seed") is not None:
+                    Fn.set_dropout_seed(state["dropout_seed"], next(self.model.parameters()).device)
 
     def load_judge(self, model_path, load_optimizer):
         self.judge.load_state_dict(torch.load(f"{model_path}.judge.ckpt"))
@@ -261,7 +273,11 @@ class Solver(object):
         c, tag = self.config, self.config["tag"]
         self.model.train()
         best_cer, best_model = 200, None
-        for epoch in range(c["epochs"]):
+        first = 0
+        prog = getattr(self, "progress", {})
+        if c.get("resume") and prog.get("phase") == "sup_pretrain":      # `resume: true` is not a reference key
+            first, best_cer = int(prog["epoch"]) + 1, float(prog.get("best_cer", best_cer))
+        for epoch in range(first, c["epochs"]):
             if epoch <= c["tf_decay_epochs"]:                                     # solver.py:416-419
                 tf_rate = c["init_tf_rate"] - (c["init_tf_rate"] - c["tf_rate_lowerbound"]) * (epoch / c["tf_decay_epochs"])
             else:
@@ -276,6 +292,7 @@ class Solver(object):
             for i, (p, g) in enumerate(zip(hyp[:5], ref[:5])):
                 self.log("text_summary", f"{tag}/supervised/prediction-{i}", p, epoch)
                 self.log("text_summary", f"{tag}/supervised/ground_truth-{i}", g, epoch)
+            self.progress = {"phase": "sup_pretrain", "epoch": epoch, "best_cer": float(min(cer, best_cer))}
             if cer < best_cer:
                 best_cer = cer
                 self.save_model(self._path())

@@ -130,3 +130,35 @@ class Logger:
     def text_summary(self, tag, value, step):
         self._f.write(self._json.dumps({"tag": tag, "text": str(value), "step": int(step)}) + "\n")
         self._f.flush()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# resume sidecar. The reference writes `<path>.ckpt` / `<path>.opt` only (solver.py:38-53), which
+# is not enough to continue a run: the epoch / iteration counters, the best CER so far and the random streams (torch,
+# numpy, and the device seed the dropout masks are a function of) are lost. They go into `<path>.resume`, a plain
+# pickle of python / numpy objects next to the two reference files, which stay byte-compatible with the reference.
+# ------------------------------------------------------------------------------------------------------------------
+def save_resume_state(path, progress, dropout_seed=None):
+    import pickle
+    payload = {"version": 1, "progress": dict(progress), "torch_rng": torch.get_rng_state().numpy().tobytes(),
+               "numpy_rng": np.random.get_state(), "dropout_seed": None if dropout_seed is None else int(dropout_seed)}
+    tmp = f"{path}.tmp"
+    with open(tmp, "wb") as f:
+        pickle.dump(payload, f)
+    import os
+    os.replace(tmp, path)          # a crash while writing never leaves a truncated sidecar behind
+    return payload
+
+
+def load_resume_state(path, restore_rng=True):
+    """-> payload dict, or None when there is no sidecar (a checkpoint written by the reference)."""
+    import os
+    import pickle
+    if not os.path.exists(path):
+        return None
+    with open(path, "rb") as f:
+        payload = pickle.load(f)
+    if restore_rng:
+        torch.set_rng_state(torch.frombuffer(bytearray(payload["torch_rng"]), dtype=torch.uint8))
+        np.random.set_state(payload["numpy_rng"])
+    return payload

@@ -155,3 +155,24 @@ def test_zeros_many_carves_aligned_zeroed_views():
         v.fill_(i + 1)                       # writing one view must not leak into another
     for i, v in enumerate(views):
         assert bool((v == i + 1).all())
+
+
+def test_resume_sidecar_round_trip(tmp_path):
+    """utils.save_resume_state / load_resume_state (SURVEY 8(f) rank 3): counters and random streams survive a restart;
+    a checkpoint without a sidecar (written by the reference) loads as 'no resume information'."""
+    U = pkg("utils")
+    path = str(tmp_path / "model.resume")
+    assert U.load_resume_state(path) is None
+    torch.manual_seed(123)
+    np.random.seed(456)
+    torch.rand(3), np.random.rand(3)                                  # advance both streams past their seeds
+    U.save_resume_state(path, {"phase": "sup_pretrain", "epoch": 4, "best_cer": 0.25}, dropout_seed=987654321)
+    want_t, want_n = torch.rand(5), np.random.rand(5)                 # what the run would have drawn next
+    torch.manual_seed(1)
+    np.random.seed(2)
+    state = U.load_resume_state(path)
+    assert state["progress"] == {"phase": "sup_pretrain", "epoch": 4, "best_cer": 0.25}
+    assert state["dropout_seed"] == 987654321 and state["version"] == 1
+    assert torch.equal(torch.rand(5), want_t) and np.array_equal(np.random.rand(5), want_n)
+    assert not os.path.exists(path + ".tmp")
+    assert U.load_resume_state(path, restore_rng=False)["progress"]["epoch"] == 4
