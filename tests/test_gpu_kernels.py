@@ -48,9 +48,10 @@ def test_att_param_grads_split_equals_single_pass_and_torch(B, L, Te, A, C):
     dP3, dm3, dg3 = run(3)
     dP1, dm1, dg1 = run(1)
     dP2, dm2, dg2 = run(2)
-    assert torch.allclose(dP1, dP3, rtol=1e-6, atol=1e-6) and not dm1.any() and not dg1.any()     # dP only
-    assert torch.allclose(dm2, dm3, rtol=1e-6, atol=1e-6) and torch.allclose(dg2, dg3, rtol=1e-6, atol=1e-6)
-    assert not dP2.any()                                                                           # parameters only
+    def close(a, b):      # the instances are compiled separately (different FMA contraction): equal to f32 rounding
+        return float((a - b).abs().max()) <= 1e-5 * float(b.abs().max())
+    assert close(dP1, dP3) and not dm1.any() and not dg1.any()                                     # dP only
+    assert close(dm2, dm3) and close(dg2, dg3) and not dP2.any()                                   # parameters only
     # torch fp32/fp64 reference (the kernel recomputes tanh with tanh.approx: 2^-11 relative)
     s = torch.tanh(P.double()[:, None] + dz.double()[:, :, None] + torch.einsum("blec,ac->blea", conv[..., :C].double(), matt.double()))
     ds = de.double()[..., None] * gv.double() * (1 - s * s)
