@@ -71,5 +71,12 @@ def test_solver_entry_points(tmp_path):
         assert 0 <= cer2 and os.path.exists(os.path.join(root, "test.txt"))
         val_loss, cer3, hyp, ref = s2.validation()
         assert np.isfinite(val_loss) and len(hyp) == len(ref) == 4
+        # resume sidecar: written next to the reference's files, restored with the optimiser,
+        # and `resume: true` continues the supervised phase at the next epoch instead of starting over
+        assert os.path.exists(os.path.join(root, "m.resume")) and os.path.exists(os.path.join(root, "m-001.resume"))
+        assert s2.progress.get("phase") == "sup_pretrain" and s2.progress.get("epoch") == 1
+        s3 = S.Solver(dict(cfg, resume=True, epochs=3), load_model=True)
+        s3.sup_pretrain()
+        assert s3.progress["epoch"] == 2 and os.path.exists(os.path.join(root, "m-002.ckpt"))
     finally:
         os.chdir(cwd)
