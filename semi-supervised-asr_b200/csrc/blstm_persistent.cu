@@ -65,23 +65,6 @@ bool geom_for(int H, Geom& g) {
   return g.MTW <= 2 && g.KTW <= kMaxKTW && g.UGC <= kMaxUGC;
 }
 
-__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void st_async_b32(uint32_t addr, uint32_t v, uint32_t mbar) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
-               ::"r"(addr), "r"(v), "r"(mbar) : "memory");
-}
-__device__ __forceinline__ void st_async_v4(uint32_t addr, uint4 v, uint32_t mbar) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
-               ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(mbar) : "memory");
-}
-__device__ __forceinline__ void st_async_v2(uint32_t addr, uint32_t v0, uint32_t v1, uint32_t mbar) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];"
-               ::"r"(addr), "r"(v0), "r"(v1), "r"(mbar) : "memory");
-}
 // Asynchronous global->shared copies (LDGSTS): the per-timestep operands are prefetched kPF steps
 // ahead without occupying registers or the load scoreboard (a register ring made every branch of
 // the step loop wait for DRAM: profiles/r01_persist_v2_stalls.txt).

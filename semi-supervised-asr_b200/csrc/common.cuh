@@ -182,6 +182,41 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // ----------------------------------------------------------------------------------------
+// distributed shared memory: remote stores that carry their own completion (st.async + mbarrier
+// complete_tx). The payload and the transaction count land in the destination CTA together, so the
+// consumer needs only a CTA-scope mbarrier wait: no cluster barrier, no fence.
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_async_b32(uint32_t addr, uint32_t v, uint32_t mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+               ::"r"(addr), "r"(v), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void st_async_v2(uint32_t addr, uint32_t v0, uint32_t v1, uint32_t mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];"
+               ::"r"(addr), "r"(v0), "r"(v1), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void st_async_v4(uint32_t addr, uint4 v, uint32_t mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+               ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(mbar) : "memory");
+}
+// Bounded CTA-scope wait with a tag for the trap message (a protocol bug must trap, not hang the GPU box). The
+// report lives in a cold, non-inlined function so that printf's argument buffer does not grow the callers' frames.
+static __device__ __noinline__ void mbar_timeout(int tag) {
+  printf("las: mbarrier %d wait timeout (block %d,%d thread %d)\n", tag, blockIdx.x, blockIdx.y, threadIdx.x);
+  __trap();
+}
+__device__ __forceinline__ void mbar_wait_tag(uint64_t* bar, uint32_t parity, int tag) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 24)) mbar_timeout(tag);
+  }
+}
+
+// ----------------------------------------------------------------------------------------
 // TMA (cp.async.bulk.tensor) 2D load, global -> shared, completes on an mbarrier
 // ----------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {

@@ -4,17 +4,33 @@
 // 16 CTAs by output row and stay resident in REGISTERS as mma.m16n8k16 A fragments for the whole
 // sequence; per-utterance attention operands (P = mlp_enc(enc_h), Q = mlp_o.weight(enc_h)) are
 // sharded by encoder frame over the G = 16/NB "owner" CTAs of each utterance and stay resident in
-// SHARED MEMORY. Per step the CTAs exchange only small vectors through distributed shared memory
-// (st.shared::cluster) and meet at cluster barriers:
+// SHARED MEMORY. Per step the CTAs exchange only small vectors through distributed shared memory.
+// Every exchange is a set of st.async stores that carry their own completion (mbarrier complete_tx in
+// the destination CTA); the consumer waits on a CTA-scope mbarrier phase. There is NO cluster barrier
+// and no fence in the step loop (the first version met at 4 barrier.cluster pairs per step: 27 % of
+// a forward step, and the release fence stalled on every store in flight):
 //
 //   P1  gates = embx_t + Wr [z_{t-1}; c_{t-1}]   row-sharded MMA -> LSTM cell -> z_t shard
-//       -> broadcast z_t (bf16 B-fragment words) to all 16 CTAs                     | barrier
-//   P2  dz = mlp_dec z_t  (row-sharded MMA) -> to the owners of each utterance      | barrier
+//       -> z_t (bf16 B-fragment words) to all 16 CTAs                     [mbarrier bz[buf]]
+//       (warps that have no cell epilogue run the location conv of w_{t-1} meanwhile)
+//   P2  dz = mlp_dec z_t  (row-sharded MMA) -> to the owners of each utterance      [bdz]
 //   P3  owners: e = gvec . tanh(P + dz + mlp_att conv(w_{t-1})) for their frames (the mlp_att
-//       contraction on tensor cores, conv split hi/lo), local softmax statistics, partial
-//       context sum_te p[te] Q[te] -> reduce-scatter among the owners                | barrier
-//   P4  owners: combine statistics -> w_t, c_t = (sum_te w_t[te] Q[te]) + mlp_o.bias
-//       -> broadcast c_t to all 16 CTAs                                              | barrier
+//       contraction on tensor cores, conv split hi/lo) -> all owners of the utterance  [be]
+//   P4  owners: softmax over all Te frames -> w_t, c_t = (sum_te w_t[te] Q[te]) + mlp_o.bias
+//       -> c_t to all 16 CTAs                                                 [bc[buf]]
+//
+// Write-after-read safety without barriers (X = any sender, Y = the receiving CTA):
+//   zB[buf] ([z_t; c_t], double buffered): X writes z_{t+1} / c_{t+1} into zB[t&1] only after its own
+//     P1(t+1), which waited for z_t AND c_t from every CTA / owner, Y included; Y sends z_t after the
+//     __syncthreads that ends its gate MMA of step t (the last reader of zB[t&1], which held
+//     [z_{t-1}; c_{t-1}]; the mlp_dec MMA of step t-1 read it even earlier).
+//   dzv: X writes dz_{t+1} after P1(t+1), i.e. after c_t from Y, which Y sends at the end of P4(t),
+//     after its P3(t) readers of dzv passed two __syncthreads.
+//   e_all: a sibling owner writes e_{t+1} after P1(t+1), i.e. after c_t from Y, sent after Y's softmax
+//     of step t has read e_all.
+//   mbarrier phases: the same argument shows no complete_tx of phase k+1 can reach a barrier before
+//     its phase k completed; thread 0 re-arms (arrive.expect_tx) right after its own wait, and a
+//     complete_tx that arrives before the re-arm only makes the tx-count transiently negative.
 //
 // c_t = mlp_o(sum_te w[te] enc_h[te]) is evaluated as sum_te w[te] (mlp_o.weight enc_h[te]) + bias
 // (softmax weights sum to one), which removes mlp_o from the serial loop.
@@ -28,6 +44,7 @@ namespace las {
 namespace {
 
 constexpr int kCS = 16;        // CTAs per cluster
+constexpr int kSmemMax = 226 * 1024;   // dynamic shared memory both kernels may use (227 KB per CTA minus the static part)
 constexpr int kThreads = 512;
 constexpr int kWarps = 16;
 constexpr int kMaxFG = 14;     // gate fragments per warp
@@ -43,9 +60,10 @@ struct DGeom {
   int TR, TT, WPT, NTW;  // frames per owner, 16-frame tiles, warps per tile, 8-wide att n-tiles per warp
   int AT8, OS, OTs;      // A/8; context dims per owner; 16-row tiles of an owner's context slice
   int KTe, KTc, NC;      // k-tiles over all Te frames; k-tiles over the conv taps; 8-channel n-tiles of the conv
+  int cw0, WPTc;         // location conv: first warp, warps per frame tile (the warps behind the cell-epilogue warps)
   int Pld, QTld, Tw;     // row strides of the P slice (f32) and of the transposed Q slice (bf16); padded alignment length
   // shared-memory carve-up (byte offsets)
-  int o_zB, o_red, o_dzv, o_cred, o_wbuf, o_cwB, o_matt, o_gv, o_P, o_Q, o_epart, o_eall, o_pun, o_wred;
+  int o_zB, o_red, o_red2, o_dzv, o_cred, o_wbuf, o_cwB, o_matt, o_gv, o_P, o_Q, o_epart, o_eall, o_pun, o_wred;
   int smem;
 };
 
@@ -74,6 +92,12 @@ bool dec_geom(const las_dec_args* a, int NB, DGeom& g) {
   g.TT = (g.TR + 15) / 16;
   if (g.TT > kWarps) return false;
   g.WPT = kWarps / g.TT;
+  {
+    // the conv of w_{t-1} runs next to the cell epilogue of step t, on the warps the epilogue leaves idle
+    const int epi_warps = (g.UPC * NB + 31) / 32;
+    g.cw0 = epi_warps < kWarps - g.TT ? epi_warps : kWarps - g.TT;
+    g.WPTc = (kWarps - g.cw0) / g.TT;
+  }
   g.AT8 = A / 8;
   g.NTW = (g.AT8 + g.WPT - 1) / g.WPT;
   g.KTe = (Te + 15) / 16;
@@ -87,6 +111,7 @@ bool dec_geom(const las_dec_args* a, int NB, DGeom& g) {
   auto take = [&](int bytes) { const int o = off; off += rup(bytes, 16); return o; };
   g.o_zB = take(2 * g.KTp * 256);
   g.o_red = take(kWarps * 128 * 4);
+  g.o_red2 = take(kWarps * 128 * 4);
   g.o_dzv = take(A * 4);
   g.o_cred = take(kWarps * 32 * 32);
   g.o_wbuf = take(g.Tw * 4);
@@ -100,7 +125,7 @@ bool dec_geom(const las_dec_args* a, int NB, DGeom& g) {
   g.o_pun = take(g.KTe * 16 * 4);
   g.o_wred = take(2 * kWarps * 4);
   g.smem = off;
-  return g.smem <= 220 * 1024;
+  return g.smem <= kSmemMax;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -200,12 +225,19 @@ struct DecFwdP {
 __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __grid_constant__ DecFwdP p_in) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ DecFwdP p;
+  __shared__ __align__(8) uint64_t bars[6];   // bz[0], bz[1], bc[0], bc[1], bdz, be (see the header comment)
   for (int i = threadIdx.x; i < static_cast<int>(sizeof(DecFwdP) / 4); i += kThreads)
     reinterpret_cast<uint32_t*>(&p)[i] = reinterpret_cast<const uint32_t*>(&p_in)[i];
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 6; ++i) mbar_init(&bars[i], 1);
+    fence_mbar_init();
+  }
   __syncthreads();
   const DGeom& g = p.g;
+  uint64_t* bz = bars; uint64_t* bc = bars + 2; uint64_t* bdz = bars + 4; uint64_t* be = bars + 5;
   uint32_t* zB = reinterpret_cast<uint32_t*>(smem + g.o_zB);       // [2][KTp][32][2]
-  float* red = reinterpret_cast<float*>(smem + g.o_red);           // [16][32][4]
+  float* red = reinterpret_cast<float*>(smem + g.o_red);           // [16][32][4] gate partial sums (P1)
+  float* red2 = reinterpret_cast<float*>(smem + g.o_red2);         // [16][32][4] mlp_dec partial sums (P2)
   float* dzv = reinterpret_cast<float*>(smem + g.o_dzv);           // [A]
   float4* cred = reinterpret_cast<float4*>(smem + g.o_cred);       // [16 warps][2][32] partial conv accumulators
   float* wbuf = reinterpret_cast<float*>(smem + g.o_wbuf);         // [Te + 2K + 48], w[j] at wbuf[K + j]
@@ -331,10 +363,15 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
   // P3: (frame tile, attention-dim slice) of this warp
   const int e_tt = warp / g.WPT, e_wi = warp % g.WPT;
   const bool e_act = warp < g.TT * g.WPT && ntl > 0;
-  // conv k-tiles of my frame tile: taps that can touch a valid alignment entry
   const int cm = te0 + 16 * e_tt;
-  const int ckt_lo = max(0, K - (cm + 15)) >> 4;
-  const int ckt_hi = (cm < Te) ? (min(2 * K, K - cm + Te - 1) >> 4) : -1;
+  // location conv (runs next to the cell epilogue): (frame tile, K split) of this warp
+  const int cv = warp - g.cw0;
+  const bool c_act = cv >= 0 && cv < g.TT * g.WPTc && ntl > 0;
+  const int c_tt = c_act ? cv / g.WPTc : 0, c_wi = c_act ? cv % g.WPTc : 0;
+  // conv k-tiles of that frame tile: taps that can touch a valid alignment entry
+  const int cmc = te0 + 16 * c_tt;
+  const int ckt_lo = max(0, K - (cmc + 15)) >> 4;
+  const int ckt_hi = (cmc < Te) ? (min(2 * K, K - cmc + Te - 1) >> 4) : -1;
   float* csave_ptr = p.conv_save ? p.conv_save + (static_cast<int64_t>(own_ok ? b_own : 0) * L * Te + cm) * 16 : nullptr;
   // P4
   float* ws_row = p.ws + (static_cast<int64_t>(own_ok ? b_own : 0) * R + 1) * Te;
@@ -342,16 +379,33 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
   const int o_l0 = 16 * c_mt + gq;                         // local context dims o_l0, o_l0 + 8 (lanes with tig == 0)
   // cluster-mapped base addresses
   const uint32_t zB_base = smem_u32(zB), dzv_base = smem_u32(dzv), eall_base = smem_u32(e_all);
+  const uint32_t bars_base = smem_u32(bars);      // bz[i] at +8i, bc[i] at +16+8i, bdz at +32, be at +40
   const float scal = p.att_scaling;
   const bool drop_on = p.drop_p > 0.f;
+  // bytes a barrier phase counts: z_t of all NB columns from all CTAs; c_t of the valid utterances; dz and the
+  // energies of my own utterance
+#define TX_Z (2u * p.Hd * g.NB)
+#define TX_C (2u * p.O * max(0, min(g.NB, p.B - static_cast<int>(blockIdx.y) * g.NB)))
+#define TX_DZ (4u * p.A)
+#define TX_E (4u * p.Te)
+  if (tid == 0) {
+    const uint32_t tx_z = TX_Z, tx_c = TX_C, tx_dz = TX_DZ, tx_e = TX_E;
+    mbar_arrive_expect_tx(&bz[1], tx_z);      // step 0 writes buffer 1
+    mbar_arrive_expect_tx(&bc[1], tx_c);
+    if (own_ok) {
+      mbar_arrive_expect_tx(bdz, tx_dz);
+      mbar_arrive_expect_tx(be, tx_e);
+    }
+  }
 
-  cluster_barrier();   // every CTA's shared memory is initialised before any remote store
+  cluster_barrier();   // every CTA's shared memory and barriers are initialised before any remote store
   const bool trace = p.dbg != nullptr && blockIdx.y == 0 && rank == 0 && tid == 0;
 #define DTRACE(slot) do { if (trace && t >= 8 && t < 12) p.dbg[(t - 8) * 16 + (slot)] = clock64(); } while (0)
 
   for (int t = 0; t < L; ++t) {
-    const int par = t & 1;
-    const int zb_nxt_w = (par ^ 1) * g.KTp * 64;     // word offset of the buffer that receives [z_t; c_t]
+    const int par = t & 1, nxt = par ^ 1;
+    const int zb_nxt_w = nxt * g.KTp * 64;     // word offset of the buffer that receives [z_t; c_t]
+    const uint32_t ph2 = (t >> 1) & 1;            // phase parity of bz[nxt] / bc[nxt] at this step
 
     // ================= P1: LSTM cell =================
     DTRACE(0);
@@ -361,6 +415,16 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
       for (int k = 0; k < 4; ++k) ex[k] = __ldg(ex_ptr + k * Hd);
     }
     ex_ptr += 4 * Hd;
+    if (t > 0) {      // [z_{t-1}; c_{t-1}] complete in zB[par]
+      const uint32_t php = ((t - 1) >> 1) & 1;
+      mbar_wait_tag(&bz[par], php, 0);
+      mbar_wait_tag(&bc[par], php, 1);
+    }
+    if (tid == 0 && t + 1 < L) {   // step t+1 writes zB[par]: its previous phase (step t-1) is complete
+      mbar_arrive_expect_tx(&bz[par], TX_Z);
+      mbar_arrive_expect_tx(&bc[par], TX_C);
+    }
+    DTRACE(1);
     if (g_act) {
       float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
       // padded fragments (zero A) read padded, all-zero k-tiles of the state buffer
@@ -377,17 +441,12 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
       reinterpret_cast<float4*>(red)[warp * 32 + lane] =
           make_float4(acc0[0] + acc1[0], acc0[1] + acc1[1], acc0[2] + acc1[2], acc0[3] + acc1[3]);
     }
-    DTRACE(1);
     __syncthreads();
     DTRACE(2);
-    // Global stores of a phase's results are issued AFTER the phase's cluster barrier: the barrier's release is a
-    // memory fence that waits for every store the thread has in flight, and HBM/L2 write acknowledgements ahead of
-    // it were 12 % of this kernel's stall samples (ERRBAR, profiles/r01z_ncu_full_summary.txt). Stored after the
-    // barrier, they complete under the next phase.
-    uint2 sv_pk = make_uint2(0u, 0u);
-    __nv_bfloat16 sv_z = __float2bfloat16(0.f);
     if (warp < epi_warps) {
       uint32_t zbits = 0u;
+      uint2 sv_pk = make_uint2(0u, 0u);
+      __nv_bfloat16 sv_z = __float2bfloat16(0.f);
       if (epi) {
         const int ul4 = ulc & 3;
         const float gi = red_gather(red, e_w0, g.KSg, ul4, n_e) + ex[0];
@@ -412,39 +471,26 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
         const uint32_t w0 = (ulc & 2) ? wo : wp, w1 = (ulc & 2) ? wp : wo;
         const uint32_t off = zB_base + 4u * static_cast<uint32_t>(zb_nxt_w + z_word);
 #pragma unroll
-        for (int i = 0; i < kCS / 4; ++i) st_remote_v2_u32(mapa(off, (ulc & 3) * (kCS / 4) + i), w0, w1);
-      }
-    }
-    DTRACE(3);
-    cluster_barrier();
-    DTRACE(4);
-    if (epi_ok) {
-      reinterpret_cast<uint2*>(p.gates_save)[sv_idx] = sv_pk;
-      p.c_save[sv_idx] = cell;
-      zc_z_ptr[0] = sv_z;
-    }
-    sv_idx += Hd; zc_z_ptr += ZC;
-
-    // ================= P2: dz = mlp_dec z_t; location conv of w_{t-1} on tensor cores =================
-    if (d_act) {
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-      const uint2* hb = reinterpret_cast<const uint2*>(zB + zb_nxt_w) + lane + d_kt0 * 32;
-#pragma unroll
-      for (int j = 0; j < kMaxFD; ++j) {
-        if (j < nfd) {
-          const uint2 b = hb[j * 32];
-          const uint32_t Af[4] = {Ad[j].x, Ad[j].y, Ad[j].z, Ad[j].w};
-          mma_bf16_16816(acc, Af, b.x, b.y);
+        for (int i = 0; i < kCS / 4; ++i) {
+          const uint32_t dst = (ulc & 3) * (kCS / 4) + i;
+          st_async_v2(mapa_u32(off, dst), w0, w1, mapa_u32(bars_base + 8u * nxt, dst));
         }
       }
-      reinterpret_cast<float4*>(red)[warp * 32 + lane] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      if (epi_ok) {     // saved activations: off the critical path, after the sends
+        reinterpret_cast<uint2*>(p.gates_save)[sv_idx] = sv_pk;
+        p.c_save[sv_idx] = cell;
+        zc_z_ptr[0] = sv_z;
+      }
     }
-    if (e_act) {
+    sv_idx += Hd; zc_z_ptr += ZC;
+    DTRACE(3);
+    // location conv of w_{t-1} on tensor cores (independent of z_t: overlaps the cell epilogue and the z_t hop)
+    if (c_act) {
       // conv[r][c] = sum_k x[r + k] cw[c][k], x[i] = wbuf[cm + i]: a Hankel matrix times the weights.
       // A fragment of k-tile kt: a0 = y(2kt), a1 = a2 = y(2kt+1), a3 = y(2kt+2), y(j) = x[g + 2tig + 8j .. +1]
       float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
-      const float* xb = wbuf + cm + gq + 2 * tig;
-      for (int kt = ckt_lo + e_wi; kt <= ckt_hi; kt += g.WPT) {
+      const float* xb = wbuf + cmc + gq + 2 * tig;
+      for (int kt = ckt_lo + c_wi; kt <= ckt_hi; kt += g.WPTc) {
         const float* xk = xb + 16 * kt;
         uint32_t Ah[4], Al[4];
         split_bf16x2(xk[0], xk[1], Ah[0], Al[0]);
@@ -462,29 +508,51 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
           mma_bf16_16816(c1, Ah, b1.z, b1.w);
         }
       }
-      cred[(warp * 2) * 32 + lane] = make_float4(c0[0], c0[1], c0[2], c0[3]);
-      cred[(warp * 2 + 1) * 32 + lane] = make_float4(c1[0], c1[1], c1[2], c1[3]);
+      cred[(cv * 2) * 32 + lane] = make_float4(c0[0], c0[1], c0[2], c0[3]);
+      cred[(cv * 2 + 1) * 32 + lane] = make_float4(c1[0], c1[1], c1[2], c1[3]);
+    }
+    DTRACE(4);
+
+    // ================= P2: dz = mlp_dec z_t =================
+    if (d_act) {
+      mbar_wait_tag(&bz[nxt], ph2, 2);          // z_t of every CTA has landed in zB[nxt]
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      const uint2* hb = reinterpret_cast<const uint2*>(zB + zb_nxt_w) + lane + d_kt0 * 32;
+#pragma unroll
+      for (int j = 0; j < kMaxFD; ++j) {
+        if (j < nfd) {
+          const uint2 b = hb[j * 32];
+          const uint32_t Af[4] = {Ad[j].x, Ad[j].y, Ad[j].z, Ad[j].w};
+          mma_bf16_16816(acc, Af, b.x, b.y);
+        }
+      }
+      reinterpret_cast<float4*>(red2)[warp * 32 + lane] = make_float4(acc[0], acc[1], acc[2], acc[3]);
     }
     __syncthreads();
-    float dz_v = 0.f;
-    if (depi_ok) {
-      dz_v = red_gather(red, d_w0, g.KSd, al & 15, n_d) + pbar_d;
-      const uint32_t off = dzv_base + 4u * a_d;
-      for (int qq = 0; qq < G; ++qq) st_remote_f32(mapa(off, n_d * G + qq), dz_v);
-    }
     DTRACE(5);
-    cluster_barrier();
-    DTRACE(6);
-    if (depi_ok) dzf_ptr[0] = dz_v;
+    if (depi_ok) {
+      const float dz_v = red_gather(red2, d_w0, g.KSd, al & 15, n_d) + pbar_d;
+      const uint32_t off = dzv_base + 4u * a_d;
+      for (int qq = 0; qq < G; ++qq) {
+        const uint32_t dst = n_d * G + qq;
+        st_async_b32(mapa_u32(off, dst), __float_as_uint(dz_v), mapa_u32(bars_base + 32u, dst));
+      }
+      dzf_ptr[0] = dz_v;
+    }
     dzf_ptr += A;
+    DTRACE(6);
 
     // ================= P3: energies of my frames -> all owners of the utterance =================
+    if (own_ok && (e_act || warp == 0)) {
+      mbar_wait_tag(bdz, par, 3);                // dz_t of my utterance is complete in dzv
+      if (tid == 0 && t + 1 < L) mbar_arrive_expect_tx(bdz, TX_DZ);
+    }
     if (e_act) {
       const int r0 = 16 * e_tt + gq, r1 = r0 + 8;
       // conv features in A-fragment position: sum of the K-split partials of my frame tile
       float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int w = 0; w < g.WPT; ++w) {
-        const float4 a = cred[((e_tt * g.WPT + w) * 2) * 32 + lane], b = cred[((e_tt * g.WPT + w) * 2 + 1) * 32 + lane];
+      for (int w = 0; w < g.WPTc; ++w) {
+        const float4 a = cred[((e_tt * g.WPTc + w) * 2) * 32 + lane], b = cred[((e_tt * g.WPTc + w) * 2 + 1) * 32 + lane];
         s0.x += a.x; s0.y += a.y; s0.z += a.z; s0.w += a.w;
         s1.x += b.x; s1.y += b.y; s1.z += b.z; s1.w += b.w;
       }
@@ -542,16 +610,19 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
       for (int w = 0; w < g.WPT; ++w) e += epart[w * g.TT * 16 + tid];
       e *= scal;
       const uint32_t off = eall_base + 4u * (te0 + tid);
-      for (int qq = 0; qq < G; ++qq) st_remote_f32(mapa(off, n_own * G + qq), e);
+      for (int qq = 0; qq < G; ++qq) {
+        const uint32_t dst = n_own * G + qq;
+        st_async_b32(mapa_u32(off, dst), __float_as_uint(e), mapa_u32(bars_base + 40u, dst));
+      }
     }
     DTRACE(9);
-    cluster_barrier();
-    DTRACE(10);
 
     // ================= P4: softmax over all Te frames (every owner), context slice, broadcast =================
-    float w_keep = 0.f, ca_keep = 0.f, cb_keep = 0.f;
-    __nv_bfloat16 ha_keep = __float2bfloat16(0.f), hb_keep = ha_keep;
-    bool va_keep = false, vb_keep = false;
+    if (own_ok) {
+      mbar_wait_tag(be, par, 4);                 // the energies of all Te frames are complete in e_all
+      if (tid == 0 && t + 1 < L) mbar_arrive_expect_tx(be, TX_E);
+    }
+    DTRACE(10);
     {
       const bool fr = own_ok && tid < Te;
       const float e = fr ? e_all[tid] : -INFINITY;
@@ -570,6 +641,7 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
 #pragma unroll
       for (int w = 0; w < kWarps; ++w) S += wred[kWarps + w];
       const float invS = own_ok ? 1.f / S : 0.f;
+      float w_keep = 0.f;
       if (fr) {
         w_keep = pv * invS;
         wbuf[K + tid] = w_keep;
@@ -598,9 +670,9 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
         __nv_bfloat16 ha = __float2bfloat16(0.f), hb = ha;
         if (va) ha = __float2bfloat16(ca + p.cbias[static_cast<int64_t>(b_own) * O + oa]);
         if (vb) hb = __float2bfloat16(cb + p.cbias[static_cast<int64_t>(b_own) * O + ob]);
-        va_keep = va; vb_keep = vb; ca_keep = ca; cb_keep = cb; ha_keep = ha; hb_keep = hb;
+        const __nv_bfloat16 ha_keep = ha, hb_keep = hb;     // the output layer (zc in global memory) sees c_t
         if (drop_on) {
-          // what the NEXT step's gates see is dropout(c_t); the output layer (zc in global memory) sees c_t
+          // what the NEXT step's gates see is dropout(c_t)
           const unsigned long long seed = *p.seed_dev, base = (static_cast<unsigned long long>(b_own) * R + t + 1) * O;
           const float sc = 1.f / (1.f - p.drop_p);
           if (va) ha = dropout_keep(seed, p.drop_site, base + oa, p.drop_p) ? __float2bfloat16(__bfloat162float(ha) * sc) : __float2bfloat16(0.f);
@@ -620,40 +692,41 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
         const uint32_t xb0 = __shfl_xor_sync(0xffffffffu, qb0, 16), xb1 = __shfl_xor_sync(0xffffffffu, qb1, 16);
         if (tig == 0 && va) {     // OS % 16 == 0 on this path: every tile is full
           const bool hi = (gq & 4) != 0;
-          const uint32_t A0 = hi ? xa0 : qa0, A1 = hi ? xa1 : qa1, A2 = hi ? qa0 : xa0, A3 = hi ? qa1 : xa1;
-          const uint32_t B0 = hi ? xb0 : qb0, B1 = hi ? xb1 : qb1, B2 = hi ? qb0 : xb0, B3 = hi ? qb1 : xb1;
+          const uint4 VA = hi ? make_uint4(xa0, xa1, qa0, qa1) : make_uint4(qa0, qa1, xa0, xa1);
+          const uint4 VB = hi ? make_uint4(xb0, xb1, qb0, qb1) : make_uint4(qb0, qb1, xb0, xb1);
           const uint32_t off = zB_base + 4u * static_cast<uint32_t>(zb_nxt_w + qfrag_word(Hd + q * OS + 16 * c_mt, n_own));
 #pragma unroll
           for (int i = 0; i < 2; ++i) {
-            const uint32_t dst = mapa(off, 2 * gq + i);
-            st_remote_v4_u32(dst, A0, A1, A2, A3);
-            st_remote_v4_u32(dst + 16u, B0, B1, B2, B3);
+            const uint32_t dst = mapa_u32(off, 2 * gq + i), bar = mapa_u32(bars_base + 16u + 8u * nxt, 2 * gq + i);
+            st_async_v4(dst, VA, bar);
+            st_async_v4(dst + 16u, VB, bar);
+          }
+        }
+        // saved for the output layer and the backward pass (after the sends: off the critical path)
+        if (va | vb) {
+          __nv_bfloat16* zrow = p.zc + (static_cast<int64_t>(b_own) * R + t + 1) * ZC + Hd;
+          float* crow = p.cpre ? p.cpre + (static_cast<int64_t>(b_own) * L + t) * O : nullptr;
+          if (va) {
+            if (crow) crow[oa] = ca;
+            zrow[oa] = ha_keep;
+          }
+          if (vb) {
+            if (crow) crow[ob] = cb;
+            zrow[ob] = hb_keep;
           }
         }
       }
+      if (own_ok && tid >= te0 && tid < te0 + ntl) ws_row[tid] = w_keep;      // tid < Te holds: te0 + ntl <= Te
     }
     DTRACE(11);
-    cluster_barrier();
-    DTRACE(12);
-    if (own_ok) {
-      if (tid >= te0 && tid < te0 + ntl) ws_row[tid] = w_keep;      // tid < Te holds: te0 + ntl <= Te
-      if (va_keep | vb_keep) {
-        const int oa = q * OS + o_l0, ob = oa + 8;
-        __nv_bfloat16* zrow = p.zc + (static_cast<int64_t>(b_own) * R + t + 1) * ZC + Hd;
-        float* crow = p.cpre ? p.cpre + (static_cast<int64_t>(b_own) * L + t) * O : nullptr;
-        if (va_keep) {
-          if (crow) crow[oa] = ca_keep;
-          zrow[oa] = ha_keep;
-        }
-        if (vb_keep) {
-          if (crow) crow[ob] = cb_keep;
-          zrow[ob] = hb_keep;
-        }
-      }
-    }
     ws_row += Te;
   }
+  cluster_barrier();   // nobody exits while remote stores may still target its shared memory
 #undef DTRACE
+#undef TX_Z
+#undef TX_C
+#undef TX_DZ
+#undef TX_E
 }
 
 // ==========================================================================================
@@ -661,11 +734,24 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
 // (more registers per thread: the row-sharded W^T fragments need 96 of them).
 //
 //   A  d[z_t; c_t] rows of this CTA = dzc_all_t + Wr^T dgates_{t+1}   (dgates all-gathered in the
-//      previous iteration) -> dc rows to the owners of each utterance             | barrier
+//      previous iteration) -> dc rows to the owners of each utterance             [mbarrier b_dc]
 //   B  owners: dw = Q dc + (conv-input gradient from step t+1); softmax backward; energy backward
 //      with tanh recomputed on tensor cores (P, dz_t, conv_t saved by the forward); ddz partial
-//      -> all CTAs; conv-input gradient for step t-1 -> sibling owners            | barrier
-//   C  dz_t += mlp_dec^T ddz; LSTM cell backward -> dgates_t -> all CTAs          | barrier
+//      -> all CTAs [b_ddz]; conv-input gradient for step t-1 -> sibling owners   [b_dwn]
+//   C  dz_t += mlp_dec^T ddz; LSTM cell backward -> dgates_t -> all CTAs          [b_dg]
+//
+// As in the forward kernel every exchange is st.async + mbarrier complete_tx; the step loop has no
+// cluster barrier. Write-after-read safety (X = sender, Y = receiver):
+//   dgB: X writes dgates_{t-1} at C(t-1) after b_ddz(t-1), i.e. after every owner's B(t-1), i.e. after
+//     dc from every CTA (Y included), which Y sends after the __syncthreads that ends its Wr^T MMA of
+//     step t-1 -- the only reader of dgB (dgates_t).
+//   dcbuf: X writes dc_{t-1} at A(t-1) after b_dg(t), i.e. after Y's C(t) sends, which follow Y's B(t).
+//   ddz_rx: an owner writes at B(t-1) after b_dc(t-1), i.e. after Y's A(t-1), which follows Y's C(t).
+//   dwn_rx is double buffered by step parity and has a whole step of slack.
+//
+// The conv-input gradient dwn[j] = sum_{tl,c} dconv[tl][c] cw[c][j - te + K] is evaluated as the small GEMM
+// G[tl][m] = sum_c dconv[tl][c] cw[c][m] on tensor cores (bf16 hi/lo split), stored skewed (column j = m + te - K)
+// so that the anti-diagonal sums become fixed-order, conflict-free column sums.
 //
 // Parameter gradients that are plain sums over (b, t) are NOT accumulated here: the kernel saves
 // de_t, dc_t, ddz_t, dgates_t, dconv_t and the post-loop kernels / GEMMs reduce them in parallel.
@@ -674,7 +760,6 @@ constexpr int kBT = 384;
 constexpr int kBW = 12;
 constexpr int kMaxFB = 20;     // Wr^T fragments per warp
 constexpr int kMaxFD2 = 4;     // mlp_dec^T fragments per warp
-constexpr int kCwLd = 20;      // row stride (floats) of the transposed conv weights: conflict-free LDS.128 over 8 consecutive taps
 
 struct BGeom {
   int NB, G, UPC, OPC, RPC;    // utterances per cluster, owners per utterance, z units / c dims / rows per CTA
@@ -683,7 +768,8 @@ struct BGeom {
   int TR, TT, WPT, NTW2;       // frames per owner, 16-frame tiles, warps per tile, 16-wide attention k-tiles per warp
   int KTo, AT8, NC, NT8;       // O/16; A/8; conv channel n-tiles; 8-wide tiles over the conv taps
   int Pld, Qld;
-  int o_dgB, o_red, o_dcbuf, o_P, o_Q, o_matt, o_matt2, o_cwB2, o_dwnrx, o_ddzrx, o_ddzB, o_wt, o_cpre, o_dzv,
+  int GR, Gld;                 // conv-input gradient: rows of G per pass, row stride (== 3 mod 32: conflict-free skewed stores)
+  int o_dgB, o_red, o_redC, o_dcbuf, o_P, o_Q, o_matt, o_matt2, o_cwB3, o_dwnrx, o_ddzrx, o_ddzB, o_wt, o_cpre, o_dzv,
       o_conv, o_de, o_dwpart, o_dwns, o_dwnout, o_dwnpart, o_gv, o_wred, o_scratch;
   int smem;
 };
@@ -716,12 +802,13 @@ bool dec_bgeom(const las_dec_args* a, int NB, BGeom& g) {
   auto take = [&](int bytes) { const int o = off; off += rup(bytes, 16); return o; };
   g.o_dgB = take(g.KSb * g.FB * 256);
   g.o_red = take(kBW * 128 * 4);
+  g.o_redC = take(kBW * 128 * 4);
   g.o_dcbuf = take(O * 4);
   g.o_P = take(g.TT * 16 * g.Pld * 2);
   g.o_Q = take(g.TT * 16 * g.Qld * 2);
   g.o_matt = take(g.AT8 * 32 * 16);
   g.o_matt2 = take(g.KTa * 2 * 32 * 8);
-  g.o_cwB2 = take(ksz * kCwLd * 4);
+  g.o_cwB3 = take(g.NT8 * 32 * 16);
   g.o_dwnrx = take(2 * g.G * Te * 4);
   g.o_ddzrx = take(g.G * NB * A * 4);
   g.o_ddzB = take(g.KTap * 256);
@@ -736,10 +823,16 @@ bool dec_bgeom(const las_dec_args* a, int NB, BGeom& g) {
   g.o_dwnpart = take((kBT / Te > 0 ? kBT / Te : 1) * Te * 4);
   g.o_gv = take(A * 4);
   g.o_wred = take(kBW * 4);
-  // phase-B scratch: ddz partials [TT][A] f32 + dconv partial accumulators [12 warps][2][32] float4
-  g.o_scratch = take(g.TT * A * 4 + kBW * 2 * 32 * 16);
+  // phase-B scratch: ddz partials [TT][A] f32 + dconv partial accumulators [12 warps][2][32] float4; afterwards
+  // the skewed G tile [GR][Gld] of the conv-input gradient
+  g.GR = g.TT >= 2 ? 32 : 16;
+  g.Gld = (Te + 28) / 32 * 32 + 3;
+  {
+    const int s1 = g.TT * A * 4 + kBW * 2 * 32 * 16, s2 = g.GR * g.Gld * 4;
+    g.o_scratch = take(s1 > s2 ? s1 : s2);
+  }
   g.smem = off;
-  return g.smem <= 220 * 1024;
+  return g.smem <= kSmemMax;
 }
 
 struct DecBwdP {
@@ -773,18 +866,25 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_constant__ DecBwdP p_in) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ DecBwdP p;
+  __shared__ __align__(8) uint64_t bars[4];   // b_dg, b_dc, b_ddz, b_dwn (see the comment above)
   for (int i = threadIdx.x; i < static_cast<int>(sizeof(DecBwdP) / 4); i += kBT)
     reinterpret_cast<uint32_t*>(&p)[i] = reinterpret_cast<const uint32_t*>(&p_in)[i];
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
+    fence_mbar_init();
+  }
   __syncthreads();
   const BGeom& g = p.g;
+  uint64_t* b_dg = bars; uint64_t* b_dc = bars + 1; uint64_t* b_ddz = bars + 2; uint64_t* b_dwn = bars + 3;
   uint32_t* dgB = reinterpret_cast<uint32_t*>(smem + g.o_dgB);     // [KSb*FB][32][2] all-gathered dgates_{t+1}
-  float* red = reinterpret_cast<float*>(smem + g.o_red);           // [12][32][4]
+  float* red = reinterpret_cast<float*>(smem + g.o_red);           // [12][32][4] phase A partial sums
+  float* redC = reinterpret_cast<float*>(smem + g.o_redC);         // [12][32][4] phase C partial sums
   float* dcbuf = reinterpret_cast<float*>(smem + g.o_dcbuf);       // [O] dc_t of my utterance
   __nv_bfloat16* P_s = reinterpret_cast<__nv_bfloat16*>(smem + g.o_P);
   __nv_bfloat16* Q_s = reinterpret_cast<__nv_bfloat16*>(smem + g.o_Q);   // [TT*16][Qld] my frames of Q
   uint4* mattB = reinterpret_cast<uint4*>(smem + g.o_matt);        // [AT8][32]      k = channel, n = attention dim
   uint2* mattB2 = reinterpret_cast<uint2*>(smem + g.o_matt2);      // [KTa][2][32]   k = attention dim, n = channel
-  float* cw_t = reinterpret_cast<float*>(smem + g.o_cwB2);         // [2K+1][kCwLd] transposed conv weights (channels padded to 16)
+  uint4* cwB3 = reinterpret_cast<uint4*>(smem + g.o_cwB3);         // [NT8][32] conv-weight B fragments: k = channel, n = tap (hi0, hi1, lo0, lo1)
   float* dwn_part = reinterpret_cast<float*>(smem + g.o_dwnpart);  // [kBT/Te][Te]
   float* dwn_rx = reinterpret_cast<float*>(smem + g.o_dwnrx);      // [2][G][Te]
   float* ddz_rx = reinterpret_cast<float*>(smem + g.o_ddzrx);      // [G][NB][A] f32 partials (owner partials cancel: bf16 is not enough)
@@ -801,6 +901,7 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
   float* wred = reinterpret_cast<float*>(smem + g.o_wred);
   float* ddz_part = reinterpret_cast<float*>(smem + g.o_scratch);  // [TT][A]
   float4* dcred = reinterpret_cast<float4*>(smem + g.o_scratch + g.TT * p.A * 4);   // [12][2][32]
+  float* Gs = reinterpret_cast<float*>(smem + g.o_scratch);        // [GR][Gld] skewed G tile (after ddz_part / dcred are consumed)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tig = lane & 3;
   const uint32_t rank = cluster_rank();
@@ -872,9 +973,19 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
     }
     mattB2[i] = make_uint2(pack_bf16x2(m[0], m[1]), pack_bf16x2(m[2], m[3]));
   }
-  for (int i = tid; i < ksz * kCwLd; i += kBT) {
-    const int k = i / kCwLd, c = i % kCwLd;
-    cw_t[i] = (c < C) ? p.conv_w[c * ksz + k] : 0.f;
+  for (int i = tid; i < g.NT8 * 32; i += kBT) {
+    // k = channel 2*(l & 3) + {0, 1, 8, 9}, n = tap 8*nt + (l >> 2)
+    const int nt = i >> 5, l = i & 31, m = 8 * nt + (l >> 2), c0 = 2 * (l & 3);
+    float w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = c0 + (k & 1) + 8 * (k >> 1);
+      w[k] = (c < C && m < ksz) ? p.conv_w[c * ksz + m] : 0.f;
+    }
+    uint4 v;
+    split_bf16x2(w[0], w[1], v.x, v.z);
+    split_bf16x2(w[2], w[3], v.y, v.w);
+    cwB3[i] = v;
   }
   for (int i = tid; i < g.TT * 16 * g.Pld; i += kBT) {
     const int r = i / g.Pld, a = i % g.Pld;
@@ -910,6 +1021,22 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
   // cluster-mapped bases
   const uint32_t dgB_base = smem_u32(dgB), dcbuf_base = smem_u32(dcbuf), dwnrx_base = smem_u32(dwn_rx),
                  ddzrx_base = smem_u32(ddz_rx);
+  const uint32_t bars_base = smem_u32(bars);      // b_dg +0, b_dc +8, b_ddz +16, b_dwn +24
+  // bytes per barrier phase: dgates of all NB columns from all CTAs; dc of my utterance; ddz partials of every valid
+  // owner; conv-input gradient partials of my utterance's owners
+#define TX_DG (8u * p.Hd * g.NB)
+#define TX_DC (4u * p.O)
+#define TX_DDZ (4u * p.A * g.G * max(0, min(g.NB, p.B - static_cast<int>(blockIdx.y) * g.NB)))
+#define TX_DWN (4u * p.Te * g.G)
+  if (tid == 0) {
+    const uint32_t tx_dg = TX_DG, tx_dc = TX_DC, tx_ddz = TX_DDZ, tx_dwn = TX_DWN;
+    mbar_arrive_expect_tx(b_dg, tx_dg);        // dgates_{L-1}, sent at C(L-1)
+    mbar_arrive_expect_tx(b_ddz, tx_ddz);
+    if (own_ok) {
+      mbar_arrive_expect_tx(b_dc, tx_dc);
+      if (L > 1) mbar_arrive_expect_tx(b_dwn, tx_dwn);
+    }
+  }
 
   __syncthreads();
   cluster_barrier();
@@ -918,6 +1045,7 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
 
   for (int t = L - 1; t >= 0; --t) {
     const int par = t & 1;
+    const uint32_t ph = (L - 1 - t) & 1;           // phase parity of the barriers filled during this step
     DTRACE(0);
     // ---------------- prefetch of this step's saved activations (consumed in phases B and C)
     if (own_ok) {
@@ -941,6 +1069,10 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
       }
     }
     // ================= phase A: d[z_t; c_t] rows = dzc_all + Wr^T dgates_{t+1} =================
+    if (t < L - 1) {
+      mbar_wait_tag(b_dg, ph ^ 1u, 10);            // dgates_{t+1} (sent at C(t+1)) complete in dgB
+      if (tid == 0) mbar_arrive_expect_tx(b_dg, TX_DG);     // next phase: the dgates_t sends of this step's phase C
+    }
     if (b_act) {
       float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
       const uint2* hb = reinterpret_cast<const uint2*>(dgB) + lane + b_kt0 * 32;
@@ -956,8 +1088,8 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
       reinterpret_cast<float4*>(red)[warp * 32 + lane] =
           make_float4(acc0[0] + acc1[0], acc0[1] + acc1[1], acc0[2] + acc1[2], acc0[3] + acc1[3]);
     }
-    __syncthreads();
-    float dc_keep = 0.f;
+    cp_async_wait_all();
+    __syncthreads();      // partial sums in `red`; the prefetched rows are visible to every thread
     if (epi_ok) {
       float mm = red_gather(red, a_w0, g.KSb, row_l & 15, n_e);
       if (p.drop_p > 0.f && !is_z)   // the path through the cell input of step t+1 carries that step's dropout mask
@@ -967,23 +1099,28 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
       if (is_z) {
         dz_acc = v;
       } else {
-        dc_keep = v;
         const uint32_t off = dcbuf_base + 4u * o_e;
-        for (int qq = 0; qq < G; ++qq) st_remote_f32(mapa(off, n_e * G + qq), v);
+        for (int qq = 0; qq < G; ++qq) {
+          const uint32_t dst = n_e * G + qq;
+          st_async_b32(mapa_u32(off, dst), __float_as_uint(v), mapa_u32(bars_base + 8u, dst));
+        }
+        p.dc_all[(static_cast<int64_t>(b_e) * L + t) * O + o_e] = v;
+        p.dcz_all[(static_cast<int64_t>(b_e) * R + t + 1) * ZC + Hd + o_e] = __float2bfloat16(v);
       }
     }
     dzc_ptr -= ZC;
-    cp_async_wait_all();
     DTRACE(1);
-    cluster_barrier();
-    DTRACE(2);
-    // global stores follow the barrier (its release fence would wait for their acknowledgements; see the forward kernel)
-    if (epi_ok && !is_z) {
-      p.dc_all[(static_cast<int64_t>(b_e) * L + t) * O + o_e] = dc_keep;
-      p.dcz_all[(static_cast<int64_t>(b_e) * R + t + 1) * ZC + Hd + o_e] = __float2bfloat16(dc_keep);
-    }
 
     // ================= phase B: attention backward for my frames =================
+    if (own_ok) {
+      mbar_wait_tag(b_dc, ph, 11);                 // dc_t of my utterance complete in dcbuf
+      if (tid == 0 && t > 0) mbar_arrive_expect_tx(b_dc, TX_DC);
+      if (t < L - 1) {
+        mbar_wait_tag(b_dwn, ph ^ 1u, 12);         // conv-input gradient partials sent at B(t+1)
+        if (tid == 0 && t > 0) mbar_arrive_expect_tx(b_dwn, TX_DWN);
+      }
+    }
+    DTRACE(2);
     // B1: dw = Q dc (tensor cores, K split over the warps of a frame tile); softmax dot product
     {
       float part = 0.f;
@@ -1107,8 +1244,9 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
             v.x += x.x; v.y += x.y; v.z += x.z; v.w += x.w;
           }
         const uint32_t off = ddzrx_base + 4u * ((q * NB + n_own) * A + 4 * aq);
+        const uint4 vb = make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
 #pragma unroll
-        for (int r = 0; r < kCS; ++r) st_remote_v4_f32(mapa(off, r), v.x, v.y, v.z, v.w);
+        for (int r = 0; r < kCS; ++r) st_async_v4(mapa_u32(off, r), vb, mapa_u32(bars_base + 16u, r));
       }
     }
     if (e_act && e_wi == 0) {
@@ -1139,54 +1277,85 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
         if (c0 + 9 < C) drow[(gq + 8) * C + c0 + 9] = s1.w;
       }
     }
-    __syncthreads();
-    // conv-input gradient of my frames for step t-1: dwn[j] = sum_{tl,c} dconv[tl][c] cw[c][j - te + K].
-    // thread -> (output frame j, frame residue); deterministic two-stage sum (no shared-memory float atomics)
+    __syncthreads();      // dconv of all my frames in conv_s; ddz_part / dcred are free (Gs aliases them)
+    // conv-input gradient of my frames for step t-1: dwn[j] = sum_{tl,c} dconv[tl][c] cw[c][j - (te0+tl) + K].
+    // G[tl][m] = sum_c dconv[tl][c] cw[c][m] on tensor cores (GR rows of G per pass), stored at column
+    // j = m + te0 + tl - K; thread (gi, j) then adds its rows tl = gi, gi + ngrp, .. in a fixed order.
     const int ngrp = max(1, kBT / Te);
-    if (own_ok && t > 0 && tid < ngrp * Te) {
+    if (own_ok && t > 0 && ntl > 0) {
       const int gi = tid / Te, j = tid - gi * Te;
-      float acc[12];
-#pragma unroll
-      for (int c = 0; c < 12; ++c) acc[c] = 0.f;
-      float acc2[4] = {0.f, 0.f, 0.f, 0.f};
-      const int nc4 = (C + 3) >> 2;
-      for (int tl = gi; tl < ntl; tl += ngrp) {
-        const int k = j - (te0 + tl) + K;
-        if (k < 0 || k > 2 * K) continue;
-        const float4* dr = reinterpret_cast<const float4*>(conv_s + tl * 16);
-        const float4* cr = reinterpret_cast<const float4*>(cw_t + k * kCwLd);
-        const float4 d0 = dr[0], d1 = dr[1], w0 = cr[0], w1 = cr[1];
-        acc[0] = fmaf(d0.x, w0.x, acc[0]); acc[1] = fmaf(d0.y, w0.y, acc[1]); acc[2] = fmaf(d0.z, w0.z, acc[2]); acc[3] = fmaf(d0.w, w0.w, acc[3]);
-        acc[4] = fmaf(d1.x, w1.x, acc[4]); acc[5] = fmaf(d1.y, w1.y, acc[5]); acc[6] = fmaf(d1.z, w1.z, acc[6]); acc[7] = fmaf(d1.w, w1.w, acc[7]);
-        if (nc4 > 2) {
-          const float4 d2 = dr[2], w2 = cr[2];
-          acc[8] = fmaf(d2.x, w2.x, acc[8]); acc[9] = fmaf(d2.y, w2.y, acc[9]); acc[10] = fmaf(d2.z, w2.z, acc[10]); acc[11] = fmaf(d2.w, w2.w, acc[11]);
+      const int mtp = g.GR >> 4;                 // m-tiles per pass
+      const int wm = warp % mtp, wn = warp / mtp, nws = kBW / mtp;
+      float sacc = 0.f;
+      for (int r_base = 0; r_base < g.TT * 16; r_base += g.GR) {
+        if (r_base + 16 * wm < g.TT * 16) {
+          const int r0 = r_base + 16 * wm + gq, r1 = r0 + 8;
+          uint32_t Ah[4], Al[4];
+          {
+            const float2 v0 = *reinterpret_cast<const float2*>(conv_s + r0 * 16 + 2 * tig);
+            const float2 v1 = *reinterpret_cast<const float2*>(conv_s + r1 * 16 + 2 * tig);
+            const float2 v2 = *reinterpret_cast<const float2*>(conv_s + r0 * 16 + 2 * tig + 8);
+            const float2 v3 = *reinterpret_cast<const float2*>(conv_s + r1 * 16 + 2 * tig + 8);
+            split_bf16x2(v0.x, v0.y, Ah[0], Al[0]);
+            split_bf16x2(v1.x, v1.y, Ah[1], Al[1]);
+            split_bf16x2(v2.x, v2.y, Ah[2], Al[2]);
+            split_bf16x2(v3.x, v3.y, Ah[3], Al[3]);
+          }
+          // column of element (row r, tap m): j = m + te0 + r - K
+          float* g0 = Gs + (r0 - r_base) * g.Gld + (te0 + r0 - K);
+          float* g1 = Gs + (r1 - r_base) * g.Gld + (te0 + r1 - K);
+          for (int nt = wn; nt < g.NT8; nt += nws) {
+            const uint4 bw = cwB3[nt * 32 + lane];
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            mma_bf16_16816(acc, Ah, bw.x, bw.y);
+            mma_bf16_16816(acc, Al, bw.x, bw.y);
+            mma_bf16_16816(acc, Ah, bw.z, bw.w);
+            const int m0 = 8 * nt + 2 * tig;
+            const int j0 = m0 + te0 + r0 - K, j1 = m0 + te0 + r1 - K;
+            if (r0 < ntl) {
+              if (m0 < ksz && j0 >= 0 && j0 < Te) g0[m0] = acc[0];
+              if (m0 + 1 < ksz && j0 + 1 >= 0 && j0 + 1 < Te) g0[m0 + 1] = acc[1];
+            }
+            if (r1 < ntl) {
+              if (m0 < ksz && j1 >= 0 && j1 < Te) g1[m0] = acc[2];
+              if (m0 + 1 < ksz && j1 + 1 >= 0 && j1 + 1 < Te) g1[m0 + 1] = acc[3];
+            }
+          }
         }
-        if (nc4 > 3) {
-          const float4 d3 = dr[3], w3 = cr[3];
-          acc2[0] = fmaf(d3.x, w3.x, acc2[0]); acc2[1] = fmaf(d3.y, w3.y, acc2[1]); acc2[2] = fmaf(d3.z, w3.z, acc2[2]); acc2[3] = fmaf(d3.w, w3.w, acc2[3]);
+        __syncthreads();
+        if (tid < ngrp * Te) {
+          const int r_end = min(r_base + g.GR, ntl);
+          // first row >= r_base of my residue class
+          int tl = r_base + ((gi - r_base % ngrp) + ngrp) % ngrp;
+          for (; tl < r_end; tl += ngrp) {
+            const int k = j - (te0 + tl) + K;
+            if (k >= 0 && k <= 2 * K) sacc += Gs[(tl - r_base) * g.Gld + j];
+          }
         }
+        __syncthreads();
       }
-      float sacc = (acc2[0] + acc2[1]) + (acc2[2] + acc2[3]);
-#pragma unroll
-      for (int c = 0; c < 12; ++c) sacc += acc[c];
-      dwn_part[gi * Te + j] = sacc;
+      if (tid < ngrp * Te) dwn_part[gi * Te + j] = sacc;
     }
     __syncthreads();
     if (own_ok && t > 0) {
       // partial conv-input gradient -> every owner of this utterance (slot q, parity of step t-1)
       for (int j = tid; j < Te; j += kBT) {
         float v = 0.f;
-        for (int gi = 0; gi < ngrp; ++gi) v += dwn_part[gi * Te + j];
-        for (int qq = 0; qq < G; ++qq)
-          st_remote_f32(mapa(dwnrx_base + 4u * (((par ^ 1) * G + q) * Te + j), n_own * G + qq), v);
+        if (ntl > 0)
+          for (int gi = 0; gi < ngrp; ++gi) v += dwn_part[gi * Te + j];
+        for (int qq = 0; qq < G; ++qq) {
+          const uint32_t dst = n_own * G + qq;
+          st_async_b32(mapa_u32(dwnrx_base + 4u * (((par ^ 1) * G + q) * Te + j), dst), __float_as_uint(v),
+                       mapa_u32(bars_base + 24u, dst));
+        }
       }
     }
     DTRACE(5);
-    cluster_barrier();
-    DTRACE(6);
 
     // ================= phase C: dz_t += mlp_dec^T ddz; cell backward; dgates -> all CTAs =================
+    mbar_wait_tag(b_ddz, ph, 13);                  // ddz partials of every owner complete in ddz_rx
+    if (tid == 0 && t > 0) mbar_arrive_expect_tx(b_ddz, TX_DDZ);
+    DTRACE(6);
     for (int idx = tid; idx < NB * A2; idx += kBT) {
       const int n = idx / A2, ap = idx - n * A2;
       float v0 = 0.f, v1 = 0.f;
@@ -1211,13 +1380,13 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
           mma_bf16_16816(acc, Af, b.x, b.y);
         }
       }
-      reinterpret_cast<float4*>(red)[warp * 32 + lane] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      reinterpret_cast<float4*>(redC)[warp * 32 + lane] = make_float4(acc[0], acc[1], acc[2], acc[3]);
     }
     __syncthreads();
     uint32_t w4[4] = {0u, 0u, 0u, 0u};
     {
       if (epi_ok && is_z) {
-        const float dh = dz_acc + red_gather(red, c_w0, g.KSd, row_l & 15, n_e);
+        const float dh = dz_acc + red_gather(redC, c_w0, g.KSd, row_l & 15, n_e);
         const float2 if_ = __half22float2(*reinterpret_cast<const __half2*>(&gpk.x));
         const float2 go_ = __half22float2(*reinterpret_cast<const __half2*>(&gpk.y));
         const float i = if_.x, f = if_.y, gc = go_.x, o = go_.y;
@@ -1240,21 +1409,26 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
         if (epi && is_z && (row_l & 1) == 0) {
           const int kt = u_e >> 2, pp = (u_e >> 1) & 1;
           const uint32_t off = dgB_base + 4u * static_cast<uint32_t>((kt * 32 + n_e * 4 + 2 * pp) * 2);
+          const uint4 vd = make_uint4(wd[0], wd[1], wd[2], wd[3]);
 #pragma unroll
-          for (int r = 0; r < kCS; ++r) st_remote_v4_u32(mapa(off, r), wd[0], wd[1], wd[2], wd[3]);
+          for (int r = 0; r < kCS; ++r) st_async_v4(mapa_u32(off, r), vd, mapa_u32(bars_base, r));
         }
       }
     }
     DTRACE(7);
-    cluster_barrier();
-    DTRACE(8);
     if (epi_ok && is_z) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) dg_ptr[k * Hd] = __ushort_as_bfloat16(static_cast<unsigned short>(w4[k]));
     }
     sv_idx -= Hd; dg_ptr -= 4 * Hd;
+    DTRACE(8);
   }
+  cluster_barrier();   // nobody exits while remote stores may still target its shared memory
 #undef DTRACE
+#undef TX_DG
+#undef TX_DC
+#undef TX_DDZ
+#undef TX_DWN
 }
 
 // A[row i][k] = W[k*ld + col(i)] for the rows a CTA owns in the backward kernel:
@@ -1327,11 +1501,11 @@ int dec_persist_supported(const las_dec_args* a) {
     g_dec_persist_checked = true;
     g_dec_persist_clusters = 0;
     if (cudaFuncSetAttribute(dec_persist_fwd_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
-        cudaFuncSetAttribute(dec_persist_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) == cudaSuccess) {
+        cudaFuncSetAttribute(dec_persist_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax) == cudaSuccess) {
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(kCS, 1, 1);
       cfg.blockDim = dim3(kThreads);
-      cfg.dynamicSmemBytes = 220 * 1024;
+      cfg.dynamicSmemBytes = kSmemMax;
       cudaLaunchAttribute at[1];
       at[0].id = cudaLaunchAttributeClusterDimension;
       at[0].val.clusterDim.x = kCS;
@@ -1372,7 +1546,7 @@ int dec_persist_bwd(const las_dec_args* a, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     LAS_CUDA(cudaFuncSetAttribute(dec_persist_bwd_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    LAS_CUDA(cudaFuncSetAttribute(dec_persist_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    LAS_CUDA(cudaFuncSetAttribute(dec_persist_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     attr_set = true;
   }
   DecBwdP p;
@@ -1428,7 +1602,7 @@ int dec_persist_fwd(const las_dec_args* a, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     LAS_CUDA(cudaFuncSetAttribute(dec_persist_fwd_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    LAS_CUDA(cudaFuncSetAttribute(dec_persist_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    LAS_CUDA(cudaFuncSetAttribute(dec_persist_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     attr_set = true;
   }
   DecFwdP p;

@@ -67,7 +67,7 @@ if os.environ.get("LAS_TRACE"):
     torch.cuda.synchronize()
     LIB.lib().las_set_debug_buffer(None)
     d = dbg.cpu()[64:128].view(4, 16)
-    names = ["A:mma+epi", "BAR_A", "B1-2:dw,de", "B3:energy", "B4:ddz,dwn", "BAR_B", "C:cell", "BAR_C"]
+    names = ["A:mma+epi", "wait dc", "B1-2:dw,de", "B3:energy", "B4:ddz,dwn", "wait ddz", "C:cell", "stores"]
     print(" ".join(f"{n:>11s}" for n in names))
     for s_ in range(4):
         row = d[s_]

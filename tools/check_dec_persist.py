@@ -70,8 +70,8 @@ if os.environ.get("LAS_TRACE"):
     torch.cuda.synchronize()
     LIB.lib().las_set_debug_buffer(None)
     d = dbg.cpu().view(8, 16)
-    names = ["mma", "sync", "epi", "BAR1", "dz+conv", "BAR2", "energy", "sync", "e-send", "BAR3", "softmax+ctx", "BAR4"]
+    names = ["wait z,c", "mma+sync", "epi+send", "conv", "wait z+dz", "dz-send", "wait dz+E", "sync", "e-send", "wait e", "smax+ctx"]
     print(" ".join(f"{n:>9s}" for n in names))
     for s_ in range(4):
         row = d[s_]
-        print(" ".join(f"{int(row[i + 1] - row[i]):9d}" for i in range(12)), "| step", int(d[s_ + 1, 0] - row[0]) if s_ < 3 else "")
+        print(" ".join(f"{int(row[i + 1] - row[i]):9d}" for i in range(11)), "| step", int(d[s_ + 1, 0] - row[0]) if s_ < 3 else "")
