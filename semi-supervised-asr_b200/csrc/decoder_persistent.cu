@@ -49,6 +49,7 @@ constexpr int kThreads = 512;
 constexpr int kWarps = 16;
 constexpr int kMaxFG = 14;     // gate fragments per warp
 constexpr int kMaxFD = 3;      // mlp_dec fragments per warp
+constexpr int kPFd = 4;        // decoder steps of global-memory prefetch distance (cp.async rings)
 
 struct DGeom {
   int NB, G;             // utterances per cluster, owner CTAs per utterance
@@ -60,10 +61,10 @@ struct DGeom {
   int TR, TT, WPT, NTW;  // frames per owner, 16-frame tiles, warps per tile, 8-wide att n-tiles per warp
   int AT8, OS, OTs;      // A/8; context dims per owner; 16-row tiles of an owner's context slice
   int KTe, KTc, NC;      // k-tiles over all Te frames; k-tiles over the conv taps; 8-channel n-tiles of the conv
-  int cw0, WPTc;         // location conv: first warp, warps per frame tile (the warps behind the cell-epilogue warps)
+  int cw0, WPTc;         // location conv: 1 = only non-lead warps take part, warps per frame tile
   int Pld, QTld, Tw;     // row strides of the P slice (f32) and of the transposed Q slice (bf16); padded alignment length
   // shared-memory carve-up (byte offsets)
-  int o_zB, o_red, o_red2, o_dzv, o_cred, o_wbuf, o_cwB, o_matt, o_gv, o_P, o_Q, o_epart, o_eall, o_pun, o_wred;
+  int o_zB, o_red, o_red2, o_decA, o_exr, o_pb, o_dzv, o_cred, o_wbuf, o_cwB, o_matt, o_gv, o_P, o_Q, o_epart, o_eall, o_pun, o_wred;
   int smem;
 };
 
@@ -92,12 +93,10 @@ bool dec_geom(const las_dec_args* a, int NB, DGeom& g) {
   g.TT = (g.TR + 15) / 16;
   if (g.TT > kWarps) return false;
   g.WPT = kWarps / g.TT;
-  {
-    // the conv of w_{t-1} runs next to the cell epilogue of step t, on the warps the epilogue leaves idle
-    const int epi_warps = (g.UPC * NB + 31) / 32;
-    g.cw0 = epi_warps < kWarps - g.TT ? epi_warps : kWarps - g.TT;
-    g.WPTc = (kWarps - g.cw0) / g.TT;
-  }
+  // the conv of w_{t-1} runs next to the cell epilogue of step t, on the warps that do not lead a gate tile
+  // (cw0 = 1); when there are fewer of those than frame tiles, every warp takes part after its own P1 work (cw0 = 0)
+  g.cw0 = (kWarps - g.GT >= g.TT) ? 1 : 0;
+  g.WPTc = (g.cw0 ? kWarps - g.GT : kWarps) / g.TT;
   g.AT8 = A / 8;
   g.NTW = (g.AT8 + g.WPT - 1) / g.WPT;
   g.KTe = (Te + 15) / 16;
@@ -112,6 +111,9 @@ bool dec_geom(const las_dec_args* a, int NB, DGeom& g) {
   g.o_zB = take(2 * g.KTp * 256);
   g.o_red = take(kWarps * 128 * 4);
   g.o_red2 = take(kWarps * 128 * 4);
+  g.o_decA = take(kWarps * kMaxFD * 32 * 16);    // mlp_dec A fragments of this CTA: [warp][FD][32] uint4
+  g.o_exr = take(kPFd * 4 * g.GT * 32 * 4);      // embx ring: [kPFd][4 gates][GT lead warps x 32 lanes] f32
+  g.o_pb = take(g.nAT * 32 * 16);                // frame means of P in the dz consumers' fragment order
   g.o_dzv = take(A * 4);
   g.o_cred = take(kWarps * 32 * 32);
   g.o_wbuf = take(g.Tw * 4);
@@ -160,6 +162,14 @@ __device__ __forceinline__ void cluster_barrier() {
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// Named barriers (ids 1..15; 0 is __syncthreads): producers arrive without waiting, the consumer syncs.
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // Position (in 32-bit words) of the B-fragment word that holds K elements (k, k+1), k even, of
 // column n in a [KT][32][2] fragment buffer.
 __device__ __forceinline__ int bfrag_word(int k, int n) {
@@ -193,6 +203,21 @@ __device__ __forceinline__ void split_bf16x2(float x, float y, uint32_t& hi, uin
   const float2 h = unpack_bf16x2(hi);
   lo = pack_bf16x2(x - h.x, y - h.y);
 }
+
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_n() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 struct DecFwdP {
   int B, L, Te, Hd, O, A, C, K;
@@ -248,10 +273,12 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
   __nv_bfloat16* QT_s = reinterpret_cast<__nv_bfloat16*>(smem + g.o_Q);   // [OTs*16][QTld]  my context dims of Q, transposed
   float* epart = reinterpret_cast<float*>(smem + g.o_epart);       // [WPT][TT*16]
   float* e_all = reinterpret_cast<float*>(smem + g.o_eall);        // [G*TR] scaled energies of all frames (written by the owners)
-  float* p_un = reinterpret_cast<float*>(smem + g.o_pun);          // [KTe*16] exp(e - max), zero padded
+  uint2* pB = reinterpret_cast<uint2*>(smem + g.o_pun);            // [KTe*8] softmax numerators of frames (2i, 2i+1): bf16x2 hi, lo
   float* wred = reinterpret_cast<float*>(smem + g.o_wred);         // [2][16]
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tig = lane & 3;
+  const int tid = threadIdx.x, lane = tid & 31, gq = lane >> 2, tig = lane & 3;
+  // provably warp-uniform warp index: everything derived from it (tile / split / role indices) can live in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const uint32_t rank = cluster_rank();
   const int cl = blockIdx.y;
   const int NB = g.NB, G = g.G, UPC = g.UPC, TR = g.TR, OS = g.OS;
@@ -280,20 +307,22 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
   const int d_tile = warp / g.KSd, d_ks = warp % g.KSd;
   const bool d_act = d_tile < nATr;
   const int d_kt0 = d_ks * g.FD;
-  uint4 Ad[kMaxFD];
+  // the mlp_dec fragments (3 per warp) live in shared memory: the kernel is at its register limit (128 x 512 threads)
+  uint4* decA = reinterpret_cast<uint4*>(smem + g.o_decA) + warp * kMaxFD * 32 + lane;
 #pragma unroll
   for (int j = 0; j < kMaxFD; ++j) {
-    Ad[j] = make_uint4(0u, 0u, 0u, 0u);
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
     if (d_act && j < g.FD && d_kt0 + j < g.KTd)
-      Ad[j] = __ldg(reinterpret_cast<const uint4*>(p.dec_pk) +
-                    (static_cast<int64_t>(rank + kCS * d_tile) * g.KTd + d_kt0 + j) * 32 + lane);
+      v = __ldg(reinterpret_cast<const uint4*>(p.dec_pk) +
+                (static_cast<int64_t>(rank + kCS * d_tile) * g.KTd + d_kt0 + j) * 32 + lane);
+    decA[j * 32] = v;
   }
   const int nfg = g.FG, nfd = g.FD;
 
   // ---------------- resident attention operands (shared memory)
   for (int i = tid; i < 2 * g.KTp * 64; i += kThreads) zB[i] = 0u;
   for (int i = tid; i < g.Tw; i += kThreads) wbuf[i] = 0.f;
-  for (int i = tid; i < g.KTe * 16; i += kThreads) p_un[i] = 0.f;
+  for (int i = tid; i < g.KTe * 8; i += kThreads) pB[i] = make_uint2(0u, 0u);
   for (int i = tid; i < kWarps * 64; i += kThreads) cred[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int i = tid; i < g.KTc * 64; i += kThreads) {
     // B fragment of the conv weights: k = tap, n = channel 8*nc + (l >> 2)
@@ -338,34 +367,71 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
   }
 
   // ---------------- roles of this thread
-  // P1 epilogue: thread -> (utterance n, local unit ulc)
-  const int n_e = tid / UPC, ulc = tid % UPC;
-  const bool epi = tid < UPC * NB;
+  // P1: the K-split warps of a gate tile hand their partial accumulators to the tile's lead warp (g_ks == 0) through
+  // shared memory (one conflict-free float4 per lane, a named barrier per tile: no block-wide barrier in P1). After
+  // one xor-16 exchange each lane of the lead warp holds all four gates of ONE (unit, utterance): unit = quad's
+  // unit gq & 3, utterance = 2 tig + (gq >> 2) (the C fragment keeps gates {gl, gl + 2} of two utterances per lane).
+  const bool g_lead = g_act && g_ks == 0;
+  const int gl = gq >> 2, ul = gq & 3;
+  const int n_e = 2 * tig + gl;
+  const bool epi = g_lead && n_e < NB;
   const int b_e = cl * NB + n_e;
   const bool epi_ok = epi && b_e < p.B;
-  const int u_e = rank * UPC + ulc;                       // global hidden unit
-  const int epi_warps = (UPC * NB + 31) / 32;
-  const int e_w0 = (epi ? (ulc >> 2) : 0) * g.KSg;        // first contributing warp of my gate tile
-  const int z_word = qfrag_word(u_e & ~3, epi ? n_e : 0);   // first word of my unit's quad
+  const int u_e = rank * UPC + 4 * (g_act ? g_tile : 0) + ul;     // global hidden unit
+  const int z_word = qfrag_word(u_e & ~3, epi ? n_e : 0);          // first word of my unit's quad
+  float4* redP = reinterpret_cast<float4*>(red);                   // [GT][KSg - 1][32] partial accumulators
   float cell = 0.f;
+  float inv_w = 1.f;                             // 1 / (sum of the softmax numerators held in wbuf); the initial alignment is normalised
+  // Input-projection terms embx[b][t][gate*Hd + u]: prefetched kPFd steps ahead with cp.async into a thread-private
+  // ring slot (plain loads at the top of the step are sunk by ptxas to their first use, in the cell epilogue).
   const float* ex_ptr = p.embx + static_cast<int64_t>(epi_ok ? b_e : 0) * R * 4 * Hd + u_e;
+  const int exs = g.GT * 32;                     // ring stride between gates
+  float* exr = reinterpret_cast<float*>(smem + g.o_exr) + (g_act ? g_tile : 0) * 32 + lane;
+  int pf_t = 0;
+  auto prefetch_ex = [&]() {
+    if (epi_ok && pf_t < L) {
+      float* dst = exr + (pf_t % kPFd) * 4 * exs;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) cp_async4(dst + k * exs, ex_ptr + k * Hd);
+    }
+    ex_ptr += 4 * Hd;
+    ++pf_t;
+    cp_async_commit();
+  };
+#pragma unroll 1
+  for (int i = 0; i < kPFd; ++i) prefetch_ex();
   int64_t sv_idx = static_cast<int64_t>(epi_ok ? b_e : 0) * L * Hd + u_e;
   __nv_bfloat16* zc_z_ptr = p.zc + (static_cast<int64_t>(epi_ok ? b_e : 0) * R + 1) * ZC + u_e;
-  // P2 epilogue: thread -> (utterance n, local mlp_dec row)
-  const int drows = 16 * nATr;
-  const int n_d = drows > 0 ? tid / drows : 0, al = drows > 0 ? tid % drows : 0;
-  const bool depi = drows > 0 && tid < drows * NB;
-  const int a_d = (rank + kCS * (al >> 4)) * 16 + (al & 15);
-  const bool depi_ok = depi && a_d < A && (cl * NB + n_d) < p.B;
-  const int d_w0 = (al >> 4) * g.KSd;
+  // P2: warp w < nATr sums the K-split partials of mlp_dec tile w in fragment order, a 4x4 transpose among the lanes
+  // that share (gq >> 2, tig) gives lane j = gq & 3 four CONSECUTIVE attention dims of one utterance:
+  //   dims a_d .. a_d + 3 with a_d = 16 * tile + 4 * (gq >> 2) + 8 * (j >> 1), utterance n_d = 2 tig + (j & 1)
+  // (one 16-byte st.async per owner instead of four 4-byte ones; one 16-byte store to dzf)
+  const bool d_lead = warp < nATr;
+  const int n_d = 2 * tig + (ul & 1);
+  const int a_d = (static_cast<int>(rank) + kCS * warp) * 16 + 4 * gl + 8 * (ul >> 1);
+  const bool depi_ok = d_lead && n_d < NB && a_d < A && (cl * NB + n_d) < p.B;
   float* dzf_ptr = p.dzf + static_cast<int64_t>(depi_ok ? cl * NB + n_d : 0) * L * A + (depi_ok ? a_d : 0);
-  const float pbar_d = depi_ok ? p.pbar[static_cast<int64_t>(cl * NB + n_d) * A + a_d] : 0.f;
+  {
+    // frame means of P for the accumulator elements of this lane: rows gq, gq + 8 of the tile, utterances 2tig, 2tig+1
+    float4* pb = reinterpret_cast<float4*>(smem + g.o_pb);
+    if (d_lead) {
+      const int a0 = (static_cast<int>(rank) + kCS * warp) * 16 + gq, a1 = a0 + 8;
+      const int b0 = cl * NB + 2 * tig, b1 = b0 + 1;
+      const bool v0 = 2 * tig < NB && b0 < p.B, v1 = 2 * tig + 1 < NB && b1 < p.B;
+      pb[warp * 32 + lane] = make_float4((v0 && a0 < A) ? p.pbar[static_cast<int64_t>(b0) * A + a0] : 0.f,
+                                         (v1 && a0 < A) ? p.pbar[static_cast<int64_t>(b1) * A + a0] : 0.f,
+                                         (v0 && a1 < A) ? p.pbar[static_cast<int64_t>(b0) * A + a1] : 0.f,
+                                         (v1 && a1 < A) ? p.pbar[static_cast<int64_t>(b1) * A + a1] : 0.f);
+    }
+  }
   // P3: (frame tile, attention-dim slice) of this warp
   const int e_tt = warp / g.WPT, e_wi = warp % g.WPT;
   const bool e_act = warp < g.TT * g.WPT && ntl > 0;
   const int cm = te0 + 16 * e_tt;
-  // location conv (runs next to the cell epilogue): (frame tile, K split) of this warp
-  const int cv = warp - g.cw0;
+  // location conv (runs next to the cell epilogue): (frame tile, K split) of this warp. Lead warps sit at
+  // 0, KSg, 2 KSg, ..: the conv slots are the remaining warps in order.
+  const int n_lead_before = min(g.GT, (warp + g.KSg - 1) / g.KSg);
+  const int cv = g.cw0 ? (g_lead ? -1 : warp - n_lead_before) : warp;
   const bool c_act = cv >= 0 && cv < g.TT * g.WPTc && ntl > 0;
   const int c_tt = c_act ? cv / g.WPTc : 0, c_wi = c_act ? cv % g.WPTc : 0;
   // conv k-tiles of that frame tile: taps that can touch a valid alignment entry
@@ -377,6 +443,11 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
   float* ws_row = p.ws + (static_cast<int64_t>(own_ok ? b_own : 0) * R + 1) * Te;
   const int c_mt = warp;                                   // context m-tile of this warp (if < OTs)
   const int o_l0 = 16 * c_mt + gq;                         // local context dims o_l0, o_l0 + 8 (lanes with tig == 0)
+  float cb_a = 0.f, cb_b = 0.f;                            // their bias terms (constant over the steps)
+  if (own_ok && c_mt < g.OTs && tig == 0) {
+    if (o_l0 < OS) cb_a = p.cbias[static_cast<int64_t>(b_own) * O + q * OS + o_l0];
+    if (o_l0 + 8 < OS) cb_b = p.cbias[static_cast<int64_t>(b_own) * O + q * OS + o_l0 + 8];
+  }
   // cluster-mapped base addresses
   const uint32_t zB_base = smem_u32(zB), dzv_base = smem_u32(dzv), eall_base = smem_u32(e_all);
   const uint32_t bars_base = smem_u32(bars);      // bz[i] at +8i, bc[i] at +16+8i, bdz at +32, be at +40
@@ -399,8 +470,9 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
   }
 
   cluster_barrier();   // every CTA's shared memory and barriers are initialised before any remote store
-  const bool trace = p.dbg != nullptr && blockIdx.y == 0 && rank == 0 && tid == 0;
-#define DTRACE(slot) do { if (trace && t >= 8 && t < 12) p.dbg[(t - 8) * 16 + (slot)] = clock64(); } while (0)
+  // clock64() phase trace: lane 0 of every warp of CTA (rank 0, cluster 0), steps 8..11 -> dbg[warp][step][slot]
+  const bool trace = p.dbg != nullptr && blockIdx.y == 0 && rank == 0 && lane == 0;
+#define DTRACE(slot) do { if (trace && t >= 8 && t < 12) p.dbg[(warp * 4 + (t - 8)) * 16 + (slot)] = clock64(); } while (0)
 
   for (int t = 0; t < L; ++t) {
     const int par = t & 1, nxt = par ^ 1;
@@ -409,12 +481,6 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
 
     // ================= P1: LSTM cell =================
     DTRACE(0);
-    float ex[4] = {0.f, 0.f, 0.f, 0.f};
-    if (epi_ok) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) ex[k] = __ldg(ex_ptr + k * Hd);
-    }
-    ex_ptr += 4 * Hd;
     if (t > 0) {      // [z_{t-1}; c_{t-1}] complete in zB[par]
       const uint32_t php = ((t - 1) >> 1) & 1;
       mbar_wait_tag(&bz[par], php, 0);
@@ -438,48 +504,65 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
           else mma_bf16_16816(acc0, Af, b.x, b.y);
         }
       }
-      reinterpret_cast<float4*>(red)[warp * 32 + lane] =
-          make_float4(acc0[0] + acc1[0], acc0[1] + acc1[1], acc0[2] + acc1[2], acc0[3] + acc1[3]);
-    }
-    __syncthreads();
-    DTRACE(2);
-    if (warp < epi_warps) {
-      uint32_t zbits = 0u;
-      uint2 sv_pk = make_uint2(0u, 0u);
-      __nv_bfloat16 sv_z = __float2bfloat16(0.f);
-      if (epi) {
-        const int ul4 = ulc & 3;
-        const float gi = red_gather(red, e_w0, g.KSg, ul4, n_e) + ex[0];
-        const float gf = red_gather(red, e_w0, g.KSg, 4 + ul4, n_e) + ex[1];
-        const float gg = red_gather(red, e_w0, g.KSg, 8 + ul4, n_e) + ex[2];
-        const float go = red_gather(red, e_w0, g.KSg, 12 + ul4, n_e) + ex[3];
-        const float i = sigmoid_acc(gi), f = sigmoid_acc(gf), gc = tanh_acc(gg), o = sigmoid_acc(go);
-        cell = f * cell + i * gc;
-        const __nv_bfloat16 zb16 = __float2bfloat16(o * tanh_acc(cell));
-        zbits = epi_ok ? static_cast<uint32_t>(__bfloat16_as_ushort(zb16)) : 0u;
-        __half2 lo = __floats2half2_rn(i, f), hi = __floats2half2_rn(gc, o);
-        sv_pk.x = *reinterpret_cast<uint32_t*>(&lo);
-        sv_pk.y = *reinterpret_cast<uint32_t*>(&hi);
-        sv_z = zb16;
-      }
-      // the 4 lanes of a quad (UPC % 4 == 0, so they are lanes 4j..4j+3) gather its two words; each then pushes
-      // the 8 bytes to a quarter of the cluster
-      const uint32_t nb = __shfl_xor_sync(0xffffffffu, zbits, 1);
-      const uint32_t wp = (ulc & 1) ? (nb | (zbits << 16)) : (zbits | (nb << 16));
-      const uint32_t wo = __shfl_xor_sync(0xffffffffu, wp, 2);
-      if (epi) {
-        const uint32_t w0 = (ulc & 2) ? wo : wp, w1 = (ulc & 2) ? wp : wo;
-        const uint32_t off = zB_base + 4u * static_cast<uint32_t>(zb_nxt_w + z_word);
-#pragma unroll
-        for (int i = 0; i < kCS / 4; ++i) {
-          const uint32_t dst = (ulc & 3) * (kCS / 4) + i;
-          st_async_v2(mapa_u32(off, dst), w0, w1, mapa_u32(bars_base + 8u * nxt, dst));
+      float cf[4] = {acc0[0] + acc1[0], acc0[1] + acc1[1], acc0[2] + acc1[2], acc0[3] + acc1[3]};
+      const int nks = g.KSg;
+      if (!g_lead) {
+        redP[(g_tile * (nks - 1) + g_ks - 1) * 32 + lane] = make_float4(cf[0], cf[1], cf[2], cf[3]);
+        named_bar_arrive(1 + g_tile, 32 * nks);       // producer: does not wait
+        DTRACE(2);
+      } else {
+        if (nks > 1) {
+          named_bar_sync(1 + g_tile, 32 * nks);
+          for (int ks = 0; ks < nks - 1; ++ks) {
+            const float4 v = redP[(g_tile * (nks - 1) + ks) * 32 + lane];
+            cf[0] += v.x; cf[1] += v.y; cf[2] += v.z; cf[3] += v.w;
+          }
         }
-      }
-      if (epi_ok) {     // saved activations: off the critical path, after the sends
-        reinterpret_cast<uint2*>(p.gates_save)[sv_idx] = sv_pk;
-        p.c_save[sv_idx] = cell;
-        zc_z_ptr[0] = sv_z;
+        DTRACE(2);
+        // C fragment: cf[0], cf[1] = row gq (gate gl of unit ul), cf[2], cf[3] = row gq + 8 (gate gl + 2), utterances
+        // 2 tig, 2 tig + 1. Lanes gq and gq ^ 4 trade halves: each ends up with all four gates of (ul, 2 tig + gl).
+        const float r0 = __shfl_xor_sync(0xffffffffu, gl ? cf[0] : cf[1], 16);
+        const float r1 = __shfl_xor_sync(0xffffffffu, gl ? cf[2] : cf[3], 16);
+        cp_async_wait_n<kPFd - 1>();      // this step's embx terms have landed in my ring slot
+        uint32_t zbits = 0u;
+        uint2 sv_pk = make_uint2(0u, 0u);
+        __nv_bfloat16 sv_z = __float2bfloat16(0.f);
+        if (epi_ok) {
+          const float* er = exr + (t % kPFd) * 4 * exs;
+          const float gi = (gl ? r0 : cf[0]) + er[0];
+          const float gf = (gl ? cf[1] : r0) + er[exs];
+          const float gg = (gl ? r1 : cf[2]) + er[2 * exs];
+          const float go = (gl ? cf[3] : r1) + er[3 * exs];
+          const float i = sigmoid_acc(gi), f = sigmoid_acc(gf), gc = tanh_acc(gg), o = sigmoid_acc(go);
+          cell = f * cell + i * gc;
+          sv_z = __float2bfloat16(o * tanh_acc(cell));
+          zbits = static_cast<uint32_t>(__bfloat16_as_ushort(sv_z));
+          __half2 lo = __floats2half2_rn(i, f), hi = __floats2half2_rn(gc, o);
+          sv_pk.x = *reinterpret_cast<uint32_t*>(&lo);
+          sv_pk.y = *reinterpret_cast<uint32_t*>(&hi);
+        }
+        DTRACE(12);
+        // the 4 lanes ul = 0..3 of (gl, tig) gather the quad's two words; each then pushes the 8 bytes to a quarter
+        // of the cluster
+        const uint32_t nb = __shfl_xor_sync(0xffffffffu, zbits, 4);
+        const uint32_t wp = (ul & 1) ? (nb | (zbits << 16)) : (zbits | (nb << 16));
+        const uint32_t wo = __shfl_xor_sync(0xffffffffu, wp, 8);
+        if (epi) {
+          const uint32_t w0 = (ul & 2) ? wo : wp, w1 = (ul & 2) ? wp : wo;
+          const uint32_t off = zB_base + 4u * static_cast<uint32_t>(zb_nxt_w + z_word);
+#pragma unroll
+          for (int i = 0; i < kCS / 4; ++i) {
+            const uint32_t dst = ul * (kCS / 4) + i;
+            st_async_v2(mapa_u32(off, dst), w0, w1, mapa_u32(bars_base + 8u * nxt, dst));
+          }
+        }
+        DTRACE(13);
+        if (epi_ok) {     // saved activations: off the critical path, after the sends
+          reinterpret_cast<uint2*>(p.gates_save)[sv_idx] = sv_pk;
+          p.c_save[sv_idx] = cell;
+          zc_z_ptr[0] = sv_z;
+        }
+        prefetch_ex();    // refill my ring slot (step t + kPFd)
       }
     }
     sv_idx += Hd; zc_z_ptr += ZC;
@@ -522,7 +605,8 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
       for (int j = 0; j < kMaxFD; ++j) {
         if (j < nfd) {
           const uint2 b = hb[j * 32];
-          const uint32_t Af[4] = {Ad[j].x, Ad[j].y, Ad[j].z, Ad[j].w};
+          const uint4 a4 = decA[j * 32];
+          const uint32_t Af[4] = {a4.x, a4.y, a4.z, a4.w};
           mma_bf16_16816(acc, Af, b.x, b.y);
         }
       }
@@ -530,14 +614,35 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
     }
     __syncthreads();
     DTRACE(5);
-    if (depi_ok) {
-      const float dz_v = red_gather(red2, d_w0, g.KSd, al & 15, n_d) + pbar_d;
-      const uint32_t off = dzv_base + 4u * a_d;
-      for (int qq = 0; qq < G; ++qq) {
-        const uint32_t dst = n_d * G + qq;
-        st_async_b32(mapa_u32(off, dst), __float_as_uint(dz_v), mapa_u32(bars_base + 32u, dst));
+    if (d_lead) {
+      // sum of the K-split partials of tile `warp` in fragment order (conflict-free 16-byte loads), plus the frame mean
+      float4 m = reinterpret_cast<const float4*>(smem + g.o_pb)[warp * 32 + lane];
+      for (int ks = 0; ks < g.KSd; ++ks) {
+        const float4 v = reinterpret_cast<const float4*>(red2)[(warp * g.KSd + ks) * 32 + lane];
+        m.x += v.x; m.y += v.y; m.z += v.z; m.w += v.w;
       }
-      dzf_ptr[0] = dz_v;
+      // 4x4 transpose among the lanes ul = 0..3 of (gl, tig): element k of lane ul = M[ul][k] with k = (row half, utterance
+      // parity) = (a0,n0), (a0,n1), (a1,n0), (a1,n1); lane j receives M[0..3][j]: four consecutive dims of one utterance
+      {
+        const bool odd = (ul & 1) != 0;
+        const float s0 = __shfl_xor_sync(0xffffffffu, odd ? m.x : m.y, 4);
+        const float s1 = __shfl_xor_sync(0xffffffffu, odd ? m.z : m.w, 4);
+        // even lane: (M[ul][0], M[ul+1][0], M[ul][2], M[ul+1][2]); odd lane: (M[ul-1][1], M[ul][1], M[ul-1][3], M[ul][3])
+        const float y0 = odd ? s0 : m.x, y1 = odd ? m.y : s0, y2 = odd ? s1 : m.z, y3 = odd ? m.w : s1;
+        const bool hi = (ul & 2) != 0;
+        const float t0 = __shfl_xor_sync(0xffffffffu, hi ? y0 : y2, 8);
+        const float t1 = __shfl_xor_sync(0xffffffffu, hi ? y1 : y3, 8);
+        m = hi ? make_float4(t0, t1, y2, y3) : make_float4(y0, y1, t0, t1);
+      }
+      if (depi_ok) {
+        const uint4 mv = make_uint4(__float_as_uint(m.x), __float_as_uint(m.y), __float_as_uint(m.z), __float_as_uint(m.w));
+        const uint32_t off = dzv_base + 4u * a_d;
+        for (int qq = 0; qq < G; ++qq) {
+          const uint32_t dst = n_d * G + qq;
+          st_async_v4(mapa_u32(off, dst), mv, mapa_u32(bars_base + 32u, dst));
+        }
+        *reinterpret_cast<float4*>(dzf_ptr) = m;
+      }
     }
     dzf_ptr += A;
     DTRACE(6);
@@ -556,6 +661,9 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
         s0.x += a.x; s0.y += a.y; s0.z += a.z; s0.w += a.w;
         s1.x += b.x; s1.y += b.y; s1.z += b.z; s1.w += b.w;
       }
+      // the conv ran on the UNNORMALISED softmax numerators of step t-1 (wbuf, see P4): scale by 1 / their sum
+      s0.x *= inv_w; s0.y *= inv_w; s0.z *= inv_w; s0.w *= inv_w;
+      s1.x *= inv_w; s1.y *= inv_w; s1.z *= inv_w; s1.w *= inv_w;
       if (e_wi == 0 && csave_ptr) {
         if (r0 < ntl) {
           *reinterpret_cast<float2*>(csave_ptr + gq * 16 + 2 * tig) = make_float2(s0.x, s0.y);
@@ -624,52 +732,60 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
     }
     DTRACE(10);
     {
+      // Every warp finds the maximum over all Te energies on its own (a few shared-memory loads and shuffles, bit-identical
+      // in all warps); the frame-owner warps then produce the numerators and their per-warp sums: ONE block barrier.
       const bool fr = own_ok && tid < Te;
-      const float e = fr ? e_all[tid] : -INFINITY;
-      float mx = warp_max(e);
-      if (lane == 0) wred[warp] = mx;
-      __syncthreads();
-      float M = wred[0];
-#pragma unroll
-      for (int w = 1; w < kWarps; ++w) M = fmaxf(M, wred[w]);
-      const float pv = fr ? __expf(e - M) : 0.f;
-      if (fr) p_un[tid] = pv;
-      const float sm_ = warp_sum(pv);
-      if (lane == 0) wred[kWarps + warp] = sm_;
-      __syncthreads();
-      float S = 0.f;
-#pragma unroll
-      for (int w = 0; w < kWarps; ++w) S += wred[kWarps + w];
-      const float invS = own_ok ? 1.f / S : 0.f;
-      float w_keep = 0.f;
-      if (fr) {
-        w_keep = pv * invS;
-        wbuf[K + tid] = w_keep;
+      float mx = -INFINITY;
+      if (own_ok) {
+        for (int i = lane; i < Te; i += 32) mx = fmaxf(mx, e_all[i]);
+        mx = warp_max(mx);
       }
-      // context slice on tensor cores: c[o] = sum_te QT[o][te] p[te]  (M = my context dims, K = frames, N = column 0)
+      const float pv = fr ? __expf(e_all[tid] - mx) : 0.f;
+      const int nFW = (Te + 31) >> 5;
+      if (warp < nFW) {
+        const float sw = warp_sum(pv);
+        if (lane == 0) wred[warp] = sw;
+        // The next step's location conv reads the f32 numerators (P3 scales its result by 1/S): complete after the
+        // barrier below, so that P1 of the next step needs no block-wide barrier of its own. The context MMA reads
+        // them as ready-made B-fragment words (bf16 hi/lo pairs of frames (2i, 2i+1)).
+        const float pn = __shfl_down_sync(0xffffffffu, pv, 1);
+        if (fr) wbuf[K + tid] = pv;
+        if ((tid & 1) == 0 && tid < g.KTe * 16) {
+          uint2 hl;
+          split_bf16x2(pv, pn, hl.x, hl.y);
+          pB[tid >> 1] = hl;
+        }
+      }
+      __syncthreads();     // numerators complete; every reader of e_all is done before any c_t leaves this CTA
+      DTRACE(14);
+      float S = 0.f;
+      for (int w = 0; w < nFW; ++w) S += wred[w];
+      const float invS = own_ok ? 1.f / S : 0.f;
+      const float w_keep = pv * invS;
+      inv_w = invS;
+      // context slice on tensor cores: c[o] = sum_te QT[o][te] p[te]  (M = my context dims, K = frames; every column of B
+      // holds p, column 0 is read back)
       if (own_ok && c_mt < g.OTs) {
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        float acc[4] = {0.f, 0.f, 0.f, 0.f}, accl[4] = {0.f, 0.f, 0.f, 0.f};
         const uint32_t* q0 = reinterpret_cast<const uint32_t*>(QT_s + o_l0 * g.QTld) + tig;
         const uint32_t* q1 = reinterpret_cast<const uint32_t*>(QT_s + (o_l0 + 8) * g.QTld) + tig;
+        const uint2* pbt = pB + tig;
+#pragma unroll 2
         for (int kt = 0; kt < g.KTe; ++kt) {
           const uint32_t Af[4] = {q0[kt * 8], q1[kt * 8], q0[kt * 8 + 4], q1[kt * 8 + 4]};
-          uint32_t bh0 = 0u, bh1 = 0u, bl0 = 0u, bl1 = 0u;
-          if (gq == 0) {
-            const float2 v0 = *reinterpret_cast<const float2*>(p_un + 16 * kt + 2 * tig);
-            const float2 v1 = *reinterpret_cast<const float2*>(p_un + 16 * kt + 2 * tig + 8);
-            split_bf16x2(v0.x, v0.y, bh0, bl0);
-            split_bf16x2(v1.x, v1.y, bh1, bl1);
-          }
-          mma_bf16_16816(acc, Af, bh0, bh1);
-          mma_bf16_16816(acc, Af, bl0, bl1);
+          const uint2 v0 = pbt[kt * 8], v1 = pbt[kt * 8 + 4];
+          mma_bf16_16816(acc, Af, v0.x, v1.x);
+          mma_bf16_16816(accl, Af, v0.y, v1.y);
         }
+        acc[0] += accl[0]; acc[2] += accl[2];
+        DTRACE(15);
         // lanes with tig == 0 hold column 0: rows o_l0 (acc[0]) and o_l0 + 8 (acc[2])
         const int oa = q * OS + o_l0, ob = oa + 8;
         const bool va = tig == 0 && o_l0 < OS, vb = tig == 0 && o_l0 + 8 < OS;
         const float ca = acc[0] * invS, cb = acc[2] * invS;
         __nv_bfloat16 ha = __float2bfloat16(0.f), hb = ha;
-        if (va) ha = __float2bfloat16(ca + p.cbias[static_cast<int64_t>(b_own) * O + oa]);
-        if (vb) hb = __float2bfloat16(cb + p.cbias[static_cast<int64_t>(b_own) * O + ob]);
+        if (va) ha = __float2bfloat16(ca + cb_a);
+        if (vb) hb = __float2bfloat16(cb + cb_b);
         const __nv_bfloat16 ha_keep = ha, hb_keep = hb;     // the output layer (zc in global memory) sees c_t
         if (drop_on) {
           // what the NEXT step's gates see is dropout(c_t)
@@ -812,10 +928,11 @@ bool dec_bgeom(const las_dec_args* a, int NB, BGeom& g) {
   g.o_dwnrx = take(2 * g.G * Te * 4);
   g.o_ddzrx = take(g.G * NB * A * 4);
   g.o_ddzB = take(g.KTap * 256);
-  g.o_wt = take(Te * 4);
-  g.o_cpre = take(O * 4);
-  g.o_dzv = take(A * 4);
-  g.o_conv = take(g.TT * 16 * 16 * 4);
+  // rows of the saved activations, prefetched one step ahead: two buffers each
+  g.o_wt = take(2 * rup(Te * 4, 16));
+  g.o_cpre = take(2 * O * 4);
+  g.o_dzv = take(2 * A * 4);
+  g.o_conv = take(2 * g.TT * 16 * 16 * 4);
   g.o_de = take(g.TT * 16 * 4);
   g.o_dwpart = take(g.WPT * g.TT * 16 * 4);
   g.o_dwns = take(Te * 4);
@@ -855,14 +972,6 @@ struct DecBwdP {
   long long* dbg;
 };
 
-__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
 __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_constant__ DecBwdP p_in) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ DecBwdP p;
@@ -889,10 +998,10 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
   float* dwn_rx = reinterpret_cast<float*>(smem + g.o_dwnrx);      // [2][G][Te]
   float* ddz_rx = reinterpret_cast<float*>(smem + g.o_ddzrx);      // [G][NB][A] f32 partials (owner partials cancel: bf16 is not enough)
   uint32_t* ddzB = reinterpret_cast<uint32_t*>(smem + g.o_ddzB);   // [KTap][32][2]
-  float* wt_s = reinterpret_cast<float*>(smem + g.o_wt);           // [Te] w_t
-  float* cpre_s = reinterpret_cast<float*>(smem + g.o_cpre);       // [O]
-  float* dzv = reinterpret_cast<float*>(smem + g.o_dzv);           // [A]
-  float* conv_s = reinterpret_cast<float*>(smem + g.o_conv);       // [TT*16][16]
+  float* wt_s2 = reinterpret_cast<float*>(smem + g.o_wt);          // [2][Te (padded to 16 B)] w_t
+  float* cpre_s2 = reinterpret_cast<float*>(smem + g.o_cpre);      // [2][O]
+  float* dzv2 = reinterpret_cast<float*>(smem + g.o_dzv);          // [2][A]
+  float* conv_s2 = reinterpret_cast<float*>(smem + g.o_conv);      // [2][TT*16][16] conv features of the step; reused for its dconv
   float* de_s = reinterpret_cast<float*>(smem + g.o_de);           // [TT*16]
   float* dwpart = reinterpret_cast<float*>(smem + g.o_dwpart);     // [WPT][TT*16]
   float* dwn_s = reinterpret_cast<float*>(smem + g.o_dwns);        // [Te]
@@ -903,7 +1012,9 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
   float4* dcred = reinterpret_cast<float4*>(smem + g.o_scratch + g.TT * p.A * 4);   // [12][2][32]
   float* Gs = reinterpret_cast<float*>(smem + g.o_scratch);        // [GR][Gld] skewed G tile (after ddz_part / dcred are consumed)
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tig = lane & 3;
+  const int tid = threadIdx.x, lane = tid & 31, gq = lane >> 2, tig = lane & 3;
+  // provably warp-uniform warp index: everything derived from it (tile / split / role indices) can live in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const uint32_t rank = cluster_rank();
   const int cl = blockIdx.y;
   const int NB = g.NB, G = g.G, UPC = g.UPC, OPC = g.OPC, RPC = g.RPC, TR = g.TR;
@@ -946,7 +1057,7 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
   for (int i = tid; i < g.KTap * 64; i += kBT) ddzB[i] = 0u;
   for (int i = tid; i < 2 * G * Te; i += kBT) dwn_rx[i] = 0.f;
   for (int i = tid; i < G * NB * A; i += kBT) ddz_rx[i] = 0.f;
-  for (int i = tid; i < g.TT * 16 * 16; i += kBT) conv_s[i] = 0.f;
+  for (int i = tid; i < 2 * g.TT * 16 * 16; i += kBT) conv_s2[i] = 0.f;
   for (int i = tid; i < g.TT * 16; i += kBT) de_s[i] = 0.f;
   for (int i = tid; i < A; i += kBT) gv_s[i] = p.gvec[i];
   for (int i = tid; i < g.AT8 * 32; i += kBT) {
@@ -1040,34 +1151,55 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
 
   __syncthreads();
   cluster_barrier();
-  const bool trace = p.dbg != nullptr && blockIdx.y == 0 && rank == 0 && tid == 0;
-#define DTRACE(slot) do { if (trace && t <= L - 9 && t > L - 13) p.dbg[64 + (L - 9 - t) * 16 + (slot)] = clock64(); } while (0)
+  const bool trace = p.dbg != nullptr && blockIdx.y == 0 && rank == 0 && lane == 0;
+#define DTRACE(slot) do { if (trace && t <= L - 9 && t > L - 13) p.dbg[1024 + (warp * 4 + (L - 9 - t)) * 16 + (slot)] = clock64(); } while (0)
+
+  // Saved activations of a step (rows of ws, cpre, dzf, conv_save) are fetched with cp.async ONE STEP AHEAD into the
+  // other half of a double buffer: waiting for them inside the step put an L2/HBM round trip in front of phase A's
+  // block barrier every step.
+  const int wt_ld = (Te + 3) & ~3, cv_ld = g.TT * 16 * 16;
+  auto prefetch_rows = [&](int ts) {
+    if (own_ok && ts >= 0) {
+      const int hb = ts & 1;
+      const float* wrow = p.ws + (static_cast<int64_t>(bo) * R + ts + 1) * Te;
+      for (int i = tid; i < Te; i += kBT) cp_async4(wt_s2 + hb * wt_ld + i, wrow + i);
+      const float* crow = p.cpre + (static_cast<int64_t>(bo) * L + ts) * O;
+      for (int i = tid; i < O / 4; i += kBT) cp_async16(cpre_s2 + hb * O + 4 * i, crow + 4 * i);
+      const float* zrow = p.dzf + (static_cast<int64_t>(bo) * L + ts) * A;
+      for (int i = tid; i < A / 4; i += kBT) cp_async16(dzv2 + hb * A + 4 * i, zrow + 4 * i);
+      const float* cvrow = p.conv_save + ((static_cast<int64_t>(bo) * L + ts) * Te + te0) * 16;
+      for (int i = tid; i < ntl * 4; i += kBT) cp_async16(conv_s2 + hb * cv_ld + 4 * i, cvrow + 4 * i);
+    }
+    cp_async_commit();
+  };
+  prefetch_rows(L - 1);
+  // the cell state entering step t is the one leaving step t-1: loaded once, carried to the next iteration
+  float c_carry = 0.f;
+  if (epi_ok && is_z) c_carry = __ldg(p.c_save + sv_idx);
 
   for (int t = L - 1; t >= 0; --t) {
     const int par = t & 1;
     const uint32_t ph = (L - 1 - t) & 1;           // phase parity of the barriers filled during this step
     DTRACE(0);
-    // ---------------- prefetch of this step's saved activations (consumed in phases B and C)
-    if (own_ok) {
-      const float* wrow = p.ws + (static_cast<int64_t>(bo) * R + t + 1) * Te;
-      for (int i = tid; i < Te; i += kBT) cp_async4(wt_s + i, wrow + i);
-      const float* crow = p.cpre + (static_cast<int64_t>(bo) * L + t) * O;
-      for (int i = tid; i < O / 4; i += kBT) cp_async16(cpre_s + 4 * i, crow + 4 * i);
-      const float* zrow = p.dzf + (static_cast<int64_t>(bo) * L + t) * A;
-      for (int i = tid; i < A / 4; i += kBT) cp_async16(dzv + 4 * i, zrow + 4 * i);
-      const float* cvrow = p.conv_save + ((static_cast<int64_t>(bo) * L + t) * Te + te0) * 16;
-      for (int i = tid; i < ntl * 4; i += kBT) cp_async16(conv_s + 4 * i, cvrow + 4 * i);
-    }
-    float dzc_v = 0.f, c_cur = 0.f, c_prev = 0.f;
+    prefetch_rows(t - 1);
+    float* wt_s = wt_s2 + par * wt_ld;
+    float* cpre_s = cpre_s2 + par * O;
+    float* dzv = dzv2 + par * A;
+    float* conv_s = conv_s2 + par * cv_ld;
+    // per-thread operands of this step: volatile loads, so that ptxas cannot sink them to their first use (phase A's
+    // epilogue / phase C), where their latency would be exposed
+    float dzc_v = 0.f, c_prev = 0.f;
+    const float c_cur = c_carry;
     uint2 gpk = make_uint2(0u, 0u);
     if (epi_ok) {
-      dzc_v = __ldg(dzc_ptr);
+      asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(dzc_v) : "l"(dzc_ptr));
       if (is_z) {
-        gpk = __ldg(reinterpret_cast<const uint2*>(p.gates_save) + sv_idx);
-        c_cur = __ldg(p.c_save + sv_idx);
-        if (t > 0) c_prev = __ldg(p.c_save + sv_idx - Hd);
+        asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(gpk.x), "=r"(gpk.y)
+                     : "l"(reinterpret_cast<const uint2*>(p.gates_save) + sv_idx));
+        if (t > 0) asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(c_prev) : "l"(p.c_save + sv_idx - Hd));
       }
     }
+    c_carry = c_prev;
     // ================= phase A: d[z_t; c_t] rows = dzc_all + Wr^T dgates_{t+1} =================
     if (t < L - 1) {
       mbar_wait_tag(b_dg, ph ^ 1u, 10);            // dgates_{t+1} (sent at C(t+1)) complete in dgB
@@ -1088,7 +1220,7 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
       reinterpret_cast<float4*>(red)[warp * 32 + lane] =
           make_float4(acc0[0] + acc1[0], acc0[1] + acc1[1], acc0[2] + acc1[2], acc0[3] + acc1[3]);
     }
-    cp_async_wait_all();
+    cp_async_wait_n<1>();   // this step's rows (fetched during the previous step) have landed; the next step's may be in flight
     __syncthreads();      // partial sums in `red`; the prefetched rows are visible to every thread
     if (epi_ok) {
       float mm = red_gather(red, a_w0, g.KSb, row_l & 15, n_e);

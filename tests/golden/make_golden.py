@@ -116,11 +116,38 @@ def case_lm_and_ssl(ref, name, seed, B, Tmax, D, H, subsample, V, E, A, C, ksz, 
                    bos=1, eos=2, pad=0, ls_weight=ls, labeldist=labeldist)
     m.train()
     judge.train()
+    # A freshly initialised model gives nearly flat logits: the free-running argmax of the unpaired pass then sits on
+    # near-ties (top-2 margins of 1e-5 on logits of 0.3), where an fp32 and a bf16 implementation legitimately pick
+    # different tokens and nothing after the first difference can be compared. The reference is therefore trained on
+    # the paired batch (its own supervised step, solver.py:375-385) until every free-running step of the unpaired pass
+    # is decisive: top-2 margin > 4 * 3e-2 * max|logit| (twice the margin tests/test_gpu_ssl.py asserts).
+    uxs_probe = torch.from_numpy(ux)
+    Lu_probe = int(uxs_probe.size(1) * proportion)
+    pre_opt = torch.optim.Adam(m.parameters(), lr=5e-3)
+    pretrain_steps = -1
+    for it in range(3000):
+        with torch.no_grad():
+            pl, _, pp, _ = m(uxs_probe, ulens, ys=None, sample=False, label_smoothing=False, max_dec_timesteps=Lu_probe,
+                             smooth=True, scaling=3)
+        top2 = pl.topk(2, dim=-1).values
+        # ... and not all <EOS> (solver.py:478 would divide 0 by 0): at least a third of the tokens are real
+        if bool(((top2[..., 0] - top2[..., 1]) > 4 * 3e-2 * pl.abs().max()).all()) and float((pp != 2).float().mean()) > 0.33:
+            pretrain_steps = it
+            break
+        _, lp, _, _ = m(torch.from_numpy(x), lens, ys=[torch.from_numpy(y) for y in ys], tf_rate=1.0, sample=False)
+        pre_opt.zero_grad()
+        (-torch.mean(lp)).backward()
+        torch.nn.utils.clip_grad_norm_(m.parameters(), max_norm=5)
+        pre_opt.step()
+    assert pretrain_steps >= 0, "the unpaired free run never became decisive"
+    print(name, "pre-trained for", pretrain_steps, "steps; min margin / max|logit| =",
+          float(((top2[..., 0] - top2[..., 1]).min() / pl.abs().max())))
+    m.zero_grad()
     p0 = sd_numpy(m)
     j0 = sd_numpy(judge)
     out = {"x": x, "ilens": np.array(lens), "ux": ux, "uilens": np.array(ulens), "labeldist": labeldist,
            "proportion": np.float64(proportion), "subsample": np.array(subsample), "ls_weight": np.float32(ls),
-           "n_ys": np.int64(len(ys))}
+           "n_ys": np.int64(len(ys)), "pretrain_steps": np.int64(pretrain_steps)}
     for i, y in enumerate(ys):
         out[f"ys_{i}"] = y
     # ---- judge pre-train step (solver.py:288-297), text sorted by length descending
@@ -229,6 +256,10 @@ if __name__ == "__main__":
     torch.set_num_threads(4)
     if os.environ.get("ONLY_HOST"):
         case_host_plumbing("host_plumbing", seed=31)
+        sys.exit(0)
+    if os.environ.get("ONLY_SSL"):
+        case_lm_and_ssl(ref, "ssl_small", seed=21, B=3, Tmax=30, D=16, H=16, subsample=[2, 2], V=11, E=8, A=16,
+                        C=3, ksz=4, ls=0.05, JE=8, JH=24)
         sys.exit(0)
     # odd padded extents at every pyramid level, ragged lengths
     case_supervised(ref, "sup_small_odd", seed=11, B=4, Tmax=37, D=24, H=16, n_layers=3, subsample=[2, 2, 2],

@@ -154,7 +154,7 @@ def test_ssl_generator_step_at_reference_layer_sizes():
     # Unpaired batches are drawn until the two hypotheses agree everywhere (then the unsupervised term and the
     # gradient through the free run are compared too).
     agreed = None
-    for useed in (24, 25, 26, 27, 28, 29):
+    for useed in range(24, 36):
         rng = np.random.RandomState(useed)
         ulens = sorted([320] + [int(rng.randint(160, 321)) for _ in range(3)], reverse=True)
         ux = np.zeros((4, 320, 249), dtype=np.float32)
@@ -174,8 +174,7 @@ def test_ssl_generator_step_at_reference_layer_sizes():
         if not bool(diff.any()):
             agreed = useed
             break
-    if agreed is None:
-        pytest.skip("free-running hypotheses differed at near-ties for every unpaired batch tried")
+    assert agreed is not None, "free-running hypotheses differed at near-ties for every unpaired batch tried"
     lm, PJ = _lm(34, 25, labeldist)
     (loss_o, sup_o, unsup_o), grads_o, _, _ = O.ssl_step((torch.from_numpy(x), lens, ys), (torch.from_numpy(ux), ulens),
                                                         P, PJ, {}, cfg["sub"], 0.125, 0.05, labeldist, labeldist, fast=True)

@@ -73,22 +73,19 @@ def test_ssl_generator_step():
     ref_l = torch.from_numpy(g["u_logits"])
     top2 = ref_l.topk(2, dim=-1).values
     margin_ok = (top2[..., 0] - top2[..., 1]) > 2 * ACT_TOL * ref_l.abs().max()
-    all_safe = bool(margin_ok.all())
-    for b in range(u_pred.shape[0]):
-        n = 0
-        while n < u_pred.shape[1] and bool(margin_ok[b, n]):
-            n += 1
-        assert torch.equal(u_pred[b, :n].cpu(), torch.from_numpy(g["u_pred"])[b, :n]), (b, n)
+    # the fixture's model was trained until every free-running step is decisive (tests/golden/make_golden.py), so
+    # the whole hypothesis, the unsupervised term and the gradient through the free run are pinned by the reference
+    assert bool(margin_ok.all()), "ssl_small.npz holds near-ties: regenerate it with tests/golden/make_golden.py"
+    assert bool((torch.from_numpy(g["u_pred"]) != 2).any())            # not the 0/0 case of solver.py:478
+    assert torch.equal(u_pred.cpu(), torch.from_numpy(g["u_pred"]))
     assert abs(float(sup) - float(g["sup"])) < 1e-3 * abs(float(g["sup"]))
-    if all_safe:
-        assert torch.equal(u_pred.cpu(), torch.from_numpy(g["u_pred"]))
-        assert rel_err(u_logp, g["u_logp"]) < ACT_TOL
-        assert rel_err(lm_probs, g["lm_probs"]) < ACT_TOL
-        assert abs(float(unsup) - float(g["unsup"])) < 5e-3 * abs(float(g["unsup"]))
-        assert abs(float(loss) - float(g["loss"])) < 1e-3 * abs(float(g["loss"]))
-        m.zero_grad()
-        loss.backward()
-        _check_grads(list(m.named_parameters()), G["g"])
+    assert rel_err(u_logp, g["u_logp"]) < ACT_TOL
+    assert rel_err(lm_probs, g["lm_probs"]) < ACT_TOL
+    assert abs(float(unsup) - float(g["unsup"])) < 5e-3 * abs(float(g["unsup"]))
+    assert abs(float(loss) - float(g["loss"])) < 1e-3 * abs(float(g["loss"]))
+    m.zero_grad()
+    loss.backward()
+    _check_grads(list(m.named_parameters()), G["g"])
 
 
 def test_smooth_mode_gradient_reaches_earlier_steps():

@@ -60,15 +60,18 @@ if os.environ.get("LAS_TRACE"):
     ys_in = torch.randint(3, V, (B, L + 1), device=dev)
     ys_out = torch.randint(3, V, (B, L), device=dev)
     Fn.DEC_PERSISTENT = True
-    dbg = torch.zeros(256, device=dev, dtype=torch.int64)
+    dbg = torch.zeros(2048, device=dev, dtype=torch.int64)
     LIB.lib().las_set_debug_buffer(dbg.data_ptr())
     logits, logp, pred, ws = dec.forward_dev(enc_h, lens, ys_in, ys_out, L, 0)
     (-logp.mean()).backward()
     torch.cuda.synchronize()
     LIB.lib().las_set_debug_buffer(None)
-    d = dbg.cpu()[64:128].view(4, 16)
+    d = dbg.cpu()[1024:1024 + 12 * 64].view(12, 4, 16)
     names = ["A:mma+epi", "wait dc", "B1-2:dw,de", "B3:energy", "B4:ddz,dwn", "wait ddz", "C:cell", "stores"]
-    print(" ".join(f"{n:>11s}" for n in names))
-    for s_ in range(4):
-        row = d[s_]
-        print(" ".join(f"{int(row[i + 1] - row[i]):11d}" for i in range(8)), "| step", int(d[s_ + 1, 0] - row[0]) if s_ < 3 else "")
+    print("per-warp phase durations (cycles), second traced step")
+    print("warp " + " ".join(f"{n:>11s}" for n in names) + " |     step")
+    for w in range(12):
+        row, nxt = d[w, 1], d[w, 2]
+        if int(row[0]) == 0:
+            continue
+        print(f"{w:4d} " + " ".join(f"{int(row[i + 1] - row[i]):11d}" for i in range(8)) + f" | {int(nxt[0] - row[0]):8d}")

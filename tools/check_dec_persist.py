@@ -62,16 +62,26 @@ if os.environ.get("LAS_PROF") or os.environ.get("LAS_TRACE"):
 
 if os.environ.get("LAS_TRACE"):
     LIB = pkg("_lib")
-    dbg = torch.zeros(128, device="cuda", dtype=torch.int64)
+    dbg = torch.zeros(2048, device="cuda", dtype=torch.int64)
     LIB.lib().las_set_debug_buffer(dbg.data_ptr())
     Fn.DEC_PERSISTENT = True
     with torch.no_grad():
         dec.forward_dev(enc_h, lens, ys_in, ys_out, L, 0)
     torch.cuda.synchronize()
     LIB.lib().las_set_debug_buffer(None)
-    d = dbg.cpu().view(8, 16)
+    d = dbg.cpu()[:1024].view(16, 4, 16)
     names = ["wait z,c", "mma+sync", "epi+send", "conv", "wait z+dz", "dz-send", "wait dz+E", "sync", "e-send", "wait e", "smax+ctx"]
-    print(" ".join(f"{n:>9s}" for n in names))
-    for s_ in range(4):
-        row = d[s_]
-        print(" ".join(f"{int(row[i + 1] - row[i]):9d}" for i in range(11)), "| step", int(d[s_ + 1, 0] - row[0]) if s_ < 3 else "")
+    print("per-warp phase durations (cycles), step 9; slots 12/13 = epilogue math done / sends done (relative to slot 2)")
+    print("warp " + " ".join(f"{n:>9s}" for n in names) + " |     step   epi-math  epi-sends")
+    for w in range(16):
+        row, nxt = d[w, 1], d[w, 2]
+        if int(row[0]) == 0:
+            continue
+        print(f"{w:4d} " + " ".join(f"{int(row[i + 1] - row[i]):9d}" for i in range(11)) + f" | {int(nxt[0] - row[0]):8d}"
+              + (f" {int(row[12] - row[2]):10d} {int(row[13] - row[2]):10d}" if int(row[12]) else " " * 22)
+              + f" | softmax {int(row[14] - row[10]):6d}" + (f" ctx-mma {int(row[15] - row[14]):6d} tail {int(row[11] - row[15]):6d}" if int(row[15]) else ""))
+    t0 = int(d[0, 1, 0])
+    print("absolute slot times of step 9 relative to warp 0 slot 0:")
+    for w in range(16):
+        if int(d[w, 1, 0]):
+            print(f"{w:4d} " + " ".join(f"{int(d[w, 1, i]) - t0:7d}" for i in range(12)))
