@@ -35,6 +35,7 @@
 // c_t = mlp_o(sum_te w[te] enc_h[te]) is evaluated as sum_te w[te] (mlp_o.weight enc_h[te]) + bias
 // (softmax weights sum to one), which removes mlp_o from the serial loop.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "las_internal.h"
 #include "../../include/las_b200.h"
@@ -68,12 +69,11 @@ struct DGeom {
   int smem;
 };
 
-inline int rup(int x, int m) { return (x + m - 1) / m * m; }
+constexpr int rup(int x, int m) { return (x + m - 1) / m * m; }
 
 // Returns false when the problem is not served by the persistent kernel.
-bool dec_geom(const las_dec_args* a, int NB, DGeom& g) {
-  const int Hd = a->Hd, O = a->O, A = a->A, Te = a->Te;
-  if (Hd % 64 != 0 || Hd > 320 || O % 16 != 0 || A % 8 != 0 || A > 512 || a->C > 16 || Te > kThreads) return false;
+constexpr bool dec_geom_c(int Hd, int O, int A, int Te, int C, int K, int NB, DGeom& g) {
+  if (Hd % 64 != 0 || Hd > 320 || O % 16 != 0 || A % 8 != 0 || A > 512 || C > 16 || Te > kThreads) return false;
   g.NB = NB; g.G = kCS / NB;
   g.UPC = Hd / kCS; g.GT = g.UPC / 4;
   g.KTg = (Hd + O) / 16; g.KTd = Hd / 16;
@@ -100,12 +100,12 @@ bool dec_geom(const las_dec_args* a, int NB, DGeom& g) {
   g.AT8 = A / 8;
   g.NTW = (g.AT8 + g.WPT - 1) / g.WPT;
   g.KTe = (Te + 15) / 16;
-  const int ksz = 2 * a->K + 1;
+  const int ksz = 2 * K + 1;
   g.KTc = (ksz + 15) / 16;
-  g.NC = a->C > 8 ? 2 : 1;
+  g.NC = C > 8 ? 2 : 1;
   g.Pld = A + ((8 - A % 16) + 16) % 16;   // bf16 row stride, word stride == 4 (mod 8): conflict-free 32-bit fragment loads
   g.QTld = 16 * g.KTe + 8;                // word stride == 4 (mod 8): conflict-free 32-bit fragment loads
-  g.Tw = Te + 2 * a->K + 48;              // the Hankel fragments of the last frame tile read up to 45 words past the end
+  g.Tw = Te + 2 * K + 48;                 // the Hankel fragments of the last frame tile read up to 45 words past the end
   int off = 0;
   auto take = [&](int bytes) { const int o = off; off += rup(bytes, 16); return o; };
   g.o_zB = take(2 * g.KTp * 256);
@@ -129,6 +129,24 @@ bool dec_geom(const las_dec_args* a, int NB, DGeom& g) {
   g.smem = off;
   return g.smem <= kSmemMax;
 }
+inline bool dec_geom(const las_dec_args* a, int NB, DGeom& g) {
+  return dec_geom_c(a->Hd, a->O, a->A, a->Te, a->C, a->K, NB, g);
+}
+
+// Compile-time geometry of the reference's own layer sizes (config.yaml: dec_hidden_dim = att_dim = att_odim = 320,
+// conv_kernel_size 100, 10 conv channels) for 8 utterances per cluster and up to 128 encoder frames (T <= 1024 input
+// frames). The kernels are instantiated once with this geometry as constants (shared-memory offsets, tile counts and
+// role indices fold into immediates: both kernels sit at their register limit, and with a 220 KB shared-memory
+// carve-out the L1 is so small that every spilled register is an L2 round trip on the serial path) and once with the
+// geometry read from the launch parameters (everything else).
+constexpr int kS_Hd = 320, kS_O = 320, kS_A = 320, kS_Te = 128, kS_C = 10, kS_K = 100, kS_NB = 8;
+constexpr DGeom make_static_dgeom() {
+  DGeom g{};
+  g.smem = dec_geom_c(kS_Hd, kS_O, kS_A, kS_Te, kS_C, kS_K, kS_NB, g) ? g.smem : -1;
+  return g;
+}
+constexpr DGeom kSF = make_static_dgeom();
+static_assert(kSF.smem > 0, "static forward geometry must fit");
 
 // ------------------------------------------------------------------------------------------
 // cluster primitives
@@ -189,12 +207,27 @@ __device__ __forceinline__ void st_remote_v2_u32(uint32_t addr, uint32_t a, uint
   asm volatile("st.shared::cluster.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
 }
 
-// Element (row, col) of a 16x8 accumulator tile, summed over the KS K-split warps w0 .. w0+KS-1.
+// Partial sums of a 16x8 accumulator tile in a gather-friendly layout: element (row, col) of slot s (= the K-split
+// warp that produced it) sits at word s * kRedLd + 9 * row + col. Threads that read consecutive rows of one column
+// (the per-element epilogues of the backward kernel) hit 32 distinct banks; the fragment-order layout gave 8-way
+// conflicts on every one of those loads.
+constexpr int kRedLd = 16 * 9;
+__device__ __forceinline__ void red_store(float* red, int slot, int gq, int tig, const float (&acc)[4]) {
+  float* r = red + slot * kRedLd + 9 * gq + 2 * tig;
+  r[0] = acc[0]; r[1] = acc[1]; r[72] = acc[2]; r[73] = acc[3];
+}
+// Element (row, col), summed over the KS K-split warps w0 .. w0+KS-1.
 __device__ __forceinline__ float red_gather(const float* red, int w0, int KS, int row, int col) {
-  const float* r = red + (w0 * 32 + (row & 7) * 4 + (col >> 1)) * 4 + (row >> 3) * 2 + (col & 1);
+  const float* r = red + w0 * kRedLd + 9 * row + col;
   float s = 0.f;
-  for (int i = 0; i < KS; ++i) s += r[i * 128];
+  for (int i = 0; i < KS; ++i) s += r[i * kRedLd];
   return s;
+}
+// Bulk copy from this CTA's shared memory into a peer's (cluster-mapped address), completing on the peer's mbarrier.
+// The source must have been made visible to the async proxy (fence_proxy_async_smem() by its writers, then a barrier).
+__device__ __forceinline__ void dsmem_bulk_copy(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t mbar_cluster) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_cluster), "r"(src_cta), "r"(bytes), "r"(mbar_cluster) : "memory");
 }
 
 // bf16 hi/lo split of a float pair: x ~= hi + lo with ~16 mantissa bits in total
@@ -247,6 +280,7 @@ struct DecFwdP {
 // Kernel parameters are copied to shared memory first: every cluster barrier (acquire) invalidates
 // the constant/L1 caches, and a constant-bank miss per parameter read was the dominant stall of
 // the first version of this kernel (profiles/r01_decfwd_v1_stalls.txt).
+template <bool kS>
 __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __grid_constant__ DecFwdP p_in) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ DecFwdP p;
@@ -259,30 +293,32 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
   }
   __syncthreads();
   const DGeom& g = p.g;
+#define GEO(x) (kS ? kSF.x : g.x)
   uint64_t* bz = bars; uint64_t* bc = bars + 2; uint64_t* bdz = bars + 4; uint64_t* be = bars + 5;
-  uint32_t* zB = reinterpret_cast<uint32_t*>(smem + g.o_zB);       // [2][KTp][32][2]
-  float* red = reinterpret_cast<float*>(smem + g.o_red);           // [16][32][4] gate partial sums (P1)
-  float* red2 = reinterpret_cast<float*>(smem + g.o_red2);         // [16][32][4] mlp_dec partial sums (P2)
-  float* dzv = reinterpret_cast<float*>(smem + g.o_dzv);           // [A]
-  float4* cred = reinterpret_cast<float4*>(smem + g.o_cred);       // [16 warps][2][32] partial conv accumulators
-  float* wbuf = reinterpret_cast<float*>(smem + g.o_wbuf);         // [Te + 2K + 48], w[j] at wbuf[K + j]
-  uint4* cwB = reinterpret_cast<uint4*>(smem + g.o_cwB);           // [KTc][2][32] conv-weight B fragments (hi0, hi1, lo0, lo1)
-  uint4* mattB = reinterpret_cast<uint4*>(smem + g.o_matt);        // [AT8][32] mlp_att B fragments (hi0, hi1, lo0, lo1)
-  float* gv_s = reinterpret_cast<float*>(smem + g.o_gv);           // [A]
-  __nv_bfloat16* P_s = reinterpret_cast<__nv_bfloat16*>(smem + g.o_P);   // [TT*16][Pld]   my frames of P (bf16: below the error of the bf16 GEMM that made it)
-  __nv_bfloat16* QT_s = reinterpret_cast<__nv_bfloat16*>(smem + g.o_Q);   // [OTs*16][QTld]  my context dims of Q, transposed
-  float* epart = reinterpret_cast<float*>(smem + g.o_epart);       // [WPT][TT*16]
-  float* e_all = reinterpret_cast<float*>(smem + g.o_eall);        // [G*TR] scaled energies of all frames (written by the owners)
-  uint2* pB = reinterpret_cast<uint2*>(smem + g.o_pun);            // [KTe*8] softmax numerators of frames (2i, 2i+1): bf16x2 hi, lo
-  float* wred = reinterpret_cast<float*>(smem + g.o_wred);         // [2][16]
+  uint32_t* zB = reinterpret_cast<uint32_t*>(smem + GEO(o_zB));       // [2][KTp][32][2]
+  float* red = reinterpret_cast<float*>(smem + GEO(o_red));           // [16][32][4] gate partial sums (P1)
+  float* red2 = reinterpret_cast<float*>(smem + GEO(o_red2));         // [16][32][4] mlp_dec partial sums (P2)
+  float* dzv = reinterpret_cast<float*>(smem + GEO(o_dzv));           // [A]
+  float4* cred = reinterpret_cast<float4*>(smem + GEO(o_cred));       // [16 warps][2][32] partial conv accumulators
+  float* wbuf = reinterpret_cast<float*>(smem + GEO(o_wbuf));         // [Te + 2K + 48], w[j] at wbuf[K + j]
+  uint4* cwB = reinterpret_cast<uint4*>(smem + GEO(o_cwB));           // [KTc][2][32] conv-weight B fragments (hi0, hi1, lo0, lo1)
+  uint4* mattB = reinterpret_cast<uint4*>(smem + GEO(o_matt));        // [AT8][32] mlp_att B fragments (hi0, hi1, lo0, lo1)
+  float* gv_s = reinterpret_cast<float*>(smem + GEO(o_gv));           // [A]
+  __nv_bfloat16* P_s = reinterpret_cast<__nv_bfloat16*>(smem + GEO(o_P));   // [TT*16][Pld]   my frames of P (bf16: below the error of the bf16 GEMM that made it)
+  __nv_bfloat16* QT_s = reinterpret_cast<__nv_bfloat16*>(smem + GEO(o_Q));   // [OTs*16][QTld]  my context dims of Q, transposed
+  float* epart = reinterpret_cast<float*>(smem + GEO(o_epart));       // [WPT][TT*16]
+  float* e_all = reinterpret_cast<float*>(smem + GEO(o_eall));        // [G*TR] scaled energies of all frames (written by the owners)
+  uint2* pB = reinterpret_cast<uint2*>(smem + GEO(o_pun));            // [KTe*8] softmax numerators of frames (2i, 2i+1): bf16x2 hi, lo
+  float* wred = reinterpret_cast<float*>(smem + GEO(o_wred));         // [2][16]
 
   const int tid = threadIdx.x, lane = tid & 31, gq = lane >> 2, tig = lane & 3;
   // provably warp-uniform warp index: everything derived from it (tile / split / role indices) can live in uniform registers
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const uint32_t rank = cluster_rank();
   const int cl = blockIdx.y;
-  const int NB = g.NB, G = g.G, UPC = g.UPC, TR = g.TR, OS = g.OS;
-  const int Hd = p.Hd, O = p.O, A = p.A, Te = p.Te, L = p.L, K = p.K, C = p.C;
+  const int NB = GEO(NB), G = GEO(G), UPC = GEO(UPC), TR = GEO(TR), OS = GEO(OS);
+  const int Hd = kS ? kS_Hd : p.Hd, O = kS ? kS_O : p.O, A = kS ? kS_A : p.A, K = kS ? kS_K : p.K;
+  const int Te = p.Te, L = p.L, C = p.C;
   const int ZC = Hd + O, R = L + 1, ksz = 2 * K + 1;
   const int n_own = rank / G, q = rank % G;
   const int b_own = cl * NB + n_own;
@@ -292,39 +328,39 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
 
   // ---------------- resident weights (registers)
   // gate phase: warp = tile * KSg + ks holds k-tiles [ks*FG, ks*FG + FG) of its tile
-  const int g_tile = warp / g.KSg, g_ks = warp % g.KSg;
-  const bool g_act = g_tile < g.GT;
-  const int g_kt0 = g_ks * g.FG;
+  const int g_tile = warp / GEO(KSg), g_ks = warp % GEO(KSg);
+  const bool g_act = g_tile < GEO(GT);
+  const int g_kt0 = g_ks * GEO(FG);
   uint4 Ag[kMaxFG];
 #pragma unroll
   for (int j = 0; j < kMaxFG; ++j) {
     Ag[j] = make_uint4(0u, 0u, 0u, 0u);
-    if (g_act && j < g.FG && g_kt0 + j < g.KTg)
+    if (g_act && j < GEO(FG) && g_kt0 + j < GEO(KTg))
       Ag[j] = __ldg(reinterpret_cast<const uint4*>(p.wr_pk) +
-                    (static_cast<int64_t>(rank * g.GT + g_tile) * g.KTg + g_kt0 + j) * 32 + lane);
+                    (static_cast<int64_t>(rank * GEO(GT) + g_tile) * GEO(KTg) + g_kt0 + j) * 32 + lane);
   }
-  const int nATr = (g.AT > static_cast<int>(rank)) ? (g.AT - 1 - static_cast<int>(rank)) / kCS + 1 : 0;   // my mlp_dec tiles
-  const int d_tile = warp / g.KSd, d_ks = warp % g.KSd;
+  const int nATr = (GEO(AT) > static_cast<int>(rank)) ? (GEO(AT) - 1 - static_cast<int>(rank)) / kCS + 1 : 0;   // my mlp_dec tiles
+  const int d_tile = warp / GEO(KSd), d_ks = warp % GEO(KSd);
   const bool d_act = d_tile < nATr;
-  const int d_kt0 = d_ks * g.FD;
+  const int d_kt0 = d_ks * GEO(FD);
   // the mlp_dec fragments (3 per warp) live in shared memory: the kernel is at its register limit (128 x 512 threads)
-  uint4* decA = reinterpret_cast<uint4*>(smem + g.o_decA) + warp * kMaxFD * 32 + lane;
+  uint4* decA = reinterpret_cast<uint4*>(smem + GEO(o_decA)) + warp * kMaxFD * 32 + lane;
 #pragma unroll
   for (int j = 0; j < kMaxFD; ++j) {
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (d_act && j < g.FD && d_kt0 + j < g.KTd)
+    if (d_act && j < GEO(FD) && d_kt0 + j < GEO(KTd))
       v = __ldg(reinterpret_cast<const uint4*>(p.dec_pk) +
-                (static_cast<int64_t>(rank + kCS * d_tile) * g.KTd + d_kt0 + j) * 32 + lane);
+                (static_cast<int64_t>(rank + kCS * d_tile) * GEO(KTd) + d_kt0 + j) * 32 + lane);
     decA[j * 32] = v;
   }
-  const int nfg = g.FG, nfd = g.FD;
+  const int nfg = GEO(FG), nfd = GEO(FD);
 
   // ---------------- resident attention operands (shared memory)
-  for (int i = tid; i < 2 * g.KTp * 64; i += kThreads) zB[i] = 0u;
-  for (int i = tid; i < g.Tw; i += kThreads) wbuf[i] = 0.f;
-  for (int i = tid; i < g.KTe * 8; i += kThreads) pB[i] = make_uint2(0u, 0u);
+  for (int i = tid; i < 2 * GEO(KTp) * 64; i += kThreads) zB[i] = 0u;
+  for (int i = tid; i < GEO(Tw); i += kThreads) wbuf[i] = 0.f;
+  for (int i = tid; i < GEO(KTe) * 8; i += kThreads) pB[i] = make_uint2(0u, 0u);
   for (int i = tid; i < kWarps * 64; i += kThreads) cred[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int i = tid; i < g.KTc * 64; i += kThreads) {
+  for (int i = tid; i < GEO(KTc) * 64; i += kThreads) {
     // B fragment of the conv weights: k = tap, n = channel 8*nc + (l >> 2)
     const int kt = i >> 6, nc = (i >> 5) & 1, l = i & 31, c = 8 * nc + (l >> 2), k0 = 16 * kt + 2 * (l & 3);
     float m[4];
@@ -339,7 +375,7 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
     cwB[i] = v;
   }
   for (int i = tid; i < A; i += kThreads) gv_s[i] = p.gvec[i];
-  for (int i = tid; i < g.AT8 * 32; i += kThreads) {
+  for (int i = tid; i < GEO(AT8) * 32; i += kThreads) {
     const int nt = i >> 5, l = i & 31, a = 8 * nt + (l >> 2), c0 = 2 * (l & 3);
     float m[4];
 #pragma unroll
@@ -352,16 +388,16 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
     split_bf16x2(m[2], m[3], v.y, v.w);
     mattB[i] = v;
   }
-  for (int i = tid; i < g.TT * 16 * g.Pld; i += kThreads) {
-    const int r = i / g.Pld, a = i % g.Pld;
+  for (int i = tid; i < GEO(TT) * 16 * GEO(Pld); i += kThreads) {
+    const int r = i / GEO(Pld), a = i % GEO(Pld);
     P_s[i] = __float2bfloat16((r < ntl && a < A) ? p.P[(static_cast<int64_t>(b_own) * Te + te0 + r) * A + a] : 0.f);
   }
-  for (int i = tid; i < g.OTs * 16 * g.QTld; i += kThreads) QT_s[i] = __float2bfloat16(0.f);
+  for (int i = tid; i < GEO(OTs) * 16 * GEO(QTld); i += kThreads) QT_s[i] = __float2bfloat16(0.f);
   __syncthreads();
   if (own_ok) {
     for (int i = tid; i < Te * OS; i += kThreads) {
       const int te = i / OS, ol = i % OS;
-      QT_s[ol * g.QTld + te] = p.Q[(static_cast<int64_t>(b_own) * Te + te) * O + q * OS + ol];
+      QT_s[ol * GEO(QTld) + te] = p.Q[(static_cast<int64_t>(b_own) * Te + te) * O + q * OS + ol];
     }
     for (int i = tid; i < Te; i += kThreads) wbuf[K + i] = p.ws[static_cast<int64_t>(b_own) * R * Te + i];
   }
@@ -385,8 +421,8 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
   // Input-projection terms embx[b][t][gate*Hd + u]: prefetched kPFd steps ahead with cp.async into a thread-private
   // ring slot (plain loads at the top of the step are sunk by ptxas to their first use, in the cell epilogue).
   const float* ex_ptr = p.embx + static_cast<int64_t>(epi_ok ? b_e : 0) * R * 4 * Hd + u_e;
-  const int exs = g.GT * 32;                     // ring stride between gates
-  float* exr = reinterpret_cast<float*>(smem + g.o_exr) + (g_act ? g_tile : 0) * 32 + lane;
+  const int exs = GEO(GT) * 32;                     // ring stride between gates
+  float* exr = reinterpret_cast<float*>(smem + GEO(o_exr)) + (g_act ? g_tile : 0) * 32 + lane;
   int pf_t = 0;
   auto prefetch_ex = [&]() {
     if (epi_ok && pf_t < L) {
@@ -413,7 +449,7 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
   float* dzf_ptr = p.dzf + static_cast<int64_t>(depi_ok ? cl * NB + n_d : 0) * L * A + (depi_ok ? a_d : 0);
   {
     // frame means of P for the accumulator elements of this lane: rows gq, gq + 8 of the tile, utterances 2tig, 2tig+1
-    float4* pb = reinterpret_cast<float4*>(smem + g.o_pb);
+    float4* pb = reinterpret_cast<float4*>(smem + GEO(o_pb));
     if (d_lead) {
       const int a0 = (static_cast<int>(rank) + kCS * warp) * 16 + gq, a1 = a0 + 8;
       const int b0 = cl * NB + 2 * tig, b1 = b0 + 1;
@@ -425,15 +461,15 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
     }
   }
   // P3: (frame tile, attention-dim slice) of this warp
-  const int e_tt = warp / g.WPT, e_wi = warp % g.WPT;
-  const bool e_act = warp < g.TT * g.WPT && ntl > 0;
+  const int e_tt = warp / GEO(WPT), e_wi = warp % GEO(WPT);
+  const bool e_act = warp < GEO(TT) * GEO(WPT) && ntl > 0;
   const int cm = te0 + 16 * e_tt;
   // location conv (runs next to the cell epilogue): (frame tile, K split) of this warp. Lead warps sit at
   // 0, KSg, 2 KSg, ..: the conv slots are the remaining warps in order.
-  const int n_lead_before = min(g.GT, (warp + g.KSg - 1) / g.KSg);
-  const int cv = g.cw0 ? (g_lead ? -1 : warp - n_lead_before) : warp;
-  const bool c_act = cv >= 0 && cv < g.TT * g.WPTc && ntl > 0;
-  const int c_tt = c_act ? cv / g.WPTc : 0, c_wi = c_act ? cv % g.WPTc : 0;
+  const int n_lead_before = min(GEO(GT), (warp + GEO(KSg) - 1) / GEO(KSg));
+  const int cv = GEO(cw0) ? (g_lead ? -1 : warp - n_lead_before) : warp;
+  const bool c_act = cv >= 0 && cv < GEO(TT) * GEO(WPTc) && ntl > 0;
+  const int c_tt = c_act ? cv / GEO(WPTc) : 0, c_wi = c_act ? cv % GEO(WPTc) : 0;
   // conv k-tiles of that frame tile: taps that can touch a valid alignment entry
   const int cmc = te0 + 16 * c_tt;
   const int ckt_lo = max(0, K - (cmc + 15)) >> 4;
@@ -444,7 +480,7 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
   const int c_mt = warp;                                   // context m-tile of this warp (if < OTs)
   const int o_l0 = 16 * c_mt + gq;                         // local context dims o_l0, o_l0 + 8 (lanes with tig == 0)
   float cb_a = 0.f, cb_b = 0.f;                            // their bias terms (constant over the steps)
-  if (own_ok && c_mt < g.OTs && tig == 0) {
+  if (own_ok && c_mt < GEO(OTs) && tig == 0) {
     if (o_l0 < OS) cb_a = p.cbias[static_cast<int64_t>(b_own) * O + q * OS + o_l0];
     if (o_l0 + 8 < OS) cb_b = p.cbias[static_cast<int64_t>(b_own) * O + q * OS + o_l0 + 8];
   }
@@ -455,9 +491,9 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
   const bool drop_on = p.drop_p > 0.f;
   // bytes a barrier phase counts: z_t of all NB columns from all CTAs; c_t of the valid utterances; dz and the
   // energies of my own utterance
-#define TX_Z (2u * p.Hd * g.NB)
-#define TX_C (2u * p.O * max(0, min(g.NB, p.B - static_cast<int>(blockIdx.y) * g.NB)))
-#define TX_DZ (4u * p.A)
+#define TX_Z (2u * Hd * GEO(NB))
+#define TX_C (2u * O * max(0, min(GEO(NB), p.B - static_cast<int>(blockIdx.y) * GEO(NB))))
+#define TX_DZ (4u * A)
 #define TX_E (4u * p.Te)
   if (tid == 0) {
     const uint32_t tx_z = TX_Z, tx_c = TX_C, tx_dz = TX_DZ, tx_e = TX_E;
@@ -476,7 +512,7 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
 
   for (int t = 0; t < L; ++t) {
     const int par = t & 1, nxt = par ^ 1;
-    const int zb_nxt_w = nxt * g.KTp * 64;     // word offset of the buffer that receives [z_t; c_t]
+    const int zb_nxt_w = nxt * GEO(KTp) * 64;     // word offset of the buffer that receives [z_t; c_t]
     const uint32_t ph2 = (t >> 1) & 1;            // phase parity of bz[nxt] / bc[nxt] at this step
 
     // ================= P1: LSTM cell =================
@@ -494,7 +530,7 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
     if (g_act) {
       float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
       // padded fragments (zero A) read padded, all-zero k-tiles of the state buffer
-      const uint2* hb = reinterpret_cast<const uint2*>(zB + par * g.KTp * 64) + lane + g_kt0 * 32;
+      const uint2* hb = reinterpret_cast<const uint2*>(zB + par * GEO(KTp) * 64) + lane + g_kt0 * 32;
 #pragma unroll
       for (int j = 0; j < kMaxFG; ++j) {
         if (j < nfg) {
@@ -505,7 +541,7 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
         }
       }
       float cf[4] = {acc0[0] + acc1[0], acc0[1] + acc1[1], acc0[2] + acc1[2], acc0[3] + acc1[3]};
-      const int nks = g.KSg;
+      const int nks = GEO(KSg);
       if (!g_lead) {
         redP[(g_tile * (nks - 1) + g_ks - 1) * 32 + lane] = make_float4(cf[0], cf[1], cf[2], cf[3]);
         named_bar_arrive(1 + g_tile, 32 * nks);       // producer: does not wait
@@ -573,7 +609,7 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
       // A fragment of k-tile kt: a0 = y(2kt), a1 = a2 = y(2kt+1), a3 = y(2kt+2), y(j) = x[g + 2tig + 8j .. +1]
       float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
       const float* xb = wbuf + cmc + gq + 2 * tig;
-      for (int kt = ckt_lo + c_wi; kt <= ckt_hi; kt += g.WPTc) {
+      for (int kt = ckt_lo + c_wi; kt <= ckt_hi; kt += GEO(WPTc)) {
         const float* xk = xb + 16 * kt;
         uint32_t Ah[4], Al[4];
         split_bf16x2(xk[0], xk[1], Ah[0], Al[0]);
@@ -584,7 +620,7 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
         mma_bf16_16816(c0, Ah, b0.x, b0.y);
         mma_bf16_16816(c0, Al, b0.x, b0.y);
         mma_bf16_16816(c0, Ah, b0.z, b0.w);
-        if (g.NC > 1) {
+        if (GEO(NC) > 1) {
           const uint4 b1 = cwB[(kt * 2 + 1) * 32 + lane];
           mma_bf16_16816(c1, Ah, b1.x, b1.y);
           mma_bf16_16816(c1, Al, b1.x, b1.y);
@@ -616,9 +652,9 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
     DTRACE(5);
     if (d_lead) {
       // sum of the K-split partials of tile `warp` in fragment order (conflict-free 16-byte loads), plus the frame mean
-      float4 m = reinterpret_cast<const float4*>(smem + g.o_pb)[warp * 32 + lane];
-      for (int ks = 0; ks < g.KSd; ++ks) {
-        const float4 v = reinterpret_cast<const float4*>(red2)[(warp * g.KSd + ks) * 32 + lane];
+      float4 m = reinterpret_cast<const float4*>(smem + GEO(o_pb))[warp * 32 + lane];
+      for (int ks = 0; ks < GEO(KSd); ++ks) {
+        const float4 v = reinterpret_cast<const float4*>(red2)[(warp * GEO(KSd) + ks) * 32 + lane];
         m.x += v.x; m.y += v.y; m.z += v.z; m.w += v.w;
       }
       // 4x4 transpose among the lanes ul = 0..3 of (gl, tig): element k of lane ul = M[ul][k] with k = (row half, utterance
@@ -656,8 +692,8 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
       const int r0 = 16 * e_tt + gq, r1 = r0 + 8;
       // conv features in A-fragment position: sum of the K-split partials of my frame tile
       float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int w = 0; w < g.WPTc; ++w) {
-        const float4 a = cred[((e_tt * g.WPTc + w) * 2) * 32 + lane], b = cred[((e_tt * g.WPTc + w) * 2 + 1) * 32 + lane];
+      for (int w = 0; w < GEO(WPTc); ++w) {
+        const float4 a = cred[((e_tt * GEO(WPTc) + w) * 2) * 32 + lane], b = cred[((e_tt * GEO(WPTc) + w) * 2 + 1) * 32 + lane];
         s0.x += a.x; s0.y += a.y; s0.z += a.z; s0.w += a.w;
         s1.x += b.x; s1.y += b.y; s1.z += b.z; s1.w += b.w;
       }
@@ -680,11 +716,11 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
       split_bf16x2(s1.x, s1.y, Ah[2], Al[2]);
       split_bf16x2(s1.z, s1.w, Ah[3], Al[3]);
       float e0 = 0.f, e1 = 0.f;
-      const int nt_end = min((e_wi + 1) * g.NTW, g.AT8);
-      const __nv_bfloat16* P0 = P_s + r0 * g.Pld + 2 * tig;
-      const __nv_bfloat16* P1 = P_s + r1 * g.Pld + 2 * tig;
+      const int nt_end = min((e_wi + 1) * GEO(NTW), GEO(AT8));
+      const __nv_bfloat16* P0 = P_s + r0 * GEO(Pld) + 2 * tig;
+      const __nv_bfloat16* P1 = P_s + r1 * GEO(Pld) + 2 * tig;
 #pragma unroll 2
-      for (int nt = e_wi * g.NTW; nt < nt_end; ++nt) {
+      for (int nt = e_wi * GEO(NTW); nt < nt_end; ++nt) {
         const uint4 bm = mattB[nt * 32 + lane];
         const int a = 8 * nt;
         const float2 p0 = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(P0 + a));
@@ -705,8 +741,8 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
       e1 += __shfl_xor_sync(0xffffffffu, e1, 1);
       e1 += __shfl_xor_sync(0xffffffffu, e1, 2);
       if (tig == 0) {
-        epart[e_wi * g.TT * 16 + r0] = e0;
-        epart[e_wi * g.TT * 16 + r1] = e1;
+        epart[e_wi * GEO(TT) * 16 + r0] = e0;
+        epart[e_wi * GEO(TT) * 16 + r1] = e1;
       }
     }
     if (csave_ptr) csave_ptr += Te * 16;
@@ -715,7 +751,7 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
     DTRACE(8);
     if (tid < ntl) {
       float e = 0.f;
-      for (int w = 0; w < g.WPT; ++w) e += epart[w * g.TT * 16 + tid];
+      for (int w = 0; w < GEO(WPT); ++w) e += epart[w * GEO(TT) * 16 + tid];
       e *= scal;
       const uint32_t off = eall_base + 4u * (te0 + tid);
       for (int qq = 0; qq < G; ++qq) {
@@ -750,7 +786,7 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
         // them as ready-made B-fragment words (bf16 hi/lo pairs of frames (2i, 2i+1)).
         const float pn = __shfl_down_sync(0xffffffffu, pv, 1);
         if (fr) wbuf[K + tid] = pv;
-        if ((tid & 1) == 0 && tid < g.KTe * 16) {
+        if ((tid & 1) == 0 && tid < GEO(KTe) * 16) {
           uint2 hl;
           split_bf16x2(pv, pn, hl.x, hl.y);
           pB[tid >> 1] = hl;
@@ -765,13 +801,13 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
       inv_w = invS;
       // context slice on tensor cores: c[o] = sum_te QT[o][te] p[te]  (M = my context dims, K = frames; every column of B
       // holds p, column 0 is read back)
-      if (own_ok && c_mt < g.OTs) {
+      if (own_ok && c_mt < GEO(OTs)) {
         float acc[4] = {0.f, 0.f, 0.f, 0.f}, accl[4] = {0.f, 0.f, 0.f, 0.f};
-        const uint32_t* q0 = reinterpret_cast<const uint32_t*>(QT_s + o_l0 * g.QTld) + tig;
-        const uint32_t* q1 = reinterpret_cast<const uint32_t*>(QT_s + (o_l0 + 8) * g.QTld) + tig;
+        const uint32_t* q0 = reinterpret_cast<const uint32_t*>(QT_s + o_l0 * GEO(QTld)) + tig;
+        const uint32_t* q1 = reinterpret_cast<const uint32_t*>(QT_s + (o_l0 + 8) * GEO(QTld)) + tig;
         const uint2* pbt = pB + tig;
 #pragma unroll 2
-        for (int kt = 0; kt < g.KTe; ++kt) {
+        for (int kt = 0; kt < GEO(KTe); ++kt) {
           const uint32_t Af[4] = {q0[kt * 8], q1[kt * 8], q0[kt * 8 + 4], q1[kt * 8 + 4]};
           const uint2 v0 = pbt[kt * 8], v1 = pbt[kt * 8 + 4];
           mma_bf16_16816(acc, Af, v0.x, v1.x);
@@ -843,6 +879,7 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
 #undef TX_C
 #undef TX_DZ
 #undef TX_E
+#undef GEO
 }
 
 // ==========================================================================================
@@ -890,9 +927,8 @@ struct BGeom {
   int smem;
 };
 
-bool dec_bgeom(const las_dec_args* a, int NB, BGeom& g) {
-  const int Hd = a->Hd, O = a->O, A = a->A, Te = a->Te;
-  if (Hd % 64 != 0 || Hd > 320 || O % 16 != 0 || A % 16 != 0 || A > 512 || a->C > 16 || Te > kBT) return false;
+constexpr bool dec_bgeom_c(int Hd, int O, int A, int Te, int C, int K, int NB, BGeom& g) {
+  if (Hd % 64 != 0 || Hd > 320 || O % 16 != 0 || A % 16 != 0 || A > 512 || C > 16 || Te > kBT) return false;
   g.NB = NB; g.G = kCS / NB;
   g.UPC = Hd / kCS; g.OPC = O / kCS; g.RPC = g.UPC + g.OPC;
   if (g.RPC * NB > kBT) return false;
@@ -909,23 +945,23 @@ bool dec_bgeom(const las_dec_args* a, int NB, BGeom& g) {
   if (g.TT > kBW) return false;
   g.WPT = kBW / g.TT;
   g.NTW2 = (g.KTa + g.WPT - 1) / g.WPT;
-  g.KTo = O / 16; g.AT8 = A / 8; g.NC = a->C > 8 ? 2 : 1;
-  const int ksz = 2 * a->K + 1;
+  g.KTo = O / 16; g.AT8 = A / 8; g.NC = C > 8 ? 2 : 1;
+  const int ksz = 2 * K + 1;
   g.NT8 = (ksz + 7) / 8;
   g.Pld = A + ((8 - A % 16) + 16) % 16;
   g.Qld = O + ((8 - O % 16) + 16) % 16;
   int off = 0;
   auto take = [&](int bytes) { const int o = off; off += rup(bytes, 16); return o; };
   g.o_dgB = take(g.KSb * g.FB * 256);
-  g.o_red = take(kBW * 128 * 4);
-  g.o_redC = take(kBW * 128 * 4);
+  g.o_red = take(kBW * kRedLd * 4);
+  g.o_redC = take(kBW * kRedLd * 4);
   g.o_dcbuf = take(O * 4);
   g.o_P = take(g.TT * 16 * g.Pld * 2);
   g.o_Q = take(g.TT * 16 * g.Qld * 2);
   g.o_matt = take(g.AT8 * 32 * 16);
   g.o_matt2 = take(g.KTa * 2 * 32 * 8);
   g.o_cwB3 = take(g.NT8 * 32 * 16);
-  g.o_dwnrx = take(2 * g.G * Te * 4);
+  g.o_dwnrx = take(2 * g.G * rup(Te, 4) * 4);
   g.o_ddzrx = take(g.G * NB * A * 4);
   g.o_ddzB = take(g.KTap * 256);
   // rows of the saved activations, prefetched one step ahead: two buffers each
@@ -951,6 +987,16 @@ bool dec_bgeom(const las_dec_args* a, int NB, BGeom& g) {
   g.smem = off;
   return g.smem <= kSmemMax;
 }
+inline bool dec_bgeom(const las_dec_args* a, int NB, BGeom& g) {
+  return dec_bgeom_c(a->Hd, a->O, a->A, a->Te, a->C, a->K, NB, g);
+}
+constexpr BGeom make_static_bgeom() {
+  BGeom g{};
+  g.smem = dec_bgeom_c(kS_Hd, kS_O, kS_A, kS_Te, kS_C, kS_K, kS_NB, g) ? g.smem : -1;
+  return g;
+}
+constexpr BGeom kSB = make_static_bgeom();
+static_assert(kSB.smem > 0, "static backward geometry must fit");
 
 struct DecBwdP {
   int B, L, Te, Hd, O, A, C, K;
@@ -972,6 +1018,7 @@ struct DecBwdP {
   long long* dbg;
 };
 
+template <bool kS>
 __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_constant__ DecBwdP p_in) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ DecBwdP p;
@@ -984,41 +1031,43 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
   }
   __syncthreads();
   const BGeom& g = p.g;
+#define GEO(x) (kS ? kSB.x : g.x)
   uint64_t* b_dg = bars; uint64_t* b_dc = bars + 1; uint64_t* b_ddz = bars + 2; uint64_t* b_dwn = bars + 3;
-  uint32_t* dgB = reinterpret_cast<uint32_t*>(smem + g.o_dgB);     // [KSb*FB][32][2] all-gathered dgates_{t+1}
-  float* red = reinterpret_cast<float*>(smem + g.o_red);           // [12][32][4] phase A partial sums
-  float* redC = reinterpret_cast<float*>(smem + g.o_redC);         // [12][32][4] phase C partial sums
-  float* dcbuf = reinterpret_cast<float*>(smem + g.o_dcbuf);       // [O] dc_t of my utterance
-  __nv_bfloat16* P_s = reinterpret_cast<__nv_bfloat16*>(smem + g.o_P);
-  __nv_bfloat16* Q_s = reinterpret_cast<__nv_bfloat16*>(smem + g.o_Q);   // [TT*16][Qld] my frames of Q
-  uint4* mattB = reinterpret_cast<uint4*>(smem + g.o_matt);        // [AT8][32]      k = channel, n = attention dim
-  uint2* mattB2 = reinterpret_cast<uint2*>(smem + g.o_matt2);      // [KTa][2][32]   k = attention dim, n = channel
-  uint4* cwB3 = reinterpret_cast<uint4*>(smem + g.o_cwB3);         // [NT8][32] conv-weight B fragments: k = channel, n = tap (hi0, hi1, lo0, lo1)
-  float* dwn_part = reinterpret_cast<float*>(smem + g.o_dwnpart);  // [kBT/Te][Te]
-  float* dwn_rx = reinterpret_cast<float*>(smem + g.o_dwnrx);      // [2][G][Te]
-  float* ddz_rx = reinterpret_cast<float*>(smem + g.o_ddzrx);      // [G][NB][A] f32 partials (owner partials cancel: bf16 is not enough)
-  uint32_t* ddzB = reinterpret_cast<uint32_t*>(smem + g.o_ddzB);   // [KTap][32][2]
-  float* wt_s2 = reinterpret_cast<float*>(smem + g.o_wt);          // [2][Te (padded to 16 B)] w_t
-  float* cpre_s2 = reinterpret_cast<float*>(smem + g.o_cpre);      // [2][O]
-  float* dzv2 = reinterpret_cast<float*>(smem + g.o_dzv);          // [2][A]
-  float* conv_s2 = reinterpret_cast<float*>(smem + g.o_conv);      // [2][TT*16][16] conv features of the step; reused for its dconv
-  float* de_s = reinterpret_cast<float*>(smem + g.o_de);           // [TT*16]
-  float* dwpart = reinterpret_cast<float*>(smem + g.o_dwpart);     // [WPT][TT*16]
-  float* dwn_s = reinterpret_cast<float*>(smem + g.o_dwns);        // [Te]
-  float* dwn_out = reinterpret_cast<float*>(smem + g.o_dwnout);    // [Te]
-  float* gv_s = reinterpret_cast<float*>(smem + g.o_gv);
-  float* wred = reinterpret_cast<float*>(smem + g.o_wred);
-  float* ddz_part = reinterpret_cast<float*>(smem + g.o_scratch);  // [TT][A]
-  float4* dcred = reinterpret_cast<float4*>(smem + g.o_scratch + g.TT * p.A * 4);   // [12][2][32]
-  float* Gs = reinterpret_cast<float*>(smem + g.o_scratch);        // [GR][Gld] skewed G tile (after ddz_part / dcred are consumed)
+  uint32_t* dgB = reinterpret_cast<uint32_t*>(smem + GEO(o_dgB));     // [KSb*FB][32][2] all-gathered dgates_{t+1}
+  float* red = reinterpret_cast<float*>(smem + GEO(o_red));           // [12][32][4] phase A partial sums
+  float* redC = reinterpret_cast<float*>(smem + GEO(o_redC));         // [12][32][4] phase C partial sums
+  float* dcbuf = reinterpret_cast<float*>(smem + GEO(o_dcbuf));       // [O] dc_t of my utterance
+  __nv_bfloat16* P_s = reinterpret_cast<__nv_bfloat16*>(smem + GEO(o_P));
+  __nv_bfloat16* Q_s = reinterpret_cast<__nv_bfloat16*>(smem + GEO(o_Q));   // [TT*16][Qld] my frames of Q
+  uint4* mattB = reinterpret_cast<uint4*>(smem + GEO(o_matt));        // [AT8][32]      k = channel, n = attention dim
+  uint2* mattB2 = reinterpret_cast<uint2*>(smem + GEO(o_matt2));      // [KTa][2][32]   k = attention dim, n = channel
+  uint4* cwB3 = reinterpret_cast<uint4*>(smem + GEO(o_cwB3));         // [NT8][32] conv-weight B fragments: k = channel, n = tap (hi0, hi1, lo0, lo1)
+  float* dwn_part = reinterpret_cast<float*>(smem + GEO(o_dwnpart));  // [kBT/Te][Te]
+  float* dwn_rx = reinterpret_cast<float*>(smem + GEO(o_dwnrx));      // [2][G][Te]
+  float* ddz_rx = reinterpret_cast<float*>(smem + GEO(o_ddzrx));      // [G][NB][A] f32 partials (owner partials cancel: bf16 is not enough)
+  uint32_t* ddzB = reinterpret_cast<uint32_t*>(smem + GEO(o_ddzB));   // [KTap][32][2]
+  float* wt_s2 = reinterpret_cast<float*>(smem + GEO(o_wt));          // [2][Te (padded to 16 B)] w_t
+  float* cpre_s2 = reinterpret_cast<float*>(smem + GEO(o_cpre));      // [2][O]
+  float* dzv2 = reinterpret_cast<float*>(smem + GEO(o_dzv));          // [2][A]
+  float* conv_s2 = reinterpret_cast<float*>(smem + GEO(o_conv));      // [2][TT*16][16] conv features of the step; reused for its dconv
+  float* de_s = reinterpret_cast<float*>(smem + GEO(o_de));           // [TT*16]
+  float* dwpart = reinterpret_cast<float*>(smem + GEO(o_dwpart));     // [WPT][TT*16]
+  float* dwn_s = reinterpret_cast<float*>(smem + GEO(o_dwns));        // [Te]
+  float* dwn_out = reinterpret_cast<float*>(smem + GEO(o_dwnout));    // [Te]
+  float* gv_s = reinterpret_cast<float*>(smem + GEO(o_gv));
+  float* wred = reinterpret_cast<float*>(smem + GEO(o_wred));
+  float* ddz_part = reinterpret_cast<float*>(smem + GEO(o_scratch));  // [TT][A]
+  float4* dcred = reinterpret_cast<float4*>(smem + GEO(o_scratch) + GEO(TT) * (kS ? kS_A : p.A) * 4);   // [12][2][32]
+  float* Gs = reinterpret_cast<float*>(smem + GEO(o_scratch));        // [GR][Gld] skewed G tile (after ddz_part / dcred are consumed)
 
   const int tid = threadIdx.x, lane = tid & 31, gq = lane >> 2, tig = lane & 3;
   // provably warp-uniform warp index: everything derived from it (tile / split / role indices) can live in uniform registers
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const uint32_t rank = cluster_rank();
   const int cl = blockIdx.y;
-  const int NB = g.NB, G = g.G, UPC = g.UPC, OPC = g.OPC, RPC = g.RPC, TR = g.TR;
-  const int Hd = p.Hd, O = p.O, A = p.A, Te = p.Te, L = p.L, K = p.K, C = p.C;
+  const int NB = GEO(NB), G = GEO(G), UPC = GEO(UPC), OPC = GEO(OPC), RPC = GEO(RPC), TR = GEO(TR);
+  const int Hd = kS ? kS_Hd : p.Hd, O = kS ? kS_O : p.O, A = kS ? kS_A : p.A, K = kS ? kS_K : p.K;
+  const int Te = p.Te, L = p.L, C = p.C;
   const int ZC = Hd + O, R = L + 1, ksz = 2 * K + 1, A2 = A >> 1;
   const int n_own = rank / G, q = rank % G;
   const int b_own = cl * NB + n_own;
@@ -1028,39 +1077,39 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
   const float scal = p.att_scaling;
 
   // ---------------- resident weights (registers)
-  const int b_tile = warp / g.KSb, b_ks = warp % g.KSb;
-  const bool b_act = b_tile < g.MTb;
-  const int b_kt0 = b_ks * g.FB;
+  const int b_tile = warp / GEO(KSb), b_ks = warp % GEO(KSb);
+  const bool b_act = b_tile < GEO(MTb);
+  const int b_kt0 = b_ks * GEO(FB);
   uint4 Ab[kMaxFB];
 #pragma unroll
   for (int j = 0; j < kMaxFB; ++j) {
     Ab[j] = make_uint4(0u, 0u, 0u, 0u);
-    if (b_act && j < g.FB && b_kt0 + j < g.KTb)
+    if (b_act && j < GEO(FB) && b_kt0 + j < GEO(KTb))
       Ab[j] = __ldg(reinterpret_cast<const uint4*>(p.wrT_pk) +
-                    (static_cast<int64_t>(rank * g.MTb + b_tile) * g.KTb + b_kt0 + j) * 32 + lane);
+                    (static_cast<int64_t>(rank * GEO(MTb) + b_tile) * GEO(KTb) + b_kt0 + j) * 32 + lane);
   }
-  const int d_tile = warp / g.KSd, d_ks = warp % g.KSd;
-  const bool d_act = d_tile < g.MTd;
-  const int d_kt0 = d_ks * g.FD;
+  const int d_tile = warp / GEO(KSd), d_ks = warp % GEO(KSd);
+  const bool d_act = d_tile < GEO(MTd);
+  const int d_kt0 = d_ks * GEO(FD);
   uint4 Ad[kMaxFD2];
 #pragma unroll
   for (int j = 0; j < kMaxFD2; ++j) {
     Ad[j] = make_uint4(0u, 0u, 0u, 0u);
-    if (d_act && j < g.FD && d_kt0 + j < g.KTa)
+    if (d_act && j < GEO(FD) && d_kt0 + j < GEO(KTa))
       Ad[j] = __ldg(reinterpret_cast<const uint4*>(p.decT_pk) +
-                    (static_cast<int64_t>(rank * g.MTd + d_tile) * g.KTa + d_kt0 + j) * 32 + lane);
+                    (static_cast<int64_t>(rank * GEO(MTd) + d_tile) * GEO(KTa) + d_kt0 + j) * 32 + lane);
   }
-  const int nfb = g.FB, nfd = g.FD;
+  const int nfb = GEO(FB), nfd = GEO(FD);
 
   // ---------------- resident operands (shared memory)
-  for (int i = tid; i < g.KSb * g.FB * 64; i += kBT) dgB[i] = 0u;
-  for (int i = tid; i < g.KTap * 64; i += kBT) ddzB[i] = 0u;
-  for (int i = tid; i < 2 * G * Te; i += kBT) dwn_rx[i] = 0.f;
+  for (int i = tid; i < GEO(KSb) * GEO(FB) * 64; i += kBT) dgB[i] = 0u;
+  for (int i = tid; i < GEO(KTap) * 64; i += kBT) ddzB[i] = 0u;
+  for (int i = tid; i < 2 * G * ((Te + 3) & ~3); i += kBT) dwn_rx[i] = 0.f;
   for (int i = tid; i < G * NB * A; i += kBT) ddz_rx[i] = 0.f;
-  for (int i = tid; i < 2 * g.TT * 16 * 16; i += kBT) conv_s2[i] = 0.f;
-  for (int i = tid; i < g.TT * 16; i += kBT) de_s[i] = 0.f;
+  for (int i = tid; i < 2 * GEO(TT) * 16 * 16; i += kBT) conv_s2[i] = 0.f;
+  for (int i = tid; i < GEO(TT) * 16; i += kBT) de_s[i] = 0.f;
   for (int i = tid; i < A; i += kBT) gv_s[i] = p.gvec[i];
-  for (int i = tid; i < g.AT8 * 32; i += kBT) {
+  for (int i = tid; i < GEO(AT8) * 32; i += kBT) {
     const int nt = i >> 5, l = i & 31, a = 8 * nt + (l >> 2), c0 = 2 * (l & 3);
     float m[4];
 #pragma unroll
@@ -1073,7 +1122,7 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
     split_bf16x2(m[2], m[3], v.y, v.w);
     mattB[i] = v;
   }
-  for (int i = tid; i < g.KTa * 64; i += kBT) {
+  for (int i = tid; i < GEO(KTa) * 64; i += kBT) {
     // k = attention dim 16*kt + .., n = channel 8*nc + (l >> 2)
     const int kt = i >> 6, nc = (i >> 5) & 1, l = i & 31, c = 8 * nc + (l >> 2), a0 = 16 * kt + 2 * (l & 3);
     float m[4];
@@ -1084,7 +1133,7 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
     }
     mattB2[i] = make_uint2(pack_bf16x2(m[0], m[1]), pack_bf16x2(m[2], m[3]));
   }
-  for (int i = tid; i < g.NT8 * 32; i += kBT) {
+  for (int i = tid; i < GEO(NT8) * 32; i += kBT) {
     // k = channel 2*(l & 3) + {0, 1, 8, 9}, n = tap 8*nt + (l >> 2)
     const int nt = i >> 5, l = i & 31, m = 8 * nt + (l >> 2), c0 = 2 * (l & 3);
     float w[4];
@@ -1098,12 +1147,12 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
     split_bf16x2(w[2], w[3], v.y, v.w);
     cwB3[i] = v;
   }
-  for (int i = tid; i < g.TT * 16 * g.Pld; i += kBT) {
-    const int r = i / g.Pld, a = i % g.Pld;
+  for (int i = tid; i < GEO(TT) * 16 * GEO(Pld); i += kBT) {
+    const int r = i / GEO(Pld), a = i % GEO(Pld);
     P_s[i] = __float2bfloat16((r < ntl && a < A) ? p.P[(static_cast<int64_t>(b_own) * Te + te0 + r) * A + a] : 0.f);
   }
-  for (int i = tid; i < g.TT * 16 * g.Qld; i += kBT) {
-    const int r = i / g.Qld, o = i % g.Qld;
+  for (int i = tid; i < GEO(TT) * 16 * GEO(Qld); i += kBT) {
+    const int r = i / GEO(Qld), o = i % GEO(Qld);
     Q_s[i] = (r < ntl && o < O) ? p.Q[(static_cast<int64_t>(b_own) * Te + te0 + r) * O + o] : __float2bfloat16(0.f);
   }
 
@@ -1117,16 +1166,16 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
   const int u_e = rank * UPC + row_l;                    // hidden unit (is_z)
   const int o_e = rank * OPC + (row_l - UPC);            // context dim (!is_z)
   const int col_e = is_z ? u_e : Hd + o_e;               // column of [z; c]
-  const int a_w0 = (row_l >> 4) * g.KSb;                 // first contributing warp (phase A)
-  const int c_w0 = (row_l >> 4) * g.KSd;                 // first contributing warp (phase C, is_z rows)
+  const int a_w0 = (row_l >> 4) * GEO(KSb);                 // first contributing warp (phase A)
+  const int c_w0 = (row_l >> 4) * GEO(KSd);                 // first contributing warp (phase C, is_z rows)
   float dcell = 0.f, dz_acc = 0.f;
   const int bb = epi_ok ? b_e : 0;
   const float* dzc_ptr = p.dzc_all + (static_cast<int64_t>(bb) * R + L) * ZC + col_e;          // row t+1, t = L-1
   int64_t sv_idx = (static_cast<int64_t>(bb) * L + (L - 1)) * Hd + (is_z ? u_e : 0);           // gates / c_save of step t
   __nv_bfloat16* dg_ptr = p.dgates + (static_cast<int64_t>(bb) * R + (L - 1)) * 4 * Hd + (is_z ? u_e : 0);
   // phase B
-  const int e_tt = warp / g.WPT, e_wi = warp % g.WPT;
-  const bool e_act = warp < g.TT * g.WPT && ntl > 0;
+  const int e_tt = warp / GEO(WPT), e_wi = warp % GEO(WPT);
+  const bool e_act = warp < GEO(TT) * GEO(WPT) && ntl > 0;
   const int cm = te0 + 16 * e_tt;                        // first frame of my frame tile
   const int bo = own_ok ? b_own : 0;
   // cluster-mapped bases
@@ -1135,10 +1184,12 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
   const uint32_t bars_base = smem_u32(bars);      // b_dg +0, b_dc +8, b_ddz +16, b_dwn +24
   // bytes per barrier phase: dgates of all NB columns from all CTAs; dc of my utterance; ddz partials of every valid
   // owner; conv-input gradient partials of my utterance's owners
-#define TX_DG (8u * p.Hd * g.NB)
-#define TX_DC (4u * p.O)
-#define TX_DDZ (4u * p.A * g.G * max(0, min(g.NB, p.B - static_cast<int>(blockIdx.y) * g.NB)))
-#define TX_DWN (4u * p.Te * g.G)
+  // dgates, ddz and the conv-input gradient travel as bulk copies from the sender's own slice (its local copy is written
+  // directly): every barrier counts the bytes of the OTHER contributors only
+#define TX_DG ((kCS - 1u) * (GEO(UPC) / 4) * 256u)
+#define TX_DC (4u * O)
+#define TX_DDZ (4u * A * (GEO(G) * max(0, min(GEO(NB), p.B - static_cast<int>(blockIdx.y) * GEO(NB))) - (own_ok ? 1 : 0)))
+#define TX_DWN (4u * ((p.Te + 3) & ~3) * (GEO(G) - 1))
   if (tid == 0) {
     const uint32_t tx_dg = TX_DG, tx_dc = TX_DC, tx_ddz = TX_DDZ, tx_dwn = TX_DWN;
     mbar_arrive_expect_tx(b_dg, tx_dg);        // dgates_{L-1}, sent at C(L-1)
@@ -1157,7 +1208,7 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
   // Saved activations of a step (rows of ws, cpre, dzf, conv_save) are fetched with cp.async ONE STEP AHEAD into the
   // other half of a double buffer: waiting for them inside the step put an L2/HBM round trip in front of phase A's
   // block barrier every step.
-  const int wt_ld = (Te + 3) & ~3, cv_ld = g.TT * 16 * 16;
+  const int wt_ld = (Te + 3) & ~3, cv_ld = GEO(TT) * 16 * 16, Tep = (Te + 3) & ~3;
   auto prefetch_rows = [&](int ts) {
     if (own_ok && ts >= 0) {
       const int hb = ts & 1;
@@ -1205,6 +1256,7 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
       mbar_wait_tag(b_dg, ph ^ 1u, 10);            // dgates_{t+1} (sent at C(t+1)) complete in dgB
       if (tid == 0) mbar_arrive_expect_tx(b_dg, TX_DG);     // next phase: the dgates_t sends of this step's phase C
     }
+    DTRACE(9);
     if (b_act) {
       float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
       const uint2* hb = reinterpret_cast<const uint2*>(dgB) + lane + b_kt0 * 32;
@@ -1217,13 +1269,15 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
           else mma_bf16_16816(acc0, Af, b.x, b.y);
         }
       }
-      reinterpret_cast<float4*>(red)[warp * 32 + lane] =
-          make_float4(acc0[0] + acc1[0], acc0[1] + acc1[1], acc0[2] + acc1[2], acc0[3] + acc1[3]);
+      const float accs[4] = {acc0[0] + acc1[0], acc0[1] + acc1[1], acc0[2] + acc1[2], acc0[3] + acc1[3]};
+      red_store(red, warp, gq, tig, accs);
     }
+    DTRACE(10);
     cp_async_wait_n<1>();   // this step's rows (fetched during the previous step) have landed; the next step's may be in flight
     __syncthreads();      // partial sums in `red`; the prefetched rows are visible to every thread
+    DTRACE(11);
     if (epi_ok) {
-      float mm = red_gather(red, a_w0, g.KSb, row_l & 15, n_e);
+      float mm = red_gather(red, a_w0, GEO(KSb), row_l & 15, n_e);
       if (p.drop_p > 0.f && !is_z)   // the path through the cell input of step t+1 carries that step's dropout mask
         mm = dropout_keep(*p.seed_dev, p.drop_site, (static_cast<unsigned long long>(b_e) * R + t + 1) * O + o_e, p.drop_p)
                  ? mm / (1.f - p.drop_p) : 0.f;
@@ -1261,7 +1315,7 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
         for (int o2 = tid + kBT; o2 < O; o2 += kBT) part = fmaf(dcbuf[o2], cpre_s[o2], part);
         if (tid < Te) {
           float dn = 0.f;
-          for (int qq = 0; qq < G; ++qq) dn += dwn_rx[(par * G + qq) * Te + tid];
+          for (int qq = 0; qq < G; ++qq) dn += dwn_rx[(par * G + qq) * Tep + tid];
           dwn_s[tid] = dn;
           part = fmaf(wt_s[tid], dn, part);
         }
@@ -1271,9 +1325,9 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
     }
     if (e_act) {
       float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
-      const uint32_t* q0 = reinterpret_cast<const uint32_t*>(Q_s + (16 * e_tt + gq) * g.Qld) + tig;
-      const uint32_t* q1 = reinterpret_cast<const uint32_t*>(Q_s + (16 * e_tt + gq + 8) * g.Qld) + tig;
-      for (int kt = e_wi; kt < g.KTo; kt += g.WPT) {
+      const uint32_t* q0 = reinterpret_cast<const uint32_t*>(Q_s + (16 * e_tt + gq) * GEO(Qld)) + tig;
+      const uint32_t* q1 = reinterpret_cast<const uint32_t*>(Q_s + (16 * e_tt + gq + 8) * GEO(Qld)) + tig;
+      for (int kt = e_wi; kt < GEO(KTo); kt += GEO(WPT)) {
         const uint32_t Af[4] = {q0[kt * 8], q1[kt * 8], q0[kt * 8 + 4], q1[kt * 8 + 4]};
         uint32_t bh0 = 0u, bh1 = 0u, bl0 = 0u, bl1 = 0u;
         if (gq == 0) {
@@ -1286,17 +1340,17 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
         mma_bf16_16816(acc1, Af, bl0, bl1);
       }
       if (tig == 0) {
-        dwpart[e_wi * g.TT * 16 + 16 * e_tt + gq] = acc0[0] + acc1[0];
-        dwpart[e_wi * g.TT * 16 + 16 * e_tt + gq + 8] = acc0[2] + acc1[2];
+        dwpart[e_wi * GEO(TT) * 16 + 16 * e_tt + gq] = acc0[0] + acc1[0];
+        dwpart[e_wi * GEO(TT) * 16 + 16 * e_tt + gq + 8] = acc0[2] + acc1[2];
       }
     }
     __syncthreads();
     // B2: de = scal * w_t * (dw - <w_t, dw>)
-    if (tid < g.TT * 16) {
+    if (tid < GEO(TT) * 16) {
       float de = 0.f;
       if (tid < ntl) {
         float dw = dwn_s[te0 + tid];
-        for (int w = 0; w < g.WPT; ++w) dw += dwpart[w * g.TT * 16 + tid];
+        for (int w = 0; w < GEO(WPT); ++w) dw += dwpart[w * GEO(TT) * 16 + tid];
         float dot = 0.f;
 #pragma unroll
         for (int w = 0; w < kBW; ++w) dot += wred[w];
@@ -1323,10 +1377,10 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
       }
       const float de0 = de_s[r0], de1 = de_s[r1];
       float dcv0[4] = {0.f, 0.f, 0.f, 0.f}, dcv1[4] = {0.f, 0.f, 0.f, 0.f};
-      const __nv_bfloat16* P0 = P_s + r0 * g.Pld + 2 * tig;
-      const __nv_bfloat16* P1 = P_s + r1 * g.Pld + 2 * tig;
-      const int kt_end = min((e_wi + 1) * g.NTW2, g.KTa);
-      for (int kt2 = e_wi * g.NTW2; kt2 < kt_end; ++kt2) {
+      const __nv_bfloat16* P0 = P_s + r0 * GEO(Pld) + 2 * tig;
+      const __nv_bfloat16* P1 = P_s + r1 * GEO(Pld) + 2 * tig;
+      const int kt_end = min((e_wi + 1) * GEO(NTW2), GEO(KTa));
+      for (int kt2 = e_wi * GEO(NTW2); kt2 < kt_end; ++kt2) {
         uint32_t Dh[4], Dl[4];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -1355,7 +1409,7 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
         const uint2 b0 = mattB2[(kt2 * 2) * 32 + lane];
         mma_bf16_16816(dcv0, Dh, b0.x, b0.y);
         mma_bf16_16816(dcv0, Dl, b0.x, b0.y);
-        if (g.NC > 1) {
+        if (GEO(NC) > 1) {
           const uint2 b1 = mattB2[(kt2 * 2 + 1) * 32 + lane];
           mma_bf16_16816(dcv1, Dh, b1.x, b1.y);
           mma_bf16_16816(dcv1, Dl, b1.x, b1.y);
@@ -1371,21 +1425,19 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
       for (int aq = tid; aq < (A >> 2); aq += kBT) {      // 4 attention dims per thread: 16-byte remote stores
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (ntl > 0)
-          for (int tt = 0; tt < g.TT; ++tt) {
+          for (int tt = 0; tt < GEO(TT); ++tt) {
             const float4 x = *reinterpret_cast<const float4*>(ddz_part + tt * A + 4 * aq);
             v.x += x.x; v.y += x.y; v.z += x.z; v.w += x.w;
           }
-        const uint32_t off = ddzrx_base + 4u * ((q * NB + n_own) * A + 4 * aq);
-        const uint4 vb = make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
-#pragma unroll
-        for (int r = 0; r < kCS; ++r) st_async_v4(mapa_u32(off, r), vb, mapa_u32(bars_base + 16u, r));
+        *reinterpret_cast<float4*>(ddz_rx + (q * NB + n_own) * A + 4 * aq) = v;      // my own slot, locally
       }
+      fence_proxy_async_smem();     // ... which the bulk copies below read through the async proxy
     }
     if (e_act && e_wi == 0) {
       // dconv of my frame tile: sum of the partials of the WPT warps -> conv_s (reused) and dattc_all
       float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int w = 0; w < g.WPT; ++w) {
-        const float4 a = dcred[((e_tt * g.WPT + w) * 2) * 32 + lane], b = dcred[((e_tt * g.WPT + w) * 2 + 1) * 32 + lane];
+      for (int w = 0; w < GEO(WPT); ++w) {
+        const float4 a = dcred[((e_tt * GEO(WPT) + w) * 2) * 32 + lane], b = dcred[((e_tt * GEO(WPT) + w) * 2 + 1) * 32 + lane];
         s0.x += a.x; s0.y += a.y; s0.z += a.z; s0.w += a.w;
         s1.x += b.x; s1.y += b.y; s1.z += b.z; s1.w += b.w;
       }
@@ -1410,17 +1462,23 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
       }
     }
     __syncthreads();      // dconv of all my frames in conv_s; ddz_part / dcred are free (Gs aliases them)
+    DTRACE(12);
+    if (own_ok && warp == 0 && lane < kCS && lane != static_cast<int>(rank)) {
+      // my ddz partial -> the same slot of every other CTA: one 4A-byte bulk copy per peer (was A/4 x 16 st.async)
+      const uint32_t off = ddzrx_base + 4u * ((q * NB + n_own) * A);
+      dsmem_bulk_copy(mapa_u32(off, lane), off, 4u * A, mapa_u32(bars_base + 16u, lane));
+    }
     // conv-input gradient of my frames for step t-1: dwn[j] = sum_{tl,c} dconv[tl][c] cw[c][j - (te0+tl) + K].
     // G[tl][m] = sum_c dconv[tl][c] cw[c][m] on tensor cores (GR rows of G per pass), stored at column
     // j = m + te0 + tl - K; thread (gi, j) then adds its rows tl = gi, gi + ngrp, .. in a fixed order.
     const int ngrp = max(1, kBT / Te);
     if (own_ok && t > 0 && ntl > 0) {
       const int gi = tid / Te, j = tid - gi * Te;
-      const int mtp = g.GR >> 4;                 // m-tiles per pass
+      const int mtp = GEO(GR) >> 4;                 // m-tiles per pass
       const int wm = warp % mtp, wn = warp / mtp, nws = kBW / mtp;
       float sacc = 0.f;
-      for (int r_base = 0; r_base < g.TT * 16; r_base += g.GR) {
-        if (r_base + 16 * wm < g.TT * 16) {
+      for (int r_base = 0; r_base < GEO(TT) * 16; r_base += GEO(GR)) {
+        if (r_base + 16 * wm < GEO(TT) * 16) {
           const int r0 = r_base + 16 * wm + gq, r1 = r0 + 8;
           uint32_t Ah[4], Al[4];
           {
@@ -1434,9 +1492,9 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
             split_bf16x2(v3.x, v3.y, Ah[3], Al[3]);
           }
           // column of element (row r, tap m): j = m + te0 + r - K
-          float* g0 = Gs + (r0 - r_base) * g.Gld + (te0 + r0 - K);
-          float* g1 = Gs + (r1 - r_base) * g.Gld + (te0 + r1 - K);
-          for (int nt = wn; nt < g.NT8; nt += nws) {
+          float* g0 = Gs + (r0 - r_base) * GEO(Gld) + (te0 + r0 - K);
+          float* g1 = Gs + (r1 - r_base) * GEO(Gld) + (te0 + r1 - K);
+          for (int nt = wn; nt < GEO(NT8); nt += nws) {
             const uint4 bw = cwB3[nt * 32 + lane];
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
             mma_bf16_16816(acc, Ah, bw.x, bw.y);
@@ -1456,31 +1514,29 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
         }
         __syncthreads();
         if (tid < ngrp * Te) {
-          const int r_end = min(r_base + g.GR, ntl);
-          // first row >= r_base of my residue class
-          int tl = r_base + ((gi - r_base % ngrp) + ngrp) % ngrp;
-          for (; tl < r_end; tl += ngrp) {
-            const int k = j - (te0 + tl) + K;
-            if (k >= 0 && k <= 2 * K) sacc += Gs[(tl - r_base) * g.Gld + j];
-          }
+          // rows of this pass whose taps reach column j: te0 + tl in [j - K, j + K]; my residue class tl % ngrp == gi
+          const int lo_tl = max(r_base, j - te0 - K), hi_tl = min(min(r_base + GEO(GR), ntl) - 1, j - te0 + K);
+          int tl = lo_tl + ((gi - lo_tl) % ngrp + ngrp) % ngrp;
+          const float* gp = Gs + (tl - r_base) * GEO(Gld) + j;
+          for (; tl <= hi_tl; tl += ngrp, gp += ngrp * GEO(Gld)) sacc += *gp;
         }
         __syncthreads();
       }
       if (tid < ngrp * Te) dwn_part[gi * Te + j] = sacc;
     }
+    DTRACE(13);
     __syncthreads();
+    DTRACE(14);
     if (own_ok && t > 0) {
-      // partial conv-input gradient -> every owner of this utterance (slot q, parity of step t-1)
-      for (int j = tid; j < Te; j += kBT) {
+      // partial conv-input gradient -> slot q (parity of step t-1) of every owner of this utterance: written into my own
+      // copy here, bulk-copied to the sibling owners after the next block barrier (phase C)
+      for (int j = tid; j < Tep; j += kBT) {
         float v = 0.f;
-        if (ntl > 0)
+        if (ntl > 0 && j < Te)
           for (int gi = 0; gi < ngrp; ++gi) v += dwn_part[gi * Te + j];
-        for (int qq = 0; qq < G; ++qq) {
-          const uint32_t dst = n_own * G + qq;
-          st_async_b32(mapa_u32(dwnrx_base + 4u * (((par ^ 1) * G + q) * Te + j), dst), __float_as_uint(v),
-                       mapa_u32(bars_base + 24u, dst));
-        }
+        dwn_rx[((par ^ 1) * G + q) * Tep + j] = v;
       }
+      fence_proxy_async_smem();
     }
     DTRACE(5);
 
@@ -1501,6 +1557,11 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
         *reinterpret_cast<float2*>(p.ddz_all + (static_cast<int64_t>(b) * R + t + 1) * A + 2 * ap) = make_float2(v0, v1);
     }
     __syncthreads();
+    if (own_ok && t > 0 && warp == 1 && lane < G && lane != q) {
+      const uint32_t off = dwnrx_base + 4u * (((par ^ 1) * G + q) * Tep);
+      const uint32_t dst = n_own * G + lane;
+      dsmem_bulk_copy(mapa_u32(off, dst), off, 4u * Tep, mapa_u32(bars_base + 24u, dst));
+    }
     if (d_act) {
       float acc[4] = {0.f, 0.f, 0.f, 0.f};
       const uint2* hb = reinterpret_cast<const uint2*>(ddzB) + lane + d_kt0 * 32;
@@ -1512,13 +1573,13 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
           mma_bf16_16816(acc, Af, b.x, b.y);
         }
       }
-      reinterpret_cast<float4*>(redC)[warp * 32 + lane] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      red_store(redC, warp, gq, tig, acc);
     }
     __syncthreads();
     uint32_t w4[4] = {0u, 0u, 0u, 0u};
     {
       if (epi_ok && is_z) {
-        const float dh = dz_acc + red_gather(redC, c_w0, g.KSd, row_l & 15, n_e);
+        const float dh = dz_acc + red_gather(redC, c_w0, GEO(KSd), row_l & 15, n_e);
         const float2 if_ = __half22float2(*reinterpret_cast<const __half2*>(&gpk.x));
         const float2 go_ = __half22float2(*reinterpret_cast<const __half2*>(&gpk.y));
         const float i = if_.x, f = if_.y, gc = go_.x, o = go_.y;
@@ -1540,12 +1601,18 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
         for (int k = 0; k < 4; ++k) wd[k] = w4[k] | (__shfl_down_sync(0xffffffffu, w4[k], 1) << 16);
         if (epi && is_z && (row_l & 1) == 0) {
           const int kt = u_e >> 2, pp = (u_e >> 1) & 1;
-          const uint32_t off = dgB_base + 4u * static_cast<uint32_t>((kt * 32 + n_e * 4 + 2 * pp) * 2);
-          const uint4 vd = make_uint4(wd[0], wd[1], wd[2], wd[3]);
-#pragma unroll
-          for (int r = 0; r < kCS; ++r) st_async_v4(mapa_u32(off, r), vd, mapa_u32(bars_base, r));
+          // my own slice of dgB (the k-tiles of my hidden units: contiguous), written locally
+          *reinterpret_cast<uint4*>(dgB + (kt * 32 + n_e * 4 + 2 * pp) * 2) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
         }
       }
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (warp == 0 && lane < kCS && lane != static_cast<int>(rank)) {
+      // dgates_t of my units -> the same slice of every other CTA: one bulk copy per peer (was UPC/2 * NB x 16 st.async)
+      const uint32_t slice = (UPC / 4) * 256u;
+      const uint32_t off = dgB_base + rank * slice;
+      dsmem_bulk_copy(mapa_u32(off, lane), off, slice, mapa_u32(bars_base, lane));
     }
     DTRACE(7);
     if (epi_ok && is_z) {
@@ -1561,6 +1628,7 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
 #undef TX_DC
 #undef TX_DDZ
 #undef TX_DWN
+#undef GEO
 }
 
 // A[row i][k] = W[k*ld + col(i)] for the rows a CTA owns in the backward kernel:
@@ -1605,9 +1673,16 @@ __global__ void pack_rowsel_kernel(const float* __restrict__ W, int64_t ld, int 
 }
 
 bool g_dec_persist_checked = false;
+unsigned long long g_dec_static_launches = 0, g_dec_generic_launches = 0;   // path counters (las_path_counters)
 int g_dec_persist_clusters = 0;   // co-resident 16-CTA clusters the device offers (0 = unavailable)
 
 }  // namespace
+
+// Is this problem served by the kernels instantiated on the compile-time geometry (kSF / kSB)?
+static bool use_static_geom(const las_dec_args* a, int nb) {
+  return nb == kS_NB && a->Hd == kS_Hd && a->O == kS_O && a->A == kS_A && a->K == kS_K && a->C > 8 && a->C <= 16 &&
+         a->Te <= kS_Te && getenv("LAS_DEC_NO_STATIC") == nullptr;
+}
 
 // Utterances per cluster for a batch of B: the smallest power of two for which all clusters are
 // co-resident (a second wave doubles the latency of the whole loop), capped by shared memory.
@@ -1632,8 +1707,8 @@ int dec_persist_supported(const las_dec_args* a) {
     // does the device schedule a 16-CTA (non-portable) cluster of this kernel at all?
     g_dec_persist_checked = true;
     g_dec_persist_clusters = 0;
-    if (cudaFuncSetAttribute(dec_persist_fwd_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
-        cudaFuncSetAttribute(dec_persist_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax) == cudaSuccess) {
+    if (cudaFuncSetAttribute(dec_persist_fwd_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+        cudaFuncSetAttribute(dec_persist_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax) == cudaSuccess) {
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(kCS, 1, 1);
       cfg.blockDim = dim3(kThreads);
@@ -1646,7 +1721,7 @@ int dec_persist_supported(const las_dec_args* a) {
       cfg.attrs = at;
       cfg.numAttrs = 1;
       int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, dec_persist_fwd_kernel, &cfg) == cudaSuccess) g_dec_persist_clusters = n;
+      if (cudaOccupancyMaxActiveClusters(&n, dec_persist_fwd_kernel<false>, &cfg) == cudaSuccess) g_dec_persist_clusters = n;
     }
     (void)cudaGetLastError();
   }
@@ -1677,10 +1752,14 @@ int dec_persist_bwd(const las_dec_args* a, cudaStream_t stream) {
               "persistent decoder backward: missing buffers");
   static bool attr_set = false;
   if (!attr_set) {
-    LAS_CUDA(cudaFuncSetAttribute(dec_persist_bwd_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    LAS_CUDA(cudaFuncSetAttribute(dec_persist_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+    LAS_CUDA(cudaFuncSetAttribute(dec_persist_bwd_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    LAS_CUDA(cudaFuncSetAttribute(dec_persist_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+    LAS_CUDA(cudaFuncSetAttribute(dec_persist_bwd_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    LAS_CUDA(cudaFuncSetAttribute(dec_persist_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     attr_set = true;
   }
+  const bool stat = use_static_geom(a, nb);
+  if (stat) bg = kSB;
   DecBwdP p;
   p.B = a->B; p.L = a->L; p.Te = a->Te; p.Hd = a->Hd; p.O = a->O; p.A = a->A; p.C = a->C; p.K = a->K;
   p.att_scaling = a->att_scaling;
@@ -1697,7 +1776,9 @@ int dec_persist_bwd(const las_dec_args* a, cudaStream_t stream) {
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute at[1];
   cluster_cfg(cfg, at, (a->B + nb - 1) / nb, kBT, bg.smem, stream);
-  LAS_CUDA(cudaLaunchKernelEx(&cfg, dec_persist_bwd_kernel, p));
+  if (stat) LAS_CUDA(cudaLaunchKernelEx(&cfg, dec_persist_bwd_kernel<true>, p));
+  else LAS_CUDA(cudaLaunchKernelEx(&cfg, dec_persist_bwd_kernel<false>, p));
+  ++(stat ? g_dec_static_launches : g_dec_generic_launches);
   ++g_launches;
   return 0;
 }
@@ -1733,10 +1814,14 @@ int dec_persist_fwd(const las_dec_args* a, cudaStream_t stream) {
   LAS_REQUIRE(nb > 0, "persistent decoder: unsupported geometry");
   static bool attr_set = false;
   if (!attr_set) {
-    LAS_CUDA(cudaFuncSetAttribute(dec_persist_fwd_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    LAS_CUDA(cudaFuncSetAttribute(dec_persist_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+    LAS_CUDA(cudaFuncSetAttribute(dec_persist_fwd_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    LAS_CUDA(cudaFuncSetAttribute(dec_persist_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+    LAS_CUDA(cudaFuncSetAttribute(dec_persist_fwd_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    LAS_CUDA(cudaFuncSetAttribute(dec_persist_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     attr_set = true;
   }
+  const bool stat = use_static_geom(a, nb);
+  if (stat) g = kSF;
   DecFwdP p;
   p.B = a->B; p.L = a->L; p.Te = a->Te; p.Hd = a->Hd; p.O = a->O; p.A = a->A; p.C = a->C; p.K = a->K;
   p.att_scaling = a->att_scaling;
@@ -1761,7 +1846,9 @@ int dec_persist_fwd(const las_dec_args* a, cudaStream_t stream) {
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  LAS_CUDA(cudaLaunchKernelEx(&cfg, dec_persist_fwd_kernel, p));
+  if (stat) LAS_CUDA(cudaLaunchKernelEx(&cfg, dec_persist_fwd_kernel<true>, p));
+  else LAS_CUDA(cudaLaunchKernelEx(&cfg, dec_persist_fwd_kernel<false>, p));
+  ++(stat ? g_dec_static_launches : g_dec_generic_launches);
   ++g_launches;
   return 0;
 }

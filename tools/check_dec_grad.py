@@ -74,4 +74,6 @@ if os.environ.get("LAS_TRACE"):
         row, nxt = d[w, 1], d[w, 2]
         if int(row[0]) == 0:
             continue
-        print(f"{w:4d} " + " ".join(f"{int(row[i + 1] - row[i]):11d}" for i in range(8)) + f" | {int(nxt[0] - row[0]):8d}")
+        print(f"{w:4d} " + " ".join(f"{int(row[i + 1] - row[i]):11d}" for i in range(8)) + f" | {int(nxt[0] - row[0]):8d}"
+              + f" | A: wait-dg {int(row[9] - row[0])} mma {int(row[10] - row[9])} sync {int(row[11] - row[10])} epi {int(row[1] - row[11])}"
+              + f" | B4: ddz+dconv {int(row[12] - row[4])} G-passes {int(row[13] - row[12])} sync {int(row[14] - row[13])} dwn-out {int(row[5] - row[14])}")
