@@ -1494,22 +1494,40 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
           // column of element (row r, tap m): j = m + te0 + r - K
           float* g0 = Gs + (r0 - r_base) * GEO(Gld) + (te0 + r0 - K);
           float* g1 = Gs + (r1 - r_base) * GEO(Gld) + (te0 + r1 - K);
-          for (int nt = wn; nt < GEO(NT8); nt += nws) {
+          // taps m with 0 <= m + cb < Te (cb = te0 + r - K) and m < ksz, as one unsigned range check per element
+          const int cb0 = te0 + r0 - K, cb1 = te0 + r1 - K;
+          const unsigned lim0 = r0 < ntl ? static_cast<unsigned>(Te) : 0u, lim1 = r1 < ntl ? static_cast<unsigned>(Te) : 0u;
+          auto put = [&](int nt, const float (&acc)[4]) {
+            const int m0 = 8 * nt + 2 * tig;
+            if (m0 < ksz) {
+              if (static_cast<unsigned>(m0 + cb0) < lim0) g0[m0] = acc[0];
+              if (static_cast<unsigned>(m0 + cb1) < lim1) g1[m0] = acc[2];
+            }
+            if (m0 + 1 < ksz) {
+              if (static_cast<unsigned>(m0 + 1 + cb0) < lim0) g0[m0 + 1] = acc[1];
+              if (static_cast<unsigned>(m0 + 1 + cb1) < lim1) g1[m0 + 1] = acc[3];
+            }
+          };
+          int nt = wn;
+          for (; nt + nws < GEO(NT8); nt += 2 * nws) {      // two independent n-tiles in flight
+            const uint4 bw = cwB3[nt * 32 + lane], bv = cwB3[(nt + nws) * 32 + lane];
+            float acc[4] = {0.f, 0.f, 0.f, 0.f}, acd[4] = {0.f, 0.f, 0.f, 0.f};
+            mma_bf16_16816(acc, Ah, bw.x, bw.y);
+            mma_bf16_16816(acd, Ah, bv.x, bv.y);
+            mma_bf16_16816(acc, Al, bw.x, bw.y);
+            mma_bf16_16816(acd, Al, bv.x, bv.y);
+            mma_bf16_16816(acc, Ah, bw.z, bw.w);
+            mma_bf16_16816(acd, Ah, bv.z, bv.w);
+            put(nt, acc);
+            put(nt + nws, acd);
+          }
+          if (nt < GEO(NT8)) {
             const uint4 bw = cwB3[nt * 32 + lane];
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
             mma_bf16_16816(acc, Ah, bw.x, bw.y);
             mma_bf16_16816(acc, Al, bw.x, bw.y);
             mma_bf16_16816(acc, Ah, bw.z, bw.w);
-            const int m0 = 8 * nt + 2 * tig;
-            const int j0 = m0 + te0 + r0 - K, j1 = m0 + te0 + r1 - K;
-            if (r0 < ntl) {
-              if (m0 < ksz && j0 >= 0 && j0 < Te) g0[m0] = acc[0];
-              if (m0 + 1 < ksz && j0 + 1 >= 0 && j0 + 1 < Te) g0[m0 + 1] = acc[1];
-            }
-            if (r1 < ntl) {
-              if (m0 < ksz && j1 >= 0 && j1 < Te) g1[m0] = acc[2];
-              if (m0 + 1 < ksz && j1 + 1 >= 0 && j1 + 1 < Te) g1[m0 + 1] = acc[3];
-            }
+            put(nt, acc);
           }
         }
         __syncthreads();
@@ -1518,7 +1536,13 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
           const int lo_tl = max(r_base, j - te0 - K), hi_tl = min(min(r_base + GEO(GR), ntl) - 1, j - te0 + K);
           int tl = lo_tl + ((gi - lo_tl) % ngrp + ngrp) % ngrp;
           const float* gp = Gs + (tl - r_base) * GEO(Gld) + j;
-          for (; tl <= hi_tl; tl += ngrp, gp += ngrp * GEO(Gld)) sacc += *gp;
+          const int gstep = ngrp * GEO(Gld);
+          float s1 = 0.f, s2 = 0.f, s3 = 0.f;           // four loads in flight (fixed summation order)
+          for (; tl + 3 * ngrp <= hi_tl; tl += 4 * ngrp, gp += 4 * gstep) {
+            sacc += gp[0]; s1 += gp[gstep]; s2 += gp[2 * gstep]; s3 += gp[3 * gstep];
+          }
+          for (; tl <= hi_tl; tl += ngrp, gp += gstep) sacc += *gp;
+          sacc += (s1 + s2) + s3;
         }
         __syncthreads();
       }

@@ -119,8 +119,12 @@ def case_lm_and_ssl(ref, name, seed, B, Tmax, D, H, subsample, V, E, A, C, ksz, 
     # A freshly initialised model gives nearly flat logits: the free-running argmax of the unpaired pass then sits on
     # near-ties (top-2 margins of 1e-5 on logits of 0.3), where an fp32 and a bf16 implementation legitimately pick
     # different tokens and nothing after the first difference can be compared. The reference is therefore trained on
-    # the paired batch (its own supervised step, solver.py:375-385) until every free-running step of the unpaired pass
+    # a paired batch (its own supervised step, solver.py:375-385) until every free-running step of the unpaired pass
     # is decisive: top-2 margin > 4 * 3e-2 * max|logit| (twice the margin tests/test_gpu_ssl.py asserts).
+    # (The training batch is a DIFFERENT random paired batch: on the fixture's own paired batch the model stays far from
+    # converged, so the supervised gradient keeps its full size and bf16 rounding noise stays small next to it.)
+    rng_pre = np.random.RandomState(seed + 1000)
+    xa, lensa, ysa = synth_batch(rng_pre, B, Tmax, D, V)
     uxs_probe = torch.from_numpy(ux)
     Lu_probe = int(uxs_probe.size(1) * proportion)
     pre_opt = torch.optim.Adam(m.parameters(), lr=5e-3)
@@ -134,7 +138,7 @@ def case_lm_and_ssl(ref, name, seed, B, Tmax, D, H, subsample, V, E, A, C, ksz, 
         if bool(((top2[..., 0] - top2[..., 1]) > 4 * 3e-2 * pl.abs().max()).all()) and float((pp != 2).float().mean()) > 0.33:
             pretrain_steps = it
             break
-        _, lp, _, _ = m(torch.from_numpy(x), lens, ys=[torch.from_numpy(y) for y in ys], tf_rate=1.0, sample=False)
+        _, lp, _, _ = m(torch.from_numpy(xa), lensa, ys=[torch.from_numpy(y) for y in ysa], tf_rate=1.0, sample=False)
         pre_opt.zero_grad()
         (-torch.mean(lp)).backward()
         torch.nn.utils.clip_grad_norm_(m.parameters(), max_norm=5)
