@@ -2,7 +2,9 @@
 si284-shaped, batch 32 per GPU, T~1000 frames, bf16 MMA operands / f32 state) on N B200s.
 
   python bench.py [--gpus N] [--steps K] [--warmup W]          our CUDA path (one rank per GPU)
-  python bench.py --impl reference ...                         the reference's CPU path (oracle port)
+  python bench.py --impl reference ...                         the reference's own CPU path (oracle/_ref: its unmodified
+                                                               model.py + the step body of solver.py:375-385; the
+                                                               oracle port only where oracle/_ref is absent)
 
 A "step" = forward + loss + backward + clip + AMSGrad on one synthetic WSJ-shaped batch
 (SURVEY.md §8(d)). `value`: inputs already resident in HBM (graph replay only); `e2e`: the same
@@ -31,9 +33,18 @@ CFG = dict(input_dim=249, enc_hidden_dim=320, enc_n_layers=3, subsample=[2, 2, 2
 # algorithmic work per utterance-step, SURVEY.md §8(d) / BASELINE.md §4 (config 2)
 FLOP_PER_UTT = 19.81e9
 HBM_BYTES_PER_UTT = 51e6
-# dram__bytes_read.sum + dram__bytes_write.sum of one lstm_persist_fwd_kernel launch (B=32, T=1000, H=320, both
-# directions) from the committed `ncu --set full` capture
-NCU_TRAFFIC_BYTES = 329358848 + 366706176
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the serial kernels at config 2, from the committed
+# `ncu --set full` captures (profiles/*_ncu_full_summary.txt); None = not captured for the current build
+NCU_TRAFFIC = {
+    "lstm_persist_fwd": (329358848 + 366706176, "profiles/r03_ncu_full_summary.txt, layer 0"),
+    "lstm_persist_bwd": (None, None),
+    "dec_persist_fwd": (None, None),
+    "dec_persist_bwd": (None, None),
+}
+try:                      # refreshed by tools/ncu_summary.py from the round's capture
+    NCU_TRAFFIC.update({k: tuple(v) for k, v in json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).items()})
+except Exception:
+    pass
 
 
 def synth_batch(rng, B, Tmax, D, V):
@@ -106,38 +117,83 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_reference_run(steps, warmup, threads, B=8, Tmax=1000):
-    """The reference's CPU path for the same step (oracle port: same torch CPU ops as model.py /
-    solver.py:375-385, incl. torch's packed CPU LSTM), on a bounded sample: batches of B=8."""
-    from oracle import las_oracle as O
+def _cfg_kwargs(ld, dropout):
+    return dict(input_dim=CFG["input_dim"], enc_hidden_dim=CFG["enc_hidden_dim"], enc_n_layers=CFG["enc_n_layers"],
+                subsample=CFG["subsample"], dropout_rate=dropout, dec_hidden_dim=CFG["dec_hidden_dim"],
+                att_dim=CFG["att_dim"], conv_channels=CFG["conv_channels"], conv_kernel_size=CFG["conv_kernel_size"],
+                att_odim=CFG["att_odim"], embedding_dim=CFG["embedding_dim"], output_dim=CFG["V"],
+                ls_weight=CFG["ls_weight"], labeldist=ld)
+
+
+def cpu_reference_run(steps, warmup, threads, B=32, Tmax=1000, dropout=0.3):
+    """The reference's CPU path for the same step on the same synthetic batch law (B=32, Tmax=1000, dropout 0.3).
+    kind "reference": oracle/_ref -- the reference's UNMODIFIED model.py (E2E on torch CPU fp32, nn.LSTM over packed
+    sequences) driven by the step body of solver.py:375-385 (forward, -mean(log_probs), backward, clip_grad_norm_,
+    Adam(amsgrad)); kind "port": the oracle restatement, only where oracle/_ref is absent.
+    -> (utt/s, s/step, sample description, kind)"""
     torch.set_num_threads(threads)
     rng = np.random.RandomState(1234)
-    M = importlib.import_module(PKG + ".model")
     x, lens, ys = synth_batch(rng, B, Tmax, CFG["input_dim"], CFG["V"])
     ld = labeldist_of(ys, CFG["V"])
     torch.manual_seed(1234)
-    m = M.E2E(input_dim=CFG["input_dim"], enc_hidden_dim=CFG["enc_hidden_dim"], enc_n_layers=CFG["enc_n_layers"],
-              subsample=CFG["subsample"], dropout_rate=0.0, dec_hidden_dim=CFG["dec_hidden_dim"],
-              att_dim=CFG["att_dim"], conv_channels=CFG["conv_channels"], conv_kernel_size=CFG["conv_kernel_size"],
-              att_odim=CFG["att_odim"], embedding_dim=CFG["embedding_dim"], output_dim=CFG["V"],
-              ls_weight=CFG["ls_weight"], labeldist=ld)
-    P = {k: v.detach().clone() for k, v in m.state_dict().items()}
-    state = {}
     xt = torch.from_numpy(x)
+    from oracle import build_ref
     times = []
-    for i in range(warmup + steps):
-        t0 = time.perf_counter()
-        _, _, _, new = O.supervised_step(xt, lens, ys, P, state, CFG["subsample"], CFG["ls_weight"], ld,
-                                         lr=CFG["lr"], weight_decay=CFG["weight_decay"],
-                                         max_grad_norm=CFG["max_grad_norm"], fast=True)
-        for k in new:
-            P[k] = new[k]
-            if k.startswith("attention."):
-                P["decoder." + k] = new[k]
-        dt = time.perf_counter() - t0
-        if i >= warmup:
-            times.append(dt)
-    return B * len(times) / sum(times), float(np.mean(times)), f"B={B} utterances, Tmax={Tmax}, {len(times)} step(s)"
+    if build_ref.available():
+        kind = "reference"
+        R = build_ref.import_reference()
+        assert not torch.cuda.is_available(), "the reference moves itself to a visible GPU (utils.cc): hide it"
+        m = R.E2E(**_cfg_kwargs(ld, dropout))
+        m.train()
+        opt = torch.optim.Adam(m.parameters(), lr=CFG["lr"], weight_decay=CFG["weight_decay"], amsgrad=True)  # solver.py:152
+        yt = [torch.from_numpy(y) for y in ys]
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            _, log_probs, _, _ = m(xt, lens, yt, tf_rate=1.0, sample=False)      # solver.py:375
+            loss = -torch.mean(log_probs)                                          # solver.py:377
+            opt.zero_grad()
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(m.parameters(), max_norm=CFG["max_grad_norm"])   # solver.py:384
+            opt.step()
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    else:
+        kind = "port"
+        from oracle import las_oracle as O
+        M = importlib.import_module(PKG + ".model")
+        m = M.E2E(**_cfg_kwargs(ld, 0.0))
+        P = {k: v.detach().clone() for k, v in m.state_dict().items()}
+        state = {}
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            _, _, _, new = O.supervised_step(xt, lens, ys, P, state, CFG["subsample"], CFG["ls_weight"], ld,
+                                             lr=CFG["lr"], weight_decay=CFG["weight_decay"],
+                                             max_grad_norm=CFG["max_grad_norm"], fast=True)
+            for k in new:
+                P[k] = new[k]
+                if k.startswith("attention."):
+                    P["decoder." + k] = new[k]
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    sample = (f"{len(times)} step(s) of the full workload batch (B={B}, Tmax={Tmax}, dropout {dropout if kind == 'reference' else 0.0}), "
+              f"torch {torch.__version__} CPU fp32, {threads} threads")
+    return B * len(times) / sum(times), float(np.mean(times)), sample, kind
+
+
+def cpu_baseline_subprocess(cores):
+    """The CPU arm in a child process with the GPUs hidden (the reference's utils.cc moves every module to a visible
+    GPU; CUDA is already initialised in this process). -> the child's JSON line."""
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    res = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         env=env, capture_output=True, text=True, timeout=1200)
+    for line in reversed(res.stdout.strip().splitlines()):
+        if line.startswith("{"):
+            return json.loads(line)
+    raise RuntimeError("CPU baseline child failed: " + res.stderr[-2000:])
 
 
 def main():
@@ -165,14 +221,22 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        steps = max(1, min(args.steps, 3))
-        v, sec, sample = cpu_reference_run(steps, min(args.warmup, 1), cores)
+        if torch.cuda.is_available() and os.environ.get("CUDA_VISIBLE_DEVICES", None) != "":
+            # the reference's utils.cc() moves every module to a visible GPU: re-run with the GPUs hidden
+            env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+            sys.exit(subprocess.call([sys.executable] + sys.argv, env=env))
+        # bounded sample: the unmodified reference needs ~1-2 minutes per B=32 step on 8-16 cores (its decoder loop is
+        # 126 Python iterations of Conv2d(1, 10, (1, 201)) + small matmuls, and autograd replays them)
+        steps = max(1, min(args.steps, 2))
+        warm = 0
+        v, sec, sample, kind = cpu_reference_run(steps, warm, cores, B=args.batch, Tmax=args.tmax, dropout=args.dropout)
         print(json.dumps({
             "impl": "reference", "metric": "train utterances/sec", "value": v, "unit": "utt/s", "n_gpus": args.gpus,
-            "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload, "sample": sample},
-            "cpu_baseline": {"value": v, "unit": "utt/s", "cores": cores, "kind": "port", "sample": sample},
+            "config": {"workload": workload, "global_batch": args.batch, "dropout": args.dropout if kind == "reference" else 0.0,
+                       "sample": sample},
+            "cpu_baseline": {"value": v, "unit": "utt/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
@@ -192,11 +256,7 @@ def main():
     # one geometry for all batches (graph replay): pad label lists to a common Lmax via the longest utterance
     ld = labeldist_of([y for b in batches for y in b[2]], CFG["V"])
     torch.manual_seed(1234)
-    m = M.E2E(input_dim=CFG["input_dim"], enc_hidden_dim=CFG["enc_hidden_dim"], enc_n_layers=CFG["enc_n_layers"],
-              subsample=CFG["subsample"], dropout_rate=args.dropout, dec_hidden_dim=CFG["dec_hidden_dim"],
-              att_dim=CFG["att_dim"], conv_channels=CFG["conv_channels"], conv_kernel_size=CFG["conv_kernel_size"],
-              att_odim=CFG["att_odim"], embedding_dim=CFG["embedding_dim"], output_dim=CFG["V"],
-              ls_weight=CFG["ls_weight"], labeldist=ld).to(dev)
+    m = M.E2E(**_cfg_kwargs(ld, args.dropout)).to(dev)
     if world > 1:                                      # identical initial weights on every rank
         for p in m.parameters():
             torch.distributed.broadcast(p.data, 0)
@@ -293,7 +353,10 @@ def main():
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
-    roof = kernel_roofline(dev, hbm_peak, "measured" if peaks else "fallback")
+    step_us = ms / args.steps * 1e3
+    roofs = kernel_rooflines(tr, keys[0], args.batch, args.tmax, step_us, hbm_peak, peaks.get("bf16_tflops_sustained", 1400.0),
+                             "measured" if peaks else "fallback")
+    roof = max((r for r in roofs if r["bound"] == "hbm"), key=lambda r: r["us_per_step"])
     out = {
         "metric": "train utterances/sec", "value": value, "unit": "utt/s", "n_gpus": world, "steps": args.steps,
         "warmup": W, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -311,61 +374,81 @@ def main():
                           "frac_of_bf16_sustained": FLOP_PER_UTT * args.batch / (ms / args.steps * 1e-3) / 1e12 / tf_peak,
                           "algorithmic_hbm_gbs": HBM_BYTES_PER_UTT * args.batch / (ms / args.steps * 1e-3) / 1e9},
         "roofline": roof,
+        "roofline_by_kernel": roofs,
         "loss_first_last": [losses[0], losses[-1]],
     }
     if not args.no_cpu_baseline:
-        v, sec, sample = cpu_reference_run(2, 1, cores)
-        out["cpu_baseline"] = {"value": v, "unit": "utt/s", "cores": cores, "kind": "port", "sample": sample,
-                               "s_per_step": sec}
+        child = cpu_baseline_subprocess(cores)
+        out["cpu_baseline"] = dict(child["cpu_baseline"], s_per_step=child["ms_per_step"] * 1e-3)
     print(json.dumps(out))
     if world > 1:
         torch.distributed.destroy_process_group()
 
 
-def kernel_roofline(dev, hbm_peak, which):
-    """Dominant kernel = the cluster-persistent BLSTM recurrence of encoder layer 0 (longest serial
-    chain of the step). Timed live with CUDA events around las_lstm_seq_fwd on the current stream."""
-    Fn = importlib.import_module(PKG + ".functional")
+def kernel_rooflines(tr, key, B, Tmax, step_us, hbm_peak, tf_peak, which):
+    """Per-kernel-family roofline entries for the serial kernels and the GEMM family. Durations are measured HERE:
+    one eager (graph-off) step of the same trainer with a CUDA-event pair recorded around every C-ABI call on the
+    stream it launches on (`_lib.TIMER`); shares are relative to the graph-replay step time of the timed region.
+    Algorithmic bytes follow SURVEY.md 8(d)'s bf16 "reserve-space" model: per (utterance, timestep,
+    direction) a recurrence pass moves 20 H bytes -- forward: gate pre-activations 8H read, h 2H + gates/cell 10H
+    written; backward: gates/cell 10H + dy 2H read, gate gradients 8H written; a decoder pass streams enc_h and P
+    (Te x (H + A) bf16) once per step and utterance."""
     LIB = importlib.import_module(PKG + "._lib")
-    B, T, H = 32, 1000, CFG["enc_hidden_dim"]
-    torch.manual_seed(0)
-    xproj = torch.randn(B * T, 8 * H, device=dev) * 0.1
-    w = [torch.randn(4 * H, H, device=dev) * 0.05 for _ in range(2)]
-    whh = torch.cat([Fn.pack_afrag(w[0], 3, H), Fn.pack_afrag(w[1], 3, H)])
-    lens = torch.full((B,), T, device=dev, dtype=torch.int32)
-    y = torch.zeros(B, T, 2 * H, device=dev, dtype=torch.bfloat16)
-    hprev = torch.empty_like(y)
-    rec = torch.empty(2 * B * T * H, 4, device=dev, dtype=torch.int32)
-
-    def run():
-        Fn.call("las_lstm_persist_fwd", Fn.ptr(xproj), Fn.ptr(whh), Fn.ptr(lens), B, T, H, 2, Fn.ptr(y), T * 2 * H, 2 * H,
-                0, Fn.ptr(hprev), T * 2 * H, 2 * H, Fn.ptr(rec))
-    g = torch.cuda.CUDAGraph()
-    run()
+    H, A = CFG["enc_hidden_dim"], CFG["att_dim"]
+    use_graph = tr.use_graph
+    tr.use_graph = False
+    tr.run(key)                                  # warm (allocator, lazy attributes) with the timer off
     torch.cuda.synchronize()
-    with torch.cuda.graph(g):
-        run()
-    for _ in range(2):
-        g.replay()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(3):
-        g.replay()
-    e1.record()
-    torch.cuda.synchronize()
-    us = e0.elapsed_time(e1) * 1e3 / 3            # one launch = the whole T-step sequence, both directions
-    # algorithmic HBM bytes of one launch (DESIGN.md "kernels"): W_hh fragments once (2*4H*H*2 B), per (b, t):
-    # xproj row 8H*4 B read; y 2H*2 B, hprev 2H*2 B and the 16-byte activation records (gates 4 x f16, c, tanh c:
-    # 2H*16 B) written.
-    bytes_per_launch = 2 * 4 * H * H * 2 + B * T * (8 * H * 4 + 2 * H * 2 + 2 * H * 2 + 2 * H * 16)
-    ach = bytes_per_launch / (us * 1e-6) / 1e9
-    return {"kernel": "lstm_persist_fwd_kernel (BLSTM layer 0: T=1000 timesteps, both directions, one launch)",
-            "bound": "hbm", "achieved": ach, "peak": hbm_peak, "peak_source": which, "unit": "GB/s",
-            "frac": ach / hbm_peak, "traffic": NCU_TRAFFIC_BYTES, "traffic_source": "profiles/r03_ncu_full_summary.txt (dram read 329.4 MB + write 366.7 MB per launch)",
-            "us_per_launch": us, "us_per_timestep": us / T,
-            "algorithmic_bytes_per_launch": bytes_per_launch,
-            "note": "latency-bound serial recurrence: T dependent steps, each a per-warp chain MMA -> gate math -> DSMEM push (DESIGN.md 4b); HBM traffic equals the algorithmic bytes, the time does not"}
+    LIB.TIMER = []
+    try:
+        tr.run(key)
+        torch.cuda.synchronize()
+        rows = [(n, e0.elapsed_time(e1) * 1e3) for n, e0, e1 in LIB.TIMER]
+    finally:
+        LIB.TIMER = None
+        tr.use_graph = use_graph
+    fam = {}
+    for n, us in rows:
+        f = {"las_lstm_persist_fwd": "lstm_persist_fwd", "las_lstm_persist_bwd": "lstm_persist_bwd",
+             "las_dec_fwd": "dec_persist_fwd", "las_dec_bwd": "dec_persist_bwd", "las_gemm_bf16_ws": "gemm_tcgen05"}.get(n)
+        if f:
+            fam.setdefault(f, []).append(us)
+    # timesteps per pass over the pyramid (config 2: 1000 + 500 + 250), decoder geometry
+    T_l, t = [], Tmax
+    for sub in CFG["subsample"]:
+        T_l.append(t)
+        t = (t + 1) // sub if sub > 1 else t
+    Te, Lp1 = t, int(np.clip(round(0.125 * Tmax), 2, 250)) + 1
+    rec_bytes = sum(B * tl * 2 * 20 * H for tl in T_l) + len(T_l) * 2 * 4 * H * H * 2
+    dec_bytes = B * Lp1 * Te * (H + A) * 2
+    alg = {"lstm_persist_fwd": rec_bytes, "lstm_persist_bwd": rec_bytes, "dec_persist_fwd": dec_bytes, "dec_persist_bwd": dec_bytes}
+    names = {"lstm_persist_fwd": "lstm_persist_fwd_kernel (pBLSTM recurrence, all layers: one launch per layer)",
+             "lstm_persist_bwd": "lstm_persist_bwd_kernel (pBLSTM BPTT, all layers: one launch per layer)",
+             "dec_persist_fwd": "dec_persist_fwd_kernel (attention decoder, all L+1 steps in one launch)",
+             "dec_persist_bwd": "dec_persist_bwd_kernel (attention decoder BPTT, one launch)"}
+    out = []
+    for f in ("lstm_persist_bwd", "lstm_persist_fwd", "dec_persist_bwd", "dec_persist_fwd"):
+        if f not in fam:
+            continue
+        us = sum(fam[f])
+        ach = alg[f] / (us * 1e-6) / 1e9
+        traffic, src = NCU_TRAFFIC.get(f, (None, None))
+        steps_serial = sum(T_l) if f.startswith("lstm") else Lp1
+        out.append({"kernel": names[f], "bound": "hbm", "launches_per_step": len(fam[f]), "us_per_step": us,
+                    "share_of_step": us / step_us, "achieved": ach, "peak": hbm_peak, "peak_source": which, "unit": "GB/s",
+                    "frac": ach / hbm_peak, "algorithmic_bytes": alg[f], "traffic": traffic, "traffic_source": src,
+                    "us_per_timestep": us / steps_serial,
+                    "note": "latency-bound serial chain (dependent timesteps; DESIGN.md 4b/5): the HBM fraction is low by construction"})
+    if "gemm_tcgen05" in fam:
+        us = sum(fam["gemm_tcgen05"])
+        flops = 0.488 * FLOP_PER_UTT * B          # SURVEY 8(d): dense GEMMs are 48.8 % of the step's algorithmic FLOPs
+        ach = flops / (us * 1e-6) / 1e12
+        out.append({"kernel": "gemm_kernel (tcgen05 + TMA; every dense contraction of the step)", "bound": "tensor",
+                    "launches_per_step": len(fam["gemm_tcgen05"]), "us_per_step": us, "share_of_step": us / step_us,
+                    "achieved": ach, "peak": tf_peak, "peak_source": which, "unit": "TFLOP/s", "frac": ach / tf_peak,
+                    "traffic": None,
+                    "note": "sum of per-launch durations incl. side-stream launches that run concurrently with the serial kernels"})
+    return out
 
 
 if __name__ == "__main__":

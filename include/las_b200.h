@@ -33,6 +33,19 @@ int las_version(void);
 int las_num_sms(void);
 /* kernels launched by this library since load (host counter; bench.py reports the per-step delta) */
 unsigned long long las_launch_count(void);
+/* Calls per code path since load (or the last reset): which implementation an entry point actually took. A test
+ * (or a run) can assert that the cluster-persistent kernels ran instead of discovering a silent per-timestep path
+ * as a 2x slower step. out: LAS_PATH_COUNTERS values (may be NULL); reset != 0 zeroes them. Returns the count. */
+#define LAS_PATH_LSTM_PERSIST_FWD 0
+#define LAS_PATH_LSTM_PERSIST_BWD 1
+#define LAS_PATH_LSTM_STEP_FWD 2
+#define LAS_PATH_LSTM_STEP_BWD 3
+#define LAS_PATH_DEC_PERSIST_FWD 4
+#define LAS_PATH_DEC_PERSIST_BWD 5
+#define LAS_PATH_DEC_STEP_FWD 6
+#define LAS_PATH_DEC_STEP_BWD 7
+#define LAS_PATH_COUNTERS 8
+int las_path_counters(unsigned long long* out, int reset);
 
 /* Dense contraction D[m,n] = sum_k A[m,k]*B[n,k] (+bias[n]) (relu) (+=C) on tcgen05 tensor
  * cores, bf16 operands, f32 accumulation, operands fetched by TMA.
@@ -119,6 +132,13 @@ int64_t las_afrag_bytes(int rows, int cols, int mode, int H);
 int las_smallmm(const void* a_pk, int M, int K, const void* v, int v_is_f32, int64_t ldv, int N,
                 const float* bias, const float* add, int64_t ld_add, float* out_f32, int64_t ld_out,
                 void* out_bf16, int64_t ld_outb, void* stream);
+/* One stand-alone LSTM cell step with explicit state (nn.LSTMCell; one timestep of nn.LSTM given (h0, c0): the
+ * reference's LM.forward_step, model.py:535-542). gates = bias + W_hh h + W_ih x; c_state [B, H] f32 is updated in
+ * place, h_out bf16 [B, ld_ho] written (must not alias h_in). whh_pk / wih_pk: las_pack_afrag mode 1; h_in bf16
+ * [B, ld_h], x bf16 [B, ld_x] (columns finite up to the next multiple of 16 of H / Kx); bias f32 [4H]. */
+int las_lstm_cell_step(const void* whh_pk, const void* wih_pk, const float* bias, const void* h_in, int64_t ld_h,
+                       const void* x, int64_t ld_x, int Kx, float* c_state, void* h_out, int64_t ld_ho, int B, int H,
+                       void* stream);
 int64_t las_lstm_ws_bytes(int B, int H, int ndir);
 int las_lstm_seq_fwd(const float* xproj, const void* whh_pk, const int32_t* lens, int B, int T, int H,
                      int ndir, void* y, int64_t y_ld_b, int64_t y_ld_t, int rep_row, void* hprev,
@@ -276,6 +296,11 @@ int las_att_param_grads_part(const float* P, const float* dzf, const float* conv
                              const float* mlp_att, const float* gvec, int B, int L, int Te, int A, int C, int what,
                              float* dP, float* part_ws, float* dmlp_att, float* dgvec, void* stream);
 int las_dec_fwd(const las_dec_args* args_host, void* stream);
+/* One stand-alone AttLoc.forward (model.py:139-173) on the per-step kernels, buffer conventions of las_dec_fwd:
+ * reads the decoder state z from zc[:, t+1, :Hd] and the previous alignment from ws[:, t]; writes the alignment
+ * ws[:, t+1], the context ctx[:, t+1] and c = mlp_o(context) into zc[:, t+1, Hd:]. Needs only the attention
+ * operands (enc_h, P, mlp_dec_pk, mlp_o_pk, mlp_o_b, conv_w, mlp_att, gvec, e_buf, dzf). */
+int las_att_step(const las_dec_args* args_host, int t, void* stream);
 int las_dec_bwd(const las_dec_args* args_host, void* stream);
 
 #ifdef __cplusplus

@@ -42,6 +42,7 @@ SIGNATURES = {
     "las_version": (c_int, []),
     "las_num_sms": (c_int, []),
     "las_launch_count": (ctypes.c_ulonglong, []),
+    "las_path_counters": (c_int, [P, I]),
     "las_gemm_bf16": (c_int, [P, L, I, P, L, I, P, L, I, P, I, I, I, I, I, P]),
     "las_gemm_bf16_ws": (c_int, [P, L, I, P, L, I, P, L, I, P, I, I, I, I, I, P, L, P]),
     "las_cvt_pad_bf16": (c_int, [P, L, L, I, P, L, P]),
@@ -58,6 +59,7 @@ SIGNATURES = {
     "las_pack_afrag": (c_int, [P, L, I, I, I, I, I, I, P, P]),
     "las_afrag_bytes": (c_int64, [I, I, I, I]),
     "las_smallmm": (c_int, [P, I, I, P, I, L, I, P, P, L, P, L, P, L, P]),
+    "las_lstm_cell_step": (c_int, [P, P, P, P, L, P, L, I, P, P, L, I, I, P]),
     "las_lstm_ws_bytes": (c_int64, [I, I, I]),
     "las_lstm_seq_fwd": (c_int, [P, P, P, I, I, I, I, P, L, L, I, P, L, L, P, P, P, P]),
     "las_lstm_seq_bwd": (c_int, [P, L, L, I, P, I, P, I, I, I, I, P, P, P, L, L, P, P]),
@@ -81,6 +83,7 @@ SIGNATURES = {
     "las_att_param_grads_part": (c_int, [P, P, P, P, P, P, I, I, I, I, I, I, P, P, P, P, P]),
     "las_dec_fwd": (c_int, [ctypes.POINTER(DecArgs), P]),
     "las_dec_bwd": (c_int, [ctypes.POINTER(DecArgs), P]),
+    "las_att_step": (c_int, [ctypes.POINTER(DecArgs), I, P]),
 }
 
 
@@ -120,6 +123,18 @@ def check(rc):
         raise LasError(lib().las_last_error().decode("utf-8", "replace"))
 
 
+PATH_NAMES = ("lstm_persist_fwd", "lstm_persist_bwd", "lstm_step_fwd", "lstm_step_bwd", "dec_persist_fwd",
+              "dec_persist_bwd", "dec_step_fwd", "dec_step_bwd")
+
+
+def path_counters(reset=False):
+    """{path name: calls} since load / the last reset (las_path_counters): which kernels the entry points chose."""
+    buf = (ctypes.c_ulonglong * len(PATH_NAMES))()
+    n = lib().las_path_counters(buf, int(bool(reset)))
+    assert n == len(PATH_NAMES)
+    return dict(zip(PATH_NAMES, (int(v) for v in buf)))
+
+
 def ptr(t):
     """Device pointer of a torch tensor (or None -> NULL)."""
     if t is None:
@@ -135,7 +150,21 @@ def stream_ptr():
     return torch.cuda.current_stream().cuda_stream
 
 
+# Per-call device timing (bench.py's per-kernel roofline): set TIMER to a list and every entry-point call made through
+# call() appends (name, start_event, end_event), both recorded on the stream the kernels are launched on.
+TIMER = None
+
+
 def call(name, *args):
     """Invoke an int-returning C-ABI function on torch's current stream; raise LasError on failure."""
     fn = getattr(lib(), name)
-    check(fn(*args, stream_ptr()))
+    if TIMER is None:
+        check(fn(*args, stream_ptr()))
+        return
+    import torch
+    s = torch.cuda.current_stream()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(s)
+    check(fn(*args, s.cuda_stream))
+    e1.record(s)
+    TIMER.append((name, e0, e1))

@@ -11,6 +11,7 @@ namespace las {
 
 static thread_local char g_err[512] = "";
 unsigned long long g_launches = 0;
+unsigned long long g_path[LAS_PATH_COUNTERS] = {0};
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -47,6 +48,14 @@ int las_version(void) { return LAS_B200_VERSION; }
 int las_num_sms(void) { return las::num_sms(); }
 
 unsigned long long las_launch_count(void) { return las::g_launches; }
+
+int las_path_counters(unsigned long long* out, int reset) {
+  for (int i = 0; i < LAS_PATH_COUNTERS; ++i) {
+    if (out) out[i] = las::g_path[i];
+    if (reset) las::g_path[i] = 0;
+  }
+  return LAS_PATH_COUNTERS;
+}
 
 int las_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb,
                   int b_mn_major, void* C, int64_t ldc, int c_is_bf16, const float* bias, int M,

@@ -14,6 +14,7 @@ namespace las {
 // ----------------------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
 extern unsigned long long g_launches;  // kernels launched by this library (las_launch_count())
+extern unsigned long long g_path[];     // calls per code path (las_path_counters(); indices LAS_PATH_* in las_b200.h)
 int check_cuda(cudaError_t e, const char* what);
 
 #define LAS_CUDA(expr)                                   \

@@ -954,6 +954,10 @@ int las_att_param_grads(const float* P, const float* dzf, const float* conv_save
                                   dgvec, stream_);
 }
 
+// Per-step launches of decoder steps [t_begin, t_end). `with_cell`: LSTMCell update (1); the attention (2)-(5) always
+// runs; `with_out`: output layer + next embedding of the free-running modes (6)-(7).
+static int dec_fwd_steps(const las_dec_args* a, cudaStream_t stream, int t_begin, int t_end, bool with_cell, bool with_out);
+
 int las_dec_fwd(const las_dec_args* a, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (int rc = check_args(a)) return rc;
@@ -961,8 +965,24 @@ int las_dec_fwd(const las_dec_args* a, void* stream_) {
   LAS_REQUIRE(t_begin >= 0 && t_begin <= t_end, "decoder: step range [%d, %d) invalid", t_begin, t_end);
   if (dec_persist_supported(a)) {
     LAS_REQUIRE(t_begin == 0 && t_end == a->L, "decoder: the persistent kernel runs all steps in one launch");
+    ++g_path[LAS_PATH_DEC_PERSIST_FWD];
     return dec_persist_fwd(a, stream);   // one cluster-persistent launch
   }
+  ++g_path[LAS_PATH_DEC_STEP_FWD];
+  return dec_fwd_steps(a, stream, t_begin, t_end, true, true);
+}
+
+// One stand-alone AttLoc.forward (model.py:139-173) on the per-step kernels: reads the decoder state z from
+// zc[:, t+1, :Hd] and the previous alignment from ws[:, t], writes ws[:, t+1], ctx[:, t+1] and c = mlp_o(context)
+// into zc[:, t+1, Hd:]. Buffer conventions as las_dec_fwd; no cell / output-layer operands are needed.
+int las_att_step(const las_dec_args* a, int t, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (int rc = check_args(a)) return rc;
+  LAS_REQUIRE(t >= 0 && t < a->L, "attention step %d outside [0, %d)", t, a->L);
+  return dec_fwd_steps(a, stream, t, t + 1, false, false);
+}
+
+static int dec_fwd_steps(const las_dec_args* a, cudaStream_t stream, int t_begin, int t_end, bool with_cell, bool with_out) {
   const int B = a->B, L = a->L, Te = a->Te, Hd = a->Hd, O = a->O, A = a->A, V = a->V, E = a->E;
   const int ZC = Hd + O;
   const int64_t R = L + 1;  // rows per utterance in the per-step buffers
@@ -975,8 +995,8 @@ int las_dec_fwd(const las_dec_args* a, void* stream_) {
   else { if (int rc = ensure_smem(att_energy_fwd_kernel<16>, esmem)) return rc; }
   const size_t csmem = (Te + 2 + 8 + 8 * 32 * 2) * sizeof(float);
   if (int rc = ensure_smem(att_ctx_fwd_kernel, csmem)) return rc;
-  const bool free_run = a->mode != 0;
-  const bool drop = a->drop_p > 0.f;
+  const bool free_run = a->mode != 0 && with_out;
+  const bool drop = a->drop_p > 0.f && with_cell;
   if (drop) LAS_REQUIRE(a->seed_dev && a->zcd, "decoder: dropout needs seed_dev and the zcd buffer");
   __nv_bfloat16* zcd = static_cast<__nv_bfloat16*>(a->zcd);
   __nv_bfloat16* zc = static_cast<__nv_bfloat16*>(a->zc);
@@ -1013,7 +1033,7 @@ int las_dec_fwd(const las_dec_args* a, void* stream_) {
     cp.v1 = (drop ? zcd : zc) + static_cast<int64_t>(t) * ZC;      // cell input: c_{t-1} after dropout (model.py:285)
     cp.hout = zc + static_cast<int64_t>(t + 1) * ZC;
     if (free_run) cp.v2 = emb_op + static_cast<int64_t>(t) * Ep;
-    launch_cell_fwd(cp, stream);
+    if (with_cell) launch_cell_fwd(cp, stream);
     // (2) decoder-state projection mlp_dec(z_t)   (model.py:163)
     float* dz_t = a->dzf + static_cast<int64_t>(t) * A;
     smallmm(static_cast<const uint32_t*>(a->mlp_dec_pk), A, Hd, zc + static_cast<int64_t>(t + 1) * ZC, 0, R * ZC, B,
@@ -1062,7 +1082,11 @@ int las_dec_fwd(const las_dec_args* a, void* stream_) {
 int las_dec_bwd(const las_dec_args* a, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (int rc = check_args(a)) return rc;
-  if (dec_persist_supported(a)) return dec_persist_bwd(a, stream);   // one cluster-persistent launch
+  if (dec_persist_supported(a)) {
+    ++g_path[LAS_PATH_DEC_PERSIST_BWD];
+    return dec_persist_bwd(a, stream);   // one cluster-persistent launch
+  }
+  ++g_path[LAS_PATH_DEC_STEP_BWD];
   const bool smooth = a->mode == 2;
   const bool drop = a->drop_p > 0.f;
   if (drop) LAS_REQUIRE(a->seed_dev, "decoder backward: dropout needs seed_dev");

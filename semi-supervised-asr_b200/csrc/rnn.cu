@@ -469,12 +469,40 @@ int las_lstm_seq_fwd(const float* xproj, const void* whh_pk, const int32_t* lens
   LAS_CUDA(cudaMemsetAsync(ws, 0, static_cast<size_t>(las_lstm_ws_bytes(B, H, ndir)), stream));
   p.v1_ld = Kp; p.v1_dir = static_cast<int64_t>(B) * Kp;
   p.hout_ld = Kp; p.hout_dir = p.v1_dir;
+  ++g_path[LAS_PATH_LSTM_STEP_FWD];
   for (int s = 0; s < T; ++s) {
     p.step = s;
     p.v1 = hbuf + static_cast<size_t>(s & 1) * ndir * B * Kp;
     p.hout = hbuf + static_cast<size_t>((s + 1) & 1) * ndir * B * Kp;
     launch_cell_fwd(p, stream);
   }
+  LAS_LAUNCH_CHECK();
+  return 0;
+}
+
+// One stand-alone LSTM cell step with explicit state (nn.LSTMCell / one timestep of nn.LSTM with (h0, c0); the
+// reference's LM.forward_step, model.py:535-542): gates = bias + W_hh h + W_ih x, c_state updated in place,
+// h_out written. whh_pk / wih_pk: las_pack_afrag mode 1 (gate-interleaved). h_in bf16 [B, ld_h] (columns up to the
+// next multiple of 16 of H finite), x bf16 [B, ld_x] (likewise for the input width Kx), bias f32 [4H] (b_ih + b_hh),
+// c_state f32 [B, H], h_out bf16 [B, ld_ho] (must not alias h_in).
+int las_lstm_cell_step(const void* whh_pk, const void* wih_pk, const float* bias, const void* h_in, int64_t ld_h,
+                       const void* x, int64_t ld_x, int Kx, float* c_state, void* h_out, int64_t ld_ho, int B, int H,
+                       void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  LAS_REQUIRE(H % 8 == 0, "lstm cell: hidden size %d must be a multiple of 8", H);
+  LAS_REQUIRE(h_in != h_out, "lstm cell: h_out must not alias h_in");
+  if (B == 0) return 0;
+  CellFwdParams p = {};
+  p.B = B; p.T = 1; p.H = H; p.ndir = 1; p.UG = H / 8;
+  p.xproj = bias; p.xp_ld_b = 0; p.xp_ld_t = 0; p.xp_ld_dir = 0;
+  p.a1 = static_cast<const uint32_t*>(whh_pk); p.KT1 = (H + 15) / 16; p.a_dir = 0;
+  p.v1 = static_cast<const __nv_bfloat16*>(h_in); p.v1_ld = ld_h; p.v1_dir = 0;
+  p.a2 = static_cast<const uint32_t*>(wih_pk); p.KT2 = (Kx + 15) / 16;
+  p.v2 = static_cast<const __nv_bfloat16*>(x); p.v2_ld = ld_x;
+  p.lens = nullptr; p.c_state = c_state;
+  p.hout = static_cast<__nv_bfloat16*>(h_out); p.hout_ld = ld_ho; p.hout_dir = 0;
+  p.y = nullptr; p.hprev = nullptr; p.gates_save = nullptr; p.c_save = nullptr; p.rep_row = 0; p.step = 0;
+  launch_cell_fwd(p, stream);
   LAS_LAUNCH_CHECK();
   return 0;
 }
@@ -491,6 +519,7 @@ int las_lstm_seq_bwd(const float* dy, int64_t dy_ld_b, int64_t dy_ld_t, int rep_
   LAS_REQUIRE(H % 8 == 0, "lstm: hidden size %d must be a multiple of 8", H);
   if (B == 0 || T == 0) return 0;
   LAS_REQUIRE(whhT_layout == 0, "lstm bwd: owner-ordered weights belong to las_lstm_persist_bwd");
+  ++g_path[LAS_PATH_LSTM_STEP_BWD];
   CellBwdParams p = {};
   p.dy = dy; p.dy_ld_b = dy_ld_b; p.dy_ld_t = dy_ld_t; p.rep_row = rep_row;
   p.dh_extra = nullptr; p.dhx_ld = 0;
@@ -523,6 +552,7 @@ int las_lstm_persist_fwd(const float* xproj, const void* whh_pk, const int32_t* 
   LAS_REQUIRE(persist_supported(H), "persistent LSTM: hidden size %d unsupported (or switched off)", H);
   LAS_REQUIRE(ndir == 1 || ndir == 2, "lstm: ndir must be 1 or 2");
   if (B == 0 || T == 0) return 0;
+  ++g_path[LAS_PATH_LSTM_PERSIST_FWD];
   int rc = persist_lstm_fwd(xproj, whh_pk, lens, B, T, H, ndir, y, y_ld_b, y_ld_t, rep_row, hprev, hp_ld_b, hp_ld_t,
                             rec, static_cast<cudaStream_t>(stream));
   if (rc) return rc;
@@ -535,6 +565,7 @@ int las_lstm_persist_bwd(const float* dy, int64_t dy_ld_b, int64_t dy_ld_t, int 
                          const void* rec, void* dG, int64_t dg_ld_b, int64_t dg_ld_t, void* stream) {
   LAS_REQUIRE(persist_supported(H), "persistent LSTM: hidden size %d unsupported (or switched off)", H);
   if (B == 0 || T == 0) return 0;
+  ++g_path[LAS_PATH_LSTM_PERSIST_BWD];
   int rc = persist_lstm_bwd(dy, dy_ld_b, dy_ld_t, rep_row, whhT_owner_pk, lens, B, T, H, ndir, rec, dG, dg_ld_b,
                             dg_ld_t, static_cast<cudaStream_t>(stream));
   if (rc) return rc;

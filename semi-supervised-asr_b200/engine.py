@@ -32,39 +32,130 @@ def build_targets(ys, bos, eos, pad):
     return ys_in, ys_out
 
 
-class _Static:
-    """Device + pinned-host staging buffers of one batch geometry, and its captured graph."""
+class _Arena:
+    """Named device / page-locked host buffers that only ever grow to the largest extent requested so far; every
+    batch geometry gets VIEWS of them (all starting at the buffer base). Memory is therefore bounded by the largest
+    batch, not by the number of distinct (B, Tmax, Lmax) seen (reference batches almost never repeat a geometry).
+    Growing a buffer moves it: `gen` is bumped so that owners of captured graphs (which hold raw addresses) drop
+    them. `reserve()` the configured maxima up front and nothing ever moves."""
 
-    def __init__(self, B, T, D, L, dev):
-        self.x = torch.zeros(B, T, D, device=dev, dtype=torch.float32)
-        self.lens = torch.zeros(B, device=dev, dtype=torch.int32)
-        self.ys_in = torch.zeros(B, L + 1, device=dev, dtype=torch.int64)
-        self.ys_out = torch.zeros(B, L, device=dev, dtype=torch.int64)
-        self.h_lens = torch.zeros(B, dtype=torch.int32).pin_memory()
-        self.h_ys_in = torch.zeros(B, L + 1, dtype=torch.int64).pin_memory()
-        self.h_ys_out = torch.zeros(B, L, dtype=torch.int64).pin_memory()
-        self.graph = None
-        self.loss = None
-        self.norm = None
-        self.seen = 0
-        self.slots = [None, None]          # double-buffered upload targets of the pipelined path (steps())
+    def __init__(self, dev):
+        self.dev = dev
+        self.bufs = {}
+        self.gen = 0
+
+    def get(self, name, shape, dtype, pinned=False):
+        n = int(torch.Size(shape).numel())
+        buf = self.bufs.get(name)
+        if buf is None or buf.numel() < n:
+            if buf is not None:
+                torch.cuda.synchronize(self.dev)     # copies / kernels in flight may still use the old storage
+                self.gen += 1
+                n_alloc = max(n, int(buf.numel() * 1.25))
+            else:
+                n_alloc = n
+            if pinned:
+                buf = torch.zeros(max(n_alloc, 1), dtype=dtype).pin_memory()
+            else:
+                buf = torch.zeros(max(n_alloc, 1), device=self.dev, dtype=dtype)
+            self.bufs[name] = buf
+        assert buf.dtype == dtype
+        return buf[:n].view(shape)
+
+    def nbytes(self):
+        return sum(b.numel() * b.element_size() for b in self.bufs.values() if b.is_cuda)
+
+
+class _Views:
+    """Views of one batch geometry into the arena: the graph's static inputs, their pinned host staging, and the
+    two upload slots of the pipelined path."""
+
+    def __init__(self, arena, B, T, D, L, prefix=""):
+        g = lambda name, shape, dtype, pinned=False: arena.get(prefix + name, shape, dtype, pinned)
+        i32, i64, f32 = torch.int32, torch.int64, torch.float32
+        self.x = g("x", (B, T, D), f32)
+        self.lens = g("lens", (B,), i32)
+        self.ys_in = g("ys_in", (B, L + 1), i64)
+        self.ys_out = g("ys_out", (B, L), i64)
+        self.h_lens = g("h_lens", (B,), i32, True)
+        self.h_ys_in = g("h_ys_in", (B, L + 1), i64, True)
+        self.h_ys_out = g("h_ys_out", (B, L), i64, True)
 
 
 class _Slot:
-    """One upload target: device copies of a batch plus the pinned host staging of its small integer tensors."""
+    """State of one upload slot (its buffers are arena views made per batch)."""
 
-    def __init__(self, st):
-        self.x = torch.empty_like(st.x)
-        self.lens, self.ys_in, self.ys_out = torch.empty_like(st.lens), torch.empty_like(st.ys_in), torch.empty_like(st.ys_out)
-        self.h_lens = torch.zeros_like(st.h_lens).pin_memory()
-        self.h_ys_in = torch.zeros_like(st.h_ys_in).pin_memory()
-        self.h_ys_out = torch.zeros_like(st.h_ys_out).pin_memory()
+    def __init__(self):
         self.ready = torch.cuda.Event()    # upload finished (recorded on the copy stream)
         self.consumed = None               # device copy into the static buffers finished (recorded on the main stream)
+        self.used = False
+        self.views = None
+
+
+class _GraphCache:
+    """LRU of captured step graphs, keyed by batch geometry, all captured into ONE shared memory pool (a private
+    pool per graph would hold ~1 GB of activations each). A geometry is run eagerly on first sight, captured on
+    the second, evicted when more than `max_graphs` others have been used since. Entries captured against an older
+    arena generation or other optimiser hyper-parameters (they are baked into the captured launches by value) are
+    dropped."""
+
+    def __init__(self, max_graphs=8, max_seen=4096):
+        import collections
+        self.max_graphs, self.max_seen = int(max_graphs), int(max_seen)
+        self.graphs = collections.OrderedDict()
+        self.seen = collections.OrderedDict()
+        self.pool = None
+        self.captures, self.evictions = 0, 0
+
+    def lookup(self, key, stamp):
+        ent = self.graphs.get(key)
+        if ent is not None and ent["stamp"] != stamp:
+            del self.graphs[key]
+            ent = None
+        if ent is not None:
+            self.graphs.move_to_end(key)
+        return ent
+
+    def sighting(self, key):
+        """Number of earlier sightings of this geometry (bounded memory: oldest keys are forgotten)."""
+        n = self.seen.pop(key, 0)
+        self.seen[key] = n + 1
+        while len(self.seen) > self.max_seen:
+            self.seen.popitem(last=False)
+        return n
+
+    def store(self, key, ent):
+        self.graphs[key] = ent
+        self.captures += 1
+        while len(self.graphs) > max(1, self.max_graphs):
+            self.graphs.popitem(last=False)
+            self.evictions += 1
+
+    def clear(self):
+        self.graphs.clear()
+
+    def pool_handle(self):
+        """The shared pool. torch releases a pool when the last graph captured into it dies (and asserts if the handle
+        is used again), which evicting or invalidating every entry would do: a trivial anchor graph keeps it alive."""
+        if self.pool is None:
+            self.pool = torch.cuda.graph_pool_handle()
+            self._anchor = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._anchor, pool=self.pool):
+                self._anchor_out = torch.zeros(8, device="cuda")
+        return self.pool
+
+
+def _hyper_stamp(opt):
+    g = opt.param_groups[0]
+    return (float(g["lr"]), tuple(float(b) for b in g["betas"]), float(g["eps"]), float(g["weight_decay"]))
+
+
+def _host_lens(ilens):
+    return [int(l) for l in (ilens.tolist() if torch.is_tensor(ilens) else ilens)]
 
 
 class SupervisedTrainer:
-    def __init__(self, model, optimizer, max_grad_norm=5.0, use_graph=True, process_group=None):
+    def __init__(self, model, optimizer, max_grad_norm=5.0, use_graph=True, process_group=None, max_graphs=8):
         self.model = model
         self.opt = optimizer
         self.max_grad_norm = max_grad_norm
@@ -73,9 +164,11 @@ class SupervisedTrainer:
         self.world = 1
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(process_group)
-        self.static = {}
+        self.arena = None
+        self.cache = _GraphCache(max_graphs)
+        self.slots = None
         self.launches_per_step = None
-        self.update_graph, self.update_norm = None, None
+        self.update_graph, self.update_norm, self.update_stamp = None, None, None
         self.cap_stream = None
         self.copy_stream = None
         self.rb_dev, self.rb_host, self.rb_stream = None, None, None
@@ -110,28 +203,58 @@ class SupervisedTrainer:
             torch.distributed.all_reduce(self.opt.flat_grad, group=self.pg)
         return loss, self._update()
 
-    def stage(self, xs, ilens, ys):
-        """Host -> device copies of one batch into the static buffers of its geometry."""
+    # ---- geometry -> arena views
+    def _dev(self):
+        return next(self.model.parameters()).device
+
+    def _arena(self):
+        if self.arena is None:
+            self.arena = _Arena(self._dev())
+        return self.arena
+
+    def reserve(self, B, T, D, L):
+        """Size every staging buffer for the largest batch the run can produce (e.g. config batch_size,
+        max_feature_length, input_dim, max_text_length + 1): no buffer then ever moves and no graph is dropped."""
+        _Views(self._arena(), B, T, D, L)
+        for k in range(2):
+            _Views(self._arena(), B, T, D, L, prefix=f"slot{k}.")
+
+    def _geometry(self, xs, ilens, ys):
         m = self.model
-        dev = next(m.parameters()).device
-        host_lens = [int(l) for l in (ilens.tolist() if torch.is_tensor(ilens) else ilens)]
+        host_lens = _host_lens(ilens)
         T = max(host_lens)
         ys_in, ys_out = build_targets(ys, m.decoder.bos, m.decoder.eos, m.decoder.pad)
         B, L = ys_out.shape
         key = (B, T, xs.shape[2], L)
-        st = self.static.get(key)
-        if st is None:
-            st = self.static[key] = _Static(B, T, xs.shape[2], L, dev)
+        return key, _Views(self._arena(), *key), host_lens, T, ys_in, ys_out
+
+    def staged(self, key):
+        """The static device buffers (x, lens, ys_in, ys_out views) a step on geometry `key` reads."""
+        return _Views(self._arena(), *key)
+
+    def stage(self, xs, ilens, ys):
+        """Host -> device copies of one batch into the static buffers (views of its geometry)."""
+        key, st, host_lens, T, ys_in, ys_out = self._geometry(xs, ilens, ys)
         st.x.copy_(xs[:, :T], non_blocking=True)
         if self.input_noise_std > 0:
             st.x.add_(torch.randn_like(st.x), alpha=float(self.input_noise_std))
+        self._staging_wait()
         st.h_lens.copy_(torch.tensor(host_lens, dtype=torch.int32))
         st.h_ys_in.copy_(torch.from_numpy(ys_in))
         st.h_ys_out.copy_(torch.from_numpy(ys_out))
         st.lens.copy_(st.h_lens, non_blocking=True)
         st.ys_in.copy_(st.h_ys_in, non_blocking=True)
         st.ys_out.copy_(st.h_ys_out, non_blocking=True)
+        self._stage_ev = torch.cuda.Event()
+        self._stage_ev.record(torch.cuda.current_stream(st.x.device))
         return key
+
+    def _staging_wait(self):
+        """The pinned staging of stage() is shared by all geometries: the previous batch's H2D copies must have
+        left the host before it is overwritten."""
+        ev = getattr(self, "_stage_ev", None)
+        if ev is not None:
+            ev.synchronize()
 
     def run(self, key):
         """One train step on the batch currently staged for `key`. Returns (loss, grad_norm) device tensors.
@@ -140,96 +263,90 @@ class SupervisedTrainer:
         optimiser another, with the NCCL all-reduce of the flat gradient issued eagerly between them (a
         collective recorded inside a capture is not executed at capture time, which would desynchronise ranks
         that meet a new batch geometry at different steps)."""
-        st = self.static[key]
-        L = key[3]
+        B, T, D, L = key
+        st = _Views(self._arena(), B, T, D, L)
         self.model.train()
         if not self.use_graph:
             return self._body(st, L)
-        if st.graph is None:
-            if st.seen == 0:                       # first sight of a geometry: eager (also warms lazy init)
-                st.seen = 1
+        stamp = (self.arena.gen, _hyper_stamp(self.opt), self.max_grad_norm)
+        ent = self.cache.lookup(key, stamp)
+        if ent is None:
+            if self.cache.sighting(key) == 0:      # first sight of a geometry: eager (also warms lazy init)
                 return self._body(st, L)
             g = torch.cuda.CUDAGraph()
             Fn.warm_deferred(st.x.device)       # side stream + its workspace exist before the capture
+            pool = self.cache.pool_handle()
             torch.cuda.synchronize()
             if self.cap_stream is None:
                 # the critical path is captured on a high-priority stream: when both are pending, its CTAs are
                 # scheduled before those of the (default-priority) weight-gradient side stream
                 self.cap_stream = torch.cuda.Stream(device=st.x.device, priority=-1)
-            with torch.cuda.graph(g, stream=self.cap_stream):
+            ent = {"stamp": stamp}
+            with torch.cuda.graph(g, pool=pool, stream=self.cap_stream):
                 if self.world == 1:
-                    st.loss, st.norm = self._body(st, L)
+                    ent["loss"], ent["norm"] = self._body(st, L)
                 else:
-                    st.loss = self._fwd_bwd(st, L)
-            st.graph = g
-            if self.world > 1 and self.update_graph is None:
-                torch.cuda.synchronize()
-                gu = torch.cuda.CUDAGraph()
-                step0 = self.opt.step_dev.clone()
-                with torch.cuda.graph(gu):
-                    self.update_norm = self._update()
-                self.update_graph = gu
-                self.opt.step_dev.copy_(step0)     # nothing ran during capture, but keep the counter explicit
-        st.graph.replay()
+                    ent["loss"] = self._fwd_bwd(st, L)
+            ent["graph"] = g
+            self.cache.store(key, ent)
+        if self.world > 1 and (self.update_graph is None or self.update_stamp != stamp[1:]):
+            torch.cuda.synchronize()
+            gu = torch.cuda.CUDAGraph()
+            step0 = self.opt.step_dev.clone()
+            with torch.cuda.graph(gu):
+                self.update_norm = self._update()
+            self.update_graph, self.update_stamp = gu, stamp[1:]
+            self.opt.step_dev.copy_(step0)     # nothing ran during capture, but keep the counter explicit
+        ent["graph"].replay()
         if self.world == 1:
-            return st.loss, st.norm
+            return ent["loss"], ent["norm"]
         torch.distributed.all_reduce(self.opt.flat_grad, group=self.pg)
         self.update_graph.replay()
-        return st.loss, self.update_norm
+        return ent["loss"], self.update_norm
 
     def step(self, xs, ilens, ys):
         return self.run(self.stage(xs, ilens, ys))
 
     # ---- pipelined epoch: the host->device copy of batch i+1 overlaps the train step of batch i
-    def _geometry(self, xs, ilens, ys):
-        m = self.model
-        dev = next(m.parameters()).device
-        host_lens = [int(l) for l in (ilens.tolist() if torch.is_tensor(ilens) else ilens)]
-        T = max(host_lens)
-        ys_in, ys_out = build_targets(ys, m.decoder.bos, m.decoder.eos, m.decoder.pad)
-        B, L = ys_out.shape
-        key = (B, T, xs.shape[2], L)
-        st = self.static.get(key)
-        if st is None:
-            st = self.static[key] = _Static(B, T, xs.shape[2], L, dev)
-        return key, st, host_lens, T, ys_in, ys_out
-
     def upload(self, xs, ilens, ys, slot):
         """Start the H2D copies of one batch into upload slot `slot` (0/1) on the copy stream. Returns a handle."""
         key, st, host_lens, T, ys_in, ys_out = self._geometry(xs, ilens, ys)
         if self.copy_stream is None:
             self.copy_stream = torch.cuda.Stream(device=st.x.device)
-        sl = st.slots[slot]
-        if sl is None:
-            sl = st.slots[slot] = _Slot(st)
-        else:
+        if self.slots is None:
+            self.slots = [_Slot(), _Slot()]
+        sl = self.slots[slot]
+        if sl.used:
             sl.ready.synchronize()                     # the previous upload from these pinned buffers has left the host
-        sl.h_lens.copy_(torch.tensor(host_lens, dtype=torch.int32))
-        sl.h_ys_in.copy_(torch.from_numpy(ys_in))
-        sl.h_ys_out.copy_(torch.from_numpy(ys_out))
+        sl.views = v = _Views(self.arena, *key, prefix=f"slot{slot}.")
+        sl.used = True
+        v.h_lens.copy_(torch.tensor(host_lens, dtype=torch.int32))
+        v.h_ys_in.copy_(torch.from_numpy(ys_in))
+        v.h_ys_out.copy_(torch.from_numpy(ys_out))
         cs = self.copy_stream
         if sl.consumed is not None:
             cs.wait_event(sl.consumed)                 # the step that used this slot has copied it out
         with torch.cuda.stream(cs):
-            sl.x.copy_(xs[:, :T], non_blocking=True)
-            sl.lens.copy_(sl.h_lens, non_blocking=True)
-            sl.ys_in.copy_(sl.h_ys_in, non_blocking=True)
-            sl.ys_out.copy_(sl.h_ys_out, non_blocking=True)
+            v.x.copy_(xs[:, :T], non_blocking=True)
+            v.lens.copy_(v.h_lens, non_blocking=True)
+            v.ys_in.copy_(v.h_ys_in, non_blocking=True)
+            v.ys_out.copy_(v.h_ys_out, non_blocking=True)
             sl.ready.record(cs)
         return key, slot
 
     def run_uploaded(self, handle):
         key, slot = handle
-        st = self.static[key]
-        sl = st.slots[slot]
+        st = _Views(self.arena, *key)
+        sl = self.slots[slot]
+        v = _Views(self.arena, *key, prefix=f"slot{slot}.")     # (the arena may have grown since upload(): re-view)
         main = torch.cuda.current_stream(st.x.device)
         main.wait_event(sl.ready)
-        st.x.copy_(sl.x, non_blocking=True)            # device-to-device: ~10 us for 32 MB
+        st.x.copy_(v.x, non_blocking=True)             # device-to-device: ~10 us for 32 MB
         if self.input_noise_std > 0:
             st.x.add_(torch.randn_like(st.x), alpha=float(self.input_noise_std))
-        st.lens.copy_(sl.lens, non_blocking=True)
-        st.ys_in.copy_(sl.ys_in, non_blocking=True)
-        st.ys_out.copy_(sl.ys_out, non_blocking=True)
+        st.lens.copy_(v.lens, non_blocking=True)
+        st.ys_in.copy_(v.ys_in, non_blocking=True)
+        st.ys_out.copy_(v.ys_out, non_blocking=True)
         sl.consumed = torch.cuda.Event()
         sl.consumed.record(main)
         return self.run(key)
@@ -317,7 +434,7 @@ class SSLTrainer:
     `.grad` fields (dis_opt never steps in this phase)."""
 
     def __init__(self, model, judge, optimizer, max_grad_norm=5.0, unsup_weight=0.001, proportion=0.125,
-                 smooth=True, scaling=3.0, guard_empty_mask=True, use_graph=False):
+                 smooth=True, scaling=3.0, guard_empty_mask=False, use_graph=False, max_graphs=4):
         self.guard_empty_mask = guard_empty_mask
         self.model, self.judge, self.opt = model, judge, optimizer
         self.max_grad_norm, self.unsup_weight, self.proportion = max_grad_norm, unsup_weight, proportion
@@ -325,7 +442,8 @@ class SSLTrainer:
         # graph mode (fused optimiser only): the whole generator step -- both encoder/decoder passes, the judge, the
         # backward with its side-stream weight gradients, clip + AMSGrad -- is captured once per batch geometry
         self.use_graph = use_graph and hasattr(optimizer, "clip_and_step") and os.environ.get("LAS_NO_GRAPH", "0") != "1"
-        self.static = {}
+        self.arena = None
+        self.cache = _GraphCache(max_graphs)
         self.cap_stream = None
         self.world = 1
         if torch.distributed.is_available() and torch.distributed.is_initialized():
@@ -393,23 +511,19 @@ class SSLTrainer:
         return loss.detach(), sup.detach(), unsup.detach(), norm
 
     def stage(self, lab, unlab):
-        """Host -> device copies of one (paired, unpaired) batch pair into the static buffers of its geometry."""
+        """Host -> device copies of one (paired, unpaired) batch pair into the static buffers (arena views)."""
         (xs, ilens, ys), (uxs, uilens) = lab, unlab
         m = self.model
         dev = next(m.parameters()).device
-        host_lens = [int(l) for l in (ilens.tolist() if torch.is_tensor(ilens) else ilens)]
-        uhost = [int(l) for l in (uilens.tolist() if torch.is_tensor(uilens) else uilens)]
+        host_lens, uhost = _host_lens(ilens), _host_lens(uilens)
         T, Tu = max(host_lens), max(uhost)
         ys_in, ys_out = build_targets(ys, m.decoder.bos, m.decoder.eos, m.decoder.pad)
         B, L = ys_out.shape
         Lu = int(uxs.size(1) * self.proportion)                                    # solver.py:469 (padded extent as given)
         key = (B, T, xs.shape[2], L, len(uhost), Tu, Lu)
-        st = self.static.get(key)
-        if st is None:
-            st = self.static[key] = _Static(B, T, xs.shape[2], L, dev)
-            st.ux = torch.zeros(len(uhost), Tu, xs.shape[2], device=dev, dtype=torch.float32)
-            st.ulens = torch.zeros(len(uhost), device=dev, dtype=torch.int32)
-            st.out = None
+        if self.arena is None:
+            self.arena = _Arena(dev)
+        st = self._views(key)
         st.x.copy_(xs[:, :T], non_blocking=True)
         st.ux.copy_(uxs[:, :Tu], non_blocking=True)
         st.lens.copy_(torch.tensor(host_lens, dtype=torch.int32), non_blocking=True)
@@ -418,26 +532,36 @@ class SSLTrainer:
         st.ys_out.copy_(torch.from_numpy(ys_out), non_blocking=True)
         return key
 
+    def _views(self, key):
+        B, T, D, L, Bu, Tu, Lu = key
+        st = _Views(self.arena, B, T, D, L)
+        st.ux = self.arena.get("ux", (Bu, Tu, D), torch.float32)
+        st.ulens = self.arena.get("ulens", (Bu,), torch.int32)
+        return st
+
     def run(self, key):
-        st = self.static[key]
+        st = self._views(key)
         L, Lu = key[3], key[6]
         self.model.train()
         self.judge.train()
-        if st.graph is None:
-            if st.seen == 0:                       # first sight of a geometry: eager (also warms lazy init)
-                st.seen = 1
-                out = self._body_dev(st, L, Lu)
-                return self._finish(out)
+        stamp = (self.arena.gen, _hyper_stamp(self.opt), self.max_grad_norm, self.unsup_weight, self.scaling)
+        ent = self.cache.lookup(key, stamp)
+        if ent is None:
+            if self.cache.sighting(key) == 0:      # first sight of a geometry: eager (also warms lazy init)
+                return self._finish(self._body_dev(st, L, Lu))
             g = torch.cuda.CUDAGraph()
             Fn.warm_deferred(st.x.device)
+            pool = self.cache.pool_handle()
             torch.cuda.synchronize()
             if self.cap_stream is None:
                 self.cap_stream = torch.cuda.Stream(device=st.x.device, priority=-1)
-            with torch.cuda.graph(g, stream=self.cap_stream):
-                st.out = self._body_dev(st, L, Lu)
-            st.graph = g
-        st.graph.replay()
-        return self._finish(st.out)
+            ent = {"stamp": stamp}
+            with torch.cuda.graph(g, pool=pool, stream=self.cap_stream):
+                ent["out"] = self._body_dev(st, L, Lu)
+            ent["graph"] = g
+            self.cache.store(key, ent)
+        ent["graph"].replay()
+        return self._finish(ent["out"])
 
     def _finish(self, out):
         loss, sup, unsup, norm = out
@@ -461,10 +585,18 @@ class SSLTrainer:
 
 class JudgeTrainer:
     """`Solver.judge_train_one_iteration` (solver.py:288-301): masked LM loss over len+5 positions, backward,
-    clip, plain Adam step."""
+    clip, plain Adam step. With the fused optimiser on one GPU the whole step is captured as one CUDA graph per
+    (B, Lmax+5) geometry (a few hundred timestep launches otherwise issued from Python)."""
 
-    def __init__(self, judge, optimizer, max_grad_norm=5.0):
+    def __init__(self, judge, optimizer, max_grad_norm=5.0, use_graph=True, max_graphs=32):
         self.judge, self.opt, self.max_grad_norm = judge, optimizer, max_grad_norm
+        world = 1
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            world = torch.distributed.get_world_size()
+        self.use_graph = (use_graph and hasattr(optimizer, "clip_and_step") and world == 1
+                          and os.environ.get("LAS_NO_GRAPH", "0") != "1")
+        self.arena = None
+        self.cache = _GraphCache(max_graphs)
 
     def losses(self, ys):
         log_probs, probs, _ = self.judge(ys)
@@ -472,8 +604,64 @@ class JudgeTrainer:
         avg_prob = self.judge.mask_and_cal_sum(probs, ys)
         return loss, avg_prob
 
+    # ---- device-resident step (graph mode)
+    def _views(self, B, Lm):
+        g = self.arena.get
+        st = type("JudgeViews", (), {})()
+        st.ys_in, st.ys_out = g("ys_in", (B, Lm), torch.int64), g("ys_out", (B, Lm), torch.int64)
+        st.lens, st.mask, st.inv = g("lens", (B,), torch.int32), g("mask", (B, Lm), torch.float32), g("inv", (1,), torch.float32)
+        return st
+
+    def stage(self, ys):
+        j = self.judge
+        dev = j.embedding.weight.device
+        ys_in, ys_out, lens = j.targets(ys)
+        B, Lm = ys_in.shape
+        if self.arena is None:
+            self.arena = _Arena(dev)
+        st = self._views(B, Lm)
+        mask = (np.arange(Lm)[None, :] < np.asarray(lens)[:, None]).astype(np.float32)   # utils._seq_mask (model.py:565-573)
+        st.ys_in.copy_(torch.from_numpy(ys_in), non_blocking=True)
+        st.ys_out.copy_(torch.from_numpy(ys_out), non_blocking=True)
+        st.lens.copy_(torch.tensor(lens, dtype=torch.int32), non_blocking=True)
+        st.mask.copy_(torch.from_numpy(mask), non_blocking=True)
+        st.inv.copy_(torch.tensor([1.0 / float(sum(lens))]), non_blocking=True)
+        return B, Lm
+
+    def _body(self, st, Lm):
+        log_probs, probs, _ = self.judge.forward_dev(st.ys_in, st.ys_out, st.lens, Lm)
+        loss = -torch.sum(log_probs * st.mask) * st.inv[0]
+        avg_prob = torch.sum(probs * st.mask) * st.inv[0]
+        self.opt.zero_grad()
+        with Fn.deferred_wgrad():
+            loss.backward()
+        norm = self.opt.clip_and_step(self.max_grad_norm, grad_scale=1.0)
+        return loss.detach(), avg_prob.detach(), norm
+
+    def run(self, key):
+        B, Lm = key
+        st = self._views(B, Lm)
+        stamp = (self.arena.gen, _hyper_stamp(self.opt), self.max_grad_norm)
+        ent = self.cache.lookup(key, stamp)
+        if ent is None:
+            if self.cache.sighting(key) == 0:
+                return self._body(st, Lm)
+            g = torch.cuda.CUDAGraph()
+            Fn.warm_deferred(st.mask.device)
+            pool = self.cache.pool_handle()
+            torch.cuda.synchronize()
+            ent = {"stamp": stamp}
+            with torch.cuda.graph(g, pool=pool):
+                ent["out"] = self._body(st, Lm)
+            ent["graph"] = g
+            self.cache.store(key, ent)
+        ent["graph"].replay()
+        return ent["out"]
+
     def step(self, ys):
         self.judge.train()
+        if self.use_graph:
+            return self.run(self.stage(ys))
         loss, avg_prob = self.losses(ys)
         self.opt.zero_grad()
         with Fn.deferred_wgrad():

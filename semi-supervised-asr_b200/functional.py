@@ -720,13 +720,13 @@ class DecoderFn(torch.autograd.Function):
             t0 = 0
             while t0 < L:
                 a.t_begin, a.t_end = t0, min(L, t0 + es["chunk"])
-                _lib.check(_lib.lib().las_dec_fwd(ctypes.byref(a), _lib.stream_ptr()))
+                call("las_dec_fwd", ctypes.byref(a))
                 t0 = a.t_end
                 if t0 < L and bool((pred[:, :t0] == es["eos"]).any(dim=1).all()):     # one host sync per chunk
                     break
             es["last_steps"] = t0
         else:
-            _lib.check(_lib.lib().las_dec_fwd(ctypes.byref(a), _lib.stream_ptr()))
+            call("las_dec_fwd", ctypes.byref(a))
         out_bf = Pk["out_bf"]                                                         # [V, ZC]
         if mode == 0:
             logits = gemm(zc, ZC, 0, out_bf, ZC, 0, B * R, V, ZC, bias=W["out_b"]).view(B, R, V)
@@ -822,7 +822,7 @@ class DecoderFn(torch.autograd.Function):
             a.cbias, a.pbar, a.P = ptr(pers["cbias"]), ptr(pers["Pbar"]), ptr(pers["Pc"])
             if not L_.las_dec_persistent_supported(ctypes.byref(a)):
                 raise _lib.LasError("decoder backward: the forward ran the persistent kernel but the backward would not")
-        _lib.check(_lib.lib().las_dec_bwd(ctypes.byref(a), _lib.stream_ptr()))
+        call("las_dec_bwd", ctypes.byref(a))
         # ---- critical path: gradient w.r.t. the encoder states
         dP_bf = None
         scope = wgrad_scope(ctx.wts, S, pers, (de_all if pers is not None else None), dl, (dl_bf if mode != 2 else None),
@@ -924,6 +924,142 @@ class DecoderFn(torch.autograd.Function):
             glist = sc.deliver([grads[k] for k in DEC_WEIGHTS])
         ctx.saved = None
         return (denc, None, None, None, None, None, None, None, None, None, *glist)
+
+
+# --------------------------------------------------------------------------------------------
+# stand-alone single steps of the reference's module surface (AttLoc.forward model.py:139-173, Decoder.forward_step
+# model.py:283-294, LM.forward_step model.py:535-542). Inference-only thin callers of the per-step kernels: training
+# goes through DecoderFn / LMFn, which run whole sequences. Results carry bf16 rounding of z, c and h (the kernels'
+# state operands are bf16).
+# --------------------------------------------------------------------------------------------
+def attention_precompute(enc_pad, W):
+    """The per-utterance cache of AttLoc (model.py:141-144): (enc_bf [B*Te, H] bf16, P = mlp_enc(enc_h) f32 [B*Te, A])."""
+    B, Te, H = enc_pad.shape
+    enc_bf = cvt_bf16(enc_pad.float().contiguous().reshape(B * Te, H))
+    mlp_enc_bf = cvt_bf16(W["mlp_enc_w"])
+    A = W["mlp_enc_w"].shape[0]
+    return enc_bf, gemm(enc_bf, H, 0, mlp_enc_bf, H, 0, B * Te, A, H, bias=W["mlp_enc_b"])
+
+
+def _step_args(W, enc_bf, Pm, B, Te, K, att_scaling):
+    """las_dec_args for ONE step (L = 1, two rows per buffer) with the attention operands filled in."""
+    dev = enc_bf.device
+    H = enc_bf.shape[1]
+    a, (_, _, _, Hd, O, A, V, E, C) = _dec_common(enc_bf.view(B, Te, H), W, 1, K)
+    a.mode, a.att_scaling, a.smooth_scaling = 1, float(att_scaling), 1.0
+    ZC = Hd + O
+    ws, zc, cx = zeros_many(dev, [((B, 2, Te), torch.float32), ((B * 2 * ZC + 64,), BF16), ((B * 2 * H + 64,), BF16)])
+    e_buf = torch.empty(B, Te, device=dev, dtype=torch.float32)
+    dzf = torch.empty(B, 1, A, device=dev, dtype=torch.float32)
+    ops = dict(mlp_dec_pk=pack_afrag(W["mlp_dec_w"], 0), mlp_o_pk=pack_afrag(W["mlp_o_w"], 0),
+               conv_w=W["conv_w"].reshape(C, -1).contiguous(), mlp_att=W["mlp_att_w"].contiguous(),
+               gvec=W["gvec_w"].reshape(-1).contiguous(), mlp_o_b=W["mlp_o_b"].contiguous())
+    a.enc_h, a.P = ptr(enc_bf), ptr(Pm)
+    a.mlp_dec_pk, a.mlp_o_pk, a.mlp_o_b = ptr(ops["mlp_dec_pk"]), ptr(ops["mlp_o_pk"]), ptr(ops["mlp_o_b"])
+    a.conv_w, a.mlp_att, a.gvec = ptr(ops["conv_w"]), ptr(ops["mlp_att"]), ptr(ops["gvec"])
+    a.ws, a.zc, a.ctx, a.e_buf, a.dzf = ptr(ws), ptr(zc), ptr(cx), ptr(e_buf), ptr(dzf)
+    return a, dict(ws=ws, zc=zc.narrow(0, 0, B * 2 * ZC).view(B, 2, ZC), cx=cx, e_buf=e_buf, dzf=dzf, ops=ops), (Hd, O, A, V, E, C)
+
+
+def _initial_alignment(bufs, enc_lens, att_prev, B, Te):
+    if att_prev is None:
+        call("las_att_init", ptr(lens_tensor(enc_lens, bufs["ws"].device)), B, Te, ptr(bufs["ws"]), 2 * Te)
+    else:
+        bufs["ws"][:, 0].copy_(att_prev.reshape(B, Te))
+
+
+@torch.no_grad()
+def attention_step(W, enc_bf, Pm, B, Te, enc_lens, dec_z, att_prev, K, scaling):
+    """AttLoc.forward for one decoder state: -> (c f32 [B, O], w f32 [B, Te])."""
+    a, bufs, (Hd, O, A, V, E, C) = _step_args(W, enc_bf, Pm, B, Te, K, scaling)
+    _initial_alignment(bufs, enc_lens, att_prev, B, Te)
+    if dec_z is not None:
+        bufs["zc"][:, 1, :Hd].copy_(dec_z.reshape(B, Hd))
+    call("las_att_step", ctypes.byref(a), 0)
+    return bufs["zc"][:, 1, Hd:].float(), bufs["ws"][:, 1].clone()
+
+
+@torch.no_grad()
+def decoder_step(W, enc_bf, Pm, B, Te, enc_lens, emb, dec_z, dec_c, c, w, K, p_drop, att_scaling=2.0):
+    """Decoder.forward_step: dropout([emb; c]) -> LSTMCell -> attention -> output layer.
+    -> (logit [B, V], dec_z [B, Hd], dec_c [B, Hd], c [B, O], w [B, Te]), all f32."""
+    dev = enc_bf.device
+    a, bufs, (Hd, O, A, V, E, C) = _step_args(W, enc_bf, Pm, B, Te, K, att_scaling)
+    ZC, Ep = Hd + O, _r16(E)
+    _initial_alignment(bufs, enc_lens, w, B, Te)
+    zc = bufs["zc"]
+    zc[:, 0, :Hd].copy_(dec_z.reshape(B, Hd))
+    zc[:, 0, Hd:].copy_(c.reshape(B, O))
+    c_state = dec_c.reshape(B, Hd).float().clone()
+    emb_op = torch.zeros(B * 2 * Ep + 64, device=dev, dtype=BF16)
+    emb_rows = emb_op[:B * 2 * Ep].view(B, 2, Ep)
+    emb_rows[:, 0, :E].copy_(emb.reshape(B, E))
+    wr_cat = torch.cat([W["w_hh"], W["w_ih"][:, E:]], dim=1).contiguous()
+    ops = dict(wr_pk=pack_afrag(wr_cat, 1, Hd), we_pk=pack_afrag(W["w_ih"][:, :E].contiguous(), 1, Hd),
+               out_pk=pack_afrag(W["out_w"], 0), cell_bias=(W["b_ih"] + W["b_hh"]).contiguous())
+    logits = torch.zeros(B, 2, V, device=dev, dtype=torch.float32)
+    pred = torch.zeros(B, 1, device=dev, dtype=torch.int64)
+    gates = torch.empty(B, 1, Hd, 4, device=dev, dtype=torch.float16)
+    csave = torch.empty(B, 1, Hd, device=dev, dtype=torch.float32)
+    a.wr_pk, a.we_pk, a.out_pk, a.cell_bias, a.out_b = (ptr(ops["wr_pk"]), ptr(ops["we_pk"]), ptr(ops["out_pk"]),
+                                                       ptr(ops["cell_bias"]), ptr(W["out_b"]))
+    a.emb_w, a.emb_op, a.logits, a.pred, a.c_state = ptr(W["emb_w"]), ptr(emb_op), ptr(logits), ptr(pred), ptr(c_state)
+    a.gates_save, a.c_save = ptr(gates), ptr(csave)
+    zcd = None
+    if p_drop > 0:                                     # model.py:284-285: dropout over the concatenated [emb; c]
+        site0 = new_sites()
+        a.drop_p, a.drop_site, a.seed_dev = float(p_drop), site0, ptr(dropout_seed(dev))
+        dropout_(emb_op, B, 2, E, 2 * Ep, Ep, 0, p_drop, site0 + 1)
+        zcd = torch.zeros(B * 2 * ZC + 64, device=dev, dtype=BF16)
+        zcd[:B * 2 * ZC].view(B, 2, ZC).copy_(zc)
+        dropout_(zcd[Hd:], B, 2, O, 2 * ZC, ZC, 0, p_drop, site0)
+        a.zcd = ptr(zcd)
+    call("las_dec_fwd", ctypes.byref(a))
+    return logits[:, 1].clone(), zc[:, 1, :Hd].float(), c_state, zc[:, 1, Hd:].float(), bufs["ws"][:, 1].clone()
+
+
+def lm_step_operands(lstm_weights, out_w):
+    """Weight packs of LM.forward_step (build once per decode): per layer (whh_pk, wih_pk, bias, H, Kin), output pack."""
+    layers = []
+    for w_ih, w_hh, b_ih, b_hh in lstm_weights:
+        H = w_hh.shape[1]
+        layers.append((pack_afrag(w_hh, 1, H), pack_afrag(w_ih, 1, H), (b_ih + b_hh).contiguous(), H, w_ih.shape[1]))
+    return layers, pack_afrag(out_w, 0)
+
+
+@torch.no_grad()
+def lm_step(ops, out_b, V, x, h, c, p_drop=0.0):
+    """One timestep of the n-layer LM LSTM with explicit state + the output layer (model.py:535-542).
+    x f32 [B, E]; h, c f32 [n_layers, B, H] or None (zeros). -> (logit [B, V], h, c) f32."""
+    layers, out_pk = ops
+    dev = x.device
+    B = x.shape[0]
+    n = len(layers)
+    H = layers[0][3]
+    h_new = torch.empty(n, B, H, device=dev, dtype=torch.float32)
+    c_new = torch.zeros(n, B, H, device=dev, dtype=torch.float32) if c is None else c.float().clone().contiguous()
+    cur = x.reshape(B, -1).float()
+    site0 = new_sites() if p_drop > 0 else 0
+    for l, (whh_pk, wih_pk, bias, Hl, Kin) in enumerate(layers):
+        Kp, Hp = _r16(Kin), _r16(Hl)
+        x_bf = torch.zeros(B, Kp, device=dev, dtype=BF16)
+        x_bf[:, :Kin].copy_(cur)
+        h_in = torch.zeros(B, Hp, device=dev, dtype=BF16)
+        if h is not None:
+            h_in[:, :Hl].copy_(h[l])
+        h_out = torch.zeros(B, Hp, device=dev, dtype=BF16)
+        call("las_lstm_cell_step", ptr(whh_pk), ptr(wih_pk), ptr(bias), ptr(h_in), Hp, ptr(x_bf), Kp, Kin, ptr(c_new[l]),
+             ptr(h_out), Hp, B, Hl)
+        h_new[l].copy_(h_out[:, :Hl])
+        cur = h_out[:, :Hl].float()
+        if p_drop > 0 and l + 1 < n:                   # nn.LSTM(dropout=p) between layers, training mode only
+            cur = cur.contiguous()
+            dropout_(cur, B, 1, Hl, Hl, Hl, 0, p_drop, site0 + l)
+    top = torch.zeros(B, _r16(H), device=dev, dtype=BF16)
+    top[:, :H].copy_(cur)
+    logit = torch.empty(B, V, device=dev, dtype=torch.float32)
+    call("las_smallmm", ptr(out_pk), V, H, ptr(top), 0, top.shape[1], B, ptr(out_b), None, 0, ptr(logit), V, None, 0)
+    return logit, h_new, c_new
 
 
 # --------------------------------------------------------------------------------------------

@@ -124,6 +124,28 @@ class AttLoc(torch.nn.Module):
         return [self.mlp_enc.weight, self.mlp_enc.bias, self.mlp_dec.weight, self.mlp_att.weight,
                 self.loc_conv.weight, self.gvec.weight, self.mlp_o.weight, self.mlp_o.bias]
 
+    def _wdict(self):
+        return dict(zip(("mlp_enc_w", "mlp_enc_b", "mlp_dec_w", "mlp_att_w", "conv_w", "gvec_w", "mlp_o_w", "mlp_o_b"),
+                        self._weights()))
+
+    def _precompute(self, enc_pad):
+        """model.py:141-144: enc_h and mlp_enc(enc_h) are cached until reset()."""
+        if self.pre_compute_enc_h is None:
+            self.enc_h = enc_pad
+            self.enc_length = enc_pad.size(1)
+            self._enc_bf, P = Fn.attention_precompute(enc_pad, self._wdict())
+            self.pre_compute_enc_h = P.view(enc_pad.size(0), enc_pad.size(1), -1)
+        return self._enc_bf, self.pre_compute_enc_h.view(-1, self.att_dim)
+
+    def forward(self, enc_pad, enc_len, dec_z, att_prev, scaling=2.0):
+        """model.py:139-173, one attention read (inference-only; the training path runs the attention inside the
+        fused decoder loop). -> (c [B, att_odim], w [B, Te])."""
+        enc_pad = cc(enc_pad)
+        B, Te, _ = enc_pad.shape
+        enc_bf, P = self._precompute(enc_pad)
+        W = dict(self._wdict(), emb_w=enc_pad.new_zeros(1, 1), w_hh=enc_pad.new_zeros(4 * self.decoder_dim, self.decoder_dim))
+        return Fn.attention_step(W, enc_bf, P, B, Te, enc_len, dec_z, att_prev, self.conv_kernel_size, scaling)
+
 
 class Decoder(torch.nn.Module):
     """model.py:256-367."""
@@ -153,6 +175,16 @@ class Decoder(torch.nn.Module):
         att = self.attention
         return [self.embedding.weight, self.LSTMCell.weight_ih, self.LSTMCell.weight_hh, self.LSTMCell.bias_ih,
                 self.LSTMCell.bias_hh, self.output_layer.weight, self.output_layer.bias] + att._weights()
+
+    def forward_step(self, emb, dec_z, dec_c, c, w, enc_pad, enc_len):
+        """model.py:283-294, one decoder step with explicit state (inference-only; `Decoder.forward` runs whole
+        sequences through the fused kernels). -> (logit, dec_z, dec_c, c, w)."""
+        enc_pad = cc(enc_pad)
+        B, Te, _ = enc_pad.shape
+        enc_bf, P = self.attention._precompute(enc_pad)
+        W = dict(zip(Fn.DEC_WEIGHTS, self._weights()))
+        p = float(self.dropout_rate) if self.training else 0.0
+        return Fn.decoder_step(W, enc_bf, P, B, Te, enc_len, cc(emb), dec_z, dec_c, c, w, self.attention.conv_kernel_size, p)
 
     def forward(self, enc_pad, enc_len, ys=None, tf_rate=1.0, max_dec_timesteps=500, sample=False, smooth=False,
                 scaling=1.0, label_smoothing=True):
@@ -265,20 +297,26 @@ class LM(torch.nn.Module):
                   getattr(self.LSTM, f"bias_ih_l{l}"), getattr(self.LSTM, f"bias_hh_l{l}")]
         return w + [self.output_layer.weight, self.output_layer.bias]
 
+    def targets(self, ys):
+        """model.py:496-499: ys_in = [BOS, y], ys_out = [y, EOS], both EOS-padded to max(len) + 5; lens = len + 5.
+        -> (ys_in, ys_out) int64 numpy [B, Lm], lens list[int]."""
+        ys_host = [y.detach().cpu().numpy().astype(np.int64) if torch.is_tensor(y) else np.asarray(y, np.int64) for y in ys]
+        B = len(ys_host)
+        Lm = max(len(y) for y in ys_host) + 5
+        ys_in = np.full((B, Lm), self.eos, dtype=np.int64)
+        ys_out = np.full((B, Lm), self.eos, dtype=np.int64)
+        for b, y in enumerate(ys_host):
+            ys_in[b, 0] = self.bos
+            ys_in[b, 1:1 + len(y)] = y
+            ys_out[b, :len(y)] = y
+        return ys_in, ys_out, [len(y) + 5 for y in ys_host]
+
     def forward(self, ys=None, discrete_input=True):
         dev = self.embedding.weight.device
         if discrete_input:
-            ys_host = [y.detach().cpu().numpy().astype(np.int64) if torch.is_tensor(y) else np.asarray(y, np.int64)
-                       for y in ys]
-            B = len(ys_host)
-            Lm = max(len(y) for y in ys_host) + 5                          # model.py:496-499
-            ys_in = np.full((B, Lm), self.eos, dtype=np.int64)
-            ys_out = np.full((B, Lm), self.eos, dtype=np.int64)
-            for b, y in enumerate(ys_host):
-                ys_in[b, 0] = self.bos
-                ys_in[b, 1:1 + len(y)] = y
-                ys_out[b, :len(y)] = y
-            lens = Fn.lens_tensor([len(y) + 5 for y in ys_host], dev)
+            ys_in, ys_out, lens = self.targets(ys)
+            Lm = ys_in.shape[1]
+            lens = Fn.lens_tensor(lens, dev)
             ys_in_dev = torch.from_numpy(ys_in).to(dev)
             ys_out_dev = torch.from_numpy(ys_out).to(dev)
         else:
@@ -288,12 +326,47 @@ class LM(torch.nn.Module):
             ys_out_dev = ys.contiguous()
             lens = None
             Lm = ys.size(1)
+        return self.forward_dev(ys_in_dev, ys_out_dev, lens, Lm)
+
+    def forward_dev(self, ys_in_dev, ys_out_dev, lens, Lm):
+        """Device-resident variant (no host work; CUDA-graph capturable)."""
+        dev = self.embedding.weight.device
         p = float(self.dropout_rate) if self.training else 0.0
         logits = Fn.LMFn.apply(ys_in_dev, lens, self.n_layers, self.pad, p, *self._weights())
         ls = self.ls_weight if (self.ls_weight > 0 and self.training) else 0.0
         dist = self.vlabeldist.to(dev) if ls > 0 else None
         ys_log_probs, ys_probs, predictions = Fn.CELabelSmoothFn.apply(logits, ys_out_dev, dist, ls, 0, Lm)
         return ys_log_probs, ys_probs, predictions
+
+    def _step_ops(self):
+        lw = [tuple(getattr(self.LSTM, f"{n}_l{l}") for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"))
+              for l in range(self.n_layers)]
+        return Fn.lm_step_operands(lw, self.output_layer.weight)
+
+    def forward_step(self, emb, dec_z=None, dec_c=None, _ops=None):
+        """model.py:535-542 ("only use in decode stage"): one LSTM timestep with explicit state + output layer.
+        emb [B, 1, E]; dec_z / dec_c [n_layers, B, H] or None. -> (logit [B, V], dec_z, dec_c)."""
+        emb = cc(emb)
+        p = float(self.dropout_rate) if (self.training and self.n_layers > 1) else 0.0
+        return Fn.lm_step(_ops or self._step_ops(), self.output_layer.bias, self.output_dim, emb.reshape(emb.size(0), -1),
+                          dec_z, dec_c, p)
+
+    @torch.no_grad()
+    def decode(self, n_samples=5, sample=False, max_dec_timesteps=500):
+        """model.py:544-563: free-running generation from <BOS>, greedy or sampled. -> predictions int64 [n, steps]."""
+        dev = self.embedding.weight.device
+        ops = self._step_ops()
+        tok = torch.full((n_samples,), self.bos, device=dev, dtype=torch.int64)
+        dec_z, dec_c, predictions = None, None, []
+        for _ in range(max_dec_timesteps):
+            emb = self.embedding.weight.index_select(0, tok).unsqueeze(1)
+            logit, dec_z, dec_c = self.forward_step(emb, dec_z, dec_c, _ops=ops)
+            if sample:
+                tok = torch.multinomial(torch.softmax(logit, dim=-1), 1).squeeze(1)   # Categorical(logits).sample()
+            else:
+                tok = torch.argmax(logit, dim=-1)
+            predictions.append(tok)
+        return torch.stack(predictions, dim=1)
 
     def mask_and_cal_sum(self, log_probs, ys, mask=None):
         if mask is None:

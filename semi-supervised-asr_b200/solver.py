@@ -8,7 +8,8 @@ engines in engine.py; everything else here is host glue.
 
 Data parallelism (new; the reference is single-process): when torch.distributed is initialised every rank builds
 the same Solver, `batch_size` is the per-rank batch, batches are dealt by data.BatchLoader and gradients are
-summed with one NCCL all-reduce per step (engine.py). Rank 0 alone validates, logs and writes checkpoints.
+summed with one NCCL all-reduce per step (engine.py). Every rank decodes the (small) dev set itself -- all ranks
+therefore agree on the best-CER bookkeeping without a broadcast -- and rank 0 alone logs and writes checkpoints.
 """
 import os
 import pickle
@@ -57,7 +58,8 @@ class Solver(object):
             torch.save(self.model.state_dict(), f"{model_path}.ckpt")
             torch.save(self.gen_opt.state_dict(), f"{model_path}.opt")
             try:      # the sidecar is an addition to the reference's two files; it must never cost a checkpoint
-                save_resume_state(f"{model_path}.resume", getattr(self, "progress", {}), Fn.current_dropout_seed())
+                save_resume_state(f"{model_path}.resume", getattr(self, "progress", {}), Fn.current_dropout_seed(),
+                                  loader_rng={n: getattr(self, n).rng_state() for n in self._TRAIN_LOADERS})
             except Exception as e:      # noqa: BLE001
                 self.say(f"warning: resume sidecar not written ({e})")
 
@@ -83,6 +85,9 @@ class Solver(object):
                 self.progress = dict(state["progress"])
                 if state.get("dropout_seed") is not None:
                     Fn.set_dropout_seed(state["dropout_seed"], next(self.model.parameters()).device)
+                for n, rs in (state.get("loader_rng") or {}).items():
+                    if hasattr(self, n):
+                        getattr(self, n).set_rng_state(rs)
 
     def load_judge(self, model_path, load_optimizer):
         self.judge.load_state_dict(torch.load(f"{model_path}.judge.ckpt"))
@@ -104,11 +109,17 @@ class Solver(object):
         frames = sum(x.shape[0] for x, _ in self.train_lab_dataset)
         return sum(len(y) for _, y in self.train_lab_dataset) / frames
 
+    _TRAIN_LOADERS = ("train_lab_loader", "train_unlab_x_loader", "train_unlab_y_loader")
+
     def get_data_loaders(self):
         c = self.config
         root = c["dataset_root_dir"]
         mk = lambda name, **kw: PickleDataset(os.path.join(root, f"{name}.pkl"), **kw)
-        dp = dict(rank=self.rank, world=self.world)
+        # not reference keys: `loader_prefetch: n` collates n batches ahead on a background thread into page-locked
+        # buffers (the reference's DataLoader runs with num_workers=0); `bucket_batches: true` shuffles whole batches
+        # of length-sorted utterances instead of utterances
+        dp = dict(rank=self.rank, world=self.world, prefetch=int(c.get("loader_prefetch", 2)),
+                  bucket=bool(c.get("bucket_batches", False)))
         self.train_lab_dataset = mk(c["labeled_set"], config=c, sort=True)
         self.train_lab_loader = BatchLoader(self.train_lab_dataset, c["batch_size"], c["shuffle"], False, collate, **dp)
         self.train_unlab_x_dataset = mk(c["unlabeled_speech_set"], config=c, sort=True)
@@ -149,8 +160,16 @@ class Solver(object):
                                                     use_graph=c.get("cuda_graph", True))
         self.ssl_trainer = engine.SSLTrainer(self.model, self.judge, self.gen_opt, max_grad_norm=c["max_grad_norm"],
                                              unsup_weight=c["unsup_weight"], proportion=self.proportion,
-                                             smooth=c["smooth_embedding"], scaling=c["softmax_scaling"])
+                                             smooth=c["smooth_embedding"], scaling=c["softmax_scaling"],
+                                             # not a reference key: `guard_empty_mask: true` replaces solver.py:478's 0/0
+                                             # (every free-run token == <EOS>) by 0; the default is the reference's NaN
+                                             guard_empty_mask=bool(c.get("guard_empty_mask", False)))
         self.judge_trainer = engine.JudgeTrainer(self.judge, self.dis_opt, max_grad_norm=c["max_grad_norm"])
+        if len(self.train_lab_dataset):
+            # staging buffers sized once for the largest batch this run can draw: nothing is re-allocated per geometry
+            Tmax = max(f.shape[0] for f, _ in self.train_lab_dataset)
+            Lmax = max(len(y) for _, y in self.train_lab_dataset) + 1
+            self.sup_trainer.reserve(c["batch_size"], Tmax, c["input_dim"], Lmax)
 
     # ------------------------------------------------------------------ evaluation (solver.py:176-286)
     def ind2sent(self, all_prediction, all_ys):
@@ -167,8 +186,12 @@ class Solver(object):
             ys.sort(key=lambda y: len(y), reverse=True)
             log_probs, _, _ = self.judge(ys)
             total += float(-self.judge.mask_and_cal_sum(log_probs, ys))
+        # solver.py:200-206: five sampled continuations from <BOS>, for the text summaries
+        predictions = self.judge.decode(n_samples=5, sample=True, max_dec_timesteps=int(self.config.get("lm_decode_steps", 500)))
+        sents = to_sents(remove_pad_eos(predictions.cpu().numpy().tolist(), eos=self.vocab["<EOS>"]), self.vocab,
+                         self.non_lang_syms)
         self.judge.train()
-        return total / max(1, len(self.dev_loader)), []      # LM.decode sampling (model.py:544-563) is out of scope
+        return total / max(1, len(self.dev_loader)), sents
 
     @torch.no_grad()
     def _decode_set(self, loader, with_loss):

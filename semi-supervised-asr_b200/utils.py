@@ -138,10 +138,13 @@ class Logger:
 # numpy, and the device seed the dropout masks are a function of) are lost. They go into `<path>.resume`, a plain
 # pickle of python / numpy objects next to the two reference files, which stay byte-compatible with the reference.
 # ------------------------------------------------------------------------------------------------------------------
-def save_resume_state(path, progress, dropout_seed=None):
+def save_resume_state(path, progress, dropout_seed=None, loader_rng=None):
+    """`loader_rng`: {loader name: numpy RandomState state} -- the shuffle streams of the data.BatchLoader objects, so a
+    resumed run draws the permutations the uninterrupted run would have drawn next."""
     import pickle
     payload = {"version": 1, "progress": dict(progress), "torch_rng": torch.get_rng_state().numpy().tobytes(),
-               "numpy_rng": np.random.get_state(), "dropout_seed": None if dropout_seed is None else int(dropout_seed)}
+               "numpy_rng": np.random.get_state(), "dropout_seed": None if dropout_seed is None else int(dropout_seed),
+               "loader_rng": dict(loader_rng or {})}
     tmp = f"{path}.tmp"
     with open(tmp, "wb") as f:
         pickle.dump(payload, f)

@@ -118,10 +118,73 @@ def test_on_device_input_noise():
     batch = _batch(G)
     _, _, tr = _trainer(G, use_graph=False)
     key = tr.stage(*batch)
-    clean = tr.static[key].x.clone()
+    clean = tr.staged(key).x.clone()
     tr.input_noise_std = 0.5
     key = tr.stage(*batch)
-    noise = (tr.static[key].x - clean).flatten()
+    noise = (tr.staged(key).x - clean).flatten()
     assert abs(float(noise.mean())) < 0.05 and abs(float(noise.std()) - 0.5) < 0.05
     loss, _ = tr.run(key)
     assert bool(torch.isfinite(loss))
+
+
+def test_geometry_stream_keeps_device_memory_flat():
+    """Reference batches almost never repeat a (B, Tmax, Lmax) geometry (shuffle: True, T 30..2300, L 2..250). The
+    staging buffers are views of max-extent arenas and captured graphs live in a bounded LRU sharing one pool: 300
+    distinct geometries must not grow device memory (the first version allocated ~100 MB per new geometry)."""
+    G = load_golden("sup_small_odd")
+    g = G["raw"]
+    m, opt, tr = _trainer(G, use_graph=True)
+    tr.cache.max_graphs = 4
+    D = g["x"].shape[2]
+    rng = np.random.RandomState(0)
+    V = m.decoder.output_layer.bias.numel()
+    tr.reserve(4, 64, D, 14)
+
+    def batch(T, L):
+        lens = sorted([T] + [int(rng.randint(T // 2 + 1, T + 1)) for _ in range(3)], reverse=True)
+        x = np.zeros((4, T, D), dtype=np.float32)
+        for b, l in enumerate(lens):
+            x[b, :l] = rng.randn(l, D)
+        ys = [torch.from_numpy(rng.randint(3, V, size=L if b == 0 else int(rng.randint(1, L + 1))).astype(np.int64)) for b in range(4)]
+        return torch.from_numpy(x), lens, ys
+
+    geoms = [(T, L) for T in range(20, 60) for L in range(3, 13)]
+    rng.shuffle(geoms)
+    geoms = geoms[:300]
+    mem = []
+    for i, (T, L) in enumerate(geoms):
+        loss, _ = tr.step(*batch(T, L))
+        if i in (4, 5, 6):                       # a repeated geometry is captured on its second sighting, replayed after
+            loss, _ = tr.step(*batch(*geoms[4]))
+        if i % 50 == 49:
+            torch.cuda.synchronize()
+            assert bool(torch.isfinite(loss))
+            mem.append(torch.cuda.memory_allocated())
+    assert tr.cache.captures >= 1 and len(tr.cache.graphs) <= 4
+    assert max(mem[1:]) - mem[1] < 8 << 20, mem    # flat after the first 100 geometries (allocator noise only)
+    assert tr.arena.gen == 0                       # reserve() sized the arenas: nothing ever moved
+    # a batch larger than anything reserved grows the arenas once and drops the captured graphs
+    tr.step(*batch(80, 13))
+    assert tr.arena.gen >= 1
+    loss, _ = tr.step(*batch(*geoms[4]))
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(loss))
+
+
+def test_learning_rate_change_reaches_a_captured_step():
+    """Optimiser hyper-parameters are baked into captured launches by value: a changed lr must invalidate the graph
+    (solver.py:519 adjust_learning_rate before ssl_train) instead of being silently ignored on replay."""
+    G = load_golden("sup_small_odd")
+    batch = _batch(G)
+    m, opt, tr = _trainer(G, use_graph=True)
+    for _ in range(3):
+        tr.step(*batch)                              # eager, capture, replay
+    assert tr.cache.captures == 1
+    p = next(m.parameters())
+    before = p.detach().clone()
+    opt.param_groups[0]["lr"] = 0.0
+    tr.step(*batch)
+    torch.cuda.synchronize()
+    assert tr.cache.captures == 2                    # re-captured with the new value
+    wd_only = (p.detach() - before).abs().max()
+    assert float(wd_only) == 0.0, float(wd_only)     # lr = 0: nothing moves

@@ -101,6 +101,82 @@ def test_batch_dealing_partitions_and_balances():
         assert sorted(ia + ib, reverse=True) == ig and ia == ig[0::2] and ib == ig[1::2]
 
 
+def _toy_items(n, seed=3):
+    rng = np.random.RandomState(seed)
+    return [(rng.randn(int(T), 2).astype(np.float32), list(range(3, 3 + int(T) // 7 + 1))) for T in rng.randint(5, 60, size=n)]
+
+
+def test_every_rank_takes_the_same_number_of_steps_on_a_short_tail():
+    """A tail global batch with fewer utterances than ranks used to leave the high ranks without a shard (they skipped
+    the step while the others entered the all-reduce: deadlock). Now it is dropped on every rank."""
+    D = pkg("data")
+    world, bs = 4, 3
+    for n in (12, 13, 14, 15, 16, 25):
+        items = _toy_items(n)
+        per_rank = [list(D.BatchLoader(items, bs, True, False, D.collate, rank=r, world=world, seed=11)) for r in range(world)]
+        steps = [len(b) for b in per_rank]
+        assert len(set(steps)) == 1 and steps[0] == len(D.BatchLoader(items, bs, True, False, D.collate, rank=0, world=world)), (n, steps)
+        assert all(len(ilens) >= 1 for b in per_rank for _, ilens, _ in b)
+        seen = sum(len(ilens) for b in per_rank for _, ilens, _ in b)
+        tail = n % (bs * world)
+        assert seen == (n - tail if 0 < tail < world else n), (n, seen)
+    # world == 1 (the reference's case) never drops anything
+    assert sum(len(i) for _, i, _ in D.BatchLoader(_toy_items(13), 4, True, False, D.collate)) == 13
+
+
+def test_prefetch_thread_yields_the_same_batches():
+    D = pkg("data")
+    items = _toy_items(23)
+    a = list(D.BatchLoader(items, 4, True, False, D.collate, seed=5))
+    b = list(D.BatchLoader(items, 4, True, False, D.collate, seed=5, prefetch=2, pin=False))
+    assert len(a) == len(b) == 6
+    for (xa, ia, ya), (xb, ib, yb) in zip(a, b):
+        assert torch.equal(xa, xb) and ia == ib and all(torch.equal(u, v) for u, v in zip(ya, yb))
+    # collating into a caller-provided flat buffer (the pinned ring) gives the same padded batch, stale contents cleared
+    buf = torch.full((4 * 60 * 2 + 7,), 9.0)
+    xs, ilens, _ = D.collate(items[:4], out=buf)
+    ref, ilens2, _ = D.collate(items[:4])
+    assert torch.equal(xs, ref) and ilens == ilens2 and xs.data_ptr() == buf.data_ptr()
+    # an abandoned iterator stops its worker
+    it = iter(D.BatchLoader(items, 4, True, False, D.collate, seed=5, prefetch=1, pin=False))
+    next(it)
+    it.close()
+
+    class Boom:
+        def __len__(self):
+            return 8
+
+        def __getitem__(self, i):
+            raise KeyError("broken item")
+
+    with pytest.raises(KeyError):
+        list(D.BatchLoader(Boom(), 4, False, False, D.collate, prefetch=2, pin=False))
+
+
+def test_bucketed_batches_hold_neighbouring_lengths():
+    D = pkg("data")
+    items = sorted(_toy_items(40), key=lambda it: it[0].shape[0])
+    batches = list(D.BatchLoader(items, 8, True, False, D.collate, seed=1, bucket=True))
+    assert len(batches) == 5
+    spans = sorted((min(i), max(i)) for _, i, _ in batches)
+    assert all(spans[k][1] <= spans[k + 1][0] for k in range(4))          # disjoint length ranges
+    assert sorted(l for _, i, _ in batches for l in i) == [it[0].shape[0] for it in items]
+    order = [max(i) for _, i, _ in batches]
+    assert order != sorted(order)                                         # ... visited in shuffled order
+
+
+def test_loader_shuffle_stream_round_trips_through_the_sidecar(tmp_path):
+    D, U = pkg("data"), pkg("utils")
+    items = _toy_items(20)
+    ld = D.BatchLoader(items, 4, True, False, D.collate, seed=9)
+    list(ld)                                                              # epoch 0 consumed
+    U.save_resume_state(str(tmp_path / "m.resume"), {"epoch": 0}, loader_rng={"train_lab_loader": ld.rng_state()})
+    want = [i for _, i, _ in ld]                                          # epoch 1 of the uninterrupted run
+    ld2 = D.BatchLoader(items, 4, True, False, D.collate, seed=9)
+    ld2.set_rng_state(U.load_resume_state(str(tmp_path / "m.resume"), restore_rng=False)["loader_rng"]["train_lab_loader"])
+    assert [i for _, i, _ in ld2] == want
+
+
 GLOO_WORKER = r"""
 import os, sys
 sys.path.insert(0, sys.argv[1])
@@ -119,6 +195,15 @@ for xs, ilens, ys in D.BatchLoader(items, 3, True, False, D.collate, rank=rank, 
 dist.all_reduce(tot); dist.all_reduce(n)
 ref = sum(float(torch.from_numpy(f).double().sum()) for f, _ in items)
 assert int(n) == len(items) and abs(float(tot) - ref) < 1e-9, (float(n), float(tot), ref)
+# a dataset whose tail global batch (1 utterance) is smaller than the world: every rank must take the same number of
+# steps, each ending in a collective -- this used to hang
+items13 = items + [(rng.randn(9, 2).astype(np.float32), [3])]
+steps = 0
+for xs, ilens, ys in D.BatchLoader(items13, 3, True, False, D.collate, rank=rank, world=world, seed=5, prefetch=1, pin=False):
+    t = torch.ones(1); dist.all_reduce(t); assert int(t) == world
+    steps += 1
+cnt = torch.tensor([float(steps)]); dist.all_reduce(cnt, op=dist.ReduceOp.MAX)
+assert steps == int(cnt) == 2, (steps, int(cnt))
 # gradient averaging as engine._clip_and_step does it for a stock optimiser
 p = torch.nn.Parameter(torch.zeros(4)); p.grad = torch.full((4,), float(rank + 1))
 opt = torch.optim.SGD([p], lr=1.0)

@@ -79,7 +79,7 @@ def config4(args, dev):
     gen_opt = OPT.FusedAdam(m.parameters(), lr=1e-4, weight_decay=1e-6, amsgrad=True)
     dis_opt = OPT.FusedAdam(lm.parameters(), lr=2e-4)
     ssl = E.SSLTrainer(m, lm, gen_opt, max_grad_norm=5.0, unsup_weight=0.001, proportion=0.125, smooth=True, scaling=3.0,
-                       use_graph=not args.no_graph)
+                       use_graph=not args.no_graph, guard_empty_mask=True)
     jt = E.JudgeTrainer(lm, dis_opt, max_grad_norm=5.0)
     lab = (torch.from_numpy(x).to(dev), lens, [torch.from_numpy(y).to(dev) for y in ys])
     unlab = (torch.from_numpy(ux).to(dev), ulens)
@@ -101,7 +101,7 @@ def config4(args, dev):
          "loss": first[0], "sup": first[1], "unsup": first[2], "steps": args.steps, "dropout": args.dropout,
          "free_run_diag": diag, "cuda_graph": not args.no_graph},
         {"config": 4, "workload": "judge (LM 2x640) pre-train step on a text batch of 32 (L<=125+5)", "ms_per_step": ms_j,
-         "n_gpus": WORLD, "texts_per_s": 32 * WORLD / (ms_j * 1e-3), "steps": args.steps, "cuda_graph": False},
+         "n_gpus": WORLD, "texts_per_s": 32 * WORLD / (ms_j * 1e-3), "steps": args.steps, "cuda_graph": jt.use_graph},
     ]
 
 
