@@ -60,6 +60,23 @@ def synth_batch(rng, B, Tmax, D, V):
     return x, lens, ys
 
 
+def synth_shard(seed, B, world, rank, Tmax, D, V):
+    """One GLOBAL batch of B * world utterances under synth_batch's length law (the same on every rank), dealt over
+    the ranks the way data.shard_items deals a real batch (sorted by frame count, round-robin), so the ranks of a
+    data-parallel run get DIFFERENT (Tmax, Lmax) geometries and the straggler cost of uneven shards is in the
+    measurement. Only this rank's utterances are materialised. -> (x [B, T_r, D], lens, ys, all_ys)"""
+    rng = np.random.RandomState(seed)
+    n = B * world
+    lens = sorted([Tmax] + [int(rng.randint(int(0.4 * Tmax), Tmax + 1)) for _ in range(n - 1)], reverse=True)
+    all_ys = [rng.randint(3, V, size=int(np.clip(round(0.125 * l), 2, 250))).astype(np.int64) for l in lens]
+    mine = list(range(n))[rank::world]                   # data.shard_items on a batch already sorted descending
+    T = lens[mine[0]]
+    x = np.zeros((len(mine), T, D), dtype=np.float32)
+    for b, i in enumerate(mine):
+        x[b, :lens[i]] = np.random.RandomState(seed * 100003 + i).standard_normal((lens[i], D)).astype(np.float32)
+    return x, [lens[i] for i in mine], [all_ys[i] for i in mine], all_ys
+
+
 def labeldist_of(ys, V):
     cnt = np.zeros(V)
     for y in ys:
@@ -250,11 +267,10 @@ def main():
     OPT = importlib.import_module(PKG + ".optim")
     LIB = importlib.import_module(PKG + "._lib")
 
-    rng = np.random.RandomState(1234 + rank)
-    nb = 4                                             # distinct synthetic batches, cycled
-    batches = [synth_batch(rng, args.batch, args.tmax, CFG["input_dim"], CFG["V"]) for _ in range(nb)]
-    # one geometry for all batches (graph replay): pad label lists to a common Lmax via the longest utterance
-    ld = labeldist_of([y for b in batches for y in b[2]], CFG["V"])
+    nb = 4                                             # distinct synthetic global batches, cycled
+    shards = [synth_shard(1234 + k, args.batch, world, rank, args.tmax, CFG["input_dim"], CFG["V"]) for k in range(nb)]
+    batches = [s[:3] for s in shards]
+    ld = labeldist_of([y for s in shards for y in s[3]], CFG["V"])
     torch.manual_seed(1234)
     m = M.E2E(**_cfg_kwargs(ld, args.dropout)).to(dev)
     if world > 1:                                      # identical initial weights on every rank
@@ -364,6 +380,8 @@ def main():
         "config": {"workload": workload, "global_batch": args.batch * world, "parallelism": f"dp{world}",
                    "precision": "bf16 MMA operands, f32 accumulate/state/master weights", "dropout": args.dropout,
                    "cuda_graph": not args.no_graph,
+                   "batches": f"{nb} global batches of {args.batch * world} utterances cycled, each dealt over the ranks by "
+                              "sorted round-robin (data.shard_items): per-rank Tmax/Lmax differ",
                    "l2": "working set per step (>1 GB of saved activations) exceeds the 126 MB L2; no flush"},
         "e2e": {"value": e2e, "unit": "utt/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": 8},

@@ -15,13 +15,14 @@ import torch
 from . import functional as Fn
 
 
-def build_targets(ys, bos, eos, pad):
+def build_targets(ys, bos, eos, pad, L_min=0):
     """model.py:301-306: ys_in = [BOS, y], ys_out = [y, EOS], both EOS-padded; plus one guard
-    column (PAD) so that every per-step buffer has L+1 rows. Returns (ys_in [B, L+1], ys_out [B, L])."""
+    column (PAD) so that every per-step buffer has L+1 rows. Returns (ys_in [B, L+1], ys_out [B, L]).
+    L_min: pad to at least this many steps (the global Lmax + 1 of a data-parallel batch, global-exact mode)."""
     ys_host = [y.detach().cpu().numpy().astype(np.int64) if torch.is_tensor(y) else np.asarray(y, np.int64)
                for y in ys]
     B = len(ys_host)
-    L = max(len(y) for y in ys_host) + 1
+    L = max(max(len(y) for y in ys_host) + 1, int(L_min))
     ys_in = np.full((B, L + 1), eos, dtype=np.int64)
     ys_out = np.full((B, L), eos, dtype=np.int64)
     for b, y in enumerate(ys_host):
@@ -80,6 +81,7 @@ class _Views:
         self.h_lens = g("h_lens", (B,), i32, True)
         self.h_ys_in = g("h_ys_in", (B, L + 1), i64, True)
         self.h_ys_out = g("h_ys_out", (B, L), i64, True)
+        self.inv = g("inv", (1,), f32)          # global-exact data parallelism: 1 / (global B * (global Lmax + 1))
 
 
 class _Slot:
@@ -155,7 +157,16 @@ def _host_lens(ilens):
 
 
 class SupervisedTrainer:
-    def __init__(self, model, optimizer, max_grad_norm=5.0, use_graph=True, process_group=None, max_graphs=8):
+    def __init__(self, model, optimizer, max_grad_norm=5.0, use_graph=True, process_group=None, max_graphs=8,
+                 global_exact=False):
+        """global_exact (data parallel only): every shard is padded to the GLOBAL Tmax / Lmax and its
+        loss is -sum(log_probs) / (global B * (global Lmax + 1)); the summed gradients then equal the single-GPU
+        gradient of the concatenated batch up to floating-point reassociation (the reference's loss couples the
+        utterances of a batch through its padded extents). Costs one small host-synchronous
+        all-reduce per step to agree on the extents. Default: standard DDP (each rank's loss is the reference loss
+        of its shard, gradients averaged)."""
+        self.global_exact = bool(global_exact)
+        self.global_shape = None          # (T, L, B) override used instead of the collective (tests)
         self.model = model
         self.opt = optimizer
         self.max_grad_norm = max_grad_norm
@@ -188,14 +199,17 @@ class SupervisedTrainer:
         enc_h = enc.forward_dev(st.x, st.lens)
         enc_lens = enc.out_lens_dev(st.lens)
         _, logp, _, _ = m.decoder.forward_dev(enc_h, enc_lens, st.ys_in, st.ys_out, L, 0)
-        loss = -torch.mean(logp)                                   # solver.py:377 (ALL B x (Lmax+1) positions)
+        if self.global_exact:
+            loss = -torch.sum(logp) * st.inv[0]                    # this shard's share of the global mean
+        else:
+            loss = -torch.mean(logp)                               # solver.py:377 (ALL B x (Lmax+1) positions)
         self.opt.zero_grad()
         with Fn.deferred_wgrad():      # weight-gradient contractions run on a side stream, joined on exit
             loss.backward()
         return loss.detach()
 
     def _update(self):
-        return self.opt.clip_and_step(self.max_grad_norm, grad_scale=1.0 / self.world)
+        return self.opt.clip_and_step(self.max_grad_norm, grad_scale=1.0 if self.global_exact else 1.0 / self.world)
 
     def _body(self, st, L):
         loss = self._fwd_bwd(st, L)
@@ -219,14 +233,44 @@ class SupervisedTrainer:
         for k in range(2):
             _Views(self._arena(), B, T, D, L, prefix=f"slot{k}.")
 
+    def _global_extents(self, T, L, B):
+        """(global Tmax, global Lmax + 1, global B) of this step's data-parallel batch."""
+        if self.global_shape is not None:
+            return self.global_shape
+        if self.world == 1:
+            return T, L, B
+        t = torch.tensor([T, L, B], device=self._dev(), dtype=torch.int64)
+        mx, sm = t.clone(), t.clone()
+        torch.distributed.all_reduce(mx, op=torch.distributed.ReduceOp.MAX, group=self.pg)
+        torch.distributed.all_reduce(sm, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+        return int(mx[0]), int(mx[1]), int(sm[2])
+
     def _geometry(self, xs, ilens, ys):
+        """-> (key, views, host_lens, T_local, ys_in, ys_out); key = (B, T, D, L) is the PADDED geometry the step runs
+        at (the shard's own extents, or the global ones in global-exact mode)."""
         m = self.model
         host_lens = _host_lens(ilens)
-        T = max(host_lens)
-        ys_in, ys_out = build_targets(ys, m.decoder.bos, m.decoder.eos, m.decoder.pad)
+        Tl = max(host_lens)
+        T, L_min, inv = Tl, 0, None
+        if self.global_exact:
+            L_loc = max(len(y) for y in ys) + 1
+            T, L_min, Bg = self._global_extents(Tl, L_loc, len(host_lens))
+            inv = 1.0 / float(Bg * L_min)
+        ys_in, ys_out = build_targets(ys, m.decoder.bos, m.decoder.eos, m.decoder.pad, L_min)
         B, L = ys_out.shape
         key = (B, T, xs.shape[2], L)
-        return key, _Views(self._arena(), *key), host_lens, T, ys_in, ys_out
+        st = _Views(self._arena(), *key)
+        if inv is not None:
+            st.inv.fill_(inv)
+        return key, st, host_lens, Tl, ys_in, ys_out
+
+    @staticmethod
+    def _copy_x(dst, xs, Tl):
+        """Features into the [B, T, D] staging view; frames past the shard's own longest utterance are zero (global-exact
+        padding)."""
+        dst[:, :Tl].copy_(xs[:, :Tl], non_blocking=True)
+        if Tl < dst.shape[1]:
+            dst[:, Tl:].zero_()
 
     def staged(self, key):
         """The static device buffers (x, lens, ys_in, ys_out views) a step on geometry `key` reads."""
@@ -235,7 +279,7 @@ class SupervisedTrainer:
     def stage(self, xs, ilens, ys):
         """Host -> device copies of one batch into the static buffers (views of its geometry)."""
         key, st, host_lens, T, ys_in, ys_out = self._geometry(xs, ilens, ys)
-        st.x.copy_(xs[:, :T], non_blocking=True)
+        self._copy_x(st.x, xs, T)
         if self.input_noise_std > 0:
             st.x.add_(torch.randn_like(st.x), alpha=float(self.input_noise_std))
         self._staging_wait()
@@ -268,7 +312,7 @@ class SupervisedTrainer:
         self.model.train()
         if not self.use_graph:
             return self._body(st, L)
-        stamp = (self.arena.gen, _hyper_stamp(self.opt), self.max_grad_norm)
+        stamp = (self.arena.gen, _hyper_stamp(self.opt), self.max_grad_norm, self.global_exact)
         ent = self.cache.lookup(key, stamp)
         if ent is None:
             if self.cache.sighting(key) == 0:      # first sight of a geometry: eager (also warms lazy init)
@@ -327,7 +371,7 @@ class SupervisedTrainer:
         if sl.consumed is not None:
             cs.wait_event(sl.consumed)                 # the step that used this slot has copied it out
         with torch.cuda.stream(cs):
-            v.x.copy_(xs[:, :T], non_blocking=True)
+            self._copy_x(v.x, xs, T)
             v.lens.copy_(v.h_lens, non_blocking=True)
             v.ys_in.copy_(v.h_ys_in, non_blocking=True)
             v.ys_out.copy_(v.h_ys_out, non_blocking=True)

@@ -188,3 +188,38 @@ def test_learning_rate_change_reaches_a_captured_step():
     assert tr.cache.captures == 2                    # re-captured with the new value
     wd_only = (p.detach() - before).abs().max()
     assert float(wd_only) == 0.0, float(wd_only)     # lr = 0: nothing moves
+
+
+def test_global_exact_shards_sum_to_the_single_gpu_gradient():
+    """SURVEY 8(e) "global-exact" data parallelism, emulated on one GPU: the shards of a batch (dealt as
+    data.shard_items deals them), each padded to the global Tmax / Lmax and scaled by 1 / (global B (Lmax + 1)), give
+    gradients whose SUM is the gradient of the whole batch, and losses whose sum is its loss. (tools/dp_check.py runs
+    the same comparison over NCCL ranks.)"""
+    G = load_golden("sup_small_odd")
+    g = G["raw"]
+    D = pkg("data")
+    m, opt, tr = _trainer(G, use_graph=False)
+    xs, ilens, ys = _batch(G)
+    key = tr.stage(xs, ilens, ys)
+    loss_full = float(tr._fwd_bwd(tr.staged(key), key[3]))
+    g_full = opt.flat_grad.clone()
+    assert abs(loss_full - float(g["loss"])) < 1e-3 * abs(float(g["loss"]))
+    items = [(g["x"][b, :ilens[b]], G["ys"][b].tolist()) for b in range(len(ilens))]
+    world = 2
+    tr.global_exact = True
+    tr.global_shape = (key[1], key[3], key[0])                     # global Tmax, Lmax + 1, B
+    g_sum, loss_sum = torch.zeros_like(g_full), 0.0
+    for r in range(world):
+        sx, sl, sy = D.collate(D.shard_items(items, r, world, lambda it: it[0].shape[0]))
+        assert len(sl) == 2
+        k = tr.stage(sx, sl, sy)
+        assert k[1:] == key[1:] and k[0] == 2                       # padded to the global extents
+        loss_sum += float(tr._fwd_bwd(tr.staged(k), k[3]))
+        g_sum += opt.flat_grad
+    assert abs(loss_sum - loss_full) < 1e-4 * abs(loss_full), (loss_sum, loss_full)
+    assert cosine(g_sum, g_full) >= 0.9999, cosine(g_sum, g_full)
+    assert abs(float(g_sum.norm()) - float(g_full.norm())) < 1e-2 * float(g_full.norm())
+    # standard DDP semantics (the default) differ: each shard is padded to its OWN extents and averaged
+    tr.global_exact, tr.global_shape = False, None
+    k = tr.stage(*D.collate(D.shard_items(items, 1, world, lambda it: it[0].shape[0])))
+    assert k[1] <= key[1] and k[3] <= key[3]
