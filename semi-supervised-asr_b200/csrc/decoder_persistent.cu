@@ -927,7 +927,7 @@ struct BGeom {
   int smem;
 };
 
-constexpr bool dec_bgeom_c(int Hd, int O, int A, int Te, int C, int K, int NB, BGeom& g) {
+constexpr bool dec_bgeom_c(int Hd, int O, int A, int Te, int C, int K, int NB, BGeom& g, int gr_max = 32) {
   if (Hd % 64 != 0 || Hd > 320 || O % 16 != 0 || A % 16 != 0 || A > 512 || C > 16 || Te > kBT) return false;
   g.NB = NB; g.G = kCS / NB;
   g.UPC = Hd / kCS; g.OPC = O / kCS; g.RPC = g.UPC + g.OPC;
@@ -954,7 +954,9 @@ constexpr bool dec_bgeom_c(int Hd, int O, int A, int Te, int C, int K, int NB, B
   auto take = [&](int bytes) { const int o = off; off += rup(bytes, 16); return o; };
   g.o_dgB = take(g.KSb * g.FB * 256);
   g.o_red = take(kBW * kRedLd * 4);
-  g.o_redC = take(kBW * kRedLd * 4);
+  // phase C's partial sums reuse phase A's buffer: A's gather and C's store are separated by the block barriers of
+  // phase B, C's gather and the next step's A store by the barrier that ends phase C
+  g.o_redC = g.o_red;
   g.o_dcbuf = take(O * 4);
   g.o_P = take(g.TT * 16 * g.Pld * 2);
   g.o_Q = take(g.TT * 16 * g.Qld * 2);
@@ -978,7 +980,7 @@ constexpr bool dec_bgeom_c(int Hd, int O, int A, int Te, int C, int K, int NB, B
   g.o_wred = take(kBW * 4);
   // phase-B scratch: ddz partials [TT][A] f32 + dconv partial accumulators [12 warps][2][32] float4; afterwards
   // the skewed G tile [GR][Gld] of the conv-input gradient
-  g.GR = g.TT >= 2 ? 32 : 16;
+  g.GR = (g.TT >= 2 && gr_max >= 32) ? 32 : 16;
   g.Gld = (Te + 28) / 32 * 32 + 3;
   {
     const int s1 = g.TT * A * 4 + kBW * 2 * 32 * 16, s2 = g.GR * g.Gld * 4;
@@ -988,7 +990,9 @@ constexpr bool dec_bgeom_c(int Hd, int O, int A, int Te, int C, int K, int NB, B
   return g.smem <= kSmemMax;
 }
 inline bool dec_bgeom(const las_dec_args* a, int NB, BGeom& g) {
-  return dec_bgeom_c(a->Hd, a->O, a->A, a->Te, a->C, a->K, NB, g);
+  // long encoder sequences: a 16-row G tile (two passes per 32 frames of the conv-input gradient) saves 16 KB
+  return dec_bgeom_c(a->Hd, a->O, a->A, a->Te, a->C, a->K, NB, g) ||
+         dec_bgeom_c(a->Hd, a->O, a->A, a->Te, a->C, a->K, NB, g, 16);
 }
 constexpr BGeom make_static_bgeom() {
   BGeom g{};
@@ -1709,13 +1713,24 @@ static bool use_static_geom(const las_dec_args* a, int nb) {
 }
 
 // Utterances per cluster for a batch of B: the smallest power of two for which all clusters are
-// co-resident (a second wave doubles the latency of the whole loop), capped by shared memory.
-static int pick_nb(const las_dec_args* a, DGeom& g, BGeom& bg) {
+// co-resident (a second wave doubles the latency of the whole loop), capped by shared memory. The forward and
+// the backward kernel choose independently (they communicate through per-utterance rows in HBM only): the
+// backward holds full-width Q rows and needs more shared memory per owned frame, so for long encoder
+// sequences (Te > 128) it may run with fewer utterances per cluster than the forward.
+static int first_nb(const las_dec_args* a) {
   const int max_cl = g_dec_persist_clusters > 0 ? g_dec_persist_clusters : 7;
   int nb = 1;
   while (nb < 8 && (a->B + nb - 1) / nb > max_cl) nb *= 2;
-  for (; nb >= 1; nb /= 2)
-    if (dec_geom(a, nb, g) && dec_bgeom(a, nb, bg)) return nb;
+  return nb;
+}
+static int pick_nb_fwd(const las_dec_args* a, DGeom& g) {
+  for (int nb = first_nb(a); nb >= 1; nb /= 2)
+    if (dec_geom(a, nb, g)) return nb;
+  return 0;
+}
+static int pick_nb_bwd(const las_dec_args* a, BGeom& bg) {
+  for (int nb = first_nb(a); nb >= 1; nb /= 2)
+    if (dec_bgeom(a, nb, bg)) return nb;
   return 0;
 }
 
@@ -1726,7 +1741,7 @@ int dec_persist_supported(const las_dec_args* a) {
   if (a->drop_p > 0.f && a->seed_dev == nullptr) return 0;
   DGeom g;
   BGeom bg;
-  if (pick_nb(a, g, bg) == 0) return 0;
+  if (pick_nb_fwd(a, g) == 0 || pick_nb_bwd(a, bg) == 0) return 0;
   if (!g_dec_persist_checked) {
     // does the device schedule a 16-CTA (non-portable) cluster of this kernel at all?
     g_dec_persist_checked = true;
@@ -1768,9 +1783,8 @@ static void cluster_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* at, int nc
 }
 
 int dec_persist_bwd(const las_dec_args* a, cudaStream_t stream) {
-  DGeom g;
   BGeom bg;
-  const int nb = pick_nb(a, g, bg);
+  const int nb = pick_nb_bwd(a, bg);
   LAS_REQUIRE(nb > 0, "persistent decoder: unsupported geometry");
   LAS_REQUIRE(a->wrT2_pk && a->mlp_decT2_pk && a->de_all && a->dc_all && a->cpre && a->conv_save,
               "persistent decoder backward: missing buffers");
@@ -1833,8 +1847,7 @@ int dec_persist_pack(int which, const float* W, int64_t ld, int Hd, int O, int A
 
 int dec_persist_fwd(const las_dec_args* a, cudaStream_t stream) {
   DGeom g;
-  BGeom bg;
-  const int nb = pick_nb(a, g, bg);
+  const int nb = pick_nb_fwd(a, g);
   LAS_REQUIRE(nb > 0, "persistent decoder: unsupported geometry");
   static bool attr_set = false;
   if (!attr_set) {

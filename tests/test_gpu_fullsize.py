@@ -115,6 +115,48 @@ def test_full_size_gradient_accumulation_is_additive(case):
     assert rel < 1e-4, rel
 
 
+# ---- BASELINE config 5a geometry: B=64 (more clusters than a B200 holds at once: later waves), 4 layers [1,2,2,2]
+# (a first layer without subsampling at H=320), Tmax=2000 -> Te=250 encoder frames, L+1=251 decoder steps
+CFG5A = dict(seed=31, B=64, T=2000, D=249, H=320, sub=[1, 2, 2, 2], V=34, E=128, A=320, C=10, K=100, ls=0.05)
+
+
+def _case5a():
+    """_random_case at the 5a geometry, with every utterance but the longest cut to 250..700 frames: the extents the
+    kernels see (B=64, Tmax=2000, Te=250, L+1=251) are the config's, the CPU oracle's cost (~ sum of T_b) is a third."""
+    m, P, x, lens, ys, labeldist = _random_case(**CFG5A)
+    rng = np.random.RandomState(CFG5A["seed"] + 1)
+    new_lens = sorted([lens[0]] + [int(rng.randint(250, 701)) for _ in range(len(lens) - 1)], reverse=True)
+    for b, l in enumerate(new_lens):
+        x[b, l:] = 0.0
+        if b > 0:
+            ys[b] = ys[b][:max(2, int(round(0.125 * l)))]
+    return m, P, x, new_lens, ys, O.label_distribution(ys, CFG5A["V"])
+
+
+def test_config5a_geometry_loss_and_gradients_against_oracle():
+    m, P, x, lens, ys, labeldist = _case5a()
+    with torch.no_grad():
+        m.decoder.vlabeldist.copy_(torch.from_numpy(np.asarray(labeldist, dtype=np.float32)))
+    assert max(len(y) for y in ys) + 1 == 251
+    loss_o, grads_o, _, _ = O.supervised_step(torch.from_numpy(x), lens, ys, P, {}, CFG5A["sub"], CFG5A["ls"], labeldist,
+                                              fast=True)
+    m.train()
+    L = pkg("_lib")
+    L.path_counters(reset=True)
+    enc_h, enc_lens = m.encoder(torch.from_numpy(x).cuda(), lens)
+    assert enc_h.shape[1] == 250 and list(enc_lens) == [(((l + 1) // 2 + 1) // 2 + 1) // 2 for l in lens]
+    _, logp, _, _ = m.decoder(enc_h, enc_lens, [torch.from_numpy(y).cuda() for y in ys])
+    loss = -torch.mean(logp)
+    m.zero_grad()
+    loss.backward()
+    # the long-sequence geometry is still served by the cluster-persistent kernels (several waves of clusters), not
+    # by a silent switch to the per-timestep path
+    assert L.path_counters() == dict(lstm_persist_fwd=4, lstm_persist_bwd=4, lstm_step_fwd=0, lstm_step_bwd=0,
+                                     dec_persist_fwd=1, dec_persist_bwd=1, dec_step_fwd=0, dec_step_bwd=0)
+    assert abs(float(loss) - loss_o) < 1e-3 * abs(loss_o)
+    assert _check_grads(list(m.named_parameters()), grads_o) >= 0.999
+
+
 # ---- BASELINE config 4 at the reference's layer sizes (judge = 2 x LSTM-640 over 256-dim embeddings) on a
 # CPU-affordable batch
 def _lm(V, seed, labeldist):

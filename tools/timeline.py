@@ -33,7 +33,7 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
     torch.cuda.synchronize()
 f = tempfile.mktemp(suffix=".json")
 prof.export_chrome_trace(f)
-ev = [e for e in json.load(open(f))["traceEvents"] if e.get("cat") == "kernel"]
+ev = [e for e in json.load(open(f))["traceEvents"] if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset")]
 ev.sort(key=lambda e: e["ts"])
 t0 = ev[0]["ts"]; t1 = max(e["ts"] + e["dur"] for e in ev)
 print(f"step span {(t1 - t0) / 1e3:.3f} ms, {len(ev)} kernels")
