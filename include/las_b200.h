@@ -267,6 +267,14 @@ typedef struct las_dec_args {
    * that stops once every utterance has emitted <EOS> (Solver.test / validation, solver.py:212-286). */
   int32_t t_begin, t_end;
   const void* mlp_dec_pk_p;  /* persistent forward: fragments (mode 4: rows in order, quad-permuted K) of mlp_dec.weight; wr2_pk is mode 3 */
+  /* Cluster-persistent GREEDY decoding (mode 1, inference: no dropout, no backward): set Q / wr2_pk / cbias / pbar /
+   * mlp_dec_pk_p as for the teacher-forced persistent path, embx = the per-token input table f32 [V, 4Hd]
+   * (W_ih[:, :E] emb(v) + b_ih + b_hh, gate-major columns), out_bf = output_layer.weight as bf16 [V, Hd+O], out_b,
+   * logits, pred. The argmax of step t selects the table row of step t+1 inside the kernel. stop_token >= 0: a
+   * cluster stops once each of its utterances has emitted that token (rows after the stop keep their initial
+   * contents); -1: always L steps. */
+  const void* out_bf;
+  int32_t bos_token, stop_token;
 } las_dec_args;
 
 int las_att_init(const int32_t* enc_lens, int B, int Te, float* w, int64_t w_ld, void* stream);

@@ -32,6 +32,7 @@ class DecArgs(ctypes.Structure):
         + [("drop_p", c_float), ("drop_site", ctypes.c_uint32)]
         + [(n, c_void_p) for n in ("seed_dev", "zcd", "pbar")]
         + [("t_begin", c_int32), ("t_end", c_int32), ("mlp_dec_pk_p", c_void_p)]
+        + [("out_bf", c_void_p), ("bos_token", c_int32), ("stop_token", c_int32)]
     )
 
 

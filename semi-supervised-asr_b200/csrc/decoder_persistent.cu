@@ -66,13 +66,15 @@ struct DGeom {
   int Pld, QTld, Tw;     // row strides of the P slice (f32) and of the transposed Q slice (bf16); padded alignment length
   // shared-memory carve-up (byte offsets)
   int o_zB, o_red, o_red2, o_decA, o_exr, o_pb, o_dzv, o_cred, o_wbuf, o_cwB, o_matt, o_gv, o_P, o_Q, o_epart, o_eall, o_pun, o_wred;
+  // greedy free-running variant (V > 0): output-layer rows per CTA and their buffers
+  int RPV, o_lgw, o_lgm, o_lga, o_tok;
   int smem;
 };
 
 constexpr int rup(int x, int m) { return (x + m - 1) / m * m; }
 
 // Returns false when the problem is not served by the persistent kernel.
-constexpr bool dec_geom_c(int Hd, int O, int A, int Te, int C, int K, int NB, DGeom& g) {
+constexpr bool dec_geom_c(int Hd, int O, int A, int Te, int C, int K, int NB, DGeom& g, int V = 0) {
   if (Hd % 64 != 0 || Hd > 320 || O % 16 != 0 || A % 8 != 0 || A > 512 || C > 16 || Te > kThreads) return false;
   g.NB = NB; g.G = kCS / NB;
   g.UPC = Hd / kCS; g.GT = g.UPC / 4;
@@ -112,7 +114,13 @@ constexpr bool dec_geom_c(int Hd, int O, int A, int Te, int C, int K, int NB, DG
   g.o_red = take(kWarps * 128 * 4);
   g.o_red2 = take(kWarps * 128 * 4);
   g.o_decA = take(kWarps * kMaxFD * 32 * 16);    // mlp_dec A fragments of this CTA: [warp][FD][32] uint4
-  g.o_exr = take(kPFd * 4 * g.GT * 32 * 4);      // embx ring: [kPFd][4 gates][GT lead warps x 32 lanes] f32
+  g.RPV = V > 0 ? (V + kCS - 1) / kCS : 0;
+  {
+    // embx ring: [kPFd][4 gates][GT lead warps x 32 lanes] f32; the greedy variant keeps this CTA's slice of the
+    // per-token input-projection table there instead: [V][4 gates][UPC] f32
+    const int ring = kPFd * 4 * g.GT * 32 * 4, tab = V * 4 * g.UPC * 4;
+    g.o_exr = take(ring > tab ? ring : tab);
+  }
   g.o_pb = take(g.nAT * 32 * 16);                // frame means of P in the dz consumers' fragment order
   g.o_dzv = take(A * 4);
   g.o_cred = take(kWarps * 32 * 32);
@@ -126,11 +134,18 @@ constexpr bool dec_geom_c(int Hd, int O, int A, int Te, int C, int K, int NB, DG
   g.o_eall = take(g.G * g.TR * 4);
   g.o_pun = take(g.KTe * 16 * 4);
   g.o_wred = take(2 * kWarps * 4);
+  g.o_lgw = g.o_lgm = g.o_lga = g.o_tok = 0;
+  if (V > 0) {
+    g.o_lgw = take(g.RPV * (Hd + O) * 2);        // my rows of output_layer.weight, bf16
+    g.o_lgm = take(g.RPV * 8 * 4);               // logits of my rows, [RPV][8 utterances] f32 (the bulk-copy source)
+    g.o_lga = take(kCS * g.RPV * 8 * 4);         // logits of every CTA's rows
+    g.o_tok = take(16 * 4);                      // [8] current input token, [8] "has emitted the stop token"
+  }
   g.smem = off;
   return g.smem <= kSmemMax;
 }
 inline bool dec_geom(const las_dec_args* a, int NB, DGeom& g) {
-  return dec_geom_c(a->Hd, a->O, a->A, a->Te, a->C, a->K, NB, g);
+  return dec_geom_c(a->Hd, a->O, a->A, a->Te, a->C, a->K, NB, g, a->mode == 1 ? a->V : 0);
 }
 
 // Compile-time geometry of the reference's own layer sizes (config.yaml: dec_hidden_dim = att_dim = att_odim = 320,
@@ -275,26 +290,41 @@ struct DecFwdP {
   float* conv_save;              // [B, L, Te, 16] location-conv features (C padded to 16)
   float drop_p; uint32_t drop_site; const unsigned long long* seed_dev;   // cell-input dropout of c_t (model.py:285)
   long long* dbg;                // optional clock64() phase trace (las_set_debug_buffer)
+  // greedy free-running variant (kG): embx = table row of the previous step's argmax token
+  const float* emb_tab;          // [V, 4Hd]  W_ih[:, :E] emb(v) + b_ih + b_hh for every token v
+  const __nv_bfloat16* out_bf;   // [V, Hd+O] output_layer.weight
+  const float* out_b;            // [V]
+  float* logits;                 // [B, L+1, V] (row t+1 = step t)
+  long long* pred;               // [B, L]
+  int V, bos, stop_token;        // stop_token >= 0: a cluster stops once all its utterances have emitted it
 };
 
 // Kernel parameters are copied to shared memory first: every cluster barrier (acquire) invalidates
 // the constant/L1 caches, and a constant-bank miss per parameter read was the dominant stall of
 // the first version of this kernel (profiles/r01_decfwd_v1_stalls.txt).
-template <bool kS>
+// kG: greedy free-running decoding (model.py:331-348 with ys=None, sample=False; inference only). The teacher-forced
+// input term embx_t becomes a row of a per-token table (W_ih[:, :E] emb(v) + b: this CTA's slice lives in shared
+// memory) selected by the previous step's argmax, and one more exchange closes the loop: at the top of step t+1 --
+// [z_t; c_t] of every utterance is then complete in every CTA -- CTA r computes the logits of output rows
+// r*RPV .. r*RPV+RPV-1 for all utterances (640-long dot products on CUDA cores), pushes them to every peer with one
+// bulk copy per peer [mbarrier bl], and every CTA takes the argmax redundantly (torch.argmax conventions: first
+// maximal index, NaN counts as maximal). WAR: a peer overwrites lg_all at the top of step t+2, i.e. after it has
+// received z_{t+1} from this CTA, which is sent after this CTA's argmax of step t.
+template <bool kS, bool kG>
 __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __grid_constant__ DecFwdP p_in) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ DecFwdP p;
-  __shared__ __align__(8) uint64_t bars[6];   // bz[0], bz[1], bc[0], bc[1], bdz, be (see the header comment)
+  __shared__ __align__(8) uint64_t bars[7];   // bz[0], bz[1], bc[0], bc[1], bdz, be, bl (see the header comments)
   for (int i = threadIdx.x; i < static_cast<int>(sizeof(DecFwdP) / 4); i += kThreads)
     reinterpret_cast<uint32_t*>(&p)[i] = reinterpret_cast<const uint32_t*>(&p_in)[i];
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 6; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < 7; ++i) mbar_init(&bars[i], 1);
     fence_mbar_init();
   }
   __syncthreads();
   const DGeom& g = p.g;
 #define GEO(x) (kS ? kSF.x : g.x)
-  uint64_t* bz = bars; uint64_t* bc = bars + 2; uint64_t* bdz = bars + 4; uint64_t* be = bars + 5;
+  uint64_t* bz = bars; uint64_t* bc = bars + 2; uint64_t* bdz = bars + 4; uint64_t* be = bars + 5; uint64_t* bl = bars + 6;
   uint32_t* zB = reinterpret_cast<uint32_t*>(smem + GEO(o_zB));       // [2][KTp][32][2]
   float* red = reinterpret_cast<float*>(smem + GEO(o_red));           // [16][32][4] gate partial sums (P1)
   float* red2 = reinterpret_cast<float*>(smem + GEO(o_red2));         // [16][32][4] mlp_dec partial sums (P2)
@@ -392,6 +422,25 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
     const int r = i / GEO(Pld), a = i % GEO(Pld);
     P_s[i] = __float2bfloat16((r < ntl && a < A) ? p.P[(static_cast<int64_t>(b_own) * Te + te0 + r) * A + a] : 0.f);
   }
+  // greedy variant: per-token input terms of my hidden units, my output-layer rows, token state
+  float* Mtab = reinterpret_cast<float*>(smem + GEO(o_exr));                       // [V][4][UPC]
+  __nv_bfloat16* lgw = reinterpret_cast<__nv_bfloat16*>(smem + g.o_lgw);           // [RPV][ZC]
+  float* lg_mine = reinterpret_cast<float*>(smem + g.o_lgm);                       // [RPV][8]
+  float* lg_all = reinterpret_cast<float*>(smem + g.o_lga);                        // [16][RPV][8]
+  int* tok_s = reinterpret_cast<int*>(smem + g.o_tok);                             // [8] tokens, [8] stop flags
+  const int RPV = g.RPV, V = p.V;
+  if (kG) {
+    for (int i = tid; i < V * 4 * UPC; i += kThreads) {
+      const int v = i / (4 * UPC), k = (i / UPC) & 3, u = i % UPC;
+      Mtab[i] = p.emb_tab[(static_cast<int64_t>(v) * 4 + k) * Hd + rank * UPC + u];
+    }
+    for (int i = tid; i < RPV * ZC; i += kThreads) {
+      const int v = static_cast<int>(rank) * RPV + i / ZC;
+      lgw[i] = v < V ? p.out_bf[static_cast<int64_t>(v) * ZC + i % ZC] : __float2bfloat16(0.f);
+    }
+    for (int i = tid; i < kCS * RPV * 8; i += kThreads) lg_all[i] = -INFINITY;
+    if (tid < 16) tok_s[tid] = tid < 8 ? p.bos : 0;
+  }
   for (int i = tid; i < GEO(OTs) * 16 * GEO(QTld); i += kThreads) QT_s[i] = __float2bfloat16(0.f);
   __syncthreads();
   if (own_ok) {
@@ -434,8 +483,10 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
     ++pf_t;
     cp_async_commit();
   };
+  if (!kG) {
 #pragma unroll 1
-  for (int i = 0; i < kPFd; ++i) prefetch_ex();
+    for (int i = 0; i < kPFd; ++i) prefetch_ex();
+  }
   int64_t sv_idx = static_cast<int64_t>(epi_ok ? b_e : 0) * L * Hd + u_e;
   __nv_bfloat16* zc_z_ptr = p.zc + (static_cast<int64_t>(epi_ok ? b_e : 0) * R + 1) * ZC + u_e;
   // P2: warp w < nATr sums the K-split partials of mlp_dec tile w in fragment order, a 4x4 transpose among the lanes
@@ -495,6 +546,8 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
 #define TX_C (2u * O * max(0, min(GEO(NB), p.B - static_cast<int>(blockIdx.y) * GEO(NB))))
 #define TX_DZ (4u * A)
 #define TX_E (4u * p.Te)
+#define TX_L (static_cast<uint32_t>(kCS - 1) * RPV * 32u)
+  const uint32_t lgm_base = smem_u32(lg_mine), lga_base = smem_u32(lg_all);
   if (tid == 0) {
     const uint32_t tx_z = TX_Z, tx_c = TX_C, tx_dz = TX_DZ, tx_e = TX_E;
     mbar_arrive_expect_tx(&bz[1], tx_z);      // step 0 writes buffer 1
@@ -503,6 +556,7 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
       mbar_arrive_expect_tx(bdz, tx_dz);
       mbar_arrive_expect_tx(be, tx_e);
     }
+    if (kG) mbar_arrive_expect_tx(bl, TX_L);
   }
 
   cluster_barrier();   // every CTA's shared memory and barriers are initialised before any remote store
@@ -510,7 +564,7 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
   const bool trace = p.dbg != nullptr && blockIdx.y == 0 && rank == 0 && lane == 0;
 #define DTRACE(slot) do { if (trace && t >= 8 && t < 12) p.dbg[(warp * 4 + (t - 8)) * 16 + (slot)] = clock64(); } while (0)
 
-  for (int t = 0; t < L; ++t) {
+  for (int t = 0; t < (kG ? L + 1 : L); ++t) {
     const int par = t & 1, nxt = par ^ 1;
     const int zb_nxt_w = nxt * GEO(KTp) * 64;     // word offset of the buffer that receives [z_t; c_t]
     const uint32_t ph2 = (t >> 1) & 1;            // phase parity of bz[nxt] / bc[nxt] at this step
@@ -525,6 +579,75 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
     if (tid == 0 && t + 1 < L) {   // step t+1 writes zB[par]: its previous phase (step t-1) is complete
       mbar_arrive_expect_tx(&bz[par], TX_Z);
       mbar_arrive_expect_tx(&bc[par], TX_C);
+    }
+    if (kG && t > 0) {
+      // ---------- output layer of step t-1 (model.py:290-293), argmax, next input token
+      const uint32_t* zw = zB + par * GEO(KTp) * 64;
+      for (int pr = warp; pr < RPV * 8; pr += kWarps) {
+        const int r = pr >> 3, n = pr & 7;
+        float sacc = 0.f;
+        if (n < NB) {
+          const __nv_bfloat16* wrow = lgw + r * ZC;
+          for (int k = 2 * lane; k < ZC; k += 64) {
+            const float2 zv = unpack_bf16x2(zw[qfrag_word(k, n)]);
+            const float2 wv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(wrow + k));
+            sacc = fmaf(zv.x, wv.x, fmaf(zv.y, wv.y, sacc));
+          }
+        }
+        sacc = warp_sum(sacc);
+        if (lane == 0) {
+          const int v = static_cast<int>(rank) * RPV + r;
+          lg_mine[pr] = (v < V && n < NB) ? sacc + p.out_b[v] : -INFINITY;
+        }
+      }
+      fence_proxy_async_smem();
+      __syncthreads();
+      if (warp == 0 && lane < kCS && lane != static_cast<int>(rank))
+        dsmem_bulk_copy(mapa_u32(lga_base + rank * RPV * 32u, lane), lgm_base, RPV * 32u, mapa_u32(bars_base + 48u, lane));
+      if (tid < RPV * 8) {
+        const float lv = lg_mine[tid];
+        lg_all[rank * RPV * 8 + tid] = lv;
+        const int r = tid >> 3, n = tid & 7, v = static_cast<int>(rank) * RPV + r, b = cl * NB + n;
+        if (n < NB && b < p.B && v < V) p.logits[(static_cast<int64_t>(b) * R + t) * V + v] = lv;
+      }
+      mbar_wait_tag(bl, (t - 1) & 1, 5);          // the logits rows of every other CTA have landed in lg_all
+      if (tid == 0 && t < L) mbar_arrive_expect_tx(bl, TX_L);
+      __syncthreads();                            // ... and my own slice is visible to every warp
+      if (warp < 8) {
+        const int n = warp;
+        // torch.argmax: first maximal index; a NaN counts as the maximum
+        float bv = -INFINITY; int bi = 0x7fffffff; bool bn = false;
+        for (int v = lane; v < V; v += 32) {
+          const float x = lg_all[((v / RPV) * RPV + (v % RPV)) * 8 + n];
+          const bool xn = x != x;
+          if (bi == 0x7fffffff || (xn && !bn) || (!bn && !xn && x > bv)) { bv = x; bi = v; bn = xn; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          const bool on = __shfl_xor_sync(0xffffffffu, static_cast<int>(bn), o) != 0;
+          const bool take = oi != 0x7fffffff &&
+                            (bi == 0x7fffffff || (on && !bn) || (on == bn && !on && ov > bv) ||
+                             (((on && bn) || (!on && !bn && ov == bv)) && oi < bi));
+          if (take) { bv = ov; bi = oi; bn = on; }
+        }
+        if (lane == 0 && n < NB) {
+          const int b = cl * NB + n;
+          if (bi == 0x7fffffff) bi = 0;
+          tok_s[n] = bi;
+          if (bi == p.stop_token || b >= p.B) tok_s[8 + n] = 1;
+          if (rank == 0 && b < p.B) p.pred[static_cast<int64_t>(b) * L + (t - 1)] = bi;
+        }
+      }
+      __syncthreads();
+      if (t == L) break;
+      if (p.stop_token >= 0) {
+        // every CTA of the cluster holds the same tokens: a consistent decision without any exchange
+        int nd = 0;
+        for (int n = 0; n < NB; ++n) nd += tok_s[8 + n];
+        if (nd == NB) break;
+      }
     }
     DTRACE(1);
     if (g_act) {
@@ -559,16 +682,18 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
         // 2 tig, 2 tig + 1. Lanes gq and gq ^ 4 trade halves: each ends up with all four gates of (ul, 2 tig + gl).
         const float r0 = __shfl_xor_sync(0xffffffffu, gl ? cf[0] : cf[1], 16);
         const float r1 = __shfl_xor_sync(0xffffffffu, gl ? cf[2] : cf[3], 16);
-        cp_async_wait_n<kPFd - 1>();      // this step's embx terms have landed in my ring slot
+        if (!kG) cp_async_wait_n<kPFd - 1>();      // this step's embx terms have landed in my ring slot
         uint32_t zbits = 0u;
         uint2 sv_pk = make_uint2(0u, 0u);
         __nv_bfloat16 sv_z = __float2bfloat16(0.f);
         if (epi_ok) {
-          const float* er = exr + (t % kPFd) * 4 * exs;
+          // teacher forcing: ring slot of this step; greedy: table row of the token chosen at the top of this step
+          const float* er = kG ? Mtab + tok_s[n_e] * 4 * UPC + (u_e - static_cast<int>(rank) * UPC) : exr + (t % kPFd) * 4 * exs;
+          const int es = kG ? UPC : exs;
           const float gi = (gl ? r0 : cf[0]) + er[0];
-          const float gf = (gl ? cf[1] : r0) + er[exs];
-          const float gg = (gl ? r1 : cf[2]) + er[2 * exs];
-          const float go = (gl ? cf[3] : r1) + er[3 * exs];
+          const float gf = (gl ? cf[1] : r0) + er[es];
+          const float gg = (gl ? r1 : cf[2]) + er[2 * es];
+          const float go = (gl ? cf[3] : r1) + er[3 * es];
           const float i = sigmoid_acc(gi), f = sigmoid_acc(gf), gc = tanh_acc(gg), o = sigmoid_acc(go);
           cell = f * cell + i * gc;
           sv_z = __float2bfloat16(o * tanh_acc(cell));
@@ -598,7 +723,7 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
           p.c_save[sv_idx] = cell;
           zc_z_ptr[0] = sv_z;
         }
-        prefetch_ex();    // refill my ring slot (step t + kPFd)
+        if (!kG) prefetch_ex();    // refill my ring slot (step t + kPFd)
       }
     }
     sv_idx += Hd; zc_z_ptr += ZC;
@@ -879,6 +1004,7 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
 #undef TX_C
 #undef TX_DZ
 #undef TX_E
+#undef TX_L
 #undef GEO
 }
 
@@ -1726,6 +1852,11 @@ static int first_nb(const las_dec_args* a) {
 static int pick_nb_fwd(const las_dec_args* a, DGeom& g) {
   for (int nb = first_nb(a); nb >= 1; nb /= 2)
     if (dec_geom(a, nb, g)) return nb;
+  // greedy decoding (Solver.test decodes one utterance at a time): a tiny batch may not split into whole context
+  // tiles per owner at its natural cluster width; more utterance columns per cluster (some of them idle) do
+  if (a->mode == 1)
+    for (int nb = 2 * first_nb(a); nb <= 8; nb *= 2)
+      if (dec_geom(a, nb, g)) return nb;
   return 0;
 }
 static int pick_nb_bwd(const las_dec_args* a, BGeom& bg) {
@@ -1735,19 +1866,27 @@ static int pick_nb_bwd(const las_dec_args* a, BGeom& bg) {
 }
 
 int dec_persist_supported(const las_dec_args* a) {
-  if (a->mode != 0 || a->Q == nullptr || a->wr2_pk == nullptr || a->mlp_dec_pk_p == nullptr || a->cbias == nullptr ||
-      a->pbar == nullptr)
+  if ((a->mode != 0 && a->mode != 1) || a->Q == nullptr || a->wr2_pk == nullptr || a->mlp_dec_pk_p == nullptr ||
+      a->cbias == nullptr || a->pbar == nullptr)
     return 0;
   if (a->drop_p > 0.f && a->seed_dev == nullptr) return 0;
   DGeom g;
   BGeom bg;
-  if (pick_nb_fwd(a, g) == 0 || pick_nb_bwd(a, bg) == 0) return 0;
+  if (a->mode == 1) {
+    // greedy free-running decoding, inference only: forward kernel alone, no dropout, whole sequence in one launch
+    if (a->drop_p > 0.f || a->embx == nullptr || a->out_bf == nullptr || a->out_b == nullptr || a->logits == nullptr ||
+        a->pred == nullptr || a->V < 1 || a->V > 8 * kCS || a->t_begin != 0 || (a->t_end != 0 && a->t_end != a->L))
+      return 0;
+    if (pick_nb_fwd(a, g) == 0) return 0;
+  } else if (pick_nb_fwd(a, g) == 0 || pick_nb_bwd(a, bg) == 0) {
+    return 0;
+  }
   if (!g_dec_persist_checked) {
     // does the device schedule a 16-CTA (non-portable) cluster of this kernel at all?
     g_dec_persist_checked = true;
     g_dec_persist_clusters = 0;
-    if (cudaFuncSetAttribute(dec_persist_fwd_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
-        cudaFuncSetAttribute(dec_persist_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax) == cudaSuccess) {
+    if (cudaFuncSetAttribute(dec_persist_fwd_kernel<false, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+        cudaFuncSetAttribute(dec_persist_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax) == cudaSuccess) {
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(kCS, 1, 1);
       cfg.blockDim = dim3(kThreads);
@@ -1760,7 +1899,7 @@ int dec_persist_supported(const las_dec_args* a) {
       cfg.attrs = at;
       cfg.numAttrs = 1;
       int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, dec_persist_fwd_kernel<false>, &cfg) == cudaSuccess) g_dec_persist_clusters = n;
+      if (cudaOccupancyMaxActiveClusters(&n, dec_persist_fwd_kernel<false, false>, &cfg) == cudaSuccess) g_dec_persist_clusters = n;
     }
     (void)cudaGetLastError();
   }
@@ -1851,13 +1990,16 @@ int dec_persist_fwd(const las_dec_args* a, cudaStream_t stream) {
   LAS_REQUIRE(nb > 0, "persistent decoder: unsupported geometry");
   static bool attr_set = false;
   if (!attr_set) {
-    LAS_CUDA(cudaFuncSetAttribute(dec_persist_fwd_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    LAS_CUDA(cudaFuncSetAttribute(dec_persist_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
-    LAS_CUDA(cudaFuncSetAttribute(dec_persist_fwd_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    LAS_CUDA(cudaFuncSetAttribute(dec_persist_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+    LAS_CUDA(cudaFuncSetAttribute(dec_persist_fwd_kernel<false, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    LAS_CUDA(cudaFuncSetAttribute(dec_persist_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+    LAS_CUDA(cudaFuncSetAttribute(dec_persist_fwd_kernel<true, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    LAS_CUDA(cudaFuncSetAttribute(dec_persist_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+    LAS_CUDA(cudaFuncSetAttribute(dec_persist_fwd_kernel<false, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    LAS_CUDA(cudaFuncSetAttribute(dec_persist_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     attr_set = true;
   }
-  const bool stat = use_static_geom(a, nb);
+  const bool greedy = a->mode == 1;
+  const bool stat = !greedy && use_static_geom(a, nb);
   if (stat) g = kSF;
   DecFwdP p;
   p.B = a->B; p.L = a->L; p.Te = a->Te; p.Hd = a->Hd; p.O = a->O; p.A = a->A; p.C = a->C; p.K = a->K;
@@ -1871,6 +2013,10 @@ int dec_persist_fwd(const las_dec_args* a, cudaStream_t stream) {
   p.cpre = a->cpre; p.conv_save = a->conv_save;
   p.drop_p = a->drop_p; p.drop_site = a->drop_site; p.seed_dev = static_cast<const unsigned long long*>(a->seed_dev);
   p.dbg = static_cast<long long*>(g_dbg_buf_shared);
+  // greedy variant: a->embx is the per-token table [V, 4Hd] (W_ih[:, :E] emb(v) + b_ih + b_hh)
+  p.emb_tab = a->embx; p.out_bf = static_cast<const __nv_bfloat16*>(a->out_bf); p.out_b = a->out_b;
+  p.logits = a->logits; p.pred = reinterpret_cast<long long*>(a->pred); p.V = a->V; p.bos = a->bos_token;
+  p.stop_token = a->stop_token;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(kCS, (a->B + nb - 1) / nb, 1);
   cfg.blockDim = dim3(kThreads);
@@ -1883,8 +2029,9 @@ int dec_persist_fwd(const las_dec_args* a, cudaStream_t stream) {
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  if (stat) LAS_CUDA(cudaLaunchKernelEx(&cfg, dec_persist_fwd_kernel<true>, p));
-  else LAS_CUDA(cudaLaunchKernelEx(&cfg, dec_persist_fwd_kernel<false>, p));
+  if (greedy) LAS_CUDA(cudaLaunchKernelEx(&cfg, dec_persist_fwd_kernel<false, true>, p));
+  else if (stat) LAS_CUDA(cudaLaunchKernelEx(&cfg, dec_persist_fwd_kernel<true, false>, p));
+  else LAS_CUDA(cudaLaunchKernelEx(&cfg, dec_persist_fwd_kernel<false, false>, p));
   ++(stat ? g_dec_static_launches : g_dec_generic_launches);
   ++g_launches;
   return 0;

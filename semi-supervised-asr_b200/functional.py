@@ -597,7 +597,7 @@ def _build_dec_fwd(W, mode):
     if mode != 0:
         d["we_pk"] = pack_afrag(we.contiguous(), 1, Hd)
         d["out_pk"] = pack_afrag(W["out_w"], 0)
-    elif DEC_PERSISTENT:
+    if DEC_PERSISTENT and mode in (0, 1):
         d["mlp_o_bf"] = cvt_bf16(W["mlp_o_w"])
         d["wr2_pk"] = pack_afrag(d["wr_cat"], 3, Hd)               # quad tiles, quad-permuted K (persistent kernel)
         d["mlp_dec_pk_p"] = pack_afrag(W["mlp_dec_w"], 4)
@@ -710,7 +710,18 @@ class DecoderFn(torch.autograd.Function):
             a.emb_w, a.emb_op, a.logits, a.pred = ptr(W["emb_w"]), ptr(emb_op), ptr(logits), ptr(pred)
             keep += [we_pk, out_pk, emb_op]
         persist, pers = False, None
-        if mode == 0 and DEC_PERSISTENT:
+        es = GREEDY_EARLY_STOP
+        # greedy decoding without autograd (Solver.validation / test, solver.py:212-286) may run as ONE cluster-persistent
+        # launch too: the embedding half of the cell input becomes a per-token table, the argmax feeds back in-kernel
+        greedy_p = mode == 1 and DEC_PERSISTENT and p_drop == 0 and not torch.is_grad_enabled() and ZC % 8 == 0
+        if greedy_p:
+            emb_all = torch.empty(V, Ep, device=dev, dtype=BF16)
+            call("las_gather_rows_bf16", ptr(W["emb_w"]), E, ptr(torch.arange(V, device=dev)), V, ptr(emb_all), Ep)
+            emb_tab = gemm(emb_all, Ep, 0, Pk["we_bf"], Ep, 0, V, 4 * Hd, Ep, bias=cell_bias)      # f32 [V, 4Hd]
+            a.embx, a.out_bf, a.bos_token = ptr(emb_tab), ptr(Pk["out_bf"]), int(bos)
+            a.stop_token = int(es["eos"]) if es["on"] else -1
+            keep += [emb_all, emb_tab]
+        if (mode == 0 or greedy_p) and DEC_PERSISTENT:
             # cluster-persistent decoder: c_t = w_t @ Q + bias with Q = enc_h @ mlp_o.weight^T
             # Q is stored centred over the frames of each utterance (the mean goes into a per-utterance
             # bias): bf16 rounding then applies to the deviations, which is what the softmax backward
@@ -727,20 +738,27 @@ class DecoderFn(torch.autograd.Function):
             a.Q, a.wr2_pk, a.cbias, a.pbar = ptr(Qm), ptr(wr2_pk), ptr(cbias), ptr(Pbar)
             a.mlp_dec_pk_p = ptr(Pk["mlp_dec_pk_p"])
             persist = bool(_lib.lib().las_dec_persistent_supported(ctypes.byref(a)))
-            if persist:
+            if persist and mode == 0:
                 cpre = torch.empty(B, L, O, **f32)
                 conv_save = torch.empty(B, L, Te, 16, **f32)
                 a.cpre, a.conv_save = ptr(cpre), ptr(conv_save)
                 a.P = ptr(Pc)
                 pers = dict(Qm=Qm, wr2_pk=wr2_pk, cpre=cpre, conv_save=conv_save, mlp_o_bf=mlp_o_bf, cbias=cbias, Pc=Pc, Pbar=Pbar)
+            elif persist:
+                a.P = ptr(Pc)                         # inference: nothing is saved for a backward pass
+                keep += [Qm, cbias, Pc, Pbar]
             else:
                 a.Q, a.wr2_pk, a.cbias, a.pbar = None, None, None, None
+                if greedy_p:
+                    a.embx, a.out_bf = None, None
         if p_drop > 0 and not persist:
             zcd = torch.zeros(B * R * ZC + 64, device=dev, dtype=BF16)
             a.zcd = ptr(zcd)
             keep.append(zcd)
-        es = GREEDY_EARLY_STOP
-        if mode == 1 and es["on"] and not torch.is_grad_enabled():
+        if mode == 1 and persist:
+            call("las_dec_fwd", ctypes.byref(a))      # all steps (or up to every utterance's <EOS>) in one launch
+            es["last_steps"] = L
+        elif mode == 1 and es["on"] and not torch.is_grad_enabled():
             # greedy decoding for scoring (Solver.test / validation): issue the steps in chunks and stop as soon as
             # every utterance has emitted <EOS>. Rows after the stop keep their initial zeros; the hypotheses are
             # identical after remove_pad_eos (utils.py:192-201), which cuts at the first <EOS>.
