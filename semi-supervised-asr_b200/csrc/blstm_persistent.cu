@@ -40,20 +40,27 @@ struct Geom {
 struct FGeom {
   int Q, CS, WPC, KT;
 };
+// Hidden sizes above 320 (the LM judge's 640, model.py:466) do not fit the register file of an 8..10-CTA cluster:
+// "wide" geometry = 16-CTA clusters, and the recurrent weights beyond what the registers hold (forward: k-tiles
+// kMaxKT.., backward: m-tiles 2..) stay resident in SHARED memory as ready-made A fragments.
+constexpr int kWideKTS = 20;
+constexpr int kWidePF = 4;    // backward: prefetch ring depth of the wide geometry (shared memory holds weights)   // forward: k-tiles per warp kept in shared memory (wide geometry)
 bool fgeom_for(int H, FGeom& g, int max_cs = 8) {
   if (H % 8 != 0 || H < 8) return false;
   g.Q = H / 4;
+  if (H > 16 * kMaxKT) max_cs = 16;
   const int cs0 = g.Q < max_cs ? g.Q : max_cs;
   g.WPC = (g.Q + cs0 - 1) / cs0;
   g.CS = (g.Q + g.WPC - 1) / g.WPC;
   g.KT = (H + 15) / 16;
-  return g.WPC <= 12 && g.KT <= kMaxKT;
+  return g.WPC <= 12 && g.KT <= kMaxKT + kWideKTS;
 }
 
 bool geom_for(int H, Geom& g) {
-  if (H % 8 != 0 || H < 8 || H > 8 * 8 * kMaxUGC) return false;
+  if (H % 8 != 0 || H < 8 || H > 8 * 16 * kMaxUGC) return false;
   g.UG = H / 8;
-  const int cs0 = g.UG < 8 ? g.UG : 8;
+  const int csm = H > 8 * 8 * kMaxUGC ? 16 : 8;      // wide geometry above H = 320
+  const int cs0 = g.UG < csm ? g.UG : csm;
   g.UGC = (g.UG + cs0 - 1) / cs0;
   g.CS = (g.UG + g.UGC - 1) / g.UGC;
   g.KT = (H + 15) / 16;
@@ -62,6 +69,7 @@ bool geom_for(int H, Geom& g) {
   g.JT = (H + 15) / 16;
   const int W = 2 * g.UGC;
   g.MTW = (g.JT + W - 1) / W;
+  if (csm == 16) return g.MTW <= 4 && g.UGC <= kMaxUGC;   // m-tiles 2, 3 of a warp live in shared memory
   return g.MTW <= 2 && g.KTW <= kMaxKTW && g.UGC <= kMaxUGC;
 }
 
@@ -122,7 +130,7 @@ struct FwdP {
 // quad rank*WPC + w: its m16 tile holds their 16 gate rows, K = all of H, so a warp needs no partial-sum
 // exchange with other warps and the step loop contains no block-wide barrier: warps are paced only by the
 // mbarrier that counts the bytes of h_t arriving from the cluster.
-template <bool kFastAct>
+template <bool kFastAct, int KTS>
 __global__ void __launch_bounds__(384, 1) lstm_persist_fwd_kernel(FwdP p) {
   extern __shared__ __align__(16) uint8_t smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);                    // [2]
@@ -157,11 +165,18 @@ __global__ void __launch_bounds__(384, 1) lstm_persist_fwd_kernel(FwdP p) {
   if (quad_ok) {
     // resident recurrent weights: A fragments of this warp's quad over the whole K range
     uint4 A[kMaxKT];
+    // wide geometry: k-tiles kMaxKT .. kMaxKT + KTS - 1 of this warp in shared memory, [warp][KTS][32 lanes] x 16 B
+    uint4* As = reinterpret_cast<uint4*>(smem + 16 + 2 * p.KT * 256 + kPF * blockDim.x * 16) + warp * KTS * 32 + lane;
     {
       const uint4* src = reinterpret_cast<const uint4*>(p.whh_pk) +
                          (static_cast<int64_t>(dir) * p.Q + quad) * p.KT * 32 + lane;
 #pragma unroll
       for (int kt = 0; kt < kMaxKT; ++kt) A[kt] = kt < p.KT ? __ldg(src + kt * 32) : make_uint4(0u, 0u, 0u, 0u);
+      if (KTS > 0) {
+#pragma unroll 4
+        for (int j = 0; j < KTS; ++j)
+          As[j * 32] = kMaxKT + j < p.KT ? __ldg(src + (kMaxKT + j) * 32) : make_uint4(0u, 0u, 0u, 0u);
+      }
     }
     // element owned by this lane after the in-warp gate exchange: unit u, utterance n
     const int gl = g >> 2, ul = g & 3;
@@ -236,12 +251,24 @@ __global__ void __launch_bounds__(384, 1) lstm_persist_fwd_kernel(FwdP p) {
         LAS_TRACE(1);
         if (threadIdx.x == 0 && s + 2 < T) mbar_arrive_expect_tx(&full[buf], tx_bytes);  // re-arm for step s+2
         const uint2* hb = reinterpret_cast<const uint2*>(hs + buf * p.KT * 64) + tig * 8 + (g ^ ((tig >> 1) << 2));
-        if (p.KT == kMaxKT) {     // H = 320: no per-k-tile bound check in the instruction stream
+        if (p.KT == kMaxKT || KTS > 0) {     // H = 320 (or wide): no per-k-tile bound check in the instruction stream
 #pragma unroll
           for (int kt = 0; kt < kMaxKT; ++kt) {
             const uint2 b = hb[kt * 32];
             const uint32_t Af[4] = {A[kt].x, A[kt].y, A[kt].z, A[kt].w};
             mma_bf16_16816(acc[kt & 3], Af, b.x, b.y);
+          }
+          if (KTS > 0) {          // the shared-memory resident part of the weights (zero fragments past KT)
+            const int nks = p.KT - kMaxKT;
+#pragma unroll 4
+            for (int j = 0; j < KTS; ++j) {
+              if (j < nks) {
+                const uint2 b = hb[(kMaxKT + j) * 32];
+                const uint4 a4 = As[j * 32];
+                const uint32_t Af[4] = {a4.x, a4.y, a4.z, a4.w};
+                mma_bf16_16816(acc[j & 3], Af, b.x, b.y);
+              }
+            }
           }
         } else {
 #pragma unroll
@@ -345,13 +372,17 @@ struct BwdP {
 };
 
 // grid (CS, ceil(B/8), ndir), cluster (CS,1,1), block 64*UGC (= 8 utterances x UPC units).
+// MTS: m-tiles (16 hidden units) per warp whose W_hh^T fragments live in shared memory, after the 2 held in
+// registers (wide geometry: 2; otherwise 0); CSM: largest cluster size served; PF: prefetch ring depth.
+template <int MTS, int CSM, int PF>
 __global__ void __launch_bounds__(320, 1) lstm_persist_bwd_kernel(BwdP p) {
   extern __shared__ __align__(16) uint8_t smem[];
+  constexpr int MT = 2 + MTS;
   const int UPC = 8 * p.UGC, KTC = 2 * p.UGC;
   uint64_t* pfull = reinterpret_cast<uint64_t*>(smem);                   // [2]
   float* part = reinterpret_cast<float*>(smem + 16);                     // [2][CS][UPC*8]
   uint32_t* dgs = reinterpret_cast<uint32_t*>(smem + 16 + 2 * p.CSn * UPC * 8 * 4);   // [KTC][32][2]
-  float* pring = reinterpret_cast<float*>(dgs + KTC * 64);                             // [kPF][threads][8]
+  float* pring = reinterpret_cast<float*>(dgs + KTC * 64);                             // [PF][threads][8]
   cg::cluster_group cluster = cg::this_cluster();
   const uint32_t rank = cluster.block_rank(), CS = cluster.num_blocks();
   const int grp = blockIdx.y, dir = blockIdx.z;
@@ -375,19 +406,22 @@ __global__ void __launch_bounds__(320, 1) lstm_persist_bwd_kernel(BwdP p) {
 
   // resident W_hh^T fragments: rows = this warp's 16-unit tiles, K = this CTA's own gate rows
   uint4 A[2][kMaxKTW];
+  // wide geometry: the fragments of m-tiles 2 .. MT-1 of this warp, [warp][MTS][kMaxKTW][32 lanes] x 16 B
+  uint4* As = reinterpret_cast<uint4*>(pring + static_cast<int64_t>(PF) * blockDim.x * 8) + warp * MTS * kMaxKTW * 32 + lane;
   {
     const int KTtot = p.CSn * KTC;
     const int64_t a_dir = static_cast<int64_t>(p.JT) * KTtot * 128;
 #pragma unroll
-    for (int m = 0; m < 2; ++m)
+    for (int m = 0; m < MT; ++m)
 #pragma unroll
       for (int kc = 0; kc < kMaxKTW; ++kc) {
         const int mt = warp * p.MTW + m;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
         if (m < p.MTW && mt < p.JT && kc < KTC)
-          A[m][kc] = __ldg(reinterpret_cast<const uint4*>(p.wT_pk + dir * a_dir) +
-                           (static_cast<int64_t>(mt) * KTtot + rank * KTC + kc) * 32 + lane);
-        else
-          A[m][kc] = make_uint4(0u, 0u, 0u, 0u);
+          v = __ldg(reinterpret_cast<const uint4*>(p.wT_pk + dir * a_dir) +
+                    (static_cast<int64_t>(mt) * KTtot + rank * KTC + kc) * 32 + lane);
+        if (m < 2) A[m][kc] = v;
+        else As[((m - 2) * kMaxKTW + kc) * 32] = v;
       }
   }
 
@@ -416,7 +450,7 @@ __global__ void __launch_bounds__(320, 1) lstm_persist_bwd_kernel(BwdP p) {
   auto prefetch = [&]() {
     const int t = (dir == 0) ? (T - 1 - pf_s) : pf_s;
     if (pf_s < T && t < len) {
-      float* dst = pslot + (pf_s % kPF) * ring_stride;
+      float* dst = pslot + (pf_s % PF) * ring_stride;
       cp_async<16>(dst, p.rec + sv_run);
       if (dy_run) {
         cp_async<4>(dst + 4, dy_run);
@@ -428,17 +462,17 @@ __global__ void __launch_bounds__(320, 1) lstm_persist_bwd_kernel(BwdP p) {
     if (dy_run) dy_run += dy_step;
     cp_async_commit();
   };
-  for (int i = 0; i < kPF; ++i) prefetch();
+  for (int i = 0; i < PF; ++i) prefetch();
 
   // reduce-scatter destinations of this lane's partial sums (buffer 0; buffer 1 is part_buf_bytes further)
   // Lanes tig and tig^1 trade halves of their C fragments so that each holds 4 consecutive utterances of ONE unit
   // (even tig: row g, odd tig: row g+8) and sends them as one 16-byte st.async.
-  uint32_t sc_dst[2], sc_bar[2];
-  bool sc_ok[2];
+  uint32_t sc_dst[MT], sc_bar[MT];
+  bool sc_ok[MT];
   const uint32_t part_buf_bytes = static_cast<uint32_t>(p.CSn) * UPC * 8 * 4;
   const int hh_own = tig & 1;
 #pragma unroll
-  for (int m = 0; m < 2; ++m) {
+  for (int m = 0; m < MT; ++m) {
     const int mt = warp * p.MTW + m;
     const int j = 16 * mt + g + 8 * hh_own;
     sc_ok[m] = m < p.MTW && mt < p.JT && j < H;
@@ -460,13 +494,13 @@ __global__ void __launch_bounds__(320, 1) lstm_persist_bwd_kernel(BwdP p) {
     LAS_TRACE(0);
     // operands of the gate-derivative math into registers, then the ring slot is refilled right away: the loads
     // and the cp.async issue are hidden behind the MMA and the DSMEM round trip below instead of following them
-    cp_async_wait<kPF - 2>();   // this step's and the next step's operands have landed
+    cp_async_wait<PF - 2>();   // this step's and the next step's operands have landed
     float4 rc = make_float4(0.f, 0.f, 0.f, 0.f);
     float c_prev = 0.f, dy_in = 0.f;
     if (active) {
-      const float* q = pslot + (s % kPF) * ring_stride;
+      const float* q = pslot + (s % PF) * ring_stride;
       rc = *reinterpret_cast<const float4*>(q);
-      const float* qn = pslot + ((s + 1) % kPF) * ring_stride;
+      const float* qn = pslot + ((s + 1) % PF) * ring_stride;
       if (dir == 0) { if (t > 0) c_prev = qn[2]; }
       else          { if (t + 1 < len) c_prev = qn[2]; }
       if (p.dy) {
@@ -479,21 +513,27 @@ __global__ void __launch_bounds__(320, 1) lstm_persist_bwd_kernel(BwdP p) {
     if (s > 0) {
       const int buf = s & 1;
       // partial dh for this warp's unit tiles from this CTA's own gate gradients of the previous step
-      float acc[2][2][4];
+      float acc[MT][2][4];
 #pragma unroll
-      for (int a = 0; a < 2; ++a)
+      for (int a = 0; a < MT; ++a)
 #pragma unroll
         for (int b = 0; b < 2; ++b)
 #pragma unroll
           for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
       const uint2* db = reinterpret_cast<const uint2*>(dgs) + lane;
-      if (KTC == kMaxKTW) {       // H = 320: no per-k-tile bound check in the instruction stream
+      if (KTC == kMaxKTW) {       // H = 320 / 640: no per-k-tile bound check in the instruction stream
 #pragma unroll
         for (int kc = 0; kc < kMaxKTW; ++kc) {
           const uint2 b = db[kc * 32];
 #pragma unroll
           for (int m = 0; m < 2; ++m) {
             const uint32_t Af[4] = {A[m][kc].x, A[m][kc].y, A[m][kc].z, A[m][kc].w};
+            mma_bf16_16816(acc[m][kc & 1], Af, b.x, b.y);
+          }
+#pragma unroll
+          for (int m = 2; m < MT; ++m) {          // fragments resident in shared memory (zero past JT / MTW)
+            const uint4 a4 = As[((m - 2) * kMaxKTW + kc) * 32];
+            const uint32_t Af[4] = {a4.x, a4.y, a4.z, a4.w};
             mma_bf16_16816(acc[m][kc & 1], Af, b.x, b.y);
           }
         }
@@ -507,13 +547,19 @@ __global__ void __launch_bounds__(320, 1) lstm_persist_bwd_kernel(BwdP p) {
               const uint32_t Af[4] = {A[m][kc].x, A[m][kc].y, A[m][kc].z, A[m][kc].w};
               mma_bf16_16816(acc[m][kc & 1], Af, b.x, b.y);
             }
+#pragma unroll
+            for (int m = 2; m < MT; ++m) {
+              const uint4 a4 = As[((m - 2) * kMaxKTW + kc) * 32];
+              const uint32_t Af[4] = {a4.x, a4.y, a4.z, a4.w};
+              mma_bf16_16816(acc[m][kc & 1], Af, b.x, b.y);
+            }
           }
         }
       }
       LAS_TRACE(1);
       // scatter the partial sums to the CTAs that own the units
 #pragma unroll
-      for (int m = 0; m < 2; ++m) {
+      for (int m = 0; m < MT; ++m) {
         float v[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) v[c] = acc[m][0][c] + acc[m][1][c];
@@ -533,10 +579,11 @@ __global__ void __launch_bounds__(320, 1) lstm_persist_bwd_kernel(BwdP p) {
       const float* pp = part + static_cast<int64_t>(buf) * p.CSn * UPC * 8 + threadIdx.x;
       // the CS <= 8 partial sums: all loads first, then a tree (a serial load-add chain was 15 % of this kernel's
       // stall samples, profiles/r02_ncu_full_summary.txt)
-      float pv[8];
+      float pv[CSM];
 #pragma unroll
-      for (uint32_t src = 0; src < 8; ++src) pv[src] = src < CS ? pp[src * UPC * 8] : 0.f;
+      for (uint32_t src = 0; src < CSM; ++src) pv[src] = src < CS ? pp[src * UPC * 8] : 0.f;
       dh = ((pv[0] + pv[1]) + (pv[2] + pv[3])) + ((pv[4] + pv[5]) + (pv[6] + pv[7]));
+      if (CSM > 8) dh += ((pv[CSM - 8] + pv[CSM - 7]) + (pv[CSM - 6] + pv[CSM - 5])) + ((pv[CSM - 4] + pv[CSM - 3]) + (pv[CSM - 2] + pv[CSM - 1]));
     }
     // gate derivatives (same math as cell_bwd_kernel)
     float d4[4] = {0.f, 0.f, 0.f, 0.f};
@@ -621,13 +668,20 @@ bool persist_enabled() {
 
 template <typename Kern, typename P>
 int launch_cluster(Kern kern, const P& p, int CS, int NG, int ndir, int threads, size_t smem, cudaStream_t stream) {
-  static bool attr_set = false;   // one instance per kernel (template instantiation)
-  if (!attr_set) {
-    LAS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    LAS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    attr_set = true;
+  // attributes once per KERNEL: instantiations of one kernel template share this function (same pointer type)
+  static const void* done[8] = {nullptr};
+  bool attr_set = false;
+  int slot = -1;
+  for (int i = 0; i < 8; ++i) {
+    if (done[i] == reinterpret_cast<const void*>(kern)) attr_set = true;
+    if (done[i] == nullptr && slot < 0) slot = i;
   }
-  LAS_REQUIRE(smem <= 200 * 1024, "persistent LSTM: %zu bytes of shared memory needed", smem);
+  if (!attr_set) {
+    LAS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    LAS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    if (slot >= 0) done[slot] = reinterpret_cast<const void*>(kern);
+  }
+  LAS_REQUIRE(smem <= 224 * 1024, "persistent LSTM: %zu bytes of shared memory needed", smem);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(CS, NG, ndir);
   cfg.blockDim = dim3(threads);
@@ -663,9 +717,9 @@ static int fwd_max_clusters(const FGeom& f) {
   cfg.gridDim = dim3(f.CS, 1, 1); cfg.blockDim = dim3(threads);
   cfg.dynamicSmemBytes = 16 + static_cast<size_t>(2) * f.KT * 256 + static_cast<size_t>(kPF) * threads * 16;
   int n = 0;
-  if (cudaFuncSetAttribute(lstm_persist_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
-      cudaFuncSetAttribute(lstm_persist_fwd_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
-      cudaOccupancyMaxActiveClusters(&n, lstm_persist_fwd_kernel<false>, &cfg) != cudaSuccess)
+  if (cudaFuncSetAttribute(lstm_persist_fwd_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+      cudaFuncSetAttribute(lstm_persist_fwd_kernel<false, 0>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
+      cudaOccupancyMaxActiveClusters(&n, lstm_persist_fwd_kernel<false, 0>, &cfg) != cudaSuccess)
     n = -1;
   (void)cudaGetLastError();
   c = n > 0 ? n : -1;
@@ -690,9 +744,9 @@ int persist_lstm_fwd(const float* xproj, const void* whh_pk, const int32_t* lens
   {
     const int need = ((B + kNB - 1) / kNB) * ndir;
     FGeom g10;
-    if (fgeom_for(H, g10, 10) && g10.CS > 8 && fwd_max_clusters(g10) >= need) g = g10;
+    if (g.KT <= kMaxKT && fgeom_for(H, g10, 10) && g10.CS > 8 && fwd_max_clusters(g10) >= need) g = g10;
     static const char* force = getenv("LAS_FWD_CS");     // development aid: pin the forward cluster size
-    if (force) {
+    if (force && g.KT <= kMaxKT) {
       FGeom c;
       if (fgeom_for(H, c, atoi(force))) g = c;
     }
@@ -712,13 +766,19 @@ int persist_lstm_fwd(const float* xproj, const void* whh_pk, const int32_t* lens
   p.Q = g.Q; p.WPC = g.WPC; p.KT = g.KT;
   p.dbg = static_cast<long long*>(g_dbg_buf);
   const int threads = 32 * g.WPC;
-  const size_t smem = 16 + static_cast<size_t>(2) * g.KT * 256 + static_cast<size_t>(kPF) * threads * 16;
+  const bool wide = g.KT > kMaxKT;
+  const size_t smem = 16 + static_cast<size_t>(2) * g.KT * 256 + static_cast<size_t>(kPF) * threads * 16 +
+                      (wide ? static_cast<size_t>(g.WPC) * kWideKTS * 512 : 0);
   // MUFU.TANH gate activations by default: at config-2 size loss and gradients are as close to the fp32 oracle as with
   // the ex2/rcp forms (tools/parity_report.py: whole-model cosine 0.999996 either way; the 2^-11 error is below the
   // bf16 rounding of h that feeds the next step) and the step is 7 % shorter. LAS_FAST_ACT=0 selects the ex2/rcp forms.
   static const bool fast_act = getenv("LAS_FAST_ACT") == nullptr || atoi(getenv("LAS_FAST_ACT")) != 0;
-  if (fast_act) return launch_cluster(lstm_persist_fwd_kernel<true>, p, g.CS, (B + kNB - 1) / kNB, ndir, threads, smem, stream);
-  return launch_cluster(lstm_persist_fwd_kernel<false>, p, g.CS, (B + kNB - 1) / kNB, ndir, threads, smem, stream);
+  if (wide) {
+    if (fast_act) return launch_cluster(lstm_persist_fwd_kernel<true, kWideKTS>, p, g.CS, (B + kNB - 1) / kNB, ndir, threads, smem, stream);
+    return launch_cluster(lstm_persist_fwd_kernel<false, kWideKTS>, p, g.CS, (B + kNB - 1) / kNB, ndir, threads, smem, stream);
+  }
+  if (fast_act) return launch_cluster(lstm_persist_fwd_kernel<true, 0>, p, g.CS, (B + kNB - 1) / kNB, ndir, threads, smem, stream);
+  return launch_cluster(lstm_persist_fwd_kernel<false, 0>, p, g.CS, (B + kNB - 1) / kNB, ndir, threads, smem, stream);
 }
 
 int persist_lstm_bwd(const float* dy, int64_t dy_ld_b, int64_t dy_ld_t, int rep_row, const void* wT_owner_pk,
@@ -738,9 +798,15 @@ int persist_lstm_bwd(const float* dy, int64_t dy_ld_b, int64_t dy_ld_t, int rep_
   p.UGC = g.UGC; p.JT = g.JT; p.MTW = g.MTW; p.CSn = g.CS;
   p.dbg = static_cast<long long*>(g_dbg_buf);
   const int UPC = 8 * g.UGC;
+  if (g.CS > 8 || g.MTW > 2) {
+    // wide geometry: 16-CTA clusters, two more m-tiles per warp from shared memory, a 4-deep prefetch ring
+    const size_t smem = 16 + static_cast<size_t>(2) * g.CS * UPC * 8 * 4 + static_cast<size_t>(2 * g.UGC) * 256 +
+                        static_cast<size_t>(kWidePF) * 64 * g.UGC * 8 * 4 + static_cast<size_t>(2 * g.UGC) * 2 * kMaxKTW * 512;
+    return launch_cluster(lstm_persist_bwd_kernel<2, 16, kWidePF>, p, g.CS, (B + kNB - 1) / kNB, ndir, 64 * g.UGC, smem, stream);
+  }
   const size_t smem = 16 + static_cast<size_t>(2) * g.CS * UPC * 8 * 4 + static_cast<size_t>(2 * g.UGC) * 256 +
                       static_cast<size_t>(kPF) * 64 * g.UGC * 8 * 4;
-  return launch_cluster(lstm_persist_bwd_kernel, p, g.CS, (B + kNB - 1) / kNB, ndir, 64 * g.UGC, smem, stream);
+  return launch_cluster(lstm_persist_bwd_kernel<0, 8, kPF>, p, g.CS, (B + kNB - 1) / kNB, ndir, 64 * g.UGC, smem, stream);
 }
 
 }  // namespace las
@@ -785,15 +851,15 @@ int las_lstm_persist_max_clusters(int which, int H) {
     const int threads = 32 * f.WPC;
     cfg.gridDim = dim3(f.CS, 1, 1); cfg.blockDim = dim3(threads); at[0].val.clusterDim.x = f.CS;
     cfg.dynamicSmemBytes = 16 + static_cast<size_t>(2) * f.KT * 256 + static_cast<size_t>(kPF) * threads * 16;
-    cudaFuncSetAttribute(lstm_persist_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (cudaOccupancyMaxActiveClusters(&n, lstm_persist_fwd_kernel<false>, &cfg) != cudaSuccess) n = -1;
+    cudaFuncSetAttribute(lstm_persist_fwd_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (cudaOccupancyMaxActiveClusters(&n, lstm_persist_fwd_kernel<false, 0>, &cfg) != cudaSuccess) n = -1;
   } else {
     const int UPC = 8 * g.UGC;
     cfg.gridDim = dim3(g.CS, 1, 1); cfg.blockDim = dim3(64 * g.UGC); at[0].val.clusterDim.x = g.CS;
     cfg.dynamicSmemBytes = 16 + static_cast<size_t>(2) * g.CS * UPC * 8 * 4 + static_cast<size_t>(2 * g.UGC) * 256 +
                            static_cast<size_t>(kPF) * 64 * g.UGC * 8 * 4;
-    cudaFuncSetAttribute(lstm_persist_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (cudaOccupancyMaxActiveClusters(&n, lstm_persist_bwd_kernel, &cfg) != cudaSuccess) n = -1;
+    cudaFuncSetAttribute(lstm_persist_bwd_kernel<0, 8, kPF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (cudaOccupancyMaxActiveClusters(&n, lstm_persist_bwd_kernel<0, 8, kPF>, &cfg) != cudaSuccess) n = -1;
   }
   (void)cudaGetLastError();
   return n;
