@@ -358,10 +358,6 @@ def main():
         torch.cuda.synchronize()
         launches = int(LIB.lib().las_launch_count() - c0)
         tr.use_graph = tr2_graph
-    if rank != 0:
-        if world > 1:
-            torch.distributed.destroy_process_group()
-        return
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -370,8 +366,13 @@ def main():
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
     step_us = ms / args.steps * 1e3
+    # every rank takes part: the profiled step contains the gradient all-reduce
     roofs = kernel_rooflines(tr, keys[0], args.batch, args.tmax, step_us, hbm_peak, peaks.get("bf16_tflops_sustained", 1400.0),
                              "measured" if peaks else "fallback")
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
     roof = max((r for r in roofs if r["bound"] == "hbm"), key=lambda r: r["us_per_step"])
     out = {
         "metric": "train utterances/sec", "value": value, "unit": "utt/s", "n_gpus": world, "steps": args.steps,

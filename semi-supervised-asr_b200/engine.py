@@ -158,7 +158,7 @@ def _host_lens(ilens):
 
 class SupervisedTrainer:
     def __init__(self, model, optimizer, max_grad_norm=5.0, use_graph=True, process_group=None, max_graphs=8,
-                 global_exact=False):
+                 global_exact=False, overlap_allreduce=True):
         """global_exact (data parallel only): every shard is padded to the GLOBAL Tmax / Lmax and its
         loss is -sum(log_probs) / (global B * (global Lmax + 1)); the summed gradients then equal the single-GPU
         gradient of the concatenated batch up to floating-point reassociation (the reference's loss couples the
@@ -167,6 +167,13 @@ class SupervisedTrainer:
         of its shard, gradients averaged)."""
         self.global_exact = bool(global_exact)
         self.global_shape = None          # (T, L, B) override used instead of the collective (tests)
+        # Data parallel: the encoder's first layer gets an autograd graph (and a captured CUDA graph) of its own, so
+        # that the gradients of everything else -- 80 % of the bytes -- are all-reduced on a communication stream,
+        # outside any capture, WHILE that layer's BPTT (the last and longest kernel of the backward pass) runs.
+        self.overlap_allreduce = bool(overlap_allreduce) and os.environ.get("LAS_NO_OVERLAP", "0") != "1"
+        self.force_split = False          # tests: take the two-part step on one GPU (no collective is issued)
+        self.comm_stream = None
+        self._buckets = None
         self.model = model
         self.opt = optimizer
         self.max_grad_norm = max_grad_norm
@@ -208,10 +215,75 @@ class SupervisedTrainer:
             loss.backward()
         return loss.detach()
 
+    # ---- data parallel with the exchange overlapped: the step in two parts
+    def _split(self):
+        return ((self.world > 1 and self.overlap_allreduce) or self.force_split) and len(self.model.encoder.enc2.layers) > 1
+
+    def _part1(self, st, L):
+        """Forward, loss, backward of everything except encoder layer 0. -> (loss, y0, y0_leaf)"""
+        m = self.model
+        enc = m.encoder.enc2
+        jobs = enc.prep_jobs() + m.decoder.prep_jobs(0)
+        jobs.sort(key=lambda j: "bwd" in j[0])
+        Fn.prepare_ahead(jobs)
+        enc_h, y0, y0_leaf = enc.forward_dev_split(st.x, st.lens)
+        enc_lens = enc.out_lens_dev(st.lens)
+        _, logp, _, _ = m.decoder.forward_dev(enc_h, enc_lens, st.ys_in, st.ys_out, L, 0)
+        loss = -torch.sum(logp) * st.inv[0] if self.global_exact else -torch.mean(logp)
+        self.opt.zero_grad()
+        with Fn.deferred_wgrad():
+            loss.backward()
+        return loss.detach(), y0, y0_leaf
+
+    def _part2(self, y0, y0_leaf):
+        """Backward of encoder layer 0 (BPTT + its weight gradients)."""
+        with Fn.deferred_wgrad():
+            y0.backward(y0_leaf.grad)
+
+    def _bucket_ranges(self):
+        """(ranges exchanged during part 2, ranges exchanged after it) as views of the flat gradient: the second set is
+        what part 2 writes -- encoder layer 0's LSTM and projection parameters."""
+        if self._buckets is None:
+            enc = self.model.encoder.enc2
+            late = {id(p) for p in list(enc.layers[0].parameters()) + list(enc.project_layers[0].parameters())}
+            a, b = [], []
+            for p, o in zip(self.opt.params, self.opt.offsets):
+                dst = b if id(p) in late else a
+                if dst and dst[-1][1] == o:
+                    dst[-1][1] = o + (p.numel() + 3) // 4 * 4
+                else:
+                    dst.append([o, o + (p.numel() + 3) // 4 * 4])
+            g = self.opt.flat_grad
+            self._buckets = ([g[s:e] for s, e in a], [g[s:e] for s, e in b])
+        return self._buckets
+
+    def _exchange_overlapped(self, run_part2):
+        """all-reduce of the early bucket on the communication stream while `run_part2()` executes on the main stream,
+        then the late bucket on the main stream."""
+        dev = self.opt.flat_grad.device
+        main = torch.cuda.current_stream(dev)
+        if self.comm_stream is None:
+            self.comm_stream = torch.cuda.Stream(device=dev)
+        early, late = self._bucket_ranges()
+        self.comm_stream.wait_stream(main)                   # part 1 (and its weight gradients) is complete
+        with torch.cuda.stream(self.comm_stream):
+            for t in early:
+                if self.world > 1:
+                    torch.distributed.all_reduce(t, group=self.pg)
+        run_part2()
+        for t in late:
+            if self.world > 1:
+                torch.distributed.all_reduce(t, group=self.pg)
+        main.wait_stream(self.comm_stream)
+
     def _update(self):
         return self.opt.clip_and_step(self.max_grad_norm, grad_scale=1.0 if self.global_exact else 1.0 / self.world)
 
     def _body(self, st, L):
+        if self._split():
+            loss, y0, y0_leaf = self._part1(st, L)
+            self._exchange_overlapped(lambda: self._part2(y0, y0_leaf))
+            return loss, self._update()
         loss = self._fwd_bwd(st, L)
         if self.world > 1:
             torch.distributed.all_reduce(self.opt.flat_grad, group=self.pg)
@@ -312,7 +384,7 @@ class SupervisedTrainer:
         self.model.train()
         if not self.use_graph:
             return self._body(st, L)
-        stamp = (self.arena.gen, _hyper_stamp(self.opt), self.max_grad_norm, self.global_exact)
+        stamp = (self.arena.gen, _hyper_stamp(self.opt), self.max_grad_norm, self.global_exact, self._split())
         ent = self.cache.lookup(key, stamp)
         if ent is None:
             if self.cache.sighting(key) == 0:      # first sight of a geometry: eager (also warms lazy init)
@@ -326,14 +398,24 @@ class SupervisedTrainer:
                 # scheduled before those of the (default-priority) weight-gradient side stream
                 self.cap_stream = torch.cuda.Stream(device=st.x.device, priority=-1)
             ent = {"stamp": stamp}
-            with torch.cuda.graph(g, pool=pool, stream=self.cap_stream):
-                if self.world == 1:
-                    ent["loss"], ent["norm"] = self._body(st, L)
-                else:
-                    ent["loss"] = self._fwd_bwd(st, L)
+            if self._split():
+                with torch.cuda.graph(g, pool=pool, stream=self.cap_stream):
+                    ent["loss"], y0, y0_leaf = self._part1(st, L)
+                g2 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g2, pool=pool, stream=self.cap_stream):
+                    self._part2(y0, y0_leaf)
+                ent["graph2"] = g2
+                ent["keep"] = (y0, y0_leaf)
+            else:
+                with torch.cuda.graph(g, pool=pool, stream=self.cap_stream):
+                    if self.world == 1:
+                        ent["loss"], ent["norm"] = self._body(st, L)
+                    else:
+                        ent["loss"] = self._fwd_bwd(st, L)
             ent["graph"] = g
             self.cache.store(key, ent)
-        if self.world > 1 and (self.update_graph is None or self.update_stamp != stamp[1:]):
+        two_part = "graph2" in ent
+        if (self.world > 1 or two_part) and (self.update_graph is None or self.update_stamp != stamp[1:]):
             torch.cuda.synchronize()
             gu = torch.cuda.CUDAGraph()
             step0 = self.opt.step_dev.clone()
@@ -342,9 +424,12 @@ class SupervisedTrainer:
             self.update_graph, self.update_stamp = gu, stamp[1:]
             self.opt.step_dev.copy_(step0)     # nothing ran during capture, but keep the counter explicit
         ent["graph"].replay()
-        if self.world == 1:
+        if self.world == 1 and not two_part:
             return ent["loss"], ent["norm"]
-        torch.distributed.all_reduce(self.opt.flat_grad, group=self.pg)
+        if two_part:
+            self._exchange_overlapped(ent["graph2"].replay)
+        else:
+            torch.distributed.all_reduce(self.opt.flat_grad, group=self.pg)
         self.update_graph.replay()
         return ent["loss"], self.update_norm
 

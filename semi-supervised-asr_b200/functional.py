@@ -540,7 +540,8 @@ class EncoderFn(torch.autograd.Function):
                 grads[10 * i + 8:10 * i + 10] = sc.deliver([gemm(dz, Ho, 1, y, Kp, 1, Ho, Kp, n), colsum(dz, Ho)])
                 if i == 0 and sc.deferred:
                     run_late_jobs()           # parked side-stream work runs next to the longest BPTT kernel
-            dx, dG = lstm_layer_bwd(lsaved, [w_hh, w_hh_r], dy, need_dx=i > 0)
+            need_x = i > 0 or ctx.needs_input_grad[0]      # the input's gradient only when somebody asked (split encoder)
+            dx, dG = lstm_layer_bwd(lsaved, [w_hh, w_hh_r], dy, need_dx=need_x)
             del dy
             # LSTM weight gradients from dG (overlap the next layer's BPTT; layer 0's are the exposed tail)
             with wgrad_scope(lw[:8], dG, lsaved) as sc:
@@ -550,8 +551,14 @@ class EncoderFn(torch.autograd.Function):
                                                        d_wcat[4 * H:, :Din], d_whh[1], d_bcat[4 * H:], d_bcat[4 * H:]])
             if i > 0:
                 dout = dx
+        dinput = None
+        if ctx.needs_input_grad[0]:
+            Dp0 = dx.shape[1]
+            dinput = dx.view(B, -1, Dp0)[:, :, :ctx.D]
+            if Dp0 != ctx.D:
+                dinput = dinput.contiguous()
         ctx.saved = None
-        return (None, None, None, None, *grads)
+        return (dinput, None, None, None, *grads)
 
 
 # --------------------------------------------------------------------------------------------

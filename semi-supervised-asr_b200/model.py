@@ -69,6 +69,24 @@ class pBLSTM(torch.nn.Module):
         p = float(self.dropout_rate) if self.training else 0.0
         return Fn.EncoderFn.apply(xpad, lens_dev, tuple(int(s) for s in self.subsample), p, *self._weights())
 
+    def forward_dev_split(self, xpad, lens_dev):
+        """The same as forward_dev, as two autograd graphs: layer 0, then layers 1.. on a detached copy of its output.
+        -> (enc_h, y0, y0_leaf): after `loss.backward()` the gradient sits in `y0_leaf.grad`, and
+        `y0.backward(y0_leaf.grad)` runs layer 0's backward on its own -- the data-parallel trainer exchanges all other
+        gradients while that last (and longest) BPTT kernel runs."""
+        p = float(self.dropout_rate) if self.training else 0.0
+        w = self._weights()
+        subs = tuple(int(s) for s in self.subsample)
+        y0 = Fn.EncoderFn.apply(xpad, lens_dev, subs[:1], p, *w[:10])
+        if len(subs) == 1:
+            return y0, None, None
+        lens1 = lens_dev
+        if subs[0] > 1:
+            lens1 = torch.empty_like(lens_dev)
+            Fn.call("las_pyramid_lens", Fn.ptr(lens_dev), lens_dev.numel(), subs[0], Fn.ptr(lens1))
+        y0_leaf = y0.detach().requires_grad_(True)
+        return Fn.EncoderFn.apply(y0_leaf, lens1, subs[1:], p, *w[10:]), y0, y0_leaf
+
     def out_lens_dev(self, lens_dev):
         """(len + 1) // sub per pyramid level, on the device (model.py:92)."""
         cur = lens_dev

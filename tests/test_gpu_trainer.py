@@ -223,3 +223,31 @@ def test_global_exact_shards_sum_to_the_single_gpu_gradient():
     tr.global_exact, tr.global_shape = False, None
     k = tr.stage(*D.collate(D.shard_items(items, 1, world, lambda it: it[0].shape[0])))
     assert k[1] <= key[1] and k[3] <= key[3]
+
+
+def test_two_part_step_equals_the_single_graph_step():
+    """The data-parallel trainer runs the step in two parts (everything except encoder layer 0, then layer 0's backward
+    as its own autograd graph and CUDA graph) so that the gradient exchange overlaps the last BPTT kernel. On one GPU,
+    with no collective issued, the two-part step must follow the one-graph step exactly -- eagerly and as graphs."""
+    G = load_golden("sup_small_odd")
+    batch = _batch(G)
+    traj = {}
+    for split in (False, True):
+        for use_graph in (False, True):
+            m, opt, tr = _trainer(G, use_graph)
+            tr.force_split = split
+            out = []
+            for _ in range(5):
+                loss, norm = tr.step(*batch)
+                out.append((float(loss), float(norm)))
+            traj[(split, use_graph)] = np.array(out)
+            if split and use_graph:
+                assert tr.cache.captures == 1 and "graph2" in next(iter(tr.cache.graphs.values()))
+                early, late = tr._bucket_ranges()
+                n = sum(t.numel() for t in early) + sum(t.numel() for t in late)
+                assert n == opt.flat_grad.numel() and len(late) == 2          # layer-0 LSTM weights + its projection
+    ref = traj[(False, False)]
+    assert abs(ref[0, 0] - float(G["raw"]["loss"])) < 1e-3 * abs(float(G["raw"]["loss"]))
+    for k, v in traj.items():
+        assert np.allclose(v[:, 0], ref[:, 0], rtol=2e-3), (k, v, ref)
+        assert np.allclose(v[:, 1], ref[:, 1], rtol=5e-2), (k, v, ref)
