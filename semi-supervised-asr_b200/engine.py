@@ -158,7 +158,7 @@ def _host_lens(ilens):
 
 class SupervisedTrainer:
     def __init__(self, model, optimizer, max_grad_norm=5.0, use_graph=True, process_group=None, max_graphs=8,
-                 global_exact=False, overlap_allreduce=True):
+                 global_exact=False, overlap_allreduce=False):
         """global_exact (data parallel only): every shard is padded to the GLOBAL Tmax / Lmax and its
         loss is -sum(log_probs) / (global B * (global Lmax + 1)); the summed gradients then equal the single-GPU
         gradient of the concatenated batch up to floating-point reassociation (the reference's loss couples the
@@ -167,10 +167,14 @@ class SupervisedTrainer:
         of its shard, gradients averaged)."""
         self.global_exact = bool(global_exact)
         self.global_shape = None          # (T, L, B) override used instead of the collective (tests)
-        # Data parallel: the encoder's first layer gets an autograd graph (and a captured CUDA graph) of its own, so
-        # that the gradients of everything else -- 80 % of the bytes -- are all-reduced on a communication stream,
-        # outside any capture, WHILE that layer's BPTT (the last and longest kernel of the backward pass) runs.
-        self.overlap_allreduce = bool(overlap_allreduce) and os.environ.get("LAS_NO_OVERLAP", "0") != "1"
+        # Data parallel, overlap_allreduce=True: the encoder's first layer gets an autograd graph (and a captured CUDA
+        # graph) of its own, so that the gradients of everything else -- 80 % of the bytes -- are all-reduced on a
+        # communication stream, outside any capture, WHILE that layer's BPTT (the last and longest kernel of the backward
+        # pass) runs. Measured on 2 B200s it LOSES (8.31 vs 8.07 ms per step end to end): the graph boundary forces the
+        # join of the weight-gradient stream before layer 0's BPTT, which puts layer 1's weight-gradient GEMMs (otherwise
+        # hidden under that kernel) on the critical path, and costs one more graph launch -- more than the ~0.1 ms
+        # exchange it hides. Off by default; LAS_OVERLAP=1 switches it on.
+        self.overlap_allreduce = bool(overlap_allreduce) or os.environ.get("LAS_OVERLAP", "0") == "1"
         self.force_split = False          # tests: take the two-part step on one GPU (no collective is issued)
         self.comm_stream = None
         self._buckets = None
