@@ -352,6 +352,18 @@ class SupervisedTrainer:
         """The static device buffers (x, lens, ys_in, ys_out views) a step on geometry `key` reads."""
         return _Views(self._arena(), *key)
 
+    def snapshot(self, key):
+        """Device copies of the batch currently staged for `key` (the staging arenas are shared by all geometries, so a
+        later stage() overwrites them); `restore` puts one back with device-to-device copies only."""
+        st = self.staged(key)
+        return tuple(t.clone() for t in (st.x, st.lens, st.ys_in, st.ys_out, st.inv))
+
+    def restore(self, key, snap):
+        st = self.staged(key)
+        for dst, src in zip((st.x, st.lens, st.ys_in, st.ys_out, st.inv), snap):
+            dst.copy_(src, non_blocking=True)
+        return key
+
     def stage(self, xs, ilens, ys):
         """Host -> device copies of one batch into the static buffers (views of its geometry)."""
         key, st, host_lens, T, ys_in, ys_out = self._geometry(xs, ilens, ys)
