@@ -6,6 +6,7 @@
 // Row conventions: every per-step buffer is [B, L+1, width]; row r of zc/ctx/ws/logits holds the
 // value produced by step r-1 (row 0 = initial state), so "the state entering step t" is row t and
 // the shifted weight-gradient GEMMs after the loop need no special case at t = 0.
+#include <stdlib.h>
 #include "common.cuh"
 #include "las_internal.h"
 #include "../../include/las_b200.h"
@@ -835,6 +836,133 @@ __global__ void __launch_bounds__(MAXT, MINB) att_param_grad_kernel(const float*
   }
 }
 
+// dP alone (the part of the above that the encoder's backward waits for), with the mlp_att contraction on tensor cores:
+// for a tile of 16 frames and one step t, x[frame][a] = P + dz_t + conv_t[frame][:] . mlp_att[a][:] is one
+// mma.m16n8k16 per 8 attention dims (rows = frames, K = the <= 16 conv channels, bf16 hi/lo split of both operands as
+// in the forward kernel: 3 MMAs), initialised from P + dz_t; the element-wise tail (tanh, 1 - s^2, times de gv, sum over
+// t) stays in the accumulator layout. Per element ~6 issued instructions instead of ~25 (12 of them FMAs on operands
+// every thread fetched from shared memory for itself). grid (ceil(Te/16), B), block A (a warp = 32 attention dims).
+constexpr int kDPT = 8;        // decoder steps per shared-memory chunk
+constexpr int kDPld = 24;      // row stride (floats) of a staged conv row: conflict-free 8-byte fragment loads
+__device__ __forceinline__ void split2_bf16(float x, float y, uint32_t& hi, uint32_t& lo) {
+  hi = pack_bf16x2(x, y);
+  const float2 h = unpack_bf16x2(hi);
+  lo = pack_bf16x2(x - h.x, y - h.y);
+}
+__global__ void __launch_bounds__(320, 2) att_dp_mma_kernel(const float* __restrict__ P, const float* __restrict__ dzf,
+                                                            const float* __restrict__ conv_save,
+                                                            const float* __restrict__ de_all,
+                                                            const float* __restrict__ mlp_att,
+                                                            const float* __restrict__ gvec, int B, int L, int Te, int A,
+                                                            int C, float* __restrict__ dP) {
+  __shared__ __align__(16) float conv_s[2][kDPT][16][kDPld];
+  __shared__ float de_s[2][kDPT][16];
+  const int b = blockIdx.y, te0 = blockIdx.x * 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, tig = lane & 3;
+  const int ntl = min(16, Te - te0);
+  const int a_w = 32 * warp;                        // this warp's attention dims a_w .. a_w + 31 (4 n-tiles)
+  // constant operands: B fragments of mlp_att^T (k = channel, n = attention dim), P tile, gvec
+  uint32_t Bh[4][2], Bl[4][2];
+  float pv[4][4], gv[4][2], dp[4][4];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    const int an = a_w + 8 * nt + gq;               // B fragment column of this lane
+    float m[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = 2 * tig + (k & 1) + 8 * (k >> 1);
+      m[k] = (an < A && c < C) ? mlp_att[an * C + c] : 0.f;
+    }
+    split2_bf16(m[0], m[1], Bh[nt][0], Bl[nt][0]);
+    split2_bf16(m[2], m[3], Bh[nt][1], Bl[nt][1]);
+    const int ac = a_w + 8 * nt + 2 * tig;          // accumulator columns ac, ac + 1
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int fr = gq + 8 * (e >> 1), a = ac + (e & 1);
+      pv[nt][e] = (fr < ntl && a < A) ? P[(static_cast<int64_t>(b) * Te + te0 + fr) * A + a] : 0.f;
+      dp[nt][e] = 0.f;
+    }
+    gv[nt][0] = ac < A ? gvec[ac] : 0.f;
+    gv[nt][1] = ac + 1 < A ? gvec[ac + 1] : 0.f;
+  }
+  auto stage = [&](int chunk, int buf) {
+    const int t0 = chunk * kDPT;
+    for (int i = threadIdx.x; i < kDPT * 16 * 4; i += blockDim.x) {
+      const int q4 = i & 3, f = (i >> 2) & 15, tt = i >> 6, t = t0 + tt;
+      float* dst = &conv_s[buf][tt][f][4 * q4];
+      if (t < L && f < ntl) {
+        const float* src = conv_save + ((static_cast<int64_t>(b) * L + t) * Te + te0 + f) * 16 + 4 * q4;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+      } else {
+        *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    for (int i = threadIdx.x; i < kDPT * 16; i += blockDim.x) {
+      const int f = i & 15, tt = i >> 4, t = t0 + tt;
+      float* dst = &de_s[buf][tt][f];
+      if (t < L && f < ntl) {
+        const float* src = de_all + (static_cast<int64_t>(b) * L + t) * Te + te0 + f;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+      } else {
+        *dst = 0.f;
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  const int nchunks = (L + kDPT - 1) / kDPT;
+  const float* dz_row = dzf + static_cast<int64_t>(b) * L * A + a_w + 2 * tig;
+  stage(0, 0);
+  for (int ch = 0; ch < nchunks; ++ch) {
+    const int buf = ch & 1;
+    if (ch + 1 < nchunks) stage(ch + 1, buf ^ 1);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncthreads();
+    const int tn = min(kDPT, L - ch * kDPT);
+    for (int tt = 0; tt < tn; ++tt) {
+      // A fragments of this step's conv tile (rows = frames gq / gq + 8, k = channels 2tig.. / 2tig + 8..)
+      const float2 c00 = *reinterpret_cast<const float2*>(&conv_s[buf][tt][gq][2 * tig]);
+      const float2 c10 = *reinterpret_cast<const float2*>(&conv_s[buf][tt][gq + 8][2 * tig]);
+      const float2 c01 = *reinterpret_cast<const float2*>(&conv_s[buf][tt][gq][2 * tig + 8]);
+      const float2 c11 = *reinterpret_cast<const float2*>(&conv_s[buf][tt][gq + 8][2 * tig + 8]);
+      uint32_t Ah[4], Al[4];
+      split2_bf16(c00.x, c00.y, Ah[0], Al[0]);
+      split2_bf16(c10.x, c10.y, Ah[1], Al[1]);
+      split2_bf16(c01.x, c01.y, Ah[2], Al[2]);
+      split2_bf16(c11.x, c11.y, Ah[3], Al[3]);
+      const float de0 = de_s[buf][tt][gq], de1 = de_s[buf][tt][gq + 8];
+      const float* dzp = dz_row + static_cast<int64_t>(ch * kDPT + tt) * A;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int ac = a_w + 8 * nt + 2 * tig;
+        float2 dz = make_float2(0.f, 0.f);
+        if (ac + 1 < A) dz = __ldg(reinterpret_cast<const float2*>(dzp + 8 * nt));
+        float x[4] = {pv[nt][0] + dz.x, pv[nt][1] + dz.y, pv[nt][2] + dz.x, pv[nt][3] + dz.y};
+        mma_bf16_16816(x, Ah, Bh[nt][0], Bh[nt][1]);
+        mma_bf16_16816(x, Al, Bh[nt][0], Bh[nt][1]);
+        mma_bf16_16816(x, Ah, Bl[nt][0], Bl[nt][1]);
+        const float g0 = gv[nt][0], g1 = gv[nt][1];
+        const float s0 = tanh_fast(x[0]), s1 = tanh_fast(x[1]), s2 = tanh_fast(x[2]), s3 = tanh_fast(x[3]);
+        dp[nt][0] = fmaf(de0 * g0, 1.f - s0 * s0, dp[nt][0]);
+        dp[nt][1] = fmaf(de0 * g1, 1.f - s1 * s1, dp[nt][1]);
+        dp[nt][2] = fmaf(de1 * g0, 1.f - s2 * s2, dp[nt][2]);
+        dp[nt][3] = fmaf(de1 * g1, 1.f - s3 * s3, dp[nt][3]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    const int ac = a_w + 8 * nt + 2 * tig;
+    if (ac + 1 < A) {
+      if (gq < ntl)
+        *reinterpret_cast<float2*>(dP + (static_cast<int64_t>(b) * Te + te0 + gq) * A + ac) = make_float2(dp[nt][0], dp[nt][1]);
+      if (gq + 8 < ntl)
+        *reinterpret_cast<float2*>(dP + (static_cast<int64_t>(b) * Te + te0 + gq + 8) * A + ac) = make_float2(dp[nt][2], dp[nt][3]);
+    }
+  }
+}
+
 static size_t energy_smem(const las_dec_args* a, int CM, int nwarps, bool bwd) {
   const int ksz = 2 * a->K + 1;
   size_t f = a->Te + 2 * a->K + static_cast<size_t>(a->C) * ksz + kTT * CM;
@@ -916,6 +1044,15 @@ int las_att_param_grads_part(const float* P, const float* dzf, const float* conv
   if (B == 0 || Te == 0 || L == 0) return 0;
   const int CM = (C + 3) / 4 * 4;          // channel count padded to whole float4 pieces: no FMAs on padding beyond that
   const int threads = (A + 31) / 32 * 32;
+  static const bool dp_mma = getenv("LAS_DP_MMA") == nullptr || atoi(getenv("LAS_DP_MMA")) != 0;
+  if (what == 1 && dp_mma && A % 32 == 0 && A <= 320 && reinterpret_cast<uintptr_t>(dzf) % 8 == 0 &&
+      reinterpret_cast<uintptr_t>(dP) % 8 == 0) {
+    // the critical-path half (dP alone): tensor-core form
+    att_dp_mma_kernel<<<dim3((Te + 15) / 16, B), A, 0, stream>>>(P, dzf, conv_save, de_all, mlp_att, gvec, B, L, Te, A, C, dP);
+    ++g_launches;
+    LAS_LAUNCH_CHECK();
+    return 0;
+  }
   const dim3 grid((Te + kPG - 1) / kPG, B);
   // blocks of <= 320 threads are compiled for two CTAs per SM (<= 102 registers): the loop is latency-bound
 #define LAS_APG2(CMV, W)                                                                                               \

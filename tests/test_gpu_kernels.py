@@ -23,7 +23,7 @@ def test_att_dq_matches_einsum(B, L, Te, O):
     assert torch.allclose(dQ.double(), want, rtol=1e-5, atol=1e-5)
 
 
-@pytest.mark.parametrize("B,L,Te,A,C", [(3, 11, 13, 48, 5), (2, 40, 30, 320, 10), (4, 5, 7, 64, 16)])
+@pytest.mark.parametrize("B,L,Te,A,C", [(3, 11, 13, 48, 5), (2, 40, 30, 320, 10), (4, 5, 7, 64, 16), (3, 126, 125, 320, 10)])
 def test_att_param_grads_split_equals_single_pass_and_torch(B, L, Te, A, C):
     Fn, LIB = pkg("functional"), pkg("_lib")
     dev = torch.device("cuda")
@@ -48,14 +48,17 @@ def test_att_param_grads_split_equals_single_pass_and_torch(B, L, Te, A, C):
     dP3, dm3, dg3 = run(3)
     dP1, dm1, dg1 = run(1)
     dP2, dm2, dg2 = run(2)
-    def close(a, b):      # the instances are compiled separately (different FMA contraction): equal to f32 rounding
-        return float((a - b).abs().max()) <= 1e-5 * float(b.abs().max())
-    assert close(dP1, dP3) and not dm1.any() and not dg1.any()                                     # dP only
+    def close(a, b, tol=1e-5):      # the instances are compiled separately (different FMA contraction): equal to f32 rounding
+        return float((a - b).abs().max()) <= tol * float(b.abs().max())
+    # dP only: for att_dim % 32 == 0 this is the tensor-core kernel (mlp_att contraction as split-bf16 MMAs: ~2^-16
+    # relative per product instead of f32)
+    assert close(dP1, dP3, 1e-5 if A % 32 else 5e-4) and not dm1.any() and not dg1.any()
     assert close(dm2, dm3) and close(dg2, dg3) and not dP2.any()                                   # parameters only
     # torch fp32/fp64 reference (the kernel recomputes tanh with tanh.approx: 2^-11 relative)
     s = torch.tanh(P.double()[:, None] + dz.double()[:, :, None] + torch.einsum("blec,ac->blea", conv[..., :C].double(), matt.double()))
     ds = de.double()[..., None] * gv.double() * (1 - s * s)
-    for got, want in ((dP3.view(B, Te, A), ds.sum(1)), (dm3, torch.einsum("blea,blec->ac", ds, conv[..., :C].double())),
+    for got, want in ((dP3.view(B, Te, A), ds.sum(1)), (dP1.view(B, Te, A), ds.sum(1)),
+                      (dm3, torch.einsum("blea,blec->ac", ds, conv[..., :C].double())),
                       (dg3, torch.einsum("ble,blea->a", de.double(), s))):
         err = float((got.double() - want).abs().max() / want.abs().max())
         assert err < 5e-3, err
