@@ -347,6 +347,30 @@ def main():
     e3.record()
     barrier()
     ms_e2e = e2.elapsed_time(e3)
+    # ---- the same, starting one level further up: utterances in the reference's pickle item format (feature [T, D]
+    # float32 array, token list) -> data.BatchLoader (sorting, zero-padding and collation on a background thread
+    # straight into page-locked buffers) -> SupervisedTrainer.steps. One GPU only (every rank would need every item).
+    ms_loader = None
+    if world == 1:
+        D = importlib.import_module(PKG + ".data")
+        items = [(np.ascontiguousarray(x[b, :l]), ys[b].tolist()) for x, lens_b, ys in batches for b, l in enumerate(lens_b)]
+        loader = D.BatchLoader(items, args.batch, shuffle=False, drop_last=True, prefetch=2)
+        epochs = (args.steps + nb - 1) // nb
+
+        def stream():
+            for _ in range(epochs):
+                yield from loader
+        for _ in tr.steps(b for b in loader):          # one untimed pass: ring buffers allocated and pinned
+            pass
+        barrier()
+        e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e4.record()
+        n_l = 0
+        for loss, _ in tr.steps(stream()):
+            n_l += 1
+        e5.record()
+        barrier()
+        ms_loader = e4.elapsed_time(e5) / n_l
     clocks = sampler.stop()
     t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:
@@ -398,6 +422,10 @@ def main():
                    "l2": "working set per step (>1 GB of saved activations) exceeds the 126 MB L2; no flush"},
         "e2e": {"value": e2e, "unit": "utt/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": 8},
+        "e2e_from_items": (None if ms_loader is None else
+                           {"value": args.batch / (ms_loader * 1e-3), "unit": "utt/s", "ms_per_step": ms_loader,
+                            "what": "pickle-format items -> data.BatchLoader(prefetch=2: background collation into pinned "
+                                    "buffers) -> SupervisedTrainer.steps; H2D and loss read-back every step"}),
         "gpu_launches": launches * args.steps,
         "gpu_launches_per_step": launches,
         "clocks": clocks,
