@@ -16,7 +16,7 @@ m = M.E2E(input_dim=249, enc_hidden_dim=320, enc_n_layers=3, subsample=[2, 2, 2]
           conv_channels=10, conv_kernel_size=100, att_odim=320, embedding_dim=128, output_dim=34, ls_weight=0.05, labeldist=ld).to(dev)
 lm = M.LM(output_dim=34, embedding_dim=256, hidden_dim=640, dropout_rate=0.5, n_layers=2, bos=1, eos=2, pad=0, ls_weight=0.05, labeldist=ld).to(dev)
 opt = OPT.FusedAdam(m.parameters(), lr=1e-4, weight_decay=1e-6, amsgrad=True)
-tr = E.SSLTrainer(m, lm, opt, proportion=0.125, use_graph=True)
+tr = E.SSLTrainer(m, lm, opt, proportion=0.125, use_graph=True, guard_empty_mask=True)
 lab = (torch.from_numpy(x).to(dev), lens, [torch.from_numpy(y).to(dev) for y in ys])
 unlab = (torch.from_numpy(ux).to(dev), ulens)
 for _ in range(3):
