@@ -275,6 +275,13 @@ typedef struct las_dec_args {
    * contents); -1: always L steps. */
   const void* out_bf;
   int32_t bos_token, stop_token;
+  /* mode 1 on the per-step kernels only. Scheduled sampling (model.py:327-329): tok_teacher = ys_in int64 [B, L+1],
+   * tf_mask uint8 [L+1]: step r consumes the teacher token where tf_mask[r] != 0, else the previous step's prediction.
+   * sample != 0: the prediction is drawn from softmax(logits) (Categorical sampling, model.py:349-351; needs seed_dev)
+   * instead of the argmax. */
+  const int64_t* tok_teacher;
+  const uint8_t* tf_mask;
+  int32_t sample, _pad3;
 } las_dec_args;
 
 int las_att_init(const int32_t* enc_lens, int B, int Te, float* w, int64_t w_ld, void* stream);

@@ -205,10 +205,12 @@ def attloc_step(enc_h, pre_enc, dec_z, att_prev, P, prefix="attention", scaling=
 
 def decoder_forward(enc_h, enc_lens, P, ys=None, max_dec_timesteps=500, smooth=False, scaling=1.0,
                     label_smoothing=True, ls_weight=0.0, labeldist=None, training=True,
-                    bos=BOS, eos=EOS):
-    """Decoder.forward (model.py:296-367) with dropout disabled and tf_rate = 1.0 (config.yaml
-    pins it). ys given -> teacher forcing; ys None -> free run with argmax feedback,
-    or the smooth embedding softmax(scaling*logit) @ E (model.py:341)."""
+                    bos=BOS, eos=EOS, tf_draws=None):
+    """Decoder.forward (model.py:296-367) with dropout disabled. ys given -> teacher forcing; ys None -> free run
+    with argmax feedback, or the smooth embedding softmax(scaling*logit) @ E (model.py:341).
+    tf_draws (scheduled sampling, model.py:327-329): one boolean per step -- the outcome of the reference's
+    `np.random.random_sample() <= tf_rate` -- where False feeds the previous step's argmax back instead of the
+    teacher's token (step 0 always takes the teacher's <BOS>). None = tf_rate 1.0 (config.yaml pins it)."""
     B, Te, _ = enc_h.shape
     emb_w = P["decoder.embedding.weight"]
     w_ih, w_hh = P["decoder.LSTMCell.weight_ih"], P["decoder.LSTMCell.weight_hh"]
@@ -232,7 +234,10 @@ def decoder_forward(enc_h, enc_lens, P, ys=None, max_dec_timesteps=500, smooth=F
     logit = None
     for t in range(olength):
         if ys is not None:
-            emb = eys[:, t]
+            if tf_draws is None or t == 0 or bool(tf_draws[t]):
+                emb = eys[:, t]
+            else:
+                emb = F.embedding(preds[-1], emb_w, padding_idx=PAD)
         elif t == 0:
             emb = F.embedding(torch.full((B,), bos, dtype=torch.long), emb_w, padding_idx=PAD)
         elif smooth:

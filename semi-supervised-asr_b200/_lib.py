@@ -33,6 +33,7 @@ class DecArgs(ctypes.Structure):
         + [(n, c_void_p) for n in ("seed_dev", "zcd", "pbar")]
         + [("t_begin", c_int32), ("t_end", c_int32), ("mlp_dec_pk_p", c_void_p)]
         + [("out_bf", c_void_p), ("bos_token", c_int32), ("stop_token", c_int32)]
+        + [("tok_teacher", c_void_p), ("tf_mask", c_void_p), ("sample", c_int32), ("_pad3", c_int32)]
     )
 
 

@@ -222,6 +222,12 @@ struct NextEmbParams {
   float scaling; int smooth;
   int64_t* pred; int64_t pred_ld;       // pred[b*pred_ld]
   __nv_bfloat16* emb_out; int64_t eo_ld;
+  // scheduled sampling (model.py:327-329: teacher token with probability tf_rate, else the previous prediction) and
+  // Categorical sampling of the prediction (model.py:349-351); both only in the non-smooth branch
+  const int64_t* teacher;               // [B, R] teacher tokens (ys_in) or nullptr
+  const uint8_t* tf_mask;               // [R]: 1 = step `row` consumes the teacher token
+  int sample; uint32_t sample_site;
+  const unsigned long long* sample_seed;
 };
 // One CTA (4 warps) per utterance; dynamic shared memory: V floats (softmax numerators).
 __global__ void __launch_bounds__(128) next_emb_kernel(NextEmbParams p) {
@@ -233,8 +239,29 @@ __global__ void __launch_bounds__(128) next_emb_kernel(NextEmbParams p) {
   const float* x = p.logits + b * p.lg_ld;
   if (warp == 0) {
     float mx;
-    const int amax = warp_argmax(x, p.V, lane, &mx);
-    if (lane == 0) { s_mx = mx; s_amax = amax; p.pred[b * p.pred_ld] = amax; }
+    int amax = warp_argmax(x, p.V, lane, &mx);
+    if (lane == 0) {
+      if (p.sample) {
+        // Categorical(logits).sample(): inverse CDF of softmax(logits) at one counter-based uniform per (utterance, step)
+        const unsigned long long sd = *p.sample_seed;
+        const uint4 r = philox4x32_10(make_uint2(static_cast<uint32_t>(sd), static_cast<uint32_t>(sd >> 32)),
+                                      make_uint4(static_cast<uint32_t>(b), static_cast<uint32_t>(p.row), p.sample_site, 0x53414d50u));
+        const float u = (static_cast<float>(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f);
+        float tot = 0.f;
+        for (int v = 0; v < p.V; ++v) tot += __expf(x[v] - mx);
+        float acc = 0.f;
+        int pick = p.V - 1;
+        for (int v = 0; v < p.V; ++v) {
+          acc += __expf(x[v] - mx);
+          if (acc >= u * tot) { pick = v; break; }
+        }
+        amax = pick;
+      }
+      p.pred[b * p.pred_ld] = amax;
+      // the token the NEXT step consumes: the teacher's when scheduled sampling says so
+      if (p.teacher && p.tf_mask[p.row]) amax = static_cast<int>(p.teacher[static_cast<int64_t>(b) * p.R + p.row]);
+      s_mx = mx; s_amax = amax;
+    }
   }
   __syncthreads();
   const float mx = s_mx;
@@ -1152,6 +1179,8 @@ static int dec_fwd_steps(const las_dec_args* a, cudaStream_t stream, int t_begin
   const bool free_run = a->mode != 0 && with_out;
   const bool drop = a->drop_p > 0.f && with_cell;
   if (drop) LAS_REQUIRE(a->seed_dev && a->zcd, "decoder: dropout needs seed_dev and the zcd buffer");
+  if (a->mode == 1 && a->sample) LAS_REQUIRE(a->seed_dev, "decoder: sampling needs seed_dev");
+  if (a->mode == 1 && a->tok_teacher) LAS_REQUIRE(a->tf_mask, "decoder: scheduled sampling needs tf_mask");
   __nv_bfloat16* zcd = static_cast<__nv_bfloat16*>(a->zcd);
   __nv_bfloat16* zc = static_cast<__nv_bfloat16*>(a->zc);
   __nv_bfloat16* ctx = static_cast<__nv_bfloat16*>(a->ctx);
@@ -1225,6 +1254,9 @@ static int dec_fwd_steps(const las_dec_args* a, cudaStream_t stream, int t_begin
       np.B = B; np.V = V; np.E = E; np.logits = lg; np.lg_ld = R * V; np.emb_w = a->emb_w;
       np.scaling = a->smooth_scaling; np.smooth = (a->mode == 2);
       np.pred = a->pred + t; np.pred_ld = L;
+      np.teacher = a->mode == 1 ? a->tok_teacher : nullptr; np.tf_mask = a->tf_mask;
+      np.sample = a->mode == 1 ? a->sample : 0; np.sample_site = a->drop_site + 7;
+      np.sample_seed = static_cast<const unsigned long long*>(a->seed_dev);
       np.emb_out = emb_op + static_cast<int64_t>(t + 1) * Ep; np.eo_ld = R * Ep;
       next_emb_kernel<<<B, 128, V * sizeof(float), stream>>>(np); ++g_launches;
     }

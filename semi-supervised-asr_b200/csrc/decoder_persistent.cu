@@ -1875,7 +1875,8 @@ int dec_persist_supported(const las_dec_args* a) {
   if (a->mode == 1) {
     // greedy free-running decoding, inference only: forward kernel alone, no dropout, whole sequence in one launch
     if (a->drop_p > 0.f || a->embx == nullptr || a->out_bf == nullptr || a->out_b == nullptr || a->logits == nullptr ||
-        a->pred == nullptr || a->V < 1 || a->V > 8 * kCS || a->t_begin != 0 || (a->t_end != 0 && a->t_end != a->L))
+        a->pred == nullptr || a->V < 1 || a->V > 8 * kCS || a->t_begin != 0 || (a->t_end != 0 && a->t_end != a->L) ||
+        a->tok_teacher != nullptr || a->sample != 0)
       return 0;
     if (pick_nb_fwd(a, g) == 0) return 0;
   } else if (pick_nb_fwd(a, g) == 0 || pick_nb_bwd(a, bg) == 0) {

@@ -658,7 +658,10 @@ class DecoderFn(torch.autograd.Function):
     unused), ws_alloc f32 [B, L+1, Te] (row 0 = initial alignment), pred int64 [B, L] or None)."""
 
     @staticmethod
-    def forward(ctx, enc_h, enc_lens, ys_in, L, mode, smooth_scaling, att_scaling, K, bos, p_drop, *wts):
+    def forward(ctx, enc_h, enc_lens, ys_in, L, mode, smooth_scaling, att_scaling, K, bos, p_drop, tf_mask, sample, *wts):
+        """tf_mask: None, or a uint8 tensor [L+1] for scheduled sampling (mode 1 with teacher tokens `ys_in`: step r
+        consumes the teacher token where tf_mask[r] != 0, else the previous prediction; model.py:327-329). sample:
+        the prediction is drawn from softmax(logits) instead of the argmax (mode 1, model.py:349-351)."""
         W = dict(zip(DEC_WEIGHTS, wts))
         dev = enc_h.device
         site0 = new_sites() if p_drop > 0 else 0
@@ -720,7 +723,13 @@ class DecoderFn(torch.autograd.Function):
         es = GREEDY_EARLY_STOP
         # greedy decoding without autograd (Solver.validation / test, solver.py:212-286) may run as ONE cluster-persistent
         # launch too: the embedding half of the cell input becomes a per-token table, the argmax feeds back in-kernel
-        greedy_p = mode == 1 and DEC_PERSISTENT and p_drop == 0 and not torch.is_grad_enabled() and ZC % 8 == 0
+        greedy_p = (mode == 1 and DEC_PERSISTENT and p_drop == 0 and not torch.is_grad_enabled() and ZC % 8 == 0
+                    and tf_mask is None and not sample)
+        if mode == 1 and (tf_mask is not None or sample):
+            if tf_mask is not None:
+                a.tok_teacher, a.tf_mask = ptr(ys_in), ptr(tf_mask)
+            a.sample = int(bool(sample))
+            a.seed_dev, a.drop_site = ptr(dropout_seed(dev)), (site0 if p_drop > 0 else new_sites())
         if greedy_p:
             emb_all = torch.empty(V, Ep, device=dev, dtype=BF16)
             call("las_gather_rows_bf16", ptr(W["emb_w"]), E, ptr(torch.arange(V, device=dev)), V, ptr(emb_all), Ep)
@@ -780,13 +789,20 @@ class DecoderFn(torch.autograd.Function):
         else:
             call("las_dec_fwd", ctypes.byref(a))
         out_bf = Pk["out_bf"]                                                         # [V, ZC]
+        tok_in = None
+        if mode == 1:
+            # the token each step consumed: <BOS>, then the previous prediction -- or the teacher's token where the
+            # scheduled-sampling mask says so (the backward scatters the embedding gradient to these rows)
+            tok_in = torch.cat([torch.full((B, 1), int(bos), device=dev, dtype=torch.int64), pred], dim=1)     # [B, R]
+            if tf_mask is not None:
+                tok_in = torch.where(tf_mask.to(torch.bool).unsqueeze(0), ys_in, tok_in)
         if mode == 0:
             logits = gemm(zc, ZC, 0, out_bf, ZC, 0, B * R, V, ZC, bias=W["out_b"]).view(B, R, V)
         ctx.geom = (B, Te, H, Hd, O, A, V, E, C, K, L, mode, att_scaling, smooth_scaling)
         ctx.drop = (float(p_drop), site0)
         ctx.saved = dict(enc_bf=enc_bf, Pm=Pm, mlp_enc_bf=mlp_enc_bf, wr_cat=wr_cat, ws=ws, zc=zc, cx=cx, dzf=dzf,
                          gates=gates, csave=csave, conv_w=conv_w, mlp_att=mlp_att, gvec=gvec, emb_in=emb_in,
-                         out_bf=out_bf, ys_in=ys_in, keep=keep, pers=pers, bos=bos, we_bf=Pk["we_bf"], Pk=Pk,
+                         out_bf=out_bf, ys_in=ys_in, keep=keep, pers=pers, bos=bos, we_bf=Pk["we_bf"], Pk=Pk, tok_in=tok_in,
                          logits=logits if mode != 0 else None,
                          emb_op=(emb_op[:B * R * Ep].view(B * R, Ep) if mode != 0 else None))
         ctx.W = W
@@ -934,10 +950,10 @@ class DecoderFn(torch.autograd.Function):
                 lg = S["logits"]                                                          # [B, R, V], row r = step r-1
                 if mode == 2:
                     p_all = torch.softmax(lg * smooth_scaling, dim=-1)
+                    p_all = torch.cat([torch.nn.functional.one_hot(torch.full((B, 1), S["bos"], device=dev), V).float(),
+                                       p_all[:, 1:]], dim=1)                              # row r feeds step r
                 else:
-                    p_all = torch.nn.functional.one_hot(lg.argmax(-1), V).float()
-                p_all = torch.cat([torch.nn.functional.one_hot(torch.full((B, 1), S["bos"], device=dev), V).float(),
-                                   p_all[:, 1:]], dim=1)                                  # row r feeds step r
+                    p_all = torch.nn.functional.one_hot(S["tok_in"], V).float()          # the tokens the steps consumed
                 p_bf = cvt_bf16(p_all.reshape(n, V))
                 de_bf = cvt_bf16(demb_rows)
                 d_emb = gemm(p_bf, p_bf.shape[1], 1, de_bf, de_bf.shape[1], 1, V, Ep, n)[:, :E].contiguous()
@@ -975,7 +991,7 @@ class DecoderFn(torch.autograd.Function):
                 grads["gvec_w"] = None
             glist = sc.deliver([grads[k] for k in DEC_WEIGHTS])
         ctx.saved = None
-        return (denc, None, None, None, None, None, None, None, None, None, *glist)
+        return (denc, None, None, None, None, None, None, None, None, None, None, None, *glist)
 
 
 # --------------------------------------------------------------------------------------------

@@ -206,16 +206,13 @@ class Decoder(torch.nn.Module):
 
     def forward(self, enc_pad, enc_len, ys=None, tf_rate=1.0, max_dec_timesteps=500, sample=False, smooth=False,
                 scaling=1.0, label_smoothing=True):
-        if sample:
-            raise NotImplementedError("Categorical sampling (model.py:350) is not used by any Solver path")
         dev = enc_pad.device
         B = enc_pad.size(0)
         self.attention.reset()
         enc_lens_dev = Fn.lens_tensor(enc_len, dev)
         teacher = ys is not None and len(ys) > 0
+        tf_mask = None
         if teacher:
-            if tf_rate < 1.0:
-                raise NotImplementedError("scheduled sampling (tf_rate < 1) is not implemented; config pins 1.0")
             ys_host = [y.detach().cpu().numpy().astype(np.int64) if torch.is_tensor(y) else np.asarray(y, np.int64)
                        for y in ys]
             L = max(len(y) for y in ys_host) + 1
@@ -229,26 +226,51 @@ class Decoder(torch.nn.Module):
             ys_in_dev = torch.from_numpy(ys_in).to(dev)
             ys_out_dev = torch.from_numpy(ys_out).to(dev)
             mode = 0
+            if tf_rate < 1.0:
+                # scheduled sampling (model.py:327-329): ONE host draw per step for the whole batch, from numpy's global
+                # stream exactly as the reference draws it; step 0 always consumes <BOS>. The step loop then runs on the
+                # free-running per-timestep kernels with the teacher's token substituted where the draw says so.
+                draws = [np.random.random_sample() <= tf_rate for _ in range(L)]
+                tf_mask = torch.tensor([1] + [int(d) for d in draws[1:]] + [1], dtype=torch.uint8, device=dev)
+                mode = 1
         else:
             L = int(max_dec_timesteps)
             ys_in_dev, ys_out_dev = None, None
             mode = 2 if smooth else 1
-        return self.forward_dev(enc_pad, enc_lens_dev, ys_in_dev, ys_out_dev, L, mode, scaling, label_smoothing)
+        return self.forward_dev(enc_pad, enc_lens_dev, ys_in_dev, ys_out_dev, L, mode, scaling, label_smoothing,
+                                tf_mask=tf_mask, sample=sample)
 
     def prep_jobs(self, mode=0):
         return Fn.decoder_prep_jobs(self._weights(), mode)
 
-    def forward_dev(self, enc_pad, enc_lens_dev, ys_in_dev, ys_out_dev, L, mode, scaling=1.0, label_smoothing=True):
+    def forward_dev(self, enc_pad, enc_lens_dev, ys_in_dev, ys_out_dev, L, mode, scaling=1.0, label_smoothing=True,
+                    tf_mask=None, sample=False):
         """Device-resident variant (CUDA-graph capturable). ys_in_dev int64 [B, L+1] = [BOS, y, EOS.., PAD],
-        ys_out_dev int64 [B, L] = [y, EOS..]; mode 0 teacher forcing, 1 greedy, 2 smooth free-run."""
+        ys_out_dev int64 [B, L] = [y, EOS..]; mode 0 teacher forcing, 1 greedy (with `tf_mask`: scheduled sampling
+        between the teacher's tokens and the model's own predictions), 2 smooth free-run. `sample`: predictions are
+        drawn from softmax(logits) instead of the argmax (model.py:349-351)."""
         dev = enc_pad.device
         p = float(self.dropout_rate) if self.training else 0.0
+        in_kernel_sample = bool(sample) and mode == 1            # the only mode that feeds the prediction back
         logits_alloc, ws_alloc, pred = Fn.DecoderFn.apply(
             enc_pad.float().contiguous(), enc_lens_dev, ys_in_dev, L, mode, float(scaling), 2.0,
-            self.attention.conv_kernel_size, self.bos, p, *self._weights())
+            self.attention.conv_kernel_size, self.bos, p, tf_mask, in_kernel_sample, *self._weights())
         ls = self.ls_weight if (label_smoothing and self.ls_weight > 0 and self.training) else 0.0
         dist = self.vlabeldist.to(dev) if ls > 0 else None
-        ys_log_probs, _, prediction = Fn.CELabelSmoothFn.apply(logits_alloc, ys_out_dev, dist, ls, 1, L)
+        targets, sampled = ys_out_dev, None
+        if sample:
+            # Categorical(logits).sample() (model.py:349-351): in-kernel where the prediction is fed back (mode 1), after
+            # the loop where it is an output only; without targets the sampled tokens are what is scored (model.py:361)
+            if mode == 1:
+                sampled = pred
+            else:
+                V = logits_alloc.size(2)
+                sampled = torch.multinomial(torch.softmax(logits_alloc[:, 1:].detach(), dim=-1).reshape(-1, V), 1).view(-1, L)
+            if targets is None:
+                targets = sampled
+        ys_log_probs, _, prediction = Fn.CELabelSmoothFn.apply(logits_alloc, targets, dist, ls, 1, L)
+        if sampled is not None:
+            prediction = sampled
         return logits_alloc[:, 1:], ys_log_probs, prediction, ws_alloc[:, 1:]
 
 

@@ -270,9 +270,9 @@ class Solver(object):
             self.save_judge(self._path(f"-{epoch:03d}"))
 
     def sup_train_one_epoch(self, epoch, tf_rate):
-        if tf_rate < 1.0:
-            raise NotImplementedError("scheduled sampling (tf_rate < 1) is not implemented; config.yaml pins 1.0")
         c, tag = self.config, self.config["tag"]
+        if tf_rate < 1.0:
+            return self._sup_train_one_epoch_scheduled(epoch, tf_rate)
         steps = len(self.train_lab_loader)
         total = 0.0
         # solver.py:370-373: Gaussian input noise from `gaussian_epoch` on -- drawn on the device after the upload
@@ -291,6 +291,30 @@ class Solver(object):
             if self.logger is not None and (i + 1) % max(1, c.get("log_every", 50)) == 0:
                 self.log("scalar_summary", f"{tag}/train_loss", loss.item(), epoch * steps + i + 1)
         return float(total) / max(1, steps)
+
+    def _sup_train_one_epoch_scheduled(self, epoch, tf_rate):
+        """solver.py:360-393 with tf_rate < 1 (scheduled sampling, model.py:327-329): the per-step choice between the
+        teacher's token and the model's own prediction is a host draw, so these steps run eagerly through
+        `E2E.forward(..., tf_rate=...)` (free-running per-timestep kernels) instead of the captured graph."""
+        c, tag = self.config, self.config["tag"]
+        steps = len(self.train_lab_loader)
+        total = 0.0
+        noisy = bool(c["add_gaussian"]) and epoch >= c["gaussian_epoch"]
+        for i, (xs, ilens, ys) in enumerate(self.train_lab_loader):
+            xs, ys = cc(xs), [cc(y) for y in ys]
+            if noisy:
+                xs = xs + torch.randn_like(xs) * float(c["gaussian_std"])
+            self.model.train()
+            _, log_probs, _, _ = self.model(xs, ilens, ys, tf_rate=tf_rate, sample=False)      # solver.py:375
+            loss = -torch.mean(log_probs)
+            self.gen_opt.zero_grad()
+            with Fn.deferred_wgrad():
+                loss.backward()
+            engine._clip_and_step(self.gen_opt, list(self.model.parameters()), c["max_grad_norm"])
+            total += float(loss)
+            if self.logger is not None and (i + 1) % max(1, c.get("log_every", 50)) == 0:
+                self.log("scalar_summary", f"{tag}/train_loss", float(loss), epoch * steps + i + 1)
+        return total / max(1, steps)
 
     def sup_pretrain(self):
         c, tag = self.config, self.config["tag"]

@@ -97,6 +97,72 @@ def case_supervised(ref, name, seed, B, Tmax, D, H, n_layers, subsample, V, E, A
     print(name, "loss", loss.item(), "norm", float(norm), "enc_lens", enc_lens)
 
 
+def case_scheduled(ref, name, seed, B, Tmax, D, H, n_layers, subsample, V, E, A, C, ksz, ls, tf_rate, np_seed):
+    """Scheduled sampling (model.py:327-329, tf_rate < 1): the reference draws np.random.random_sample() once per decoder
+    step and feeds the previous ARGMAX back where the draw exceeds tf_rate. The model is first trained (tf_rate = 1) on
+    its own batch until every step of the scheduled forward is decisive (top-2 margin well above the bf16 tolerance), so
+    that the fed-back tokens -- and with them every later step -- are pinned by the reference."""
+    torch.manual_seed(seed)
+    rng = np.random.RandomState(seed)
+    x, lens, ys = synth_batch(rng, B, Tmax, D, V)
+    cnt = np.zeros(V)
+    for y in ys:
+        for t in y:
+            cnt[t] += 1
+    cnt[2] += len(ys)
+    labeldist = cnt / cnt.sum()
+    m = ref.E2E(input_dim=D, enc_hidden_dim=H, enc_n_layers=n_layers, subsample=subsample, dropout_rate=0.0,
+                dec_hidden_dim=H, att_dim=A, conv_channels=C, conv_kernel_size=ksz, att_odim=H,
+                embedding_dim=E, output_dim=V, ls_weight=ls, labeldist=labeldist)
+    m.train()
+    xs = torch.from_numpy(x)
+    yst = [torch.from_numpy(y) for y in ys]
+    # ... trained towards OTHER label sequences of the same lengths, so that the decisive predictions it feeds back
+    # differ from the teacher's tokens (otherwise the scheduled forward would coincide with teacher forcing)
+    rng2 = np.random.RandomState(seed + 1000)
+    ysa = [torch.from_numpy(rng2.randint(3, V, size=len(y)).astype(np.int64)) for y in ys]
+    pre_opt = torch.optim.Adam(m.parameters(), lr=5e-3)
+    steps = -1
+    for it in range(3000):
+        np.random.seed(np_seed)
+        with torch.no_grad():
+            pl, _, pp, _ = m(xs, lens, yst, tf_rate=tf_rate, sample=False)
+        top2 = pl.topk(2, dim=-1).values
+        if bool(((top2[..., 0] - top2[..., 1]) > 4 * 3e-2 * pl.abs().max()).all()):
+            steps = it
+            break
+        _, lp, _, _ = m(xs, lens, ysa, tf_rate=1.0, sample=False)
+        pre_opt.zero_grad()
+        (-torch.mean(lp)).backward()
+        torch.nn.utils.clip_grad_norm_(m.parameters(), max_norm=5)
+        pre_opt.step()
+    assert steps >= 0, "the scheduled forward never became decisive"
+    m.zero_grad()
+    params0 = sd_numpy(m)
+    np.random.seed(np_seed)
+    L = max(len(y) for y in ys) + 1
+    draws = np.array([np.random.random_sample() <= tf_rate for _ in range(L)])
+    np.random.seed(np_seed)
+    logits, log_probs, prediction, ws = m(xs, lens, yst, tf_rate=tf_rate, sample=False)
+    loss = -torch.mean(log_probs)
+    loss.backward()
+    grads = {k: p.grad.detach().numpy().copy() for k, p in m.named_parameters()}
+    assert not draws[1:].all() and draws[1:].any(), "choose a seed that mixes teacher and model tokens"
+    out = {"x": x, "ilens": np.array(lens), "logits": logits.detach().numpy(), "log_probs": log_probs.detach().numpy(),
+           "prediction": prediction.numpy(), "ws": ws.detach().numpy(), "loss": np.float32(loss.item()),
+           "labeldist": labeldist, "subsample": np.array(subsample), "ls_weight": np.float32(ls),
+           "tf_rate": np.float32(tf_rate), "np_seed": np.int64(np_seed), "draws": draws, "n_ys": np.int64(len(ys)),
+           "pretrain_steps": np.int64(steps)}
+    for i, y in enumerate(ys):
+        out[f"ys_{i}"] = y
+    for k, v in params0.items():
+        out["p0/" + k] = v
+    for k, v in grads.items():
+        out["g/" + k] = v
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "pre-trained", steps, "steps; loss", loss.item(), "draws", draws.astype(int).tolist())
+
+
 def case_lm_and_ssl(ref, name, seed, B, Tmax, D, H, subsample, V, E, A, C, ksz, ls, JE, JH):
     torch.manual_seed(seed)
     rng = np.random.RandomState(seed)
@@ -261,6 +327,10 @@ if __name__ == "__main__":
     if os.environ.get("ONLY_HOST"):
         case_host_plumbing("host_plumbing", seed=31)
         sys.exit(0)
+    if os.environ.get("ONLY_SCHED"):
+        case_scheduled(ref, "sched_small", seed=17, B=3, Tmax=33, D=20, H=16, n_layers=2, subsample=[2, 2], V=10, E=8,
+                       A=16, C=3, ksz=4, ls=0.05, tf_rate=0.5, np_seed=5)
+        sys.exit(0)
     if os.environ.get("ONLY_SSL"):
         case_lm_and_ssl(ref, "ssl_small", seed=21, B=3, Tmax=30, D=16, H=16, subsample=[2, 2], V=11, E=8, A=16,
                         C=3, ksz=4, ls=0.05, JE=8, JH=24)
@@ -275,5 +345,7 @@ if __name__ == "__main__":
     case_supervised(ref, "sup_b1_widekernel", seed=13, B=1, Tmax=19, D=16, H=8, n_layers=2, subsample=[2, 2],
                     V=9, E=8, A=8, C=2, ksz=10, ls=0.05)
     case_host_plumbing("host_plumbing", seed=31)
+    case_scheduled(ref, "sched_small", seed=17, B=3, Tmax=33, D=20, H=16, n_layers=2, subsample=[2, 2], V=10, E=8,
+                   A=16, C=3, ksz=4, ls=0.05, tf_rate=0.5, np_seed=5)
     case_lm_and_ssl(ref, "ssl_small", seed=21, B=3, Tmax=30, D=16, H=16, subsample=[2, 2], V=11, E=8, A=16,
                     C=3, ksz=4, ls=0.05, JE=8, JH=24)

@@ -211,3 +211,54 @@ def test_greedy_early_stop_gives_the_same_hypotheses():
     has_eos = bool((full == 2).any(dim=1).all())
     if has_eos:
         assert Fn.GREEDY_EARLY_STOP["last_steps"] < 64             # it really stopped early
+
+
+def test_scheduled_sampling_matches_reference():
+    """tf_rate < 1 (model.py:327-329): numpy's global stream gives the same per-step draws the reference drew; the steps
+    that fall to the model consume its own argmax. Golden fixture from the reference (decisive margins), so the fed-back
+    tokens, the logits after them, the loss and the gradients are all pinned."""
+    G = load_golden("sched_small")
+    g = G["raw"]
+    m = e2e_from_golden(G).train()
+    x, lens = torch.from_numpy(g["x"]).cuda(), g["ilens"].tolist()
+    ys = [torch.from_numpy(y).cuda() for y in G["ys"]]
+    np.random.seed(int(g["np_seed"]))
+    logits, logp, pred, ws = m(x, lens, ys, tf_rate=float(g["tf_rate"]), sample=False)
+    assert torch.equal(pred.cpu(), torch.from_numpy(g["prediction"]))
+    assert rel_err(logits, g["logits"]) < ACT_TOL
+    assert rel_err(logp, g["log_probs"]) < ACT_TOL
+    assert float((ws.cpu() - torch.from_numpy(g["ws"])).abs().max()) < 5e-3
+    loss = -torch.mean(logp)
+    assert abs(float(loss) - float(g["loss"])) < 1e-3 * abs(float(g["loss"]))
+    m.zero_grad()
+    loss.backward()
+    _check_grads(list(m.named_parameters()), G["g"])
+    # tf_rate = 1 on the same model is a different computation (the fixture mixes in model tokens that differ from the teacher's)
+    tf_logits = m(x, lens, ys, tf_rate=1.0)[0]
+    assert rel_err(tf_logits, g["logits"]) > 10 * ACT_TOL
+
+
+def test_sampled_predictions():
+    """sample=True (model.py:349-351): free-running decoding feeds back a token drawn from softmax(logits); the returned
+    log-probabilities are those of the drawn tokens (model.py:361)."""
+    G = load_golden("sup_small_odd")
+    g = G["raw"]
+    m = e2e_from_golden(G).eval()
+    x, lens = torch.from_numpy(g["x"]).cuda(), g["ilens"].tolist()
+    V = m.decoder.output_layer.bias.numel()
+    with torch.no_grad():
+        outs = [m(x, lens, ys=None, max_dec_timesteps=16, sample=True) for _ in range(3)]
+        greedy = m(x, lens, ys=None, max_dec_timesteps=16, sample=False)
+    for logits, logp, pred, _ in outs:
+        assert int(pred.min()) >= 0 and int(pred.max()) < V and tuple(pred.shape) == (x.size(0), 16)
+        want = torch.gather(torch.log_softmax(logits, dim=-1), 2, pred.unsqueeze(2)).squeeze(2)
+        assert float((logp - want).abs().max()) < 1e-4
+    assert not (torch.equal(outs[0][2], outs[1][2]) and torch.equal(outs[1][2], outs[2][2]))     # fresh draws per call
+    assert not torch.equal(outs[0][2], greedy[2])                     # near-uniform untrained model: not the argmax path
+    # a peaked output layer makes sampling and argmax coincide
+    with torch.no_grad():
+        m.decoder.output_layer.weight.mul_(0.0)
+        m.decoder.output_layer.bias.zero_()
+        m.decoder.output_layer.bias[5] = 30.0
+        _, _, pred, _ = m(x, lens, ys=None, max_dec_timesteps=8, sample=True)
+    assert bool((pred == 5).all())

@@ -148,3 +148,29 @@ def test_masks_and_targets_bit_exact():
     assert yo.tolist() == [[5, 6, 2, 2, 2, 2, 2], [7, 2, 2, 2, 2, 2, 2]]
     w = O.initial_attention([4, 2], 5)
     assert w[0].tolist() == [0.25, 0.25, 0.25, 0.25, 0.0] and w[1].tolist() == [0.5, 0.5, 0, 0, 0]
+
+
+def test_scheduled_sampling_matches_reference():
+    """tf_rate < 1 (model.py:327-329): with the reference's own per-step draws the oracle reproduces its logits, the
+    fed-back predictions, the loss and every gradient (fixture: tests/golden/make_golden.py::case_scheduled)."""
+    G = load_golden("sched_small")
+    g = G["raw"]
+    draws = g["draws"].astype(bool)
+    assert not draws[1:].all() and draws[1:].any()
+    leaves, full = O._with_grad(G["p0"])
+    x, lens, ys = torch.from_numpy(g["x"]), g["ilens"].tolist(), G["ys"]
+    logits, logp, pred, ws = O.e2e_forward(x, lens, full, g["subsample"].tolist(), ys=ys, ls_weight=float(g["ls_weight"]),
+                                           labeldist=g["labeldist"], training=True, tf_draws=draws)
+    assert torch.equal(pred, torch.from_numpy(g["prediction"]))
+    assert torch.allclose(logits, torch.from_numpy(g["logits"]), rtol=1e-4, atol=1e-5)
+    assert torch.allclose(logp, torch.from_numpy(g["log_probs"]), rtol=1e-4, atol=1e-5)
+    loss = -torch.mean(logp)
+    assert abs(float(loss) - float(g["loss"])) < 1e-5
+    loss.backward()
+    for k, gv in G["g"].items():
+        if k in leaves:
+            assert cosine(leaves[k].grad, gv) > 0.99999, k
+    # the teacher-forced forward of the same model differs (the fixture really mixes in model tokens)
+    tf_logits = O.e2e_forward(x, lens, full, g["subsample"].tolist(), ys=ys, ls_weight=float(g["ls_weight"]),
+                              labeldist=g["labeldist"], training=True)[0]
+    assert float((tf_logits - logits).abs().max()) > 1e-3
