@@ -176,6 +176,7 @@ class SupervisedTrainer:
         # exchange it hides. Off by default; LAS_OVERLAP=1 switches it on.
         self.overlap_allreduce = bool(overlap_allreduce) or os.environ.get("LAS_OVERLAP", "0") == "1"
         self.force_split = False          # tests: take the two-part step on one GPU (no collective is issued)
+        self._stage_ev = None             # H2D copies of the last stage() (its pinned staging is shared by all geometries)
         self.comm_stream = None
         self._buckets = None
         self.model = model
@@ -384,9 +385,8 @@ class SupervisedTrainer:
     def _staging_wait(self):
         """The pinned staging of stage() is shared by all geometries: the previous batch's H2D copies must have
         left the host before it is overwritten."""
-        ev = getattr(self, "_stage_ev", None)
-        if ev is not None:
-            ev.synchronize()
+        if self._stage_ev is not None:
+            self._stage_ev.synchronize()
 
     def run(self, key):
         """One train step on the batch currently staged for `key`. Returns (loss, grad_norm) device tensors.
