@@ -114,6 +114,18 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
   }
 }
 
+// timesteps a cluster has to walk: the longest of its (up to) 8 utterances, T without a length vector
+__device__ __forceinline__ int group_steps(const int32_t* lens, int grp, int B, int T, int walk_all) {
+  if (lens == nullptr || walk_all) return T;
+  int m = 0;
+#pragma unroll
+  for (int i = 0; i < kNB; ++i) {
+    const int nn = grp * kNB + i;
+    if (nn < B) m = max(m, min(__ldg(lens + nn), T));
+  }
+  return m;
+}
+
 struct FwdP {
   const float* xproj; int64_t xp_ld_b, xp_ld_t;   // gate-minor columns: [dir*4H + 4*u + gate]
   const uint32_t* whh_pk;      // [ndir][Q][KT][32][4] (las_pack_afrag mode 3: tile = 4 units x 4 gates, quad-permuted K)
@@ -123,6 +135,7 @@ struct FwdP {
   uint4* rec;                  // [ndir][B][T][H] x 16 B: (i,f) f16x2 | (g,o) f16x2 | c f32 | tanh(c) f32
   int B, T, H, rep_row;
   int Q, WPC, KT;
+  int walk_all;                // debugging switch LAS_LSTM_WALK_ALL=1: every cluster walks all T timesteps
   long long* dbg;              // optional clock64() trace of cluster (0,0,0) (las_set_debug_buffer)
 };
 
@@ -148,6 +161,11 @@ __global__ void __launch_bounds__(384, 1) lstm_persist_fwd_kernel(FwdP p) {
   const bool quad_ok = quad < p.Q;
   const uint32_t tx_bytes = static_cast<uint32_t>(p.H) * 16u;
   const int T = p.T, H = p.H;
+  // A cluster only walks the timesteps its own 8 utterances have (Tg = the longest of them): past that every
+  // element is inactive, the state is frozen and only zero rows of y are left to write (tail loop below). Batches
+  // are sorted by length, so when there are more clusters than the device holds (B = 64: 16 against 15) the late
+  // clusters are the short ones and the second wave ends with the first instead of doubling the launch.
+  const int Tg = group_steps(p.lens, blockIdx.y, p.B, T, p.walk_all);
 
   if (threadIdx.x == 0) {
     mbar_init(&full[0], 1);
@@ -157,8 +175,8 @@ __global__ void __launch_bounds__(384, 1) lstm_persist_fwd_kernel(FwdP p) {
   for (int i = threadIdx.x; i < 2 * p.KT * 64; i += blockDim.x) hs[i] = 0u;
   __syncthreads();
   if (threadIdx.x == 0) {
-    if (T > 1) mbar_arrive_expect_tx(&full[1], tx_bytes);   // h_0 -> consumed by step 1
-    if (T > 2) mbar_arrive_expect_tx(&full[0], tx_bytes);   // h_1 -> consumed by step 2
+    if (Tg > 1) mbar_arrive_expect_tx(&full[1], tx_bytes);   // h_0 -> consumed by step 1
+    if (Tg > 2) mbar_arrive_expect_tx(&full[0], tx_bytes);   // h_1 -> consumed by step 2
   }
   cluster.sync();   // every CTA's barriers are armed before any remote store can arrive
 
@@ -192,12 +210,12 @@ __global__ void __launch_bounds__(384, 1) lstm_persist_fwd_kernel(FwdP p) {
     float4* xslot = xring + threadIdx.x;
     const int ring_stride = blockDim.x;
     const int64_t xstep = (dir == 0) ? p.xp_ld_t : -p.xp_ld_t;
-    const float* xsrc = p.xproj + n * p.xp_ld_b + static_cast<int64_t>(dir == 0 ? 0 : T - 1) * p.xp_ld_t +
+    const float* xsrc = p.xproj + n * p.xp_ld_b + static_cast<int64_t>(dir == 0 ? 0 : Tg - 1) * p.xp_ld_t +
                         static_cast<int64_t>(dir) * 4 * H + 4 * u;
     int pf_s = 0;   // next step to prefetch
     auto prefetch_xp = [&]() {
-      if (pf_s < T) {
-        const int t = (dir == 0) ? pf_s : (T - 1 - pf_s);
+      if (pf_s < Tg) {
+        const int t = (dir == 0) ? pf_s : (Tg - 1 - pf_s);
         if (t < len) cp_async<16>(xslot + (pf_s % kPF) * ring_stride, xsrc);
         xsrc += xstep;
       }
@@ -207,7 +225,7 @@ __global__ void __launch_bounds__(384, 1) lstm_persist_fwd_kernel(FwdP p) {
     for (int i = 0; i < kPF; ++i) prefetch_xp();
 
     // running global pointers (start at the first processed timestep)
-    const int t0 = (dir == 0) ? 0 : T - 1;
+    const int t0 = (dir == 0) ? 0 : Tg - 1;
     const int64_t rec_step = (dir == 0) ? H : -H;
     const int64_t y_step = (dir == 0) ? p.y_ld_t : -p.y_ld_t;
     const int64_t hp_step = (dir == 0) ? p.hp_ld_t : -p.hp_ld_t;
@@ -237,8 +255,8 @@ __global__ void __launch_bounds__(384, 1) lstm_persist_fwd_kernel(FwdP p) {
 #else
 #define LAS_TRACE(slot) do { (void)trace; } while (0)
 #endif
-    for (int s = 0; s < T; ++s) {
-      const int t = (dir == 0) ? s : (T - 1 - s);
+    for (int s = 0; s < Tg; ++s) {
+      const int t = (dir == 0) ? s : (Tg - 1 - s);
       LAS_TRACE(0);
       float acc[4][4];
 #pragma unroll
@@ -249,7 +267,7 @@ __global__ void __launch_bounds__(384, 1) lstm_persist_fwd_kernel(FwdP p) {
         const int buf = s & 1;
         mbar_wait_cluster(&full[buf], ((s - 1) >> 1) & 1);
         LAS_TRACE(1);
-        if (threadIdx.x == 0 && s + 2 < T) mbar_arrive_expect_tx(&full[buf], tx_bytes);  // re-arm for step s+2
+        if (threadIdx.x == 0 && s + 2 < Tg) mbar_arrive_expect_tx(&full[buf], tx_bytes);  // re-arm for step s+2
         const uint2* hb = reinterpret_cast<const uint2*>(hs + buf * p.KT * 64) + tig * 8 + (g ^ ((tig >> 1) << 2));
         if (p.KT == kMaxKT || KTS > 0) {     // H = 320 (or wide): no per-k-tile bound check in the instruction stream
 #pragma unroll
@@ -318,7 +336,7 @@ __global__ void __launch_bounds__(384, 1) lstm_persist_fwd_kernel(FwdP p) {
       const uint32_t x0 = __shfl_xor_sync(0xffffffffu, qw.x, 16);
       const uint32_t x1 = __shfl_xor_sync(0xffffffffu, qw.y, 16);
       // critical path first: the new state goes to the peers before anything is written to HBM
-      if (s + 1 < T) {
+      if (s + 1 < Tg) {
         const int nbuf = (s + 1) & 1;
         const uint4 v = gl ? make_uint4(x0, x1, qw.x, qw.y) : make_uint4(qw.x, qw.y, x0, x1);
         if (peer_ok) st_async_v4(hs_remote + nbuf * hs_buf_bytes, v, bar_remote + nbuf * 8u);
@@ -355,6 +373,20 @@ __global__ void __launch_bounds__(384, 1) lstm_persist_fwd_kernel(FwdP p) {
       LAS_TRACE(7);
     }
 #undef LAS_TRACE
+    // rows Tg .. T-1: nobody in this cluster is active there. y is zero (pad_packed_sequence); the entering state is
+    // the frozen last h in the forward direction and the zero initial state in the reverse one (its walk starts at
+    // Tg - 1), exactly what the full-length loop wrote.
+    if (Tg < T && n < p.B && ul < 2) {
+      __nv_bfloat16* yt = p.y + n * p.y_ld_b + static_cast<int64_t>(Tg) * p.y_ld_t + static_cast<int64_t>(dir) * H + 4 * quad;
+      __nv_bfloat16* ht = p.hprev ? p.hprev + n * p.hp_ld_b + static_cast<int64_t>(Tg) * p.hp_ld_t + static_cast<int64_t>(dir) * H + 4 * quad : nullptr;
+      const uint2 hv = (dir == 0) ? quad_prev : make_uint2(0u, 0u);
+      if (ul == 0) {
+        const int rows = T - Tg + (p.rep_row ? 1 : 0);
+        for (int i = 0; i < rows; ++i, yt += p.y_ld_t) *reinterpret_cast<uint2*>(yt) = make_uint2(0u, 0u);
+      } else if (ht) {
+        for (int i = Tg; i < T; ++i, ht += p.hp_ld_t) *reinterpret_cast<uint2*>(ht) = hv;
+      }
+    }
   }
   cluster.sync();   // nobody exits while remote stores may still target its shared memory
 }
@@ -368,6 +400,7 @@ struct BwdP {
   int64_t dg_ld_b, dg_ld_t;
   int B, T, H, rep_row;
   int UGC, JT, MTW, CSn;
+  int walk_all;
   long long* dbg;
 };
 
@@ -390,6 +423,9 @@ __global__ void __launch_bounds__(320, 1) lstm_persist_bwd_kernel(BwdP p) {
   const int T = p.T, H = p.H;
   const int vu = max(0, min(UPC, H - static_cast<int>(rank) * UPC));     // valid units owned by this CTA
   const uint32_t tx_bytes = CS * static_cast<uint32_t>(vu) * 32u;
+  // timesteps this cluster walks (see lstm_persist_fwd_kernel): rows Tg .. T-1 of its utterances only get zero
+  // gate gradients, written by the tail loop after the recurrence
+  const int Tg = group_steps(p.lens, blockIdx.y, p.B, T, p.walk_all);
 
   if (threadIdx.x == 0) {
     mbar_init(&pfull[0], 1);
@@ -399,8 +435,8 @@ __global__ void __launch_bounds__(320, 1) lstm_persist_bwd_kernel(BwdP p) {
   for (int i = threadIdx.x; i < KTC * 64; i += blockDim.x) dgs[i] = 0u;
   __syncthreads();
   if (threadIdx.x == 0) {
-    if (T > 1) mbar_arrive_expect_tx(&pfull[1], tx_bytes);
-    if (T > 2) mbar_arrive_expect_tx(&pfull[0], tx_bytes);
+    if (Tg > 1) mbar_arrive_expect_tx(&pfull[1], tx_bytes);
+    if (Tg > 2) mbar_arrive_expect_tx(&pfull[0], tx_bytes);
   }
   cluster.sync();
 
@@ -439,7 +475,7 @@ __global__ void __launch_bounds__(320, 1) lstm_persist_bwd_kernel(BwdP p) {
   float* pslot = pring + static_cast<int64_t>(threadIdx.x) * 8;
   const int ring_stride = blockDim.x * 8;
   // running source offsets (first processed timestep: t = T-1 for the forward direction, 0 for the reverse)
-  const int tb0 = (dir == 0) ? T - 1 : 0;
+  const int tb0 = (dir == 0) ? Tg - 1 : 0;
   const int64_t sv_step = (dir == 0) ? -H : H;
   const int64_t dy_step = (dir == 0) ? -p.dy_ld_t : p.dy_ld_t;
   int64_t sv_run = ((static_cast<int64_t>(dir) * p.B + nb) * T + tb0) * H + uo;
@@ -448,8 +484,8 @@ __global__ void __launch_bounds__(320, 1) lstm_persist_bwd_kernel(BwdP p) {
   __nv_bfloat16* dg_run = p.dG + nb * p.dg_ld_b + tb0 * p.dg_ld_t + static_cast<int64_t>(dir) * 4 * H + 4 * uo;
   int pf_s = 0;
   auto prefetch = [&]() {
-    const int t = (dir == 0) ? (T - 1 - pf_s) : pf_s;
-    if (pf_s < T && t < len) {
+    const int t = (dir == 0) ? (Tg - 1 - pf_s) : pf_s;
+    if (pf_s < Tg && t < len) {
       float* dst = pslot + (pf_s % PF) * ring_stride;
       cp_async<16>(dst, p.rec + sv_run);
       if (dy_run) {
@@ -488,8 +524,8 @@ __global__ void __launch_bounds__(320, 1) lstm_persist_bwd_kernel(BwdP p) {
 #else
 #define LAS_TRACE(slot) do { (void)trace; } while (0)
 #endif
-  for (int s = 0; s < T; ++s) {
-    const int t = (dir == 0) ? (T - 1 - s) : s;
+  for (int s = 0; s < Tg; ++s) {
+    const int t = (dir == 0) ? (Tg - 1 - s) : s;
     const bool active = t < len;
     LAS_TRACE(0);
     // operands of the gate-derivative math into registers, then the ring slot is refilled right away: the loads
@@ -575,7 +611,7 @@ __global__ void __launch_bounds__(320, 1) lstm_persist_bwd_kernel(BwdP p) {
       LAS_TRACE(2);
       mbar_wait_cluster(&pfull[buf], ((s - 1) >> 1) & 1);
       LAS_TRACE(3);
-      if (threadIdx.x == 0 && s + 2 < T) mbar_arrive_expect_tx(&pfull[buf], tx_bytes);
+      if (threadIdx.x == 0 && s + 2 < Tg) mbar_arrive_expect_tx(&pfull[buf], tx_bytes);
       const float* pp = part + static_cast<int64_t>(buf) * p.CSn * UPC * 8 + threadIdx.x;
       // the CS <= 8 partial sums: all loads first, then a tree (a serial load-add chain was 15 % of this kernel's
       // stall samples, profiles/r02_ncu_full_summary.txt)
@@ -609,7 +645,7 @@ __global__ void __launch_bounds__(320, 1) lstm_persist_bwd_kernel(BwdP p) {
       *reinterpret_cast<uint2*>(dg_run) = pk;
     }
     dg_run += dg_step;
-    if (s + 1 < T && uo < H) {
+    if (s + 1 < Tg && uo < H) {
       // B fragments of the next step's MMA: K index k = gate*UPC + ul within this CTA
       __nv_bfloat16* d16 = reinterpret_cast<__nv_bfloat16*>(dgs);
 #pragma unroll
@@ -625,6 +661,10 @@ __global__ void __launch_bounds__(320, 1) lstm_persist_bwd_kernel(BwdP p) {
     LAS_TRACE(7);
   }
 #undef LAS_TRACE
+  if (own) {
+    __nv_bfloat16* dz = p.dG + nb * p.dg_ld_b + static_cast<int64_t>(Tg) * p.dg_ld_t + static_cast<int64_t>(dir) * 4 * H + 4 * uo;
+    for (int i = Tg; i < T; ++i, dz += p.dg_ld_t) *reinterpret_cast<uint2*>(dz) = make_uint2(0u, 0u);
+  }
   cluster.sync();
 }
 
@@ -726,6 +766,11 @@ static int fwd_max_clusters(const FGeom& f) {
   return n > 0 ? n : 0;
 }
 
+static int walk_all_steps() {
+  static const int v = (getenv("LAS_LSTM_WALK_ALL") != nullptr && atoi(getenv("LAS_LSTM_WALK_ALL")) != 0) ? 1 : 0;
+  return v;
+}
+
 int persist_supported(int H) {
   Geom g;
   FGeom f;
@@ -764,6 +809,7 @@ int persist_lstm_fwd(const float* xproj, const void* whh_pk, const int32_t* lens
   p.rec = static_cast<uint4*>(rec);
   p.B = B; p.T = T; p.H = H; p.rep_row = rep_row;
   p.Q = g.Q; p.WPC = g.WPC; p.KT = g.KT;
+  p.walk_all = walk_all_steps();
   p.dbg = static_cast<long long*>(g_dbg_buf);
   const int threads = 32 * g.WPC;
   const bool wide = g.KT > kMaxKT;
@@ -796,6 +842,7 @@ int persist_lstm_bwd(const float* dy, int64_t dy_ld_b, int64_t dy_ld_t, int rep_
   p.dG = static_cast<__nv_bfloat16*>(dG); p.dg_ld_b = dg_ld_b; p.dg_ld_t = dg_ld_t;
   p.B = B; p.T = T; p.H = H;
   p.UGC = g.UGC; p.JT = g.JT; p.MTW = g.MTW; p.CSn = g.CS;
+  p.walk_all = walk_all_steps();
   p.dbg = static_cast<long long*>(g_dbg_buf);
   const int UPC = 8 * g.UGC;
   if (g.CS > 8 || g.MTW > 2) {

@@ -53,7 +53,10 @@ CASES = [dict(seed=1, B=3, T=9, D=16, H=8), dict(seed=2, B=11, T=22, D=24, H=64)
          dict(seed=4, B=5, T=31, D=32, H=320), dict(seed=5, B=17, T=12, D=16, H=24),
          # "wide" geometry of the persistent kernels (16-CTA clusters, part of the recurrent weights resident in shared
          # memory): the LM judge's hidden size 640 (model.py:466) and a size in between
-         dict(seed=6, B=9, T=24, D=32, H=640), dict(seed=7, B=4, T=11, D=24, H=400)]
+         dict(seed=6, B=9, T=24, D=32, H=640), dict(seed=7, B=4, T=11, D=24, H=400),
+         # three clusters per direction with an odd T: the later (shorter) groups stop at their own longest utterance
+         # and fill the rest of y / hprev / dG (and the replicated row) in the tail loop
+         dict(seed=8, B=19, T=15, D=16, H=32)]
 
 
 @pytest.mark.parametrize("persistent", [False, True])
