@@ -162,6 +162,18 @@ constexpr DGeom make_static_dgeom() {
 }
 constexpr DGeom kSF = make_static_dgeom();
 static_assert(kSF.smem > 0, "static forward geometry must fit");
+// Second compile-time geometry: the same layer sizes with 4 utterances per cluster and up to 256 encoder frames
+// (BASELINE config 5a: T = 2000 input frames behind [1,2,2,2], where an utterance's P / Q slices only fit with four
+// owner CTAs each; also batches of 13..28 at config-2 lengths). The run-time-geometry instance needs ~1.8x the
+// cycles per step on these problems (spills + index arithmetic on the serial path).
+constexpr int kS2_Te = 256, kS2_NB = 4;
+constexpr DGeom make_static_dgeom2() {
+  DGeom g{};
+  g.smem = dec_geom_c(kS_Hd, kS_O, kS_A, kS2_Te, kS_C, kS_K, kS2_NB, g) ? g.smem : -1;
+  return g;
+}
+constexpr DGeom kSF2 = make_static_dgeom2();
+static_assert(kSF2.smem > 0, "second static forward geometry must fit");
 
 // ------------------------------------------------------------------------------------------
 // cluster primitives
@@ -310,7 +322,7 @@ struct DecFwdP {
 // bulk copy per peer [mbarrier bl], and every CTA takes the argmax redundantly (torch.argmax conventions: first
 // maximal index, NaN counts as maximal). WAR: a peer overwrites lg_all at the top of step t+2, i.e. after it has
 // received z_{t+1} from this CTA, which is sent after this CTA's argmax of step t.
-template <bool kS, bool kG>
+template <int kS, bool kG>
 __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __grid_constant__ DecFwdP p_in) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ DecFwdP p;
@@ -323,7 +335,7 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
   }
   __syncthreads();
   const DGeom& g = p.g;
-#define GEO(x) (kS ? kSF.x : g.x)
+#define GEO(x) (kS == 1 ? kSF.x : kS == 2 ? kSF2.x : g.x)
   uint64_t* bz = bars; uint64_t* bc = bars + 2; uint64_t* bdz = bars + 4; uint64_t* be = bars + 5; uint64_t* bl = bars + 6;
   uint32_t* zB = reinterpret_cast<uint32_t*>(smem + GEO(o_zB));       // [2][KTp][32][2]
   float* red = reinterpret_cast<float*>(smem + GEO(o_red));           // [16][32][4] gate partial sums (P1)
@@ -1127,6 +1139,15 @@ constexpr BGeom make_static_bgeom() {
 }
 constexpr BGeom kSB = make_static_bgeom();
 static_assert(kSB.smem > 0, "static backward geometry must fit");
+constexpr BGeom make_static_bgeom2() {
+  BGeom g{};
+  if (dec_bgeom_c(kS_Hd, kS_O, kS_A, kS2_Te, kS_C, kS_K, kS2_NB, g)) return g;
+  g = BGeom{};
+  g.smem = dec_bgeom_c(kS_Hd, kS_O, kS_A, kS2_Te, kS_C, kS_K, kS2_NB, g, 16) ? g.smem : -1;
+  return g;
+}
+constexpr BGeom kSB2 = make_static_bgeom2();
+static_assert(kSB2.smem > 0, "second static backward geometry must fit");
 
 struct DecBwdP {
   int B, L, Te, Hd, O, A, C, K;
@@ -1148,7 +1169,7 @@ struct DecBwdP {
   long long* dbg;
 };
 
-template <bool kS>
+template <int kS>
 __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_constant__ DecBwdP p_in) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ DecBwdP p;
@@ -1161,7 +1182,7 @@ __global__ void __launch_bounds__(kBT, 1) dec_persist_bwd_kernel(const __grid_co
   }
   __syncthreads();
   const BGeom& g = p.g;
-#define GEO(x) (kS ? kSB.x : g.x)
+#define GEO(x) (kS == 1 ? kSB.x : kS == 2 ? kSB2.x : g.x)
   uint64_t* b_dg = bars; uint64_t* b_dc = bars + 1; uint64_t* b_ddz = bars + 2; uint64_t* b_dwn = bars + 3;
   uint32_t* dgB = reinterpret_cast<uint32_t*>(smem + GEO(o_dgB));     // [KSb*FB][32][2] all-gathered dgates_{t+1}
   float* red = reinterpret_cast<float*>(smem + GEO(o_red));           // [12][32][4] phase A partial sums
@@ -1833,9 +1854,13 @@ int g_dec_persist_clusters = 0;   // co-resident 16-CTA clusters the device offe
 }  // namespace
 
 // Is this problem served by the kernels instantiated on the compile-time geometry (kSF / kSB)?
-static bool use_static_geom(const las_dec_args* a, int nb) {
-  return nb == kS_NB && a->Hd == kS_Hd && a->O == kS_O && a->A == kS_A && a->K == kS_K && a->C > 8 && a->C <= 16 &&
-         a->Te <= kS_Te && getenv("LAS_DEC_NO_STATIC") == nullptr;
+static int use_static_geom(const las_dec_args* a, int nb) {
+  if (!(a->Hd == kS_Hd && a->O == kS_O && a->A == kS_A && a->K == kS_K && a->C > 8 && a->C <= 16) ||
+      getenv("LAS_DEC_NO_STATIC") != nullptr)
+    return 0;
+  if (nb == kS_NB && a->Te <= kS_Te) return 1;
+  if (nb == kS2_NB && a->Te <= kS2_Te && getenv("LAS_DEC_NO_STATIC2") == nullptr) return 2;
+  return 0;
 }
 
 // Utterances per cluster for a batch of B: the smallest power of two for which all clusters are
@@ -1886,8 +1911,8 @@ int dec_persist_supported(const las_dec_args* a) {
     // does the device schedule a 16-CTA (non-portable) cluster of this kernel at all?
     g_dec_persist_checked = true;
     g_dec_persist_clusters = 0;
-    if (cudaFuncSetAttribute(dec_persist_fwd_kernel<false, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
-        cudaFuncSetAttribute(dec_persist_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax) == cudaSuccess) {
+    if (cudaFuncSetAttribute(dec_persist_fwd_kernel<0, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+        cudaFuncSetAttribute(dec_persist_fwd_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax) == cudaSuccess) {
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(kCS, 1, 1);
       cfg.blockDim = dim3(kThreads);
@@ -1900,7 +1925,7 @@ int dec_persist_supported(const las_dec_args* a) {
       cfg.attrs = at;
       cfg.numAttrs = 1;
       int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, dec_persist_fwd_kernel<false, false>, &cfg) == cudaSuccess) g_dec_persist_clusters = n;
+      if (cudaOccupancyMaxActiveClusters(&n, dec_persist_fwd_kernel<0, false>, &cfg) == cudaSuccess) g_dec_persist_clusters = n;
     }
     (void)cudaGetLastError();
   }
@@ -1930,14 +1955,17 @@ int dec_persist_bwd(const las_dec_args* a, cudaStream_t stream) {
               "persistent decoder backward: missing buffers");
   static bool attr_set = false;
   if (!attr_set) {
-    LAS_CUDA(cudaFuncSetAttribute(dec_persist_bwd_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    LAS_CUDA(cudaFuncSetAttribute(dec_persist_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
-    LAS_CUDA(cudaFuncSetAttribute(dec_persist_bwd_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    LAS_CUDA(cudaFuncSetAttribute(dec_persist_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+    LAS_CUDA(cudaFuncSetAttribute(dec_persist_bwd_kernel<0>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    LAS_CUDA(cudaFuncSetAttribute(dec_persist_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+    LAS_CUDA(cudaFuncSetAttribute(dec_persist_bwd_kernel<1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    LAS_CUDA(cudaFuncSetAttribute(dec_persist_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+    LAS_CUDA(cudaFuncSetAttribute(dec_persist_bwd_kernel<2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    LAS_CUDA(cudaFuncSetAttribute(dec_persist_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     attr_set = true;
   }
-  const bool stat = use_static_geom(a, nb);
-  if (stat) bg = kSB;
+  const int stat = use_static_geom(a, nb);
+  if (stat == 1) bg = kSB;
+  else if (stat == 2) bg = kSB2;
   DecBwdP p;
   p.B = a->B; p.L = a->L; p.Te = a->Te; p.Hd = a->Hd; p.O = a->O; p.A = a->A; p.C = a->C; p.K = a->K;
   p.att_scaling = a->att_scaling;
@@ -1954,8 +1982,9 @@ int dec_persist_bwd(const las_dec_args* a, cudaStream_t stream) {
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute at[1];
   cluster_cfg(cfg, at, (a->B + nb - 1) / nb, kBT, bg.smem, stream);
-  if (stat) LAS_CUDA(cudaLaunchKernelEx(&cfg, dec_persist_bwd_kernel<true>, p));
-  else LAS_CUDA(cudaLaunchKernelEx(&cfg, dec_persist_bwd_kernel<false>, p));
+  if (stat == 1) LAS_CUDA(cudaLaunchKernelEx(&cfg, dec_persist_bwd_kernel<1>, p));
+  else if (stat == 2) LAS_CUDA(cudaLaunchKernelEx(&cfg, dec_persist_bwd_kernel<2>, p));
+  else LAS_CUDA(cudaLaunchKernelEx(&cfg, dec_persist_bwd_kernel<0>, p));
   ++(stat ? g_dec_static_launches : g_dec_generic_launches);
   ++g_launches;
   return 0;
@@ -1991,17 +2020,20 @@ int dec_persist_fwd(const las_dec_args* a, cudaStream_t stream) {
   LAS_REQUIRE(nb > 0, "persistent decoder: unsupported geometry");
   static bool attr_set = false;
   if (!attr_set) {
-    LAS_CUDA(cudaFuncSetAttribute(dec_persist_fwd_kernel<false, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    LAS_CUDA(cudaFuncSetAttribute(dec_persist_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
-    LAS_CUDA(cudaFuncSetAttribute(dec_persist_fwd_kernel<true, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    LAS_CUDA(cudaFuncSetAttribute(dec_persist_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
-    LAS_CUDA(cudaFuncSetAttribute(dec_persist_fwd_kernel<false, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    LAS_CUDA(cudaFuncSetAttribute(dec_persist_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+    LAS_CUDA(cudaFuncSetAttribute(dec_persist_fwd_kernel<0, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    LAS_CUDA(cudaFuncSetAttribute(dec_persist_fwd_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+    LAS_CUDA(cudaFuncSetAttribute(dec_persist_fwd_kernel<1, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    LAS_CUDA(cudaFuncSetAttribute(dec_persist_fwd_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+    LAS_CUDA(cudaFuncSetAttribute(dec_persist_fwd_kernel<2, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    LAS_CUDA(cudaFuncSetAttribute(dec_persist_fwd_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+    LAS_CUDA(cudaFuncSetAttribute(dec_persist_fwd_kernel<0, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    LAS_CUDA(cudaFuncSetAttribute(dec_persist_fwd_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     attr_set = true;
   }
   const bool greedy = a->mode == 1;
-  const bool stat = !greedy && use_static_geom(a, nb);
-  if (stat) g = kSF;
+  const int stat = greedy ? 0 : use_static_geom(a, nb);
+  if (stat == 1) g = kSF;
+  else if (stat == 2) g = kSF2;
   DecFwdP p;
   p.B = a->B; p.L = a->L; p.Te = a->Te; p.Hd = a->Hd; p.O = a->O; p.A = a->A; p.C = a->C; p.K = a->K;
   p.att_scaling = a->att_scaling;
@@ -2030,9 +2062,10 @@ int dec_persist_fwd(const las_dec_args* a, cudaStream_t stream) {
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  if (greedy) LAS_CUDA(cudaLaunchKernelEx(&cfg, dec_persist_fwd_kernel<false, true>, p));
-  else if (stat) LAS_CUDA(cudaLaunchKernelEx(&cfg, dec_persist_fwd_kernel<true, false>, p));
-  else LAS_CUDA(cudaLaunchKernelEx(&cfg, dec_persist_fwd_kernel<false, false>, p));
+  if (greedy) LAS_CUDA(cudaLaunchKernelEx(&cfg, dec_persist_fwd_kernel<0, true>, p));
+  else if (stat == 1) LAS_CUDA(cudaLaunchKernelEx(&cfg, dec_persist_fwd_kernel<1, false>, p));
+  else if (stat == 2) LAS_CUDA(cudaLaunchKernelEx(&cfg, dec_persist_fwd_kernel<2, false>, p));
+  else LAS_CUDA(cudaLaunchKernelEx(&cfg, dec_persist_fwd_kernel<0, false>, p));
   ++(stat ? g_dec_static_launches : g_dec_generic_launches);
   ++g_launches;
   return 0;
