@@ -13,7 +13,12 @@
 
 namespace las {
 
-constexpr int kTT = 32;  // encoder frames per CTA in the attention energy kernels
+#ifndef LAS_KTT
+#define LAS_KTT 8
+#endif
+// encoder frames per CTA in the per-timestep attention kernels. 8 (was 32): at B = 32, Te = 125 a launch is 512 CTAs of
+// 8 frames, four or more resident per SM, instead of 128 CTAs that each walk 32 frames with 10 warps per SM
+constexpr int kTT = LAS_KTT;
 
 __device__ __forceinline__ float block_reduce_sum(float v, float* red, int nwarps) {
   v = warp_sum(v);

@@ -590,6 +590,8 @@ class SSLTrainer:
         self.arena = None
         self.cache = _GraphCache(max_graphs)
         self.cap_stream = None
+        self.pair_stream = None
+        self.overlap_passes = os.environ.get("LAS_SSL_OVERLAP", "1") != "0"
         self.world = 1
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world = torch.distributed.get_world_size()
@@ -628,11 +630,30 @@ class SSLTrainer:
 
     # ---- device-resident body (no host work; CUDA-graph capturable)
     def _body_dev(self, st, L, Lu):
+        """The paired pass runs on a stream of its own (`overlap_passes`, default on; LAS_SSL_OVERLAP=0 turns it off):
+        its forward is forked at the beginning of the step, and autograd runs every backward node on the stream of its
+        forward, so the paired pass's cluster-persistent kernels (64-80 SMs, latency-bound) execute next to the
+        unpaired pass's free-running decoder (~2 500 small per-timestep kernels) instead of in front of it. The two
+        passes share nothing but the weights (read-only until the optimiser) and the gradient buffers, which are only
+        written on the single weight-gradient stream (functional.wgrad_scope) or by autograd's own accumulation."""
         m = self.model
         enc, dec = m.encoder.enc2, m.decoder
+        dev = st.x.device
         jobs = enc.prep_jobs() + dec.prep_jobs(2 if self.smooth else 1) + dec.prep_jobs(0)
         jobs.sort(key=lambda j: "bwd" in j[0])
         Fn.prepare_ahead(jobs)
+        main = torch.cuda.current_stream(dev)
+        ps = self._pair_stream(dev) if self.overlap_passes else None
+
+        def paired():
+            enc_h = enc.forward_dev(st.x, st.lens)
+            _, logp, _, _ = dec.forward_dev(enc_h, enc.out_lens_dev(st.lens), st.ys_in, st.ys_out, L, 0)
+            return -torch.mean(logp)
+
+        if ps is not None:
+            ps.wait_stream(main)
+            with torch.cuda.stream(ps):
+                sup = paired()
         u_enc = enc.forward_dev(st.ux, st.ulens)
         _, u_logp, u_pred, _ = dec.forward_dev(u_enc, enc.out_lens_dev(st.ulens), None, None, Lu, 2 if self.smooth else 1,
                                                self.scaling, False)
@@ -643,17 +664,27 @@ class SSLTrainer:
         if self.guard_empty_mask:
             denom = denom.clamp_min(1.0)
         unsup = -torch.sum(lm_probs * u_logp * mask) / denom
-        enc_h = enc.forward_dev(st.x, st.lens)
-        _, logp, _, _ = dec.forward_dev(enc_h, enc.out_lens_dev(st.lens), st.ys_in, st.ys_out, L, 0)
-        sup = -torch.mean(logp)
+        if ps is not None:
+            main.wait_stream(ps)
+        else:
+            sup = paired()
         loss = sup + self.unsup_weight * unsup
         self.opt.zero_grad()
         with Fn.deferred_wgrad():
             loss.backward()
+        if ps is not None:
+            main.wait_stream(ps)
         if self.world > 1:
             return loss.detach(), sup.detach(), unsup.detach(), None
         norm = self.opt.clip_and_step(self.max_grad_norm, grad_scale=1.0)
         return loss.detach(), sup.detach(), unsup.detach(), norm
+
+    def _pair_stream(self, dev):
+        if self.pair_stream is None:
+            self.pair_stream = torch.cuda.Stream(device=dev)
+            with torch.cuda.stream(self.pair_stream):
+                Fn._gemm_workspace(dev)           # allocated outside any capture
+        return self.pair_stream
 
     def stage(self, lab, unlab):
         """Host -> device copies of one (paired, unpaired) batch pair into the static buffers (arena views)."""
