@@ -229,6 +229,8 @@ struct NextEmbParams {
   __nv_bfloat16* emb_out; int64_t eo_ld;
   // scheduled sampling (model.py:327-329: teacher token with probability tf_rate, else the previous prediction) and
   // Categorical sampling of the prediction (model.py:349-351); both only in the non-smooth branch
+  // cell-input dropout of [z_t; c_t] -> zcd row (DropRowParams semantics; zc == nullptr: not done here)
+  const __nv_bfloat16* zc; __nv_bfloat16* zcd; int Hd, O; uint32_t zc_site;
   const int64_t* teacher;               // [B, R] teacher tokens (ys_in) or nullptr
   const uint8_t* tf_mask;               // [R]: 1 = step `row` consumes the teacher token
   int sample; uint32_t sample_site;
@@ -242,6 +244,19 @@ __global__ void __launch_bounds__(128) next_emb_kernel(NextEmbParams p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.x;
   const float* x = p.logits + b * p.lg_ld;
+  if (p.zc != nullptr) {       // the other half of the next cell input (was a launch of its own: dec_drop_fwd_kernel)
+    const int ZC = p.Hd + p.O;
+    const unsigned long long sd = *p.seed_dev;
+    const int64_t row_off = (static_cast<int64_t>(b) * p.R + p.row) * ZC;
+    for (int j = threadIdx.x; j < ZC; j += 128) {
+      __nv_bfloat16 v = p.zc[row_off + j];
+      if (j >= p.Hd) {
+        const bool keep = dropout_keep(sd, p.zc_site, (static_cast<unsigned long long>(b) * p.R + p.row) * p.O + (j - p.Hd), p.drop_p);
+        v = keep ? __float2bfloat16(__bfloat162float(v) / (1.f - p.drop_p)) : __float2bfloat16(0.f);
+      }
+      p.zcd[row_off + j] = v;
+    }
+  }
   if (warp == 0) {
     float mx;
     int amax = warp_argmax(x, p.V, lane, &mx);
@@ -1241,7 +1256,7 @@ static int dec_fwd_steps(const las_dec_args* a, cudaStream_t stream, int t_begin
     // (5) c_t = mlp_o(context)   (model.py:172) -> second half of zc row t+1
     smallmm(static_cast<const uint32_t*>(a->mlp_o_pk), O, a->H, ctx + static_cast<int64_t>(t + 1) * a->H, 0, R * a->H, B,
             a->mlp_o_b, nullptr, 0, nullptr, 0, zc + static_cast<int64_t>(t + 1) * ZC + Hd, R * ZC, stream);
-    if (drop) {
+    if (drop && !free_run) {    // (free-running modes: done inside next_emb_kernel below)
       DropRowParams dp = {};
       dp.B = B; dp.Hd = Hd; dp.O = O; dp.R = R; dp.row = t + 1; dp.p = a->drop_p;
       dp.seed_dev = static_cast<const unsigned long long*>(a->seed_dev); dp.site = a->drop_site;
@@ -1263,6 +1278,7 @@ static int dec_fwd_steps(const las_dec_args* a, cudaStream_t stream, int t_begin
       np.sample = a->mode == 1 ? a->sample : 0; np.sample_site = a->drop_site + 7;
       np.sample_seed = static_cast<const unsigned long long*>(a->seed_dev);
       np.emb_out = emb_op + static_cast<int64_t>(t + 1) * Ep; np.eo_ld = R * Ep;
+      if (drop) { np.zc = zc; np.zcd = zcd; np.Hd = Hd; np.O = O; np.zc_site = a->drop_site; }
       next_emb_kernel<<<B, 128, V * sizeof(float), stream>>>(np); ++g_launches;
     }
   }
@@ -1326,13 +1342,20 @@ int las_dec_bwd(const las_dec_args* a, void* stream_) {
   const int V = a->V, E = a->E, Ep = (E + 15) / 16 * 16;
   const int64_t Vq = (V + 3) / 4 * 4;
   for (int t = L - 1; t >= 0; --t) {
+    // In smooth mode with dropout both products of dgates_{t+1} -- W_ih[:, :E]^T (the input-embedding gradient) and
+    // Wr^T (the state gradient) -- go out as ONE launch.
+    const bool paired_mm = smooth && drop && t + 1 < L;
+    if (paired_mm)
+      smallmm_pair(static_cast<const uint32_t*>(a->weT_pk), Ep, a->demb_buf, Ep, static_cast<const uint32_t*>(a->wrT_pk), ZC,
+                   a->dcz_tot, ZC, 4 * Hd, dgates + static_cast<int64_t>(t + 1) * 4 * Hd, R * 4 * Hd, B, stream);
     if (smooth) {
       // (0) free-running smooth mode: the gradient of logit_t also arrives through emb_{t+1}; only then
       //     is the output layer's contribution to d[z_t; c_t] known
       float* dlt = a->dl_tot + static_cast<int64_t>(t + 1) * Vq;   // rows padded to Vq floats: 8-byte aligned operand loads
       if (t + 1 < L) {
-        smallmm(static_cast<const uint32_t*>(a->weT_pk), Ep, 4 * Hd, dgates + static_cast<int64_t>(t + 1) * 4 * Hd, 0,
-                R * 4 * Hd, B, nullptr, nullptr, 0, a->demb_buf, Ep, nullptr, 0, stream);
+        if (!paired_mm)
+          smallmm(static_cast<const uint32_t*>(a->weT_pk), Ep, 4 * Hd, dgates + static_cast<int64_t>(t + 1) * 4 * Hd, 0,
+                  R * 4 * Hd, B, nullptr, nullptr, 0, a->demb_buf, Ep, nullptr, 0, stream);
         SmoothBwdParams sp = {};
         sp.drop_p = a->drop_p; sp.seed_dev = static_cast<const unsigned long long*>(a->seed_dev);
         sp.site = a->drop_site + 1; sp.R = R; sp.row = t + 1;
@@ -1356,8 +1379,9 @@ int las_dec_bwd(const las_dec_args* a, void* stream_) {
               dcz_all + static_cast<int64_t>(t + 1) * ZC, R * ZC, stream);
     } else {
       // the path through the cell input of step t+1 carries that step's dropout mask on its c part
-      smallmm(static_cast<const uint32_t*>(a->wrT_pk), ZC, 4 * Hd, dgates + static_cast<int64_t>(t + 1) * 4 * Hd, 0, R * 4 * Hd, B,
-              nullptr, nullptr, 0, a->dcz_tot, ZC, nullptr, 0, stream);
+      if (!paired_mm)
+        smallmm(static_cast<const uint32_t*>(a->wrT_pk), ZC, 4 * Hd, dgates + static_cast<int64_t>(t + 1) * 4 * Hd, 0, R * 4 * Hd, B,
+                nullptr, nullptr, 0, a->dcz_tot, ZC, nullptr, 0, stream);
       DropRowParams dp = {};
       dp.B = B; dp.Hd = Hd; dp.O = O; dp.R = R; dp.row = t + 1; dp.p = a->drop_p;
       dp.seed_dev = static_cast<const unsigned long long*>(a->seed_dev); dp.site = a->drop_site;

@@ -118,6 +118,9 @@ int pack_afrag(const float* W, int64_t ld, int rows, int cols, int col_offset, i
 int smallmm(const uint32_t* a_pk, int M, int K, const void* v, int v_f32, int64_t ldv, int N,
             const float* bias, const float* add, int64_t ld_add, float* out_f32, int64_t ld_out,
             __nv_bfloat16* out_bf16, int64_t ld_outb, cudaStream_t stream);
+// two products of the same bf16 operand rows in one launch: out0 = A0 v, out1 = A1 v (f32 outputs)
+int smallmm_pair(const uint32_t* a0_pk, int M0, float* out0, int64_t ld_out0, const uint32_t* a1_pk, int M1, float* out1,
+                 int64_t ld_out1, int K, const void* v, int64_t ldv, int N, cudaStream_t stream);
 #endif
 
 }  // namespace las

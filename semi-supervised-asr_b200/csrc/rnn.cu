@@ -347,12 +347,10 @@ int launch_cell_bwd(CellBwdParams& p, cudaStream_t stream) {
 // ------------------------------------------------------------------------------------------
 // small batched mat-vec: out[n, m] = sum_k A[m, k] * v[n, k] (+ bias[m]) (+ add[n, m])
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(512) smallmm_kernel(SmallMMParams p) {
-  __shared__ float red[(kMaxWarps - 1) * 32 * 4];
+__device__ __forceinline__ void smallmm_body(const SmallMMParams& p, int mt, float* red) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, tig = lane & 3;
   const int nt = warp % p.NT, ks = warp / p.NT;
-  const int mt = blockIdx.x;
   const int n0 = (blockIdx.y * p.NT + nt) * 8;
   float acc[1][4] = {{0.f, 0.f, 0.f, 0.f}};
   if (n0 < p.N) {
@@ -377,18 +375,49 @@ __global__ void __launch_bounds__(512) smallmm_kernel(SmallMMParams p) {
   }
 }
 
-int smallmm(const uint32_t* a_pk, int M, int K, const void* v, int v_f32, int64_t ldv, int N,
-            const float* bias, const float* add, int64_t ld_add, float* out_f32, int64_t ld_out,
-            __nv_bfloat16* out_bf16, int64_t ld_outb, cudaStream_t stream) {
-  if (M == 0 || N == 0) return 0;
+__global__ void __launch_bounds__(512) smallmm_kernel(SmallMMParams p) {
+  __shared__ float red[(kMaxWarps - 1) * 32 * 4];
+  smallmm_body(p, blockIdx.x, red);
+}
+
+// Two problems with the same N and K (hence the same warp shape) in one launch: CTAs [0, p0.MT) serve the first,
+// the rest the second. The per-timestep decoder backward multiplies dgates_{t+1} by two weight matrices.
+__global__ void __launch_bounds__(512) smallmm_pair_kernel(SmallMMParams p0, SmallMMParams p1) {
+  __shared__ float red[(kMaxWarps - 1) * 32 * 4];
+  if (static_cast<int>(blockIdx.x) < p0.MT) smallmm_body(p0, blockIdx.x, red);
+  else smallmm_body(p1, blockIdx.x - p0.MT, red);
+}
+
+static SmallMMParams smallmm_params(const uint32_t* a_pk, int M, int K, const void* v, int v_f32, int64_t ldv, int N,
+                                    const float* bias, const float* add, int64_t ld_add, float* out_f32, int64_t ld_out,
+                                    __nv_bfloat16* out_bf16, int64_t ld_outb) {
   SmallMMParams p;
   p.a_pk = a_pk; p.v = v; p.v_f32 = v_f32; p.ldv = ldv; p.bias = bias; p.add = add; p.ld_add = ld_add;
   p.out_f32 = out_f32; p.ld_out = ld_out; p.out_bf16 = out_bf16; p.ld_outb = ld_outb;
   p.M = M; p.N = N; p.MT = (M + 15) / 16; p.KT = (K + 15) / 16;
   const WarpShape w = warp_shape(N, p.KT);
   p.NT = w.NT; p.KS = w.KS;
-  dim3 grid(p.MT, (N + 8 * w.NT - 1) / (8 * w.NT));
-  smallmm_kernel<<<grid, 32 * w.NT * w.KS, 0, stream>>>(p); ++g_launches;
+  return p;
+}
+
+int smallmm(const uint32_t* a_pk, int M, int K, const void* v, int v_f32, int64_t ldv, int N,
+            const float* bias, const float* add, int64_t ld_add, float* out_f32, int64_t ld_out,
+            __nv_bfloat16* out_bf16, int64_t ld_outb, cudaStream_t stream) {
+  if (M == 0 || N == 0) return 0;
+  const SmallMMParams p = smallmm_params(a_pk, M, K, v, v_f32, ldv, N, bias, add, ld_add, out_f32, ld_out, out_bf16, ld_outb);
+  dim3 grid(p.MT, (N + 8 * p.NT - 1) / (8 * p.NT));
+  smallmm_kernel<<<grid, 32 * p.NT * p.KS, 0, stream>>>(p); ++g_launches;
+  return 0;
+}
+
+// out0 = A0 v, out1 = A1 v (+ nothing else): both f32, the same operand rows v [N, ldv] (bf16) and the same K
+int smallmm_pair(const uint32_t* a0_pk, int M0, float* out0, int64_t ld_out0, const uint32_t* a1_pk, int M1, float* out1,
+                 int64_t ld_out1, int K, const void* v, int64_t ldv, int N, cudaStream_t stream) {
+  if (N == 0) return 0;
+  const SmallMMParams p0 = smallmm_params(a0_pk, M0, K, v, 0, ldv, N, nullptr, nullptr, 0, out0, ld_out0, nullptr, 0);
+  const SmallMMParams p1 = smallmm_params(a1_pk, M1, K, v, 0, ldv, N, nullptr, nullptr, 0, out1, ld_out1, nullptr, 0);
+  dim3 grid(p0.MT + p1.MT, (N + 8 * p0.NT - 1) / (8 * p0.NT));
+  smallmm_pair_kernel<<<grid, 32 * p0.NT * p0.KS, 0, stream>>>(p0, p1); ++g_launches;
   return 0;
 }
 

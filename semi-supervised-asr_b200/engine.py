@@ -650,11 +650,13 @@ class SSLTrainer:
             _, logp, _, _ = dec.forward_dev(enc_h, enc.out_lens_dev(st.lens), st.ys_in, st.ys_out, L, 0)
             return -torch.mean(logp)
 
+        u_enc = enc.forward_dev(st.ux, st.ulens)
         if ps is not None:
+            # forked AFTER the unpaired encoder: two BLSTM launches side by side need 160 of 148 SMs and each took
+            # twice as long (3.7 ms for the unpaired encoder instead of 1.9); the unpaired chain is the critical path
             ps.wait_stream(main)
             with torch.cuda.stream(ps):
                 sup = paired()
-        u_enc = enc.forward_dev(st.ux, st.ulens)
         _, u_logp, u_pred, _ = dec.forward_dev(u_enc, enc.out_lens_dev(st.ulens), None, None, Lu, 2 if self.smooth else 1,
                                                self.scaling, False)
         with torch.no_grad():

@@ -32,8 +32,18 @@ ev = [e for e in json.load(open(f))["traceEvents"] if e.get("cat") == "kernel"]
 t0 = min(e["ts"] for e in ev); t1 = max(e["ts"] + e["dur"] for e in ev)
 agg = collections.defaultdict(lambda: [0, 0.0])
 for e in ev:
-    n = e["name"].split("(")[0][-70:]
+    n = e["name"].replace("(anonymous namespace)::", "").split("(")[0][-70:]
     agg[n][0] += 1; agg[n][1] += e["dur"]
 print(f"span {(t1 - t0) / 1e3:.2f} ms, {len(ev)} kernels, sum of kernel times {sum(v for _, v in agg.values()) / 1e3:.2f} ms")
 for n, (c, v) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:22]:
     print(f"{n:72s} {c:6d} {v / 1e3:9.3f} ms  {v / c:8.1f} us")
+
+streams = collections.defaultdict(list)
+for e in ev:
+    streams[e["args"]["stream"]].append(e)
+for sid, L in sorted(streams.items(), key=lambda kv: -len(kv[1])):
+    big = sorted(L, key=lambda e: -e["dur"])[:6]
+    print(f"stream {sid}: {len(L)} kernels, busy {sum(e['dur'] for e in L) / 1e3:.2f} ms, active {(min(e['ts'] for e in L) - t0) / 1e3:.2f} .. "
+          f"{(max(e['ts'] + e['dur'] for e in L) - t0) / 1e3:.2f} ms")
+    for e in sorted(big, key=lambda e: e["ts"]):
+        print(f"      {(e['ts'] - t0) / 1e3:8.3f} ms  {e['dur']:8.1f} us  {e['name'].replace('(anonymous namespace)::', '')[:80]}")
