@@ -301,6 +301,11 @@ int las_att_dconv(const float* dattc_all, const float* ws_alloc, int L, int B, i
                   float* scratch, void* stream);
 /* floats of scratch (las_dec_args.att_part, las_att_dconv, las_att_param_grads part_ws) for these sizes */
 int64_t las_att_scratch_floats(int B, int L, int Te, int A, int C, int K);
+/* 1 when the per-timestep decoder backward (las_dec_bwd without the cluster-persistent kernel) can run its lean
+ * tensor-core energy backward for these sizes: the caller then passes las_dec_args.conv_save to las_dec_fwd (filled
+ * by the per-timestep forward as well) and las_dec_args.de_all to las_dec_bwd, and obtains dP / dmlp_att / dgvec from
+ * las_att_param_grads(_part) afterwards, exactly as after the persistent backward (model.py:156-165 backward) */
+int las_att_bwd_lean_supported(int A, int C);
 int las_att_param_grads(const float* P, const float* dzf, const float* conv_save, const float* de_all,
                         const float* mlp_att, const float* gvec, int B, int L, int Te, int A, int C, float* dP,
                         float* part_ws /* scratch: las_att_scratch_floats() */, float* dmlp_att,

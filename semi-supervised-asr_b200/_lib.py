@@ -81,6 +81,7 @@ SIGNATURES = {
     "las_att_dq": (c_int, [P, P, I, I, I, I, P, P]),
     "las_att_dconv": (c_int, [P, P, I, I, I, I, I, P, P, P]),
     "las_att_scratch_floats": (c_int64, [I, I, I, I, I, I]),
+    "las_att_bwd_lean_supported": (c_int, [I, I]),
     "las_att_param_grads": (c_int, [P, P, P, P, P, P, I, I, I, I, I, P, P, P, P, P]),
     "las_att_param_grads_part": (c_int, [P, P, P, P, P, P, I, I, I, I, I, I, P, P, P, P, P]),
     "las_dec_fwd": (c_int, [ctypes.POINTER(DecArgs), P]),

@@ -110,6 +110,8 @@ struct EnergyFwdParams {
   const float* mlp_att;  // [A, C]
   const float* gvec;     // [A]
   float* e;              // [B, Te]
+  float* conv_save;      // step slice of the [B, L, Te, 16] location-conv features (row stride cs_ld per utterance) or nullptr
+  int64_t cs_ld;
 };
 
 // grid (ceil(Te/kTT), B), block = A rounded up to a warp multiple; thread a owns attention dim a.
@@ -126,6 +128,16 @@ __global__ void __launch_bounds__(512) att_energy_fwd_kernel(EnergyFwdParams p) 
   const int a = threadIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nwarps = blockDim.x >> 5;
   conv_tile<CM>(g, p.wprev + b * p.w_ld, p.conv_w, te0, wp, cw, conv);
+  const int ntl = min(kTT, g.Te - te0);
+  if (p.conv_save != nullptr) {
+    // the backward (att_energy_bwd_mma_kernel, las_att_param_grads_part) reads the conv features instead of
+    // recomputing the 2K+1-tap correlation: rows of 16 floats, channels >= C are zero
+    float* cs = p.conv_save + b * p.cs_ld + static_cast<int64_t>(te0) * 16;
+    for (int i = threadIdx.x; i < ntl * 16; i += blockDim.x) {
+      const int tl = i >> 4, c = i & 15;
+      cs[i] = c < CM ? conv[tl * CM + c] : 0.f;
+    }
+  }
 
   float matt[CM];
 #pragma unroll
@@ -133,7 +145,6 @@ __global__ void __launch_bounds__(512) att_energy_fwd_kernel(EnergyFwdParams p) 
   const float dza = (a < g.A) ? p.dz[b * p.dz_ld + a] : 0.f;
   const float gv = (a < g.A) ? p.gvec[a] : 0.f;
   const float* Pb = p.P + (static_cast<int64_t>(b) * g.Te + te0) * g.A + a;
-  const int ntl = min(kTT, g.Te - te0);
   // all P values of the tile first: one global load per frame inside the loop made every iteration wait for L2
   // (long_scoreboard 10.6 warps/issue, 13 % issue utilisation in the first version)
   float pv[kTT];
@@ -576,6 +587,181 @@ __global__ void __launch_bounds__(512) att_energy_bwd_kernel(EnergyBwdParams p) 
     for (int c = 0; c < CM; ++c)
       if (c < g.C) pp[c * p.Ap] += dmatt[c];
     pp[CM * p.Ap] += dgv;
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// "Lean" energy backward of the per-timestep path (tensor cores): what the time loop itself needs from this phase
+// is only ddz_t (-> dz_t -> the cell) and the conv-feature gradient (-> dw_{t-1}); dP and the energy-MLP parameter
+// sums are plain sums over (b, t) and are produced after the loop by las_att_param_grads_part from the saved conv
+// features and the energy gradients de_all written here (exactly what the cluster-persistent backward does).
+// The scalar kernel above spends ~230 instructions per (warp, frame), ~100 of them in the 16-value warp reduction of
+// ds x mlp_att; here that contraction and the recomputed mlp_att(conv) are mma.m16n8k16 with bf16 hi/lo operands.
+//   grid (ceil(Te/16), B), block 32 * min(A/16, 10): warp w owns the attention k-tiles w, w + nw, ..
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t& lo) {
+  hi = pack_bf16x2(x, y);
+  const float2 h = unpack_bf16x2(hi);
+  lo = pack_bf16x2(x - h.x, y - h.y);
+}
+
+// B fragments of mlp_att for both products: mattB [A/8][32] x uint4 (k = channel, n = attention dim; hi0, hi1, lo0,
+// lo1) and mattB2 [A/16][2][32] x uint2 (k = attention dim, n = channel)
+__global__ void att_pack_matt_kernel(const float* __restrict__ mlp_att, int A, int C, uint4* __restrict__ mattB,
+                                     uint2* __restrict__ mattB2) {
+  const int NT = A / 8, KT = A / 16;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < NT * 32 + KT * 64; i += gridDim.x * blockDim.x) {
+    if (i < NT * 32) {
+      const int nt = i >> 5, l = i & 31, a = 8 * nt + (l >> 2), c0 = 2 * (l & 3);
+      float m[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = c0 + (k & 1) + 8 * (k >> 1);
+        m[k] = (c < C) ? mlp_att[a * C + c] : 0.f;
+      }
+      uint4 v;
+      split2(m[0], m[1], v.x, v.z);
+      split2(m[2], m[3], v.y, v.w);
+      mattB[i] = v;
+    } else {
+      const int j = i - NT * 32;
+      const int kt = j >> 6, nc = (j >> 5) & 1, l = j & 31, c = 8 * nc + (l >> 2), a0 = 16 * kt + 2 * (l & 3);
+      float m[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int a = a0 + (k & 1) + 8 * (k >> 1);
+        m[k] = (c < C) ? mlp_att[a * C + c] : 0.f;
+      }
+      mattB2[j] = make_uint2(pack_bf16x2(m[0], m[1]), pack_bf16x2(m[2], m[3]));
+    }
+  }
+}
+
+struct EnergyLeanParams {
+  int B, L, Te, A, C, t;
+  float scaling;
+  const float* P;                       // [B*Te, A]
+  const float* dz; int64_t dz_ld;       // mlp_dec(z_t) rows
+  const float* wcur; int64_t w_ld;      // alignment produced by step t
+  const float* dw;                      // [B, Te]
+  const float* conv_save;               // [B, L, Te, 16]
+  const uint4* mattB; const uint2* mattB2;
+  const float* gvec;
+  float* ddz; int64_t ddz_ld;           // [B] rows of A, atomically accumulated (pre-zeroed)
+  float* dattc;                         // [B, Te, C] out (this step)
+  float* de_all;                        // [B, L, Te] out
+};
+
+constexpr int kLeanWarps = 10;
+__global__ void __launch_bounds__(32 * kLeanWarps) att_energy_bwd_mma_kernel(EnergyLeanParams p) {
+  __shared__ float de_s[16];
+  __shared__ float red[kLeanWarps];
+  __shared__ float4 dcred[kLeanWarps][2][32];
+  const int b = blockIdx.y, te0 = blockIdx.x * 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, tig = lane & 3;
+  const int nw = blockDim.x >> 5;
+  const int Te = p.Te, A = p.A;
+  const int ntl = min(16, Te - te0);
+
+  // softmax backward: de = scaling * w * (dw - <w, dw>)
+  const float* wc = p.wcur + b * p.w_ld;
+  const float* dwb = p.dw + static_cast<int64_t>(b) * Te;
+  float dot = 0.f;
+  for (int i = threadIdx.x; i < Te; i += blockDim.x) dot = fmaf(wc[i], dwb[i], dot);
+  dot = block_reduce_sum(dot, red, nw);
+  if (threadIdx.x < 16) {
+    float de = 0.f;
+    if (static_cast<int>(threadIdx.x) < ntl) {
+      const int te = te0 + threadIdx.x;
+      de = p.scaling * wc[te] * (dwb[te] - dot);
+      p.de_all[(static_cast<int64_t>(b) * p.L + p.t) * Te + te] = de;
+    }
+    de_s[threadIdx.x] = de;
+  }
+  __syncthreads();
+
+  // conv features of my two rows as A fragments (k = channel)
+  const int r0 = gq, r1 = gq + 8;
+  uint32_t Ah[4], Al[4];
+  {
+    const float* cv = p.conv_save + ((static_cast<int64_t>(b) * p.L + p.t) * Te + te0) * 16;
+    const float2 z = make_float2(0.f, 0.f);
+    const float2 v0 = r0 < ntl ? *reinterpret_cast<const float2*>(cv + r0 * 16 + 2 * tig) : z;
+    const float2 v1 = r1 < ntl ? *reinterpret_cast<const float2*>(cv + r1 * 16 + 2 * tig) : z;
+    const float2 v2 = r0 < ntl ? *reinterpret_cast<const float2*>(cv + r0 * 16 + 2 * tig + 8) : z;
+    const float2 v3 = r1 < ntl ? *reinterpret_cast<const float2*>(cv + r1 * 16 + 2 * tig + 8) : z;
+    split2(v0.x, v0.y, Ah[0], Al[0]);
+    split2(v1.x, v1.y, Ah[1], Al[1]);
+    split2(v2.x, v2.y, Ah[2], Al[2]);
+    split2(v3.x, v3.y, Ah[3], Al[3]);
+  }
+  const float de0 = de_s[r0], de1 = de_s[r1];      // zero for rows past the tile: their P rows only have to be finite
+  const float* P0 = p.P + (static_cast<int64_t>(b) * Te + te0 + min(r0, ntl - 1)) * A + 2 * tig;
+  const float* P1 = p.P + (static_cast<int64_t>(b) * Te + te0 + min(r1, ntl - 1)) * A + 2 * tig;
+  const float* dzr = p.dz + b * p.dz_ld + 2 * tig;
+  const float* gvr = p.gvec + 2 * tig;
+  float* ddzr = p.ddz + b * p.ddz_ld + 2 * tig;
+  float dcv0[4] = {0.f, 0.f, 0.f, 0.f}, dcv1[4] = {0.f, 0.f, 0.f, 0.f};
+  const int KT = A >> 4;
+  for (int kt = warp; kt < KT; kt += nw) {
+    uint32_t Dh[4], Dl[4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int nt = 2 * kt + h, a = 8 * nt;
+      const uint4 bm = __ldg(p.mattB + nt * 32 + lane);
+      const float2 p0 = __ldg(reinterpret_cast<const float2*>(P0 + a));
+      const float2 p1 = __ldg(reinterpret_cast<const float2*>(P1 + a));
+      const float2 dz2 = *reinterpret_cast<const float2*>(dzr + a);
+      const float2 gv2 = __ldg(reinterpret_cast<const float2*>(gvr + a));
+      float acc[4] = {p0.x, p0.y, p1.x, p1.y};
+      mma_bf16_16816(acc, Ah, bm.x, bm.y);
+      mma_bf16_16816(acc, Al, bm.x, bm.y);
+      mma_bf16_16816(acc, Ah, bm.z, bm.w);
+      const float s00 = tanh_acc(acc[0] + dz2.x), s01 = tanh_acc(acc[1] + dz2.y);
+      const float s10 = tanh_acc(acc[2] + dz2.x), s11 = tanh_acc(acc[3] + dz2.y);
+      const float d00 = de0 * gv2.x * (1.f - s00 * s00), d01 = de0 * gv2.y * (1.f - s01 * s01);
+      const float d10 = de1 * gv2.x * (1.f - s10 * s10), d11 = de1 * gv2.y * (1.f - s11 * s11);
+      float v0 = d00 + d10, v1 = d01 + d11;       // column sums over my 2 rows, then over the 8 row groups
+      v0 += __shfl_xor_sync(0xffffffffu, v0, 4);  v1 += __shfl_xor_sync(0xffffffffu, v1, 4);
+      v0 += __shfl_xor_sync(0xffffffffu, v0, 8);  v1 += __shfl_xor_sync(0xffffffffu, v1, 8);
+      v0 += __shfl_xor_sync(0xffffffffu, v0, 16); v1 += __shfl_xor_sync(0xffffffffu, v1, 16);
+      if (gq == 0) {
+        atomicAdd(ddzr + a, v0);
+        atomicAdd(ddzr + a + 1, v1);
+      }
+      split2(d00, d01, Dh[2 * h], Dl[2 * h]);
+      split2(d10, d11, Dh[2 * h + 1], Dl[2 * h + 1]);
+    }
+    const uint2 b0 = __ldg(p.mattB2 + (kt * 2) * 32 + lane);
+    mma_bf16_16816(dcv0, Dh, b0.x, b0.y);
+    mma_bf16_16816(dcv0, Dl, b0.x, b0.y);
+    if (p.C > 8) {
+      const uint2 b1 = __ldg(p.mattB2 + (kt * 2 + 1) * 32 + lane);
+      mma_bf16_16816(dcv1, Dh, b1.x, b1.y);
+      mma_bf16_16816(dcv1, Dl, b1.x, b1.y);
+    }
+  }
+  dcred[warp][0][lane] = make_float4(dcv0[0], dcv0[1], dcv0[2], dcv0[3]);
+  dcred[warp][1][lane] = make_float4(dcv1[0], dcv1[1], dcv1[2], dcv1[3]);
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int half = threadIdx.x >> 5;      // channels 0..7 / 8..15
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int w = 0; w < nw; ++w) {
+      const float4 v = dcred[w][half][lane];
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    const int c0 = 8 * half + 2 * tig;
+    float* drow = p.dattc + (static_cast<int64_t>(b) * Te + te0) * p.C;
+    if (r0 < ntl) {
+      if (c0 < p.C) drow[r0 * p.C + c0] = s.x;
+      if (c0 + 1 < p.C) drow[r0 * p.C + c0 + 1] = s.y;
+    }
+    if (r1 < ntl) {
+      if (c0 < p.C) drow[r1 * p.C + c0] = s.z;
+      if (c0 + 1 < p.C) drow[r1 * p.C + c0 + 1] = s.w;
+    }
   }
 }
 
@@ -1080,14 +1266,25 @@ int las_att_dq(const float* ws_alloc, const float* dc_all, int L, int B, int Te,
   return 0;
 }
 
-int64_t las_att_scratch_floats(int B, int L, int Te, int A, int C, int K) {
-  // shared scratch of the attention backward: per-CTA partial sums of (a) the energy-MLP parameter
-  // gradients, (b) the conv-weight gradient
+static int64_t att_lean_pack_floats(int A) { return (static_cast<int64_t>((A + 7) / 8) * 32 * 4 + static_cast<int64_t>((A + 15) / 16) * 64 * 2 + 63) / 64 * 64; }
+static int64_t att_scratch_main_floats(int B, int L, int Te, int A, int C, int K) {
   const int64_t Ap = (A + 31) / 32 * 32;
   const int64_t a = static_cast<int64_t>((Te + kPG - 1) / kPG) * B * 17 * Ap;
   const int64_t b = static_cast<int64_t>((L + kDT - 1) / kDT) * B * C * (2 * K + 1);
   const int64_t c = static_cast<int64_t>((Te + kTT - 1) / kTT) * B * 17 * Ap;
-  return (a > b ? (a > c ? a : c) : (b > c ? b : c)) + 64;
+  return ((a > b ? (a > c ? a : c) : (b > c ? b : c)) + 64 + 63) / 64 * 64;
+}
+
+int64_t las_att_scratch_floats(int B, int L, int Te, int A, int C, int K) {
+  // shared scratch of the attention backward: per-CTA partial sums of (a) the energy-MLP parameter
+  // gradients, (b) the conv-weight gradient
+  // + the packed mlp_att fragments of the lean per-timestep energy backward, kept BEHIND the shared region
+  return att_scratch_main_floats(B, L, Te, A, C, K) + att_lean_pack_floats(A);
+}
+
+int las_att_bwd_lean_supported(int A, int C) {
+  static const bool on = getenv("LAS_ATT_LEAN") == nullptr || atoi(getenv("LAS_ATT_LEAN")) != 0;
+  return (on && A >= 16 && A % 16 == 0 && A <= 1024 && C >= 1 && C <= 16) ? 1 : 0;
 }
 
 int las_att_dconv(const float* dattc_all, const float* ws_alloc, int L, int B, int Te, int C, int K, float* dconv_w,
@@ -1244,6 +1441,8 @@ static int dec_fwd_steps(const las_dec_args* a, cudaStream_t stream, int t_begin
     // (3) energies e = gvec . tanh(P + dz + mlp_att(conv(w_{t-1})))   (model.py:156-165)
     ep.dz = dz_t;
     ep.wprev = a->ws + static_cast<int64_t>(t) * Te;
+    ep.conv_save = a->conv_save ? a->conv_save + static_cast<int64_t>(t) * Te * 16 : nullptr;
+    ep.cs_ld = static_cast<int64_t>(L) * Te * 16;
     if (CM == 4) att_energy_fwd_kernel<4><<<egrid, ethreads, esmem, stream>>>(ep);
     else if (CM == 8) att_energy_fwd_kernel<8><<<egrid, ethreads, esmem, stream>>>(ep);
     else if (CM == 12) att_energy_fwd_kernel<12><<<egrid, ethreads, esmem, stream>>>(ep);
@@ -1316,7 +1515,23 @@ int las_dec_bwd(const las_dec_args* a, void* stream_) {
   if (int rc = ensure_smem(att_dw_kernel, dsmem)) return rc;
   const dim3 egrid((Te + kTT - 1) / kTT, B);
   const int ncta = egrid.x * egrid.y;
-  LAS_CUDA(cudaMemsetAsync(a->att_part, 0, static_cast<size_t>(ncta) * (CM + 1) * Ap * sizeof(float), stream));
+  // lean energy backward (att_energy_bwd_mma_kernel): the caller saved the conv features in the forward, wants the
+  // energy gradients in de_all, and produces dP and the energy-MLP parameter sums itself after this call
+  // (las_att_param_grads_part), as it does for the cluster-persistent backward
+  const bool lean = a->conv_save != nullptr && a->de_all != nullptr && las_att_bwd_lean_supported(A, a->C) != 0;
+  EnergyLeanParams lp = {};
+  if (lean) {
+    float* pk = a->att_part + att_scratch_main_floats(B, L, Te, A, a->C, a->K);
+    uint4* mattB = reinterpret_cast<uint4*>(pk);
+    uint2* mattB2 = reinterpret_cast<uint2*>(pk + static_cast<int64_t>(A / 8) * 32 * 4);
+    att_pack_matt_kernel<<<(A / 8 * 32 + A / 16 * 64 + 255) / 256, 256, 0, stream>>>(a->mlp_att, A, a->C, mattB, mattB2); ++g_launches;
+    lp.B = B; lp.L = L; lp.Te = Te; lp.A = A; lp.C = a->C; lp.scaling = a->att_scaling;
+    lp.P = a->P; lp.dz_ld = static_cast<int64_t>(L) * A; lp.w_ld = R * Te; lp.dw = a->dw_buf;
+    lp.conv_save = a->conv_save; lp.mattB = mattB; lp.mattB2 = mattB2; lp.gvec = a->gvec;
+    lp.ddz_ld = R * A; lp.de_all = a->de_all;
+  } else {
+    LAS_CUDA(cudaMemsetAsync(a->att_part, 0, static_cast<size_t>(ncta) * (CM + 1) * Ap * sizeof(float), stream));
+  }
   LAS_CUDA(cudaMemsetAsync(a->dc_state, 0, static_cast<size_t>(B) * Hd * sizeof(float), stream));
 
   __nv_bfloat16* dgates = static_cast<__nv_bfloat16*>(a->dgates);
@@ -1403,7 +1618,12 @@ int las_dec_bwd(const las_dec_args* a, void* stream_) {
     ep.wcur = a->ws + static_cast<int64_t>(t + 1) * Te;
     ep.ddz = a->ddz_all + static_cast<int64_t>(t + 1) * A;
     ep.dattc = a->dattc_all + static_cast<int64_t>(t) * B * Te * a->C;
-    if (CM == 4) att_energy_bwd_kernel<4><<<egrid, ethreads, esmem, stream>>>(ep);
+    if (lean) {
+      lp.t = t; lp.dz = ep.dz; lp.wcur = ep.wcur; lp.ddz = ep.ddz; lp.dattc = ep.dattc;
+      const int lw = A / 16 < kLeanWarps ? A / 16 : kLeanWarps;
+      att_energy_bwd_mma_kernel<<<dim3((Te + 15) / 16, B), 32 * lw, 0, stream>>>(lp);
+    }
+    else if (CM == 4) att_energy_bwd_kernel<4><<<egrid, ethreads, esmem, stream>>>(ep);
     else if (CM == 8) att_energy_bwd_kernel<8><<<egrid, ethreads, esmem, stream>>>(ep);
     else if (CM == 12) att_energy_bwd_kernel<12><<<egrid, ethreads, esmem, stream>>>(ep);
     else att_energy_bwd_kernel<16><<<egrid, ethreads, esmem, stream>>>(ep);
@@ -1414,8 +1634,10 @@ int las_dec_bwd(const las_dec_args* a, void* stream_) {
     launch_cell_bwd(cb, stream);
   }
   // reductions that were deferred out of the loop
-  att_part_reduce_kernel<<<((a->C + 1) * A + 255) / 256, 256, 0, stream>>>(a->att_part, ncta, CM, Ap, A, a->C,
-                                                                             a->dmlp_att, a->dgvec); ++g_launches;
+  if (!lean) {
+    att_part_reduce_kernel<<<((a->C + 1) * A + 255) / 256, 256, 0, stream>>>(a->att_part, ncta, CM, Ap, A, a->C,
+                                                                               a->dmlp_att, a->dgvec); ++g_launches;
+  }
   if (int rc = launch_att_dconv(a->dattc_all, a->ws, L, B, Te, a->C, a->K, a->dconv_w, a->att_part, stream)) return rc;
   att_denc_kernel<<<dim3((Te + kDE - 1) / kDE, B), (a->H <= 256 ? 256 : 320), 0, stream>>>(a->ws, a->dctx_all, L, B, Te, a->H, a->denc, a->denc_accumulate); ++g_launches;
   LAS_LAUNCH_CHECK();

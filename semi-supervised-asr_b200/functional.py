@@ -658,8 +658,10 @@ class DecoderFn(torch.autograd.Function):
     unused), ws_alloc f32 [B, L+1, Te] (row 0 = initial alignment), pred int64 [B, L] or None)."""
 
     @staticmethod
-    def forward(ctx, enc_h, enc_lens, ys_in, L, mode, smooth_scaling, att_scaling, K, bos, p_drop, tf_mask, sample, *wts):
-        """tf_mask: None, or a uint8 tensor [L+1] for scheduled sampling (mode 1 with teacher tokens `ys_in`: step r
+    def forward(ctx, enc_h, enc_lens, ys_in, L, mode, smooth_scaling, att_scaling, K, bos, p_drop, tf_mask, sample,
+                need_grad, *wts):
+        """need_grad: a backward pass may follow (the caller's grad mode: inside Function.forward autograd is always
+        switched off, so `torch.is_grad_enabled()` cannot tell). tf_mask: None, or a uint8 tensor [L+1] for scheduled sampling (mode 1 with teacher tokens `ys_in`: step r
         consumes the teacher token where tf_mask[r] != 0, else the previous prediction; model.py:327-329). sample:
         the prediction is drawn from softmax(logits) instead of the argmax (mode 1, model.py:349-351)."""
         W = dict(zip(DEC_WEIGHTS, wts))
@@ -723,7 +725,7 @@ class DecoderFn(torch.autograd.Function):
         es = GREEDY_EARLY_STOP
         # greedy decoding without autograd (Solver.validation / test, solver.py:212-286) may run as ONE cluster-persistent
         # launch too: the embedding half of the cell input becomes a per-token table, the argmax feeds back in-kernel
-        greedy_p = (mode == 1 and DEC_PERSISTENT and p_drop == 0 and not torch.is_grad_enabled() and ZC % 8 == 0
+        greedy_p = (mode == 1 and DEC_PERSISTENT and p_drop == 0 and not need_grad and ZC % 8 == 0
                     and tf_mask is None and not sample)
         if mode == 1 and (tf_mask is not None or sample):
             if tf_mask is not None:
@@ -771,10 +773,17 @@ class DecoderFn(torch.autograd.Function):
             zcd = torch.zeros(B * R * ZC + 64, device=dev, dtype=BF16)
             a.zcd = ptr(zcd)
             keep.append(zcd)
+        conv_save_steps = None
+        if not persist and need_grad and _lib.lib().las_att_bwd_lean_supported(A, C):
+            # per-timestep path with a backward to come: the energy kernels also save the location-conv features, and
+            # the time loop of the backward runs its lean tensor-core energy kernel (dP and the energy-MLP parameter
+            # sums follow after the loop from these features and the energy gradients, as after the persistent kernel)
+            conv_save_steps = torch.empty(B, L, Te, 16, **f32)
+            a.conv_save = ptr(conv_save_steps)
         if mode == 1 and persist:
             call("las_dec_fwd", ctypes.byref(a))      # all steps (or up to every utterance's <EOS>) in one launch
             es["last_steps"] = L
-        elif mode == 1 and es["on"] and not torch.is_grad_enabled():
+        elif mode == 1 and es["on"] and not need_grad:
             # greedy decoding for scoring (Solver.test / validation): issue the steps in chunks and stop as soon as
             # every utterance has emitted <EOS>. Rows after the stop keep their initial zeros; the hypotheses are
             # identical after remove_pad_eos (utils.py:192-201), which cuts at the first <EOS>.
@@ -803,7 +812,7 @@ class DecoderFn(torch.autograd.Function):
         ctx.saved = dict(enc_bf=enc_bf, Pm=Pm, mlp_enc_bf=mlp_enc_bf, wr_cat=wr_cat, ws=ws, zc=zc, cx=cx, dzf=dzf,
                          gates=gates, csave=csave, conv_w=conv_w, mlp_att=mlp_att, gvec=gvec, emb_in=emb_in,
                          out_bf=out_bf, ys_in=ys_in, keep=keep, pers=pers, bos=bos, we_bf=Pk["we_bf"], Pk=Pk, tok_in=tok_in,
-                         logits=logits if mode != 0 else None,
+                         logits=logits if mode != 0 else None, conv_save_steps=conv_save_steps,
                          emb_op=(emb_op[:B * R * Ep].view(B * R, Ep) if mode != 0 else None))
         ctx.W = W
         ctx.wts = wts
@@ -861,7 +870,8 @@ class DecoderFn(torch.autograd.Function):
         F32 = torch.float32
         zspecs = [((n, ZC), BF16), ((n * A + 64,), F32), ((B * Te, A), F32), ((n, 4 * Hd), BF16), ((A, C), F32), ((A,), F32),
                   ((C, 2 * K + 1), F32)]
-        if pers is not None:
+        lean = pers is None and S.get("conv_save_steps") is not None
+        if pers is not None or lean:
             zspecs += [((B, L, Te), F32), ((B, L, O), F32)]
         zb = zeros_many(dev, zspecs)
         dcz_all, ddz_all, dP, dgates, d_mlp_att, d_gvec, d_conv = zb[:7]
@@ -890,19 +900,26 @@ class DecoderFn(torch.autograd.Function):
             a.cbias, a.pbar, a.P = ptr(pers["cbias"]), ptr(pers["Pbar"]), ptr(pers["Pc"])
             if not L_.las_dec_persistent_supported(ctypes.byref(a)):
                 raise _lib.LasError("decoder backward: the forward ran the persistent kernel but the backward would not")
+        if lean:
+            de_all = zb[7]
+            a.conv_save, a.de_all = ptr(S["conv_save_steps"]), ptr(de_all)
         call("las_dec_bwd", ctypes.byref(a))
         # ---- critical path: gradient w.r.t. the encoder states
         dP_bf = None
-        scope = wgrad_scope(ctx.wts, S, pers, (de_all if pers is not None else None), dl, (dl_bf if mode != 2 else None),
+        post = pers is not None or lean           # dP / energy-MLP parameter sums are produced after the time loop
+        scope = wgrad_scope(ctx.wts, S, pers, (de_all if post else None), dl, (dl_bf if mode != 2 else None),
                             dlogits, dl_tot, dgates, dcz_all, ddz_all, dP, dattc_all, att_part, d_mlp_att, d_gvec)
-        if pers is not None:
+        if post:
             # dP is all the encoder's backward waits for; when the weight gradients are deferred, the energy-MLP
             # parameter sums (the same walk over (b, t, te, a) again, tanh recomputed) run on the side stream
-            apg = (ptr(pers["Pc"]), ptr(S["dzf"]), ptr(pers["conv_save"]), ptr(de_all), ptr(S["mlp_att"]), ptr(S["gvec"]),
+            apg_P = pers["Pc"] if pers is not None else S["Pm"]
+            apg_conv = pers["conv_save"] if pers is not None else S["conv_save_steps"]
+            apg = (ptr(apg_P), ptr(S["dzf"]), ptr(apg_conv), ptr(de_all), ptr(S["mlp_att"]), ptr(S["gvec"]),
                    B, L, Te, A, C)
             apg_split = scope.deferred and os.environ.get("LAS_APG_SPLIT", "1") == "1"
             call("las_att_param_grads_part", *apg, 1 if apg_split else 3, ptr(dP), ptr(att_part), ptr(d_mlp_att),
                  ptr(d_gvec))
+        if pers is not None:
             dQ = torch.empty(B * Te, O, **f32)
             call("las_att_dq", ptr(S["ws"]), ptr(dc_all), L, B, Te, O, ptr(dQ))
             # c_t = w_t @ Q + b, Q = enc_h @ mlp_o.weight^T: d enc_h = dQ mlp_o.weight (+ dP mlp_enc.weight below)
@@ -971,12 +988,12 @@ class DecoderFn(torch.autograd.Function):
                          mlp_enc_w=d_mlp_enc_w, mlp_enc_b=d_mlp_enc_b, mlp_dec_w=d_mlp_dec, mlp_att_w=d_mlp_att,
                          conv_w=d_conv.view_as(W["conv_w"]), gvec_w=d_gvec.view_as(W["gvec_w"]), mlp_o_w=d_mlp_o_w,
                          mlp_o_b=d_mlp_o_b)
-            if pers is not None and apg_split:
+            if post and apg_split:
                 # This kernel fills every free SM with 150 us CTAs; run right away it delays the small kernels between
                 # the BPTT launches (each finds no free CTA slot). It is parked until the encoder's layer-0 BPTT, the
                 # longest serial kernel of the step, has the main stream to itself.
                 w_matt, w_gvec = ctx.wts[DEC_WEIGHTS.index("mlp_att_w")], ctx.wts[DEC_WEIGHTS.index("gvec_w")]
-                hold = (pers["Pc"], S["dzf"], pers["conv_save"], de_all, S["mlp_att"], S["gvec"], dP, att_part)
+                hold = (apg_P, S["dzf"], apg_conv, de_all, S["mlp_att"], S["gvec"], dP, att_part)
 
                 def late(apg=apg, hold=hold, d_mlp_att=d_mlp_att, d_gvec=d_gvec, w_matt=w_matt, w_gvec=w_gvec):
                     call("las_att_param_grads_part", *apg, 2, ptr(hold[6]), ptr(hold[7]), ptr(d_mlp_att), ptr(d_gvec))
@@ -991,7 +1008,7 @@ class DecoderFn(torch.autograd.Function):
                 grads["gvec_w"] = None
             glist = sc.deliver([grads[k] for k in DEC_WEIGHTS])
         ctx.saved = None
-        return (denc, None, None, None, None, None, None, None, None, None, None, None, *glist)
+        return (denc, None, None, None, None, None, None, None, None, None, None, None, None, *glist)
 
 
 # --------------------------------------------------------------------------------------------

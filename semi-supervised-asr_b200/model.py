@@ -252,9 +252,12 @@ class Decoder(torch.nn.Module):
         dev = enc_pad.device
         p = float(self.dropout_rate) if self.training else 0.0
         in_kernel_sample = bool(sample) and mode == 1            # the only mode that feeds the prediction back
+        weights = self._weights()
+        # does a backward pass follow? (decides inference-only fast paths: one-launch greedy decoding, early stop)
+        need_grad = torch.is_grad_enabled() and (enc_pad.requires_grad or any(w.requires_grad for w in weights))
         logits_alloc, ws_alloc, pred = Fn.DecoderFn.apply(
             enc_pad.float().contiguous(), enc_lens_dev, ys_in_dev, L, mode, float(scaling), 2.0,
-            self.attention.conv_kernel_size, self.bos, p, tf_mask, in_kernel_sample, *self._weights())
+            self.attention.conv_kernel_size, self.bos, p, tf_mask, in_kernel_sample, need_grad, *weights)
         ls = self.ls_weight if (label_smoothing and self.ls_weight > 0 and self.training) else 0.0
         dist = self.vlabeldist.to(dev) if ls > 0 else None
         targets, sampled = ys_out_dev, None

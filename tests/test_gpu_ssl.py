@@ -112,6 +112,47 @@ def test_smooth_mode_gradient_reaches_earlier_steps():
         assert cosine(p.grad, leaves[k].grad) >= 0.999, (k, cosine(p.grad, leaves[k].grad))
 
 
+def test_greedy_free_run_keeps_its_backward_without_dropout():
+    """Free-running decode with argmax feedback (smooth_embedding: False, model.py:338-339) in a training step with
+    dropout 0: the one-launch greedy kernel is an inference path (it saves nothing for a backward pass) and must not
+    be taken when gradients are wanted. `torch.is_grad_enabled()` is always False inside autograd.Function.forward, so
+    the decision has to come from the caller; before that fix this configuration silently back-propagated through
+    buffers the forward never wrote."""
+    from oracle import las_oracle as O
+    G = load_golden("ssl_small")
+    g = G["raw"]
+    m = e2e_from_golden(G).train()
+    ux = torch.from_numpy(g["ux"])
+    Lu = int(ux.shape[1] * float(g["proportion"]))
+    _, u_logp, u_pred, _ = m(ux.cuda(), g["uilens"].tolist(), ys=None, label_smoothing=False, max_dec_timesteps=Lu,
+                             smooth=False)
+    m.zero_grad()
+    (-u_logp.sum()).backward()
+    leaves, full = O._with_grad(G["p0"])
+    _, o_logp, o_pred, _ = O.e2e_forward(ux, g["uilens"].tolist(), full, g["subsample"].tolist(), ys=None,
+                                         max_dec_timesteps=Lu, smooth=False, label_smoothing=False,
+                                         ls_weight=float(g["ls_weight"]), labeldist=g["labeldist"], training=True)
+    (-o_logp.sum()).backward()
+    assert torch.equal(u_pred.cpu(), torch.as_tensor(o_pred).cpu())
+    assert rel_close(u_logp, o_logp)
+    for k, p in m.named_parameters():
+        if float(leaves[k].grad.norm()) > 0:
+            assert cosine(p.grad, leaves[k].grad) >= 0.999, (k, cosine(p.grad, leaves[k].grad))
+    # ... while under no_grad the same call is served by the one-launch kernel
+    L = pkg("_lib")
+    L.path_counters(reset=True)
+    with torch.no_grad():
+        _, _, n_pred, _ = m(ux.cuda(), g["uilens"].tolist(), ys=None, label_smoothing=False, max_dec_timesteps=Lu, smooth=False)
+    assert torch.equal(n_pred.cpu(), u_pred.cpu())
+    pc = L.path_counters()                      # (the small golden geometry may only have the per-timestep kernels)
+    assert pc["dec_persist_fwd"] + pc["dec_step_fwd"] >= 1, pc
+
+
+def rel_close(a, b, tol=2e-3):
+    a, b = torch.as_tensor(a).detach().cpu().double(), torch.as_tensor(b).detach().cpu().double()
+    return float((a - b).abs().max()) <= tol * float(b.abs().max() + 1e-12)
+
+
 def test_diverged_model_cannot_produce_out_of_range_tokens():
     """torch.argmax conventions (first maximal index, NaN counts as the maximum): an all-NaN logit row -- a
     diverged generator -- must give a token id in [0, V), not an out-of-range embedding index (this used to be an
