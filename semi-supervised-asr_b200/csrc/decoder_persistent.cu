@@ -174,6 +174,17 @@ constexpr DGeom make_static_dgeom2() {
 }
 constexpr DGeom kSF2 = make_static_dgeom2();
 static_assert(kSF2.smem > 0, "second static forward geometry must fit");
+// The greedy (inference) variant of both, for vocabularies of up to kS_V tokens: its layout carries the output-layer rows
+// (RPV = kS_V / 16 per CTA; a smaller vocabulary leaves the last rows unused) and the per-token input table. Solver.test
+// decodes one utterance at a time: a batch of one runs with 4 utterance columns per cluster (three of them idle).
+constexpr int kS_V = 48;
+constexpr DGeom make_static_dgeom_g(int Te, int NB) {
+  DGeom g{};
+  g.smem = dec_geom_c(kS_Hd, kS_O, kS_A, Te, kS_C, kS_K, NB, g, kS_V) ? g.smem : -1;
+  return g;
+}
+constexpr DGeom kSFg = make_static_dgeom_g(kS_Te, kS_NB), kSFg2 = make_static_dgeom_g(kS2_Te, kS2_NB);
+static_assert(kSFg.smem > 0 && kSFg2.smem > 0, "static greedy geometries must fit");
 
 // ------------------------------------------------------------------------------------------
 // cluster primitives
@@ -335,7 +346,7 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
   }
   __syncthreads();
   const DGeom& g = p.g;
-#define GEO(x) (kS == 1 ? kSF.x : kS == 2 ? kSF2.x : g.x)
+#define GEO(x) (kS == 1 ? (kG ? kSFg.x : kSF.x) : kS == 2 ? (kG ? kSFg2.x : kSF2.x) : g.x)
   uint64_t* bz = bars; uint64_t* bc = bars + 2; uint64_t* bdz = bars + 4; uint64_t* be = bars + 5; uint64_t* bl = bars + 6;
   uint32_t* zB = reinterpret_cast<uint32_t*>(smem + GEO(o_zB));       // [2][KTp][32][2]
   float* red = reinterpret_cast<float*>(smem + GEO(o_red));           // [16][32][4] gate partial sums (P1)
@@ -436,11 +447,11 @@ __global__ void __launch_bounds__(kThreads, 1) dec_persist_fwd_kernel(const __gr
   }
   // greedy variant: per-token input terms of my hidden units, my output-layer rows, token state
   float* Mtab = reinterpret_cast<float*>(smem + GEO(o_exr));                       // [V][4][UPC]
-  __nv_bfloat16* lgw = reinterpret_cast<__nv_bfloat16*>(smem + g.o_lgw);           // [RPV][ZC]
-  float* lg_mine = reinterpret_cast<float*>(smem + g.o_lgm);                       // [RPV][8]
-  float* lg_all = reinterpret_cast<float*>(smem + g.o_lga);                        // [16][RPV][8]
-  int* tok_s = reinterpret_cast<int*>(smem + g.o_tok);                             // [8] tokens, [8] stop flags
-  const int RPV = g.RPV, V = p.V;
+  __nv_bfloat16* lgw = reinterpret_cast<__nv_bfloat16*>(smem + GEO(o_lgw));        // [RPV][ZC]
+  float* lg_mine = reinterpret_cast<float*>(smem + GEO(o_lgm));                    // [RPV][8]
+  float* lg_all = reinterpret_cast<float*>(smem + GEO(o_lga));                     // [16][RPV][8]
+  int* tok_s = reinterpret_cast<int*>(smem + GEO(o_tok));                          // [8] tokens, [8] stop flags
+  const int RPV = GEO(RPV), V = p.V;
   if (kG) {
     for (int i = tid; i < V * 4 * UPC; i += kThreads) {
       const int v = i / (4 * UPC), k = (i / UPC) & 3, u = i % UPC;
@@ -2028,12 +2039,16 @@ int dec_persist_fwd(const las_dec_args* a, cudaStream_t stream) {
     LAS_CUDA(cudaFuncSetAttribute(dec_persist_fwd_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     LAS_CUDA(cudaFuncSetAttribute(dec_persist_fwd_kernel<0, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     LAS_CUDA(cudaFuncSetAttribute(dec_persist_fwd_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+    LAS_CUDA(cudaFuncSetAttribute(dec_persist_fwd_kernel<1, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    LAS_CUDA(cudaFuncSetAttribute(dec_persist_fwd_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+    LAS_CUDA(cudaFuncSetAttribute(dec_persist_fwd_kernel<2, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    LAS_CUDA(cudaFuncSetAttribute(dec_persist_fwd_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     attr_set = true;
   }
   const bool greedy = a->mode == 1;
-  const int stat = greedy ? 0 : use_static_geom(a, nb);
-  if (stat == 1) g = kSF;
-  else if (stat == 2) g = kSF2;
+  const int stat = (greedy && a->V > kS_V) ? 0 : use_static_geom(a, nb);
+  if (stat == 1) g = greedy ? kSFg : kSF;
+  else if (stat == 2) g = greedy ? kSFg2 : kSF2;
   DecFwdP p;
   p.B = a->B; p.L = a->L; p.Te = a->Te; p.Hd = a->Hd; p.O = a->O; p.A = a->A; p.C = a->C; p.K = a->K;
   p.att_scaling = a->att_scaling;
@@ -2062,7 +2077,9 @@ int dec_persist_fwd(const las_dec_args* a, cudaStream_t stream) {
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  if (greedy) LAS_CUDA(cudaLaunchKernelEx(&cfg, dec_persist_fwd_kernel<0, true>, p));
+  if (greedy && stat == 1) LAS_CUDA(cudaLaunchKernelEx(&cfg, dec_persist_fwd_kernel<1, true>, p));
+  else if (greedy && stat == 2) LAS_CUDA(cudaLaunchKernelEx(&cfg, dec_persist_fwd_kernel<2, true>, p));
+  else if (greedy) LAS_CUDA(cudaLaunchKernelEx(&cfg, dec_persist_fwd_kernel<0, true>, p));
   else if (stat == 1) LAS_CUDA(cudaLaunchKernelEx(&cfg, dec_persist_fwd_kernel<1, false>, p));
   else if (stat == 2) LAS_CUDA(cudaLaunchKernelEx(&cfg, dec_persist_fwd_kernel<2, false>, p));
   else LAS_CUDA(cudaLaunchKernelEx(&cfg, dec_persist_fwd_kernel<0, false>, p));

@@ -52,8 +52,8 @@ def _agree_until_near_tie(pred, ref_pred, ref_logits, tol=2 * ACT_TOL):
     return n_checked
 
 
-@pytest.mark.parametrize("B", [11, 1])
-def test_persistent_greedy_decode_matches_per_step_kernels_and_oracle(B):
+@pytest.mark.parametrize("B", [11, 1, 30])     # run-time geometry (2 utterances per cluster) / the two compile-time greedy
+def test_persistent_greedy_decode_matches_per_step_kernels_and_oracle(B):      # geometries: 4 (batch of one) and 8 per cluster
     cfg, m, P, x, lens = _sharp_case(B=B)
     steps = 30
     lg_p, logp_p, pred_p, ws_p, cnt_p = _decode(m, x, lens, steps, True)
