@@ -69,6 +69,23 @@ __device__ __forceinline__ float tanh_er(float x) {
   return fmaf(2.0f, r, -1.0f);
 }
 
+// Programmatic dependent launch (the per-timestep decoder chain: ~19 small dependent kernels per decoder step). A kernel
+// launched with launch_k(.., pdl = true, ..) may be scheduled while its predecessor in the stream is still running; it
+// must call pdl_wait() before it touches anything the predecessor writes (the wait returns when the predecessor has
+// completed and its memory is visible). Here every such kernel waits as its FIRST statement and then allows its own
+// dependent to be scheduled, so at most two kernels of the chain are in flight and no kernel reads or writes memory
+// before everything in front of it in the stream has finished; what overlaps is launch latency and CTA ramp-up. In a
+// kernel launched without the attribute both calls are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() {
+#ifdef LAS_PDL_TRIGGER_FIRST
+  pdl_launch_dependents(); pdl_wait();
+#else
+  pdl_wait(); pdl_launch_dependents();
+#endif
+}
+
 // argmax with torch.argmax's conventions: first maximal index; NaN counts as the maximum (first NaN wins). Always
 // returns an index in [0, V): an all-NaN row (a diverged model) must not turn into an out-of-range token id.
 __device__ __forceinline__ bool argmax_better(float av, int ai, float bv, int bi) {

@@ -118,6 +118,7 @@ struct EnergyFwdParams {
 template <int CM>
 __global__ void __launch_bounds__(512) att_energy_fwd_kernel(EnergyFwdParams p) {
   extern __shared__ float sm[];
+  pdl_enter();
   const AttGeom& g = p.g;
   const int ksz = 2 * g.K + 1;
   float* wp = sm;
@@ -184,6 +185,7 @@ struct CtxFwdParams {
 // then the context for a 64-column slice: thread = (column pair, frame group of 8).
 __global__ void __launch_bounds__(256) att_ctx_fwd_kernel(CtxFwdParams p) {
   extern __shared__ float sm[];
+  pdl_enter();
   float* w_s = sm;               // [Te]
   float* red = w_s + ((p.Te + 1) & ~1);  // [8]
   float2* part = reinterpret_cast<float2*>(red + 8);  // [8][32]
@@ -250,6 +252,7 @@ struct NextEmbParams {
 // One CTA (4 warps) per utterance; dynamic shared memory: V floats (softmax numerators).
 __global__ void __launch_bounds__(128) next_emb_kernel(NextEmbParams p) {
   extern __shared__ float ne_sm[];
+  pdl_enter();
   __shared__ float s_mx, s_inv;
   __shared__ int s_amax;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -341,6 +344,7 @@ struct SmoothBwdParams {
 // One CTA (4 warps) per utterance; dynamic shared memory: E floats (demb) + V floats (dp).
 __global__ void __launch_bounds__(128) smooth_dlogit_kernel(SmoothBwdParams p) {
   extern __shared__ float sd_sm[];
+  pdl_enter();
   float* de_s = sd_sm;            // [E]
   float* dp_s = sd_sm + p.E;      // [V]: dp[v] = <E[v, :], demb>
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -400,6 +404,7 @@ struct DropRowParams {
   float* dcz_tot; const float* dzc_row; __nv_bfloat16* dcz_row; int64_t d_ld;   // backward
 };
 __global__ void dec_drop_fwd_kernel(DropRowParams p) {
+  pdl_enter();
   const int ZC = p.Hd + p.O;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.B * ZC) return;
@@ -413,6 +418,7 @@ __global__ void dec_drop_fwd_kernel(DropRowParams p) {
   p.zcd[off] = v;
 }
 __global__ void dec_drop_bwd_kernel(DropRowParams p) {
+  pdl_enter();
   const int ZC = p.Hd + p.O;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.B * ZC) return;
@@ -450,6 +456,7 @@ struct DwParams {
 // grid (ceil(Te/kTT), B), block 256: one warp per frame.
 __global__ void __launch_bounds__(256) att_dw_kernel(DwParams p) {
   extern __shared__ float sm[];
+  pdl_enter();
   const AttGeom& g = p.g;
   const int ksz = 2 * g.K + 1;
   float* dctx_s = sm;               // [H]
@@ -504,6 +511,7 @@ struct EnergyBwdParams {
 template <int CM>
 __global__ void __launch_bounds__(512) att_energy_bwd_kernel(EnergyBwdParams p) {
   extern __shared__ float sm[];
+  pdl_enter();
   const AttGeom& g = p.g;
   const int ksz = 2 * g.K + 1;
   float* wp = sm;
@@ -656,6 +664,7 @@ struct EnergyLeanParams {
 constexpr int kLeanWarps = 10;
 __global__ void __launch_bounds__(32 * kLeanWarps) att_energy_bwd_mma_kernel(EnergyLeanParams p) {
   __shared__ float de_s[16];
+  pdl_enter();
   __shared__ float red[kLeanWarps];
   __shared__ float4 dcred[kLeanWarps][2][32];
   const int b = blockIdx.y, te0 = blockIdx.x * 16;
@@ -1427,46 +1436,51 @@ static int dec_fwd_steps(const las_dec_args* a, cudaStream_t stream, int t_begin
   xp.enc_h = static_cast<const __nv_bfloat16*>(a->enc_h); xp.w_ld = R * Te; xp.ctx_ld = R * a->H;
 
   const dim3 egrid((Te + kTT - 1) / kTT, B), cgrid(B, (a->H + 63) / 64);
+  // programmatic dependent launches along the chain (common.cuh: pdl_*); the first launch of the call follows whatever
+  // the caller enqueued (other kernels, copies, event waits) and keeps full stream order
+  const bool pdl_on = pdl_enabled();
+  bool pdl = false;
   for (int t = t_begin; t < t_end; ++t) {
     // (1) LSTMCell: gates = W [emb; c_{t-1}; z_{t-1}] + b   (model.py:284-286)
     cp.step = t;
     cp.v1 = (drop ? zcd : zc) + static_cast<int64_t>(t) * ZC;      // cell input: c_{t-1} after dropout (model.py:285)
     cp.hout = zc + static_cast<int64_t>(t + 1) * ZC;
     if (free_run) cp.v2 = emb_op + static_cast<int64_t>(t) * Ep;
-    if (with_cell) launch_cell_fwd(cp, stream);
+    if (with_cell) { launch_cell_fwd(cp, stream, pdl); pdl = pdl_on; }
     // (2) decoder-state projection mlp_dec(z_t)   (model.py:163)
     float* dz_t = a->dzf + static_cast<int64_t>(t) * A;
     smallmm(static_cast<const uint32_t*>(a->mlp_dec_pk), A, Hd, zc + static_cast<int64_t>(t + 1) * ZC, 0, R * ZC, B,
-            nullptr, nullptr, 0, dz_t, static_cast<int64_t>(L) * A, nullptr, 0, stream);
+            nullptr, nullptr, 0, dz_t, static_cast<int64_t>(L) * A, nullptr, 0, stream, pdl);
+    pdl = pdl_on;
     // (3) energies e = gvec . tanh(P + dz + mlp_att(conv(w_{t-1})))   (model.py:156-165)
     ep.dz = dz_t;
     ep.wprev = a->ws + static_cast<int64_t>(t) * Te;
     ep.conv_save = a->conv_save ? a->conv_save + static_cast<int64_t>(t) * Te * 16 : nullptr;
     ep.cs_ld = static_cast<int64_t>(L) * Te * 16;
-    if (CM == 4) att_energy_fwd_kernel<4><<<egrid, ethreads, esmem, stream>>>(ep);
-    else if (CM == 8) att_energy_fwd_kernel<8><<<egrid, ethreads, esmem, stream>>>(ep);
-    else if (CM == 12) att_energy_fwd_kernel<12><<<egrid, ethreads, esmem, stream>>>(ep);
-    else att_energy_fwd_kernel<16><<<egrid, ethreads, esmem, stream>>>(ep);
+    if (CM == 4) LAS_CUDA(launch_k(att_energy_fwd_kernel<4>, egrid, dim3(ethreads), esmem, stream, pdl, ep));
+    else if (CM == 8) LAS_CUDA(launch_k(att_energy_fwd_kernel<8>, egrid, dim3(ethreads), esmem, stream, pdl, ep));
+    else if (CM == 12) LAS_CUDA(launch_k(att_energy_fwd_kernel<12>, egrid, dim3(ethreads), esmem, stream, pdl, ep));
+    else LAS_CUDA(launch_k(att_energy_fwd_kernel<16>, egrid, dim3(ethreads), esmem, stream, pdl, ep));
     ++g_launches;
     // (4) w = softmax(scaling * e) over all Te, context = w @ enc_h   (model.py:167-171)
     xp.w_out = a->ws + static_cast<int64_t>(t + 1) * Te;
     xp.ctx = ctx + static_cast<int64_t>(t + 1) * a->H;
-    att_ctx_fwd_kernel<<<cgrid, 256, csmem, stream>>>(xp); ++g_launches;
+    LAS_CUDA(launch_k(att_ctx_fwd_kernel, cgrid, dim3(256), csmem, stream, pdl, xp)); ++g_launches;
     // (5) c_t = mlp_o(context)   (model.py:172) -> second half of zc row t+1
     smallmm(static_cast<const uint32_t*>(a->mlp_o_pk), O, a->H, ctx + static_cast<int64_t>(t + 1) * a->H, 0, R * a->H, B,
-            a->mlp_o_b, nullptr, 0, nullptr, 0, zc + static_cast<int64_t>(t + 1) * ZC + Hd, R * ZC, stream);
+            a->mlp_o_b, nullptr, 0, nullptr, 0, zc + static_cast<int64_t>(t + 1) * ZC + Hd, R * ZC, stream, pdl);
     if (drop && !free_run) {    // (free-running modes: done inside next_emb_kernel below)
       DropRowParams dp = {};
       dp.B = B; dp.Hd = Hd; dp.O = O; dp.R = R; dp.row = t + 1; dp.p = a->drop_p;
       dp.seed_dev = static_cast<const unsigned long long*>(a->seed_dev); dp.site = a->drop_site;
       dp.zc = zc; dp.zcd = zcd;
-      dec_drop_fwd_kernel<<<(B * ZC + 255) / 256, 256, 0, stream>>>(dp); ++g_launches;
+      LAS_CUDA(launch_k(dec_drop_fwd_kernel, dim3((B * ZC + 255) / 256), dim3(256), 0, stream, pdl, dp)); ++g_launches;
     }
     if (free_run) {
       // (6) logit_t = output_layer([z_t; c_t]) (model.py:290-293), (7) next input embedding
       float* lg = a->logits + static_cast<int64_t>(t + 1) * V;
       smallmm(static_cast<const uint32_t*>(a->out_pk), V, ZC, zc + static_cast<int64_t>(t + 1) * ZC, 0, R * ZC, B,
-              a->out_b, nullptr, 0, lg, R * V, nullptr, 0, stream);
+              a->out_b, nullptr, 0, lg, R * V, nullptr, 0, stream, pdl);
       NextEmbParams np = {};
       np.drop_p = a->drop_p; np.seed_dev = static_cast<const unsigned long long*>(a->seed_dev);
       np.site = a->drop_site + 1; np.R = R; np.row = t + 1;
@@ -1478,7 +1492,7 @@ static int dec_fwd_steps(const las_dec_args* a, cudaStream_t stream, int t_begin
       np.sample_seed = static_cast<const unsigned long long*>(a->seed_dev);
       np.emb_out = emb_op + static_cast<int64_t>(t + 1) * Ep; np.eo_ld = R * Ep;
       if (drop) { np.zc = zc; np.zcd = zcd; np.Hd = Hd; np.O = O; np.zc_site = a->drop_site; }
-      next_emb_kernel<<<B, 128, V * sizeof(float), stream>>>(np); ++g_launches;
+      LAS_CUDA(launch_k(next_emb_kernel, dim3(B), dim3(128), V * sizeof(float), stream, pdl, np)); ++g_launches;
     }
   }
   LAS_LAUNCH_CHECK();
@@ -1556,21 +1570,29 @@ int las_dec_bwd(const las_dec_args* a, void* stream_) {
 
   const int V = a->V, E = a->E, Ep = (E + 15) / 16 * 16;
   const int64_t Vq = (V + 3) / 4 * 4;
+  // programmatic dependent launches along the chain (see dec_fwd_steps); the launch that follows a memset / memcpy node
+  // keeps full stream order
+  const bool pdl_on = pdl_enabled();
+  bool pdl = false;
   for (int t = L - 1; t >= 0; --t) {
     // In smooth mode with dropout both products of dgates_{t+1} -- W_ih[:, :E]^T (the input-embedding gradient) and
     // Wr^T (the state gradient) -- go out as ONE launch.
     const bool paired_mm = smooth && drop && t + 1 < L;
-    if (paired_mm)
+    if (paired_mm) {
       smallmm_pair(static_cast<const uint32_t*>(a->weT_pk), Ep, a->demb_buf, Ep, static_cast<const uint32_t*>(a->wrT_pk), ZC,
-                   a->dcz_tot, ZC, 4 * Hd, dgates + static_cast<int64_t>(t + 1) * 4 * Hd, R * 4 * Hd, B, stream);
+                   a->dcz_tot, ZC, 4 * Hd, dgates + static_cast<int64_t>(t + 1) * 4 * Hd, R * 4 * Hd, B, stream, pdl);
+      pdl = pdl_on;
+    }
     if (smooth) {
       // (0) free-running smooth mode: the gradient of logit_t also arrives through emb_{t+1}; only then
       //     is the output layer's contribution to d[z_t; c_t] known
       float* dlt = a->dl_tot + static_cast<int64_t>(t + 1) * Vq;   // rows padded to Vq floats: 8-byte aligned operand loads
       if (t + 1 < L) {
-        if (!paired_mm)
+        if (!paired_mm) {
           smallmm(static_cast<const uint32_t*>(a->weT_pk), Ep, 4 * Hd, dgates + static_cast<int64_t>(t + 1) * 4 * Hd, 0,
-                  R * 4 * Hd, B, nullptr, nullptr, 0, a->demb_buf, Ep, nullptr, 0, stream);
+                  R * 4 * Hd, B, nullptr, nullptr, 0, a->demb_buf, Ep, nullptr, 0, stream, pdl);
+          pdl = pdl_on;
+        }
         SmoothBwdParams sp = {};
         sp.drop_p = a->drop_p; sp.seed_dev = static_cast<const unsigned long long*>(a->seed_dev);
         sp.site = a->drop_site + 1; sp.R = R; sp.row = t + 1;
@@ -1579,39 +1601,47 @@ int las_dec_bwd(const las_dec_args* a, void* stream_) {
         sp.demb = a->demb_buf; sp.de_ld = Ep; sp.emb_w = a->emb_w;
         sp.dlogits = a->dlogits + static_cast<int64_t>(t + 1) * V; sp.dl_ld = R * V;
         sp.dl_tot = dlt; sp.dt_ld = R * Vq;
-        smooth_dlogit_kernel<<<B, 128, (E + V) * sizeof(float), stream>>>(sp); ++g_launches;
+        LAS_CUDA(launch_k(smooth_dlogit_kernel, dim3(B), dim3(128), (E + V) * sizeof(float), stream, pdl, sp)); ++g_launches;
+        pdl = pdl_on;
       } else {
         LAS_CUDA(cudaMemcpy2DAsync(dlt, R * Vq * sizeof(float), a->dlogits + static_cast<int64_t>(t + 1) * V,
                                    R * V * sizeof(float), V * sizeof(float), B, cudaMemcpyDeviceToDevice, stream));
+        pdl = false;          // a copy node in front of the next kernel
       }
       smallmm(static_cast<const uint32_t*>(a->outT_pk), ZC, V, dlt, 1, R * Vq, B, nullptr, nullptr, 0,
-              const_cast<float*>(a->dzc_all) + static_cast<int64_t>(t + 1) * ZC, R * ZC, nullptr, 0, stream);
+              const_cast<float*>(a->dzc_all) + static_cast<int64_t>(t + 1) * ZC, R * ZC, nullptr, 0, stream, pdl);
+      pdl = pdl_on;
     }
     // (1) d[z_t; c_t] = dzc_all (from the output layer) + Wr^T dgates_{t+1}  (row L of dgates is zero)
     if (!drop) {
       smallmm(static_cast<const uint32_t*>(a->wrT_pk), ZC, 4 * Hd, dgates + static_cast<int64_t>(t + 1) * 4 * Hd, 0, R * 4 * Hd, B,
               nullptr, a->dzc_all + static_cast<int64_t>(t + 1) * ZC, R * ZC, a->dcz_tot, ZC,
-              dcz_all + static_cast<int64_t>(t + 1) * ZC, R * ZC, stream);
+              dcz_all + static_cast<int64_t>(t + 1) * ZC, R * ZC, stream, pdl);
+      pdl = pdl_on;
     } else {
       // the path through the cell input of step t+1 carries that step's dropout mask on its c part
-      if (!paired_mm)
+      if (!paired_mm) {
         smallmm(static_cast<const uint32_t*>(a->wrT_pk), ZC, 4 * Hd, dgates + static_cast<int64_t>(t + 1) * 4 * Hd, 0, R * 4 * Hd, B,
-                nullptr, nullptr, 0, a->dcz_tot, ZC, nullptr, 0, stream);
+                nullptr, nullptr, 0, a->dcz_tot, ZC, nullptr, 0, stream, pdl);
+        pdl = pdl_on;
+      }
       DropRowParams dp = {};
       dp.B = B; dp.Hd = Hd; dp.O = O; dp.R = R; dp.row = t + 1; dp.p = a->drop_p;
       dp.seed_dev = static_cast<const unsigned long long*>(a->seed_dev); dp.site = a->drop_site;
       dp.dcz_tot = a->dcz_tot; dp.dzc_row = a->dzc_all + static_cast<int64_t>(t + 1) * ZC;
       dp.dcz_row = dcz_all + static_cast<int64_t>(t + 1) * ZC; dp.d_ld = R * ZC;
-      dec_drop_bwd_kernel<<<(B * ZC + 255) / 256, 256, 0, stream>>>(dp); ++g_launches;
+      LAS_CUDA(launch_k(dec_drop_bwd_kernel, dim3((B * ZC + 255) / 256), dim3(256), 0, stream, pdl, dp)); ++g_launches;
+      pdl = pdl_on;
     }
     // (2) dcontext = mlp_o^T dc_t
     float* dctx_t = a->dctx_all + static_cast<int64_t>(t) * a->H;
     smallmm(static_cast<const uint32_t*>(a->mlp_oT_pk), a->H, O, dcz_all + static_cast<int64_t>(t + 1) * ZC + Hd, 0, R * ZC, B,
-            nullptr, nullptr, 0, dctx_t, static_cast<int64_t>(L) * a->H, nullptr, 0, stream);
+            nullptr, nullptr, 0, dctx_t, static_cast<int64_t>(L) * a->H, nullptr, 0, stream, pdl);
+    pdl = pdl_on;
     // (3) dw_t = <dcontext, enc_h> + conv-input gradient of step t+1
     wp.dctx = dctx_t;
     wp.dattc_next = (t + 1 < L) ? a->dattc_all + static_cast<int64_t>(t + 1) * B * Te * a->C : nullptr;
-    att_dw_kernel<<<egrid, 256, dsmem, stream>>>(wp); ++g_launches;
+    LAS_CUDA(launch_k(att_dw_kernel, egrid, dim3(256), dsmem, stream, pdl, wp)); ++g_launches;
     // (4) softmax + energy backward (tanh recomputed)
     ep.dz = a->dzf + static_cast<int64_t>(t) * A;
     ep.wprev = a->ws + static_cast<int64_t>(t) * Te;
@@ -1621,17 +1651,17 @@ int las_dec_bwd(const las_dec_args* a, void* stream_) {
     if (lean) {
       lp.t = t; lp.dz = ep.dz; lp.wcur = ep.wcur; lp.ddz = ep.ddz; lp.dattc = ep.dattc;
       const int lw = A / 16 < kLeanWarps ? A / 16 : kLeanWarps;
-      att_energy_bwd_mma_kernel<<<dim3((Te + 15) / 16, B), 32 * lw, 0, stream>>>(lp);
+      LAS_CUDA(launch_k(att_energy_bwd_mma_kernel, dim3((Te + 15) / 16, B), dim3(32 * lw), 0, stream, pdl, lp));
     }
-    else if (CM == 4) att_energy_bwd_kernel<4><<<egrid, ethreads, esmem, stream>>>(ep);
-    else if (CM == 8) att_energy_bwd_kernel<8><<<egrid, ethreads, esmem, stream>>>(ep);
-    else if (CM == 12) att_energy_bwd_kernel<12><<<egrid, ethreads, esmem, stream>>>(ep);
-    else att_energy_bwd_kernel<16><<<egrid, ethreads, esmem, stream>>>(ep);
+    else if (CM == 4) LAS_CUDA(launch_k(att_energy_bwd_kernel<4>, egrid, dim3(ethreads), esmem, stream, pdl, ep));
+    else if (CM == 8) LAS_CUDA(launch_k(att_energy_bwd_kernel<8>, egrid, dim3(ethreads), esmem, stream, pdl, ep));
+    else if (CM == 12) LAS_CUDA(launch_k(att_energy_bwd_kernel<12>, egrid, dim3(ethreads), esmem, stream, pdl, ep));
+    else LAS_CUDA(launch_k(att_energy_bwd_kernel<16>, egrid, dim3(ethreads), esmem, stream, pdl, ep));
     ++g_launches;
     // (5) dz_t += mlp_dec^T ddz ; LSTMCell backward -> dgates_t
     cb.step = L - 1 - t;
     cb.v = a->ddz_all; cb.v_t_fwd = t + 1;
-    launch_cell_bwd(cb, stream);
+    launch_cell_bwd(cb, stream, pdl);
   }
   // reductions that were deferred out of the loop
   if (!lean) {

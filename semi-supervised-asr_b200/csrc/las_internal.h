@@ -1,6 +1,7 @@
 // Internal (C++) interfaces shared between the translation units of liblas_b200.so.
 // The public C-ABI is include/las_b200.h.
 #pragma once
+#include <stdlib.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -110,17 +111,33 @@ struct SmallMMParams {
   int NT, KS;
 };
 
-int launch_cell_fwd(CellFwdParams& p, cudaStream_t stream);
-int launch_cell_bwd(CellBwdParams& p, cudaStream_t stream);
+// LAS_PDL=0 switches programmatic dependent launches off (every chain kernel then launches with full stream order)
+inline bool pdl_enabled() {
+  static const bool on = getenv("LAS_PDL") == nullptr || atoi(getenv("LAS_PDL")) != 0;
+  return on;
+}
+// <<<grid, block, smem, stream>>> with, optionally, the programmatic-stream-serialization attribute (common.cuh: pdl_*)
+template <typename K, typename... Args>
+inline cudaError_t launch_k(K kern, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+int launch_cell_fwd(CellFwdParams& p, cudaStream_t stream, bool pdl = false);
+int launch_cell_bwd(CellBwdParams& p, cudaStream_t stream, bool pdl = false);
 int pack_afrag(const float* W, int64_t ld, int rows, int cols, int col_offset, int mode, int H,
                bool transposed, int tiles, int KT, uint32_t* out, cudaStream_t stream);
 // out[n, m] = sum_k A[m,k] v[n,k] (+bias[m]) (+add[n,m]); A pre-packed by pack_afrag (mode 0).
 int smallmm(const uint32_t* a_pk, int M, int K, const void* v, int v_f32, int64_t ldv, int N,
             const float* bias, const float* add, int64_t ld_add, float* out_f32, int64_t ld_out,
-            __nv_bfloat16* out_bf16, int64_t ld_outb, cudaStream_t stream);
+            __nv_bfloat16* out_bf16, int64_t ld_outb, cudaStream_t stream, bool pdl = false);
 // two products of the same bf16 operand rows in one launch: out0 = A0 v, out1 = A1 v (f32 outputs)
 int smallmm_pair(const uint32_t* a0_pk, int M0, float* out0, int64_t ld_out0, const uint32_t* a1_pk, int M1, float* out1,
-                 int64_t ld_out1, int K, const void* v, int64_t ldv, int N, cudaStream_t stream);
+                 int64_t ld_out1, int K, const void* v, int64_t ldv, int N, cudaStream_t stream, bool pdl = false);
 #endif
 
 }  // namespace las

@@ -181,6 +181,7 @@ static inline WarpShape warp_shape(int N, int KT) {
 // grid (UG, ceil(B/(8*NT)), ndir); a CTA owns the 8 hidden units of unit-group blockIdx.x (all
 // four gates -> the cell update is thread-local) for 8*NT batch rows.
 __global__ void __launch_bounds__(512) cell_fwd_kernel(CellFwdParams p) {
+  pdl_enter();
   __shared__ float red[(kMaxWarps - 1) * 32 * 8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, tig = lane & 3;
@@ -259,11 +260,11 @@ __global__ void __launch_bounds__(512) cell_fwd_kernel(CellFwdParams p) {
   }
 }
 
-int launch_cell_fwd(CellFwdParams& p, cudaStream_t stream) {
+int launch_cell_fwd(CellFwdParams& p, cudaStream_t stream, bool pdl) {
   const WarpShape w = warp_shape(p.B, p.KT1 + p.KT2);
   p.NT = w.NT; p.KS = w.KS;
   dim3 grid(p.UG, (p.B + 8 * w.NT - 1) / (8 * w.NT), p.ndir);
-  cell_fwd_kernel<<<grid, 32 * w.NT * w.KS, 0, stream>>>(p); ++g_launches;
+  LAS_CUDA(launch_k(cell_fwd_kernel, grid, dim3(32 * w.NT * w.KS), 0, stream, pdl, p)); ++g_launches;
   return 0;
 }
 
@@ -274,6 +275,7 @@ int launch_cell_fwd(CellFwdParams& p, cudaStream_t stream) {
 // A = W_hh^T (encoder/LM; v = gate gradients of the step that consumed h_t) or mlp_dec^T
 // (decoder; v = gradient of the attention's decoder-state projection).
 __global__ void __launch_bounds__(512) cell_bwd_kernel(CellBwdParams p) {
+  pdl_enter();
   __shared__ float red[(kMaxWarps - 1) * 32 * 4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, tig = lane & 3;
@@ -336,11 +338,11 @@ __global__ void __launch_bounds__(512) cell_bwd_kernel(CellBwdParams p) {
   }
 }
 
-int launch_cell_bwd(CellBwdParams& p, cudaStream_t stream) {
+int launch_cell_bwd(CellBwdParams& p, cudaStream_t stream, bool pdl) {
   const WarpShape w = warp_shape(p.B, p.v ? p.KT : 1);
   p.NT = w.NT; p.KS = w.KS;
   dim3 grid((p.H + 15) / 16, (p.B + 8 * w.NT - 1) / (8 * w.NT), p.ndir);
-  cell_bwd_kernel<<<grid, 32 * w.NT * w.KS, 0, stream>>>(p); ++g_launches;
+  LAS_CUDA(launch_k(cell_bwd_kernel, grid, dim3(32 * w.NT * w.KS), 0, stream, pdl, p)); ++g_launches;
   return 0;
 }
 
@@ -377,6 +379,7 @@ __device__ __forceinline__ void smallmm_body(const SmallMMParams& p, int mt, flo
 
 __global__ void __launch_bounds__(512) smallmm_kernel(SmallMMParams p) {
   __shared__ float red[(kMaxWarps - 1) * 32 * 4];
+  pdl_enter();
   smallmm_body(p, blockIdx.x, red);
 }
 
@@ -384,6 +387,7 @@ __global__ void __launch_bounds__(512) smallmm_kernel(SmallMMParams p) {
 // the rest the second. The per-timestep decoder backward multiplies dgates_{t+1} by two weight matrices.
 __global__ void __launch_bounds__(512) smallmm_pair_kernel(SmallMMParams p0, SmallMMParams p1) {
   __shared__ float red[(kMaxWarps - 1) * 32 * 4];
+  pdl_enter();
   if (static_cast<int>(blockIdx.x) < p0.MT) smallmm_body(p0, blockIdx.x, red);
   else smallmm_body(p1, blockIdx.x - p0.MT, red);
 }
@@ -402,22 +406,22 @@ static SmallMMParams smallmm_params(const uint32_t* a_pk, int M, int K, const vo
 
 int smallmm(const uint32_t* a_pk, int M, int K, const void* v, int v_f32, int64_t ldv, int N,
             const float* bias, const float* add, int64_t ld_add, float* out_f32, int64_t ld_out,
-            __nv_bfloat16* out_bf16, int64_t ld_outb, cudaStream_t stream) {
+            __nv_bfloat16* out_bf16, int64_t ld_outb, cudaStream_t stream, bool pdl) {
   if (M == 0 || N == 0) return 0;
   const SmallMMParams p = smallmm_params(a_pk, M, K, v, v_f32, ldv, N, bias, add, ld_add, out_f32, ld_out, out_bf16, ld_outb);
   dim3 grid(p.MT, (N + 8 * p.NT - 1) / (8 * p.NT));
-  smallmm_kernel<<<grid, 32 * p.NT * p.KS, 0, stream>>>(p); ++g_launches;
+  LAS_CUDA(launch_k(smallmm_kernel, grid, dim3(32 * p.NT * p.KS), 0, stream, pdl, p)); ++g_launches;
   return 0;
 }
 
 // out0 = A0 v, out1 = A1 v (+ nothing else): both f32, the same operand rows v [N, ldv] (bf16) and the same K
 int smallmm_pair(const uint32_t* a0_pk, int M0, float* out0, int64_t ld_out0, const uint32_t* a1_pk, int M1, float* out1,
-                 int64_t ld_out1, int K, const void* v, int64_t ldv, int N, cudaStream_t stream) {
+                 int64_t ld_out1, int K, const void* v, int64_t ldv, int N, cudaStream_t stream, bool pdl) {
   if (N == 0) return 0;
   const SmallMMParams p0 = smallmm_params(a0_pk, M0, K, v, 0, ldv, N, nullptr, nullptr, 0, out0, ld_out0, nullptr, 0);
   const SmallMMParams p1 = smallmm_params(a1_pk, M1, K, v, 0, ldv, N, nullptr, nullptr, 0, out1, ld_out1, nullptr, 0);
   dim3 grid(p0.MT + p1.MT, (N + 8 * p0.NT - 1) / (8 * p0.NT));
-  smallmm_pair_kernel<<<grid, 32 * p0.NT * p0.KS, 0, stream>>>(p0, p1); ++g_launches;
+  LAS_CUDA(launch_k(smallmm_pair_kernel, grid, dim3(32 * p0.NT * p0.KS), 0, stream, pdl, p0, p1)); ++g_launches;
   return 0;
 }
 
@@ -503,7 +507,7 @@ int las_lstm_seq_fwd(const float* xproj, const void* whh_pk, const int32_t* lens
     p.step = s;
     p.v1 = hbuf + static_cast<size_t>(s & 1) * ndir * B * Kp;
     p.hout = hbuf + static_cast<size_t>((s + 1) & 1) * ndir * B * Kp;
-    launch_cell_fwd(p, stream);
+    launch_cell_fwd(p, stream, s > 0 && pdl_enabled());     // (the first step follows a memset: full stream order)
   }
   LAS_LAUNCH_CHECK();
   return 0;
@@ -569,7 +573,7 @@ int las_lstm_seq_bwd(const float* dy, int64_t dy_ld_b, int64_t dy_ld_t, int rep_
     p.v_t_fwd = (T - 1 - s) + 1;
     p.v_t_rev = s - 1;
     p.v_ld_t = dg_ld_t;
-    launch_cell_bwd(p, stream);
+    launch_cell_bwd(p, stream, s > 0 && pdl_enabled());
   }
   LAS_LAUNCH_CHECK();
   return 0;

@@ -14,7 +14,7 @@ ncu --set full --clock-control none --profile-from-start off -k regex:"lstm_pers
     -o $out/${tag}_full python bench.py --profile-step > $out/${tag}_ncu_full.log 2>&1
 python tools/ncu_summary.py $out/${tag}_full.ncu-rep > $out/${tag}_ncu_full_summary.txt 2>&1
 python tools/ssl_one_pass.py > $out/${tag}_plain_ssl.log 2>&1 || { echo "plain ssl run failed"; exit 1; }
-ncu --set full --clock-control none --profile-from-start off -k regex:"att_energy_bwd_mma|att_energy_fwd" -c 4 \
+ncu --set full --clock-control none --profile-from-start off -k regex:"att_energy_bwd_mma" -c 2 \
     -o $out/${tag}_ebwd python tools/ssl_one_pass.py > $out/${tag}_ncu_ebwd.log 2>&1
 python tools/ncu_summary.py $out/${tag}_ebwd.ncu-rep > $out/${tag}_ncu_ebwd_summary.txt 2>&1
 tail -3 $out/${tag}_launches_summary.txt
