@@ -78,13 +78,9 @@ __device__ __forceinline__ float tanh_er(float x) {
 // kernel launched without the attribute both calls are no-ops.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_enter() {
-#ifdef LAS_PDL_TRIGGER_FIRST
-  pdl_launch_dependents(); pdl_wait();
-#else
-  pdl_wait(); pdl_launch_dependents();
-#endif
-}
+// (Triggering BEFORE the wait lets the whole chain pile up on the SMs, each grid waiting on the one in front of it:
+// measured slower, config 4 20.3 against 19.1 ms.)
+__device__ __forceinline__ void pdl_enter() { pdl_wait(); pdl_launch_dependents(); }
 
 // argmax with torch.argmax's conventions: first maximal index; NaN counts as the maximum (first NaN wins). Always
 // returns an index in [0, V): an all-NaN row (a diverged model) must not turn into an out-of-range token id.
