@@ -604,6 +604,20 @@ class SSLTrainer:
             torch.cuda.synchronize()
             print(f"[ssl] lab x {tuple(xs.shape)} ilens {list(ilens)} ylens {[len(y) for y in ys]} | unlab x {tuple(uxs.shape)} "
                   f"uilens {list(uilens)} Lu {Lu}", flush=True)
+        # the paired pass on its own stream, next to the free-running loop of the unpaired pass (see _body_dev): autograd
+        # runs its backward nodes on that stream too and joins them into the caller's stream when backward() returns
+        dev = next(m.parameters()).device
+        ps = self._pair_stream(dev) if self.overlap_passes else None
+
+        def paired():
+            _, logp, _, _ = m(xs, ilens, ys)
+            return -torch.mean(logp)                                                # solver.py:482
+
+        if ps is not None:
+            main = torch.cuda.current_stream(dev)
+            ps.wait_stream(main)
+            with torch.cuda.stream(ps):
+                sup = paired()
         _, u_logp, u_pred, _ = m(uxs, uilens, ys=None, sample=False, label_smoothing=False, max_dec_timesteps=Lu,
                                  smooth=self.smooth, scaling=self.scaling)
         dbg = os.environ.get("LAS_DEBUG_SSL")
@@ -624,8 +638,10 @@ class SSLTrainer:
             # inputs on which the two differ are those where the reference's step is NaN).
             denom = denom.clamp_min(1.0)
         unsup = -torch.sum(lm_probs * u_logp * mask) / denom
-        _, logp, _, _ = m(xs, ilens, ys)
-        sup = -torch.mean(logp)                                                     # solver.py:482
+        if ps is not None:
+            main.wait_stream(ps)
+        else:
+            sup = paired()
         return sup + self.unsup_weight * unsup, sup, unsup, (u_logp, u_pred, lm_probs)
 
     # ---- device-resident body (no host work; CUDA-graph capturable)
@@ -757,6 +773,8 @@ class SSLTrainer:
         self.opt.zero_grad()
         with Fn.deferred_wgrad():
             loss.backward()
+        if self.pair_stream is not None:
+            torch.cuda.current_stream(self.pair_stream.device).wait_stream(self.pair_stream)
         norm = _clip_and_step(self.opt, list(self.model.parameters()), self.max_grad_norm)
         return loss.detach(), sup.detach(), unsup.detach(), norm
 
