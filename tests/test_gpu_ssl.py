@@ -219,6 +219,33 @@ def test_ssl_graph_step_equals_eager():
     assert np.allclose(a, b, rtol=5e-3, atol=1e-5), (a, b)
 
 
+def test_two_stream_passes_equal_the_single_stream_step():
+    """SSLTrainer runs the paired pass on a stream of its own next to the unpaired pass (engine.SSLTrainer._body_dev /
+    losses); with `overlap_passes` off both run on one stream. Same initial weights, dropout 0: the two trajectories must
+    agree to accumulation-order noise -- in eager mode and in graph mode (a missing cross-stream dependency would show up
+    as a diverging loss or gradient norm)."""
+    G = load_golden("ssl_small")
+    g = G["raw"]
+    E, OPT = pkg("engine"), pkg("optim")
+    lab = (torch.from_numpy(g["x"]).cuda(), g["ilens"].tolist(), [torch.from_numpy(y).cuda() for y in G["ys"]])
+    unlab = (torch.from_numpy(g["ux"]).cuda(), g["uilens"].tolist())
+    for use_graph in (False, True):
+        traj = {}
+        for overlap in (False, True):
+            m = e2e_from_golden(G).train()
+            lm = lm_from_golden(G).train()
+            opt = OPT.FusedAdam(m.parameters(), lr=1e-3, weight_decay=1e-6, amsgrad=True)
+            tr = E.SSLTrainer(m, lm, opt, proportion=float(g["proportion"]), use_graph=use_graph)
+            tr.overlap_passes = overlap
+            out = []
+            for _ in range(4):
+                loss, sup, unsup, norm = tr.step(lab, unlab)
+                out.append((float(loss), float(sup), float(unsup), float(norm)))
+            traj[overlap] = np.array(out)
+            assert (tr.pair_stream is not None) == overlap
+        assert np.allclose(traj[False], traj[True], rtol=5e-3, atol=1e-5), (use_graph, traj)
+
+
 def test_judge_graph_step_equals_eager():
     """JudgeTrainer in graph mode (embedding gather, both LSTM layers, CE, backward, clip + Adam in one CUDA graph
     per (B, Lmax+5)) follows the eager trainer, and its first loss is the reference's (solver.py:288-301)."""
