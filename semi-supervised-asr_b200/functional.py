@@ -904,6 +904,8 @@ class DecoderFn(torch.autograd.Function):
             de_all = zb[7]
             a.conv_save, a.de_all = ptr(S["conv_save_steps"]), ptr(de_all)
         call("las_dec_bwd", ctypes.byref(a))
+        dq_fork = torch.cuda.Event()
+        dq_fork.record(torch.cuda.current_stream(dev))      # what the dQ chain below depends on (not the dP kernel)
         # ---- critical path: gradient w.r.t. the encoder states
         dP_bf = None
         post = pers is not None or lean           # dP / energy-MLP parameter sums are produced after the time loop
@@ -920,11 +922,29 @@ class DecoderFn(torch.autograd.Function):
             call("las_att_param_grads_part", *apg, 1 if apg_split else 3, ptr(dP), ptr(att_part), ptr(d_mlp_att),
                  ptr(d_gvec))
         if pers is not None:
-            dQ = torch.empty(B * Te, O, **f32)
-            call("las_att_dq", ptr(S["ws"]), ptr(dc_all), L, B, Te, O, ptr(dQ))
-            # c_t = w_t @ Q + b, Q = enc_h @ mlp_o.weight^T: d enc_h = dQ mlp_o.weight (+ dP mlp_enc.weight below)
-            dQ_bf = cvt_bf16(dQ)
-            gemm(dQ_bf, dQ_bf.shape[1], 0, pers["mlp_o_bf"], H, 1, B * Te, H, O, out=denc.view(B * Te, H))
+            # c_t = w_t @ Q + b, Q = enc_h @ mlp_o.weight^T: d enc_h = dQ mlp_o.weight (+ dP mlp_enc.weight below).
+            # dQ does not depend on dP: with a weight-gradient stream at hand its three kernels run there, next to the
+            # dP kernel (which leaves ~20 SMs free), and the accumulating GEMM below waits for them
+            def dq_chain():
+                dQ = torch.empty(B * Te, O, **f32)
+                call("las_att_dq", ptr(S["ws"]), ptr(dc_all), L, B, Te, O, ptr(dQ))
+                dQ_bf = cvt_bf16(dQ)
+                gemm(dQ_bf, dQ_bf.shape[1], 0, pers["mlp_o_bf"], H, 1, B * Te, H, O, out=denc.view(B * Te, H))
+                return dQ, dQ_bf
+
+            if scope.deferred and os.environ.get("LAS_DQ_OVERLAP", "1") == "1":
+                main = torch.cuda.current_stream(dev)
+                side = warm_deferred(dev)
+                side.wait_event(dq_fork)
+                _DEFER["used"] = True
+                with torch.cuda.stream(side):
+                    dQ, dQ_bf = dq_chain()
+                    dq_done = torch.cuda.Event()
+                    dq_done.record(side)
+                _DEFER["keep"].append((dQ, dQ_bf, denc, dc_all))
+                main.wait_event(dq_done)
+            else:
+                dQ, dQ_bf = dq_chain()
         dP_bf = cvt_bf16(dP)
         Ap8 = dP_bf.shape[1]
         gemm(dP_bf, Ap8, 0, S["mlp_enc_bf"], H, 1, B * Te, H, A, out=denc.view(B * Te, H), accumulate=True)
